@@ -1,0 +1,170 @@
+"""ctypes binding of the restated C oracle (oracle/ma_oracle.c) -- TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import
+this; the product (core_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "libma_oracle.so")
+IDENTITY, ISO, ANISO, LOGM = range(4)
+
+# ma flag bits, ma/maAdapt.h:17-37
+SPLIT, DONT_SPLIT, COLLAPSE, DONT_COLLAPSE, CHECKED, BAD_QUALITY, OK_QUALITY = (1 << i for i in range(7))
+DONT_SWAP, LAYER = 1 << 9, 1 << 10
+NEED_NOT_SPLIT, NEED_NOT_COLLAPSE = 1 << 17, 1 << 18
+
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        L = C.CDLL(LIB_PATH)
+        vp, i64, i32, f64 = C.c_void_p, C.c_int64, C.c_int32, C.c_double
+        L.mao_det3.restype = f64
+        L.mao_det3.argtypes = [vp]
+        L.mao_eigen_qr.argtypes = [vp, vp, vp, vp]
+        L.mao_eigen.argtypes = [vp, vp, vp]
+        L.mao_transform_aniso.argtypes = [vp, vp, vp]
+        L.mao_transform_logm.argtypes = [vp, vp]
+        L.mao_logm_from_frame.argtypes = [C.c_int, vp, vp, vp]
+        L.mao_edge_lengths.argtypes = [C.c_int, vp, vp, vp, i64, vp, vp]
+        L.mao_tet_qualities.argtypes = [C.c_int, vp, vp, vp, i64, vp, C.c_int, vp]
+        L.mao_vertex_transforms.argtypes = [C.c_int, vp, vp, i64, vp]
+        L.mao_prism_ok.argtypes = [vp, vp, vp]
+        L.mao_pyramid_ok.argtypes = [vp, vp, vp]
+        L.mao_mark_entities.restype = i64
+        L.mao_mark_entities.argtypes = [i64, vp, C.c_int, f64, vp, vp, i32, i32, i32]
+        L.mao_min_quality.restype = f64
+        L.mao_min_quality.argtypes = [i64, vp]
+        L.mao_max_length.restype = f64
+        L.mao_max_length.argtypes = [i64, vp, vp]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+def det3(A):
+    A = _f64(A)
+    return lib().mao_det3(_p(A))
+
+
+def eigen(A):
+    """apf::eigen restated: returns (vals[3], vecs[3][3] eigenvector j in row j, rc)."""
+    A = _f64(A)
+    vecs = np.zeros((3, 3))
+    vals = np.zeros(3)
+    rc = lib().mao_eigen(_p(A), _p(vecs), _p(vals))
+    return vals, vecs, rc
+
+
+def logm_from_frames(h, R, variant=0):
+    """Per-vertex logM.  variant 0: LogAnisoSizeField::init (fields); 1: LogMEval (user function)."""
+    h = _f64(h).reshape(-1, 3)
+    R = _f64(R).reshape(-1, 9)
+    out = np.zeros_like(R)
+    L = lib()
+    for i in range(len(h)):
+        L.mao_logm_from_frame(variant, _p(h[i]), _p(R[i]), _p(out[i]))
+    return out
+
+
+def edge_lengths(kind, xyz, ma, mb, edge_v):
+    xyz, ma, mb, edge_v = _f64(xyz), _f64(ma), _f64(mb), _i32(edge_v)
+    ne = edge_v.size // 2
+    out = np.zeros(ne)
+    rc = lib().mao_edge_lengths(kind, _p(xyz), _p(ma), _p(mb), ne, _p(edge_v), _p(out))
+    assert rc == 1, "eigenQR did not converge / assert in reference"
+    return out
+
+
+def tet_qualities(kind, xyz, ma, mb, tet_v, use_max=True):
+    xyz, ma, mb, tet_v = _f64(xyz), _f64(ma), _f64(mb), _i32(tet_v)
+    nt = tet_v.size // 4
+    out = np.zeros(nt)
+    rc = lib().mao_tet_qualities(kind, _p(xyz), _p(ma), _p(mb), nt, _p(tet_v), int(use_max), _p(out))
+    assert rc == 1
+    return out
+
+
+def vertex_transforms(kind, ma, mb, nv):
+    ma, mb = _f64(ma), _f64(mb)
+    out = np.zeros((nv, 9))
+    lib().mao_vertex_transforms(kind, _p(ma), _p(mb), nv, _p(out))
+    return out
+
+
+def prism_ok(xyz, prism_v):
+    xyz, prism_v = _f64(xyz), _i32(prism_v).reshape(-1, 6)
+    ok = np.zeros(len(prism_v), dtype=np.int32)
+    codes = np.zeros(len(prism_v), dtype=np.int32)
+    c = C.c_int(0)
+    for i in range(len(prism_v)):
+        ok[i] = lib().mao_prism_ok(_p(xyz), _p(prism_v[i]), C.addressof(c))
+        codes[i] = c.value
+    return ok, codes
+
+
+def pyramid_ok(xyz, pyr_v):
+    xyz, pyr_v = _f64(xyz), _i32(pyr_v).reshape(-1, 5)
+    ok = np.zeros(len(pyr_v), dtype=np.int32)
+    codes = np.zeros(len(pyr_v), dtype=np.int32)
+    c = C.c_int(0)
+    for i in range(len(pyr_v)):
+        ok[i] = lib().mao_pyramid_ok(_p(xyz), _p(pyr_v[i]), C.addressof(c))
+        codes[i] = c.value
+    return ok, codes
+
+
+def mark_entities(value, cmp, thr, flags, owned, true_flag, set_false_flag, all_false_flags=0):
+    """ma::markEntities restated; flags (int32) updated in place; returns owned-true count."""
+    value = _f64(value)
+    assert flags.dtype == np.int32 and flags.flags.c_contiguous
+    ow = None if owned is None else np.ascontiguousarray(owned, dtype=np.uint8)
+    return lib().mao_mark_entities(value.size, _p(value), cmp, thr, _p(flags), _p(ow),
+                                   true_flag, set_false_flag, all_false_flags)
+
+
+def mark_edges_to_split(lengths, flags, owned=None):      # maRefine.cc:395-400
+    return mark_entities(lengths, 0, 1.5, flags, owned, SPLIT, NEED_NOT_SPLIT, DONT_SPLIT | NEED_NOT_SPLIT)
+
+
+def mark_edges_to_collapse(lengths, flags, owned=None):   # maCoarsen.cc:287-292
+    return mark_entities(lengths, 1, 0.5, flags, owned, COLLAPSE, NEED_NOT_COLLAPSE,
+                         DONT_COLLAPSE | NEED_NOT_COLLAPSE)
+
+
+def mark_bad_quality(q, flags, good_quality, owned=None):  # maShape.cc:132-136
+    return mark_entities(q, 1, good_quality, flags, owned, BAD_QUALITY, OK_QUALITY, 0)
+
+
+def min_quality(q):
+    q = _f64(q)
+    return lib().mao_min_quality(q.size, _p(q))
+
+
+def max_length(lengths, owned=None):
+    lengths = _f64(lengths)
+    ow = None if owned is None else np.ascontiguousarray(owned, dtype=np.uint8)
+    return lib().mao_max_length(lengths.size, _p(lengths), _p(ow))
