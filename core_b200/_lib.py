@@ -1,0 +1,80 @@
+"""ctypes loader of the in-tree C-ABI library core_b200/lib/libmag.so (include/mag.h).
+
+The product has no CPU fallback: if the library is missing or no CUDA device is present,
+loading / mag_create fails loudly.  Nothing under oracle/ is ever imported from here.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmag.so")
+
+# every symbol include/mag.h declares (tests/test_abi.py checks the header against this list)
+SYMBOLS = [
+    "mag_create", "mag_destroy", "mag_last_error", "mag_set_stream", "mag_synchronize",
+    "mag_set_mesh", "mag_set_coords",
+    "mag_set_metric_identity", "mag_set_metric_iso", "mag_set_metric_aniso", "mag_set_metric_logm",
+    "mag_set_flags", "mag_sweep",
+    "mag_get_edge_lengths", "mag_get_qualities", "mag_get_flags", "mag_get_layer_ok", "mag_get_stats",
+    "mag_get_near_threshold",
+    "mag_comm_unique_id", "mag_comm_init", "mag_set_edge_links", "mag_reconcile_edge_flags",
+    "mag_sync_edge_flags", "mag_allreduce_stats",
+]
+
+
+class MagStats(C.Structure):
+    _fields_ = [("n_split", C.c_int64), ("n_collapse", C.c_int64), ("n_bad", C.c_int64),
+                ("n_edges_evaluated", C.c_int64), ("n_elems_evaluated", C.c_int64),
+                ("n_near_threshold", C.c_int64), ("n_layer_unsafe", C.c_int64),
+                ("n_flag_mismatch", C.c_int64),
+                ("min_quality", C.c_double), ("max_length", C.c_double), ("sum_length", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "core_b200: %s is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32, u32, f64 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_double
+    L.mag_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.mag_destroy.argtypes = [vp]
+    L.mag_destroy.restype = None
+    L.mag_last_error.argtypes = [vp]
+    L.mag_last_error.restype = C.c_char_p
+    L.mag_set_stream.argtypes = [vp, vp]
+    L.mag_synchronize.argtypes = [vp]
+    L.mag_set_mesh.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp]
+    L.mag_set_coords.argtypes = [vp, vp]
+    L.mag_set_metric_identity.argtypes = [vp]
+    L.mag_set_metric_iso.argtypes = [vp, vp]
+    L.mag_set_metric_aniso.argtypes = [vp, vp, vp]
+    L.mag_set_metric_logm.argtypes = [vp, vp]
+    L.mag_set_flags.argtypes = [vp, vp, vp]
+    L.mag_sweep.argtypes = [vp, u32, f64, f64, f64, C.c_int, C.c_int]
+    L.mag_get_edge_lengths.argtypes = [vp, vp]
+    L.mag_get_qualities.argtypes = [vp, vp]
+    L.mag_get_flags.argtypes = [vp, vp, vp]
+    L.mag_get_layer_ok.argtypes = [vp, vp, vp]
+    L.mag_get_stats.argtypes = [vp, C.POINTER(MagStats)]
+    L.mag_get_near_threshold.argtypes = [vp, C.c_int, vp, i64, C.POINTER(i64)]
+    L.mag_comm_unique_id.argtypes = [vp]
+    L.mag_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.mag_set_edge_links.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+    L.mag_reconcile_edge_flags.argtypes = [vp, i32]
+    L.mag_sync_edge_flags.argtypes = [vp, i32]
+    L.mag_allreduce_stats.argtypes = [vp, C.POINTER(MagStats)]
+    for s in SYMBOLS:
+        if getattr(L, s).restype is C.c_int:
+            pass
+    _lib = L
+    return L

@@ -1,0 +1,147 @@
+"""Closed-form Kuhn box meshes in the entity order of apf::makeMdsBox.
+
+`kuhn_box(nx, ny, nz, ...)` produces, directly as flat arrays, the same vertices, edges
+and tets -- in the same order and with the same per-entity vertex order -- that
+`apf::makeMdsBox(nx, ny, nz, wx, wy, wz, true)` followed by iteration over
+`m->begin(d)` / `getDownward(e, 0, ..)` would export (reference: mds/apfBox.cc:179-263;
+edge orientation of the diagonals follows apf::buildElement's tri_edge_verts /
+tet_tri_verts walk, apf/apfMesh.cc:28-33,80-91).  tests/test_boxmesh.py checks the
+equivalence against the compiled reference.  It exists because MDS itself cannot hold the
+50 M-tet benchmark part in reasonable time/memory (hard part 4).
+
+`slab_part(...)` cuts a global box into x-slabs, one PUMI-style part per GPU: every part
+keeps full copies of its boundary entities, and the per-peer shared-edge lists are ordered
+identically on both sides (the contract of struct mds_links, mds/mds_net.h:33-38).
+"""
+import numpy as np
+
+# tets of one cell, vertices numbered as in BoxBuilder::buildCellRegion (apfBox.cc:250-256)
+_TET_VERTS = np.array([[0, 1, 2, 6], [0, 2, 3, 6], [0, 3, 7, 6],
+                       [0, 7, 4, 6], [0, 4, 5, 6], [0, 5, 1, 6]], dtype=np.int64)
+# cell-corner offsets (dx, dy, dz) of rv[0..7]
+_CORNER = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0],
+                    [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], dtype=np.int64)
+
+
+def box_counts(nx, ny, nz):
+    nv = (nx + 1) * (ny + 1) * (nz + 1)
+    ne = (nx * (ny + 1) * (nz + 1) + (nx + 1) * ny * (nz + 1) + (nx + 1) * (ny + 1) * nz
+          + nx * ny * (nz + 1) + (nx + 1) * ny * nz + nx * (ny + 1) * nz + nx * ny * nz)
+    nt = 6 * nx * ny * nz
+    return nv, ne, nt
+
+
+def kuhn_box(nx, ny, nz, wx=1.0, wy=1.0, wz=1.0, x0=0, gnx=None, index_dtype=np.int32):
+    """Returns (xyz [nv,3] f64, edge_v [ne,2], tet_v [nt,4]).
+
+    x0 / gnx: this box is the x-slab [x0, x0+nx] of a global box with gnx cells along x and
+    total width wx, so that shared vertices of neighbouring slabs get bit-identical
+    coordinates (w * global_index, exactly as apfBox.cc:181-184 computes them)."""
+    if gnx is None:
+        gnx = nx
+    sx, sy, sz = nx + 1, ny + 1, nz + 1
+    nv = sx * sy * sz
+    hx, hy, hz = wx / gnx, wy / ny, wz / nz
+    ix = np.arange(sx, dtype=np.int64)
+    iy = np.arange(sy, dtype=np.int64)
+    iz = np.arange(sz, dtype=np.int64)
+    xyz = np.empty((sz, sy, sx, 3), dtype=np.float64)
+    xyz[..., 0] = (hx * (ix + x0))[None, None, :]
+    xyz[..., 1] = (hy * iy)[None, :, None]
+    xyz[..., 2] = (hz * iz)[:, None, None]
+    xyz = xyz.reshape(nv, 3)
+
+    # vertex grid index and coordinates, grid order (x fastest)
+    vid = np.arange(nv, dtype=np.int64)
+    vx = vid % sx
+    vy = (vid // sx) % sy
+    vz = vid // (sx * sy)
+    stride = np.array([1, sx, sx * sy], dtype=np.int64)
+    notmax = [vx < nx, vy < ny, vz < nz]
+
+    # --- dimension-1 pass: per vertex, edges to +x, +y, +z that exist (apfBox.cc:192-207)
+    cand = np.stack([vid, vid, vid], axis=1)                       # [nv,3] first vertex
+    other = cand + stride[None, :]
+    mask = np.stack(notmax, axis=1)
+    axis_edges = np.stack([cand[mask], other[mask]], axis=1)       # row-major flatten keeps (vertex, j) order
+
+    # --- dimension-2 pass: per vertex, faces (jx, jy=(jx+1)%3); the new edge is the diagonal
+    # (fv2, fv0) = (v + e_jx + e_jy, v) created by triangle (fv0, fv1, fv2) (apfBox.cc:209-246)
+    diag_other = np.stack([vid + stride[j] + stride[(j + 1) % 3] for j in range(3)], axis=1)
+    fmask = np.stack([notmax[j] & notmax[(j + 1) % 3] for j in range(3)], axis=1)
+    face_edges = np.stack([diag_other[fmask], cand[fmask]], axis=1)
+
+    # --- dimension-3 pass: per cell the body diagonal (rv6, rv0) from tet (0,1,2,6), then 6 tets
+    cmask = notmax[0] & notmax[1] & notmax[2]
+    c0 = vid[cmask]
+    corner = c0[:, None] + (_CORNER @ stride)[None, :]              # [ncell, 8]
+    body_edges = np.stack([corner[:, 6], corner[:, 0]], axis=1)
+    tet_v = corner[:, _TET_VERTS.reshape(-1)].reshape(-1, 4)
+
+    edge_v = np.concatenate([axis_edges, face_edges, body_edges], axis=0)
+    return xyz, np.ascontiguousarray(edge_v.astype(index_dtype)), np.ascontiguousarray(tet_v.astype(index_dtype))
+
+
+def slab_bounds(gnx, nparts):
+    """x-cell ranges [lo, hi) of each slab; remainders go to the first parts."""
+    base, rem = divmod(gnx, nparts)
+    lo, out = 0, []
+    for p in range(nparts):
+        n = base + (1 if p < rem else 0)
+        out.append((lo, lo + n))
+        lo += n
+    return out
+
+
+def slab_part(gnx, ny, nz, nparts, part, wx=1.0, wy=1.0, wz=1.0):
+    """One x-slab part of the global gnx x ny x nz Kuhn box.
+
+    Returns dict(xyz, edge_v, tet_v, edge_owned [ne] u8, elem_owned [nt] u8,
+                 links = [(peer, idx int32[], peer_owns u8[])...], x0, nx).
+    Shared entities are the vertices/edges lying in the cut planes x = lo and x = hi.  Owner
+    rule (apfPM.cc:109-126): the resident part with the fewest elements, ties -> lowest part
+    id.  Shared-edge lists are sorted by the LOWER part's local edge index on both sides."""
+    bounds = slab_bounds(gnx, nparts)
+    lo, hi = bounds[part]
+    nx = hi - lo
+    xyz, edge_v, tet_v = kuhn_box(nx, ny, nz, wx, wy, wz, x0=lo, gnx=gnx)
+    sx = nx + 1
+    ne, nt = len(edge_v), len(tet_v)
+    nelem = [6 * (b[1] - b[0]) * ny * nz for b in bounds]
+
+    def plane_edges(nx_local, plane_ix):
+        """local indices (box order) of edges with both ends in the plane x = plane_ix, plus a
+        part-independent key (the (y,z) ids of both end vertices)."""
+        _, ev, _ = kuhn_box(nx_local, ny, nz) if nx_local != nx else (None, edge_v, None)
+        s = nx_local + 1
+        a, b = ev[:, 0].astype(np.int64), ev[:, 1].astype(np.int64)
+        inplane = ((a % s) == plane_ix) & ((b % s) == plane_ix)
+        idx = np.nonzero(inplane)[0]
+        key = np.stack([a[idx] // s, b[idx] // s], axis=1)         # (y + sy*z) of each end
+        return idx, key
+
+    edge_owned = np.ones(ne, dtype=np.uint8)
+    links = []
+    for peer, my_plane in ((part - 1, 0), (part + 1, nx)):
+        if peer < 0 or peer >= nparts:
+            continue
+        my_idx, my_key = plane_edges(nx, my_plane)
+        pnx = bounds[peer][1] - bounds[peer][0]
+        peer_plane = pnx if peer < part else 0
+        p_idx, p_key = plane_edges(pnx, peer_plane)
+        # match by key; order by the lower part's local index
+        def order(k):
+            return np.lexsort((k[:, 1], k[:, 0]))
+        mo, po = order(my_key), order(p_key)
+        assert np.array_equal(my_key[mo], p_key[po])
+        mine, theirs = my_idx[mo], p_idx[po]
+        lower_local = mine if part < peer else theirs
+        perm = np.argsort(lower_local, kind="stable")
+        mine = mine[perm]
+        owner = part if (nelem[part], part) < (nelem[peer], peer) else peer
+        peer_owns = np.full(len(mine), 1 if owner == peer else 0, dtype=np.uint8)
+        if owner == peer:
+            edge_owned[mine] = 0
+        links.append((peer, np.ascontiguousarray(mine.astype(np.int32)), peer_owns))
+    return dict(xyz=xyz, edge_v=edge_v, tet_v=tet_v, edge_owned=edge_owned,
+                elem_owned=np.ones(nt, dtype=np.uint8), links=links, x0=lo, nx=nx, sx=sx)

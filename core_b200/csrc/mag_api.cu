@@ -1,0 +1,356 @@
+// mag_api.cu -- the C ABI declared in include/mag.h: context, device memory, uploads, getters.
+// No CPU fallback anywhere: every entry point needs a live CUDA device.
+#include "mag_internal.h"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+int magk_pack(mag_ctx* c);
+int magk_init_stats(mag_ctx* c);
+int magk_vertex_pass(mag_ctx* c);
+int magk_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double good_q, int use_max, int fp_mode);
+double magk_key_to_double(unsigned long long k);
+void magc_destroy(mag_ctx* c);
+
+static thread_local std::string g_create_err;
+
+int mag_fail(mag_ctx* c, int code, const char* fmt, ...)
+{
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf; else g_create_err = buf;
+  return code;
+}
+
+namespace {
+
+template <class T>
+int dev_free(mag_ctx* c, T*& p)
+{
+  if (p) { MAG_CUDA(c, cudaFree(p)); p = nullptr; }
+  return MAG_OK;
+}
+template <class T>
+int dev_alloc(mag_ctx* c, T*& p, size_t count)
+{
+  int rc = dev_free(c, p);
+  if (rc) return rc;
+  if (count) MAG_CUDA(c, cudaMalloc((void**)&p, count * sizeof(T)));
+  return MAG_OK;
+}
+// grow-only buffer
+template <class T>
+int dev_reserve(mag_ctx* c, T*& p, size_t& cap, size_t count)
+{
+  if (count <= cap && p) return MAG_OK;
+  int rc = dev_alloc(c, p, count);
+  if (rc) return rc;
+  cap = count;
+  return MAG_OK;
+}
+template <class T>
+int upload(mag_ctx* c, T* dst, const T* src, size_t count)
+{
+  if (count) MAG_CUDA(c, cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  return MAG_OK;
+}
+template <class T>
+int download(mag_ctx* c, T* dst, const T* src, size_t count)
+{
+  if (count) MAG_CUDA(c, cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+  return MAG_OK;
+}
+
+int use_device(mag_ctx* c)
+{
+  MAG_CUDA(c, cudaSetDevice(c->device));
+  return MAG_OK;
+}
+
+size_t rec_doubles(int kind) { return (kind == MAG_KIND_ANISO || kind == MAG_KIND_LOGM) ? 12 : 4; }
+
+// (re)build the gather records after coordinates or the size field changed
+int repack(mag_ctx* c)
+{
+  if (c->kind == MAG_KIND_NONE || c->nv == 0 || !c->d_xyz) return MAG_OK;
+  int rc = dev_reserve(c, c->d_vedge, c->cap_vedge, (size_t)c->nv * rec_doubles(c->kind));
+  if (rc) return rc;
+  c->vertex_pass_valid = false;
+  return magk_pack(c);
+}
+
+#define CHECK_CTX(c) do { if (!(c)) return MAG_ERR_ARG; int rc_ = use_device(c); if (rc_) return rc_; } while (0)
+
+} // namespace
+
+extern "C" {
+
+const char* mag_last_error(const mag_ctx* c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+int mag_create(mag_ctx** out, int device)
+{
+  if (!out) return mag_fail(nullptr, MAG_ERR_ARG, "mag_create: null out pointer");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return mag_fail(nullptr, MAG_ERR_CUDA, "mag_create: no CUDA device (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  if (device < 0 || device >= ndev) return mag_fail(nullptr, MAG_ERR_ARG, "mag_create: device %d out of range [0,%d)", device, ndev);
+  mag_ctx* c = new mag_ctx();
+  c->device = device;
+  c->own_stream = c->stream = nullptr;
+  c->nv = c->ne = c->nt = c->np = c->npy = 0;
+  c->kind = MAG_KIND_NONE;
+  c->vertex_pass_valid = false;
+  c->d_xyz = c->d_ma = c->d_mb = c->d_vedge = c->d_vpos = c->d_vq = nullptr;
+  c->d_edge_v = c->d_tet_v = c->d_prism_v = c->d_pyr_v = nullptr;
+  c->d_edge_owned = c->d_elem_owned = nullptr;
+  c->d_edge_flags = c->d_elem_flags = nullptr;
+  c->d_len = c->d_qual = nullptr;
+  c->d_layer_ok = c->d_layer_codes = nullptr;
+  c->d_stats = nullptr; c->h_stats = nullptr;
+  c->d_block_sums = nullptr; c->n_block_sums = 0;
+  c->d_near_edge = c->d_near_elem = nullptr;
+  c->cap_vedge = c->cap_ma = c->cap_mb = 0;
+  c->last_ops = 0; c->last_fp_mode = 0;
+  c->nccl_comm = nullptr; c->nranks = 1; c->rank = 0;
+  auto fail = [&](cudaError_t err, const char* what) {
+    int rc = mag_fail(nullptr, MAG_ERR_CUDA, "mag_create: %s: %s", what, cudaGetErrorString(err));
+    delete c;
+    return rc;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e, "cudaSetDevice");
+  if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+  c->stream = c->own_stream;
+  if ((e = cudaMalloc((void**)&c->d_stats, sizeof(MagDevStats))) != cudaSuccess) return fail(e, "cudaMalloc stats");
+  if ((e = cudaMallocHost((void**)&c->h_stats, sizeof(MagDevStats))) != cudaSuccess) return fail(e, "cudaMallocHost stats");
+  if ((e = cudaMalloc((void**)&c->d_near_edge, sizeof(int64_t) * MAG_NEAR_CAP)) != cudaSuccess) return fail(e, "cudaMalloc near list");
+  if ((e = cudaMalloc((void**)&c->d_near_elem, sizeof(int64_t) * MAG_NEAR_CAP)) != cudaSuccess) return fail(e, "cudaMalloc near list");
+  int rc = magk_init_stats(c);
+  if (rc) { g_create_err = c->err; delete c; return rc; }
+  *out = c;
+  return MAG_OK;
+}
+
+void mag_destroy(mag_ctx* c)
+{
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  magc_destroy(c);
+  cudaFree(c->d_xyz); cudaFree(c->d_ma); cudaFree(c->d_mb); cudaFree(c->d_vedge); cudaFree(c->d_vpos); cudaFree(c->d_vq);
+  cudaFree(c->d_edge_v); cudaFree(c->d_tet_v); cudaFree(c->d_prism_v); cudaFree(c->d_pyr_v);
+  cudaFree(c->d_edge_owned); cudaFree(c->d_elem_owned); cudaFree(c->d_edge_flags); cudaFree(c->d_elem_flags);
+  cudaFree(c->d_len); cudaFree(c->d_qual); cudaFree(c->d_layer_ok); cudaFree(c->d_layer_codes);
+  cudaFree(c->d_stats); cudaFreeHost(c->h_stats); cudaFree(c->d_block_sums);
+  cudaFree(c->d_near_edge); cudaFree(c->d_near_elem);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+int mag_set_stream(mag_ctx* c, void* cuda_stream)
+{
+  CHECK_CTX(c);
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+  return MAG_OK;
+}
+
+int mag_synchronize(mag_ctx* c)
+{
+  CHECK_CTX(c);
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return MAG_OK;
+}
+
+int mag_set_mesh(mag_ctx* c, int64_t nv, const double* xyz, int64_t ne, const int32_t* edge_v,
+                 int64_t nt, const int32_t* tet_v, int64_t np, const int32_t* prism_v,
+                 int64_t npy, const int32_t* pyr_v, const uint8_t* edge_owned, const uint8_t* elem_owned)
+{
+  CHECK_CTX(c);
+  if (nv < 0 || ne < 0 || nt < 0 || np < 0 || npy < 0) return mag_fail(c, MAG_ERR_ARG, "mag_set_mesh: negative count");
+  if (nv > 0x7fffffffLL) return mag_fail(c, MAG_ERR_ARG, "mag_set_mesh: vertex ids are int32 (MDS_ID_TYPE=int)");
+  if ((nv && !xyz) || (ne && !edge_v) || (nt && !tet_v) || (np && !prism_v) || (npy && !pyr_v))
+    return mag_fail(c, MAG_ERR_ARG, "mag_set_mesh: null array with non-zero count");
+  int rc;
+  const int64_t nel = np + npy + nt;
+  const bool same_shape = nv == c->nv && ne == c->ne && nt == c->nt && np == c->np && npy == c->npy &&
+                          (edge_owned != nullptr) == (c->d_edge_owned != nullptr) &&
+                          (elem_owned != nullptr) == (c->d_elem_owned != nullptr);
+  if (!same_shape) {
+    if (nv != c->nv) { // size field arrays are per vertex: drop them
+      c->kind = MAG_KIND_NONE;
+      if ((rc = dev_free(c, c->d_ma)) || (rc = dev_free(c, c->d_mb)) || (rc = dev_free(c, c->d_vedge))) return rc;
+      c->cap_ma = c->cap_mb = c->cap_vedge = 0;
+    }
+    if ((rc = dev_alloc(c, c->d_xyz, (size_t)nv * 3)) || (rc = dev_alloc(c, c->d_vpos, (size_t)nv * 4)) ||
+        (rc = dev_alloc(c, c->d_vq, (size_t)nv * 10)) || (rc = dev_alloc(c, c->d_edge_v, (size_t)ne * 2)) ||
+        (rc = dev_alloc(c, c->d_tet_v, (size_t)nt * 4)) || (rc = dev_alloc(c, c->d_prism_v, (size_t)np * 6)) ||
+        (rc = dev_alloc(c, c->d_pyr_v, (size_t)npy * 5)) ||
+        (rc = dev_alloc(c, c->d_edge_owned, edge_owned ? (size_t)ne : 0)) ||
+        (rc = dev_alloc(c, c->d_elem_owned, elem_owned ? (size_t)nel : 0)) ||
+        (rc = dev_alloc(c, c->d_edge_flags, (size_t)ne)) || (rc = dev_alloc(c, c->d_elem_flags, (size_t)nel)) ||
+        (rc = dev_alloc(c, c->d_len, (size_t)ne)) || (rc = dev_alloc(c, c->d_qual, (size_t)nel)) ||
+        (rc = dev_alloc(c, c->d_layer_ok, (size_t)(np + npy))) || (rc = dev_alloc(c, c->d_layer_codes, (size_t)(np + npy))))
+      return rc;
+    c->n_block_sums = (ne + 255) / 256;
+    if ((rc = dev_alloc(c, c->d_block_sums, (size_t)c->n_block_sums))) return rc;
+    c->nv = nv; c->ne = ne; c->nt = nt; c->np = np; c->npy = npy;
+    if (ne) MAG_CUDA(c, cudaMemsetAsync(c->d_edge_flags, 0, (size_t)ne * 4, c->stream));
+    if (nel) MAG_CUDA(c, cudaMemsetAsync(c->d_elem_flags, 0, (size_t)nel * 4, c->stream));
+    if (nel) MAG_CUDA(c, cudaMemsetAsync(c->d_qual, 0, (size_t)nel * 8, c->stream));
+  }
+  if ((rc = upload(c, c->d_xyz, xyz, (size_t)nv * 3)) || (rc = upload(c, c->d_edge_v, edge_v, (size_t)ne * 2)) ||
+      (rc = upload(c, c->d_tet_v, tet_v, (size_t)nt * 4)) || (rc = upload(c, c->d_prism_v, prism_v, (size_t)np * 6)) ||
+      (rc = upload(c, c->d_pyr_v, pyr_v, (size_t)npy * 5)))
+    return rc;
+  if (edge_owned && (rc = upload(c, c->d_edge_owned, edge_owned, (size_t)ne))) return rc;
+  if (elem_owned && (rc = upload(c, c->d_elem_owned, elem_owned, (size_t)nel))) return rc;
+  return repack(c);
+}
+
+int mag_set_coords(mag_ctx* c, const double* xyz)
+{
+  CHECK_CTX(c);
+  if (!c->d_xyz || !xyz) return mag_fail(c, MAG_ERR_ARG, "mag_set_coords: no mesh set / null xyz");
+  int rc = upload(c, c->d_xyz, xyz, (size_t)c->nv * 3);
+  if (rc) return rc;
+  return repack(c);
+}
+
+static int set_metric(mag_ctx* c, int kind, const double* a, size_t na, const double* b, size_t nb)
+{
+  CHECK_CTX(c);
+  if (!c->d_xyz && c->nv) return mag_fail(c, MAG_ERR_ARG, "set metric: call mag_set_mesh first");
+  if ((na && !a) || (nb && !b)) return mag_fail(c, MAG_ERR_ARG, "set metric: null array");
+  int rc;
+  if ((rc = dev_reserve(c, c->d_ma, c->cap_ma, na)) || (rc = dev_reserve(c, c->d_mb, c->cap_mb, nb))) return rc;
+  if ((rc = upload(c, c->d_ma, a, na)) || (rc = upload(c, c->d_mb, b, nb))) return rc;
+  c->kind = kind;
+  return repack(c);
+}
+int mag_set_metric_identity(mag_ctx* c) { return set_metric(c, MAG_KIND_IDENTITY, nullptr, 0, nullptr, 0); }
+int mag_set_metric_iso(mag_ctx* c, const double* size) { return c ? set_metric(c, MAG_KIND_ISO, size, (size_t)c->nv, nullptr, 0) : MAG_ERR_ARG; }
+int mag_set_metric_aniso(mag_ctx* c, const double* h, const double* R)
+{
+  return c ? set_metric(c, MAG_KIND_ANISO, h, (size_t)c->nv * 3, R, (size_t)c->nv * 9) : MAG_ERR_ARG;
+}
+int mag_set_metric_logm(mag_ctx* c, const double* logM) { return c ? set_metric(c, MAG_KIND_LOGM, nullptr, 0, logM, (size_t)c->nv * 9) : MAG_ERR_ARG; }
+
+int mag_set_flags(mag_ctx* c, const int32_t* edge_flags, const int32_t* elem_flags)
+{
+  CHECK_CTX(c);
+  const int64_t nel = c->np + c->npy + c->nt;
+  if (c->ne) {
+    if (edge_flags) { int rc = upload(c, c->d_edge_flags, edge_flags, (size_t)c->ne); if (rc) return rc; }
+    else MAG_CUDA(c, cudaMemsetAsync(c->d_edge_flags, 0, (size_t)c->ne * 4, c->stream));
+  }
+  if (nel) {
+    if (elem_flags) { int rc = upload(c, c->d_elem_flags, elem_flags, (size_t)nel); if (rc) return rc; }
+    else MAG_CUDA(c, cudaMemsetAsync(c->d_elem_flags, 0, (size_t)nel * 4, c->stream));
+  }
+  return MAG_OK;
+}
+
+int mag_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double good_quality, int use_max_metric, int fp_mode)
+{
+  CHECK_CTX(c);
+  if (c->kind == MAG_KIND_NONE) return mag_fail(c, MAG_ERR_ARG, "mag_sweep: no size field set");
+  if (fp_mode != MAG_FP_STRICT && fp_mode != MAG_FP_FAST) return mag_fail(c, MAG_ERR_ARG, "mag_sweep: bad fp_mode %d", fp_mode);
+  if (ops & ~(uint32_t)MAG_OP_ALL) return mag_fail(c, MAG_ERR_ARG, "mag_sweep: unknown op bits 0x%x", ops);
+  int rc;
+  if ((rc = magk_init_stats(c))) return rc;
+  const bool need_vertex = (ops & (MAG_OP_QUALITIES | MAG_OP_MARK_BAD | MAG_OP_LAYER_CHECK)) != 0;
+  if (need_vertex && !c->vertex_pass_valid) {
+    if ((rc = magk_vertex_pass(c))) return rc;
+    c->vertex_pass_valid = true;
+  }
+  c->last_ops = ops;
+  c->last_fp_mode = fp_mode;
+  return magk_sweep(c, ops, max_len, min_len, good_quality, use_max_metric, fp_mode);
+}
+
+int mag_get_edge_lengths(mag_ctx* c, double* out)
+{
+  CHECK_CTX(c);
+  int rc = download(c, out, c->d_len, (size_t)c->ne);
+  if (rc) return rc;
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return MAG_OK;
+}
+int mag_get_qualities(mag_ctx* c, double* out)
+{
+  CHECK_CTX(c);
+  int rc = download(c, out, c->d_qual, (size_t)(c->np + c->npy + c->nt));
+  if (rc) return rc;
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return MAG_OK;
+}
+int mag_get_flags(mag_ctx* c, int32_t* edge_flags, int32_t* elem_flags)
+{
+  CHECK_CTX(c);
+  int rc;
+  if (edge_flags && (rc = download(c, edge_flags, c->d_edge_flags, (size_t)c->ne))) return rc;
+  if (elem_flags && (rc = download(c, elem_flags, c->d_elem_flags, (size_t)(c->np + c->npy + c->nt)))) return rc;
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return MAG_OK;
+}
+int mag_get_layer_ok(mag_ctx* c, int32_t* ok, int32_t* codes)
+{
+  CHECK_CTX(c);
+  int rc;
+  if (ok && (rc = download(c, ok, c->d_layer_ok, (size_t)(c->np + c->npy)))) return rc;
+  if (codes && (rc = download(c, codes, c->d_layer_codes, (size_t)(c->np + c->npy)))) return rc;
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return MAG_OK;
+}
+
+int mag_get_stats(mag_ctx* c, mag_stats* out)
+{
+  CHECK_CTX(c);
+  if (!out) return mag_fail(c, MAG_ERR_ARG, "mag_get_stats: null out");
+  MAG_CUDA(c, cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(MagDevStats), cudaMemcpyDeviceToHost, c->stream));
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  const MagDevStats& s = *c->h_stats;
+  out->n_split = (int64_t)s.n_split;
+  out->n_collapse = (int64_t)s.n_collapse;
+  out->n_bad = (int64_t)s.n_bad;
+  out->n_edges_evaluated = (int64_t)s.n_edges_eval;
+  out->n_elems_evaluated = (int64_t)s.n_elems_eval;
+  out->n_near_threshold = (int64_t)(s.n_near_edge + s.n_near_elem);
+  out->n_layer_unsafe = (int64_t)s.n_layer_unsafe;
+  out->n_flag_mismatch = (int64_t)s.n_flag_mismatch;
+  out->min_quality = magk_key_to_double(s.min_q_key);
+  memcpy(&out->max_length, &s.max_len_bits, 8);
+  out->sum_length = s.sum_len;
+  if (s.n_flag_err)
+    return mag_fail(c, MAG_ERR_FLAG_STATE, "%llu entities already carried the flag being marked (ma::markEntities asserts, maAdapt.cc:308)", s.n_flag_err);
+  if (s.n_eigen_fail)
+    return mag_fail(c, MAG_ERR_EIGEN, "eigenQR failed on %llu evaluations (apf::eigen asserts convergence, apfMatrix.cc:76)", s.n_eigen_fail);
+  if (s.n_nonsimplex)
+    return mag_fail(c, MAG_ERR_NONSIMPLEX, "%llu prisms/pyramids reached markBadQuality without OK_QUALITY (maQuality.cc:169-182 has no entry for them)", s.n_nonsimplex);
+  return MAG_OK;
+}
+
+int mag_get_near_threshold(mag_ctx* c, int which, int64_t* idx, int64_t cap, int64_t* n)
+{
+  CHECK_CTX(c);
+  if (!n || (which != 0 && which != 1)) return mag_fail(c, MAG_ERR_ARG, "mag_get_near_threshold: bad argument");
+  MAG_CUDA(c, cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(MagDevStats), cudaMemcpyDeviceToHost, c->stream));
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  int64_t total = (int64_t)(which ? c->h_stats->n_near_elem : c->h_stats->n_near_edge);
+  *n = total;
+  int64_t m = total < cap ? total : cap;
+  if (m > MAG_NEAR_CAP) m = MAG_NEAR_CAP;
+  if (idx && m > 0) {
+    MAG_CUDA(c, cudaMemcpyAsync(idx, which ? c->d_near_elem : c->d_near_edge, (size_t)m * 8, cudaMemcpyDeviceToHost, c->stream));
+    MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return MAG_OK;
+}
+
+} // extern "C"

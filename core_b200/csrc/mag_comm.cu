@@ -1,0 +1,223 @@
+// mag_comm.cu -- part-boundary flag exchange and global statistics over NCCL (NVLink 5 / NVSwitch).
+// Replaces, on the sweep path only, PCU's phased p2p exchange in ma::checkFlagConsistency /
+// ma::syncFlag (ma/maAdapt.cc:226-256, 498-520) and the PCU Add / Min / Max scalar reductions
+// (ma/maAdapt.cc:323, ma/maShape.cc:168, ma/maSize.cc:689).
+//
+// NCCL is bound at run time (dlopen "libnccl.so.2"): a process that already loaded a NCCL (e.g.
+// through torch.distributed) shares that one; a single-GPU user never needs NCCL installed.
+#include "mag_internal.h"
+#include <dlfcn.h>
+#include <cstring>
+#include <nccl.h>
+
+namespace {
+
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string err;
+};
+NcclApi g_nccl;
+
+bool load_nccl()
+{
+  if (g_nccl.h) return true;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { g_nccl.err = dlerror(); return false; }
+#define BIND(name)                                                                 \
+  *(void**)(&g_nccl.name) = dlsym(h, "nccl" #name);                                \
+  if (!g_nccl.name) { g_nccl.err = "missing symbol nccl" #name; dlclose(h); return false; }
+  BIND(GetUniqueId) BIND(CommInitRank) BIND(CommDestroy) BIND(Send) BIND(Recv) BIND(AllGather)
+  BIND(GroupStart) BIND(GroupEnd) BIND(GetErrorString)
+#undef BIND
+  g_nccl.h = h;
+  return true;
+}
+
+#define MAG_NCCL(c, call)                                                                       \
+  do {                                                                                          \
+    ncclResult_t r_ = (call);                                                                   \
+    if (r_ != ncclSuccess)                                                                      \
+      return mag_fail((c), MAG_ERR_NCCL, "%s:%d: %s: %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_)); \
+  } while (0)
+
+__global__ void k_gather_flags(int64_t n, const int32_t* __restrict__ idx, const int32_t* __restrict__ flags,
+                               int32_t mask, int32_t* __restrict__ out)
+{
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = flags[idx[i]] & mask;
+}
+// mode 0: compare, count mismatches, take the peer's bits where the peer owns the entity (owner wins)
+// mode 1: OR the peer's bits in (ma::syncFlag)
+__global__ void k_merge_flags(int64_t n, const int32_t* __restrict__ idx, const int32_t* __restrict__ recv,
+                              const uint8_t* __restrict__ peer_owns, int32_t mask, int mode,
+                              int32_t* __restrict__ flags, MagDevStats* st)
+{
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int32_t e = idx[i];
+  int32_t mine = flags[e], theirs = recv[i] & mask;
+  if (mode == 1) {
+    if (theirs & ~mine) atomicOr(&flags[e], theirs); // an edge can sit in several peers' lists
+    return;
+  }
+  if ((mine & mask) != theirs) {
+    atomicAdd(&st->n_flag_mismatch, 1ull);
+    if (peer_owns && peer_owns[i]) flags[e] = (mine & ~mask) | theirs;
+  }
+}
+
+int exchange(mag_ctx* c, int32_t mask, int mode)
+{
+  if (c->links.empty()) return MAG_OK;
+  if (!c->nccl_comm) return mag_fail(c, MAG_ERR_ARG, "flag exchange: call mag_comm_init first");
+  ncclComm_t comm = (ncclComm_t)c->nccl_comm;
+  for (auto& L : c->links)
+    if (L.n) k_gather_flags<<<(unsigned)((L.n + 255) / 256), 256, 0, c->stream>>>(L.n, L.d_idx, c->d_edge_flags, mask, L.d_send);
+  MAG_CUDA(c, cudaGetLastError());
+  MAG_NCCL(c, g_nccl.GroupStart());
+  for (auto& L : c->links) {
+    if (!L.n) continue;
+    MAG_NCCL(c, g_nccl.Send(L.d_send, (size_t)L.n, ncclInt32, L.peer, comm, c->stream));
+    MAG_NCCL(c, g_nccl.Recv(L.d_recv, (size_t)L.n, ncclInt32, L.peer, comm, c->stream));
+  }
+  MAG_NCCL(c, g_nccl.GroupEnd());
+  for (auto& L : c->links)
+    if (L.n) k_merge_flags<<<(unsigned)((L.n + 255) / 256), 256, 0, c->stream>>>(L.n, L.d_idx, L.d_recv, L.d_peer_owns, mask, mode, c->d_edge_flags, c->d_stats);
+  MAG_CUDA(c, cudaGetLastError());
+  return MAG_OK;
+}
+
+void free_links(mag_ctx* c)
+{
+  for (auto& L : c->links) { cudaFree(L.d_idx); cudaFree(L.d_send); cudaFree(L.d_recv); cudaFree(L.d_peer_owns); }
+  c->links.clear();
+}
+
+} // namespace
+
+void magc_destroy(mag_ctx* c)
+{
+  free_links(c);
+  if (c->nccl_comm && g_nccl.h) g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
+  c->nccl_comm = nullptr;
+}
+
+extern "C" {
+
+int mag_comm_unique_id(void* out_id)
+{
+  static_assert(sizeof(ncclUniqueId) <= MAG_UNIQUE_ID_BYTES, "unique id size");
+  if (!out_id) return MAG_ERR_ARG;
+  if (!load_nccl()) return mag_fail(nullptr, MAG_ERR_NCCL, "cannot load NCCL: %s", g_nccl.err.c_str());
+  ncclUniqueId id;
+  ncclResult_t r = g_nccl.GetUniqueId(&id);
+  if (r != ncclSuccess) return mag_fail(nullptr, MAG_ERR_NCCL, "ncclGetUniqueId: %s", g_nccl.GetErrorString(r));
+  memset(out_id, 0, MAG_UNIQUE_ID_BYTES);
+  memcpy(out_id, &id, sizeof(id));
+  return MAG_OK;
+}
+
+int mag_comm_init(mag_ctx* c, int nranks, int rank, const void* unique_id)
+{
+  if (!c) return MAG_ERR_ARG;
+  MAG_CUDA(c, cudaSetDevice(c->device));
+  if (nranks < 1 || rank < 0 || rank >= nranks || !unique_id) return mag_fail(c, MAG_ERR_ARG, "mag_comm_init: bad arguments");
+  if (!load_nccl()) return mag_fail(c, MAG_ERR_NCCL, "cannot load NCCL: %s", g_nccl.err.c_str());
+  if (c->nccl_comm) { g_nccl.CommDestroy((ncclComm_t)c->nccl_comm); c->nccl_comm = nullptr; }
+  ncclUniqueId id;
+  memcpy(&id, unique_id, sizeof(id));
+  ncclComm_t comm;
+  MAG_NCCL(c, g_nccl.CommInitRank(&comm, nranks, id, rank));
+  c->nccl_comm = comm;
+  c->nranks = nranks;
+  c->rank = rank;
+  return MAG_OK;
+}
+
+int mag_set_edge_links(mag_ctx* c, int npeers, const int32_t* peer, const int64_t* n, const int32_t* const* idx,
+                       const uint8_t* const* peer_owns)
+{
+  if (!c) return MAG_ERR_ARG;
+  MAG_CUDA(c, cudaSetDevice(c->device));
+  if (npeers < 0 || (npeers && (!peer || !n || !idx))) return mag_fail(c, MAG_ERR_ARG, "mag_set_edge_links: bad arguments");
+  free_links(c);
+  for (int k = 0; k < npeers; ++k) {
+    MagLinks L;
+    L.peer = peer[k];
+    L.n = n[k];
+    L.d_idx = L.d_send = L.d_recv = nullptr;
+    L.d_peer_owns = nullptr;
+    if (L.n) {
+      MAG_CUDA(c, cudaMalloc((void**)&L.d_idx, (size_t)L.n * 4));
+      MAG_CUDA(c, cudaMalloc((void**)&L.d_send, (size_t)L.n * 4));
+      MAG_CUDA(c, cudaMalloc((void**)&L.d_recv, (size_t)L.n * 4));
+      MAG_CUDA(c, cudaMemcpyAsync(L.d_idx, idx[k], (size_t)L.n * 4, cudaMemcpyHostToDevice, c->stream));
+      if (peer_owns && peer_owns[k]) {
+        MAG_CUDA(c, cudaMalloc((void**)&L.d_peer_owns, (size_t)L.n));
+        MAG_CUDA(c, cudaMemcpyAsync(L.d_peer_owns, peer_owns[k], (size_t)L.n, cudaMemcpyHostToDevice, c->stream));
+      }
+    }
+    c->links.push_back(L);
+  }
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return MAG_OK;
+}
+
+int mag_reconcile_edge_flags(mag_ctx* c, int32_t flag_mask)
+{
+  if (!c) return MAG_ERR_ARG;
+  MAG_CUDA(c, cudaSetDevice(c->device));
+  return exchange(c, flag_mask, 0);
+}
+int mag_sync_edge_flags(mag_ctx* c, int32_t flag_mask)
+{
+  if (!c) return MAG_ERR_ARG;
+  MAG_CUDA(c, cudaSetDevice(c->device));
+  return exchange(c, flag_mask, 1);
+}
+
+int mag_allreduce_stats(mag_ctx* c, mag_stats* global)
+{
+  if (!c || !global) return MAG_ERR_ARG;
+  MAG_CUDA(c, cudaSetDevice(c->device));
+  mag_stats mine;
+  int rc = mag_get_stats(c, &mine);
+  if (rc) return rc;
+  if (c->nranks == 1 || !c->nccl_comm) { *global = mine; return MAG_OK; }
+  // one all-gather of the whole struct (sum / min / max are different operators, so a single
+  // allreduce cannot carry them), reduced locally
+  const size_t sz = sizeof(mag_stats);
+  char* d_buf = nullptr;
+  MAG_CUDA(c, cudaMalloc((void**)&d_buf, sz * (size_t)(c->nranks + 1)));
+  MAG_CUDA(c, cudaMemcpyAsync(d_buf, &mine, sz, cudaMemcpyHostToDevice, c->stream));
+  MAG_NCCL(c, g_nccl.AllGather(d_buf, d_buf + sz, sz, ncclChar, (ncclComm_t)c->nccl_comm, c->stream));
+  std::vector<mag_stats> all((size_t)c->nranks);
+  MAG_CUDA(c, cudaMemcpyAsync(all.data(), d_buf + sz, sz * (size_t)c->nranks, cudaMemcpyDeviceToHost, c->stream));
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  MAG_CUDA(c, cudaFree(d_buf));
+  mag_stats g = all[0];
+  for (int r = 1; r < c->nranks; ++r) {
+    const mag_stats& s = all[(size_t)r];
+    g.n_split += s.n_split; g.n_collapse += s.n_collapse; g.n_bad += s.n_bad;
+    g.n_edges_evaluated += s.n_edges_evaluated; g.n_elems_evaluated += s.n_elems_evaluated;
+    g.n_near_threshold += s.n_near_threshold; g.n_layer_unsafe += s.n_layer_unsafe;
+    g.n_flag_mismatch += s.n_flag_mismatch;
+    if (s.min_quality < g.min_quality) g.min_quality = s.min_quality;
+    if (s.max_length > g.max_length) g.max_length = s.max_length;
+    g.sum_length += s.sum_length;
+  }
+  *global = g;
+  return MAG_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,91 @@
+// mag_internal.h -- context layout shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/mag.h"
+
+enum MagKind { MAG_KIND_NONE = -1, MAG_KIND_IDENTITY = 0, MAG_KIND_ISO = 1, MAG_KIND_ANISO = 2, MAG_KIND_LOGM = 3 };
+
+// device-side accumulators of one sweep (zeroed by mag_sweep)
+struct MagDevStats {
+  unsigned long long n_split, n_collapse, n_bad;
+  unsigned long long n_edges_eval, n_elems_eval;
+  unsigned long long n_near_edge, n_near_elem;
+  unsigned long long n_layer_unsafe;
+  unsigned long long n_flag_err, n_eigen_fail, n_nonsimplex;
+  unsigned long long n_flag_mismatch;
+  unsigned long long max_len_bits; // bits of a non-negative double: integer order == fp order
+  unsigned long long min_q_key;    // order-preserving key of a double (see dkey())
+  double sum_len;
+};
+
+#define MAG_NEAR_CAP (1 << 20)
+#define MAG_NEAR_REL 1e-12
+// transient bit (never visible to the caller): entity awaits strict re-evaluation
+#define MAG_PENDING_BIT (1 << 30)
+
+struct MagLinks {
+  int peer;
+  int64_t n;
+  int32_t* d_idx;       // local edge indices shared with this peer
+  int32_t* d_send;      // packed flag words to send
+  int32_t* d_recv;      // packed flag words received
+  uint8_t* d_peer_owns; // optional: 1 where the peer's copy is the owner
+};
+
+struct mag_ctx {
+  int device;
+  cudaStream_t own_stream, stream;
+  std::string err;
+
+  int64_t nv, ne, nt, np, npy;
+  int kind;
+  bool vertex_pass_valid;
+
+  // raw uploads (kept so coordinates or metric can be replaced independently)
+  double* d_xyz;   // [nv][3]
+  double* d_ma;    // iso: s[nv]; aniso: h[nv][3]
+  double* d_mb;    // aniso: R[nv][9]; logm: logM[nv][9]
+  // packed gather records
+  double* d_vedge; // per vertex: iso/identity 4 doubles {x,y,z,s}; aniso/logm 12 doubles
+  double* d_vpos;  // per vertex 4 doubles {x,y,z,det Q_v}
+  double* d_vq;    // per vertex 10 doubles {Q_v row-major, det Q_v}
+  int32_t* d_edge_v;  // [ne][2]
+  int32_t* d_tet_v;   // [nt][4]
+  int32_t* d_prism_v; // [np][6]
+  int32_t* d_pyr_v;   // [npy][5]
+  uint8_t* d_edge_owned; // may be null
+  uint8_t* d_elem_owned; // may be null
+  int32_t* d_edge_flags; // [ne]
+  int32_t* d_elem_flags; // [np+npy+nt]
+  double* d_len;         // [ne]
+  double* d_qual;        // [np+npy+nt]
+  int32_t* d_layer_ok;   // [np+npy]
+  int32_t* d_layer_codes;
+  MagDevStats* d_stats;
+  MagDevStats* h_stats;  // pinned
+  double* d_block_sums;  // per-block partial sums of owned edge lengths
+  int64_t n_block_sums;
+  int64_t* d_near_edge;  // [MAG_NEAR_CAP]
+  int64_t* d_near_elem;
+  size_t cap_vedge, cap_ma, cap_mb;
+
+  // last sweep parameters (for the near-threshold fix-up and getters)
+  uint32_t last_ops;
+  int last_fp_mode;
+
+  // multi-GPU
+  void* nccl_comm;
+  int nranks, rank;
+  std::vector<MagLinks> links;
+};
+
+int mag_fail(mag_ctx* c, int code, const char* fmt, ...);
+#define MAG_CUDA(c, call)                                                                      \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return mag_fail((c), MAG_ERR_CUDA, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)

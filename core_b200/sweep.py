@@ -1,0 +1,241 @@
+"""Host-side mirror of the reference interface for the MeshAdapt marking / quality sweep.
+
+`Part` is one mesh part resident on one B200 (one `mag_ctx`).  Method names follow the
+reference's free functions and `ma::SizeField` so tests read like the reference's own
+drivers (test/measureAnisoStats.cc, ma/maStats.cc):
+
+    markEdgesToSplit / markEdgesToCollapse / markBadQuality / getMinQuality
+    getMaximumEdgeLength / getEdgeLengthsInMetricSpace / getLinearQualitiesInMetricSpace
+
+Everything runs through the C ABI (include/mag.h); there is no CPU fallback.
+"""
+import ctypes as C
+import numpy as np
+
+from ._lib import lib, MagStats
+
+# ma/maSize.h:26-27, ma/maInput.cc:32-46
+MAXLENGTH = 1.5
+MINLENGTH = 0.5
+GOOD_QUALITY_3D = 0.027
+
+# ma/maAdapt.h:17-37
+SPLIT, DONT_SPLIT, COLLAPSE, DONT_COLLAPSE, CHECKED, BAD_QUALITY, OK_QUALITY = (1 << i for i in range(7))
+SNAP, DONT_SNAP, DONT_SWAP, LAYER, LAYER_BASE, LAYER_TOP = (1 << i for i in range(7, 13))
+NEED_NOT_SPLIT, NEED_NOT_COLLAPSE = 1 << 17, 1 << 18
+
+OP_LENGTHS, OP_MARK_SPLIT, OP_MARK_COLLAPSE, OP_QUALITIES, OP_MARK_BAD, OP_LAYER_CHECK = (1 << i for i in range(6))
+OP_ALL = 63
+FP_STRICT, FP_FAST = 0, 1
+
+ERR_NAMES = {1: "MAG_ERR_CUDA", 2: "MAG_ERR_ARG", 3: "MAG_ERR_FLAG_STATE", 4: "MAG_ERR_EIGEN",
+             5: "MAG_ERR_NONSIMPLEX", 6: "MAG_ERR_NCCL", 7: "MAG_ERR_INCONSISTENT"}
+
+
+class MagError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("%s: %s" % (ERR_NAMES.get(code, code), msg))
+        self.code = code
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    # torch tensor (pinned host memory) or anything with data_ptr()
+    return C.c_void_p(a.data_ptr())
+
+
+def _arr(a, dtype, shape=None):
+    """Contiguous view of the right dtype without copying when already so (numpy or torch)."""
+    if a is None:
+        return None
+    if not isinstance(a, np.ndarray) and hasattr(a, "data_ptr"):
+        return a
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a
+
+
+class Part:
+    def __init__(self, device=0):
+        self._L = lib()
+        h = C.c_void_p()
+        rc = self._L.mag_create(C.byref(h), int(device))
+        if rc:
+            raise MagError(rc, self._L.mag_last_error(None).decode())
+        self._h = h
+        self.device = device
+        self.nv = self.ne = self.nt = self.np_ = self.npy = 0
+        self._keep = []
+
+    # ---- plumbing
+    def _ck(self, rc):
+        if rc:
+            raise MagError(rc, self._L.mag_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            self._L.mag_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self._L.mag_set_stream(self._h, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
+
+    def synchronize(self):
+        self._ck(self._L.mag_synchronize(self._h))
+
+    @property
+    def nelem(self):
+        return self.np_ + self.npy + self.nt
+
+    # ---- export
+    def set_mesh(self, xyz, edge_v, tet_v=None, prism_v=None, pyr_v=None, edge_owned=None, elem_owned=None):
+        xyz = _arr(xyz, np.float64)
+        edge_v, tet_v = _arr(edge_v, np.int32), _arr(tet_v, np.int32)
+        prism_v, pyr_v = _arr(prism_v, np.int32), _arr(pyr_v, np.int32)
+        edge_owned, elem_owned = _arr(edge_owned, np.uint8), _arr(elem_owned, np.uint8)
+        n = lambda a, k: 0 if a is None else int(a.numel() if hasattr(a, "numel") else a.size) // k
+        self.nv, self.ne, self.nt = n(xyz, 3), n(edge_v, 2), n(tet_v, 4)
+        self.np_, self.npy = n(prism_v, 6), n(pyr_v, 5)
+        self._ck(self._L.mag_set_mesh(self._h, self.nv, _ptr(xyz), self.ne, _ptr(edge_v), self.nt, _ptr(tet_v),
+                                      self.np_, _ptr(prism_v), self.npy, _ptr(pyr_v),
+                                      _ptr(edge_owned), _ptr(elem_owned)))
+        self.synchronize()  # host buffers may be temporaries
+
+    def set_coords(self, xyz):
+        xyz = _arr(xyz, np.float64)
+        self._ck(self._L.mag_set_coords(self._h, _ptr(xyz)))
+        self.synchronize()
+
+    def set_size_field_identity(self):
+        self._ck(self._L.mag_set_metric_identity(self._h))
+
+    def set_size_field_iso(self, size):
+        size = _arr(size, np.float64)
+        self._ck(self._L.mag_set_metric_iso(self._h, _ptr(size)))
+        self.synchronize()
+
+    def set_size_field_aniso(self, h, R):
+        h, R = _arr(h, np.float64), _arr(R, np.float64)
+        self._ck(self._L.mag_set_metric_aniso(self._h, _ptr(h), _ptr(R)))
+        self.synchronize()
+
+    def set_size_field_logm(self, logM):
+        logM = _arr(logM, np.float64)
+        self._ck(self._L.mag_set_metric_logm(self._h, _ptr(logM)))
+        self.synchronize()
+
+    def set_flags(self, edge_flags=None, elem_flags=None):
+        ef, lf = _arr(edge_flags, np.int32), _arr(elem_flags, np.int32)
+        self._ck(self._L.mag_set_flags(self._h, _ptr(ef), _ptr(lf)))
+        self.synchronize()
+
+    # ---- sweep + results
+    def sweep(self, ops=OP_ALL, max_len=MAXLENGTH, min_len=MINLENGTH, good_quality=GOOD_QUALITY_3D,
+              use_max=True, fp_mode=FP_STRICT):
+        self._ck(self._L.mag_sweep(self._h, int(ops), float(max_len), float(min_len), float(good_quality),
+                                   int(bool(use_max)), int(fp_mode)))
+
+    def stats(self):
+        s = MagStats()
+        self._ck(self._L.mag_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def edge_lengths(self, out=None):
+        out = np.empty(self.ne, dtype=np.float64) if out is None else out
+        self._ck(self._L.mag_get_edge_lengths(self._h, _ptr(out)))
+        return out
+
+    def qualities(self, out=None):
+        out = np.empty(self.nelem, dtype=np.float64) if out is None else out
+        self._ck(self._L.mag_get_qualities(self._h, _ptr(out)))
+        return out
+
+    def flags(self, edge_out=None, elem_out=None):
+        ef = np.empty(self.ne, dtype=np.int32) if edge_out is None else edge_out
+        lf = np.empty(self.nelem, dtype=np.int32) if elem_out is None else elem_out
+        self._ck(self._L.mag_get_flags(self._h, _ptr(ef), _ptr(lf)))
+        return ef, lf
+
+    def layer_ok(self):
+        n = self.np_ + self.npy
+        ok, codes = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32)
+        self._ck(self._L.mag_get_layer_ok(self._h, _ptr(ok), _ptr(codes)))
+        return ok, codes
+
+    def near_threshold(self, which=0, cap=1 << 20):
+        idx = np.empty(cap, dtype=np.int64)
+        n = C.c_int64(0)
+        self._ck(self._L.mag_get_near_threshold(self._h, which, _ptr(idx), cap, C.byref(n)))
+        return idx[:min(n.value, cap)].copy(), n.value
+
+    # ---- the reference's entry points, same names and meaning
+    def markEdgesToSplit(self, fp_mode=FP_STRICT):          # ma/maRefine.cc:395-400
+        self.sweep(OP_MARK_SPLIT, fp_mode=fp_mode)
+        return self.stats()["n_split"]
+
+    def markEdgesToCollapse(self, fp_mode=FP_STRICT):       # ma/maCoarsen.cc:287-292
+        self.sweep(OP_MARK_COLLAPSE, fp_mode=fp_mode)
+        return self.stats()["n_collapse"]
+
+    def markBadQuality(self, good_quality=GOOD_QUALITY_3D, fp_mode=FP_STRICT):   # ma/maShape.cc:132-136
+        self.sweep(OP_MARK_BAD, good_quality=good_quality, fp_mode=fp_mode)
+        return self.stats()["n_bad"]
+
+    def getMinQuality(self, fp_mode=FP_STRICT):             # ma/maShape.cc:152-169
+        self.sweep(OP_QUALITIES, fp_mode=fp_mode)
+        return self.stats()["min_quality"]
+
+    def getMaximumEdgeLength(self, fp_mode=FP_STRICT):      # ma/maSize.cc:673-691
+        self.sweep(OP_LENGTHS, fp_mode=fp_mode)
+        return self.stats()["max_length"]
+
+    def getEdgeLengthsInMetricSpace(self, fp_mode=FP_STRICT):   # ma/maStats.cc:33-45
+        self.sweep(OP_LENGTHS, fp_mode=fp_mode)
+        return self.edge_lengths()
+
+    def getLinearQualitiesInMetricSpace(self, fp_mode=FP_STRICT):   # ma/maStats.cc:12-31 (cbrt in 3D)
+        self.sweep(OP_QUALITIES, fp_mode=fp_mode)
+        return np.cbrt(self.qualities()[self.np_ + self.npy:])
+
+    # ---- multi-GPU (NCCL)
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_char * 128)()
+        rc = lib().mag_comm_unique_id(buf)
+        if rc:
+            raise MagError(rc, lib().mag_last_error(None).decode())
+        return bytes(buf)
+
+    def comm_init(self, nranks, rank, unique_id):
+        buf = (C.c_char * 128).from_buffer_copy(unique_id)
+        self._ck(self._L.mag_comm_init(self._h, nranks, rank, buf))
+
+    def set_edge_links(self, links):
+        """links: list of (peer, idx int32 array, peer_owns uint8 array or None)."""
+        k = len(links)
+        peers = (C.c_int32 * k)(*[int(l[0]) for l in links])
+        ns = (C.c_int64 * k)(*[int(len(l[1])) for l in links])
+        idx = [np.ascontiguousarray(l[1], dtype=np.int32) for l in links]
+        own = [None if l[2] is None else np.ascontiguousarray(l[2], dtype=np.uint8) for l in links]
+        idxp = (C.c_void_p * k)(*[a.ctypes.data for a in idx])
+        ownp = (C.c_void_p * k)(*[None if a is None else a.ctypes.data for a in own])
+        self._ck(self._L.mag_set_edge_links(self._h, k, peers, ns, idxp, ownp))
+
+    def reconcile_edge_flags(self, mask):
+        self._ck(self._L.mag_reconcile_edge_flags(self._h, int(mask)))
+
+    def sync_edge_flags(self, mask):
+        self._ck(self._L.mag_sync_edge_flags(self._h, int(mask)))
+
+    def allreduce_stats(self):
+        s = MagStats()
+        self._ck(self._L.mag_allreduce_stats(self._h, C.byref(s)))
+        return s.as_dict()

@@ -1,0 +1,164 @@
+/* mag.h -- C ABI of the B200-native MeshAdapt marking / quality sweep.
+ *
+ * "mag" = MeshAdapt on GPU.  One opaque context per (CUDA device, mesh part).
+ * The library replaces, for whole-mesh sweeps only, the following SCOREC/core
+ * entry points (paths relative to the reference tree):
+ *
+ *   ma::SizeField::measure / shouldSplit / shouldCollapse   ma/maSize.h:30-54, ma/maSize.cc:208-224
+ *   AnisoSizeField / LogAnisoSizeField / IsoSizeField::getTransform   ma/maSize.cc:395-413, 506-522, 581-616
+ *   ma::measureElementQuality (tets, mean ratio cubed)      ma/maShape.h:24-26, ma/maQuality.cc:139-182
+ *   ma::markEdgesToSplit                                    ma/maRefine.h:52,  ma/maRefine.cc:395-400
+ *   ma::markEdgesToCollapse                                 ma/maCoarsen.cc:287-292
+ *   ma::markBadQuality / getMinQuality                      ma/maShape.cc:132-169
+ *   ma::markEntities (skip / set-flag / owned-count rules)  ma/maAdapt.cc:293-324
+ *   ma::getMaximumEdgeLength                                ma/maSize.cc:673-691
+ *   ma::isPrismOk / isPyramidOk (layer element validity)    ma/maQuality.cc:490-560
+ *   ma::checkFlagConsistency / syncFlag (part boundaries)   ma/maAdapt.cc:226-256, 498-520
+ *   PCU Add<long> / Min<double> / Max<double> on this path  ma/maAdapt.cc:323, ma/maShape.cc:168, ma/maSize.cc:689
+ *
+ * Conventions: every call returns 0 on success or a MAG_ERR_* code and never
+ * throws or aborts across the ABI; mag_last_error() gives the message.  The
+ * caller owns every host buffer; the library copies what it needs into
+ * device-resident arrays.  One host thread per context.  Plain pointers and
+ * sizes only.  There is NO CPU fallback: without a CUDA device mag_create fails.
+ *
+ * Entity order is the caller's (the adapter uses the reference's m->begin(d)
+ * iteration order).  Vertex ids are 0-based int32.  Dimension-3 entities are
+ * ordered prisms, pyramids, tets, as MDS iterates them (mds/mds.h:16-26 type
+ * order WEDGE, PYRAMID, TET); "element" arrays (flags, owned, qualities) are the
+ * concatenation [prisms | pyramids | tets].
+ */
+#ifndef MAG_H
+#define MAG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mag_ctx mag_ctx;
+
+/* error codes */
+enum {
+  MAG_OK = 0,
+  MAG_ERR_CUDA = 1,        /* CUDA runtime error (message has the call site) */
+  MAG_ERR_ARG = 2,         /* bad argument / call order */
+  MAG_ERR_FLAG_STATE = 3,  /* an entity already carried the true-flag on entry: the reference asserts (maAdapt.cc:308) */
+  MAG_ERR_EIGEN = 4,       /* eigenQR did not converge in 100 iterations / zero Wilkinson denominator: the reference asserts (apfMatrix.cc:76, mthQR.cc:228) */
+  MAG_ERR_NONSIMPLEX = 5,  /* a prism/pyramid reached markBadQuality without OK_QUALITY: the reference dereferences a null table entry (maQuality.cc:169-182) */
+  MAG_ERR_NCCL = 6,
+  MAG_ERR_INCONSISTENT = 7 /* part-boundary copies disagree on a flag: the reference asserts (maRefine.cc:430, maCoarsen.cc:305) */
+};
+
+/* ma flag bits, identical to ma/maAdapt.h:17-37 */
+enum {
+  MAG_SPLIT = 1 << 0, MAG_DONT_SPLIT = 1 << 1, MAG_COLLAPSE = 1 << 2, MAG_DONT_COLLAPSE = 1 << 3,
+  MAG_CHECKED = 1 << 4, MAG_BAD_QUALITY = 1 << 5, MAG_OK_QUALITY = 1 << 6, MAG_SNAP = 1 << 7,
+  MAG_DONT_SNAP = 1 << 8, MAG_DONT_SWAP = 1 << 9, MAG_LAYER = 1 << 10, MAG_LAYER_BASE = 1 << 11,
+  MAG_LAYER_TOP = 1 << 12, MAG_DIAGONAL_1 = 1 << 13, MAG_DIAGONAL_2 = 1 << 14, MAG_LAYER_UNSNAP = 1 << 15,
+  MAG_DONT_MOVE = 1 << 16, MAG_NEED_NOT_SPLIT = 1 << 17, MAG_NEED_NOT_COLLAPSE = 1 << 18
+};
+
+/* what one mag_sweep call does (bit mask) */
+enum {
+  MAG_OP_LENGTHS = 1 << 0,       /* measure() of EVERY edge -> mag_get_edge_lengths (ma::getEdgeLengthsInMetricSpace, maStats.cc:33-45) */
+  MAG_OP_MARK_SPLIT = 1 << 1,    /* ma::markEdgesToSplit */
+  MAG_OP_MARK_COLLAPSE = 1 << 2, /* ma::markEdgesToCollapse */
+  MAG_OP_QUALITIES = 1 << 3,     /* measureElementQuality of EVERY tet + min (ma::getMinQuality, maStats.cc:12-31 before the cbrt) */
+  MAG_OP_MARK_BAD = 1 << 4,      /* ma::markBadQuality */
+  MAG_OP_LAYER_CHECK = 1 << 5,   /* ma::isPrismOk / isPyramidOk on every prism / pyramid (ma::checkLayerShape, maLayer.cc:166-192) */
+  MAG_OP_ALL = 63
+};
+
+/* arithmetic mode */
+enum {
+  MAG_FP_STRICT = 0, /* the reference's operation order, no FMA contraction, IEEE div/sqrt: bit-identical lengths, qualities, flags
+                        (LogAniso: exp() is CUDA's, within 1 ulp of glibc -> values within 1e-12, flags identical outside the listed band) */
+  MAG_FP_FAST = 1    /* algebraically equivalent, FMA-contracted evaluation (values within 1e-12 relative); every entity whose value
+                        lands within 1e-12 relative of a threshold is re-evaluated in strict arithmetic ON THE DEVICE and listed,
+                        so flags and counts stay identical to MAG_FP_STRICT */
+};
+
+typedef struct mag_stats {
+  int64_t n_split;          /* owned edges newly marked SPLIT      (return value of ma::markEdgesToSplit) */
+  int64_t n_collapse;       /* owned edges newly marked COLLAPSE   (ma::markEdgesToCollapse) */
+  int64_t n_bad;            /* owned elements newly marked BAD_QUALITY (ma::markBadQuality) */
+  int64_t n_edges_evaluated;/* edges whose predicate was evaluated (not skipped by DONT_ / NEED_NOT_ flags) */
+  int64_t n_elems_evaluated;
+  int64_t n_near_threshold; /* entities within 1e-12 relative of a threshold (see mag_get_near_threshold) */
+  int64_t n_layer_unsafe;   /* prisms / pyramids failing isPrismOk / isPyramidOk (ma::checkLayerShape count) */
+  int64_t n_flag_mismatch;  /* part-boundary copies that disagreed before owner reconciliation (must be 0) */
+  double min_quality;       /* ma::getMinQuality: min over all tets, initial value 1.0 (valid after MAG_OP_QUALITIES) */
+  double max_length;        /* ma::getMaximumEdgeLength: max over owned edges, initial 0.0 (valid after MAG_OP_LENGTHS) */
+  double sum_length;        /* sum over owned edges (deterministic tree order, not the reference's serial order) */
+} mag_stats;
+
+/* ---- lifetime ---- */
+int mag_create(mag_ctx** out, int device);
+void mag_destroy(mag_ctx* c);
+const char* mag_last_error(const mag_ctx* c); /* c may be NULL: last error of a failed mag_create */
+/* adopt a caller-owned cudaStream_t (e.g. the caller's timing stream); NULL restores the context's own stream */
+int mag_set_stream(mag_ctx* c, void* cuda_stream);
+int mag_synchronize(mag_ctx* c);
+
+/* ---- one-time export of a part (replaces per-entity apf::Mesh2 access: apfMDS.cc:309-318, 347-351, 288-298) ----
+   xyz [nv][3]; edge_v [ne][2]; tet_v [nt][4]; prism_v [np][6]; pyr_v [npy][5] (any count may be 0, pointer NULL);
+   edge_owned [ne] / elem_owned [np+npy+nt] bytes, NULL = every entity is owned (serial mesh). */
+int mag_set_mesh(mag_ctx* c, int64_t nv, const double* xyz,
+                 int64_t ne, const int32_t* edge_v,
+                 int64_t nt, const int32_t* tet_v,
+                 int64_t np, const int32_t* prism_v,
+                 int64_t npy, const int32_t* pyr_v,
+                 const uint8_t* edge_owned, const uint8_t* elem_owned);
+/* moved vertices, same connectivity (apf::Mesh2::setPoint) */
+int mag_set_coords(mag_ctx* c, const double* xyz);
+
+/* ---- size field (vertex nodes, linear Lagrange) ---- */
+int mag_set_metric_identity(mag_ctx* c);                                   /* ma::IdentitySizeField */
+int mag_set_metric_iso(mag_ctx* c, const double* size /*[nv]*/);           /* IsoSizeField / IsoUserField */
+int mag_set_metric_aniso(mag_ctx* c, const double* h /*[nv][3]*/,
+                         const double* R /*[nv][9] row-major, frame vectors in columns*/); /* AnisoSizeField */
+int mag_set_metric_logm(mag_ctx* c, const double* logM /*[nv][9] row-major*/);           /* LogAnisoSizeField's ma_logM field */
+
+/* ---- incoming "ma_flags" words; NULL = all zero (maAdapt.cc:80-88 getFlags default) ---- */
+int mag_set_flags(mag_ctx* c, const int32_t* edge_flags /*[ne]*/, const int32_t* elem_flags /*[np+npy+nt]*/);
+
+/* ---- the sweep.  max_len / min_len = ma::MAXLENGTH / MINLENGTH (1.5 / 0.5, maSize.h:26-27);
+   good_quality = ma::Input::goodQuality; use_max_metric = measureElementQuality's useMax (default true, maShape.h:26).
+   Asynchronous on the context's stream; results are read with the getters below (which synchronize). ---- */
+int mag_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double good_quality,
+              int use_max_metric, int fp_mode);
+
+/* ---- results ---- */
+int mag_get_edge_lengths(mag_ctx* c, double* out /*[ne]*/);
+int mag_get_qualities(mag_ctx* c, double* out /*[np+npy+nt], prisms/pyramids = 0*/);
+int mag_get_flags(mag_ctx* c, int32_t* edge_flags, int32_t* elem_flags); /* either may be NULL */
+int mag_get_layer_ok(mag_ctx* c, int32_t* ok /*[np+npy]*/, int32_t* codes /*[np+npy]*/);
+int mag_get_stats(mag_ctx* c, mag_stats* out); /* this part only; also reports deferred MAG_ERR_FLAG_STATE / EIGEN / NONSIMPLEX */
+/* entities whose value lay within 1e-12 relative of a threshold in the last sweep.
+   which: 0 = edges (vs max_len or min_len), 1 = elements (vs good_quality).  Writes up to cap indices, returns the total in *n. */
+int mag_get_near_threshold(mag_ctx* c, int which, int64_t* idx, int64_t cap, int64_t* n);
+
+/* ---- multi-GPU: one part per GPU, NCCL over NVLink (replaces PCU on this path only) ---- */
+#define MAG_UNIQUE_ID_BYTES 128
+int mag_comm_unique_id(void* out_id /*[MAG_UNIQUE_ID_BYTES]*/);
+int mag_comm_init(mag_ctx* c, int nranks, int rank, const void* unique_id);
+/* part-boundary links in the layout of struct mds_links (mds/mds_net.h:33-38): for each peer part k, idx[k][0..n[k]) are the
+   local indices of the edges shared with that peer, both sides listing them in the same order.  peer_owns (may be NULL, and
+   each peer_owns[k] may be NULL) marks entries whose owner is the peer's copy (apfPM.cc:109-126, evaluated by the caller). */
+int mag_set_edge_links(mag_ctx* c, int npeers, const int32_t* peer, const int64_t* n, const int32_t* const* idx,
+                       const uint8_t* const* peer_owns);
+/* ma::checkFlagConsistency(a, 1, flag) for every bit of flag_mask: copies exchange their bits and compare; the number of
+   disagreeing copies goes to mag_stats.n_flag_mismatch (the reference asserts it is 0) and, where peer_owns says so, the
+   owner's bits overwrite the local ones. */
+int mag_reconcile_edge_flags(mag_ctx* c, int32_t flag_mask);
+/* ma::syncFlag semantics: OR the bits of flag_mask across all copies */
+int mag_sync_edge_flags(mag_ctx* c, int32_t flag_mask);
+/* global statistics: sums of counts, min of min_quality, max of max_length over all parts */
+int mag_allreduce_stats(mag_ctx* c, mag_stats* global);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAG_H */
