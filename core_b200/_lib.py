@@ -16,7 +16,8 @@ SYMBOLS = [
     "mag_set_metric_identity", "mag_set_metric_iso", "mag_set_metric_aniso", "mag_set_metric_logm",
     "mag_set_flags", "mag_sweep",
     "mag_get_edge_lengths", "mag_get_qualities", "mag_get_flags", "mag_get_layer_ok", "mag_get_stats",
-    "mag_get_near_threshold",
+    "mag_get_near_threshold", "mag_set_metric_logm_from_frames",
+    "mag_timing_begin", "mag_timing_read", "mag_launch_count",
     "mag_comm_unique_id", "mag_comm_init", "mag_set_edge_links", "mag_reconcile_edge_flags",
     "mag_sync_edge_flags", "mag_allreduce_stats",
 ]
@@ -67,14 +68,16 @@ def lib():
     L.mag_get_layer_ok.argtypes = [vp, vp, vp]
     L.mag_get_stats.argtypes = [vp, C.POINTER(MagStats)]
     L.mag_get_near_threshold.argtypes = [vp, C.c_int, vp, i64, C.POINTER(i64)]
+    L.mag_set_metric_logm_from_frames.argtypes = [vp, vp, vp, C.c_int, vp]
+    L.mag_timing_begin.argtypes = [vp, C.c_int]
+    L.mag_timing_read.argtypes = [vp, vp, C.POINTER(C.c_int)]
+    L.mag_launch_count.argtypes = [vp]
+    L.mag_launch_count.restype = i64
     L.mag_comm_unique_id.argtypes = [vp]
     L.mag_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.mag_set_edge_links.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     L.mag_reconcile_edge_flags.argtypes = [vp, i32]
     L.mag_sync_edge_flags.argtypes = [vp, i32]
     L.mag_allreduce_stats.argtypes = [vp, C.POINTER(MagStats)]
-    for s in SYMBOLS:
-        if getattr(L, s).restype is C.c_int:
-            pass
     _lib = L
     return L

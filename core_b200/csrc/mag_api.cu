@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cmath>
 
 int magk_pack(mag_ctx* c);
 int magk_init_stats(mag_ctx* c);
@@ -118,6 +119,7 @@ int mag_create(mag_ctx** out, int device)
   c->cap_vedge = c->cap_ma = c->cap_mb = 0;
   c->last_ops = 0; c->last_fp_mode = 0;
   c->nccl_comm = nullptr; c->nranks = 1; c->rank = 0;
+  c->t_slots = c->t_used = 0; c->n_launches = 0;
   auto fail = [&](cudaError_t err, const char* what) {
     int rc = mag_fail(nullptr, MAG_ERR_CUDA, "mag_create: %s: %s", what, cudaGetErrorString(err));
     delete c;
@@ -148,6 +150,7 @@ void mag_destroy(mag_ctx* c)
   cudaFree(c->d_len); cudaFree(c->d_qual); cudaFree(c->d_layer_ok); cudaFree(c->d_layer_codes);
   cudaFree(c->d_stats); cudaFreeHost(c->h_stats); cudaFree(c->d_block_sums);
   cudaFree(c->d_near_edge); cudaFree(c->d_near_elem);
+  for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -264,11 +267,6 @@ int mag_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double g
   if (ops & ~(uint32_t)MAG_OP_ALL) return mag_fail(c, MAG_ERR_ARG, "mag_sweep: unknown op bits 0x%x", ops);
   int rc;
   if ((rc = magk_init_stats(c))) return rc;
-  const bool need_vertex = (ops & (MAG_OP_QUALITIES | MAG_OP_MARK_BAD | MAG_OP_LAYER_CHECK)) != 0;
-  if (need_vertex && !c->vertex_pass_valid) {
-    if ((rc = magk_vertex_pass(c))) return rc;
-    c->vertex_pass_valid = true;
-  }
   c->last_ops = ops;
   c->last_fp_mode = fp_mode;
   return magk_sweep(c, ops, max_len, min_len, good_quality, use_max_metric, fp_mode);
@@ -333,6 +331,69 @@ int mag_get_stats(mag_ctx* c, mag_stats* out)
     return mag_fail(c, MAG_ERR_EIGEN, "eigenQR failed on %llu evaluations (apf::eigen asserts convergence, apfMatrix.cc:76)", s.n_eigen_fail);
   if (s.n_nonsimplex)
     return mag_fail(c, MAG_ERR_NONSIMPLEX, "%llu prisms/pyramids reached markBadQuality without OK_QUALITY (maQuality.cc:169-182 has no entry for them)", s.n_nonsimplex);
+  return MAG_OK;
+}
+
+int mag_timing_begin(mag_ctx* c, int max_sweeps)
+{
+  CHECK_CTX(c);
+  if (max_sweeps < 0) return mag_fail(c, MAG_ERR_ARG, "mag_timing_begin: negative slot count");
+  while ((int)c->tev.size() < 4 * max_sweeps) {
+    cudaEvent_t e;
+    MAG_CUDA(c, cudaEventCreate(&e));
+    c->tev.push_back(e);
+  }
+  c->t_slots = max_sweeps;
+  c->t_used = 0;
+  return MAG_OK;
+}
+int mag_timing_read(mag_ctx* c, float* ms, int* n_out)
+{
+  CHECK_CTX(c);
+  if (!ms || !n_out) return mag_fail(c, MAG_ERR_ARG, "mag_timing_read: null argument");
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < c->t_used; ++i)
+    for (int k = 0; k < 3; ++k)
+      MAG_CUDA(c, cudaEventElapsedTime(&ms[3 * i + k], c->tev[(size_t)4 * i + k], c->tev[(size_t)4 * i + k + 1]));
+  *n_out = c->t_used;
+  c->t_slots = c->t_used = 0;
+  return MAG_OK;
+}
+int64_t mag_launch_count(const mag_ctx* c) { return c ? c->n_launches : -1; }
+
+// host-side construction of the logM field, operation for operation as the reference
+// (apf::Matrix product order, apfMatrix.h:94-106; libm log)
+int mag_set_metric_logm_from_frames(mag_ctx* c, const double* h, const double* R, int variant, double* out_logM)
+{
+  CHECK_CTX(c);
+  if (!h || !R) return mag_fail(c, MAG_ERR_ARG, "mag_set_metric_logm_from_frames: null array");
+  std::vector<double> tmp;
+  double* M = out_logM;
+  if (!M) { tmp.resize((size_t)c->nv * 9); M = tmp.data(); }
+  for (int64_t v = 0; v < c->nv; ++v) {
+    const double* r = R + 9 * v;
+    double s[3], T[3][3];
+    for (int i = 0; i < 3; ++i) s[i] = variant ? -2 * log(h[3 * v + i]) : log(1 / h[3 * v + i] / h[3 * v + i]);
+    // T = R * diag(s): r_ij = R_i0*S_0j; += R_i1*S_1j; += R_i2*S_2j with the zeros of S kept
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        double a = r[3 * i + 0] * (j == 0 ? s[0] : 0.0);
+        a += r[3 * i + 1] * (j == 1 ? s[1] : 0.0);
+        a += r[3 * i + 2] * (j == 2 ? s[2] : 0.0);
+        T[i][j] = a;
+      }
+    // M = T * transpose(R)
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        double a = T[i][0] * r[3 * j + 0];
+        a += T[i][1] * r[3 * j + 1];
+        a += T[i][2] * r[3 * j + 2];
+        M[9 * v + 3 * i + j] = a;
+      }
+  }
+  int rc = mag_set_metric_logm(c, M);
+  if (rc) return rc;
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream)); // tmp dies here
   return MAG_OK;
 }
 

@@ -76,6 +76,11 @@ struct mag_ctx {
   uint32_t last_ops;
   int last_fp_mode;
 
+  // instrumentation
+  std::vector<cudaEvent_t> tev; // 4 events per armed sweep slot
+  int t_slots, t_used;
+  int64_t n_launches;
+
   // multi-GPU
   void* nccl_comm;
   int nranks, rank;

@@ -679,6 +679,7 @@ int magk_pack(mag_ctx* c)
     default: return mag_fail(c, MAG_ERR_ARG, "no size field set");
   }
   MAG_CUDA(c, cudaGetLastError());
+  c->n_launches++;
   return MAG_OK;
 }
 
@@ -686,6 +687,7 @@ int magk_init_stats(mag_ctx* c)
 {
   k_init_stats<<<1, 1, 0, c->stream>>>(c->d_stats);
   MAG_CUDA(c, cudaGetLastError());
+  c->n_launches++;
   return MAG_OK;
 }
 
@@ -701,6 +703,7 @@ int magk_vertex_pass(mag_ctx* c)
     default: return mag_fail(c, MAG_ERR_ARG, "no size field set");
   }
   MAG_CUDA(c, cudaGetLastError());
+  c->n_launches++;
   return MAG_OK;
 }
 
@@ -712,14 +715,16 @@ static int launch_edges(mag_ctx* c, const SweepParams& P, bool fast)
   if (fast) {
     k_edges<KIND, true><<<g, kThreads, 0, c->stream>>>(c->ne, ev, c->d_vedge, c->d_edge_owned, c->d_edge_flags, c->d_len, P, c->d_stats, c->d_block_sums, c->d_near_edge);
     if (P.ops & (MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE))
-      k_fix_edges<KIND><<<148, kThreads, 0, c->stream>>>(c->ne, ev, c->d_vedge, c->d_edge_owned, c->d_edge_flags, P, c->d_stats, c->d_near_edge);
+    { k_fix_edges<KIND><<<148, kThreads, 0, c->stream>>>(c->ne, ev, c->d_vedge, c->d_edge_owned, c->d_edge_flags, P, c->d_stats, c->d_near_edge); c->n_launches++; }
   } else {
     k_edges<KIND, false><<<g, kThreads, 0, c->stream>>>(c->ne, ev, c->d_vedge, c->d_edge_owned, c->d_edge_flags, c->d_len, P, c->d_stats, c->d_block_sums, c->d_near_edge);
   }
   MAG_CUDA(c, cudaGetLastError());
+  c->n_launches++;
   if (P.ops & MAG_OP_LENGTHS) {
     k_finish_sum<<<1, kThreads, 0, c->stream>>>((int64_t)g, c->d_block_sums, c->d_stats);
     MAG_CUDA(c, cudaGetLastError());
+    c->n_launches++;
   }
   return MAG_OK;
 }
@@ -733,11 +738,12 @@ static int launch_tets(mag_ctx* c, const SweepParams& P, bool fast)
   if (fast) {
     k_tets<KIND, true><<<g, kThreads, 0, c->stream>>>(c->nt, off, tv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_owned, c->d_elem_flags, c->d_qual, P, c->d_stats, c->d_near_elem);
     if (P.ops & MAG_OP_MARK_BAD)
-      k_fix_tets<KIND><<<148, kThreads, 0, c->stream>>>(c->nt, off, tv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_owned, c->d_elem_flags, P, c->d_stats, c->d_near_elem);
+    { k_fix_tets<KIND><<<148, kThreads, 0, c->stream>>>(c->nt, off, tv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_owned, c->d_elem_flags, P, c->d_stats, c->d_near_elem); c->n_launches++; }
   } else {
     k_tets<KIND, false><<<g, kThreads, 0, c->stream>>>(c->nt, off, tv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_owned, c->d_elem_flags, c->d_qual, P, c->d_stats, c->d_near_elem);
   }
   MAG_CUDA(c, cudaGetLastError());
+  c->n_launches++;
   return MAG_OK;
 }
 
@@ -746,6 +752,13 @@ int magk_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double 
   SweepParams P{ops, max_len, min_len, good_q, use_max};
   const bool fast = fp_mode == MAG_FP_FAST;
   int rc;
+  cudaEvent_t* tev = (c->t_used < c->t_slots) ? &c->tev[(size_t)4 * c->t_used] : nullptr;
+  if (tev) MAG_CUDA(c, cudaEventRecord(tev[0], c->stream));
+  if (ops & (MAG_OP_QUALITIES | MAG_OP_MARK_BAD | MAG_OP_LAYER_CHECK)) {
+    // per-vertex transforms are part of every quality sweep (never cached across sweeps)
+    if ((rc = magk_vertex_pass(c))) return rc;
+  }
+  if (tev) MAG_CUDA(c, cudaEventRecord(tev[1], c->stream));
   if (c->ne && (ops & (MAG_OP_LENGTHS | MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE))) {
     switch (c->kind) {
       case MAG_KIND_IDENTITY: rc = launch_edges<MAG_KIND_IDENTITY>(c, P, fast); break;
@@ -755,6 +768,7 @@ int magk_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double 
     }
     if (rc) return rc;
   }
+  if (tev) MAG_CUDA(c, cudaEventRecord(tev[2], c->stream));
   if (ops & (MAG_OP_QUALITIES | MAG_OP_MARK_BAD)) {
     if (c->nt) {
       switch (c->kind) {
@@ -768,12 +782,15 @@ int magk_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double 
     if ((ops & MAG_OP_MARK_BAD) && (c->np + c->npy)) {
       k_nonsimplex_guard<<<grid_for(c->np + c->npy), kThreads, 0, c->stream>>>(c->np + c->npy, c->d_elem_flags, P, c->d_stats);
       MAG_CUDA(c, cudaGetLastError());
+      c->n_launches++;
     }
   }
   if ((ops & MAG_OP_LAYER_CHECK) && (c->np + c->npy)) {
     k_layer<<<grid_for(c->np + c->npy), kThreads, 0, c->stream>>>(c->np, c->npy, c->d_prism_v, c->d_pyr_v, c->d_vpos, c->d_layer_ok, c->d_layer_codes, c->d_stats);
     MAG_CUDA(c, cudaGetLastError());
+    c->n_launches++;
   }
+  if (tev) { MAG_CUDA(c, cudaEventRecord(tev[3], c->stream)); c->t_used++; }
   return MAG_OK;
 }
 

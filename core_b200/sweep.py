@@ -132,10 +132,22 @@ class Part:
         self._ck(self._L.mag_set_metric_logm(self._h, _ptr(logM)))
         self.synchronize()
 
+    def set_size_field_logm_from_frames(self, h, R, variant=0, want_logm=False):
+        """LogAnisoSizeField built from sizes/frames (variant 0, maSize.cc:491-499) or from a user
+        function (variant 1, maSize.cc:343-346); the log is the host libm's, as in the reference."""
+        h, R = _arr(h, np.float64), _arr(R, np.float64)
+        out = np.empty((self.nv, 9)) if want_logm else None
+        self._ck(self._L.mag_set_metric_logm_from_frames(self._h, _ptr(h), _ptr(R), int(variant), _ptr(out)))
+        return out
+
     def set_flags(self, edge_flags=None, elem_flags=None):
         ef, lf = _arr(edge_flags, np.int32), _arr(elem_flags, np.int32)
         self._ck(self._L.mag_set_flags(self._h, _ptr(ef), _ptr(lf)))
         self.synchronize()
+
+    def clear_flags(self):
+        """Incoming flag words = 0 on every entity (asynchronous device memset)."""
+        self._ck(self._L.mag_set_flags(self._h, None, None))
 
     # ---- sweep + results
     def sweep(self, ops=OP_ALL, max_len=MAXLENGTH, min_len=MINLENGTH, good_quality=GOOD_QUALITY_3D,
@@ -175,6 +187,20 @@ class Part:
         n = C.c_int64(0)
         self._ck(self._L.mag_get_near_threshold(self._h, which, _ptr(idx), cap, C.byref(n)))
         return idx[:min(n.value, cap)].copy(), n.value
+
+    def timing_begin(self, max_sweeps):
+        self._ck(self._L.mag_timing_begin(self._h, int(max_sweeps)))
+        self._tslots = int(max_sweeps)
+
+    def timing_read(self):
+        """rows of (vertex_ms, edge_ms, elem_ms), one per sweep since timing_begin."""
+        ms = np.zeros((max(self._tslots, 1), 3), dtype=np.float32)
+        n = C.c_int(0)
+        self._ck(self._L.mag_timing_read(self._h, _ptr(ms), C.byref(n)))
+        return ms[:n.value].astype(np.float64)
+
+    def launch_count(self):
+        return int(self._L.mag_launch_count(self._h))
 
     # ---- the reference's entry points, same names and meaning
     def markEdgesToSplit(self, fp_mode=FP_STRICT):          # ma/maRefine.cc:395-400

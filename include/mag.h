@@ -140,6 +140,20 @@ int mag_get_stats(mag_ctx* c, mag_stats* out); /* this part only; also reports d
    which: 0 = edges (vs max_len or min_len), 1 = elements (vs good_quality).  Writes up to cap indices, returns the total in *n. */
 int mag_get_near_threshold(mag_ctx* c, int which, int64_t* idx, int64_t cap, int64_t* n);
 
+/* the logM vertex field from sizes + frames, computed on the host exactly as the reference does (libm log):
+   variant 0 = LogAnisoSizeField::init from fields, log(1/h/h)   (ma/maSize.cc:491-499)
+   variant 1 = LogMEval from a user function, -2*log(h)          (ma/maSize.cc:343-346)
+   then uploaded like mag_set_metric_logm.  out_logM (may be NULL) receives the [nv][9] field. */
+int mag_set_metric_logm_from_frames(mag_ctx* c, const double* h, const double* R, int variant, double* out_logM);
+
+/* ---- instrumentation (bench.py): per-sweep device times from CUDA events recorded on the context's stream around
+   the vertex pass, the edge kernels and the element kernels.  mag_timing_begin(c, n) arms n slots; each mag_sweep fills
+   the next one; mag_timing_read synchronizes and writes up to n rows {vertex_ms, edge_ms, elem_ms}; returns rows in *n_out. */
+int mag_timing_begin(mag_ctx* c, int max_sweeps);
+int mag_timing_read(mag_ctx* c, float* ms /*[max_sweeps][3]*/, int* n_out);
+/* number of CUDA kernels this context has launched so far */
+int64_t mag_launch_count(const mag_ctx* c);
+
 /* ---- multi-GPU: one part per GPU, NCCL over NVLink (replaces PCU on this path only) ---- */
 #define MAG_UNIQUE_ID_BYTES 128
 int mag_comm_unique_id(void* out_id /*[MAG_UNIQUE_ID_BYTES]*/);
