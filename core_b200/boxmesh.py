@@ -145,3 +145,64 @@ def slab_part(gnx, ny, nz, nparts, part, wx=1.0, wy=1.0, wz=1.0):
         links.append((peer, np.ascontiguousarray(mine.astype(np.int32)), peer_owns))
     return dict(xyz=xyz, edge_v=edge_v, tet_v=tet_v, edge_owned=edge_owned,
                 elem_owned=np.ones(nt, dtype=np.uint8), links=links, x0=lo, nx=nx, sx=sx)
+
+
+# ---------------------------------------------------------------------------- mixed prism / tet boxes (config 5)
+def mixed_box(n, k, index_dtype=np.int32):
+    """n^3 cells: the bottom k cell layers are 2 prisms per cell, (0,1,2|4,5,6) and (0,2,3|4,6,7) -- conforming to
+    the 0-2 bottom diagonal of the Kuhn tets (apfBox.cc:250-256) -- and Kuhn tets above.  Returns
+    (xyz, edge_v, tet_v, prism_v); edges are the unique vertex pairs of all elements sorted by (min, max) vertex
+    (a mixed mesh cannot come from makeMdsBox, so there is no reference creation order to follow; the parity
+    fixtures of tests/golden use the order apf::buildElement produced)."""
+    s = n + 1
+    g = np.arange(s) / n
+    xyz = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).transpose(2, 1, 0, 3).reshape(-1, 3).copy()
+    cx, cy, cz = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    c0 = (cx + s * (cy + s * cz)).transpose(2, 1, 0).reshape(-1)
+    zc = cz.transpose(2, 1, 0).reshape(-1)
+    stride = np.array([1, s, s * s], dtype=np.int64)
+    corner = c0[:, None] + (_CORNER @ stride)[None, :]
+    lay = zc < k
+    pc = corner[lay]
+    prism_v = np.stack([pc[:, [0, 1, 2, 4, 5, 6]], pc[:, [0, 2, 3, 4, 6, 7]]], axis=1).reshape(-1, 6)
+    tet_v = corner[~lay][:, _TET_VERTS.reshape(-1)].reshape(-1, 4)
+    pairs = [tet_v[:, [a, b]] for a, b in ((0, 1), (1, 2), (2, 0), (0, 3), (1, 3), (2, 3))]
+    pairs += [prism_v[:, [a, b]] for a, b in _PRISM_EDGES]
+    e = np.sort(np.concatenate(pairs, axis=0), axis=1)
+    edge_v = np.unique(e, axis=0)
+    return (xyz, np.ascontiguousarray(edge_v.astype(index_dtype)), np.ascontiguousarray(tet_v.astype(index_dtype)),
+            np.ascontiguousarray(prism_v.astype(index_dtype)))
+
+
+# apf prism_edge_verts / pyramid_edge_verts (apf/apfMesh.cc:62-78)
+_PRISM_EDGES = ((0, 1), (1, 2), (2, 0), (0, 3), (1, 4), (2, 5), (3, 4), (4, 5), (5, 3))
+_PYRAMID_EDGES = ((0, 1), (1, 2), (2, 3), (3, 0), (0, 4), (1, 4), (2, 4), (3, 4))
+_LAYER, _DONT_SPLIT, _DONT_COLLAPSE, _DONT_SWAP, _OK_QUALITY = 1 << 10, 1 << 1, 1 << 3, 1 << 9, 1 << 6
+
+
+def layer_closure_flags(edge_v, prism_v, pyr_v, nt):
+    """The "ma_flags" words ma::Adapt's constructor leaves on a mesh with layer elements, before any mark
+    (markLayerElements + freezeLayer, ma/maLayer.cc:11-71): every edge in the closure of a prism / pyramid gets
+    LAYER | DONT_COLLAPSE | DONT_SPLIT | DONT_SWAP, every prism / pyramid LAYER | OK_QUALITY, so all three marks skip
+    them.  This is one-time set-up done by the caller (in the reference: the Adapt constructor), not part of a
+    sweep; the result is what mag_set_flags receives.  Returns (edge_flags [ne], elem_flags [np+npy+nt])."""
+    edge_v = np.asarray(edge_v, dtype=np.int64)
+    ne = len(edge_v)
+    np_ = 0 if prism_v is None else len(prism_v)
+    npy = 0 if pyr_v is None else len(pyr_v)
+    ef = np.zeros(ne, dtype=np.int32)
+    lf = np.zeros(np_ + npy + nt, dtype=np.int32)
+    lf[:np_ + npy] = _LAYER | _OK_QUALITY
+    pairs = []
+    if np_:
+        pairs += [np.asarray(prism_v, dtype=np.int64)[:, [a, b]] for a, b in _PRISM_EDGES]
+    if npy:
+        pairs += [np.asarray(pyr_v, dtype=np.int64)[:, [a, b]] for a, b in _PYRAMID_EDGES]
+    if pairs:
+        nvmax = int(edge_v.max()) + 1
+        lay = np.sort(np.concatenate(pairs, axis=0), axis=1)
+        lay_key = np.unique(lay[:, 0] * nvmax + lay[:, 1])
+        es = np.sort(edge_v, axis=1)
+        hit = np.isin(es[:, 0] * nvmax + es[:, 1], lay_key)
+        ef[hit] = _LAYER | _DONT_COLLAPSE | _DONT_SPLIT | _DONT_SWAP
+    return ef, lf

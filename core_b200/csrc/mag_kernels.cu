@@ -295,7 +295,7 @@ struct SweepParams {
 
 __device__ __forceinline__ bool near_thr(double v, double thr)
 {
-  return fabs(v - thr) <= MAG_NEAR_REL * fabs(thr);
+  return fabs(thr) <= 1.79e308 && fabs(v - thr) <= MAG_NEAR_REL * fabs(thr);
 }
 
 // shared tail of k_edges and k_fix_edges: flag update + per-thread counters
@@ -750,6 +750,11 @@ static int launch_tets(mag_ctx* c, const SweepParams& P, bool fast)
 int magk_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double good_q, int use_max, int fp_mode)
 {
   SweepParams P{ops, max_len, min_len, good_q, use_max};
+  if (c->kind == MAG_KIND_IDENTITY) {
+    // IdentitySizeField::shouldSplit / shouldCollapse are constant false (maSize.cc:64-72): no length exceeds +inf
+    P.max_len = INFINITY;
+    P.min_len = -INFINITY;
+  }
   const bool fast = fp_mode == MAG_FP_FAST;
   int rc;
   cudaEvent_t* tev = (c->t_used < c->t_slots) ? &c->tev[(size_t)4 * c->t_used] : nullptr;

@@ -146,12 +146,15 @@ def mark_entities(value, cmp, thr, flags, owned, true_flag, set_false_flag, all_
                                    true_flag, set_false_flag, all_false_flags)
 
 
-def mark_edges_to_split(lengths, flags, owned=None):      # maRefine.cc:395-400
-    return mark_entities(lengths, 0, 1.5, flags, owned, SPLIT, NEED_NOT_SPLIT, DONT_SPLIT | NEED_NOT_SPLIT)
+def mark_edges_to_split(lengths, flags, owned=None, kind=None):      # maRefine.cc:395-400
+    # IdentitySizeField::shouldSplit / shouldCollapse are constant false (maSize.cc:64-72)
+    thr = float("inf") if kind == IDENTITY else 1.5
+    return mark_entities(lengths, 0, thr, flags, owned, SPLIT, NEED_NOT_SPLIT, DONT_SPLIT | NEED_NOT_SPLIT)
 
 
-def mark_edges_to_collapse(lengths, flags, owned=None):   # maCoarsen.cc:287-292
-    return mark_entities(lengths, 1, 0.5, flags, owned, COLLAPSE, NEED_NOT_COLLAPSE,
+def mark_edges_to_collapse(lengths, flags, owned=None, kind=None):   # maCoarsen.cc:287-292
+    thr = float("-inf") if kind == IDENTITY else 0.5
+    return mark_entities(lengths, 1, thr, flags, owned, COLLAPSE, NEED_NOT_COLLAPSE,
                          DONT_COLLAPSE | NEED_NOT_COLLAPSE)
 
 

@@ -1,0 +1,357 @@
+"""Parity of the CUDA path (through the C ABI, core_b200.Part) with the restated oracle and with the golden vectors
+the compiled reference produced.  Bar (BASELINE.json north_star): flags and counts bit-exact; lengths and qualities
+bit-exact in MAG_FP_STRICT (LogAniso: CUDA exp() vs glibc exp() -> 1e-12 relative) and within 1e-12 relative in
+MAG_FP_FAST; every entity whose value lies within 1e-12 relative of a threshold is listed."""
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def cb(built):
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    import core_b200
+    return core_b200
+
+
+def check_against(cb, p, want, kind, mode, nns=0, exact_values=None):
+    from oracle import mao
+    st = p.stats()
+    L, q = p.edge_lengths(), p.qualities()
+    ef, lf = p.flags()
+    if exact_values is None:
+        exact_values = (mode == cb.FP_STRICT and kind != mao.LOGM)
+    if exact_values:
+        assert np.array_equal(L, want["lengths"]), "lengths not bit-exact (max rel %.3g)" % util.rel_err(L, want["lengths"])
+        assert np.array_equal(q, want["qualities"]), "qualities not bit-exact"
+        assert st["min_quality"] == want["min_quality"] and st["max_length"] == want["max_length"]
+    else:
+        assert util.rel_err(L, want["lengths"]) < TOL
+        assert util.rel_err(q[nns:], want["qualities"][nns:]) < TOL
+        assert abs(st["min_quality"] - want["min_quality"]) <= TOL * abs(want["min_quality"])
+        assert abs(st["max_length"] - want["max_length"]) <= TOL * want["max_length"]
+    near_e, n_e = p.near_threshold(0)
+    near_l, n_l = p.near_threshold(1)
+    assert st["n_near_threshold"] == n_e + n_l
+    # flags: identical everywhere except (LogAniso only) on listed near-threshold entities
+    de = np.nonzero(ef != want["edge_flags"])[0]
+    dl = np.nonzero(lf != want["elem_flags"])[0]
+    if kind == mao.LOGM:
+        assert set(de.tolist()) <= set(near_e.tolist()) and set(dl.tolist()) <= set(near_l.tolist())
+    else:
+        assert len(de) == 0 and len(dl) == 0, "flags differ on %d edges / %d elements" % (len(de), len(dl))
+        assert (st["n_split"], st["n_collapse"], st["n_bad"]) == (want["n_split"], want["n_collapse"], want["n_bad"])
+    return st
+
+
+@pytest.mark.parametrize("mode", ["strict", "fast"])
+@pytest.mark.parametrize("name", util.golden_cases())
+def test_golden_reference_vectors(cb, name, mode):
+    """CUDA path vs the compiled reference's own outputs (tests/golden)."""
+    from oracle import mao
+    g = util.load(name)
+    mode = cb.FP_STRICT if mode == "strict" else cb.FP_FAST
+    kind, ma, mb = util.metric_arrays(g)
+    prism_v, pyr_v, tet_v = util.split_elements(g)
+    nns = len(prism_v) + len(pyr_v)
+    ef_in, lf_in = g["edge_flags_in"].copy(), g["elem_flags_in"].copy()
+    if nns:
+        ef_in |= g["edge_flags_ctor"]
+        lf_in |= g["elem_flags_ctor"]
+    gq = float(g["good_quality"])
+    gq = 0.027 if gq < 0 else gq
+    p = cb.Part(0)
+    p.set_mesh(g["xyz"], g["edge_v"], tet_v, prism_v if len(prism_v) else None, pyr_v if len(pyr_v) else None)
+    if kind == mao.LOGM:
+        lm = p.set_size_field_logm_from_frames(g["h"], g["R"], util.logm_variant(g), want_logm=True)
+        assert np.array_equal(lm, g["logM"]), "host-built logM field differs from the reference's ma_logM"
+    else:
+        util.set_part_metric(p, kind, ma, mb)
+    p.set_flags(ef_in, lf_in)
+    p.sweep(cb.OP_ALL, good_quality=gq, fp_mode=mode)
+    q_want = np.concatenate([np.zeros(nns), g["qualities"]]) if "qualities" in g else None
+    want = dict(lengths=g["lengths"], qualities=q_want, edge_flags=g["edge_flags_out"], elem_flags=g["elem_flags_out"],
+                n_split=int(g["counts"][0]), n_collapse=int(g["counts"][1]), n_bad=int(g["counts"][2]),
+                min_quality=float(g["min_q"]), max_length=float(g["max_len"]))
+    if q_want is None:   # mixed mesh: the reference cannot run getLinearQualities on it; use the pinned oracle for tets
+        q = mao.tet_qualities(kind, g["xyz"], ma, mb, tet_v)
+        want["qualities"] = np.concatenate([np.zeros(nns), q])
+        want["min_quality"] = mao.min_quality(q)
+    check_against(cb, p, want, kind, mode, nns)
+    if nns:
+        ok, codes = p.layer_ok()
+        assert np.array_equal(ok, g["layer_ok"][:nns]) and np.array_equal(codes, g["layer_codes"][:nns])
+    # centroid metric (useMax = false, maQuality.cc:148-153)
+    if "qualities_centroid" in g:
+        p.set_flags(None, None)
+        p.sweep(cb.OP_QUALITIES, use_max=False, fp_mode=mode)
+        q = p.qualities()
+        if mode == cb.FP_STRICT and kind != mao.LOGM:
+            assert np.array_equal(q, g["qualities_centroid"])
+        else:
+            assert util.rel_err(q, g["qualities_centroid"]) < TOL
+    p.close()
+
+
+def test_unsafe_prisms(cb):
+    g = util.load("mixed5_unsafe_layer")
+    prism_v, _, tet_v = util.split_elements(g)
+    p = cb.Part(0)
+    p.set_mesh(g["xyz"], g["edge_v"], tet_v, prism_v)
+    p.set_size_field_identity()
+    p.sweep(cb.OP_LAYER_CHECK)
+    ok, codes = p.layer_ok()
+    assert np.array_equal(ok, g["layer_ok"][:len(prism_v)]) and np.array_equal(codes, g["layer_codes"][:len(prism_v)])
+    assert p.stats()["n_layer_unsafe"] == 8
+    p.close()
+
+
+@pytest.mark.parametrize("kindname", ["identity", "iso", "aniso", "logm"])
+def test_random_box_vs_oracle(cb, kindname):
+    """Seeded jittered box, random frames / sizes, random incoming flag words and ownership, both fp modes."""
+    from oracle import mao
+    n = 14
+    rng = np.random.default_rng(42)
+    xyz, ev, tv = cb.boxmesh.kuhn_box(n, n + 1, n - 1)
+    xyz = cb.fields.jitter(xyz, 0.3 / n)
+    nv = len(xyz)
+    R = util.random_frames(nv, rng)
+    H = (1.0 / n) * np.exp(rng.uniform(-1.5, 1.5, (nv, 3)))
+    s = (1.0 / n) * np.exp(rng.uniform(-1, 1, nv))
+    kind, ma, mb = {"identity": (mao.IDENTITY, None, None), "iso": (mao.ISO, s, None), "aniso": (mao.ANISO, H, R),
+                    "logm": (mao.LOGM, None, mao.logm_from_frames(H, R, 0))}[kindname]
+    ef = np.zeros(len(ev), np.int32)
+    lf = np.zeros(len(tv), np.int32)
+    ef[rng.random(len(ev)) < 0.2] |= cb.DONT_SPLIT
+    ef[rng.random(len(ev)) < 0.2] |= cb.DONT_COLLAPSE
+    ef[rng.random(len(ev)) < 0.1] |= cb.NEED_NOT_SPLIT
+    ef[rng.random(len(ev)) < 0.1] |= cb.NEED_NOT_COLLAPSE
+    ef[rng.random(len(ev)) < 0.1] |= cb.DONT_SWAP
+    lf[rng.random(len(tv)) < 0.3] |= cb.OK_QUALITY
+    eo = (rng.random(len(ev)) < 0.9).astype(np.uint8)
+    lo = (rng.random(len(tv)) < 0.9).astype(np.uint8)
+    want = util.oracle_sweep(kind, xyz, ma, mb, ev, tv, ef, lf, eo, lo, good_quality=0.1)
+    p = cb.Part(0)
+    p.set_mesh(xyz, ev, tv, edge_owned=eo, elem_owned=lo)
+    util.set_part_metric(p, kind, ma, mb)
+    for mode in (cb.FP_STRICT, cb.FP_FAST):
+        p.set_flags(ef, lf)
+        p.sweep(cb.OP_ALL & ~cb.OP_LAYER_CHECK, good_quality=0.1, fp_mode=mode)
+        st = check_against(cb, p, want, kind, mode)
+        assert st["n_edges_evaluated"] == int(np.count_nonzero(
+            ~((ef & (cb.DONT_SPLIT | cb.NEED_NOT_SPLIT)) != 0) | ~((ef & (cb.DONT_COLLAPSE | cb.NEED_NOT_COLLAPSE)) != 0)))
+    p.close()
+
+
+def test_reference_named_entry_points(cb):
+    """The host mirror's reference-named calls (markEdgesToSplit ... getMaximumEdgeLength) one at a time, and the
+    second-sweep behaviour: NEED_NOT_* / OK_QUALITY set by the first sweep make the second one skip (maAdapt.cc:311)."""
+    from oracle import mao
+    n = 8
+    xyz, ev, tv = cb.boxmesh.kuhn_box(n, n, n)
+    h, R = cb.fields.shock_rotating(xyz, 1.0 / n)
+    want = util.oracle_sweep(mao.ANISO, xyz, h, R, ev, tv)
+    p = cb.Part(0)
+    p.set_mesh(xyz, ev, tv)
+    p.set_size_field_aniso(h, R)
+    assert p.markEdgesToSplit() == want["n_split"]
+    assert p.markEdgesToCollapse() == want["n_collapse"]
+    assert p.markBadQuality() == want["n_bad"]
+    ef, lf = p.flags()
+    assert np.array_equal(ef, want["edge_flags"]) and np.array_equal(lf, want["elem_flags"])
+    assert p.getMinQuality() == want["min_quality"]
+    assert p.getMaximumEdgeLength() == want["max_length"]
+    assert np.array_equal(p.getEdgeLengthsInMetricSpace(), want["lengths"])
+    assert np.array_equal(p.getLinearQualitiesInMetricSpace(), np.cbrt(want["qualities"]))
+    # a second markEdgesToSplit on the marked mesh: the reference asserts because SPLIT is still set
+    with pytest.raises(cb.MagError) as ei:
+        p.markEdgesToSplit()
+    assert ei.value.code == 3
+    # clear only the true flags (what ma::refine / unMarkBadQuality do) and re-mark: only un-decided entities are evaluated
+    ef &= ~(cb.SPLIT | cb.COLLAPSE)
+    lf &= ~cb.BAD_QUALITY
+    p.set_flags(ef, lf)
+    p.sweep(cb.OP_MARK_SPLIT | cb.OP_MARK_COLLAPSE | cb.OP_MARK_BAD)
+    st = p.stats()
+    assert (st["n_split"], st["n_collapse"], st["n_bad"]) == (want["n_split"], want["n_collapse"], want["n_bad"])
+    assert st["n_edges_evaluated"] == int(np.count_nonzero(
+        ((want["edge_flags"] & cb.SPLIT) != 0) | ((want["edge_flags"] & cb.COLLAPSE) != 0)))
+    assert st["n_elems_evaluated"] == want["n_bad"]
+    p.close()
+
+
+def test_near_threshold_listing(cb):
+    """An edge whose metric length is exactly the threshold: listed, and marked as the reference's strict
+    comparison decides (1.5 > 1.5 is false) in both modes."""
+    xyz = np.array([[0, 0, 0], [1.5, 0, 0], [0, 0.5, 0], [0, 0, 1.0]], dtype=np.float64)
+    ev = np.array([[0, 1], [0, 2], [0, 3], [1, 2]], dtype=np.int32)
+    tv = np.array([[0, 1, 2, 3]], dtype=np.int32)
+    p = cb.Part(0)
+    p.set_mesh(xyz, ev, tv)
+    p.set_size_field_iso(np.ones(4))
+    for mode in (cb.FP_STRICT, cb.FP_FAST):
+        p.set_flags(None, None)
+        p.sweep(cb.OP_LENGTHS | cb.OP_MARK_SPLIT | cb.OP_MARK_COLLAPSE, fp_mode=mode)
+        idx, n = p.near_threshold(0)
+        assert n == 2 and sorted(idx.tolist()) == [0, 1]
+        ef, _ = p.flags()
+        assert ef[0] == cb.NEED_NOT_SPLIT | cb.NEED_NOT_COLLAPSE      # 1.5: neither > 1.5 nor < 0.5
+        assert ef[1] == cb.NEED_NOT_SPLIT | cb.NEED_NOT_COLLAPSE      # 0.5: not < 0.5
+        assert ef[2] == cb.NEED_NOT_SPLIT | cb.NEED_NOT_COLLAPSE
+        assert ef[3] == cb.SPLIT | cb.NEED_NOT_COLLAPSE               # sqrt(2.5) = 1.58
+        assert np.array_equal(p.edge_lengths()[:3], [1.5, 0.5, 1.0])
+    p.close()
+
+
+def test_edge_cases_and_errors(cb):
+    p = cb.Part(0)
+    # sweep before any size field
+    p.set_mesh(np.zeros((2, 3)), np.array([[0, 1]], np.int32))
+    with pytest.raises(cb.MagError) as ei:
+        p.sweep()
+    assert ei.value.code == 2
+    # empty mesh: every count zero, statistics at their initial values (getMinQuality 1, getMaximumEdgeLength 0)
+    p.set_mesh(np.zeros((0, 3)), np.zeros((0, 2), np.int32), np.zeros((0, 4), np.int32))
+    p.set_size_field_identity()
+    p.sweep()
+    st = p.stats()
+    assert (st["n_split"], st["n_collapse"], st["n_bad"]) == (0, 0, 0)
+    assert st["min_quality"] == 1.0 and st["max_length"] == 0.0
+    assert len(p.edge_lengths()) == 0 and len(p.qualities()) == 0
+    # edges only (a part with no tets), zero-length edge: measure = 0 -> collapse
+    xyz = np.array([[0, 0, 0], [1, 0, 0], [1, 0, 0]], dtype=np.float64)
+    p.set_mesh(xyz, np.array([[0, 1], [1, 2]], np.int32))
+    p.set_size_field_iso(np.full(3, 0.25))
+    p.sweep()
+    st = p.stats()
+    assert (st["n_split"], st["n_collapse"]) == (1, 1)
+    assert np.array_equal(p.edge_lengths(), [4.0, 0.0])
+    # inverted tet: negative quality, BAD_QUALITY, min quality negative
+    xyz = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, -1]], dtype=np.float64)
+    p.set_mesh(xyz, np.array([[0, 1]], np.int32), np.array([[0, 1, 2, 3]], np.int32))
+    p.set_size_field_identity()
+    p.sweep()
+    st = p.stats()
+    assert st["min_quality"] < 0 and st["n_bad"] == 1
+    # a prism that reaches markBadQuality without OK_QUALITY: the reference would call a null table entry
+    xyz = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [0, 1, 1]], dtype=np.float64)
+    p.set_mesh(xyz, np.array([[0, 1]], np.int32), None, np.array([[0, 1, 2, 3, 4, 5]], np.int32))
+    p.set_size_field_identity()
+    p.sweep(cb.OP_MARK_BAD)
+    with pytest.raises(cb.MagError) as ei:
+        p.stats()
+    assert ei.value.code == 5
+    p.set_flags(None, np.array([cb.OK_QUALITY | cb.LAYER], np.int32))
+    p.sweep(cb.OP_MARK_BAD | cb.OP_LAYER_CHECK)
+    assert p.stats()["n_bad"] == 0 and p.layer_ok()[0][0] == 1
+    # bad arguments
+    with pytest.raises(cb.MagError):
+        p.sweep(ops=1 << 9)
+    with pytest.raises(cb.MagError):
+        p.sweep(fp_mode=7)
+    p.close()
+    with pytest.raises(cb.MagError):
+        cb.Part(9999)
+
+
+def test_two_parts_one_gpu_partition_invariance(cb):
+    """Two slab parts (two contexts on one device, no NCCL): shared-edge flags agree copy by copy and the owned counts
+    add up to the serial sweep of the glued box -- the partition invariance the multi-GPU path relies on."""
+    from oracle import mao
+    gnx, ny, nz = 12, 7, 6
+
+    def field(xyz):
+        f = xyz.copy()
+        f[:, 0] /= 2.0
+        return cb.fields.shock_rotating(f, 1.0 / ny)
+    xyz, ev, tv = cb.boxmesh.kuhn_box(gnx, ny, nz, wx=2.0)
+    h, R = field(xyz)
+    want = util.oracle_sweep(mao.ANISO, xyz, h, R, ev, tv)
+    tot = np.zeros(3, np.int64)
+    flags = []
+    parts = [cb.boxmesh.slab_part(gnx, ny, nz, 2, r, wx=2.0) for r in range(2)]
+    mx, mn = 0.0, 1.0
+    for part in parts:
+        p = cb.Part(0)
+        p.set_mesh(part["xyz"], part["edge_v"], part["tet_v"], edge_owned=part["edge_owned"], elem_owned=part["elem_owned"])
+        hh, RR = field(part["xyz"])
+        p.set_size_field_aniso(hh, RR)
+        p.sweep(fp_mode=cb.FP_FAST)
+        st = p.stats()
+        tot += [st["n_split"], st["n_collapse"], st["n_bad"]]
+        mx, mn = max(mx, st["max_length"]), min(mn, st["min_quality"])
+        flags.append(p.flags()[0])
+        p.close()
+    assert tot.tolist() == [want["n_split"], want["n_collapse"], want["n_bad"]]
+    (peer, idx0, _), = parts[0]["links"]
+    (_, idx1, _), = parts[1]["links"]
+    assert np.array_equal(flags[0][idx0], flags[1][idx1])
+    assert abs(mx - want["max_length"]) <= TOL * mx and abs(mn - want["min_quality"]) <= TOL * abs(mn)
+
+
+def test_full_size_properties(cb):
+    """BASELINE config 3 size (n=203: 50.2 M tets, 58.9 M edges).  The oracle cannot sweep this in seconds, so:
+    (1) a seeded random sample of 300k edges and 300k tets is checked against the oracle; (2) fast and strict flags
+    and counts are identical, values within 1e-12; (3) counts equal the number of flagged entities; (4) every entity got
+    exactly one of the true / false flags; (5) reversing the entity order leaves every per-entity result unchanged."""
+    from oracle import mao
+    n = 203
+    xyz, ev, tv = cb.boxmesh.kuhn_box(n, n, n)
+    h, R = cb.fields.shock_rotating(xyz, 1.0 / n)
+    p = cb.Part(0)
+    p.set_mesh(xyz, ev, tv)
+    p.set_size_field_aniso(h, R)
+    res = {}
+    for mode in (cb.FP_STRICT, cb.FP_FAST):
+        p.clear_flags()
+        p.sweep(cb.OP_ALL & ~cb.OP_LAYER_CHECK, fp_mode=mode)
+        st = p.stats()
+        res[mode] = (st, p.edge_lengths(), p.qualities(), *p.flags())
+    (s0, L0, q0, ef0, lf0), (s1, L1, q1, ef1, lf1) = res[cb.FP_STRICT], res[cb.FP_FAST]
+    assert np.array_equal(ef0, ef1) and np.array_equal(lf0, lf1)
+    for k in ("n_split", "n_collapse", "n_bad"):
+        assert s0[k] == s1[k]
+    assert util.rel_err(L1, L0) < TOL and util.rel_err(q1, q0) < TOL
+    assert s0["n_split"] == int(np.count_nonzero(ef0 & cb.SPLIT)) and s0["n_collapse"] == int(np.count_nonzero(ef0 & cb.COLLAPSE))
+    assert s0["n_bad"] == int(np.count_nonzero(lf0 & cb.BAD_QUALITY))
+    assert np.all(((ef0 & cb.SPLIT) != 0) ^ ((ef0 & cb.NEED_NOT_SPLIT) != 0))
+    assert np.all(((ef0 & cb.COLLAPSE) != 0) ^ ((ef0 & cb.NEED_NOT_COLLAPSE) != 0))
+    assert np.all(((lf0 & cb.BAD_QUALITY) != 0) ^ ((lf0 & cb.OK_QUALITY) != 0))
+    assert s0["max_length"] == L0.max() and s0["min_quality"] == min(1.0, q0.min())
+    rng = np.random.default_rng(7)
+    se = rng.choice(len(ev), 300000, replace=False)
+    stt = rng.choice(len(tv), 300000, replace=False)
+    assert np.array_equal(mao.edge_lengths(mao.ANISO, xyz, h, R, ev[se]), L0[se])
+    assert np.array_equal(mao.tet_qualities(mao.ANISO, xyz, h, R, tv[stt]), q0[stt])
+    # entity-order invariance
+    p.set_mesh(xyz, ev[::-1].copy(), tv[::-1].copy())
+    p.set_size_field_aniso(h, R)
+    p.sweep(cb.OP_ALL & ~cb.OP_LAYER_CHECK, fp_mode=cb.FP_FAST)
+    st = p.stats()
+    assert np.array_equal(p.edge_lengths()[::-1], L1) and np.array_equal(p.qualities()[::-1], q1)
+    efr, lfr = p.flags()
+    assert np.array_equal(efr[::-1], ef0) and np.array_equal(lfr[::-1], lf0)
+    assert (st["n_split"], st["n_bad"]) == (s0["n_split"], s0["n_bad"])
+    p.close()
+
+
+def test_nccl_two_gpus(cb):
+    """mag_comm_* over NCCL needs two devices; exercised by bench.py --gpus 2 as well."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(root, "bench.py"),
+                          "--gpus", "2", "--steps", "2", "--warmup", "1", "--n", "40", "--no-cpu", "--e2e-steps", "1"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["n_gpus"] == 2 and line["stats"]["n_flag_mismatch"] == 0

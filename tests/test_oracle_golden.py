@@ -1,0 +1,114 @@
+"""The restated oracle (oracle/ma_oracle.c) against golden vectors produced by the compiled, unmodified
+reference (tests/golden/make_golden.py), bit for bit.  This is what pins the oracle."""
+import numpy as np
+import pytest
+
+from oracle import mao
+import util
+
+
+@pytest.mark.parametrize("name", util.golden_cases())
+def test_oracle_matches_reference_golden(name, built):
+    g = util.load(name)
+    kind, ma, mb = util.metric_arrays(g)
+    prism_v, pyr_v, tet_v = util.split_elements(g)
+    nns = len(prism_v) + len(pyr_v)
+    if kind == mao.LOGM:
+        # the logM vertex field itself is part of the reference's output: rebuild it from sizes + frames
+        lm = mao.logm_from_frames(g["h"], g["R"], util.logm_variant(g))
+        assert np.array_equal(lm, g["logM"]), "logM field differs from the reference's ma_logM"
+    L = mao.edge_lengths(kind, g["xyz"], ma, mb, g["edge_v"])
+    assert np.array_equal(L, g["lengths"]), "edge lengths are not bit-identical to ma::SizeField::measure"
+    q = mao.tet_qualities(kind, g["xyz"], ma, mb, tet_v, True)
+    if "qualities" in g:
+        assert np.array_equal(q, g["qualities"])
+        assert np.array_equal(mao.tet_qualities(kind, g["xyz"], ma, mb, tet_v, False), g["qualities_centroid"])
+        assert np.array_equal(mao.vertex_transforms(kind, ma, mb, len(g["xyz"])), g["vertex_Q"])
+    # marks: start from the reference's incoming words (plus, on mixed meshes, what ma::Adapt's constructor set)
+    ef = g["edge_flags_in"].copy()
+    lf = g["elem_flags_in"].copy()
+    if nns:
+        ef |= g["edge_flags_ctor"]
+        lf |= g["elem_flags_ctor"]
+    gq = float(g["good_quality"])
+    gq = 0.027 if gq < 0 else gq
+    qall = np.concatenate([np.zeros(nns), q])
+    counts = [mao.mark_edges_to_split(L, ef, None, kind), mao.mark_edges_to_collapse(L, ef, None, kind),
+              mao.mark_bad_quality(qall, lf, gq)]
+    assert counts == g["counts"].tolist()
+    assert np.array_equal(ef, g["edge_flags_out"])
+    assert np.array_equal(lf, g["elem_flags_out"])
+    if "qualities" in g:
+        assert mao.min_quality(q) == float(g["min_q"])
+    assert mao.max_length(L) == float(g["max_len"])
+    if nns:
+        ok, codes = mao.prism_ok(g["xyz"], prism_v)
+        assert np.array_equal(ok, g["layer_ok"][:len(prism_v)])
+        assert np.array_equal(codes, g["layer_codes"][:len(prism_v)])
+
+
+def test_layer_closure_flags_golden():
+    """LAYER closure + freezeLayer flags of ma::Adapt's constructor (maLayer.cc:11-71), restated with numpy
+    from the connectivity alone: every edge of a prism gets LAYER|DONT_COLLAPSE|DONT_SPLIT|DONT_SWAP, every prism
+    LAYER|OK_QUALITY."""
+    g = util.load("mixed5_shock_rot_aniso")
+    prism_v, _, tet_v = util.split_elements(g)
+    from core_b200 import boxmesh
+    ef, lf = boxmesh.layer_closure_flags(g["edge_v"], prism_v, None, len(tet_v))
+    assert np.array_equal(ef, g["edge_flags_ctor"])
+    assert np.array_equal(lf, g["elem_flags_ctor"])
+
+
+def test_unsafe_prisms_golden(built):
+    g = util.load("mixed5_unsafe_layer")
+    prism_v, _, _ = util.split_elements(g)
+    ok, codes = mao.prism_ok(g["xyz"], prism_v)
+    assert (ok == 0).sum() == 8
+    assert np.array_equal(ok, g["layer_ok"][:len(prism_v)])
+    assert np.array_equal(codes, g["layer_codes"][:len(prism_v)])
+
+
+def test_eigen_golden_and_reference_kat(built):
+    """mth::eigenQR restated: bit-identical to the compiled reference on 206 matrices, and within the
+    reference test's own tolerance of the Octave eigenpairs listed in test/eigen_test.cc:13-56."""
+    g = dict(np.load(util.GOLDEN + "/eigen.npz"))
+    for A, vals, vecs in zip(g["A"], g["vals"], g["vecs"]):
+        v, E, rc = mao.eigen(A)
+        assert rc == 3 or rc == 1
+        assert np.array_equal(v, vals) and np.array_equal(E, vecs)
+    octave_l = np.array([[2.214902e-02, 9.112746e-01, 8.145053e+00], [4.661900e-01, 1.298152e+00, 2.055468e+00],
+                         [2.321140e-02, 5.742601e-01, 3.021677e+00], [7.303538e-02, 2.154649e+00, 7.177734e+00],
+                         [2.627564e-02, 2.587634e+00, 7.214654e+00], [9.493002e-01, 2.404829e+00, 1.008340e+01]])
+    for A, l in zip(g["A"][:6], octave_l):
+        v, E, _ = mao.eigen(A)
+        o = np.argsort(v)
+        assert np.sum((v[o] - l) ** 2) < 1e-10          # eigen_test.cc:144
+        for j in o:                                      # A e = lambda e
+            assert np.allclose(A @ E[j], v[j] * E[j], atol=1e-9)
+
+
+def test_det_kat(built):
+    """test/ma_insphere.cc:13-29: exact integer determinants of the 3x3 minors of the test's 4x4 matrix."""
+    M = np.array([[2, 5, 3, 5], [14, 9, 6, 7], [4, 9, 3, 2], [3, 7, 8, 6]], dtype=np.float64)
+    for row, want in ((0, 135.0), (1, 145.0), (2, 35.0), (3, -45.0)):
+        minor = np.ascontiguousarray(np.delete(np.delete(M, row, axis=0), 0, axis=1))
+        assert mao.det3(minor) == want
+
+
+def test_survey_smoke_values(built):
+    """n=20 unit box, iso field h = hbar (1 + 2x): nSplit 800, nCollapse 15710, nBad 0,
+    minQ 0.43199999999999933, max length 1.6508199830081591 (measured on the compiled reference)."""
+    import core_b200 as cb
+    n = 20
+    xyz, ev, tv = cb.boxmesh.kuhn_box(n, n, n)
+    s = cb.fields.iso_linear(xyz, 1.0 / n)
+    r = util.oracle_sweep(mao.ISO, xyz, s, None, ev, tv)
+    assert (r["n_split"], r["n_collapse"], r["n_bad"]) == (800, 15710, 0)
+    assert r["min_quality"] == 0.43199999999999933
+    assert r["max_length"] == 1.6508199830081591
+    assert np.cumsum(r["lengths"])[-1] / len(ev) == 0.70227441816624803   # serial sum, as the survey probe did
+    h, R = cb.fields.shock_planar(xyz, 1.0 / n)
+    r = util.oracle_sweep(mao.ANISO, xyz, h, R, ev, tv)
+    assert (r["n_split"], r["n_collapse"], r["n_bad"]) == (26732, 0, 9600)
+    assert r["min_quality"] == 0.00064551397077518649
+    assert r["max_length"] == 7.0712523453038738
