@@ -114,7 +114,7 @@ int mag_create(mag_ctx** out, int device)
   c->d_len = c->d_qual = nullptr;
   c->d_layer_ok = c->d_layer_codes = nullptr;
   c->d_stats = nullptr; c->h_stats = nullptr;
-  c->d_block_sums = nullptr; c->n_block_sums = 0;
+  c->d_block_sums = nullptr; c->n_sms = 148;
   c->d_near_edge = c->d_near_elem = nullptr;
   c->cap_vedge = c->cap_ma = c->cap_mb = 0;
   c->last_ops = 0; c->last_fp_mode = 0;
@@ -130,8 +130,8 @@ int mag_create(mag_ctx** out, int device)
   c->stream = c->own_stream;
   if ((e = cudaMalloc((void**)&c->d_stats, sizeof(MagDevStats))) != cudaSuccess) return fail(e, "cudaMalloc stats");
   if ((e = cudaMallocHost((void**)&c->h_stats, sizeof(MagDevStats))) != cudaSuccess) return fail(e, "cudaMallocHost stats");
-  if ((e = cudaMalloc((void**)&c->d_near_edge, sizeof(int64_t) * MAG_NEAR_CAP)) != cudaSuccess) return fail(e, "cudaMalloc near list");
-  if ((e = cudaMalloc((void**)&c->d_near_elem, sizeof(int64_t) * MAG_NEAR_CAP)) != cudaSuccess) return fail(e, "cudaMalloc near list");
+  if ((e = cudaMalloc((void**)&c->d_block_sums, sizeof(double) * MAG_SUM_BLOCKS)) != cudaSuccess) return fail(e, "cudaMalloc block sums");
+  if ((e = cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return fail(e, "SM count");
   int rc = magk_init_stats(c);
   if (rc) { g_create_err = c->err; delete c; return rc; }
   *out = c;
@@ -176,7 +176,8 @@ int mag_set_mesh(mag_ctx* c, int64_t nv, const double* xyz, int64_t ne, const in
 {
   CHECK_CTX(c);
   if (nv < 0 || ne < 0 || nt < 0 || np < 0 || npy < 0) return mag_fail(c, MAG_ERR_ARG, "mag_set_mesh: negative count");
-  if (nv > 0x7fffffffLL) return mag_fail(c, MAG_ERR_ARG, "mag_set_mesh: vertex ids are int32 (MDS_ID_TYPE=int)");
+  if (nv > 0x7fffffffLL || ne > 0x7fffffffLL || np + npy + nt > 0x7fffffffLL)
+    return mag_fail(c, MAG_ERR_ARG, "mag_set_mesh: entity ids are int32 (MDS_ID_TYPE=int, mds/CMakeLists.txt:7)");
   if ((nv && !xyz) || (ne && !edge_v) || (nt && !tet_v) || (np && !prism_v) || (npy && !pyr_v))
     return mag_fail(c, MAG_ERR_ARG, "mag_set_mesh: null array with non-zero count");
   int rc;
@@ -198,15 +199,15 @@ int mag_set_mesh(mag_ctx* c, int64_t nv, const double* xyz, int64_t ne, const in
         (rc = dev_alloc(c, c->d_elem_owned, elem_owned ? (size_t)nel : 0)) ||
         (rc = dev_alloc(c, c->d_edge_flags, (size_t)ne)) || (rc = dev_alloc(c, c->d_elem_flags, (size_t)nel)) ||
         (rc = dev_alloc(c, c->d_len, (size_t)ne)) || (rc = dev_alloc(c, c->d_qual, (size_t)nel)) ||
-        (rc = dev_alloc(c, c->d_layer_ok, (size_t)(np + npy))) || (rc = dev_alloc(c, c->d_layer_codes, (size_t)(np + npy))))
+        (rc = dev_alloc(c, c->d_layer_ok, (size_t)(np + npy))) || (rc = dev_alloc(c, c->d_layer_codes, (size_t)(np + npy))) ||
+        (rc = dev_alloc(c, c->d_near_edge, (size_t)ne)) || (rc = dev_alloc(c, c->d_near_elem, (size_t)nel)))
       return rc;
-    c->n_block_sums = (ne + 255) / 256;
-    if ((rc = dev_alloc(c, c->d_block_sums, (size_t)c->n_block_sums))) return rc;
     c->nv = nv; c->ne = ne; c->nt = nt; c->np = np; c->npy = npy;
-    if (ne) MAG_CUDA(c, cudaMemsetAsync(c->d_edge_flags, 0, (size_t)ne * 4, c->stream));
-    if (nel) MAG_CUDA(c, cudaMemsetAsync(c->d_elem_flags, 0, (size_t)nel * 4, c->stream));
     if (nel) MAG_CUDA(c, cudaMemsetAsync(c->d_qual, 0, (size_t)nel * 8, c->stream));
   }
+  // a new mesh starts with no flags (ma::getFlags returns 0 when the tag is absent, maAdapt.cc:80-88)
+  if (ne) MAG_CUDA(c, cudaMemsetAsync(c->d_edge_flags, 0, (size_t)ne * 4, c->stream));
+  if (nel) MAG_CUDA(c, cudaMemsetAsync(c->d_elem_flags, 0, (size_t)nel * 4, c->stream));
   if ((rc = upload(c, c->d_xyz, xyz, (size_t)nv * 3)) || (rc = upload(c, c->d_edge_v, edge_v, (size_t)ne * 2)) ||
       (rc = upload(c, c->d_tet_v, tet_v, (size_t)nt * 4)) || (rc = upload(c, c->d_prism_v, prism_v, (size_t)np * 6)) ||
       (rc = upload(c, c->d_pyr_v, pyr_v, (size_t)npy * 5)))
@@ -264,7 +265,8 @@ int mag_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double g
   CHECK_CTX(c);
   if (c->kind == MAG_KIND_NONE) return mag_fail(c, MAG_ERR_ARG, "mag_sweep: no size field set");
   if (fp_mode != MAG_FP_STRICT && fp_mode != MAG_FP_FAST) return mag_fail(c, MAG_ERR_ARG, "mag_sweep: bad fp_mode %d", fp_mode);
-  if (ops & ~(uint32_t)MAG_OP_ALL) return mag_fail(c, MAG_ERR_ARG, "mag_sweep: unknown op bits 0x%x", ops);
+  if (ops & ~(uint32_t)(MAG_OP_ALL | MAG_OP_LENGTH_SUM)) return mag_fail(c, MAG_ERR_ARG, "mag_sweep: unknown op bits 0x%x", ops);
+  if ((ops & MAG_OP_LENGTH_SUM) && !(ops & MAG_OP_LENGTHS)) return mag_fail(c, MAG_ERR_ARG, "mag_sweep: MAG_OP_LENGTH_SUM needs MAG_OP_LENGTHS");
   int rc;
   if ((rc = magk_init_stats(c))) return rc;
   c->last_ops = ops;
@@ -406,10 +408,12 @@ int mag_get_near_threshold(mag_ctx* c, int which, int64_t* idx, int64_t cap, int
   int64_t total = (int64_t)(which ? c->h_stats->n_near_elem : c->h_stats->n_near_edge);
   *n = total;
   int64_t m = total < cap ? total : cap;
-  if (m > MAG_NEAR_CAP) m = MAG_NEAR_CAP;
   if (idx && m > 0) {
-    MAG_CUDA(c, cudaMemcpyAsync(idx, which ? c->d_near_elem : c->d_near_edge, (size_t)m * 8, cudaMemcpyDeviceToHost, c->stream));
+    // the device list is int32 (MDS ids are int); widen on the host
+    std::vector<int32_t> tmp((size_t)m);
+    MAG_CUDA(c, cudaMemcpyAsync(tmp.data(), which ? c->d_near_elem : c->d_near_edge, (size_t)m * 4, cudaMemcpyDeviceToHost, c->stream));
     MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int64_t i = 0; i < m; ++i) idx[i] = tmp[(size_t)i];
   }
   return MAG_OK;
 }

@@ -21,7 +21,7 @@ struct MagDevStats {
   double sum_len;
 };
 
-#define MAG_NEAR_CAP (1 << 20)
+#define MAG_SUM_BLOCKS 1184 /* 8 x 148: fixed shape of the length-sum tree */
 #define MAG_NEAR_REL 1e-12
 // transient bit (never visible to the caller): entity awaits strict re-evaluation
 #define MAG_PENDING_BIT (1 << 30)
@@ -66,10 +66,10 @@ struct mag_ctx {
   int32_t* d_layer_codes;
   MagDevStats* d_stats;
   MagDevStats* h_stats;  // pinned
-  double* d_block_sums;  // per-block partial sums of owned edge lengths
-  int64_t n_block_sums;
-  int64_t* d_near_edge;  // [MAG_NEAR_CAP]
-  int64_t* d_near_elem;
+  double* d_block_sums;  // [MAG_SUM_BLOCKS] partial sums of owned edge lengths (MAG_OP_LENGTH_SUM)
+  int32_t* d_near_edge;  // [ne]  near-threshold edge indices of the last sweep (an entity is listed at most once)
+  int32_t* d_near_elem;  // [np+npy+nt]
+  int n_sms;
   size_t cap_vedge, cap_ma, cap_mb;
 
   // last sweep parameters (for the near-threshold fix-up and getters)

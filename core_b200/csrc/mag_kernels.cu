@@ -31,99 +31,33 @@ __host__ __device__ inline unsigned long long dkey(double d)
 }
 
 // ------------------------------------------------------------------ reductions
-__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v)
+// The edge / tet kernels are persistent (grid-stride over tiles): every thread carries its counters in registers
+// for the whole launch and the block reduces ONCE at the end -- warp REDUX, then one atomic per warp and counter.
+__device__ __forceinline__ void warp_count_to(unsigned c, unsigned long long* g)
 {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-  return v;
+  unsigned v = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(g, (unsigned long long)v);
+}
+// 64-bit max / min through two 32-bit REDUX steps (high word first)
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
+{
+  unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+  unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+  return ((unsigned long long)mh << 32) | ml;
+}
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
+{
+  unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+  unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+  unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+  return ((unsigned long long)mh << 32) | ml;
 }
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
   return v;
-}
-__device__ __forceinline__ unsigned long long warp_max(unsigned long long v)
-{
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { unsigned long long w = __shfl_down_sync(0xffffffffu, v, o); v = w > v ? w : v; }
-  return v;
-}
-__device__ __forceinline__ unsigned long long warp_min(unsigned long long v)
-{
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { unsigned long long w = __shfl_down_sync(0xffffffffu, v, o); v = w < v ? w : v; }
-  return v;
-}
-
-// packs up to 4 small counters into one u64 (16 bits each, a block has <= 1024 threads)
-__device__ __forceinline__ void block_count4(unsigned c0, unsigned c1, unsigned c2, unsigned c3,
-                                             unsigned long long* g0, unsigned long long* g1,
-                                             unsigned long long* g2, unsigned long long* g3)
-{
-  __shared__ unsigned long long sh[kThreads / 32];
-  unsigned long long p = (unsigned long long)c0 | ((unsigned long long)c1 << 16) |
-                         ((unsigned long long)c2 << 32) | ((unsigned long long)c3 << 48);
-  p = warp_sum(p);
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (lane == 0) sh[w] = p;
-  __syncthreads();
-  if (w == 0) {
-    p = lane < (kThreads / 32) ? sh[lane] : 0ull;
-    p = warp_sum(p);
-    if (lane == 0) {
-      unsigned a = (unsigned)(p & 0xffff), b = (unsigned)((p >> 16) & 0xffff);
-      unsigned cc = (unsigned)((p >> 32) & 0xffff), d = (unsigned)((p >> 48) & 0xffff);
-      if (a) atomicAdd(g0, (unsigned long long)a);
-      if (b) atomicAdd(g1, (unsigned long long)b);
-      if (cc) atomicAdd(g2, (unsigned long long)cc);
-      if (d) atomicAdd(g3, (unsigned long long)d);
-    }
-  }
-  __syncthreads();
-}
-__device__ __forceinline__ void block_max_u64(unsigned long long v, unsigned long long* g)
-{
-  __shared__ unsigned long long sh[kThreads / 32];
-  v = warp_max(v);
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (lane == 0) sh[w] = v;
-  __syncthreads();
-  if (w == 0) {
-    v = lane < (kThreads / 32) ? sh[lane] : 0ull;
-    v = warp_max(v);
-    if (lane == 0 && v) atomicMax(g, v);
-  }
-  __syncthreads();
-}
-__device__ __forceinline__ void block_min_u64(unsigned long long v, unsigned long long* g)
-{
-  __shared__ unsigned long long sh[kThreads / 32];
-  v = warp_min(v);
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (lane == 0) sh[w] = v;
-  __syncthreads();
-  if (w == 0) {
-    v = lane < (kThreads / 32) ? sh[lane] : ~0ull;
-    v = warp_min(v);
-    if (lane == 0 && v != ~0ull) atomicMin(g, v);
-  }
-  __syncthreads();
-}
-// deterministic per-block partial sum -> d_block_sums[blockIdx.x]
-__device__ __forceinline__ void block_sum_f64(double v, double* out)
-{
-  __shared__ double sh[kThreads / 32];
-  v = warp_sum(v);
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (lane == 0) sh[w] = v;
-  __syncthreads();
-  if (w == 0) {
-    v = lane < (kThreads / 32) ? sh[lane] : 0.0;
-    v = warp_sum(v);
-    if (lane == 0) *out = v;
-  }
-  __syncthreads();
 }
 
 // ------------------------------------------------------------------ record loads
@@ -312,86 +246,145 @@ __device__ __forceinline__ void mark_edge(double len, int32_t& f, bool need_spli
   }
 }
 
-template <int KIND, bool FAST>
-__global__ void __launch_bounds__(kThreads)
-k_edges(int64_t ne, const int2* __restrict__ edge_v, const double* __restrict__ vedge,
-        const uint8_t* __restrict__ owned_arr, int32_t* __restrict__ flags, double* __restrict__ lengths,
-        SweepParams P, MagDevStats* st, double* __restrict__ block_sums, int64_t* __restrict__ near_list)
+// Near-threshold work queue (one per warp, in shared memory).  An entity whose value lands within 1e-12
+// relative of a threshold is pushed here instead of being decided on the spot; whenever a warp has 32 of them it
+// drains the queue with all lanes active: the entity is appended to the global near-threshold list and, in
+// MAG_FP_FAST, re-evaluated in strict arithmetic so the flag is the reference's.  Deferring keeps the strict code
+// out of the divergent path of the main loop (structured meshes put whole families of edges exactly ON a threshold).
+constexpr int kWarps = kThreads / 32;
+constexpr int kQCap = 64;
+struct NearQueue { int32_t e[kWarps][kQCap]; int32_t f[kWarps][kQCap]; };
+
+// push: warp-collective.  qn is warp-uniform.  returns true when >= 32 entries wait
+__device__ __forceinline__ bool queue_push(NearQueue& q, int& qn, bool nr, int32_t e, int32_t f)
 {
-  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  unsigned c_split = 0, c_coll = 0, c_eval = 0, c_err = 0;
-  unsigned long long maxbits = 0;
-  double sum = 0;
-  if (e < ne) {
-    int32_t f = flags[e];
-    const int32_t f_in = f;
-    const bool do_split = P.ops & MAG_OP_MARK_SPLIT, do_coll = P.ops & MAG_OP_MARK_COLLAPSE;
-    // markEntities asserts the true flag is clear on every entity it visits (maAdapt.cc:308)
-    if ((do_split && (f & MAG_SPLIT)) || (do_coll && (f & MAG_COLLAPSE))) ++c_err;
-    const bool need_split = do_split && !(f & (MAG_DONT_SPLIT | MAG_NEED_NOT_SPLIT));
-    const bool need_coll = do_coll && !(f & (MAG_DONT_COLLAPSE | MAG_NEED_NOT_COLLAPSE));
-    const bool want_len = P.ops & MAG_OP_LENGTHS;
-    if (want_len || need_split || need_coll) {
-      int2 ev = __ldg(edge_v + e);
+  const unsigned m = __ballot_sync(0xffffffffu, nr);
+  if (!m) return false;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (nr) {
+    const int pos = qn + __popc(m & ((1u << lane) - 1u));
+    q.e[w][pos] = e;
+    q.f[w][pos] = f;
+  }
+  qn += __popc(m);
+  __syncwarp();
+  return qn >= 32;
+}
+// reserve n slots of the global near list (warp-aggregated: one atomic per drain)
+__device__ __forceinline__ unsigned long long near_reserve(unsigned long long* counter, int n)
+{
+  unsigned long long base = 0;
+  if ((threadIdx.x & 31) == 0) base = atomicAdd(counter, (unsigned long long)n);
+  return __shfl_sync(0xffffffffu, base, 0);
+}
+
+struct EdgeAcc { unsigned c_split, c_coll, c_eval, c_err; unsigned long long maxbits; };
+
+// drain n (<= 32) queued edges: entry i is handled by lane i
+template <int KIND, bool FAST>
+__device__ __noinline__ void drain_edges(NearQueue& q, int first, int n, const int2* __restrict__ edge_v,
+                                            const double* __restrict__ vedge, const uint8_t* __restrict__ owned_arr,
+                                            int32_t* __restrict__ flags, double* __restrict__ lengths, const SweepParams& P,
+                                            MagDevStats* st, int32_t* __restrict__ near_list, EdgeAcc& A)
+{
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned long long base = near_reserve(&st->n_near_edge, n);
+  if (lane < n) {
+    const int32_t e = q.e[w][first + lane];
+    near_list[base + lane] = e;
+    if (FAST) {
+      int32_t f = q.f[w][first + lane];
+      const bool need_split = (P.ops & MAG_OP_MARK_SPLIT) && !(f & (MAG_DONT_SPLIT | MAG_NEED_NOT_SPLIT));
+      const bool need_coll = (P.ops & MAG_OP_MARK_COLLAPSE) && !(f & (MAG_DONT_COLLAPSE | MAG_NEED_NOT_COLLAPSE));
+      const int2 ev = __ldg(edge_v + e);
       int eig = 0;
-      double len = FAST ? edge_length_fast<KIND>(vedge, ev.x, ev.y, &eig)
-                        : edge_length_strict<KIND>(vedge, ev.x, ev.y, &eig);
-      if (eig) atomicAdd(&st->n_eigen_fail, 1ull);
+      const double len = edge_length_strict<KIND>(vedge, ev.x, ev.y, &eig);
       const bool owned = owned_arr ? (owned_arr[e] != 0) : true;
-      if (want_len) {
-        lengths[e] = len;
-        if (owned) { maxbits = (unsigned long long)__double_as_longlong(len > 0 ? len : 0.0); sum = len; }
-      }
-      bool nr = (need_split && near_thr(len, P.max_len)) || (need_coll && near_thr(len, P.min_len));
-      if (nr) {
-        unsigned long long k = atomicAdd(&st->n_near_edge, 1ull);
-        if (k < MAG_NEAR_CAP) near_list[k] = e;
-      }
-      if (FAST && nr) {
-        flags[e] = f | MAG_PENDING_BIT; // k_fix_edges re-evaluates it in strict arithmetic
-      } else if (need_split || need_coll) {
-        ++c_eval;
-        mark_edge(len, f, need_split, need_coll, owned, P, c_split, c_coll);
-        if (f != f_in) flags[e] = f;
-      }
+      ++A.c_eval;
+      mark_edge(len, f, need_split, need_coll, owned, P, A.c_split, A.c_coll);
+      flags[e] = f;
+      if (P.ops & MAG_OP_LENGTHS) lengths[e] = len;
     }
   }
-  block_count4(c_split, c_coll, c_eval, c_err, &st->n_split, &st->n_collapse, &st->n_edges_eval, &st->n_flag_err);
-  if (P.ops & MAG_OP_LENGTHS) {
-    block_max_u64(maxbits, &st->max_len_bits);
-    block_sum_f64(sum, block_sums + blockIdx.x);
+  __syncwarp();
+}
+
+template <int KIND, bool FAST>
+__global__ void __launch_bounds__(kThreads, FAST ? 3 : 2)
+k_edges(int64_t ne, const int2* __restrict__ edge_v, const double* __restrict__ vedge,
+        const uint8_t* __restrict__ owned_arr, int32_t* __restrict__ flags, double* __restrict__ lengths,
+        SweepParams P, MagDevStats* st, int32_t* __restrict__ near_list)
+{
+  __shared__ NearQueue q;
+  EdgeAcc A{0, 0, 0, 0, 0ull};
+  int qn = 0, eig_any = 0;
+  const bool do_split = P.ops & MAG_OP_MARK_SPLIT, do_coll = P.ops & MAG_OP_MARK_COLLAPSE;
+  const bool want_len = P.ops & MAG_OP_LENGTHS;
+  const int64_t ntiles = (ne + kThreads - 1) / kThreads;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t e = tile * kThreads + threadIdx.x;
+    bool nr = false;
+    int32_t f_in = 0;
+    if (e < ne) {
+      int32_t f = f_in = flags[e];
+      // markEntities asserts the true flag is clear on every entity it visits (maAdapt.cc:308)
+      if ((do_split && (f & MAG_SPLIT)) || (do_coll && (f & MAG_COLLAPSE))) ++A.c_err;
+      const bool need_split = do_split && !(f & (MAG_DONT_SPLIT | MAG_NEED_NOT_SPLIT));
+      const bool need_coll = do_coll && !(f & (MAG_DONT_COLLAPSE | MAG_NEED_NOT_COLLAPSE));
+      if (want_len || need_split || need_coll) {
+        const int2 ev = __ldg(edge_v + e);
+        const double len = FAST ? edge_length_fast<KIND>(vedge, ev.x, ev.y, &eig_any)
+                                : edge_length_strict<KIND>(vedge, ev.x, ev.y, &eig_any);
+        const bool owned = owned_arr ? (owned_arr[e] != 0) : true;
+        if (want_len) {
+          lengths[e] = len;
+          if (owned && len > 0) {
+            const unsigned long long b = (unsigned long long)__double_as_longlong(len);
+            A.maxbits = b > A.maxbits ? b : A.maxbits;
+          }
+        }
+        nr = (need_split && near_thr(len, P.max_len)) || (need_coll && near_thr(len, P.min_len));
+        if ((need_split || need_coll) && !(FAST && nr)) {
+          ++A.c_eval;
+          mark_edge(len, f, need_split, need_coll, owned, P, A.c_split, A.c_coll);
+          if (f != f_in) flags[e] = f;
+        }
+      }
+    }
+    if (queue_push(q, qn, nr, (int32_t)e, f_in)) {
+      qn -= 32;
+      drain_edges<KIND, FAST>(q, qn, 32, edge_v, vedge, owned_arr, flags, lengths, P, st, near_list, A);
+    }
+  }
+  if (qn) drain_edges<KIND, FAST>(q, 0, qn, edge_v, vedge, owned_arr, flags, lengths, P, st, near_list, A);
+  if (eig_any) atomicAdd(&st->n_eigen_fail, 1ull);
+  warp_count_to(A.c_split, &st->n_split);
+  warp_count_to(A.c_coll, &st->n_collapse);
+  warp_count_to(A.c_eval, &st->n_edges_eval);
+  warp_count_to(A.c_err, &st->n_flag_err);
+  if (want_len) {
+    const unsigned long long m = warp_max_u64(A.maxbits);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(&st->max_len_bits, m);
   }
 }
 
-// strict re-evaluation of the edges a FAST sweep found within 1e-12 of a threshold
-// (walks the recorded list, or -- if more than MAG_NEAR_CAP entities were near -- every entity
-// carrying the pending bit)
-template <int KIND>
+// ma::getAverageEdgeLength-style sum of the stored lengths over owned edges (MAG_OP_LENGTH_SUM): a fixed-shape
+// two-level tree (per-thread strided partial -> warp -> block -> k_finish_sum), deterministic for a given ne
 __global__ void __launch_bounds__(kThreads)
-k_fix_edges(int64_t ne, const int2* __restrict__ edge_v, const double* __restrict__ vedge, const uint8_t* __restrict__ owned_arr,
-            int32_t* __restrict__ flags, SweepParams P, MagDevStats* st, const int64_t* __restrict__ near_list)
+k_sum_lengths(int64_t ne, const double* __restrict__ lengths, const uint8_t* __restrict__ owned_arr, double* __restrict__ block_sums)
 {
-  const unsigned long long nn = st->n_near_edge;
-  const bool listed = nn <= MAG_NEAR_CAP;
-  const unsigned long long n = listed ? nn : (unsigned long long)ne;
-  unsigned c_split = 0, c_coll = 0, c_eval = 0;
-  for (unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; k < n;
-       k += (unsigned long long)gridDim.x * blockDim.x) {
-    int64_t e = listed ? near_list[k] : (int64_t)k;
-    int32_t f = flags[e];
-    if (!(f & MAG_PENDING_BIT)) continue;
-    f &= ~MAG_PENDING_BIT;
-    const bool need_split = (P.ops & MAG_OP_MARK_SPLIT) && !(f & (MAG_DONT_SPLIT | MAG_NEED_NOT_SPLIT));
-    const bool need_coll = (P.ops & MAG_OP_MARK_COLLAPSE) && !(f & (MAG_DONT_COLLAPSE | MAG_NEED_NOT_COLLAPSE));
-    int2 ev = __ldg(edge_v + e);
-    int eig = 0;
-    double len = edge_length_strict<KIND>(vedge, ev.x, ev.y, &eig);
-    const bool owned = owned_arr ? (owned_arr[e] != 0) : true;
-    ++c_eval;
-    mark_edge(len, f, need_split, need_coll, owned, P, c_split, c_coll);
-    flags[e] = f;
+  __shared__ double sh[kWarps];
+  double s = 0;
+  for (int64_t e = blockIdx.x * (int64_t)kThreads + threadIdx.x; e < ne; e += (int64_t)gridDim.x * kThreads)
+    if (!owned_arr || owned_arr[e]) s += lengths[e];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < kWarps; ++i) t += sh[i];
+    block_sums[blockIdx.x] = t;
   }
-  block_count4(c_split, c_coll, c_eval, 0, &st->n_split, &st->n_collapse, &st->n_edges_eval, &st->n_flag_err);
 }
 
 // ------------------------------------------------------------------ tets
@@ -476,74 +469,88 @@ __device__ __forceinline__ void mark_tet(double q, int32_t& f, bool owned, const
   else f |= MAG_OK_QUALITY;
 }
 
+struct TetAcc { unsigned c_bad, c_eval, c_err; unsigned long long minkey; };
+
 template <int KIND, bool FAST>
-__global__ void __launch_bounds__(kThreads)
+__device__ __noinline__ void drain_tets(NearQueue& q, int first, int n, int64_t elem_off, const int4* __restrict__ tet_v,
+                                           const double* __restrict__ vpos, const double* __restrict__ vq,
+                                           const double* __restrict__ vedge, const uint8_t* __restrict__ owned_arr,
+                                           int32_t* __restrict__ flags, double* __restrict__ qual, const SweepParams& P,
+                                           MagDevStats* st, int32_t* __restrict__ near_list, TetAcc& A)
+{
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned long long base = near_reserve(&st->n_near_elem, n);
+  if (lane < n) {
+    const int32_t t = q.e[w][first + lane];
+    const int64_t el = elem_off + t;
+    near_list[base + lane] = (int32_t)el;
+    if (FAST) {
+      int32_t f = q.f[w][first + lane];
+      const int4 tv = __ldg(tet_v + t);
+      int eig = 0;
+      const double qv = tet_quality_eval<KIND, false>(tv, vpos, vq, vedge, P.use_max, &eig);
+      const bool owned = owned_arr ? (owned_arr[el] != 0) : true;
+      ++A.c_eval;
+      mark_tet(qv, f, owned, P, A.c_bad);
+      flags[el] = f;
+      if (P.ops & MAG_OP_QUALITIES) qual[el] = qv;
+    }
+  }
+  __syncwarp();
+}
+
+template <int KIND, bool FAST>
+__global__ void __launch_bounds__(kThreads, FAST ? 3 : 2)
 k_tets(int64_t nt, int64_t elem_off, const int4* __restrict__ tet_v, const double* __restrict__ vpos,
        const double* __restrict__ vq, const double* __restrict__ vedge, const uint8_t* __restrict__ owned_arr,
        int32_t* __restrict__ flags, double* __restrict__ qual, SweepParams P, MagDevStats* st,
-       int64_t* __restrict__ near_list)
+       int32_t* __restrict__ near_list)
 {
-  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  unsigned c_bad = 0, c_eval = 0, c_err = 0;
-  unsigned long long minkey = ~0ull;
-  if (t < nt) {
-    const int64_t el = elem_off + t;
-    int32_t f = flags[el];
-    const int32_t f_in = f;
-    const bool do_bad = P.ops & MAG_OP_MARK_BAD;
-    if (do_bad && (f & MAG_BAD_QUALITY)) ++c_err;
-    const bool need_bad = do_bad && !(f & MAG_OK_QUALITY);
-    const bool want_q = P.ops & MAG_OP_QUALITIES;
-    if (want_q || need_bad) {
-      int4 tv = __ldg(tet_v + t);
-      int eig = 0;
-      double q = tet_quality_eval<KIND, FAST>(tv, vpos, vq, vedge, P.use_max, &eig);
-      if (eig) atomicAdd(&st->n_eigen_fail, 1ull);
-      if (want_q) { qual[el] = q; minkey = dkey(q); }
-      const bool owned = owned_arr ? (owned_arr[el] != 0) : true;
-      bool nr = need_bad && near_thr(q, P.good_q);
-      if (nr) {
-        unsigned long long k = atomicAdd(&st->n_near_elem, 1ull);
-        if (k < MAG_NEAR_CAP) near_list[k] = el;
-      }
-      if (FAST && nr) {
-        flags[el] = f | MAG_PENDING_BIT;
-      } else if (need_bad) {
-        ++c_eval;
-        mark_tet(q, f, owned, P, c_bad);
-        if (f != f_in) flags[el] = f;
+  __shared__ NearQueue q;
+  TetAcc A{0, 0, 0, ~0ull};
+  int qn = 0, eig_any = 0;
+  const bool do_bad = P.ops & MAG_OP_MARK_BAD, want_q = P.ops & MAG_OP_QUALITIES;
+  const int64_t ntiles = (nt + kThreads - 1) / kThreads;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t t = tile * kThreads + threadIdx.x;
+    bool nr = false;
+    int32_t f_in = 0;
+    if (t < nt) {
+      const int64_t el = elem_off + t;
+      int32_t f = f_in = flags[el];
+      if (do_bad && (f & MAG_BAD_QUALITY)) ++A.c_err;
+      const bool need_bad = do_bad && !(f & MAG_OK_QUALITY);
+      if (want_q || need_bad) {
+        const int4 tv = __ldg(tet_v + t);
+        const double qv = tet_quality_eval<KIND, FAST>(tv, vpos, vq, vedge, P.use_max, &eig_any);
+        if (want_q) {
+          qual[el] = qv;
+          const unsigned long long k = dkey(qv);
+          A.minkey = k < A.minkey ? k : A.minkey;
+        }
+        nr = need_bad && near_thr(qv, P.good_q);
+        if (need_bad && !(FAST && nr)) {
+          const bool owned = owned_arr ? (owned_arr[el] != 0) : true;
+          ++A.c_eval;
+          mark_tet(qv, f, owned, P, A.c_bad);
+          if (f != f_in) flags[el] = f;
+        }
       }
     }
+    if (queue_push(q, qn, nr, (int32_t)t, f_in)) {
+      qn -= 32;
+      drain_tets<KIND, FAST>(q, qn, 32, elem_off, tet_v, vpos, vq, vedge, owned_arr, flags, qual, P, st, near_list, A);
+    }
   }
-  block_count4(c_bad, c_eval, c_err, 0, &st->n_bad, &st->n_elems_eval, &st->n_flag_err, &st->n_flag_err);
-  if (P.ops & MAG_OP_QUALITIES) block_min_u64(minkey, &st->min_q_key);
-}
-
-template <int KIND>
-__global__ void __launch_bounds__(kThreads)
-k_fix_tets(int64_t nt, int64_t elem_off, const int4* __restrict__ tet_v, const double* __restrict__ vpos,
-           const double* __restrict__ vq, const double* __restrict__ vedge, const uint8_t* __restrict__ owned_arr,
-           int32_t* __restrict__ flags, SweepParams P, MagDevStats* st, const int64_t* __restrict__ near_list)
-{
-  const unsigned long long nn = st->n_near_elem;
-  const bool listed = nn <= MAG_NEAR_CAP;
-  const unsigned long long n = listed ? nn : (unsigned long long)nt;
-  unsigned c_bad = 0, c_eval = 0;
-  for (unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; k < n;
-       k += (unsigned long long)gridDim.x * blockDim.x) {
-    int64_t el = listed ? near_list[k] : elem_off + (int64_t)k;
-    int32_t f = flags[el];
-    if (!(f & MAG_PENDING_BIT)) continue;
-    f &= ~MAG_PENDING_BIT;
-    int4 tv = __ldg(tet_v + (el - elem_off));
-    int eig = 0;
-    double q = tet_quality_eval<KIND, false>(tv, vpos, vq, vedge, P.use_max, &eig);
-    const bool owned = owned_arr ? (owned_arr[el] != 0) : true;
-    ++c_eval;
-    mark_tet(q, f, owned, P, c_bad);
-    flags[el] = f;
+  if (qn) drain_tets<KIND, FAST>(q, 0, qn, elem_off, tet_v, vpos, vq, vedge, owned_arr, flags, qual, P, st, near_list, A);
+  if (eig_any) atomicAdd(&st->n_eigen_fail, 1ull);
+  warp_count_to(A.c_bad, &st->n_bad);
+  warp_count_to(A.c_eval, &st->n_elems_eval);
+  warp_count_to(A.c_err, &st->n_flag_err);
+  if (want_q) {
+    const unsigned long long m = warp_min_u64(A.minkey);
+    if ((threadIdx.x & 31) == 0 && m != ~0ull) atomicMin(&st->min_q_key, m);
   }
-  block_count4(c_bad, c_eval, 0, 0, &st->n_bad, &st->n_elems_eval, &st->n_flag_err, &st->n_flag_err);
 }
 
 // ------------------------------------------------------------------ prisms / pyramids
@@ -707,39 +714,48 @@ int magk_vertex_pass(mag_ctx* c)
   return MAG_OK;
 }
 
+// persistent grids: resident blocks per SM x number of SMs (queried once per context)
+static unsigned persistent_grid(mag_ctx* c, int& per_sm, const void* kernel, int64_t n)
+{
+  if (per_sm < 1 &&
+      (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1))
+    per_sm = 1;
+  int64_t g = (int64_t)per_sm * c->n_sms;
+  const int64_t tiles = (n + kThreads - 1) / kThreads;
+  if (g > tiles) g = tiles;
+  return (unsigned)(g < 1 ? 1 : g);
+}
+
 template <int KIND>
 static int launch_edges(mag_ctx* c, const SweepParams& P, bool fast)
 {
-  unsigned g = grid_for(c->ne);
   const int2* ev = reinterpret_cast<const int2*>(c->d_edge_v);
   if (fast) {
-    k_edges<KIND, true><<<g, kThreads, 0, c->stream>>>(c->ne, ev, c->d_vedge, c->d_edge_owned, c->d_edge_flags, c->d_len, P, c->d_stats, c->d_block_sums, c->d_near_edge);
-    if (P.ops & (MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE))
-    { k_fix_edges<KIND><<<148, kThreads, 0, c->stream>>>(c->ne, ev, c->d_vedge, c->d_edge_owned, c->d_edge_flags, P, c->d_stats, c->d_near_edge); c->n_launches++; }
+    static int per_sm = 0;
+    const unsigned g = persistent_grid(c, per_sm, (const void*)k_edges<KIND, true>, c->ne);
+    k_edges<KIND, true><<<g, kThreads, 0, c->stream>>>(c->ne, ev, c->d_vedge, c->d_edge_owned, c->d_edge_flags, c->d_len, P, c->d_stats, c->d_near_edge);
   } else {
-    k_edges<KIND, false><<<g, kThreads, 0, c->stream>>>(c->ne, ev, c->d_vedge, c->d_edge_owned, c->d_edge_flags, c->d_len, P, c->d_stats, c->d_block_sums, c->d_near_edge);
+    static int per_sm = 0;
+    const unsigned g = persistent_grid(c, per_sm, (const void*)k_edges<KIND, false>, c->ne);
+    k_edges<KIND, false><<<g, kThreads, 0, c->stream>>>(c->ne, ev, c->d_vedge, c->d_edge_owned, c->d_edge_flags, c->d_len, P, c->d_stats, c->d_near_edge);
   }
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;
-  if (P.ops & MAG_OP_LENGTHS) {
-    k_finish_sum<<<1, kThreads, 0, c->stream>>>((int64_t)g, c->d_block_sums, c->d_stats);
-    MAG_CUDA(c, cudaGetLastError());
-    c->n_launches++;
-  }
   return MAG_OK;
 }
 
 template <int KIND>
 static int launch_tets(mag_ctx* c, const SweepParams& P, bool fast)
 {
-  unsigned g = grid_for(c->nt);
   const int4* tv = reinterpret_cast<const int4*>(c->d_tet_v);
   const int64_t off = c->np + c->npy;
   if (fast) {
+    static int per_sm = 0;
+    const unsigned g = persistent_grid(c, per_sm, (const void*)k_tets<KIND, true>, c->nt);
     k_tets<KIND, true><<<g, kThreads, 0, c->stream>>>(c->nt, off, tv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_owned, c->d_elem_flags, c->d_qual, P, c->d_stats, c->d_near_elem);
-    if (P.ops & MAG_OP_MARK_BAD)
-    { k_fix_tets<KIND><<<148, kThreads, 0, c->stream>>>(c->nt, off, tv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_owned, c->d_elem_flags, P, c->d_stats, c->d_near_elem); c->n_launches++; }
   } else {
+    static int per_sm = 0;
+    const unsigned g = persistent_grid(c, per_sm, (const void*)k_tets<KIND, false>, c->nt);
     k_tets<KIND, false><<<g, kThreads, 0, c->stream>>>(c->nt, off, tv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_owned, c->d_elem_flags, c->d_qual, P, c->d_stats, c->d_near_elem);
   }
   MAG_CUDA(c, cudaGetLastError());
@@ -772,6 +788,12 @@ int magk_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double 
       default: rc = launch_edges<MAG_KIND_LOGM>(c, P, fast); break;
     }
     if (rc) return rc;
+    if (ops & MAG_OP_LENGTH_SUM) {
+      k_sum_lengths<<<MAG_SUM_BLOCKS, kThreads, 0, c->stream>>>(c->ne, c->d_len, c->d_edge_owned, c->d_block_sums);
+      k_finish_sum<<<1, kThreads, 0, c->stream>>>((int64_t)MAG_SUM_BLOCKS, c->d_block_sums, c->d_stats);
+      MAG_CUDA(c, cudaGetLastError());
+      c->n_launches += 2;
+    }
   }
   if (tev) MAG_CUDA(c, cudaEventRecord(tev[2], c->stream));
   if (ops & (MAG_OP_QUALITIES | MAG_OP_MARK_BAD)) {

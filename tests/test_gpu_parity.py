@@ -329,7 +329,7 @@ def test_full_size_properties(cb):
     assert np.array_equal(mao.edge_lengths(mao.ANISO, xyz, h, R, ev[se]), L0[se])
     assert np.array_equal(mao.tet_qualities(mao.ANISO, xyz, h, R, tv[stt]), q0[stt])
     # entity-order invariance
-    p.set_mesh(xyz, ev[::-1].copy(), tv[::-1].copy())
+    p.set_mesh(xyz, ev[::-1].copy(), tv[::-1].copy())   # a new mesh starts with zero flag words
     p.set_size_field_aniso(h, R)
     p.sweep(cb.OP_ALL & ~cb.OP_LAYER_CHECK, fp_mode=cb.FP_FAST)
     st = p.stats()
