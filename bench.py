@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-n", type=int, default=0, help="box size of the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--jitter", type=float, default=0.0,
+                    help="move interior vertices by this fraction of the cell size (SURVEY 8d optional perturbed variant)")
     return ap.parse_args()
 
 
@@ -282,6 +284,8 @@ def run_b200(a):
         xyz, edge_v, tet_v = part["xyz"], part["edge_v"], part["tet_v"]
         edge_owned, links = part["edge_owned"], part["links"]
     hbar = 1.0 / n
+    if a.jitter > 0:
+        xyz = cb.fields.jitter(xyz, a.jitter * hbar)
     # every slab is a unit cube; the field sees the triangle-wave coordinate u(x) = 1 - |1 - (x mod 2)|, a
     # continuous function of the GLOBAL position, so both copies of a shared vertex get bit-identical values
     fxyz = xyz

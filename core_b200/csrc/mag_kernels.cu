@@ -156,22 +156,39 @@ __global__ void k_vertex_pass(int64_t nv, const double* __restrict__ vedge, doub
   q[4] = make_double2(Q.m[2][2], det);
 }
 
-// ------------------------------------------------------------------ edge metric length (strict)
+// ------------------------------------------------------------------ edge metric length
+// the two vertex records of an edge, in registers: 4 doubles each (identity / iso) or 12 (aniso / logm)
+template <int KIND>
+struct EdgeRecs {
+  static constexpr int N = (KIND == MAG_KIND_ANISO || KIND == MAG_KIND_LOGM) ? 12 : 4;
+  double a[N], b[N];
+};
+template <int KIND>
+__device__ __forceinline__ void load_edge_recs(const double* __restrict__ vedge, int2 ev, EdgeRecs<KIND>& R)
+{
+  constexpr int N = EdgeRecs<KIND>::N;
+  const double2* pa = reinterpret_cast<const double2*>(vedge + N * (size_t)ev.x);
+  const double2* pb = reinterpret_cast<const double2*>(vedge + N * (size_t)ev.y);
+#pragma unroll
+  for (int i = 0; i < N / 2; ++i) { double2 t = __ldg(pa + i); R.a[2 * i] = t.x; R.a[2 * i + 1] = t.y; }
+#pragma unroll
+  for (int i = 0; i < N / 2; ++i) { double2 t = __ldg(pb + i); R.b[2 * i] = t.x; R.b[2 * i + 1] = t.y; }
+}
+
 // MetricSizeField::measure: order 2 -> EdgeIntegration::N2, points +-0.577350269189626, weights 1
 template <int KIND>
-__device__ __forceinline__ double edge_length_strict(const double* __restrict__ vedge, int32_t a, int32_t b, int* eig_fail)
+__device__ __forceinline__ double edge_length_strict(const EdgeRecs<KIND>& R, int* eig_fail)
 {
   constexpr double XI = 0.577350269189626;
   // shape values exactly as apfShape.cc:123-124 computes them
   constexpr double NP0 = (1.0 - XI) / 2.0, NP1 = (1.0 + XI) / 2.0;       // point 0: xi = +XI
   constexpr double NM0 = (1.0 - (-XI)) / 2.0, NM1 = (1.0 + (-XI)) / 2.0; // point 1: xi = -XI
-  if (KIND == MAG_KIND_IDENTITY || KIND == MAG_KIND_ISO) {
-    double ra[4], rb[4];
-    load_rec4(vedge, a, ra);
-    load_rec4(vedge, b, rb);
-    V3 j = magst::edge_j0(V3{ra[0], ra[1], ra[2]}, V3{rb[0], rb[1], rb[2]});
-    if (KIND == MAG_KIND_IDENTITY) return magst::mul(2.0, magst::length(j)); // apf::measure, N1 rule
-    double len[2];
+  const double* ra = R.a;
+  const double* rb = R.b;
+  V3 j = magst::edge_j0(V3{ra[0], ra[1], ra[2]}, V3{rb[0], rb[1], rb[2]});
+  if (KIND == MAG_KIND_IDENTITY) return magst::mul(2.0, magst::length(j)); // apf::measure, N1 rule
+  double len[2];
+  if (KIND == MAG_KIND_ISO) {
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
       double h = magst::lerp2(ra[3], p ? NM0 : NP0, rb[3], p ? NM1 : NP1);
@@ -179,17 +196,13 @@ __device__ __forceinline__ double edge_length_strict(const double* __restrict__ 
       V3 r{magst::mul(j.x, ih), magst::mul(j.y, ih), magst::mul(j.z, ih)};
       len[p] = magst::length(r);
     }
-    return magst::add(len[0], len[1]);
   } else {
-    Rec12 ra = load_rec12(vedge, a), rb = load_rec12(vedge, b);
-    V3 j = magst::edge_j0(V3{ra.v[0], ra.v[1], ra.v[2]}, V3{rb.v[0], rb.v[1], rb.v[2]});
-    double len[2];
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
       const double n0 = p ? NM0 : NP0, n1 = p ? NM1 : NP1;
       double c[9];
 #pragma unroll
-      for (int i = 0; i < 9; ++i) c[i] = magst::lerp2(ra.v[3 + i], n0, rb.v[3 + i], n1);
+      for (int i = 0; i < 9; ++i) c[i] = magst::lerp2(ra[(3 + i) % EdgeRecs<KIND>::N], n0, rb[(3 + i) % EdgeRecs<KIND>::N], n1);
       M3 Q;
       if (KIND == MAG_KIND_ANISO) {
         magst::transform_aniso(V3{c[3], c[4], c[5]}, V3{c[6], c[7], c[8]}, c[0], c[1], c[2], Q);
@@ -201,24 +214,17 @@ __device__ __forceinline__ double edge_length_strict(const double* __restrict__ 
       }
       len[p] = magst::row0_length(j, Q);
     }
-    return magst::add(len[0], len[1]);
   }
+  return magst::add(len[0], len[1]);
 }
 
 template <int KIND>
-__device__ __forceinline__ double edge_length_fast(const double* __restrict__ vedge, int32_t a, int32_t b, int* eig_fail)
+__device__ __forceinline__ double edge_length_fast(const EdgeRecs<KIND>& R, int* eig_fail)
 {
-  if (KIND == MAG_KIND_IDENTITY || KIND == MAG_KIND_ISO) {
-    double ra[4], rb[4];
-    load_rec4(vedge, a, ra);
-    load_rec4(vedge, b, rb);
-    if (KIND == MAG_KIND_IDENTITY) return magfa::edge_identity(ra, rb);
-    return magfa::edge_iso(ra, rb);
-  } else {
-    Rec12 ra = load_rec12(vedge, a), rb = load_rec12(vedge, b);
-    if (KIND == MAG_KIND_ANISO) return magfa::edge_aniso(ra.v, rb.v);
-    return magfa::edge_logm(ra.v, rb.v, eig_fail);
-  }
+  if (KIND == MAG_KIND_IDENTITY) return magfa::edge_identity(R.a, R.b);
+  if (KIND == MAG_KIND_ISO) return magfa::edge_iso(R.a, R.b);
+  if (KIND == MAG_KIND_ANISO) return magfa::edge_aniso(R.a, R.b);
+  return magfa::edge_logm(R.a, R.b, eig_fail);
 }
 
 struct SweepParams {
@@ -251,7 +257,7 @@ __device__ __forceinline__ void mark_edge(double len, int32_t& f, bool need_spli
 // drains the queue with all lanes active: the entity is appended to the global near-threshold list and, in
 // MAG_FP_FAST, re-evaluated in strict arithmetic so the flag is the reference's.  Deferring keeps the strict code
 // out of the divergent path of the main loop (structured meshes put whole families of edges exactly ON a threshold).
-constexpr int kWarps = kThreads / 32;
+constexpr int kWarps = 16;   // queue rows: the largest block any kernel here uses is 512 threads
 constexpr int kQCap = 64;
 struct NearQueue { int32_t e[kWarps][kQCap]; int32_t f[kWarps][kQCap]; };
 
@@ -278,17 +284,68 @@ __device__ __forceinline__ unsigned long long near_reserve(unsigned long long* c
   return __shfl_sync(0xffffffffu, base, 0);
 }
 
-struct EdgeAcc { unsigned c_split, c_coll, c_eval, c_err; unsigned long long maxbits; };
-
-// drain n (<= 32) queued edges: entry i is handled by lane i
-template <int KIND, bool FAST>
-__device__ __noinline__ void drain_edges(NearQueue& q, int first, int n, const int2* __restrict__ edge_v,
-                                            const double* __restrict__ vedge, const uint8_t* __restrict__ owned_arr,
-                                            int32_t* __restrict__ flags, double* __restrict__ lengths, const SweepParams& P,
-                                            MagDevStats* st, int32_t* __restrict__ near_list, EdgeAcc& A)
+// Work distribution of the persistent kernels: chunks of kChunkTiles consecutive tiles handed out through an atomic
+// counter.  Consecutive tiles on one SM keep the vertex records they share (the next grid row of a box mesh, the
+// neighbouring elements of any reasonably numbered mesh) in that SM's L1; dynamic hand-out evens out chunks made
+// expensive by near-threshold re-evaluations or cheap by skip flags.
+#ifndef MAG_FAST_BLOCKS
+#define MAG_FAST_BLOCKS 2
+#endif
+#ifndef MAG_CHUNK_TILES
+#define MAG_CHUNK_TILES 32
+#endif
+constexpr int kChunkTiles = MAG_CHUNK_TILES;
+#ifndef MAG_EDGE_THREADS
+#define MAG_EDGE_THREADS 256
+#endif
+#ifndef MAG_EDGE_BLOCKS
+#define MAG_EDGE_BLOCKS 2
+#endif
+#ifndef MAG_TET_THREADS
+#define MAG_TET_THREADS 256
+#endif
+#ifndef MAG_TET_BLOCKS
+#define MAG_TET_BLOCKS 2
+#endif
+#ifndef MAG_TET_BLOCKS_STRICT
+#define MAG_TET_BLOCKS_STRICT 2
+#endif
+constexpr int kTetThreads = MAG_TET_THREADS;
+#ifndef MAG_EDGE_BLOCKS_STRICT
+#define MAG_EDGE_BLOCKS_STRICT 2
+#endif
+constexpr int kEdgeThreads = MAG_EDGE_THREADS;
+__device__ __forceinline__ long long next_chunk(unsigned long long* counter, long long* slot)
 {
+  __syncthreads();                       // everyone is done with the previous value of *slot
+  if (threadIdx.x == 0) *slot = (long long)atomicAdd(counter, 1ull);
+  __syncthreads();
+  return *slot;
+}
+__device__ __forceinline__ void prefetch_l1(const void* p)
+{
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+// both cache lines a 96-byte (12-double) record can touch
+__device__ __forceinline__ void prefetch_rec12(const double* __restrict__ base, int32_t vid)
+{
+  const char* p = reinterpret_cast<const char*>(base + 12 * (size_t)vid);
+  prefetch_l1(p);
+  prefetch_l1(p + 80);
+}
+
+// drain n (<= 32) queued edges: entry i is handled by lane i.  Returns bit 0: evaluated, bit 1: counted SPLIT, bit 2: counted COLLAPSE
+template <int KIND, bool FAST>
+__device__ __noinline__ unsigned drain_edges(NearQueue& q, int first, int n, const int2* __restrict__ edge_v,
+                                             const double* __restrict__ vedge, const uint8_t* __restrict__ owned_arr,
+                                             int32_t* __restrict__ flags, double* __restrict__ lengths, uint32_t ops,
+                                             double max_len, double min_len,
+                                             MagDevStats* st, int32_t* __restrict__ near_list)
+{
+  SweepParams P{ops, max_len, min_len, 0.0, 0};
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const unsigned long long base = near_reserve(&st->n_near_edge, n);
+  unsigned out = 0;
   if (lane < n) {
     const int32_t e = q.e[w][first + lane];
     near_list[base + lane] = e;
@@ -296,74 +353,143 @@ __device__ __noinline__ void drain_edges(NearQueue& q, int first, int n, const i
       int32_t f = q.f[w][first + lane];
       const bool need_split = (P.ops & MAG_OP_MARK_SPLIT) && !(f & (MAG_DONT_SPLIT | MAG_NEED_NOT_SPLIT));
       const bool need_coll = (P.ops & MAG_OP_MARK_COLLAPSE) && !(f & (MAG_DONT_COLLAPSE | MAG_NEED_NOT_COLLAPSE));
-      const int2 ev = __ldg(edge_v + e);
+      EdgeRecs<KIND> R;
+      load_edge_recs<KIND>(vedge, __ldg(edge_v + e), R);
       int eig = 0;
-      const double len = edge_length_strict<KIND>(vedge, ev.x, ev.y, &eig);
+      const double len = edge_length_strict<KIND>(R, &eig);
       const bool owned = owned_arr ? (owned_arr[e] != 0) : true;
-      ++A.c_eval;
-      mark_edge(len, f, need_split, need_coll, owned, P, A.c_split, A.c_coll);
+      unsigned cs = 0, cc = 0;
+      mark_edge(len, f, need_split, need_coll, owned, P, cs, cc);
+      out = 1u | (cs << 1) | (cc << 2);
       flags[e] = f;
       if (P.ops & MAG_OP_LENGTHS) lengths[e] = len;
     }
   }
   __syncwarp();
+  return out;
 }
 
+// Software pipeline of the edge kernel, per thread and tile k:
+//   flag word + end vertices are loaded two tiles ahead, the two vertex records one tile ahead (straight into
+//   registers, only when the flag word says the edge has to be evaluated at all), so the gather latency of tile
+//   k+1 is covered by the arithmetic of tile k.
 template <int KIND, bool FAST>
-__global__ void __launch_bounds__(kThreads, FAST ? 3 : 2)
+__global__ void __launch_bounds__(kEdgeThreads, FAST ? MAG_EDGE_BLOCKS : MAG_EDGE_BLOCKS_STRICT)
 k_edges(int64_t ne, const int2* __restrict__ edge_v, const double* __restrict__ vedge,
         const uint8_t* __restrict__ owned_arr, int32_t* __restrict__ flags, double* __restrict__ lengths,
         SweepParams P, MagDevStats* st, int32_t* __restrict__ near_list)
 {
   __shared__ NearQueue q;
-  EdgeAcc A{0, 0, 0, 0, 0ull};
+  __shared__ long long chunk_slot;
+  unsigned c_split = 0, c_coll = 0, c_eval = 0, c_err = 0;
+  unsigned long long maxbits = 0;
   int qn = 0, eig_any = 0;
   const bool do_split = P.ops & MAG_OP_MARK_SPLIT, do_coll = P.ops & MAG_OP_MARK_COLLAPSE;
   const bool want_len = P.ops & MAG_OP_LENGTHS;
-  const int64_t ntiles = (ne + kThreads - 1) / kThreads;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t e = tile * kThreads + threadIdx.x;
-    bool nr = false;
-    int32_t f_in = 0;
-    if (e < ne) {
-      int32_t f = f_in = flags[e];
-      // markEntities asserts the true flag is clear on every entity it visits (maAdapt.cc:308)
-      if ((do_split && (f & MAG_SPLIT)) || (do_coll && (f & MAG_COLLAPSE))) ++A.c_err;
-      const bool need_split = do_split && !(f & (MAG_DONT_SPLIT | MAG_NEED_NOT_SPLIT));
-      const bool need_coll = do_coll && !(f & (MAG_DONT_COLLAPSE | MAG_NEED_NOT_COLLAPSE));
-      if (want_len || need_split || need_coll) {
-        const int2 ev = __ldg(edge_v + e);
-        const double len = FAST ? edge_length_fast<KIND>(vedge, ev.x, ev.y, &eig_any)
-                                : edge_length_strict<KIND>(vedge, ev.x, ev.y, &eig_any);
-        const bool owned = owned_arr ? (owned_arr[e] != 0) : true;
-        if (want_len) {
-          lengths[e] = len;
-          if (owned && len > 0) {
-            const unsigned long long b = (unsigned long long)__double_as_longlong(len);
-            A.maxbits = b > A.maxbits ? b : A.maxbits;
+  const int32_t skip_split = do_split ? (MAG_DONT_SPLIT | MAG_NEED_NOT_SPLIT) : ~0;
+  const int32_t skip_coll = do_coll ? (MAG_DONT_COLLAPSE | MAG_NEED_NOT_COLLAPSE) : ~0;
+  const int64_t ntiles = (ne + kEdgeThreads - 1) / kEdgeThreads;
+  const int64_t nchunks = (ntiles + kChunkTiles - 1) / kChunkTiles;
+  for (;;) {
+    const long long chunk = next_chunk(&st->edge_chunk, &chunk_slot);
+    if (chunk >= nchunks) break;
+    const int64_t t0 = chunk * kChunkTiles;
+    const int64_t t1 = (t0 + kChunkTiles < ntiles) ? t0 + kChunkTiles : ntiles;
+    const int64_t e_end = (t1 * kEdgeThreads < ne) ? t1 * kEdgeThreads : ne;   // first edge past this chunk
+    int64_t e = t0 * kEdgeThreads + threadIdx.x;
+    // prologue: tile t0 fully loaded, (flag, ends) of tile t0+1 in flight
+    int32_t f_cur = 0, f_nx = 0;
+    int2 ev_nx = make_int2(0, 0);
+    EdgeRecs<KIND> R;
+    bool work_cur = false;
+    int2 ev_cur = make_int2(0, 0);
+    if (e < e_end) {
+      f_cur = flags[e];
+      work_cur = want_len || !(f_cur & skip_split) || !(f_cur & skip_coll);
+      ev_cur = __ldg(edge_v + e);
+#ifdef MAG_EDGE_PREFETCH
+      if (work_cur) load_edge_recs<KIND>(vedge, ev_cur, R);
+#endif
+    }
+    if (e + kEdgeThreads < e_end) { f_nx = flags[e + kEdgeThreads]; ev_nx = __ldg(edge_v + e + kEdgeThreads); }
+    // one pipeline step: issue the loads of tile k+1 (records into Rn; only with MAG_EDGE_PREFETCH) and k+2 (flag, ends),
+    // then compute tile k from Rc.  With record prefetch the loop is unrolled by two with the roles of the two register
+    // sets swapped, so no register copies stand between a load and its (much later) first use.
+    auto step = [&](EdgeRecs<KIND>& Rc, int32_t f_c, bool work_c, EdgeRecs<KIND>& Rn, int32_t& f_n, bool& work_n) {
+      f_n = f_nx;
+      work_n = false;
+      const int2 ev_n = ev_nx;
+      if (e + kEdgeThreads < e_end) {
+        work_n = want_len || !(f_n & skip_split) || !(f_n & skip_coll);
+#ifdef MAG_EDGE_PREFETCH
+        if (work_n) load_edge_recs<KIND>(vedge, ev_n, Rn);
+#endif
+      }
+      if (e + 2 * kEdgeThreads < e_end) { f_nx = flags[e + 2 * kEdgeThreads]; ev_nx = __ldg(edge_v + e + 2 * kEdgeThreads); }
+      bool nr = false;
+      if (e < e_end) {
+        int32_t f = f_c;
+        // markEntities asserts the true flag is clear on every entity it visits (maAdapt.cc:308)
+        if ((do_split && (f & MAG_SPLIT)) || (do_coll && (f & MAG_COLLAPSE))) ++c_err;
+        if (work_c) {
+#ifndef MAG_EDGE_PREFETCH
+          load_edge_recs<KIND>(vedge, ev_cur, Rc);   // plain version: this tile's records are gathered here
+#endif
+          const bool need_split = !(f & skip_split), need_coll = !(f & skip_coll);
+          const double len = FAST ? edge_length_fast<KIND>(Rc, &eig_any) : edge_length_strict<KIND>(Rc, &eig_any);
+          const bool owned = owned_arr ? (owned_arr[e] != 0) : true;
+          if (want_len) {
+            lengths[e] = len;
+            if (owned && len > 0) {
+              const unsigned long long b = (unsigned long long)__double_as_longlong(len);
+              maxbits = b > maxbits ? b : maxbits;
+            }
+          }
+          nr = (need_split && near_thr(len, P.max_len)) || (need_coll && near_thr(len, P.min_len));
+          if ((need_split || need_coll) && !(FAST && nr)) {
+            ++c_eval;
+            mark_edge(len, f, need_split, need_coll, owned, P, c_split, c_coll);
+            if (f != f_c) flags[e] = f;
           }
         }
-        nr = (need_split && near_thr(len, P.max_len)) || (need_coll && near_thr(len, P.min_len));
-        if ((need_split || need_coll) && !(FAST && nr)) {
-          ++A.c_eval;
-          mark_edge(len, f, need_split, need_coll, owned, P, A.c_split, A.c_coll);
-          if (f != f_in) flags[e] = f;
-        }
       }
+      if (queue_push(q, qn, nr, (int32_t)e, f_c)) {
+        qn -= 32;
+        const unsigned r = drain_edges<KIND, FAST>(q, qn, 32, edge_v, vedge, owned_arr, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list);
+        c_eval += r & 1u; c_split += (r >> 1) & 1u; c_coll += (r >> 2) & 1u;
+      }
+      e += kEdgeThreads;
+      ev_cur = ev_n;
+    };
+#ifdef MAG_EDGE_PREFETCH
+    EdgeRecs<KIND> R2;
+    int32_t f_2 = 0;
+    bool work_2 = false;
+    for (int64_t tile = t0; tile < t1; tile += 2) {
+      step(R, f_cur, work_cur, R2, f_2, work_2);
+      if (tile + 1 < t1) step(R2, f_2, work_2, R, f_cur, work_cur);
     }
-    if (queue_push(q, qn, nr, (int32_t)e, f_in)) {
-      qn -= 32;
-      drain_edges<KIND, FAST>(q, qn, 32, edge_v, vedge, owned_arr, flags, lengths, P, st, near_list, A);
+#else
+    for (int64_t tile = t0; tile < t1; ++tile) {
+      int32_t f_n;
+      bool work_n;
+      step(R, f_cur, work_cur, R, f_n, work_n);
+      f_cur = f_n;
+      work_cur = work_n;
     }
+#endif
   }
-  if (qn) drain_edges<KIND, FAST>(q, 0, qn, edge_v, vedge, owned_arr, flags, lengths, P, st, near_list, A);
+  if (qn) {
+    const unsigned r = drain_edges<KIND, FAST>(q, 0, qn, edge_v, vedge, owned_arr, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list);
+    c_eval += r & 1u; c_split += (r >> 1) & 1u; c_coll += (r >> 2) & 1u;
+  }
   if (eig_any) atomicAdd(&st->n_eigen_fail, 1ull);
-  warp_count_to(A.c_split, &st->n_split);
-  warp_count_to(A.c_coll, &st->n_collapse);
-  warp_count_to(A.c_eval, &st->n_edges_eval);
-  warp_count_to(A.c_err, &st->n_flag_err);
+  warp_count_to(c_split, &st->n_split);
+  warp_count_to(c_coll, &st->n_collapse);
+  warp_count_to(c_eval, &st->n_edges_eval);
+  warp_count_to(c_err, &st->n_flag_err);
   if (want_len) {
-    const unsigned long long m = warp_max_u64(A.maxbits);
+    const unsigned long long m = warp_max_u64(maxbits);
     if ((threadIdx.x & 31) == 0 && m) atomicMax(&st->max_len_bits, m);
   }
 }
@@ -427,32 +553,44 @@ __device__ __forceinline__ void centroid_transform(const double* __restrict__ ve
   }
 }
 
-template <int KIND, bool FAST>
+// getMetricWithMaxJacobean: strict >, first maximum wins (maQuality.cc:97-104)
+__device__ __forceinline__ int32_t best_vertex(const int4& tv, double d0, double d1, double d2, double d3)
+{
+  int32_t vb = tv.x;
+  double maxJ = -1.0;
+  if (d0 > maxJ) { maxJ = d0; vb = tv.x; }
+  if (d1 > maxJ) { maxJ = d1; vb = tv.y; }
+  if (d2 > maxJ) { maxJ = d2; vb = tv.z; }
+  if (d3 > maxJ) { maxJ = d3; vb = tv.w; }
+  return vb;
+}
+__device__ __forceinline__ void load_q(const double* __restrict__ vq, int32_t vb, M3& Q, double& detQ)
+{
+  const double2* q = reinterpret_cast<const double2*>(vq + 10 * (size_t)vb);
+  double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4);
+  Q.m[0][0] = q0.x; Q.m[0][1] = q0.y; Q.m[0][2] = q1.x;
+  Q.m[1][0] = q1.y; Q.m[1][1] = q2.x; Q.m[1][2] = q2.y;
+  Q.m[2][0] = q3.x; Q.m[2][1] = q3.y; Q.m[2][2] = q4.x;
+  detQ = q4.y;
+}
+
+// HAVE_DETS: the four det Q_v were loaded one tile ahead (dets[]), so the transform of the best vertex can be
+// requested together with the coordinates instead of after them
+template <int KIND, bool FAST, bool HAVE_DETS>
 __device__ __forceinline__ double tet_quality_eval(const int4& tv, const double* __restrict__ vpos,
                                                    const double* __restrict__ vq, const double* __restrict__ vedge,
-                                                   int use_max, int* eig)
+                                                   int use_max, int* eig, const double* dets)
 {
+  M3 Q;
+  double detQ = 0.0;
+  if (HAVE_DETS && use_max) load_q(vq, best_vertex(tv, dets[0], dets[1], dets[2], dets[3]), Q, detQ);
   double p[4][4];
   load_rec4(vpos, tv.x, p[0]);
   load_rec4(vpos, tv.y, p[1]);
   load_rec4(vpos, tv.z, p[2]);
   load_rec4(vpos, tv.w, p[3]);
-  M3 Q;
-  double detQ;
   if (use_max) {
-    // getMetricWithMaxJacobean: strict >, first maximum wins (maQuality.cc:97-104)
-    int best = 0;
-    double maxJ = -1.0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (p[i][3] > maxJ) { maxJ = p[i][3]; best = i; }
-    int32_t vb = best == 0 ? tv.x : best == 1 ? tv.y : best == 2 ? tv.z : tv.w;
-    const double2* q = reinterpret_cast<const double2*>(vq + 10 * (size_t)vb);
-    double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4);
-    Q.m[0][0] = q0.x; Q.m[0][1] = q0.y; Q.m[0][2] = q1.x;
-    Q.m[1][0] = q1.y; Q.m[1][1] = q2.x; Q.m[1][2] = q2.y;
-    Q.m[2][0] = q3.x; Q.m[2][1] = q3.y; Q.m[2][2] = q4.x;
-    detQ = q4.y;
+    if (!HAVE_DETS) load_q(vq, best_vertex(tv, p[0][3], p[1][3], p[2][3], p[3][3]), Q, detQ);
   } else {
     centroid_transform<KIND>(vedge, tv, Q, eig);
     detQ = FAST ? magst::det3(Q) : 0.0;
@@ -469,17 +607,19 @@ __device__ __forceinline__ void mark_tet(double q, int32_t& f, bool owned, const
   else f |= MAG_OK_QUALITY;
 }
 
-struct TetAcc { unsigned c_bad, c_eval, c_err; unsigned long long minkey; };
-
+// returns bit 0: evaluated, bit 1: counted BAD_QUALITY
 template <int KIND, bool FAST>
-__device__ __noinline__ void drain_tets(NearQueue& q, int first, int n, int64_t elem_off, const int4* __restrict__ tet_v,
-                                           const double* __restrict__ vpos, const double* __restrict__ vq,
-                                           const double* __restrict__ vedge, const uint8_t* __restrict__ owned_arr,
-                                           int32_t* __restrict__ flags, double* __restrict__ qual, const SweepParams& P,
-                                           MagDevStats* st, int32_t* __restrict__ near_list, TetAcc& A)
+__device__ __noinline__ unsigned drain_tets(NearQueue& q, int first, int n, int64_t elem_off, const int4* __restrict__ tet_v,
+                                            const double* __restrict__ vpos, const double* __restrict__ vq,
+                                            const double* __restrict__ vedge, const uint8_t* __restrict__ owned_arr,
+                                            int32_t* __restrict__ flags, double* __restrict__ qual, uint32_t ops,
+                                            double good_q, int use_max,
+                                            MagDevStats* st, int32_t* __restrict__ near_list)
 {
+  SweepParams P{ops, 0.0, 0.0, good_q, use_max};
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const unsigned long long base = near_reserve(&st->n_near_elem, n);
+  unsigned out = 0;
   if (lane < n) {
     const int32_t t = q.e[w][first + lane];
     const int64_t el = elem_off + t;
@@ -488,67 +628,105 @@ __device__ __noinline__ void drain_tets(NearQueue& q, int first, int n, int64_t 
       int32_t f = q.f[w][first + lane];
       const int4 tv = __ldg(tet_v + t);
       int eig = 0;
-      const double qv = tet_quality_eval<KIND, false>(tv, vpos, vq, vedge, P.use_max, &eig);
+      const double qv = tet_quality_eval<KIND, false, false>(tv, vpos, vq, vedge, P.use_max, &eig, nullptr);
       const bool owned = owned_arr ? (owned_arr[el] != 0) : true;
-      ++A.c_eval;
-      mark_tet(qv, f, owned, P, A.c_bad);
+      unsigned cb = 0;
+      mark_tet(qv, f, owned, P, cb);
+      out = 1u | (cb << 1);
       flags[el] = f;
       if (P.ops & MAG_OP_QUALITIES) qual[el] = qv;
     }
   }
   __syncwarp();
+  return out;
 }
 
+// Software pipeline of the tet kernel, per thread and tile k: flag word + vertices two tiles ahead; the four det Q_v
+// (8-byte loads out of the {x,y,z,det} records, which also pulls those records towards L1) one tile ahead, so that the
+// choice of the max-Jacobian vertex does not sit between two dependent gathers.
 template <int KIND, bool FAST>
-__global__ void __launch_bounds__(kThreads, FAST ? 3 : 2)
+__global__ void __launch_bounds__(kTetThreads, FAST ? MAG_TET_BLOCKS : MAG_TET_BLOCKS_STRICT)
 k_tets(int64_t nt, int64_t elem_off, const int4* __restrict__ tet_v, const double* __restrict__ vpos,
        const double* __restrict__ vq, const double* __restrict__ vedge, const uint8_t* __restrict__ owned_arr,
        int32_t* __restrict__ flags, double* __restrict__ qual, SweepParams P, MagDevStats* st,
        int32_t* __restrict__ near_list)
 {
   __shared__ NearQueue q;
-  TetAcc A{0, 0, 0, ~0ull};
+  __shared__ long long chunk_slot;
+  unsigned c_bad = 0, c_eval = 0, c_err = 0;
+  unsigned long long minkey = ~0ull;
   int qn = 0, eig_any = 0;
   const bool do_bad = P.ops & MAG_OP_MARK_BAD, want_q = P.ops & MAG_OP_QUALITIES;
-  const int64_t ntiles = (nt + kThreads - 1) / kThreads;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t t = tile * kThreads + threadIdx.x;
-    bool nr = false;
-    int32_t f_in = 0;
-    if (t < nt) {
-      const int64_t el = elem_off + t;
-      int32_t f = f_in = flags[el];
-      if (do_bad && (f & MAG_BAD_QUALITY)) ++A.c_err;
-      const bool need_bad = do_bad && !(f & MAG_OK_QUALITY);
-      if (want_q || need_bad) {
-        const int4 tv = __ldg(tet_v + t);
-        const double qv = tet_quality_eval<KIND, FAST>(tv, vpos, vq, vedge, P.use_max, &eig_any);
-        if (want_q) {
-          qual[el] = qv;
-          const unsigned long long k = dkey(qv);
-          A.minkey = k < A.minkey ? k : A.minkey;
-        }
-        nr = need_bad && near_thr(qv, P.good_q);
-        if (need_bad && !(FAST && nr)) {
-          const bool owned = owned_arr ? (owned_arr[el] != 0) : true;
-          ++A.c_eval;
-          mark_tet(qv, f, owned, P, A.c_bad);
-          if (f != f_in) flags[el] = f;
+  const int64_t ntiles = (nt + kTetThreads - 1) / kTetThreads;
+  const int64_t nchunks = (ntiles + kChunkTiles - 1) / kChunkTiles;
+  for (;;) {
+    const long long chunk = next_chunk(&st->elem_chunk, &chunk_slot);
+    if (chunk >= nchunks) break;
+    const int64_t t0 = chunk * kChunkTiles;
+    const int64_t t1 = (t0 + kChunkTiles < ntiles) ? t0 + kChunkTiles : ntiles;
+    const int64_t t_end = (t1 * kTetThreads < nt) ? t1 * kTetThreads : nt;
+    int64_t t = t0 * kTetThreads + threadIdx.x;
+    int32_t f_cur = 0, f_nx = 0;
+    int4 tv_cur = make_int4(0, 0, 0, 0), tv_nx = tv_cur;
+    double dets[4] = {0, 0, 0, 0};
+    auto load_dets = [&](const int4& tv, double* d) {
+      d[0] = __ldg(vpos + 4 * (size_t)tv.x + 3); d[1] = __ldg(vpos + 4 * (size_t)tv.y + 3);
+      d[2] = __ldg(vpos + 4 * (size_t)tv.z + 3); d[3] = __ldg(vpos + 4 * (size_t)tv.w + 3);
+    };
+    if (t < t_end) {
+      f_cur = flags[elem_off + t];
+      tv_cur = __ldg(tet_v + t);
+      if (want_q || (do_bad && !(f_cur & MAG_OK_QUALITY))) load_dets(tv_cur, dets);
+    }
+    if (t + kTetThreads < t_end) { f_nx = flags[elem_off + t + kTetThreads]; tv_nx = __ldg(tet_v + t + kTetThreads); }
+    for (int64_t tile = t0; tile < t1; ++tile, t += kTetThreads) {
+      const int32_t f_in = f_cur;
+      const int4 tv = tv_cur;
+      double d_cur[4] = {dets[0], dets[1], dets[2], dets[3]};
+      // next tile: its dets; tile after: flag word + vertices
+      f_cur = f_nx;
+      tv_cur = tv_nx;
+      if (t + kTetThreads < t_end && (want_q || (do_bad && !(f_cur & MAG_OK_QUALITY)))) load_dets(tv_cur, dets);
+      if (t + 2 * kTetThreads < t_end) { f_nx = flags[elem_off + t + 2 * kTetThreads]; tv_nx = __ldg(tet_v + t + 2 * kTetThreads); }
+      bool nr = false;
+      if (t < t_end) {
+        const int64_t el = elem_off + t;
+        int32_t f = f_in;
+        if (do_bad && (f & MAG_BAD_QUALITY)) ++c_err;
+        const bool need_bad = do_bad && !(f & MAG_OK_QUALITY);
+        if (want_q || need_bad) {
+          const double qv = tet_quality_eval<KIND, FAST, true>(tv, vpos, vq, vedge, P.use_max, &eig_any, d_cur);
+          if (want_q) {
+            qual[el] = qv;
+            const unsigned long long k = dkey(qv);
+            minkey = k < minkey ? k : minkey;
+          }
+          nr = need_bad && near_thr(qv, P.good_q);
+          if (need_bad && !(FAST && nr)) {
+            const bool owned = owned_arr ? (owned_arr[el] != 0) : true;
+            ++c_eval;
+            mark_tet(qv, f, owned, P, c_bad);
+            if (f != f_in) flags[el] = f;
+          }
         }
       }
-    }
-    if (queue_push(q, qn, nr, (int32_t)t, f_in)) {
-      qn -= 32;
-      drain_tets<KIND, FAST>(q, qn, 32, elem_off, tet_v, vpos, vq, vedge, owned_arr, flags, qual, P, st, near_list, A);
+      if (queue_push(q, qn, nr, (int32_t)t, f_in)) {
+        qn -= 32;
+        const unsigned r = drain_tets<KIND, FAST>(q, qn, 32, elem_off, tet_v, vpos, vq, vedge, owned_arr, flags, qual, P.ops, P.good_q, P.use_max, st, near_list);
+        c_eval += r & 1u; c_bad += (r >> 1) & 1u;
+      }
     }
   }
-  if (qn) drain_tets<KIND, FAST>(q, 0, qn, elem_off, tet_v, vpos, vq, vedge, owned_arr, flags, qual, P, st, near_list, A);
+  if (qn) {
+    const unsigned r = drain_tets<KIND, FAST>(q, 0, qn, elem_off, tet_v, vpos, vq, vedge, owned_arr, flags, qual, P.ops, P.good_q, P.use_max, st, near_list);
+    c_eval += r & 1u; c_bad += (r >> 1) & 1u;
+  }
   if (eig_any) atomicAdd(&st->n_eigen_fail, 1ull);
-  warp_count_to(A.c_bad, &st->n_bad);
-  warp_count_to(A.c_eval, &st->n_elems_eval);
-  warp_count_to(A.c_err, &st->n_flag_err);
+  warp_count_to(c_bad, &st->n_bad);
+  warp_count_to(c_eval, &st->n_elems_eval);
+  warp_count_to(c_err, &st->n_flag_err);
   if (want_q) {
-    const unsigned long long m = warp_min_u64(A.minkey);
+    const unsigned long long m = warp_min_u64(minkey);
     if ((threadIdx.x & 31) == 0 && m != ~0ull) atomicMin(&st->min_q_key, m);
   }
 }
@@ -715,13 +893,13 @@ int magk_vertex_pass(mag_ctx* c)
 }
 
 // persistent grids: resident blocks per SM x number of SMs (queried once per context)
-static unsigned persistent_grid(mag_ctx* c, int& per_sm, const void* kernel, int64_t n)
+static unsigned persistent_grid(mag_ctx* c, int& per_sm, const void* kernel, int64_t n, int threads = kThreads)
 {
   if (per_sm < 1 &&
-      (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1))
+      (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1))
     per_sm = 1;
   int64_t g = (int64_t)per_sm * c->n_sms;
-  const int64_t tiles = (n + kThreads - 1) / kThreads;
+  const int64_t tiles = (n + (int64_t)threads * kChunkTiles - 1) / ((int64_t)threads * kChunkTiles);
   if (g > tiles) g = tiles;
   return (unsigned)(g < 1 ? 1 : g);
 }
@@ -732,12 +910,12 @@ static int launch_edges(mag_ctx* c, const SweepParams& P, bool fast)
   const int2* ev = reinterpret_cast<const int2*>(c->d_edge_v);
   if (fast) {
     static int per_sm = 0;
-    const unsigned g = persistent_grid(c, per_sm, (const void*)k_edges<KIND, true>, c->ne);
-    k_edges<KIND, true><<<g, kThreads, 0, c->stream>>>(c->ne, ev, c->d_vedge, c->d_edge_owned, c->d_edge_flags, c->d_len, P, c->d_stats, c->d_near_edge);
+    const unsigned g = persistent_grid(c, per_sm, (const void*)k_edges<KIND, true>, c->ne, kEdgeThreads);
+    k_edges<KIND, true><<<g, kEdgeThreads, 0, c->stream>>>(c->ne, ev, c->d_vedge, c->d_edge_owned, c->d_edge_flags, c->d_len, P, c->d_stats, c->d_near_edge);
   } else {
     static int per_sm = 0;
-    const unsigned g = persistent_grid(c, per_sm, (const void*)k_edges<KIND, false>, c->ne);
-    k_edges<KIND, false><<<g, kThreads, 0, c->stream>>>(c->ne, ev, c->d_vedge, c->d_edge_owned, c->d_edge_flags, c->d_len, P, c->d_stats, c->d_near_edge);
+    const unsigned g = persistent_grid(c, per_sm, (const void*)k_edges<KIND, false>, c->ne, kEdgeThreads);
+    k_edges<KIND, false><<<g, kEdgeThreads, 0, c->stream>>>(c->ne, ev, c->d_vedge, c->d_edge_owned, c->d_edge_flags, c->d_len, P, c->d_stats, c->d_near_edge);
   }
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;
@@ -751,12 +929,12 @@ static int launch_tets(mag_ctx* c, const SweepParams& P, bool fast)
   const int64_t off = c->np + c->npy;
   if (fast) {
     static int per_sm = 0;
-    const unsigned g = persistent_grid(c, per_sm, (const void*)k_tets<KIND, true>, c->nt);
-    k_tets<KIND, true><<<g, kThreads, 0, c->stream>>>(c->nt, off, tv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_owned, c->d_elem_flags, c->d_qual, P, c->d_stats, c->d_near_elem);
+    const unsigned g = persistent_grid(c, per_sm, (const void*)k_tets<KIND, true>, c->nt, kTetThreads);
+    k_tets<KIND, true><<<g, kTetThreads, 0, c->stream>>>(c->nt, off, tv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_owned, c->d_elem_flags, c->d_qual, P, c->d_stats, c->d_near_elem);
   } else {
     static int per_sm = 0;
-    const unsigned g = persistent_grid(c, per_sm, (const void*)k_tets<KIND, false>, c->nt);
-    k_tets<KIND, false><<<g, kThreads, 0, c->stream>>>(c->nt, off, tv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_owned, c->d_elem_flags, c->d_qual, P, c->d_stats, c->d_near_elem);
+    const unsigned g = persistent_grid(c, per_sm, (const void*)k_tets<KIND, false>, c->nt, kTetThreads);
+    k_tets<KIND, false><<<g, kTetThreads, 0, c->stream>>>(c->nt, off, tv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_owned, c->d_elem_flags, c->d_qual, P, c->d_stats, c->d_near_elem);
   }
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;

@@ -36,34 +36,50 @@ __device__ __forceinline__ double edge_iso(const double ra[4], const double rb[4
   return l * (hp + hm) / (2.0 * hp * hm);
 }
 
-// squared metric length of d at one Gauss point with weights (n0w, n1w)
-__device__ __forceinline__ double aniso_point_sq(const double* __restrict__ a, const double* __restrict__ b,
-                                                 double wa, double wb, double dx, double dy, double dz)
+// Unnormalised Gram-Schmidt at one Gauss point, t = interpolation weight of vertex b (c = a + t (b - a)):
+//   X = c0 x c1, N0 = |c0|^2, E = |X|^2, G = c0.c1, A0 = d.c0, A1 = d.c1, D = d.X
+//   Gram-Schmidt frame: r0 = c0/sqrt(N0), r1 = (N0 c1 - G c0)/sqrt(N0^2 E ... ), r2 = X/sqrt(E), so
+//   d^T M d = A0^2/(N0 h0^2) + (N0 A1 - G A0)^2/(N0 E h1^2) + D^2/(E h2^2)
+// brought to the common denominator N0 E (h0 h1 h2)^2.  Returns numerator and denominator (both >= 0);
+// the metric length is sqrt(num/den) = num * rsqrt(num * den).
+__device__ __forceinline__ void aniso_point_nd(const double* __restrict__ a, const double* __restrict__ dl, double t,
+                                               double dx, double dy, double dz, double& num, double& den)
 {
-  double h0 = a[3] * wa + b[3] * wb, h1 = a[4] * wa + b[4] * wb, h2 = a[5] * wa + b[5] * wb;
-  double c0x = a[6] * wa + b[6] * wb, c0y = a[7] * wa + b[7] * wb, c0z = a[8] * wa + b[8] * wb;
-  double c1x = a[9] * wa + b[9] * wb, c1y = a[10] * wa + b[10] * wb, c1z = a[11] * wa + b[11] * wb;
-  double n0 = c0x * c0x + c0y * c0y + c0z * c0z;
-  double g = c0x * c1x + c0y * c1y + c0z * c1z;
-  double px = n0 * c1x - g * c0x, py = n0 * c1y - g * c0y, pz = n0 * c1z - g * c0z;
-  double n1 = px * px + py * py + pz * pz;
-  double wx = c0y * pz - c0z * py, wy = c0z * px - c0x * pz, wz = c0x * py - c0y * px;
-  double a0 = dx * c0x + dy * c0y + dz * c0z;
-  double a1 = dx * px + dy * py + dz * pz;
-  double a2 = dx * wx + dy * wy + dz * wz;
-  double q0 = h1 * h2, q1 = h0 * h2, q2 = h0 * h1, p = q0 * h0;
-  double t0 = a0 * q0, t1 = a1 * q1, t2 = a2 * q2;
-  double num = (t0 * t0) * n1 + (t1 * t1) * n0 + t2 * t2;
-  double den = (n0 * n1) * (p * p);
-  return num / den;
+  const double h0 = fma(t, dl[0], a[3]), h1 = fma(t, dl[1], a[4]), h2 = fma(t, dl[2], a[5]);
+  const double c0x = fma(t, dl[3], a[6]), c0y = fma(t, dl[4], a[7]), c0z = fma(t, dl[5], a[8]);
+  const double c1x = fma(t, dl[6], a[9]), c1y = fma(t, dl[7], a[10]), c1z = fma(t, dl[8], a[11]);
+  const double Xx = c0y * c1z - c0z * c1y, Xy = c0z * c1x - c0x * c1z, Xz = c0x * c1y - c0y * c1x;
+  const double N0 = c0x * c0x + c0y * c0y + c0z * c0z;
+  const double E = Xx * Xx + Xy * Xy + Xz * Xz;
+  const double G = c0x * c1x + c0y * c1y + c0z * c1z;
+  const double A0 = dx * c0x + dy * c0y + dz * c0z;
+  const double A1 = dx * c1x + dy * c1y + dz * c1z;
+  const double D = dx * Xx + dy * Xy + dz * Xz;
+  const double a1 = N0 * A1 - G * A0;
+  const double q0 = h1 * h2, q1 = h0 * h2, q2 = h0 * h1, pp = q0 * h0;
+  const double t0 = A0 * q0, t1 = a1 * q1, t2 = D * q2;
+  num = (t0 * t0) * E + t1 * t1 + (t2 * t2) * N0;
+  den = (N0 * E) * (pp * pp);
+}
+
+// sqrt(num/den) with one reciprocal square root (no IEEE divide / sqrt sequences); exact zero for a zero-length edge
+__device__ __forceinline__ double sqrt_ratio(double num, double den)
+{
+  const double x = num * den;
+  const double r = rsqrt(x);
+  return x > 0.0 ? num * r : 0.0;
 }
 
 __device__ __forceinline__ double edge_aniso(const double* __restrict__ a, const double* __restrict__ b)
 {
-  double dx = b[0] - a[0], dy = b[1] - a[1], dz = b[2] - a[2]; // 2d; the 1/2 is applied at the end
-  double sp = aniso_point_sq(a, b, kNP0, kNP1, dx, dy, dz);
-  double sm = aniso_point_sq(a, b, kNP1, kNP0, dx, dy, dz);
-  return 0.5 * (sqrt(sp) + sqrt(sm));
+  const double dx = b[0] - a[0], dy = b[1] - a[1], dz = b[2] - a[2]; // 2d; the 1/2 is applied at the end
+  double dl[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) dl[i] = b[3 + i] - a[3 + i];
+  double np, dp, nm, dm;
+  aniso_point_nd(a, dl, kNP1, dx, dy, dz, np, dp);  // xi = +XI: weights (kNP0, kNP1)
+  aniso_point_nd(a, dl, kNP0, dx, dy, dz, nm, dm);  // xi = -XI: weights (kNP1, kNP0)
+  return 0.5 * (sqrt_ratio(np, dp) + sqrt_ratio(nm, dm));
 }
 
 // log-Euclidean field: the reference's eigen-solver with FMA contraction allowed
@@ -83,25 +99,31 @@ __device__ __forceinline__ double edge_logm(const double* __restrict__ a, const 
   return len;
 }
 
-// mean ratio cubed with fixed Q: l_i = |e_i Q|, V = det(J) det(Q) / 6
-__device__ __forceinline__ double tet_quality(const V3 x[4], const M3& Q, double detQ)
+// mean ratio cubed with fixed Q, evaluated in metric space: y_i = (x_i - x_0) Q, the six edges are
+// y1, y2, y3, y2-y1, y3-y1, y3-y2 (the reference's 01,12,20,03,13,23 up to sign), V = det[y1;y2;y3] / 6
+// (= det(J) det(Q) / 6).  Differences are taken in physical space first so no accuracy is lost far from the origin.
+__device__ __forceinline__ double tet_quality(const V3 x[4], const M3& Q, double /*detQ*/)
 {
-  const int ea[6] = {0, 1, 2, 0, 1, 2}, eb[6] = {1, 2, 0, 3, 3, 3};
+  double y[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double ex = x[i + 1].x - x[0].x, ey = x[i + 1].y - x[0].y, ez = x[i + 1].z - x[0].z;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) y[i][k] = ex * Q.m[0][k] + ey * Q.m[1][k] + ez * Q.m[2][k];
+  }
   double s = 0;
 #pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    double ex = x[eb[i]].x - x[ea[i]].x, ey = x[eb[i]].y - x[ea[i]].y, ez = x[eb[i]].z - x[ea[i]].z;
-    double r0 = ex * Q.m[0][0] + ey * Q.m[1][0] + ez * Q.m[2][0];
-    double r1 = ex * Q.m[0][1] + ey * Q.m[1][1] + ez * Q.m[2][1];
-    double r2 = ex * Q.m[0][2] + ey * Q.m[1][2] + ez * Q.m[2][2];
-    s += r0 * r0 + r1 * r1 + r2 * r2;
+  for (int i = 0; i < 3; ++i) s += y[i][0] * y[i][0] + y[i][1] * y[i][1] + y[i][2] * y[i][2];
+  const int pa[3] = {0, 0, 1}, pb[3] = {1, 2, 2};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double u = y[pb[i]][0] - y[pa[i]][0], v = y[pb[i]][1] - y[pa[i]][1], w = y[pb[i]][2] - y[pa[i]][2];
+    s += u * u + v * v + w * w;
   }
-  double ax = x[1].x - x[0].x, ay = x[1].y - x[0].y, az = x[1].z - x[0].z;
-  double bx = x[2].x - x[0].x, by = x[2].y - x[0].y, bz = x[2].z - x[0].z;
-  double cx = x[3].x - x[0].x, cy = x[3].y - x[0].y, cz = x[3].z - x[0].z;
-  double detJ = ax * (by * cz - bz * cy) - ay * (bx * cz - bz * cx) + az * (bx * cy - by * cx);
-  double V = detJ * detQ * (1.0 / 6.0);
-  double q = 15552.0 * (V * V) / (s * s * s);
+  const double det = y[0][0] * (y[1][1] * y[2][2] - y[1][2] * y[2][1]) - y[0][1] * (y[1][0] * y[2][2] - y[1][2] * y[2][0]) +
+                     y[0][2] * (y[1][0] * y[2][1] - y[1][1] * y[2][0]);
+  const double V = det * (1.0 / 6.0);
+  const double q = 15552.0 * (V * V) / (s * s * s);
   return V < 0 ? -q : q;
 }
 
