@@ -1,0 +1,194 @@
+// adapter_check.cc -- self-check of the drop-in adapter, callable through ctypes (tests/test_adapter.py, -m gpu).
+// In ONE process it runs, on the same apf::Mesh2 (apf::makeMdsBox, jittered) and the same vertex fields:
+//   (R) the unmodified reference: ma::makeSizeField + ma::markEdgesToSplit / markEdgesToCollapse / markBadQuality /
+//       getMinQuality / getMaximumEdgeLength;
+//   (A) the adapter's bulk entry points mag::markEdgesToSplit ... on a mag::GpuSizeField;
+//   (B) the UNMODIFIED reference functions again, but with the mag::GpuSizeField / mag::shapeHandler plugged into
+//       ma::Input -- the per-entity virtuals are then served from one device sweep (sweep detection);
+// and reports every difference in flags, counts and statistics.  Test infrastructure; it ships in libmag_ma.so only so
+// that the GPU box (which has no /root/reference) can run it from the prebuilt library.
+#include "magAdapt.h"
+#include "../../include/mag.h"
+#include <ma.h>
+#include <maAdapt.h>
+#include <maRefine.h>
+#include <maShape.h>
+#include <apfMDS.h>
+#include <apfBox.h>
+#include <apfMesh2.h>
+#include <apf.h>
+#include <gmi_null.h>
+#include <gmi_mesh.h>
+#include <lionPrint.h>
+#include <PCU.h>
+#include <cmath>
+#include <vector>
+
+namespace ma {
+/* external linkage, no header in the reference (maCoarsen.cc:287, maShape.cc:132,152) */
+long markEdgesToCollapse(Adapt* a);
+int markBadQuality(Adapt* a);
+double getMinQuality(Adapt* a);
+}
+
+namespace {
+
+pcu::PCU* g_pcu = 0;
+void ensure_pcu()
+{
+  if (g_pcu) return;
+  int argc = 0; char** argv = 0;
+  pcu::Init(&argc, &argv);
+  g_pcu = new pcu::PCU;
+  lion_set_verbosity(0);
+  gmi_register_null();
+  gmi_register_mesh();
+}
+
+struct Fields { apf::Field* sizes; apf::Field* frames; };
+
+Fields make_fields(apf::Mesh2* m, const char* tag, double hbar)
+{
+  Fields f;
+  f.sizes = apf::createFieldOn(m, (std::string("sizes_") + tag).c_str(), apf::VECTOR);
+  f.frames = apf::createFieldOn(m, (std::string("frames_") + tag).c_str(), apf::MATRIX);
+  apf::MeshIterator* it = m->begin(0);
+  apf::MeshEntity* v;
+  while ((v = m->iterate(it))) {
+    apf::Vector3 p;
+    m->getPoint(v, 0, p);
+    /* rotating shock layer of BASELINE config 3: R = Rz(pi/3 y), H = (hbar (0.1 + 2 |x' - 0.5|), hbar, 2 hbar) */
+    double th = (M_PI / 3.0) * p[1], c = cos(th), s = sin(th);
+    apf::Matrix3x3 R(c, -s, 0, s, c, 0, 0, 0, 1);
+    double xp = p[0] * c + p[1] * s;
+    apf::Vector3 h(hbar * (0.1 + 2.0 * fabs(xp - 0.5)), hbar, 2.0 * hbar);
+    apf::setVector(f.sizes, v, 0, h);
+    apf::setMatrix(f.frames, v, 0, R);
+  }
+  m->end(it);
+  return f;
+}
+
+struct Marks {
+  std::vector<int> ef, lf;
+  long n_split, n_collapse; int n_bad; double min_q, max_len;
+};
+
+void collect_flags(ma::Adapt* a, Marks& k)
+{
+  apf::Mesh2* m = a->mesh;
+  apf::MeshIterator* it = m->begin(1); apf::MeshEntity* e;
+  k.ef.clear(); k.lf.clear();
+  while ((e = m->iterate(it))) k.ef.push_back(ma::getFlags(a, e));
+  m->end(it);
+  it = m->begin(3);
+  while ((e = m->iterate(it))) k.lf.push_back(ma::getFlags(a, e));
+  m->end(it);
+}
+
+long diff(const std::vector<int>& a, const std::vector<int>& b)
+{
+  if (a.size() != b.size()) return -1;
+  long n = 0;
+  for (size_t i = 0; i < a.size(); ++i) n += a[i] != b[i];
+  return n;
+}
+
+} // namespace
+
+/* report[0..4]  reference: n_split n_collapse n_bad min_q max_len
+   report[5..9]  adapter bulk (A), report[10..14] unmodified reference loops over the adapter (B)
+   report[15..18] flag words differing: A edges, A elems, B edges, B elems;  report[19] sweeps the adapter ran for B
+   returns 0 when A and B reproduce the reference exactly (fp_mode strict) / flags+counts exactly, values 1e-12 (fast). */
+extern "C" int mag_adapter_check(int n, int log_interp, int fp_mode, double jitter, double* report)
+{
+  ensure_pcu();
+  apf::Mesh2* m = apf::makeMdsBox(n, n, n, 1, 1, 1, true, g_pcu);
+  if (jitter > 0) {
+    unsigned long long s = 12345;
+    apf::MeshIterator* it = m->begin(0); apf::MeshEntity* v;
+    while ((v = m->iterate(it))) {
+      apf::Vector3 p; m->getPoint(v, 0, p);
+      bool interior = true;
+      for (int i = 0; i < 3; ++i) interior = interior && p[i] > 1e-9 && p[i] < 1 - 1e-9;
+      for (int i = 0; i < 3; ++i) {
+        s = s * 6364136223846793005ULL + 1442695040888963407ULL;
+        double u = (double)(s >> 11) / 9007199254740992.0;
+        if (interior) p[i] += jitter / n * (u - 0.5);
+      }
+      m->setPoint(v, 0, p);
+    }
+    m->end(it);
+  }
+  const double hbar = 1.0 / n;
+  Marks R, A, B;
+  { /* (R) the unmodified reference */
+    Fields f = make_fields(m, "ref", hbar);
+    ma::SizeField* sf = ma::makeSizeField(m, f.sizes, f.frames, log_interp != 0);
+    ma::Input* in = ma::makeAdvanced(ma::configureIdentity(m, sf));
+    {
+      ma::Adapt a(in);
+      R.n_split = ma::markEdgesToSplit(&a);
+      R.n_collapse = ma::markEdgesToCollapse(&a);
+      R.n_bad = ma::markBadQuality(&a);
+      R.min_q = ma::getMinQuality(&a);
+      collect_flags(&a, R);
+    }
+    R.max_len = ma::getMaximumEdgeLength(m, sf);
+    delete in;
+    delete sf; /* destroys (Aniso) or leaves (LogAniso) the input fields */
+    if (log_interp) { apf::destroyField(f.sizes); apf::destroyField(f.frames); }
+  }
+  Fields f = make_fields(m, "gpu", hbar);
+  mag::GpuSizeField* g = mag::makeSizeField(m, f.sizes, f.frames, log_interp != 0, 0);
+  g->setArithmetic(fp_mode);
+  { /* (A) the adapter's bulk entry points */
+    ma::Input* in = ma::makeAdvanced(ma::configureIdentity(m, g));
+    in->shapeHandler = mag::shapeHandler;
+    {
+      ma::Adapt a(in);
+      A.n_split = mag::markEdgesToSplit(&a);
+      A.n_collapse = mag::markEdgesToCollapse(&a);
+      A.n_bad = mag::markBadQuality(&a);
+      A.min_q = mag::getMinQuality(&a);
+      collect_flags(&a, A);
+    }
+    A.max_len = mag::getMaximumEdgeLength(m, g);
+    delete in;
+  }
+  long sweeps0 = mag_launch_count(g->ctx);
+  { /* (B) the unmodified reference loops, adapter plugged in through ma::Input */
+    ma::Input* in = ma::makeAdvanced(ma::configureIdentity(m, g));
+    in->shapeHandler = mag::shapeHandler;
+    {
+      ma::Adapt a(in);
+      B.n_split = ma::markEdgesToSplit(&a);
+      B.n_collapse = ma::markEdgesToCollapse(&a);
+      B.n_bad = ma::markBadQuality(&a);
+      B.min_q = ma::getMinQuality(&a);
+      collect_flags(&a, B);
+    }
+    B.max_len = ma::getMaximumEdgeLength(m, g);
+    delete in;
+  }
+  report[19] = (double)(mag_launch_count(g->ctx) - sweeps0);
+  delete g;
+  if (log_interp) { apf::destroyField(f.sizes); apf::destroyField(f.frames); }
+  m->destroyNative();
+  apf::destroyMesh(m);
+  const Marks* k[3] = {&R, &A, &B};
+  for (int i = 0; i < 3; ++i) {
+    report[5 * i] = (double)k[i]->n_split; report[5 * i + 1] = (double)k[i]->n_collapse; report[5 * i + 2] = k[i]->n_bad;
+    report[5 * i + 3] = k[i]->min_q; report[5 * i + 4] = k[i]->max_len;
+  }
+  report[15] = (double)diff(R.ef, A.ef); report[16] = (double)diff(R.lf, A.lf);
+  report[17] = (double)diff(R.ef, B.ef); report[18] = (double)diff(R.lf, B.lf);
+  int bad = 0;
+  for (int i = 1; i < 3; ++i) {
+    bad |= k[i]->n_split != R.n_split || k[i]->n_collapse != R.n_collapse || k[i]->n_bad != R.n_bad;
+    const double tol = (fp_mode == MAG_FP_STRICT && !log_interp) ? 0.0 : 1e-12;
+    bad |= fabs(k[i]->min_q - R.min_q) > tol * fabs(R.min_q) || fabs(k[i]->max_len - R.max_len) > tol * R.max_len;
+  }
+  for (int i = 15; i < 19; ++i) bad |= report[i] != 0;
+  return bad;
+}

@@ -1,0 +1,428 @@
+// magAdapt.cc -- see magAdapt.h.  Builds against the reference's headers; everything numeric happens behind the
+// C ABI of include/mag.h on the GPU.  The wrapped reference ma::SizeField is only consulted for entities that are
+// not part of a device sweep (cavity operators on freshly created entities) -- the rest of the reference running
+// as before, not a fallback of the sweep.
+#include "magAdapt.h"
+#include "../../include/mag.h"
+#include <maAdapt.h>
+#include <maShapeHandler.h>
+#include <maShape.h>
+#include <apfMDS.h>
+#include <apfMesh2.h>
+#include <apfShape.h>
+#include <apf.h>
+#include <pcu_util.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+
+namespace mag {
+
+static void fail(mag_ctx* c, const char* what, int rc)
+{
+  fprintf(stderr, "mag adapter: %s failed (%d): %s\n", what, rc, mag_last_error(c));
+  abort(); /* the reference's convention: PCU_ALWAYS_ASSERT -> abort (pcu_util.h:44-69) */
+}
+#define MAG_DO(c, call) do { int rc_ = (call); if (rc_) fail((c), #call, rc_); } while (0)
+
+struct Export {
+  std::vector<double> xyz, ma, mb;
+  std::vector<int> edge_v, tet_v, prism_v, pyr_v;
+  std::vector<unsigned char> edge_owned, elem_owned;
+  std::vector<ma::Entity*> edges, elems; /* iteration order; elems = prisms | pyramids | tets */
+};
+
+struct Access {
+  static GpuSizeField* create() { return new GpuSizeField(); }
+  static void init(GpuSizeField* g, int kind, int logVariant, apf::Field* sizes, apf::Field* frames, apf::Field* iso,
+                   ma::AnisotropicFunction* fa, ma::IsotropicFunction* fi)
+  {
+    g->kind = kind; g->logVariant = logVariant;
+    g->fSizes = sizes; g->fFrames = frames; g->fIso = iso; g->fnAniso = fa; g->fnIso = fi;
+  }
+  static double lengthAt(GpuSizeField* g, size_t k) { return g->lengths[k]; }
+  static double qualityOf(GpuSizeField* g, ma::Entity* e) { return g->qualities[g->tetSlot[apf::getMdsIndex(g->mesh, e)]]; }
+  static bool serveQuality(GpuSizeField* g, ma::Entity* e, double goodQuality, double& q)
+  {
+    int slot;
+    g->lastGoodQuality = goodQuality;
+    if (!g->serve(e, 3, slot)) return false;
+    q = g->qualities[slot];
+    return true;
+  }
+
+  /* one pass over the mesh in m->begin(d) order (mds.c:745-777), vertex ids compacted to 0..nv-1 */
+  static void exportMesh(GpuSizeField* g, Export& x)
+  {
+    ma::Mesh* m = g->mesh;
+    if (m->getDimension() != 3) { fprintf(stderr, "mag adapter: only 3D meshes are supported\n"); abort(); }
+    size_t nv = m->count(0);
+    std::vector<int> vslot;
+    x.xyz.resize(3 * nv);
+    if (g->kind == 1) x.ma.resize(nv);
+    else { x.ma.resize(3 * nv); x.mb.resize(9 * nv); }
+    apf::MeshIterator* it = m->begin(0);
+    ma::Entity* e;
+    int k = 0;
+    while ((e = m->iterate(it))) {
+      int id = apf::getMdsIndex(m, e);
+      if ((size_t)id >= vslot.size()) vslot.resize((size_t)id + 1 + vslot.size() / 2, -1);
+      vslot[id] = k;
+      ma::Vector p;
+      m->getPoint(e, 0, p);
+      x.xyz[3 * k] = p[0]; x.xyz[3 * k + 1] = p[1]; x.xyz[3 * k + 2] = p[2];
+      if (g->kind == 1) {
+        x.ma[k] = g->fnIso ? g->fnIso->getValue(e) : apf::getScalar(g->fIso, e, 0);
+      } else {
+        ma::Matrix R; ma::Vector h;
+        if (g->fnAniso) g->fnAniso->getValue(e, R, h);
+        else { apf::getVector(g->fSizes, e, 0, h); apf::getMatrix(g->fFrames, e, 0, R); }
+        for (int i = 0; i < 3; ++i) x.ma[3 * k + i] = h[i];
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) x.mb[9 * k + 3 * i + j] = R[i][j];
+      }
+      ++k;
+    }
+    m->end(it);
+    size_t ne = m->count(1);
+    x.edge_v.resize(2 * ne); x.edge_owned.resize(ne); x.edges.resize(ne);
+    g->edgeSlot.assign(g->edgeSlot.size(), -1);
+    it = m->begin(1); k = 0;
+    while ((e = m->iterate(it))) {
+      apf::Downward dv;
+      m->getDownward(e, 0, dv);
+      x.edge_v[2 * k] = vslot[apf::getMdsIndex(m, dv[0])];
+      x.edge_v[2 * k + 1] = vslot[apf::getMdsIndex(m, dv[1])];
+      x.edge_owned[k] = m->isOwned(e) ? 1 : 0;
+      x.edges[k] = e;
+      int id = apf::getMdsIndex(m, e);
+      if ((size_t)id >= g->edgeSlot.size()) g->edgeSlot.resize((size_t)id + 1 + g->edgeSlot.size() / 2, -1);
+      g->edgeSlot[id] = k;
+      ++k;
+    }
+    m->end(it);
+    /* dimension 3 iterates prisms, pyramids, tets (MDS type order, mds.h:16-26) */
+    std::vector<ma::Entity*> pr, py, te;
+    it = m->begin(3);
+    while ((e = m->iterate(it))) {
+      int t = m->getType(e);
+      if (t == apf::Mesh::PRISM) pr.push_back(e);
+      else if (t == apf::Mesh::PYRAMID) py.push_back(e);
+      else if (t == apf::Mesh::TET) te.push_back(e);
+      else { fprintf(stderr, "mag adapter: element type %d is not supported\n", t); abort(); }
+    }
+    m->end(it);
+    x.elems.clear();
+    x.elems.insert(x.elems.end(), pr.begin(), pr.end());
+    x.elems.insert(x.elems.end(), py.begin(), py.end());
+    x.elems.insert(x.elems.end(), te.begin(), te.end());
+    g->nNonSimplex = (long)(pr.size() + py.size());
+    x.elem_owned.resize(x.elems.size());
+    auto conn = [&](std::vector<ma::Entity*>& v, int n, std::vector<int>& out) {
+      out.resize(v.size() * n);
+      for (size_t i = 0; i < v.size(); ++i) {
+        apf::Downward dv;
+        m->getDownward(v[i], 0, dv);
+        for (int j = 0; j < n; ++j) out[i * n + j] = vslot[apf::getMdsIndex(m, dv[j])];
+      }
+    };
+    conn(pr, 6, x.prism_v); conn(py, 5, x.pyr_v); conn(te, 4, x.tet_v);
+    g->tetSlot.assign(g->tetSlot.size(), -1);
+    for (size_t i = 0; i < te.size(); ++i) {
+      int id = apf::getMdsIndex(m, te[i]);
+      if ((size_t)id >= g->tetSlot.size()) g->tetSlot.resize((size_t)id + 1 + g->tetSlot.size() / 2, -1);
+      g->tetSlot[id] = (int)(g->nNonSimplex + i);
+    }
+    for (size_t i = 0; i < x.elems.size(); ++i) x.elem_owned[i] = m->isOwned(x.elems[i]) ? 1 : 0;
+  }
+
+  static void upload(GpuSizeField* g, Export& x)
+  {
+    mag_ctx* c = g->ctx;
+    MAG_DO(c, mag_set_mesh(c, (int64_t)(x.xyz.size() / 3), x.xyz.data(), (int64_t)x.edges.size(), x.edge_v.data(),
+                           (int64_t)(x.tet_v.size() / 4), x.tet_v.data(), (int64_t)(x.prism_v.size() / 6), x.prism_v.data(),
+                           (int64_t)(x.pyr_v.size() / 5), x.pyr_v.data(), x.edge_owned.data(), x.elem_owned.data()));
+    if (g->kind == 1) MAG_DO(c, mag_set_metric_iso(c, x.ma.data()));
+    else if (g->kind == 2) MAG_DO(c, mag_set_metric_aniso(c, x.ma.data(), x.mb.data()));
+    else MAG_DO(c, mag_set_metric_logm_from_frames(c, x.ma.data(), x.mb.data(), g->logVariant, 0));
+    MAG_DO(c, mag_synchronize(c));
+  }
+
+  static int readFlags(ma::Mesh* m, ma::Tag* tag, ma::Entity* e)
+  {
+    /* ma::getFlags (maAdapt.cc:80-88): 0 when the entity has no tag */
+    if (!m->hasTag(e, tag)) return 0;
+    int f;
+    m->getIntTag(e, tag, &f);
+    return f;
+  }
+
+  /* one device sweep with the incoming "ma_flags" words of the Adapt; writes the changed words back.  Returns stats. */
+  static mag_stats sweepWithAdaptFlags(GpuSizeField* g, ma::Adapt* a, unsigned ops)
+  {
+    Export x;
+    exportMesh(g, x);
+    upload(g, x);
+    ma::Mesh* m = g->mesh;
+    std::vector<int> ef(x.edges.size()), lf(x.elems.size());
+    for (size_t i = 0; i < x.edges.size(); ++i) ef[i] = readFlags(m, a->flagsTag, x.edges[i]);
+    for (size_t i = 0; i < x.elems.size(); ++i) lf[i] = readFlags(m, a->flagsTag, x.elems[i]);
+    mag_ctx* c = g->ctx;
+    MAG_DO(c, mag_set_flags(c, ef.data(), lf.data()));
+    MAG_DO(c, mag_sweep(c, ops, ma::MAXLENGTH, ma::MINLENGTH, a->input->goodQuality, 1, g->fpMode));
+    mag_stats st;
+    MAG_DO(c, mag_get_stats(c, &st)); /* MAG_ERR_FLAG_STATE here == the reference's assert at maAdapt.cc:308 */
+    std::vector<int> ef2(ef.size()), lf2(lf.size());
+    MAG_DO(c, mag_get_flags(c, ef2.data(), lf2.data()));
+    for (size_t i = 0; i < ef.size(); ++i) if (ef2[i] != ef[i]) ma::setFlags(a, x.edges[i], ef2[i]);
+    for (size_t i = 0; i < lf.size(); ++i) if (lf2[i] != lf[i]) ma::setFlags(a, x.elems[i], lf2[i]);
+    g->dirty = true; /* the per-entity snapshot (zero incoming flags) was not refreshed by this sweep */
+    return st;
+  }
+};
+
+GpuSizeField::GpuSizeField()
+  : mesh(0), wrapped(0), ctx(0), kind(0), logVariant(0), fpMode(MAG_FP_STRICT), dirty(true), streak(0), lastGoodQuality(-1),
+    fSizes(0), fFrames(0), fIso(0), fnAniso(0), fnIso(0), nNonSimplex(0), lastDim(-1), lastId(-1)
+{
+}
+
+GpuSizeField::~GpuSizeField()
+{
+  if (ctx) mag_destroy(ctx);
+  delete wrapped; /* like the reference: an AnisoSizeField destroys the fields it was built from (maSize.cc:385-389) */
+}
+
+struct Maker {
+  static GpuSizeField* make(ma::Mesh* m, ma::SizeField* wrapped, int kind, int logVariant, apf::Field* sizes,
+                            apf::Field* frames, apf::Field* iso, ma::AnisotropicFunction* fa, ma::IsotropicFunction* fi,
+                            int device);
+};
+
+/* ------------------------------------------------------------------ per-entity service */
+bool GpuSizeField::serve(ma::Entity* e, int dim, int& slot)
+{
+  /* A whole-mesh sweep by the unmodified reference (markEntities, getMaximumEdgeLength, ma::stats) shows up as a long run
+     of per-entity queries in mesh iteration order (increasing MDS index of one type) with no size-field callback and no
+     change of the entity counts in between.  Only such a run is answered from a device sweep: kSweepDetect queries into
+     it the mesh is exported and swept ONCE, and the rest of the run is served from that snapshot.  Anything else -- an
+     out-of-order query, a callback, a changed count: a cavity operator at work -- goes to the wrapped reference field. */
+  const int id = apf::getMdsIndex(mesh, e);
+  const bool in_order = (dim == lastDim && id > lastId);
+  lastDim = dim;
+  lastId = id;
+  if (!in_order) { dirty = true; streak = 0; return false; }
+  if (!dirty && ((long)mesh->count(1) != (long)lengths.size() || (long)mesh->count(3) != (long)qualities.size())) dirty = true;
+  if (dirty) {
+    if (++streak < kSweepDetect) return false;
+    refresh(lastGoodQuality);
+  }
+  const std::vector<int>& map = dim == 1 ? edgeSlot : tetSlot;
+  if ((size_t)id >= map.size()) return false;
+  slot = map[id];
+  return slot >= 0;
+}
+
+void GpuSizeField::refresh(double goodQuality)
+{
+  Export x;
+  Access::exportMesh(this, x);
+  Access::upload(this, x);
+  mag_ctx* c = ctx;
+  MAG_DO(c, mag_set_flags(c, 0, 0));
+  unsigned ops = MAG_OP_LENGTHS | MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE | MAG_OP_QUALITIES;
+  /* non-simplex elements never reach a quality predicate here: only tets are marked */
+  MAG_DO(c, mag_sweep(c, ops, ma::MAXLENGTH, ma::MINLENGTH, goodQuality < 0 ? 0.0 : goodQuality, 1, fpMode));
+  mag_stats st;
+  MAG_DO(c, mag_get_stats(c, &st));
+  lengths.resize(x.edges.size());
+  qualities.resize(x.elems.size());
+  edgeFlags.resize(x.edges.size());
+  elemFlags.resize(x.elems.size());
+  MAG_DO(c, mag_get_edge_lengths(c, lengths.data()));
+  MAG_DO(c, mag_get_qualities(c, qualities.data()));
+  MAG_DO(c, mag_get_flags(c, edgeFlags.data(), elemFlags.data()));
+  lastGoodQuality = goodQuality;
+  dirty = false;
+  streak = 0;
+}
+
+double GpuSizeField::measure(ma::Entity* e)
+{
+  int slot;
+  if (mesh->getType(e) == apf::Mesh::EDGE && serve(e, 1, slot)) return lengths[slot];
+  return wrapped->measure(e);
+}
+bool GpuSizeField::shouldSplit(ma::Entity* edge)
+{
+  int slot;
+  if (serve(edge, 1, slot)) return (edgeFlags[slot] & MAG_SPLIT) != 0;
+  return wrapped->shouldSplit(edge);
+}
+bool GpuSizeField::shouldCollapse(ma::Entity* edge)
+{
+  int slot;
+  if (serve(edge, 1, slot)) return (edgeFlags[slot] & MAG_COLLAPSE) != 0;
+  return wrapped->shouldCollapse(edge);
+}
+/* everything below is a mesh-modification-time call: the snapshot is no longer trusted afterwards */
+void GpuSizeField::interpolate(apf::MeshElement* parent, ma::Vector const& xi, ma::Entity* newVert)
+{
+  dirty = true; streak = 0;
+  wrapped->interpolate(parent, xi, newVert);
+}
+void GpuSizeField::getTransform(apf::MeshElement* e, ma::Vector const& xi, ma::Matrix& t)
+{
+  dirty = true; streak = 0;
+  wrapped->getTransform(e, xi, t);
+}
+double GpuSizeField::getWeight(ma::Entity* e)
+{
+  dirty = true; streak = 0;
+  return wrapped->getWeight(e);
+}
+void GpuSizeField::onRefine(ma::Entity* parent, ma::EntityArray& newEntities)
+{
+  dirty = true; streak = 0;
+  wrapped->onRefine(parent, newEntities);
+}
+void GpuSizeField::onCavity(ma::EntityArray& oldElements, ma::EntityArray& newEntities)
+{
+  dirty = true; streak = 0;
+  wrapped->onCavity(oldElements, newEntities);
+}
+int GpuSizeField::getTransferDimension() { return wrapped->getTransferDimension(); }
+bool GpuSizeField::hasNodesOn(int dimension) { return wrapped->hasNodesOn(dimension); }
+
+/* ------------------------------------------------------------------ construction */
+GpuSizeField* Maker::make(ma::Mesh* m, ma::SizeField* wrapped, int kind, int logVariant, apf::Field* sizes,
+                          apf::Field* frames, apf::Field* iso, ma::AnisotropicFunction* fa, ma::IsotropicFunction* fi,
+                          int device)
+{
+  GpuSizeField* g = Access::create();
+  g->mesh = m;
+  g->wrapped = wrapped;
+  Access::init(g, kind, logVariant, sizes, frames, iso, fa, fi);
+  mag_ctx* c = 0;
+  int rc = mag_create(&c, device);
+  if (rc) fail(0, "mag_create", rc);
+  g->ctx = c;
+  return g;
+}
+
+GpuSizeField* makeSizeField(ma::Mesh* m, apf::Field* sizes, apf::Field* frames, bool logInterpolation, int device)
+{
+  /* LogAnisoSizeField::init builds ma_logM from the two fields (maSize.cc:491-499): variant 0 */
+  return Maker::make(m, ma::makeSizeField(m, sizes, frames, logInterpolation), logInterpolation ? 3 : 2, 0, sizes, frames, 0, 0, 0, device);
+}
+GpuSizeField* makeSizeField(ma::Mesh* m, ma::AnisotropicFunction* f, bool logInterpolation, int device)
+{
+  /* LogMEval evaluates -2 log(h) per vertex (maSize.cc:343-346): variant 1 */
+  return Maker::make(m, ma::makeSizeField(m, f, logInterpolation), logInterpolation ? 3 : 2, 1, 0, 0, 0, f, 0, device);
+}
+GpuSizeField* makeSizeField(ma::Mesh* m, apf::Field* size, int device)
+{
+  return Maker::make(m, ma::makeSizeField(m, size), 1, 0, 0, 0, size, 0, 0, device);
+}
+GpuSizeField* makeSizeField(ma::Mesh* m, ma::IsotropicFunction* f, int device)
+{
+  return Maker::make(m, ma::makeSizeField(m, f), 1, 0, 0, 0, 0, 0, f, device);
+}
+
+/* ------------------------------------------------------------------ bulk sweeps */
+static GpuSizeField* gpuField(ma::SizeField* sf)
+{
+  GpuSizeField* g = dynamic_cast<GpuSizeField*>(sf);
+  if (!g) { fprintf(stderr, "mag adapter: the size field is not a mag::GpuSizeField\n"); abort(); }
+  return g;
+}
+
+long markEdgesToSplit(ma::Adapt* a)
+{
+  GpuSizeField* g = gpuField(a->sizeField);
+  mag_stats st = Access::sweepWithAdaptFlags(g, a, MAG_OP_MARK_SPLIT);
+  return a->mesh->getPCU()->Add<long>((long)st.n_split); /* maAdapt.cc:323 */
+}
+long markEdgesToCollapse(ma::Adapt* a)
+{
+  GpuSizeField* g = gpuField(a->sizeField);
+  mag_stats st = Access::sweepWithAdaptFlags(g, a, MAG_OP_MARK_COLLAPSE);
+  return a->mesh->getPCU()->Add<long>((long)st.n_collapse);
+}
+int markBadQuality(ma::Adapt* a)
+{
+  GpuSizeField* g = gpuField(a->sizeField);
+  mag_stats st = Access::sweepWithAdaptFlags(g, a, MAG_OP_MARK_BAD);
+  return (int)a->mesh->getPCU()->Add<long>((long)st.n_bad);
+}
+double getMinQuality(ma::Adapt* a)
+{
+  GpuSizeField* g = gpuField(a->sizeField);
+  mag_stats st = Access::sweepWithAdaptFlags(g, a, MAG_OP_QUALITIES);
+  return a->mesh->getPCU()->Min<double>(st.min_quality); /* maShape.cc:168 */
+}
+double getMaximumEdgeLength(ma::Mesh* m, ma::SizeField* sf)
+{
+  GpuSizeField* g = gpuField(sf);
+  g->refresh(-1);
+  mag_stats st;
+  MAG_DO(g->ctx, mag_get_stats(g->ctx, &st));
+  return m->getPCU()->Max<double>(st.max_length); /* maSize.cc:689 */
+}
+void getEdgeLengthsInMetricSpace(ma::Mesh* m, ma::SizeField* sf, std::vector<double>& out)
+{
+  GpuSizeField* g = gpuField(sf);
+  g->refresh(-1);
+  /* ma::stats keeps owned edges only, iteration order (maStats.cc:33-45) */
+  out.clear();
+  apf::MeshIterator* it = m->begin(1);
+  ma::Entity* e;
+  size_t k = 0;
+  while ((e = m->iterate(it))) { if (m->isOwned(e)) out.push_back(Access::lengthAt(g, k)); ++k; }
+  m->end(it);
+}
+void getLinearQualitiesInMetricSpace(ma::Mesh* m, ma::SizeField* sf, std::vector<double>& out)
+{
+  GpuSizeField* g = gpuField(sf);
+  g->refresh(-1);
+  /* owned simplex elements, cbrt of the mean ratio cubed (maStats.cc:12-31) */
+  out.clear();
+  apf::MeshIterator* it = m->begin(3);
+  ma::Entity* e;
+  while ((e = m->iterate(it))) {
+    if (m->getType(e) != apf::Mesh::TET || !m->isOwned(e)) continue;
+    out.push_back(cbrt(Access::qualityOf(g, e)));
+  }
+  m->end(it);
+}
+
+/* ------------------------------------------------------------------ shape handler */
+class GpuShapeHandler : public ma::ShapeHandler
+{
+  public:
+    GpuShapeHandler(ma::Adapt* a_) : a(a_), inner(ma::getShapeHandler(a_)) {}
+    ~GpuShapeHandler() { delete inner; }
+    double getQuality(ma::Entity* e)
+    {
+      GpuSizeField* g = dynamic_cast<GpuSizeField*>(a->sizeField);
+      double q;
+      if (g && a->mesh->getType(e) == apf::Mesh::TET) {
+        if (Access::serveQuality(g, e, a->input->goodQuality, q)) return q;
+        /* LinearHandler::getQuality (maShapeHandler.cc:27-30) on the wrapped reference field */
+        if (a->mesh->getShape()->getOrder() == 1) return ma::measureElementQuality(a->mesh, g->wrapped, e);
+      }
+      return inner->getQuality(e);
+    }
+    /* SolutionTransfer interface: the linear handler's behaviour, unchanged */
+    bool hasNodesOn(int dimension) { return inner->hasNodesOn(dimension); }
+    void onVertex(apf::MeshElement* parent, ma::Vector const& xi, ma::Entity* vert) { inner->onVertex(parent, xi, vert); }
+    void onRefine(ma::Entity* parent, ma::EntityArray& newEntities) { inner->onRefine(parent, newEntities); }
+    void onCavity(ma::EntityArray& oldElements, ma::EntityArray& newEntities) { inner->onCavity(oldElements, newEntities); }
+    int getTransferDimension() { return inner->getTransferDimension(); }
+  private:
+    ma::Adapt* a;
+    ma::ShapeHandler* inner;
+};
+
+ma::ShapeHandler* shapeHandler(ma::Adapt* a) { return new GpuShapeHandler(a); }
+
+}

@@ -1,0 +1,101 @@
+// magAdapt.h -- C++ drop-in adapter between SCOREC/core's MeshAdapt and the mag C ABI (include/mag.h).
+//
+// Host side of the boundary, written in the reference's own language against the reference's own headers
+// (ma/maSize.h, ma/maAdapt.h, ma/maShapeHandler.h, apf/apfMesh2.h, mds/apfMDS.h).  It replaces, for whole-mesh sweeps:
+//
+//   ma::makeSizeField(...)            ma/maSize.h:108-113   ->  mag::makeSizeField(...)  (same overloads, + CUDA device)
+//   ma::markEdgesToSplit(Adapt*)      ma/maRefine.cc:395    ->  mag::markEdgesToSplit(Adapt*)
+//   ma::markEdgesToCollapse(Adapt*)   ma/maCoarsen.cc:287   ->  mag::markEdgesToCollapse(Adapt*)
+//   ma::markBadQuality(Adapt*)        ma/maShape.cc:132     ->  mag::markBadQuality(Adapt*)
+//   ma::getMinQuality(Adapt*)         ma/maShape.cc:152     ->  mag::getMinQuality(Adapt*)
+//   ma::getMaximumEdgeLength(m, sf)   ma/maSize.cc:673      ->  mag::getMaximumEdgeLength(m, sf)
+//   ma::getEdgeLengthsInMetricSpace / getLinearQualitiesInMetricSpace   ma/maStats.cc:12-45  ->  mag::... (same vectors)
+//   ma::getShapeHandler(Adapt*)       ma/maShapeHandler.cc  ->  mag::shapeHandler  (an ma::ShapeHandlerFunction for Input::shapeHandler)
+//
+// mag::GpuSizeField IS an ma::SizeField: it can be put in ma::Input::sizeField and the UNMODIFIED reference keeps
+// working -- the per-entity virtuals (measure / shouldSplit / shouldCollapse) are answered from the last device sweep
+// while the mesh is unchanged, and delegated to the wrapped reference size field (the rest of the reference running as
+// before) for entities created since.  A sweep over the whole mesh by the unmodified ma::markEntities loop is detected
+// after kSweepDetect consecutive per-entity queries without an intervening mesh change and turned into ONE device
+// sweep.  Error convention: like the reference, failures abort through PCU-style fail-fast (mag::fail prints the
+// mag_last_error text and calls abort()).
+#ifndef MAG_ADAPT_H
+#define MAG_ADAPT_H
+
+#include <maSize.h>
+#include <maInput.h>
+#include <vector>
+
+struct mag_ctx;
+namespace ma { class Adapt; class ShapeHandler; }
+
+namespace mag {
+
+class GpuSizeField : public ma::SizeField
+{
+  public:
+    ~GpuSizeField();
+    /* ma::SizeField */
+    double measure(ma::Entity* e);
+    bool shouldSplit(ma::Entity* edge);
+    bool shouldCollapse(ma::Entity* edge);
+    void interpolate(apf::MeshElement* parent, ma::Vector const& xi, ma::Entity* newVert);
+    void getTransform(apf::MeshElement* e, ma::Vector const& xi, ma::Matrix& t);
+    double getWeight(ma::Entity* e);
+    void onRefine(ma::Entity* parent, ma::EntityArray& newEntities);
+    void onCavity(ma::EntityArray& oldElements, ma::EntityArray& newEntities);
+    int getTransferDimension();
+    bool hasNodesOn(int dimension);
+
+    /* the mesh or the field changed behind our back (e.g. coordinates moved by the caller) */
+    void invalidate() { dirty = true; }
+    /* MAG_FP_STRICT (default) or MAG_FP_FAST, see include/mag.h */
+    void setArithmetic(int fp_mode) { fpMode = fp_mode; invalidate(); }
+    /* re-export the mesh + field and run one full device sweep now */
+    void refresh(double goodQuality = -1);
+
+    ma::Mesh* mesh;
+    ma::SizeField* wrapped;  /* the reference size field built from the same inputs (owned) */
+    mag_ctx* ctx;
+
+  private:
+    friend struct Access;
+    GpuSizeField();
+    enum { kSweepDetect = 4096 };
+    int kind;        /* 1 iso, 2 aniso, 3 logm */
+    int logVariant;  /* 0 fields (maSize.cc:491-499), 1 user function (maSize.cc:343-346) */
+    int fpMode;
+    bool dirty;
+    long streak;     /* consecutive per-entity sweep-like queries since the last mesh change */
+    double lastGoodQuality;
+    apf::Field* fSizes; apf::Field* fFrames; apf::Field* fIso;
+    ma::AnisotropicFunction* fnAniso; ma::IsotropicFunction* fnIso;
+    std::vector<int> edgeSlot, tetSlot;           /* MDS index -> position in the exported arrays (-1: not exported) */
+    std::vector<double> lengths, qualities;       /* host copies of the last sweep */
+    std::vector<int> edgeFlags, elemFlags;        /* flags of the last sweep run on zero incoming words */
+    long nNonSimplex;
+    int lastDim, lastId;  /* last per-entity query: dimension and MDS index */
+    bool serve(ma::Entity* e, int dim, int& slot);
+};
+
+/* same overloads as ma::makeSizeField (ma/maSize.h:108-113) plus the CUDA device ordinal */
+GpuSizeField* makeSizeField(ma::Mesh* m, apf::Field* sizes, apf::Field* frames, bool logInterpolation = false, int device = 0);
+GpuSizeField* makeSizeField(ma::Mesh* m, ma::AnisotropicFunction* f, bool logInterpolation = false, int device = 0);
+GpuSizeField* makeSizeField(ma::Mesh* m, apf::Field* size, int device = 0);
+GpuSizeField* makeSizeField(ma::Mesh* m, ma::IsotropicFunction* f, int device = 0);
+
+/* bulk replacements of the reference sweeps; a->sizeField must be a GpuSizeField (otherwise they abort) */
+long markEdgesToSplit(ma::Adapt* a);
+long markEdgesToCollapse(ma::Adapt* a);
+int markBadQuality(ma::Adapt* a);
+double getMinQuality(ma::Adapt* a);
+double getMaximumEdgeLength(ma::Mesh* m, ma::SizeField* sf);
+void getEdgeLengthsInMetricSpace(ma::Mesh* m, ma::SizeField* sf, std::vector<double>& lengths);
+void getLinearQualitiesInMetricSpace(ma::Mesh* m, ma::SizeField* sf, std::vector<double>& qualities);
+
+/* ma::ShapeHandlerFunction: in->shapeHandler = mag::shapeHandler; getQuality(e) is then served from the device sweep */
+ma::ShapeHandler* shapeHandler(ma::Adapt* a);
+
+}
+
+#endif

@@ -386,8 +386,8 @@ k_edges(int64_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
   int qn = 0, eig_any = 0;
   const bool do_split = P.ops & MAG_OP_MARK_SPLIT, do_coll = P.ops & MAG_OP_MARK_COLLAPSE;
   const bool want_len = P.ops & MAG_OP_LENGTHS;
-  const int32_t skip_split = do_split ? (MAG_DONT_SPLIT | MAG_NEED_NOT_SPLIT) : ~0;
-  const int32_t skip_coll = do_coll ? (MAG_DONT_COLLAPSE | MAG_NEED_NOT_COLLAPSE) : ~0;
+  constexpr int32_t skip_split = MAG_DONT_SPLIT | MAG_NEED_NOT_SPLIT, skip_coll = MAG_DONT_COLLAPSE | MAG_NEED_NOT_COLLAPSE;
+  auto has_work = [&](int32_t f) { return want_len || (do_split && !(f & skip_split)) || (do_coll && !(f & skip_coll)); };
   const int64_t ntiles = (ne + kEdgeThreads - 1) / kEdgeThreads;
   const int64_t nchunks = (ntiles + kChunkTiles - 1) / kChunkTiles;
   for (;;) {
@@ -405,7 +405,7 @@ k_edges(int64_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
     int2 ev_cur = make_int2(0, 0);
     if (e < e_end) {
       f_cur = flags[e];
-      work_cur = want_len || !(f_cur & skip_split) || !(f_cur & skip_coll);
+      work_cur = has_work(f_cur);
       ev_cur = __ldg(edge_v + e);
 #ifdef MAG_EDGE_PREFETCH
       if (work_cur) load_edge_recs<KIND>(vedge, ev_cur, R);
@@ -420,7 +420,7 @@ k_edges(int64_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
       work_n = false;
       const int2 ev_n = ev_nx;
       if (e + kEdgeThreads < e_end) {
-        work_n = want_len || !(f_n & skip_split) || !(f_n & skip_coll);
+        work_n = has_work(f_n);
 #ifdef MAG_EDGE_PREFETCH
         if (work_n) load_edge_recs<KIND>(vedge, ev_n, Rn);
 #endif
@@ -435,7 +435,7 @@ k_edges(int64_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
 #ifndef MAG_EDGE_PREFETCH
           load_edge_recs<KIND>(vedge, ev_cur, Rc);   // plain version: this tile's records are gathered here
 #endif
-          const bool need_split = !(f & skip_split), need_coll = !(f & skip_coll);
+          const bool need_split = do_split && !(f & skip_split), need_coll = do_coll && !(f & skip_coll);
           const double len = FAST ? edge_length_fast<KIND>(Rc, &eig_any) : edge_length_strict<KIND>(Rc, &eig_any);
           const bool owned = owned_arr ? (owned_arr[e] != 0) : true;
           if (want_len) {

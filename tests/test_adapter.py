@@ -1,0 +1,36 @@
+"""The C++ drop-in adapter (core_b200/adapter) against the unmodified reference, in one process: libmag_ma.so holds the
+adapter, the compiled reference it plugs into, and the self-check of core_b200/adapter/adapter_check.cc.  The library is
+built where /root/reference exists (the build container) and travels to the GPU box prebuilt."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "core_b200", "lib", "libmag_ma.so")
+
+
+def test_adapter_sources_cite_reference():
+    src = open(os.path.join(ROOT, "core_b200", "adapter", "magAdapt.h")).read()
+    for cite in ("ma/maSize.h", "ma/maRefine.cc", "ma/maCoarsen.cc", "ma/maShape.cc", "ma/maStats.cc"):
+        assert cite in src
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("log_interp,fp_mode", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_adapter_reproduces_reference(built, log_interp, fp_mode):
+    if not os.path.exists(LIB):
+        pytest.skip("libmag_ma.so not built (needs the reference headers)")
+    L = C.CDLL(LIB)
+    L.mag_adapter_check.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p]
+    rep = np.zeros(20)
+    rc = L.mag_adapter_check(16, log_interp, fp_mode, 0.25, rep.ctypes.data_as(C.c_void_p))
+    ref, bulk, loops = rep[0:5], rep[5:10], rep[10:15]
+    assert rc == 0, "adapter differs from the reference: ref=%s bulk=%s loops=%s flagdiffs=%s" % (ref, bulk, loops, rep[15:19])
+    assert ref[0] > 0 and ref[2] > 0                       # the case marks something
+    assert np.array_equal(ref[:3], bulk[:3]) and np.array_equal(ref[:3], loops[:3])
+    assert np.all(rep[15:19] == 0)
+    # the unmodified reference loops (5 whole-mesh sweeps: split, collapse, bad, minq, maxlen) were served by a handful
+    # of device sweeps, not by per-entity evaluation
+    assert 0 < rep[19] <= 5 * 8

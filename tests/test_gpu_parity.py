@@ -160,6 +160,8 @@ def test_reference_named_entry_points(cb):
     p.set_mesh(xyz, ev, tv)
     p.set_size_field_aniso(h, R)
     assert p.markEdgesToSplit() == want["n_split"]
+    ef, lf = p.flags()       # a single mark touches only its own two bits
+    assert np.array_equal(ef, want["edge_flags"] & (cb.SPLIT | cb.NEED_NOT_SPLIT)) and not lf.any()
     assert p.markEdgesToCollapse() == want["n_collapse"]
     assert p.markBadQuality() == want["n_bad"]
     ef, lf = p.flags()
