@@ -9,6 +9,7 @@
 int magk_pack(mag_ctx* c);
 int magk_init_stats(mag_ctx* c);
 int magk_vertex_pass(mag_ctx* c);
+int magk_build_schedule(mag_ctx* c);
 int magk_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double good_q, int use_max, int fp_mode);
 double magk_key_to_double(unsigned long long k);
 void magc_destroy(mag_ctx* c);
@@ -115,6 +116,7 @@ int mag_create(mag_ctx** out, int device)
   c->d_layer_ok = c->d_layer_codes = nullptr;
   c->d_stats = nullptr; c->h_stats = nullptr;
   c->d_block_sums = nullptr; c->n_sms = 148;
+  c->d_edge_order = c->d_tet_order = nullptr;
   c->d_near_edge = c->d_near_elem = nullptr;
   c->cap_vedge = c->cap_ma = c->cap_mb = 0;
   c->last_ops = 0; c->last_fp_mode = 0;
@@ -149,7 +151,7 @@ void mag_destroy(mag_ctx* c)
   cudaFree(c->d_edge_owned); cudaFree(c->d_elem_owned); cudaFree(c->d_edge_flags); cudaFree(c->d_elem_flags);
   cudaFree(c->d_len); cudaFree(c->d_qual); cudaFree(c->d_layer_ok); cudaFree(c->d_layer_codes);
   cudaFree(c->d_stats); cudaFreeHost(c->h_stats); cudaFree(c->d_block_sums);
-  cudaFree(c->d_near_edge); cudaFree(c->d_near_elem);
+  cudaFree(c->d_near_edge); cudaFree(c->d_near_elem); cudaFree(c->d_edge_order); cudaFree(c->d_tet_order);
   for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
@@ -214,6 +216,7 @@ int mag_set_mesh(mag_ctx* c, int64_t nv, const double* xyz, int64_t ne, const in
     return rc;
   if (edge_owned && (rc = upload(c, c->d_edge_owned, edge_owned, (size_t)ne))) return rc;
   if (elem_owned && (rc = upload(c, c->d_elem_owned, elem_owned, (size_t)nel))) return rc;
+  if ((rc = magk_build_schedule(c))) return rc;
   return repack(c);
 }
 

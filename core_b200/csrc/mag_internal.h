@@ -71,6 +71,8 @@ struct mag_ctx {
   int32_t* d_near_edge;  // [ne]  near-threshold edge indices of the last sweep (an entity is listed at most once)
   int32_t* d_near_elem;  // [np+npy+nt]
   int n_sms;
+  int32_t* d_edge_order; // chunk schedule of the edge kernel (chunk indices sorted by smallest vertex id)
+  int32_t* d_tet_order;
   size_t cap_vedge, cap_ma, cap_mb;
 
   // last sweep parameters (for the near-threshold fix-up and getters)

@@ -377,7 +377,7 @@ template <int KIND, bool FAST>
 __global__ void __launch_bounds__(kEdgeThreads, FAST ? MAG_EDGE_BLOCKS : MAG_EDGE_BLOCKS_STRICT)
 k_edges(int64_t ne, const int2* __restrict__ edge_v, const double* __restrict__ vedge,
         const uint8_t* __restrict__ owned_arr, int32_t* __restrict__ flags, double* __restrict__ lengths,
-        SweepParams P, MagDevStats* st, int32_t* __restrict__ near_list)
+        SweepParams P, MagDevStats* st, int32_t* __restrict__ near_list, const int32_t* __restrict__ chunk_order)
 {
   __shared__ NearQueue q;
   __shared__ long long chunk_slot;
@@ -391,8 +391,9 @@ k_edges(int64_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
   const int64_t ntiles = (ne + kEdgeThreads - 1) / kEdgeThreads;
   const int64_t nchunks = (ntiles + kChunkTiles - 1) / kChunkTiles;
   for (;;) {
-    const long long chunk = next_chunk(&st->edge_chunk, &chunk_slot);
-    if (chunk >= nchunks) break;
+    const long long ticket = next_chunk(&st->edge_chunk, &chunk_slot);
+    if (ticket >= nchunks) break;
+    const long long chunk = chunk_order[ticket];
     const int64_t t0 = chunk * kChunkTiles;
     const int64_t t1 = (t0 + kChunkTiles < ntiles) ? t0 + kChunkTiles : ntiles;
     const int64_t e_end = (t1 * kEdgeThreads < ne) ? t1 * kEdgeThreads : ne;   // first edge past this chunk
@@ -649,7 +650,7 @@ __global__ void __launch_bounds__(kTetThreads, FAST ? MAG_TET_BLOCKS : MAG_TET_B
 k_tets(int64_t nt, int64_t elem_off, const int4* __restrict__ tet_v, const double* __restrict__ vpos,
        const double* __restrict__ vq, const double* __restrict__ vedge, const uint8_t* __restrict__ owned_arr,
        int32_t* __restrict__ flags, double* __restrict__ qual, SweepParams P, MagDevStats* st,
-       int32_t* __restrict__ near_list)
+       int32_t* __restrict__ near_list, const int32_t* __restrict__ chunk_order)
 {
   __shared__ NearQueue q;
   __shared__ long long chunk_slot;
@@ -660,8 +661,9 @@ k_tets(int64_t nt, int64_t elem_off, const int4* __restrict__ tet_v, const doubl
   const int64_t ntiles = (nt + kTetThreads - 1) / kTetThreads;
   const int64_t nchunks = (ntiles + kChunkTiles - 1) / kChunkTiles;
   for (;;) {
-    const long long chunk = next_chunk(&st->elem_chunk, &chunk_slot);
-    if (chunk >= nchunks) break;
+    const long long ticket = next_chunk(&st->elem_chunk, &chunk_slot);
+    if (ticket >= nchunks) break;
+    const long long chunk = chunk_order[ticket];
     const int64_t t0 = chunk * kChunkTiles;
     const int64_t t1 = (t0 + kChunkTiles < ntiles) ? t0 + kChunkTiles : ntiles;
     const int64_t t_end = (t1 * kTetThreads < nt) ? t1 * kTetThreads : nt;
@@ -847,6 +849,27 @@ __global__ void k_finish_sum(int64_t n, const double* __restrict__ part, MagDevS
   if (threadIdx.x == 0) st->sum_len = sh[0];
 }
 
+// ------------------------------------------------------------------ chunk schedule (export time)
+// key of a chunk = smallest vertex id any of its entities touches.  Handing the chunks out in key order makes the
+// axis-edge / face-diagonal / body-diagonal families of a box mesh (or whatever families the caller's numbering has) sweep
+// the vertex array together, so a vertex record is fetched from HBM once per sweep instead of once per family.
+template <int NV>
+__global__ void __launch_bounds__(kThreads)
+k_chunk_keys(int64_t n, int64_t chunk_len, const int32_t* __restrict__ conn, int32_t* __restrict__ keys)
+{
+  __shared__ int sh[kThreads / 32];
+  const int64_t lo = blockIdx.x * chunk_len, hi = (lo + chunk_len < n) ? lo + chunk_len : n;
+  int m = 0x7fffffff;
+  for (int64_t i = lo * NV + threadIdx.x; i < hi * NV; i += kThreads) { int v = conn[i]; m = v < m ? v : m; }
+  m = __reduce_min_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < kThreads / 32; ++i) m = sh[i] < m ? sh[i] : m;
+    keys[blockIdx.x] = m;
+  }
+}
+
 inline unsigned grid_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
 } // namespace
@@ -911,11 +934,11 @@ static int launch_edges(mag_ctx* c, const SweepParams& P, bool fast)
   if (fast) {
     static int per_sm = 0;
     const unsigned g = persistent_grid(c, per_sm, (const void*)k_edges<KIND, true>, c->ne, kEdgeThreads);
-    k_edges<KIND, true><<<g, kEdgeThreads, 0, c->stream>>>(c->ne, ev, c->d_vedge, c->d_edge_owned, c->d_edge_flags, c->d_len, P, c->d_stats, c->d_near_edge);
+    k_edges<KIND, true><<<g, kEdgeThreads, 0, c->stream>>>(c->ne, ev, c->d_vedge, c->d_edge_owned, c->d_edge_flags, c->d_len, P, c->d_stats, c->d_near_edge, c->d_edge_order);
   } else {
     static int per_sm = 0;
     const unsigned g = persistent_grid(c, per_sm, (const void*)k_edges<KIND, false>, c->ne, kEdgeThreads);
-    k_edges<KIND, false><<<g, kEdgeThreads, 0, c->stream>>>(c->ne, ev, c->d_vedge, c->d_edge_owned, c->d_edge_flags, c->d_len, P, c->d_stats, c->d_near_edge);
+    k_edges<KIND, false><<<g, kEdgeThreads, 0, c->stream>>>(c->ne, ev, c->d_vedge, c->d_edge_owned, c->d_edge_flags, c->d_len, P, c->d_stats, c->d_near_edge, c->d_edge_order);
   }
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;
@@ -930,14 +953,48 @@ static int launch_tets(mag_ctx* c, const SweepParams& P, bool fast)
   if (fast) {
     static int per_sm = 0;
     const unsigned g = persistent_grid(c, per_sm, (const void*)k_tets<KIND, true>, c->nt, kTetThreads);
-    k_tets<KIND, true><<<g, kTetThreads, 0, c->stream>>>(c->nt, off, tv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_owned, c->d_elem_flags, c->d_qual, P, c->d_stats, c->d_near_elem);
+    k_tets<KIND, true><<<g, kTetThreads, 0, c->stream>>>(c->nt, off, tv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_owned, c->d_elem_flags, c->d_qual, P, c->d_stats, c->d_near_elem, c->d_tet_order);
   } else {
     static int per_sm = 0;
     const unsigned g = persistent_grid(c, per_sm, (const void*)k_tets<KIND, false>, c->nt, kTetThreads);
-    k_tets<KIND, false><<<g, kTetThreads, 0, c->stream>>>(c->nt, off, tv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_owned, c->d_elem_flags, c->d_qual, P, c->d_stats, c->d_near_elem);
+    k_tets<KIND, false><<<g, kTetThreads, 0, c->stream>>>(c->nt, off, tv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_owned, c->d_elem_flags, c->d_qual, P, c->d_stats, c->d_near_elem, c->d_tet_order);
   }
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;
+  return MAG_OK;
+}
+
+#include <algorithm>
+#include <numeric>
+// builds c->d_edge_order / c->d_tet_order: chunk indices sorted by key (stable, so equal keys keep the caller's order)
+static int build_order(mag_ctx* c, int64_t n, int64_t chunk_len, const int32_t* d_conn, int nv_per, int32_t*& d_order, int64_t& n_chunks)
+{
+  n_chunks = (n + chunk_len - 1) / chunk_len;
+  if (d_order) { MAG_CUDA(c, cudaFree(d_order)); d_order = nullptr; }
+  if (n_chunks == 0) return MAG_OK;
+  int32_t* d_keys = nullptr;
+  MAG_CUDA(c, cudaMalloc((void**)&d_keys, (size_t)n_chunks * 4));
+  MAG_CUDA(c, cudaMalloc((void**)&d_order, (size_t)n_chunks * 4));
+  if (nv_per == 2) k_chunk_keys<2><<<(unsigned)n_chunks, kThreads, 0, c->stream>>>(n, chunk_len, d_conn, d_keys);
+  else k_chunk_keys<4><<<(unsigned)n_chunks, kThreads, 0, c->stream>>>(n, chunk_len, d_conn, d_keys);
+  MAG_CUDA(c, cudaGetLastError());
+  c->n_launches++;
+  std::vector<int32_t> keys((size_t)n_chunks), order((size_t)n_chunks);
+  MAG_CUDA(c, cudaMemcpyAsync(keys.data(), d_keys, (size_t)n_chunks * 4, cudaMemcpyDeviceToHost, c->stream));
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return keys[(size_t)a] < keys[(size_t)b]; });
+  MAG_CUDA(c, cudaMemcpyAsync(d_order, order.data(), (size_t)n_chunks * 4, cudaMemcpyHostToDevice, c->stream));
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  MAG_CUDA(c, cudaFree(d_keys));
+  return MAG_OK;
+}
+int magk_build_schedule(mag_ctx* c)
+{
+  int rc;
+  int64_t nch;
+  if ((rc = build_order(c, c->ne, (int64_t)kChunkTiles * kEdgeThreads, c->d_edge_v, 2, c->d_edge_order, nch))) return rc;
+  if ((rc = build_order(c, c->nt, (int64_t)kChunkTiles * kTetThreads, c->d_tet_v, 4, c->d_tet_order, nch))) return rc;
   return MAG_OK;
 }
 
