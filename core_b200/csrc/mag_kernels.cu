@@ -60,20 +60,36 @@ __device__ __forceinline__ double warp_sum(double v)
   return v;
 }
 
-// ------------------------------------------------------------------ record loads
-struct Rec12 { double v[12]; };
-__device__ __forceinline__ Rec12 load_rec12(const double* __restrict__ base, int32_t vid)
+// ------------------------------------------------------------------ vertex arrays: chunk-major layout
+// Every per-vertex array is stored as K planes of double2: chunk k of vertex v lives at ((double2*)base)[k*nv + v].
+// Neighbouring threads work on neighbouring entities, whose vertex ids are close in any locality-preserving numbering
+// (grid order for box meshes), so one warp-wide LDG.128 of chunk k touches a couple of cache lines instead of one line
+// per lane as 96-byte-strided records would: the L1 data pipe, not HBM, is what these kernels saturate first.
+//   d_vedge  Aniso   6 planes {x,y} {z,h0} {h1,h2} {R00,R10} {R20,R01} {R11,R21}   (frame columns 0 and 1; column 2 is
+//                    overwritten by orthogonalizeR before use, maSize.cc:94-121)
+//            LogAniso 6 planes {x,y} {z,M00} {M01,M02} {M10,M11} {M12,M20} {M21,M22}
+//            Iso / Identity 2 planes {x,y} {z,s}
+//   d_vpos   2 planes {x,y} {z,det Q_v}
+//   d_vq     5 planes {Q00,Q01} {Q02,Q10} {Q11,Q12} {Q20,Q21} {Q22,det Q_v}
+__device__ __forceinline__ const double2* chunk_ptr(const double* __restrict__ base, int64_t nv, int k, int64_t v)
 {
-  const double2* p = reinterpret_cast<const double2*>(base + 12 * (size_t)vid);
+  return reinterpret_cast<const double2*>(base) + (size_t)k * (size_t)nv + (size_t)v;
+}
+__device__ __forceinline__ double2* chunk_ptr_w(double* __restrict__ base, int64_t nv, int k, int64_t v)
+{
+  return reinterpret_cast<double2*>(base) + (size_t)k * (size_t)nv + (size_t)v;
+}
+struct Rec12 { double v[12]; };
+__device__ __forceinline__ Rec12 load_rec12(const double* __restrict__ base, int64_t nv, int32_t vid)
+{
   Rec12 r;
 #pragma unroll
-  for (int i = 0; i < 6; ++i) { double2 t = __ldg(p + i); r.v[2 * i] = t.x; r.v[2 * i + 1] = t.y; }
+  for (int i = 0; i < 6; ++i) { double2 t = __ldg(chunk_ptr(base, nv, i, vid)); r.v[2 * i] = t.x; r.v[2 * i + 1] = t.y; }
   return r;
 }
-__device__ __forceinline__ void load_rec4(const double* __restrict__ base, int32_t vid, double out[4])
+__device__ __forceinline__ void load_rec4(const double* __restrict__ base, int64_t nv, int32_t vid, double out[4])
 {
-  const double2* p = reinterpret_cast<const double2*>(base + 4 * (size_t)vid);
-  double2 a = __ldg(p), b = __ldg(p + 1);
+  double2 a = __ldg(chunk_ptr(base, nv, 0, vid)), b = __ldg(chunk_ptr(base, nv, 1, vid));
   out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
 }
 
@@ -82,32 +98,33 @@ __global__ void k_pack4(int64_t nv, const double* __restrict__ xyz, const double
 {
   int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (v >= nv) return;
-  double2* o = reinterpret_cast<double2*>(rec + 4 * v);
-  o[0] = make_double2(xyz[3 * v], xyz[3 * v + 1]);
-  o[1] = make_double2(xyz[3 * v + 2], s ? s[v] : 0.0);
+  *chunk_ptr_w(rec, nv, 0, v) = make_double2(xyz[3 * v], xyz[3 * v + 1]);
+  *chunk_ptr_w(rec, nv, 1, v) = make_double2(xyz[3 * v + 2], s ? s[v] : 0.0);
 }
-// aniso: {x,y,z,h0,h1,h2,R00,R10,R20,R01,R11,R21} (frame columns 0 and 1; column 2 is
-// overwritten by orthogonalizeR before use, maSize.cc:94-121)
 __global__ void k_pack12_aniso(int64_t nv, const double* __restrict__ xyz, const double* __restrict__ h,
                                const double* __restrict__ R, double* __restrict__ rec)
 {
   int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (v >= nv) return;
-  double* o = rec + 12 * v;
   const double* r = R + 9 * v;
-  o[0] = xyz[3 * v]; o[1] = xyz[3 * v + 1]; o[2] = xyz[3 * v + 2];
-  o[3] = h[3 * v]; o[4] = h[3 * v + 1]; o[5] = h[3 * v + 2];
-  o[6] = r[0]; o[7] = r[3]; o[8] = r[6];
-  o[9] = r[1]; o[10] = r[4]; o[11] = r[7];
+  *chunk_ptr_w(rec, nv, 0, v) = make_double2(xyz[3 * v], xyz[3 * v + 1]);
+  *chunk_ptr_w(rec, nv, 1, v) = make_double2(xyz[3 * v + 2], h[3 * v]);
+  *chunk_ptr_w(rec, nv, 2, v) = make_double2(h[3 * v + 1], h[3 * v + 2]);
+  *chunk_ptr_w(rec, nv, 3, v) = make_double2(r[0], r[3]);
+  *chunk_ptr_w(rec, nv, 4, v) = make_double2(r[6], r[1]);
+  *chunk_ptr_w(rec, nv, 5, v) = make_double2(r[4], r[7]);
 }
 __global__ void k_pack12_logm(int64_t nv, const double* __restrict__ xyz, const double* __restrict__ M, double* __restrict__ rec)
 {
   int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (v >= nv) return;
-  double* o = rec + 12 * v;
-  o[0] = xyz[3 * v]; o[1] = xyz[3 * v + 1]; o[2] = xyz[3 * v + 2];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) o[3 + i] = M[9 * v + i];
+  const double* m = M + 9 * v;
+  *chunk_ptr_w(rec, nv, 0, v) = make_double2(xyz[3 * v], xyz[3 * v + 1]);
+  *chunk_ptr_w(rec, nv, 1, v) = make_double2(xyz[3 * v + 2], m[0]);
+  *chunk_ptr_w(rec, nv, 2, v) = make_double2(m[1], m[2]);
+  *chunk_ptr_w(rec, nv, 3, v) = make_double2(m[3], m[4]);
+  *chunk_ptr_w(rec, nv, 4, v) = make_double2(m[5], m[6]);
+  *chunk_ptr_w(rec, nv, 5, v) = make_double2(m[7], m[8]);
 }
 
 // ------------------------------------------------------------------ per-vertex pass
@@ -123,7 +140,7 @@ __global__ void k_vertex_pass(int64_t nv, const double* __restrict__ vedge, doub
   double x, y, z;
   if (KIND == MAG_KIND_IDENTITY || KIND == MAG_KIND_ISO) {
     double r[4];
-    load_rec4(vedge, (int32_t)v, r);
+    load_rec4(vedge, nv, (int32_t)v, r);
     x = r[0]; y = r[1]; z = r[2];
     magst::identity(Q);
     if (KIND == MAG_KIND_ISO) {
@@ -132,7 +149,7 @@ __global__ void k_vertex_pass(int64_t nv, const double* __restrict__ vedge, doub
       Q.m[0][0] = ih; Q.m[1][1] = ih; Q.m[2][2] = ih;
     }
   } else {
-    Rec12 r = load_rec12(vedge, (int32_t)v);
+    Rec12 r = load_rec12(vedge, nv, (int32_t)v);
     x = r.v[0]; y = r.v[1]; z = r.v[2];
     if (KIND == MAG_KIND_ANISO) {
       magst::transform_aniso(V3{r.v[6], r.v[7], r.v[8]}, V3{r.v[9], r.v[10], r.v[11]}, r.v[3], r.v[4], r.v[5], Q);
@@ -145,15 +162,13 @@ __global__ void k_vertex_pass(int64_t nv, const double* __restrict__ vedge, doub
     }
   }
   double det = magst::det3(Q);
-  double2* o = reinterpret_cast<double2*>(vpos + 4 * v);
-  o[0] = make_double2(x, y);
-  o[1] = make_double2(z, det);
-  double2* q = reinterpret_cast<double2*>(vq + 10 * v);
-  q[0] = make_double2(Q.m[0][0], Q.m[0][1]);
-  q[1] = make_double2(Q.m[0][2], Q.m[1][0]);
-  q[2] = make_double2(Q.m[1][1], Q.m[1][2]);
-  q[3] = make_double2(Q.m[2][0], Q.m[2][1]);
-  q[4] = make_double2(Q.m[2][2], det);
+  *chunk_ptr_w(vpos, nv, 0, v) = make_double2(x, y);
+  *chunk_ptr_w(vpos, nv, 1, v) = make_double2(z, det);
+  *chunk_ptr_w(vq, nv, 0, v) = make_double2(Q.m[0][0], Q.m[0][1]);
+  *chunk_ptr_w(vq, nv, 1, v) = make_double2(Q.m[0][2], Q.m[1][0]);
+  *chunk_ptr_w(vq, nv, 2, v) = make_double2(Q.m[1][1], Q.m[1][2]);
+  *chunk_ptr_w(vq, nv, 3, v) = make_double2(Q.m[2][0], Q.m[2][1]);
+  *chunk_ptr_w(vq, nv, 4, v) = make_double2(Q.m[2][2], det);
 }
 
 // ------------------------------------------------------------------ edge metric length
@@ -164,15 +179,13 @@ struct EdgeRecs {
   double a[N], b[N];
 };
 template <int KIND>
-__device__ __forceinline__ void load_edge_recs(const double* __restrict__ vedge, int2 ev, EdgeRecs<KIND>& R)
+__device__ __forceinline__ void load_edge_recs(const double* __restrict__ vedge, int64_t nv, int2 ev, EdgeRecs<KIND>& R)
 {
   constexpr int N = EdgeRecs<KIND>::N;
-  const double2* pa = reinterpret_cast<const double2*>(vedge + N * (size_t)ev.x);
-  const double2* pb = reinterpret_cast<const double2*>(vedge + N * (size_t)ev.y);
 #pragma unroll
-  for (int i = 0; i < N / 2; ++i) { double2 t = __ldg(pa + i); R.a[2 * i] = t.x; R.a[2 * i + 1] = t.y; }
+  for (int i = 0; i < N / 2; ++i) { double2 t = __ldg(chunk_ptr(vedge, nv, i, ev.x)); R.a[2 * i] = t.x; R.a[2 * i + 1] = t.y; }
 #pragma unroll
-  for (int i = 0; i < N / 2; ++i) { double2 t = __ldg(pb + i); R.b[2 * i] = t.x; R.b[2 * i + 1] = t.y; }
+  for (int i = 0; i < N / 2; ++i) { double2 t = __ldg(chunk_ptr(vedge, nv, i, ev.y)); R.b[2 * i] = t.x; R.b[2 * i + 1] = t.y; }
 }
 
 // MetricSizeField::measure: order 2 -> EdgeIntegration::N2, points +-0.577350269189626, weights 1
@@ -337,7 +350,7 @@ __device__ __forceinline__ void prefetch_rec12(const double* __restrict__ base, 
 // drain n (<= 32) queued edges: entry i is handled by lane i.  Returns bit 0: evaluated, bit 1: counted SPLIT, bit 2: counted COLLAPSE
 template <int KIND, bool FAST>
 __device__ __noinline__ unsigned drain_edges(NearQueue& q, int first, int n, const int2* __restrict__ edge_v,
-                                             const double* __restrict__ vedge, const uint8_t* __restrict__ owned_arr,
+                                             const double* __restrict__ vedge, int64_t nv, const uint8_t* __restrict__ owned_arr,
                                              int32_t* __restrict__ flags, double* __restrict__ lengths, uint32_t ops,
                                              double max_len, double min_len,
                                              MagDevStats* st, int32_t* __restrict__ near_list)
@@ -354,7 +367,7 @@ __device__ __noinline__ unsigned drain_edges(NearQueue& q, int first, int n, con
       const bool need_split = (P.ops & MAG_OP_MARK_SPLIT) && !(f & (MAG_DONT_SPLIT | MAG_NEED_NOT_SPLIT));
       const bool need_coll = (P.ops & MAG_OP_MARK_COLLAPSE) && !(f & (MAG_DONT_COLLAPSE | MAG_NEED_NOT_COLLAPSE));
       EdgeRecs<KIND> R;
-      load_edge_recs<KIND>(vedge, __ldg(edge_v + e), R);
+      load_edge_recs<KIND>(vedge, nv, __ldg(edge_v + e), R);
       int eig = 0;
       const double len = edge_length_strict<KIND>(R, &eig);
       const bool owned = owned_arr ? (owned_arr[e] != 0) : true;
@@ -375,7 +388,7 @@ __device__ __noinline__ unsigned drain_edges(NearQueue& q, int first, int n, con
 //   k+1 is covered by the arithmetic of tile k.
 template <int KIND, bool FAST>
 __global__ void __launch_bounds__(kEdgeThreads, FAST ? MAG_EDGE_BLOCKS : MAG_EDGE_BLOCKS_STRICT)
-k_edges(int64_t ne, const int2* __restrict__ edge_v, const double* __restrict__ vedge,
+k_edges(int64_t ne, int64_t nv, const int2* __restrict__ edge_v, const double* __restrict__ vedge,
         const uint8_t* __restrict__ owned_arr, int32_t* __restrict__ flags, double* __restrict__ lengths,
         SweepParams P, MagDevStats* st, int32_t* __restrict__ near_list, const int32_t* __restrict__ chunk_order)
 {
@@ -409,7 +422,7 @@ k_edges(int64_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
       work_cur = has_work(f_cur);
       ev_cur = __ldg(edge_v + e);
 #ifdef MAG_EDGE_PREFETCH
-      if (work_cur) load_edge_recs<KIND>(vedge, ev_cur, R);
+      if (work_cur) load_edge_recs<KIND>(vedge, nv, ev_cur, R);
 #endif
     }
     if (e + kEdgeThreads < e_end) { f_nx = flags[e + kEdgeThreads]; ev_nx = __ldg(edge_v + e + kEdgeThreads); }
@@ -423,7 +436,7 @@ k_edges(int64_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
       if (e + kEdgeThreads < e_end) {
         work_n = has_work(f_n);
 #ifdef MAG_EDGE_PREFETCH
-        if (work_n) load_edge_recs<KIND>(vedge, ev_n, Rn);
+        if (work_n) load_edge_recs<KIND>(vedge, nv, ev_n, Rn);
 #endif
       }
       if (e + 2 * kEdgeThreads < e_end) { f_nx = flags[e + 2 * kEdgeThreads]; ev_nx = __ldg(edge_v + e + 2 * kEdgeThreads); }
@@ -434,7 +447,7 @@ k_edges(int64_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
         if ((do_split && (f & MAG_SPLIT)) || (do_coll && (f & MAG_COLLAPSE))) ++c_err;
         if (work_c) {
 #ifndef MAG_EDGE_PREFETCH
-          load_edge_recs<KIND>(vedge, ev_cur, Rc);   // plain version: this tile's records are gathered here
+          load_edge_recs<KIND>(vedge, nv, ev_cur, Rc);   // plain version: this tile's records are gathered here
 #endif
           const bool need_split = do_split && !(f & skip_split), need_coll = do_coll && !(f & skip_coll);
           const double len = FAST ? edge_length_fast<KIND>(Rc, &eig_any) : edge_length_strict<KIND>(Rc, &eig_any);
@@ -456,7 +469,7 @@ k_edges(int64_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
       }
       if (queue_push(q, qn, nr, (int32_t)e, f_c)) {
         qn -= 32;
-        const unsigned r = drain_edges<KIND, FAST>(q, qn, 32, edge_v, vedge, owned_arr, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list);
+        const unsigned r = drain_edges<KIND, FAST>(q, qn, 32, edge_v, vedge, nv, owned_arr, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list);
         c_eval += r & 1u; c_split += (r >> 1) & 1u; c_coll += (r >> 2) & 1u;
       }
       e += kEdgeThreads;
@@ -481,7 +494,7 @@ k_edges(int64_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
 #endif
   }
   if (qn) {
-    const unsigned r = drain_edges<KIND, FAST>(q, 0, qn, edge_v, vedge, owned_arr, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list);
+    const unsigned r = drain_edges<KIND, FAST>(q, 0, qn, edge_v, vedge, nv, owned_arr, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list);
     c_eval += r & 1u; c_split += (r >> 1) & 1u; c_coll += (r >> 2) & 1u;
   }
   if (eig_any) atomicAdd(&st->n_eigen_fail, 1ull);
@@ -517,7 +530,7 @@ k_sum_lengths(int64_t ne, const double* __restrict__ lengths, const uint8_t* __r
 // ------------------------------------------------------------------ tets
 // centroid transform for useMax == false (maQuality.cc:148-153): N = (1-.25-.25-.25, .25, .25, .25)
 template <int KIND>
-__device__ __forceinline__ void centroid_transform(const double* __restrict__ vedge, const int4& tv, M3& Q, int* eig)
+__device__ __forceinline__ void centroid_transform(const double* __restrict__ vedge, int64_t nv, const int4& tv, M3& Q, int* eig)
 {
   constexpr double N0 = 1 - 0.25 - 0.25 - 0.25;
   const int32_t vid[4] = {tv.x, tv.y, tv.z, tv.w};
@@ -527,7 +540,7 @@ __device__ __forceinline__ void centroid_transform(const double* __restrict__ ve
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
       double r[4];
-      load_rec4(vedge, vid[n], r);
+      load_rec4(vedge, nv, vid[n], r);
       h = magst::add(h, magst::mul(r[3], n ? 0.25 : N0));
     }
     magst::identity(Q);
@@ -540,7 +553,7 @@ __device__ __forceinline__ void centroid_transform(const double* __restrict__ ve
   for (int i = 0; i < 9; ++i) c[i] = 0;
 #pragma unroll
   for (int n = 0; n < 4; ++n) {
-    Rec12 r = load_rec12(vedge, vid[n]);
+    Rec12 r = load_rec12(vedge, nv, vid[n]);
 #pragma unroll
     for (int i = 0; i < 9; ++i) c[i] = magst::add(c[i], magst::mul(r.v[3 + i], n ? 0.25 : N0));
   }
@@ -565,10 +578,10 @@ __device__ __forceinline__ int32_t best_vertex(const int4& tv, double d0, double
   if (d3 > maxJ) { maxJ = d3; vb = tv.w; }
   return vb;
 }
-__device__ __forceinline__ void load_q(const double* __restrict__ vq, int32_t vb, M3& Q, double& detQ)
+__device__ __forceinline__ void load_q(const double* __restrict__ vq, int64_t nv, int32_t vb, M3& Q, double& detQ)
 {
-  const double2* q = reinterpret_cast<const double2*>(vq + 10 * (size_t)vb);
-  double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4);
+  double2 q0 = __ldg(chunk_ptr(vq, nv, 0, vb)), q1 = __ldg(chunk_ptr(vq, nv, 1, vb)), q2 = __ldg(chunk_ptr(vq, nv, 2, vb)),
+          q3 = __ldg(chunk_ptr(vq, nv, 3, vb)), q4 = __ldg(chunk_ptr(vq, nv, 4, vb));
   Q.m[0][0] = q0.x; Q.m[0][1] = q0.y; Q.m[0][2] = q1.x;
   Q.m[1][0] = q1.y; Q.m[1][1] = q2.x; Q.m[1][2] = q2.y;
   Q.m[2][0] = q3.x; Q.m[2][1] = q3.y; Q.m[2][2] = q4.x;
@@ -578,22 +591,22 @@ __device__ __forceinline__ void load_q(const double* __restrict__ vq, int32_t vb
 // HAVE_DETS: the four det Q_v were loaded one tile ahead (dets[]), so the transform of the best vertex can be
 // requested together with the coordinates instead of after them
 template <int KIND, bool FAST, bool HAVE_DETS>
-__device__ __forceinline__ double tet_quality_eval(const int4& tv, const double* __restrict__ vpos,
+__device__ __forceinline__ double tet_quality_eval(const int4& tv, int64_t nv, const double* __restrict__ vpos,
                                                    const double* __restrict__ vq, const double* __restrict__ vedge,
                                                    int use_max, int* eig, const double* dets)
 {
   M3 Q;
   double detQ = 0.0;
-  if (HAVE_DETS && use_max) load_q(vq, best_vertex(tv, dets[0], dets[1], dets[2], dets[3]), Q, detQ);
+  if (HAVE_DETS && use_max) load_q(vq, nv, best_vertex(tv, dets[0], dets[1], dets[2], dets[3]), Q, detQ);
   double p[4][4];
-  load_rec4(vpos, tv.x, p[0]);
-  load_rec4(vpos, tv.y, p[1]);
-  load_rec4(vpos, tv.z, p[2]);
-  load_rec4(vpos, tv.w, p[3]);
+  load_rec4(vpos, nv, tv.x, p[0]);
+  load_rec4(vpos, nv, tv.y, p[1]);
+  load_rec4(vpos, nv, tv.z, p[2]);
+  load_rec4(vpos, nv, tv.w, p[3]);
   if (use_max) {
-    if (!HAVE_DETS) load_q(vq, best_vertex(tv, p[0][3], p[1][3], p[2][3], p[3][3]), Q, detQ);
+    if (!HAVE_DETS) load_q(vq, nv, best_vertex(tv, p[0][3], p[1][3], p[2][3], p[3][3]), Q, detQ);
   } else {
-    centroid_transform<KIND>(vedge, tv, Q, eig);
+    centroid_transform<KIND>(vedge, nv, tv, Q, eig);
     detQ = FAST ? magst::det3(Q) : 0.0;
   }
   V3 x[4];
@@ -610,7 +623,7 @@ __device__ __forceinline__ void mark_tet(double q, int32_t& f, bool owned, const
 
 // returns bit 0: evaluated, bit 1: counted BAD_QUALITY
 template <int KIND, bool FAST>
-__device__ __noinline__ unsigned drain_tets(NearQueue& q, int first, int n, int64_t elem_off, const int4* __restrict__ tet_v,
+__device__ __noinline__ unsigned drain_tets(NearQueue& q, int first, int n, int64_t elem_off, int64_t nv, const int4* __restrict__ tet_v,
                                             const double* __restrict__ vpos, const double* __restrict__ vq,
                                             const double* __restrict__ vedge, const uint8_t* __restrict__ owned_arr,
                                             int32_t* __restrict__ flags, double* __restrict__ qual, uint32_t ops,
@@ -629,7 +642,7 @@ __device__ __noinline__ unsigned drain_tets(NearQueue& q, int first, int n, int6
       int32_t f = q.f[w][first + lane];
       const int4 tv = __ldg(tet_v + t);
       int eig = 0;
-      const double qv = tet_quality_eval<KIND, false, false>(tv, vpos, vq, vedge, P.use_max, &eig, nullptr);
+      const double qv = tet_quality_eval<KIND, false, false>(tv, nv, vpos, vq, vedge, P.use_max, &eig, nullptr);
       const bool owned = owned_arr ? (owned_arr[el] != 0) : true;
       unsigned cb = 0;
       mark_tet(qv, f, owned, P, cb);
@@ -647,7 +660,7 @@ __device__ __noinline__ unsigned drain_tets(NearQueue& q, int first, int n, int6
 // choice of the max-Jacobian vertex does not sit between two dependent gathers.
 template <int KIND, bool FAST>
 __global__ void __launch_bounds__(kTetThreads, FAST ? MAG_TET_BLOCKS : MAG_TET_BLOCKS_STRICT)
-k_tets(int64_t nt, int64_t elem_off, const int4* __restrict__ tet_v, const double* __restrict__ vpos,
+k_tets(int64_t nt, int64_t elem_off, int64_t nv, const int4* __restrict__ tet_v, const double* __restrict__ vpos,
        const double* __restrict__ vq, const double* __restrict__ vedge, const uint8_t* __restrict__ owned_arr,
        int32_t* __restrict__ flags, double* __restrict__ qual, SweepParams P, MagDevStats* st,
        int32_t* __restrict__ near_list, const int32_t* __restrict__ chunk_order)
@@ -672,8 +685,8 @@ k_tets(int64_t nt, int64_t elem_off, const int4* __restrict__ tet_v, const doubl
     int4 tv_cur = make_int4(0, 0, 0, 0), tv_nx = tv_cur;
     double dets[4] = {0, 0, 0, 0};
     auto load_dets = [&](const int4& tv, double* d) {
-      d[0] = __ldg(vpos + 4 * (size_t)tv.x + 3); d[1] = __ldg(vpos + 4 * (size_t)tv.y + 3);
-      d[2] = __ldg(vpos + 4 * (size_t)tv.z + 3); d[3] = __ldg(vpos + 4 * (size_t)tv.w + 3);
+      d[0] = __ldg(&chunk_ptr(vpos, nv, 1, tv.x)->y); d[1] = __ldg(&chunk_ptr(vpos, nv, 1, tv.y)->y);
+      d[2] = __ldg(&chunk_ptr(vpos, nv, 1, tv.z)->y); d[3] = __ldg(&chunk_ptr(vpos, nv, 1, tv.w)->y);
     };
     if (t < t_end) {
       f_cur = flags[elem_off + t];
@@ -697,7 +710,7 @@ k_tets(int64_t nt, int64_t elem_off, const int4* __restrict__ tet_v, const doubl
         if (do_bad && (f & MAG_BAD_QUALITY)) ++c_err;
         const bool need_bad = do_bad && !(f & MAG_OK_QUALITY);
         if (want_q || need_bad) {
-          const double qv = tet_quality_eval<KIND, FAST, true>(tv, vpos, vq, vedge, P.use_max, &eig_any, d_cur);
+          const double qv = tet_quality_eval<KIND, FAST, true>(tv, nv, vpos, vq, vedge, P.use_max, &eig_any, d_cur);
           if (want_q) {
             qual[el] = qv;
             const unsigned long long k = dkey(qv);
@@ -714,13 +727,13 @@ k_tets(int64_t nt, int64_t elem_off, const int4* __restrict__ tet_v, const doubl
       }
       if (queue_push(q, qn, nr, (int32_t)t, f_in)) {
         qn -= 32;
-        const unsigned r = drain_tets<KIND, FAST>(q, qn, 32, elem_off, tet_v, vpos, vq, vedge, owned_arr, flags, qual, P.ops, P.good_q, P.use_max, st, near_list);
+        const unsigned r = drain_tets<KIND, FAST>(q, qn, 32, elem_off, nv, tet_v, vpos, vq, vedge, owned_arr, flags, qual, P.ops, P.good_q, P.use_max, st, near_list);
         c_eval += r & 1u; c_bad += (r >> 1) & 1u;
       }
     }
   }
   if (qn) {
-    const unsigned r = drain_tets<KIND, FAST>(q, 0, qn, elem_off, tet_v, vpos, vq, vedge, owned_arr, flags, qual, P.ops, P.good_q, P.use_max, st, near_list);
+    const unsigned r = drain_tets<KIND, FAST>(q, 0, qn, elem_off, nv, tet_v, vpos, vq, vedge, owned_arr, flags, qual, P.ops, P.good_q, P.use_max, st, near_list);
     c_eval += r & 1u; c_bad += (r >> 1) & 1u;
   }
   if (eig_any) atomicAdd(&st->n_eigen_fail, 1ull);
@@ -777,14 +790,14 @@ __device__ __forceinline__ int unrotate_code(int code, int rot)
     if (code & (1 << i)) out |= (1 << ((i + c_shift_table[rot]) % 3));
   return out;
 }
-__device__ __forceinline__ V3 load_pos(const double* __restrict__ vpos, int32_t v)
+__device__ __forceinline__ V3 load_pos(const double* __restrict__ vpos, int64_t nv, int32_t v)
 {
   double r[4];
-  load_rec4(vpos, v, r);
+  load_rec4(vpos, nv, v, r);
   return V3{r[0], r[1], r[2]};
 }
 // isPrismOk (maQuality.cc:490-530) / isPyramidOk (:532-560)
-__global__ void k_layer(int64_t np, int64_t npy, const int32_t* __restrict__ prism_v, const int32_t* __restrict__ pyr_v,
+__global__ void k_layer(int64_t np, int64_t npy, int64_t nv, const int32_t* __restrict__ prism_v, const int32_t* __restrict__ pyr_v,
                         const double* __restrict__ vpos, int32_t* __restrict__ ok, int32_t* __restrict__ codes, MagDevStats* st)
 {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -793,7 +806,7 @@ __global__ void k_layer(int64_t np, int64_t npy, const int32_t* __restrict__ pri
   if (i < np) {
     V3 p[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) p[k] = load_pos(vpos, prism_v[6 * i + k]);
+    for (int k = 0; k < 6; ++k) p[k] = load_pos(vpos, nv, prism_v[6 * i + k]);
     code = 0xFF;
     for (int r = 0; r < 6; ++r) {
       const int* n2o = c_prism_rotation[r];
@@ -810,7 +823,7 @@ __global__ void k_layer(int64_t np, int64_t npy, const int32_t* __restrict__ pri
     int64_t j = i - np;
     V3 p[5];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) p[k] = load_pos(vpos, pyr_v[5 * j + k]);
+    for (int k = 0; k < 5; ++k) p[k] = load_pos(vpos, nv, pyr_v[5 * j + k]);
     code = -1;
     for (int r = 0; r < 2; ++r) {
       const int* n2o = c_pyramid_rotation[r];
@@ -934,11 +947,11 @@ static int launch_edges(mag_ctx* c, const SweepParams& P, bool fast)
   if (fast) {
     static int per_sm = 0;
     const unsigned g = persistent_grid(c, per_sm, (const void*)k_edges<KIND, true>, c->ne, kEdgeThreads);
-    k_edges<KIND, true><<<g, kEdgeThreads, 0, c->stream>>>(c->ne, ev, c->d_vedge, c->d_edge_owned, c->d_edge_flags, c->d_len, P, c->d_stats, c->d_near_edge, c->d_edge_order);
+    k_edges<KIND, true><<<g, kEdgeThreads, 0, c->stream>>>(c->ne, c->nv, ev, c->d_vedge, c->d_edge_owned, c->d_edge_flags, c->d_len, P, c->d_stats, c->d_near_edge, c->d_edge_order);
   } else {
     static int per_sm = 0;
     const unsigned g = persistent_grid(c, per_sm, (const void*)k_edges<KIND, false>, c->ne, kEdgeThreads);
-    k_edges<KIND, false><<<g, kEdgeThreads, 0, c->stream>>>(c->ne, ev, c->d_vedge, c->d_edge_owned, c->d_edge_flags, c->d_len, P, c->d_stats, c->d_near_edge, c->d_edge_order);
+    k_edges<KIND, false><<<g, kEdgeThreads, 0, c->stream>>>(c->ne, c->nv, ev, c->d_vedge, c->d_edge_owned, c->d_edge_flags, c->d_len, P, c->d_stats, c->d_near_edge, c->d_edge_order);
   }
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;
@@ -953,11 +966,11 @@ static int launch_tets(mag_ctx* c, const SweepParams& P, bool fast)
   if (fast) {
     static int per_sm = 0;
     const unsigned g = persistent_grid(c, per_sm, (const void*)k_tets<KIND, true>, c->nt, kTetThreads);
-    k_tets<KIND, true><<<g, kTetThreads, 0, c->stream>>>(c->nt, off, tv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_owned, c->d_elem_flags, c->d_qual, P, c->d_stats, c->d_near_elem, c->d_tet_order);
+    k_tets<KIND, true><<<g, kTetThreads, 0, c->stream>>>(c->nt, off, c->nv, tv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_owned, c->d_elem_flags, c->d_qual, P, c->d_stats, c->d_near_elem, c->d_tet_order);
   } else {
     static int per_sm = 0;
     const unsigned g = persistent_grid(c, per_sm, (const void*)k_tets<KIND, false>, c->nt, kTetThreads);
-    k_tets<KIND, false><<<g, kTetThreads, 0, c->stream>>>(c->nt, off, tv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_owned, c->d_elem_flags, c->d_qual, P, c->d_stats, c->d_near_elem, c->d_tet_order);
+    k_tets<KIND, false><<<g, kTetThreads, 0, c->stream>>>(c->nt, off, c->nv, tv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_owned, c->d_elem_flags, c->d_qual, P, c->d_stats, c->d_near_elem, c->d_tet_order);
   }
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;
@@ -1048,7 +1061,7 @@ int magk_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double 
     }
   }
   if ((ops & MAG_OP_LAYER_CHECK) && (c->np + c->npy)) {
-    k_layer<<<grid_for(c->np + c->npy), kThreads, 0, c->stream>>>(c->np, c->npy, c->d_prism_v, c->d_pyr_v, c->d_vpos, c->d_layer_ok, c->d_layer_codes, c->d_stats);
+    k_layer<<<grid_for(c->np + c->npy), kThreads, 0, c->stream>>>(c->np, c->npy, c->nv, c->d_prism_v, c->d_pyr_v, c->d_vpos, c->d_layer_ok, c->d_layer_codes, c->d_stats);
     MAG_CUDA(c, cudaGetLastError());
     c->n_launches++;
   }

@@ -76,10 +76,22 @@ __device__ __forceinline__ double edge_aniso(const double* __restrict__ a, const
   double dl[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) dl[i] = b[3 + i] - a[3 + i];
+#ifdef MAG_EDGE_SEQ
+  // one Gauss point after the other (not unrolled): fewer live registers, less instruction-level parallelism
+  double len = 0;
+#pragma unroll 1
+  for (int p = 0; p < 2; ++p) {
+    double n_, d_;
+    aniso_point_nd(a, dl, p ? kNP0 : kNP1, dx, dy, dz, n_, d_);
+    len += sqrt_ratio(n_, d_);
+  }
+  return 0.5 * len;
+#else
   double np, dp, nm, dm;
   aniso_point_nd(a, dl, kNP1, dx, dy, dz, np, dp);  // xi = +XI: weights (kNP0, kNP1)
   aniso_point_nd(a, dl, kNP0, dx, dy, dz, nm, dm);  // xi = -XI: weights (kNP1, kNP0)
   return 0.5 * (sqrt_ratio(np, dp) + sqrt_ratio(nm, dm));
+#endif
 }
 
 // log-Euclidean field: the reference's eigen-solver with FMA contraction allowed
