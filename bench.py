@@ -429,8 +429,18 @@ def run_b200(a):
         dom_bytes = ab["edge_kernel"] if dom == "k_edges" else ab["elem_kernel"]
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
         step_ms = ms_total / a.steps
+        # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/traffic.json,
+        # written by scripts/profile_summary.py); only meaningful for the configuration that was profiled
+        traffic = None
+        try:
+            if n == 203 and a.field == "aniso" and world == 1 and a.jitter == 0:
+                tj = json.load(open(os.path.join(HERE, "profiles", "traffic.json")))
+                key = "%s<2, %d>" % (dom, 1 if a.fp == "fast" else 0)
+                traffic = float(tj[key]["dram_bytes_per_launch"])
+        except Exception:
+            traffic = None
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": int(dom_bytes), "kernel_ms": dom_ms,
                     "kernel_ms_all": {"vertex_pass": vert_ms, "edges": edge_ms, "elements": elem_ms},
                     "step_algorithmic_bytes": int(ab["total"]),
