@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmag.so")
 # every symbol include/mag.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
     "mag_create", "mag_destroy", "mag_last_error", "mag_set_stream", "mag_synchronize",
-    "mag_set_mesh", "mag_set_coords",
+    "mag_set_mesh", "mag_set_mesh_2d", "mag_set_coords",
     "mag_set_metric_identity", "mag_set_metric_iso", "mag_set_metric_aniso", "mag_set_metric_logm",
     "mag_set_flags", "mag_sweep",
     "mag_get_edge_lengths", "mag_get_qualities", "mag_get_flags", "mag_get_layer_ok", "mag_get_stats",
@@ -55,6 +55,7 @@ def lib():
     L.mag_set_stream.argtypes = [vp, vp]
     L.mag_synchronize.argtypes = [vp]
     L.mag_set_mesh.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp]
+    L.mag_set_mesh_2d.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, vp]
     L.mag_set_coords.argtypes = [vp, vp]
     L.mag_set_metric_identity.argtypes = [vp]
     L.mag_set_metric_iso.argtypes = [vp, vp]

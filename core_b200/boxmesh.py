@@ -82,6 +82,31 @@ def kuhn_box(nx, ny, nz, wx=1.0, wy=1.0, wz=1.0, x0=0, gnx=None, index_dtype=np.
     return xyz, np.ascontiguousarray(edge_v.astype(index_dtype)), np.ascontiguousarray(tet_v.astype(index_dtype))
 
 
+def tri_box(nx, ny, wx=1.0, wy=1.0, index_dtype=np.int32):
+    """The 2-D box apf::makeMdsBox(nx, ny, 0, wx, wy, 0, true) builds: (xyz [nv,3] with z = 0, edge_v, tri_v [2 nx ny, 3]).
+    Per cell the triangles (v, v+x, v+x+y) and (v+x+y, v+y, v) in that vertex order (BoxBuilder::buildTriangles,
+    apfBox.cc:209-217); edges: axis edges in vertex order, then the cell diagonals (v+x+y, v)."""
+    sx, sy = nx + 1, ny + 1
+    nv = sx * sy
+    xyz = np.zeros((sy, sx, 3), dtype=np.float64)
+    xyz[..., 0] = ((wx / nx) * np.arange(sx))[None, :]
+    xyz[..., 1] = ((wy / ny) * np.arange(sy))[:, None]
+    xyz = xyz.reshape(nv, 3)
+    vid = np.arange(nv, dtype=np.int64)
+    vx, vy = vid % sx, vid // sx
+    notmax = [vx < nx, vy < ny]
+    stride = np.array([1, sx], dtype=np.int64)
+    cand = np.stack([vid, vid], axis=1)
+    mask = np.stack(notmax, axis=1)
+    axis_edges = np.stack([cand[mask], (cand + stride[None, :])[mask]], axis=1)
+    cell = notmax[0] & notmax[1]
+    c0 = vid[cell]
+    diag = np.stack([c0 + 1 + sx, c0], axis=1)
+    tri = np.stack([np.stack([c0, c0 + 1, c0 + 1 + sx], axis=1), np.stack([c0 + 1 + sx, c0 + sx, c0], axis=1)], axis=1).reshape(-1, 3)
+    edge_v = np.concatenate([axis_edges, diag], axis=0)
+    return xyz, np.ascontiguousarray(edge_v.astype(index_dtype)), np.ascontiguousarray(tri.astype(index_dtype))
+
+
 def slab_bounds(gnx, nparts):
     """x-cell ranges [lo, hi) of each slab; remainders go to the first parts."""
     base, rem = divmod(gnx, nparts)

@@ -105,11 +105,12 @@ int mag_create(mag_ctx** out, int device)
   mag_ctx* c = new mag_ctx();
   c->device = device;
   c->own_stream = c->stream = nullptr;
-  c->nv = c->ne = c->nt = c->np = c->npy = 0;
+  c->nv = c->ne = c->nt = c->np = c->npy = c->ntri = 0;
+  c->dim = 3;
   c->kind = MAG_KIND_NONE;
   c->vertex_pass_valid = false;
   c->d_xyz = c->d_ma = c->d_mb = c->d_vedge = c->d_vpos = c->d_vq = nullptr;
-  c->d_edge_v = c->d_tet_v = c->d_prism_v = c->d_pyr_v = nullptr;
+  c->d_edge_v = c->d_tet_v = c->d_prism_v = c->d_pyr_v = c->d_tri_v = nullptr;
   c->d_edge_owned = c->d_elem_owned = nullptr;
   c->d_edge_flags = c->d_elem_flags = nullptr;
   c->d_len = c->d_qual = nullptr;
@@ -147,7 +148,7 @@ void mag_destroy(mag_ctx* c)
   cudaStreamSynchronize(c->stream);
   magc_destroy(c);
   cudaFree(c->d_xyz); cudaFree(c->d_ma); cudaFree(c->d_mb); cudaFree(c->d_vedge); cudaFree(c->d_vpos); cudaFree(c->d_vq);
-  cudaFree(c->d_edge_v); cudaFree(c->d_tet_v); cudaFree(c->d_prism_v); cudaFree(c->d_pyr_v);
+  cudaFree(c->d_edge_v); cudaFree(c->d_tet_v); cudaFree(c->d_prism_v); cudaFree(c->d_pyr_v); cudaFree(c->d_tri_v);
   cudaFree(c->d_edge_owned); cudaFree(c->d_elem_owned); cudaFree(c->d_edge_flags); cudaFree(c->d_elem_flags);
   cudaFree(c->d_len); cudaFree(c->d_qual); cudaFree(c->d_layer_ok); cudaFree(c->d_layer_codes);
   cudaFree(c->d_stats); cudaFreeHost(c->h_stats); cudaFree(c->d_block_sums);
@@ -172,19 +173,22 @@ int mag_synchronize(mag_ctx* c)
   return MAG_OK;
 }
 
-int mag_set_mesh(mag_ctx* c, int64_t nv, const double* xyz, int64_t ne, const int32_t* edge_v,
-                 int64_t nt, const int32_t* tet_v, int64_t np, const int32_t* prism_v,
-                 int64_t npy, const int32_t* pyr_v, const uint8_t* edge_owned, const uint8_t* elem_owned)
+static int set_mesh_impl(mag_ctx* c, int dim, int64_t nv, const double* xyz, int64_t ne, const int32_t* edge_v,
+                         int64_t nt, const int32_t* tet_v, int64_t np, const int32_t* prism_v,
+                         int64_t npy, const int32_t* pyr_v, int64_t ntri, const int32_t* tri_v,
+                         const uint8_t* edge_owned, const uint8_t* elem_owned)
 {
   CHECK_CTX(c);
-  if (nv < 0 || ne < 0 || nt < 0 || np < 0 || npy < 0) return mag_fail(c, MAG_ERR_ARG, "mag_set_mesh: negative count");
-  if (nv > 0x7fffffffLL || ne > 0x7fffffffLL || np + npy + nt > 0x7fffffffLL)
+  if (nv < 0 || ne < 0 || nt < 0 || np < 0 || npy < 0 || ntri < 0) return mag_fail(c, MAG_ERR_ARG, "mag_set_mesh: negative count");
+  if (nv > 0x7fffffffLL || ne > 0x7fffffffLL || np + npy + nt + ntri > 0x7fffffffLL)
     return mag_fail(c, MAG_ERR_ARG, "mag_set_mesh: entity ids are int32 (MDS_ID_TYPE=int, mds/CMakeLists.txt:7)");
-  if ((nv && !xyz) || (ne && !edge_v) || (nt && !tet_v) || (np && !prism_v) || (npy && !pyr_v))
+  if ((nv && !xyz) || (ne && !edge_v) || (nt && !tet_v) || (np && !prism_v) || (npy && !pyr_v) || (ntri && !tri_v))
     return mag_fail(c, MAG_ERR_ARG, "mag_set_mesh: null array with non-zero count");
   int rc;
-  const int64_t nel = np + npy + nt;
-  const bool same_shape = nv == c->nv && ne == c->ne && nt == c->nt && np == c->np && npy == c->npy &&
+  const int64_t nel = np + npy + nt + ntri;
+  if (dim != c->dim) c->vertex_pass_valid = false;
+  c->dim = dim;
+  const bool same_shape = nv == c->nv && ne == c->ne && nt == c->nt && np == c->np && npy == c->npy && ntri == c->ntri &&
                           (edge_owned != nullptr) == (c->d_edge_owned != nullptr) &&
                           (elem_owned != nullptr) == (c->d_elem_owned != nullptr);
   if (!same_shape) {
@@ -196,7 +200,7 @@ int mag_set_mesh(mag_ctx* c, int64_t nv, const double* xyz, int64_t ne, const in
     if ((rc = dev_alloc(c, c->d_xyz, (size_t)nv * 3)) || (rc = dev_alloc(c, c->d_vpos, (size_t)nv * 4)) ||
         (rc = dev_alloc(c, c->d_vq, (size_t)nv * 10)) || (rc = dev_alloc(c, c->d_edge_v, (size_t)ne * 2)) ||
         (rc = dev_alloc(c, c->d_tet_v, (size_t)nt * 4)) || (rc = dev_alloc(c, c->d_prism_v, (size_t)np * 6)) ||
-        (rc = dev_alloc(c, c->d_pyr_v, (size_t)npy * 5)) ||
+        (rc = dev_alloc(c, c->d_pyr_v, (size_t)npy * 5)) || (rc = dev_alloc(c, c->d_tri_v, (size_t)ntri * 3)) ||
         (rc = dev_alloc(c, c->d_edge_owned, edge_owned ? (size_t)ne : 0)) ||
         (rc = dev_alloc(c, c->d_elem_owned, elem_owned ? (size_t)nel : 0)) ||
         (rc = dev_alloc(c, c->d_edge_flags, (size_t)ne)) || (rc = dev_alloc(c, c->d_elem_flags, (size_t)nel)) ||
@@ -204,7 +208,7 @@ int mag_set_mesh(mag_ctx* c, int64_t nv, const double* xyz, int64_t ne, const in
         (rc = dev_alloc(c, c->d_layer_ok, (size_t)(np + npy))) || (rc = dev_alloc(c, c->d_layer_codes, (size_t)(np + npy))) ||
         (rc = dev_alloc(c, c->d_near_edge, (size_t)ne)) || (rc = dev_alloc(c, c->d_near_elem, (size_t)nel)))
       return rc;
-    c->nv = nv; c->ne = ne; c->nt = nt; c->np = np; c->npy = npy;
+    c->nv = nv; c->ne = ne; c->nt = nt; c->np = np; c->npy = npy; c->ntri = ntri;
     if (nel) MAG_CUDA(c, cudaMemsetAsync(c->d_qual, 0, (size_t)nel * 8, c->stream));
   }
   // a new mesh starts with no flags (ma::getFlags returns 0 when the tag is absent, maAdapt.cc:80-88)
@@ -212,12 +216,25 @@ int mag_set_mesh(mag_ctx* c, int64_t nv, const double* xyz, int64_t ne, const in
   if (nel) MAG_CUDA(c, cudaMemsetAsync(c->d_elem_flags, 0, (size_t)nel * 4, c->stream));
   if ((rc = upload(c, c->d_xyz, xyz, (size_t)nv * 3)) || (rc = upload(c, c->d_edge_v, edge_v, (size_t)ne * 2)) ||
       (rc = upload(c, c->d_tet_v, tet_v, (size_t)nt * 4)) || (rc = upload(c, c->d_prism_v, prism_v, (size_t)np * 6)) ||
-      (rc = upload(c, c->d_pyr_v, pyr_v, (size_t)npy * 5)))
+      (rc = upload(c, c->d_pyr_v, pyr_v, (size_t)npy * 5)) || (rc = upload(c, c->d_tri_v, tri_v, (size_t)ntri * 3)))
     return rc;
   if (edge_owned && (rc = upload(c, c->d_edge_owned, edge_owned, (size_t)ne))) return rc;
   if (elem_owned && (rc = upload(c, c->d_elem_owned, elem_owned, (size_t)nel))) return rc;
   if ((rc = magk_build_schedule(c))) return rc;
   return repack(c);
+}
+
+int mag_set_mesh(mag_ctx* c, int64_t nv, const double* xyz, int64_t ne, const int32_t* edge_v,
+                 int64_t nt, const int32_t* tet_v, int64_t np, const int32_t* prism_v,
+                 int64_t npy, const int32_t* pyr_v, const uint8_t* edge_owned, const uint8_t* elem_owned)
+{
+  return set_mesh_impl(c, 3, nv, xyz, ne, edge_v, nt, tet_v, np, prism_v, npy, pyr_v, 0, nullptr, edge_owned, elem_owned);
+}
+
+int mag_set_mesh_2d(mag_ctx* c, int64_t nv, const double* xyz, int64_t ne, const int32_t* edge_v,
+                    int64_t ntri, const int32_t* tri_v, const uint8_t* edge_owned, const uint8_t* elem_owned)
+{
+  return set_mesh_impl(c, 2, nv, xyz, ne, edge_v, 0, nullptr, 0, nullptr, 0, nullptr, ntri, tri_v, edge_owned, elem_owned);
 }
 
 int mag_set_coords(mag_ctx* c, const double* xyz)
@@ -251,7 +268,7 @@ int mag_set_metric_logm(mag_ctx* c, const double* logM) { return c ? set_metric(
 int mag_set_flags(mag_ctx* c, const int32_t* edge_flags, const int32_t* elem_flags)
 {
   CHECK_CTX(c);
-  const int64_t nel = c->np + c->npy + c->nt;
+  const int64_t nel = c->np + c->npy + c->nt + c->ntri;
   if (c->ne) {
     if (edge_flags) { int rc = upload(c, c->d_edge_flags, edge_flags, (size_t)c->ne); if (rc) return rc; }
     else MAG_CUDA(c, cudaMemsetAsync(c->d_edge_flags, 0, (size_t)c->ne * 4, c->stream));
@@ -288,7 +305,7 @@ int mag_get_edge_lengths(mag_ctx* c, double* out)
 int mag_get_qualities(mag_ctx* c, double* out)
 {
   CHECK_CTX(c);
-  int rc = download(c, out, c->d_qual, (size_t)(c->np + c->npy + c->nt));
+  int rc = download(c, out, c->d_qual, (size_t)(c->np + c->npy + c->nt + c->ntri));
   if (rc) return rc;
   MAG_CUDA(c, cudaStreamSynchronize(c->stream));
   return MAG_OK;
@@ -298,7 +315,7 @@ int mag_get_flags(mag_ctx* c, int32_t* edge_flags, int32_t* elem_flags)
   CHECK_CTX(c);
   int rc;
   if (edge_flags && (rc = download(c, edge_flags, c->d_edge_flags, (size_t)c->ne))) return rc;
-  if (elem_flags && (rc = download(c, elem_flags, c->d_elem_flags, (size_t)(c->np + c->npy + c->nt)))) return rc;
+  if (elem_flags && (rc = download(c, elem_flags, c->d_elem_flags, (size_t)(c->np + c->npy + c->nt + c->ntri)))) return rc;
   MAG_CUDA(c, cudaStreamSynchronize(c->stream));
   return MAG_OK;
 }

@@ -42,6 +42,8 @@ struct mag_ctx {
   std::string err;
 
   int64_t nv, ne, nt, np, npy;
+  int64_t ntri; // 2-D meshes: the elements are triangles (nt = np = npy = 0)
+  int dim;      // mesh dimension (3, or 2 after mag_set_mesh_2d)
   int kind;
   bool vertex_pass_valid;
 
@@ -57,6 +59,7 @@ struct mag_ctx {
   int32_t* d_tet_v;   // [nt][4]
   int32_t* d_prism_v; // [np][6]
   int32_t* d_pyr_v;   // [npy][5]
+  int32_t* d_tri_v;   // [ntri][3]
   uint8_t* d_edge_owned; // may be null
   uint8_t* d_elem_owned; // may be null
   int32_t* d_edge_flags; // [ne]

@@ -131,7 +131,7 @@ __global__ void k_pack12_logm(int64_t nv, const double* __restrict__ xyz, const 
 // Q_v = SizeField::getTransform(vertex, xi=0) and det Q_v (apf::getJacobianDeterminant(Q,3)).
 // The vertex shape value is exactly 1.0 so "interpolation" returns the node value.
 template <int KIND>
-__global__ void k_vertex_pass(int64_t nv, const double* __restrict__ vedge, double* __restrict__ vpos,
+__global__ void k_vertex_pass(int64_t nv, int dim, const double* __restrict__ vedge, double* __restrict__ vpos,
                               double* __restrict__ vq, MagDevStats* st)
 {
   int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -161,7 +161,9 @@ __global__ void k_vertex_pass(int64_t nv, const double* __restrict__ vedge, doub
       if (rc != 1) atomicAdd(&st->n_eigen_fail, 1ull);
     }
   }
-  double det = magst::det3(Q);
+  // apf::getJacobianDeterminant(Q, mesh dimension) (apfVectorElement.cc:68-91): det in 3-D, |row0 x row1| in 2-D
+  double det = dim == 3 ? magst::det3(Q)
+                        : magst::length(magst::cross(V3{Q.m[0][0], Q.m[0][1], Q.m[0][2]}, V3{Q.m[1][0], Q.m[1][1], Q.m[1][2]}));
   *chunk_ptr_w(vpos, nv, 0, v) = make_double2(x, y);
   *chunk_ptr_w(vpos, nv, 1, v) = make_double2(z, det);
   *chunk_ptr_w(vq, nv, 0, v) = make_double2(Q.m[0][0], Q.m[0][1]);
@@ -746,6 +748,122 @@ k_tets(int64_t nt, int64_t elem_off, int64_t nv, const int4* __restrict__ tet_v,
   }
 }
 
+// ------------------------------------------------------------------ triangles (2-D meshes)
+// measureTriQuality (maQuality.cc:110-136): 48 A^2 / (sum l^2)^2 with the transform of the max-"Jacobian" vertex
+// (|row0 x row1| of Q_v on a 2-D mesh) or of the centroid (xi = 1/3, 1/3).  2-D meshes are small next to the 3-D
+// benchmark parts, so this kernel is a plain one-thread-per-triangle grid-stride loop; near-threshold triangles are
+// re-evaluated in place.
+template <int KIND>
+__device__ __forceinline__ void centroid_transform_tri(const double* __restrict__ vedge, int64_t nv, const int32_t vid[3], M3& Q, int* eig)
+{
+  constexpr double N1 = 1. / 3., N0 = 1 - 1. / 3. - 1. / 3.;
+  if (KIND == MAG_KIND_IDENTITY) { magst::identity(Q); return; }
+  if (KIND == MAG_KIND_ISO) {
+    double h = 0;
+#pragma unroll
+    for (int n = 0; n < 3; ++n) {
+      double r[4];
+      load_rec4(vedge, nv, vid[n], r);
+      h = magst::add(h, magst::mul(r[3], n ? N1 : N0));
+    }
+    magst::identity(Q);
+    double ih = magst::div(1.0, h);
+    Q.m[0][0] = ih; Q.m[1][1] = ih; Q.m[2][2] = ih;
+    return;
+  }
+  double c[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) c[i] = 0;
+#pragma unroll
+  for (int n = 0; n < 3; ++n) {
+    Rec12 r = load_rec12(vedge, nv, vid[n]);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) c[i] = magst::add(c[i], magst::mul(r.v[3 + i], n ? N1 : N0));
+  }
+  if (KIND == MAG_KIND_ANISO) {
+    magst::transform_aniso(V3{c[3], c[4], c[5]}, V3{c[6], c[7], c[8]}, c[0], c[1], c[2], Q);
+  } else {
+    M3 A;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) A.m[i / 3][i % 3] = c[i];
+    if (magst::transform_logm(A, Q) != 1) *eig = 1;
+  }
+}
+
+template <int KIND, bool FAST>
+__device__ __forceinline__ double tri_quality_eval(const int32_t vid[3], int64_t nv, const double* __restrict__ vpos,
+                                                   const double* __restrict__ vq, const double* __restrict__ vedge,
+                                                   int use_max, int* eig)
+{
+  double p[3][4];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) load_rec4(vpos, nv, vid[i], p[i]);
+  M3 Q;
+  double detQ;
+  if (use_max) {
+    int32_t vb = vid[0];
+    double maxJ = -1.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      if (p[i][3] > maxJ) { maxJ = p[i][3]; vb = vid[i]; }
+    load_q(vq, nv, vb, Q, detQ);
+  } else {
+    centroid_transform_tri<KIND>(vedge, nv, vid, Q, eig);
+  }
+  V3 x[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) x[i] = V3{p[i][0], p[i][1], p[i][2]};
+  return FAST ? magfa::tri_quality(x, Q) : magst::tri_quality(x, Q);
+}
+
+template <int KIND, bool FAST>
+__global__ void __launch_bounds__(kThreads)
+k_tris(int64_t nt, int64_t nv, const int32_t* __restrict__ tri_v, const double* __restrict__ vpos,
+       const double* __restrict__ vq, const double* __restrict__ vedge, const uint8_t* __restrict__ owned_arr,
+       int32_t* __restrict__ flags, double* __restrict__ qual, SweepParams P, MagDevStats* st,
+       int32_t* __restrict__ near_list)
+{
+  unsigned c_bad = 0, c_eval = 0, c_err = 0;
+  unsigned long long minkey = ~0ull;
+  int eig_any = 0;
+  const bool do_bad = P.ops & MAG_OP_MARK_BAD, want_q = P.ops & MAG_OP_QUALITIES;
+  const int64_t nloop = (nt + kThreads - 1) / kThreads * kThreads;   // whole warps stay together for the reductions
+  for (int64_t t = blockIdx.x * (int64_t)kThreads + threadIdx.x; t < nloop; t += (int64_t)gridDim.x * kThreads) {
+    if (t >= nt) continue;
+    int32_t f = flags[t];
+    const int32_t f_in = f;
+    if (do_bad && (f & MAG_BAD_QUALITY)) ++c_err;
+    const bool need_bad = do_bad && !(f & MAG_OK_QUALITY);
+    if (!(want_q || need_bad)) continue;
+    const int32_t vid[3] = {tri_v[3 * t], tri_v[3 * t + 1], tri_v[3 * t + 2]};
+    double qv = tri_quality_eval<KIND, FAST>(vid, nv, vpos, vq, vedge, P.use_max, &eig_any);
+    if (need_bad && near_thr(qv, P.good_q)) {
+      const unsigned long long k = atomicAdd(&st->n_near_elem, 1ull);
+      near_list[k] = (int32_t)t;
+      if (FAST) qv = tri_quality_eval<KIND, false>(vid, nv, vpos, vq, vedge, P.use_max, &eig_any);
+    }
+    if (want_q) {
+      qual[t] = qv;
+      const unsigned long long k = dkey(qv);
+      minkey = k < minkey ? k : minkey;
+    }
+    if (need_bad) {
+      const bool owned = owned_arr ? (owned_arr[t] != 0) : true;
+      ++c_eval;
+      mark_tet(qv, f, owned, P, c_bad);
+      if (f != f_in) flags[t] = f;
+    }
+  }
+  if (eig_any) atomicAdd(&st->n_eigen_fail, 1ull);
+  warp_count_to(c_bad, &st->n_bad);
+  warp_count_to(c_eval, &st->n_elems_eval);
+  warp_count_to(c_err, &st->n_flag_err);
+  if (want_q) {
+    const unsigned long long m = warp_min_u64(minkey);
+    if ((threadIdx.x & 31) == 0 && m != ~0ull) atomicMin(&st->min_q_key, m);
+  }
+}
+
 // ------------------------------------------------------------------ prisms / pyramids
 // a non-simplex element that reaches markBadQuality without OK_QUALITY would make the
 // reference call a null table entry (maQuality.cc:169-182): report instead of crash.
@@ -917,12 +1035,25 @@ int magk_vertex_pass(mag_ctx* c)
   if (c->nv == 0) return MAG_OK;
   unsigned g = grid_for(c->nv);
   switch (c->kind) {
-    case MAG_KIND_IDENTITY: k_vertex_pass<MAG_KIND_IDENTITY><<<g, kThreads, 0, c->stream>>>(c->nv, c->d_vedge, c->d_vpos, c->d_vq, c->d_stats); break;
-    case MAG_KIND_ISO: k_vertex_pass<MAG_KIND_ISO><<<g, kThreads, 0, c->stream>>>(c->nv, c->d_vedge, c->d_vpos, c->d_vq, c->d_stats); break;
-    case MAG_KIND_ANISO: k_vertex_pass<MAG_KIND_ANISO><<<g, kThreads, 0, c->stream>>>(c->nv, c->d_vedge, c->d_vpos, c->d_vq, c->d_stats); break;
-    case MAG_KIND_LOGM: k_vertex_pass<MAG_KIND_LOGM><<<g, kThreads, 0, c->stream>>>(c->nv, c->d_vedge, c->d_vpos, c->d_vq, c->d_stats); break;
+    case MAG_KIND_IDENTITY: k_vertex_pass<MAG_KIND_IDENTITY><<<g, kThreads, 0, c->stream>>>(c->nv, c->dim, c->d_vedge, c->d_vpos, c->d_vq, c->d_stats); break;
+    case MAG_KIND_ISO: k_vertex_pass<MAG_KIND_ISO><<<g, kThreads, 0, c->stream>>>(c->nv, c->dim, c->d_vedge, c->d_vpos, c->d_vq, c->d_stats); break;
+    case MAG_KIND_ANISO: k_vertex_pass<MAG_KIND_ANISO><<<g, kThreads, 0, c->stream>>>(c->nv, c->dim, c->d_vedge, c->d_vpos, c->d_vq, c->d_stats); break;
+    case MAG_KIND_LOGM: k_vertex_pass<MAG_KIND_LOGM><<<g, kThreads, 0, c->stream>>>(c->nv, c->dim, c->d_vedge, c->d_vpos, c->d_vq, c->d_stats); break;
     default: return mag_fail(c, MAG_ERR_ARG, "no size field set");
   }
+  MAG_CUDA(c, cudaGetLastError());
+  c->n_launches++;
+  return MAG_OK;
+}
+
+template <int KIND>
+static int launch_tris(mag_ctx* c, const SweepParams& P, bool fast)
+{
+  unsigned g = grid_for(c->ntri);
+  const unsigned cap = (unsigned)c->n_sms * 8;
+  if (g > cap) g = cap;
+  if (fast) k_tris<KIND, true><<<g, kThreads, 0, c->stream>>>(c->ntri, c->nv, c->d_tri_v, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_owned, c->d_elem_flags, c->d_qual, P, c->d_stats, c->d_near_elem);
+  else k_tris<KIND, false><<<g, kThreads, 0, c->stream>>>(c->ntri, c->nv, c->d_tri_v, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_owned, c->d_elem_flags, c->d_qual, P, c->d_stats, c->d_near_elem);
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;
   return MAG_OK;
@@ -1051,6 +1182,15 @@ int magk_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double 
         case MAG_KIND_ISO: rc = launch_tets<MAG_KIND_ISO>(c, P, fast); break;
         case MAG_KIND_ANISO: rc = launch_tets<MAG_KIND_ANISO>(c, P, fast); break;
         default: rc = launch_tets<MAG_KIND_LOGM>(c, P, fast); break;
+      }
+      if (rc) return rc;
+    }
+    if (c->ntri) {
+      switch (c->kind) {
+        case MAG_KIND_IDENTITY: rc = launch_tris<MAG_KIND_IDENTITY>(c, P, fast); break;
+        case MAG_KIND_ISO: rc = launch_tris<MAG_KIND_ISO>(c, P, fast); break;
+        case MAG_KIND_ANISO: rc = launch_tris<MAG_KIND_ANISO>(c, P, fast); break;
+        default: rc = launch_tris<MAG_KIND_LOGM>(c, P, fast); break;
       }
       if (rc) return rc;
     }

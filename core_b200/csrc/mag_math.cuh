@@ -283,6 +283,29 @@ static __device__ __forceinline__ double tet_quality(const V3 x[4], const M3& Q)
   return div(mul(c, mul(V, V)), s3);
 }
 
+
+// measureTriQuality with a fixed Q (maQuality.cc:126-135): edges in tri_edge_verts order {01,12,20}, l = 2*|row0|;
+// A = |row0(JQ) x row1(JQ)| / 2 with J rows x1-x0, x2-x0 (triangle N1 rule, w = 1/2)
+static __device__ __forceinline__ double tri_quality(const V3 x[3], const M3& Q)
+{
+  const int ea[3] = {0, 1, 2}, eb[3] = {1, 2, 0};
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double l = mul(2.0, row0_length(edge_j0(x[ea[i]], x[eb[i]]), Q));
+    s = add(s, mul(l, l));
+  }
+  V3 jq[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double j0 = add(-x[0].x, x[i + 1].x), j1 = add(-x[0].y, x[i + 1].y), j2 = add(-x[0].z, x[i + 1].z);
+    jq[i].x = add(add(mul(j0, Q.m[0][0]), mul(j1, Q.m[1][0])), mul(j2, Q.m[2][0]));
+    jq[i].y = add(add(mul(j0, Q.m[0][1]), mul(j1, Q.m[1][1])), mul(j2, Q.m[2][1]));
+    jq[i].z = add(add(mul(j0, Q.m[0][2]), mul(j1, Q.m[1][2])), mul(j2, Q.m[2][2]));
+  }
+  double A = mul(1.0 / 2.0, length(cross(jq[0], jq[1])));
+  return div(mul(48.0, mul(A, A)), mul(s, s));
+}
 };
 
 typedef MagMath<StrictOps> magst;

@@ -139,4 +139,23 @@ __device__ __forceinline__ double tet_quality(const V3 x[4], const M3& Q, double
   return V < 0 ? -q : q;
 }
 
+// triangle mean ratio in metric space: y_i = (x_i - x_0) Q, edges y1, y2 - y1, y2; A = |y1 x y2| / 2
+__device__ __forceinline__ double tri_quality(const V3 x[3], const M3& Q)
+{
+  double y[2][3];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double ex = x[i + 1].x - x[0].x, ey = x[i + 1].y - x[0].y, ez = x[i + 1].z - x[0].z;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) y[i][k] = ex * Q.m[0][k] + ey * Q.m[1][k] + ez * Q.m[2][k];
+  }
+  const double u = y[1][0] - y[0][0], v = y[1][1] - y[0][1], w = y[1][2] - y[0][2];
+  const double s = (y[0][0] * y[0][0] + y[0][1] * y[0][1] + y[0][2] * y[0][2]) + (u * u + v * v + w * w) +
+                   (y[1][0] * y[1][0] + y[1][1] * y[1][1] + y[1][2] * y[1][2]);
+  const double cx = y[0][1] * y[1][2] - y[0][2] * y[1][1], cy = y[0][2] * y[1][0] - y[0][0] * y[1][2],
+               cz = y[0][0] * y[1][1] - y[0][1] * y[1][0];
+  const double A2 = 0.25 * (cx * cx + cy * cy + cz * cz);
+  return 48.0 * A2 / (s * s);
+}
+
 } // namespace magfa

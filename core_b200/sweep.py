@@ -18,6 +18,7 @@ from ._lib import lib, MagStats
 MAXLENGTH = 1.5
 MINLENGTH = 0.5
 GOOD_QUALITY_3D = 0.027
+GOOD_QUALITY_2D = 0.2
 
 # ma/maAdapt.h:17-37
 SPLIT, DONT_SPLIT, COLLAPSE, DONT_COLLAPSE, CHECKED, BAD_QUALITY, OK_QUALITY = (1 << i for i in range(7))
@@ -67,7 +68,7 @@ class Part:
             raise MagError(rc, self._L.mag_last_error(None).decode())
         self._h = h
         self.device = device
-        self.nv = self.ne = self.nt = self.np_ = self.npy = 0
+        self.nv = self.ne = self.nt = self.np_ = self.npy = self.ntri = 0
         self._keep = []
 
     # ---- plumbing
@@ -94,7 +95,7 @@ class Part:
 
     @property
     def nelem(self):
-        return self.np_ + self.npy + self.nt
+        return self.np_ + self.npy + self.nt + self.ntri
 
     # ---- export
     def set_mesh(self, xyz, edge_v, tet_v=None, prism_v=None, pyr_v=None, edge_owned=None, elem_owned=None):
@@ -105,10 +106,23 @@ class Part:
         n = lambda a, k: 0 if a is None else int(a.numel() if hasattr(a, "numel") else a.size) // k
         self.nv, self.ne, self.nt = n(xyz, 3), n(edge_v, 2), n(tet_v, 4)
         self.np_, self.npy = n(prism_v, 6), n(pyr_v, 5)
+        self.ntri = 0
         self._ck(self._L.mag_set_mesh(self._h, self.nv, _ptr(xyz), self.ne, _ptr(edge_v), self.nt, _ptr(tet_v),
                                       self.np_, _ptr(prism_v), self.npy, _ptr(pyr_v),
                                       _ptr(edge_owned), _ptr(elem_owned)))
         self.synchronize()  # host buffers may be temporaries
+
+    def set_mesh_2d(self, xyz, edge_v, tri_v, edge_owned=None, elem_owned=None):
+        """A 2-D part (triangles are the elements; ma::measureTriQuality)."""
+        xyz = _arr(xyz, np.float64)
+        edge_v, tri_v = _arr(edge_v, np.int32), _arr(tri_v, np.int32)
+        edge_owned, elem_owned = _arr(edge_owned, np.uint8), _arr(elem_owned, np.uint8)
+        n = lambda a, k: 0 if a is None else int(a.numel() if hasattr(a, "numel") else a.size) // k
+        self.nv, self.ne, self.ntri = n(xyz, 3), n(edge_v, 2), n(tri_v, 3)
+        self.nt = self.np_ = self.npy = 0
+        self._ck(self._L.mag_set_mesh_2d(self._h, self.nv, _ptr(xyz), self.ne, _ptr(edge_v), self.ntri, _ptr(tri_v),
+                                         _ptr(edge_owned), _ptr(elem_owned)))
+        self.synchronize()
 
     def set_coords(self, xyz):
         xyz = _arr(xyz, np.float64)

@@ -7,6 +7,7 @@
  *   ma::SizeField::measure / shouldSplit / shouldCollapse   ma/maSize.h:30-54, ma/maSize.cc:208-224
  *   AnisoSizeField / LogAnisoSizeField / IsoSizeField::getTransform   ma/maSize.cc:395-413, 506-522, 581-616
  *   ma::measureElementQuality (tets, mean ratio cubed)      ma/maShape.h:24-26, ma/maQuality.cc:139-182
+ *   ma::measureTriQuality (2-D meshes)                      ma/maQuality.cc:110-136
  *   ma::markEdgesToSplit                                    ma/maRefine.h:52,  ma/maRefine.cc:395-400
  *   ma::markEdgesToCollapse                                 ma/maCoarsen.cc:287-292
  *   ma::markBadQuality / getMinQuality                      ma/maShape.cc:132-169
@@ -113,6 +114,13 @@ int mag_set_mesh(mag_ctx* c, int64_t nv, const double* xyz,
                  int64_t np, const int32_t* prism_v,
                  int64_t npy, const int32_t* pyr_v,
                  const uint8_t* edge_owned, const uint8_t* elem_owned);
+/* a 2-D part: the elements are triangles (ma::measureTriQuality, ma/maQuality.cc:110-136; the max-"Jacobian" vertex is
+   chosen by |row0 x row1| of Q_v, apf/apfVectorElement.cc:75-84).  tri_v [ntri][3]; element arrays (flags, owned, qualities)
+   have ntri entries; good_quality defaults to 0.2 in 2-D (ma/maInput.cc:32-46, the caller passes it). */
+int mag_set_mesh_2d(mag_ctx* c, int64_t nv, const double* xyz,
+                    int64_t ne, const int32_t* edge_v,
+                    int64_t ntri, const int32_t* tri_v,
+                    const uint8_t* edge_owned, const uint8_t* elem_owned);
 /* moved vertices, same connectivity (apf::Mesh2::setPoint) */
 int mag_set_coords(mag_ctx* c, const double* xyz);
 

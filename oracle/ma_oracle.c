@@ -405,6 +405,72 @@ double mao_tet_quality(int kind, const double* xyz, const double* ma, const doub
   return 15552 * (V * V) / (s * s * s);
 }
 
+/* ----------------------------------------------------- triangle mean-ratio quality (2-D meshes)
+ * measureTriQuality, maQuality.cc:110-136: 48 A^2 / (sum l^2)^2 with a fixed Q;
+ * getMetricWithMaxJacobean uses getJacobianDeterminant(Q, 2) = |row0 x row1|
+ * (apfVectorElement.cc:75-84) on a 2-D mesh; triangle N1 rule: xi=(1/3,1/3), w=1/2
+ * (apfIntegrate.cc:134-145); triangle shape functions (apfShape.cc:141-170):
+ * N = (1-xi0-xi1, xi0, xi1), grads (-1,-1),(1,0),(0,1). */
+static const int tri_edge_verts[3][2] = {{0, 1}, {1, 2}, {2, 0}}; /* apfMesh.cc:28-33 */
+static double gen_det2(const double A[3][3])
+{
+  double c[3];
+  cross3(A[0], A[1], c);
+  return len3(c);
+}
+double mao_tri_quality(int kind, const double* xyz, const double* ma, const double* mb,
+                       const int32_t* tv, int use_max, int* status)
+{
+  metric_t mt = {kind, ma, mb};
+  double Q[3][3];
+  if (use_max) {
+    double maxJ = -1.0;
+    for (int i = 0; i < 3; ++i) {
+      double cq[3][3];
+      double N[1] = {1.0};
+      int rc = transform_at(&mt, tv + i, N, 1, cq);
+      if (rc != 1 && status) *status = rc;
+      double cj = gen_det2((const double(*)[3])cq);
+      if (cj > maxJ) { maxJ = cj; memcpy(Q, cq, sizeof(Q)); }
+    }
+    if (maxJ == -1.0) memset(Q, 0, sizeof(Q));
+  } else {
+    double N[3] = {1 - 1. / 3. - 1. / 3., 1. / 3., 1. / 3.};
+    int rc = transform_at(&mt, tv, N, 3, Q);
+    if (rc != 1 && status) *status = rc;
+  }
+  const double* x[3];
+  for (int i = 0; i < 3; ++i) x[i] = xyz + 3 * (size_t)tv[i];
+  double l[3];
+  for (int i = 0; i < 3; ++i) {
+    double j0[3];
+    edge_jacobian_row0(x[tri_edge_verts[i][0]], x[tri_edge_verts[i][1]], j0);
+    double m = 0;
+    m += 2 * row0_length(j0, (const double(*)[3])Q);
+    l[i] = m;
+  }
+  static const double g[3][3] = {{-1, -1, 0}, {1, 0, 0}, {0, 1, 0}};
+  double J[3][3];
+  for (int i = 0; i < 3; ++i) for (int c = 0; c < 3; ++c) J[i][c] = x[0][c] * g[0][i];
+  for (int n = 1; n < 3; ++n)
+    for (int i = 0; i < 3; ++i) for (int c = 0; c < 3; ++c) J[i][c] = J[i][c] + x[n][c] * g[n][i];
+  double JQ[3][3];
+  matmul3((const double(*)[3])J, (const double(*)[3])Q, JQ);
+  double A = 0;
+  A += (1.0 / 2.0) * gen_det2((const double(*)[3])JQ);
+  double s = 0;
+  for (int i = 0; i < 3; ++i) s += l[i] * l[i];
+  return 48 * (A * A) / (s * s);
+}
+int mao_tri_qualities(int kind, const double* xyz, const double* ma, const double* mb,
+                      int64_t nt, const int32_t* tri_v, int use_max, double* out)
+{
+  int status = 1;
+  for (int64_t t = 0; t < nt; ++t)
+    out[t] = mao_tri_quality(kind, xyz, ma, mb, tri_v + 3 * t, use_max, &status);
+  return status;
+}
+
 /* ----------------------------------------------------- prism / pyramid validity
  * isPrismOk / isPyramidOk, maQuality.cc:490-560; apf::Plane apfGeometry.cc:28-45;
  * prism_rotation / pyramid_rotation maTables.cc */

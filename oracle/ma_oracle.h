@@ -27,6 +27,10 @@ double mao_edge_length(int kind, const double* xyz, const double* ma, const doub
 int mao_vertex_transform(int kind, const double* ma, const double* mb, int32_t v, double Q[3][3]);
 double mao_tet_quality(int kind, const double* xyz, const double* ma, const double* mb,
                        const int32_t* tv, int use_max, int* status);
+double mao_tri_quality(int kind, const double* xyz, const double* ma, const double* mb,
+                       const int32_t* tv, int use_max, int* status);
+int mao_tri_qualities(int kind, const double* xyz, const double* ma, const double* mb,
+                      int64_t nt, const int32_t* tri_v, int use_max, double* out);
 int mao_prism_ok(const double* xyz, const int32_t* pv, int* good_codes);
 int mao_pyramid_ok(const double* xyz, const int32_t* pv, int* good_rotation);
 

@@ -40,6 +40,7 @@ def lib():
         L.mao_logm_from_frame.argtypes = [C.c_int, vp, vp, vp]
         L.mao_edge_lengths.argtypes = [C.c_int, vp, vp, vp, i64, vp, vp]
         L.mao_tet_qualities.argtypes = [C.c_int, vp, vp, vp, i64, vp, C.c_int, vp]
+        L.mao_tri_qualities.argtypes = [C.c_int, vp, vp, vp, i64, vp, C.c_int, vp]
         L.mao_vertex_transforms.argtypes = [C.c_int, vp, vp, i64, vp]
         L.mao_prism_ok.argtypes = [vp, vp, vp]
         L.mao_pyramid_ok.argtypes = [vp, vp, vp]
@@ -104,6 +105,16 @@ def tet_qualities(kind, xyz, ma, mb, tet_v, use_max=True):
     nt = tet_v.size // 4
     out = np.zeros(nt)
     rc = lib().mao_tet_qualities(kind, _p(xyz), _p(ma), _p(mb), nt, _p(tet_v), int(use_max), _p(out))
+    assert rc == 1
+    return out
+
+
+def tri_qualities(kind, xyz, ma, mb, tri_v, use_max=True):
+    """measureTriQuality on a 2-D mesh (maQuality.cc:110-136)."""
+    xyz, ma, mb, tri_v = _f64(xyz), _f64(ma), _f64(mb), _i32(tri_v)
+    nt = tri_v.size // 3
+    out = np.zeros(nt)
+    rc = lib().mao_tri_qualities(kind, _p(xyz), _p(ma), _p(mb), nt, _p(tri_v), int(use_max), _p(out))
     assert rc == 1
     return out
 

@@ -81,6 +81,8 @@ class RefMesh:
         self.counts = c
         self.nv, self.ne = int(c[VERTEX]), int(c[EDGE])
         self.nelem = int(c[TET] + c[HEX] + c[PRISM] + c[PYRAMID])
+        if self.nelem == 0:          # 2-D mesh: the elements are the faces
+            self.nelem = int(c[TRIANGLE] + c[QUAD])
 
     @classmethod
     def box(cls, nx, ny, nz, wx=1.0, wy=1.0, wz=1.0):

@@ -7,7 +7,7 @@
 //       ma::Input -- the per-entity virtuals are then served from one device sweep (sweep detection);
 // and reports every difference in flags, counts and statistics.  Test infrastructure; it ships in libmag_ma.so only so
 // that the GPU box (which has no /root/reference) can run it from the prebuilt library.
-#include "magAdapt.h"
+#include "../../core_b200/adapter/magAdapt.h"
 #include "../../include/mag.h"
 #include <ma.h>
 #include <maAdapt.h>

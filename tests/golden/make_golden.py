@@ -126,6 +126,18 @@ def main():
     case("jbox7_random_logfn", m, refo.KIND_LOG_FN, h, R, good_quality=0.2)
     m.close()
 
+    # 2-D box (triangles are the elements: ma::measureTriQuality), jittered in the plane, rotating shock field
+    m = refo.RefMesh.box(9, 7, 0)
+    xyz = m.export()[0]
+    inner = (xyz[:, 0] > 1e-9) & (xyz[:, 0] < 1 - 1e-9) & (xyz[:, 1] > 1e-9) & (xyz[:, 1] < 1 - 1e-9)
+    xyz[inner, :2] += (0.3 / 9) * (rng.random((int(inner.sum()), 2)) - 0.5)
+    m.set_coords(xyz)
+    h, R = fields.shock_rotating(xyz, 1.0 / 8)
+    case("tri9x7_shock_rot_aniso", m, refo.KIND_ANISO_FIELD, h, R, good_quality=0.2)
+    case("tri9x7_shock_rot_log", m, refo.KIND_LOG_FIELD, h, R, good_quality=0.2)
+    case("tri9x7_iso", m, refo.KIND_ISO_FIELD, fields.iso_linear(xyz, 1.0 / 8), good_quality=0.2)
+    m.close()
+
     # mixed prism / tet boundary-layer box (config 5 shape)
     xyz, tets, prisms = mixed_box(5, 2)
     xyz = fields.jitter(xyz, 0.3 / 5, seed=7)

@@ -1,5 +1,5 @@
 """The C++ drop-in adapter (core_b200/adapter) against the unmodified reference, in one process: libmag_ma.so holds the
-adapter, the compiled reference it plugs into, and the self-check of core_b200/adapter/adapter_check.cc.  The library is
+adapter, the compiled reference it plugs into, and the self-check of tests/adapter/adapter_check.cc.  The library is
 built where /root/reference exists (the build container) and travels to the GPU box prebuilt."""
 import ctypes as C
 import os

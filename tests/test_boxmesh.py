@@ -27,6 +27,13 @@ def test_kuhn_box_matches_live_reference(dims):
     assert np.array_equal(xyz, rx) and np.array_equal(ev, rev) and np.array_equal(tv, relv[:, :4])
 
 
+def test_tri_box_matches_makeMdsBox_golden():
+    g = util.load("tri9x7_iso")
+    xyz, ev, tv = boxmesh.tri_box(9, 7)
+    assert np.array_equal(ev, g["edge_v"]) and np.array_equal(tv, g["elem_v"][:, :3])
+    assert len(xyz) == len(g["xyz"])
+
+
 def test_box_counts():
     for n in (1, 3, 20):
         nv, ne, nt = boxmesh.box_counts(n, n, n)

@@ -57,7 +57,8 @@ def test_golden_reference_vectors(cb, name, mode):
     g = util.load(name)
     mode = cb.FP_STRICT if mode == "strict" else cb.FP_FAST
     kind, ma, mb = util.metric_arrays(g)
-    prism_v, pyr_v, tet_v = util.split_elements(g)
+    two_d = util.is_2d(g)
+    prism_v, pyr_v, tet_v = (np.zeros((0, 6), np.int32), np.zeros((0, 5), np.int32), None) if two_d else util.split_elements(g)
     nns = len(prism_v) + len(pyr_v)
     ef_in, lf_in = g["edge_flags_in"].copy(), g["elem_flags_in"].copy()
     if nns:
@@ -66,7 +67,10 @@ def test_golden_reference_vectors(cb, name, mode):
     gq = float(g["good_quality"])
     gq = 0.027 if gq < 0 else gq
     p = cb.Part(0)
-    p.set_mesh(g["xyz"], g["edge_v"], tet_v, prism_v if len(prism_v) else None, pyr_v if len(pyr_v) else None)
+    if two_d:
+        p.set_mesh_2d(g["xyz"], g["edge_v"], np.ascontiguousarray(g["elem_v"][:, :3]))
+    else:
+        p.set_mesh(g["xyz"], g["edge_v"], tet_v, prism_v if len(prism_v) else None, pyr_v if len(pyr_v) else None)
     if kind == mao.LOGM:
         lm = p.set_size_field_logm_from_frames(g["h"], g["R"], util.logm_variant(g), want_logm=True)
         assert np.array_equal(lm, g["logM"]), "host-built logM field differs from the reference's ma_logM"

@@ -11,6 +11,8 @@ import util
 def test_oracle_matches_reference_golden(name, built):
     g = util.load(name)
     kind, ma, mb = util.metric_arrays(g)
+    if util.is_2d(g):
+        return check_2d(g, kind, ma, mb)
     prism_v, pyr_v, tet_v = util.split_elements(g)
     nns = len(prism_v) + len(pyr_v)
     if kind == mao.LOGM:
@@ -45,6 +47,22 @@ def test_oracle_matches_reference_golden(name, built):
         ok, codes = mao.prism_ok(g["xyz"], prism_v)
         assert np.array_equal(ok, g["layer_ok"][:len(prism_v)])
         assert np.array_equal(codes, g["layer_codes"][:len(prism_v)])
+
+
+def check_2d(g, kind, ma, mb):
+    """2-D meshes: edges as in 3-D, elements are triangles (measureTriQuality, maQuality.cc:110-136)."""
+    tri_v = np.ascontiguousarray(g["elem_v"][:, :3])
+    L = mao.edge_lengths(kind, g["xyz"], ma, mb, g["edge_v"])
+    assert np.array_equal(L, g["lengths"])
+    q = mao.tri_qualities(kind, g["xyz"], ma, mb, tri_v, True)
+    assert np.array_equal(q, g["qualities"])
+    assert np.array_equal(mao.tri_qualities(kind, g["xyz"], ma, mb, tri_v, False), g["qualities_centroid"])
+    ef, lf = g["edge_flags_in"].copy(), g["elem_flags_in"].copy()
+    counts = [mao.mark_edges_to_split(L, ef, None, kind), mao.mark_edges_to_collapse(L, ef, None, kind),
+              mao.mark_bad_quality(q, lf, float(g["good_quality"]))]
+    assert counts == g["counts"].tolist()
+    assert np.array_equal(ef, g["edge_flags_out"]) and np.array_equal(lf, g["elem_flags_out"])
+    assert mao.min_quality(q) == float(g["min_q"]) and mao.max_length(L) == float(g["max_len"])
 
 
 def test_layer_closure_flags_golden():

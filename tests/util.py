@@ -11,7 +11,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 # reference driver kinds (oracle/refo.py) -> restated-oracle kinds
 REF_KIND_TO_MAO = {0: mao.IDENTITY, 1: mao.ISO, 2: mao.ANISO, 3: mao.LOGM, 4: mao.ANISO, 5: mao.LOGM, 6: mao.ISO}
 # apf::Mesh::Type
-TET, PRISM, PYRAMID = 4, 6, 7
+TRIANGLE, TET, PRISM, PYRAMID = 2, 4, 6, 7
 
 
 def golden_cases():
@@ -21,6 +21,10 @@ def golden_cases():
 
 def load(name):
     return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+
+
+def is_2d(g):
+    return bool(np.all(g["elem_type"] == TRIANGLE))
 
 
 def split_elements(g):
