@@ -78,7 +78,7 @@ size_t rec_doubles(int kind) { return (kind == MAG_KIND_ANISO || kind == MAG_KIN
 int repack(mag_ctx* c)
 {
   if (c->kind == MAG_KIND_NONE || c->nv == 0 || !c->d_xyz) return MAG_OK;
-  int rc = dev_reserve(c, c->d_vedge, c->cap_vedge, (size_t)c->nv * rec_doubles(c->kind));
+  int rc = dev_reserve(c, c->d_vedge, c->cap_vedge, (size_t)vpad(c->nv) * rec_doubles(c->kind));
   if (rc) return rc;
   c->vertex_pass_valid = false;
   return magk_pack(c);
@@ -180,7 +180,7 @@ static int set_mesh_impl(mag_ctx* c, int dim, int64_t nv, const double* xyz, int
 {
   CHECK_CTX(c);
   if (nv < 0 || ne < 0 || nt < 0 || np < 0 || npy < 0 || ntri < 0) return mag_fail(c, MAG_ERR_ARG, "mag_set_mesh: negative count");
-  if (nv > 0x7fffffffLL || ne > 0x7fffffffLL || np + npy + nt + ntri > 0x7fffffffLL)
+  if (nv > MAG_MAX_ENTITIES || ne > MAG_MAX_ENTITIES || np + npy + nt + ntri > MAG_MAX_ENTITIES)
     return mag_fail(c, MAG_ERR_ARG, "mag_set_mesh: entity ids are int32 (MDS_ID_TYPE=int, mds/CMakeLists.txt:7)");
   if ((nv && !xyz) || (ne && !edge_v) || (nt && !tet_v) || (np && !prism_v) || (npy && !pyr_v) || (ntri && !tri_v))
     return mag_fail(c, MAG_ERR_ARG, "mag_set_mesh: null array with non-zero count");
@@ -197,8 +197,8 @@ static int set_mesh_impl(mag_ctx* c, int dim, int64_t nv, const double* xyz, int
       if ((rc = dev_free(c, c->d_ma)) || (rc = dev_free(c, c->d_mb)) || (rc = dev_free(c, c->d_vedge))) return rc;
       c->cap_ma = c->cap_mb = c->cap_vedge = 0;
     }
-    if ((rc = dev_alloc(c, c->d_xyz, (size_t)nv * 3)) || (rc = dev_alloc(c, c->d_vpos, (size_t)nv * 4)) ||
-        (rc = dev_alloc(c, c->d_vq, (size_t)nv * 10)) || (rc = dev_alloc(c, c->d_edge_v, (size_t)ne * 2)) ||
+    if ((rc = dev_alloc(c, c->d_xyz, (size_t)nv * 3)) || (rc = dev_alloc(c, c->d_vpos, (size_t)vpad(nv) * 4)) ||
+        (rc = dev_alloc(c, c->d_vq, (size_t)vpad(nv) * 10)) || (rc = dev_alloc(c, c->d_edge_v, (size_t)ne * 2)) ||
         (rc = dev_alloc(c, c->d_tet_v, (size_t)nt * 4)) || (rc = dev_alloc(c, c->d_prism_v, (size_t)np * 6)) ||
         (rc = dev_alloc(c, c->d_pyr_v, (size_t)npy * 5)) || (rc = dev_alloc(c, c->d_tri_v, (size_t)ntri * 3)) ||
         (rc = dev_alloc(c, c->d_edge_owned, edge_owned ? (size_t)ne : 0)) ||

@@ -24,6 +24,11 @@ struct MagDevStats {
 
 #define MAG_SUM_BLOCKS 1184 /* 8 x 148: fixed shape of the length-sum tree */
 #define MAG_NEAR_REL 1e-12
+// per-vertex device arrays are stored in blocks of MAG_VBLOCK vertices (see mag_kernels.cu) and padded to whole blocks
+#define MAG_VBLOCK 32
+static inline int64_t vpad(int64_t nv) { return (nv + MAG_VBLOCK - 1) / MAG_VBLOCK * MAG_VBLOCK; }
+// entity ids are int32 (MDS_ID_TYPE=int, mds/CMakeLists.txt:7); the kernels index one chunk past the end in int32
+#define MAG_MAX_ENTITIES (0x7fffffffLL - (1LL << 20))
 // transient bit (never visible to the caller): entity awaits strict re-evaluation
 #define MAG_PENDING_BIT (1 << 30)
 

@@ -13,6 +13,7 @@
 #include "mag_math.cuh"
 #include "mag_math_fast.cuh"
 #include <cstring>
+#include <cmath>
 
 namespace {
 
@@ -60,36 +61,49 @@ __device__ __forceinline__ double warp_sum(double v)
   return v;
 }
 
-// ------------------------------------------------------------------ vertex arrays: chunk-major layout
-// Every per-vertex array is stored as K planes of double2: chunk k of vertex v lives at ((double2*)base)[k*nv + v].
+// ------------------------------------------------------------------ vertex arrays: blocked chunk-major layout
+// Every per-vertex array is stored in blocks of kVB = 32 vertices; inside a block the K 16-byte chunks of the record
+// form K planes of 32 double2:   chunk k of vertex v lives at ((double2*)base)[(v / 32) * 32 K + 32 k + v % 32].
 // Neighbouring threads work on neighbouring entities, whose vertex ids are close in any locality-preserving numbering
-// (grid order for box meshes), so one warp-wide LDG.128 of chunk k touches a couple of cache lines instead of one line
-// per lane as 96-byte-strided records would: the L1 data pipe, not HBM, is what these kernels saturate first.
-//   d_vedge  Aniso   6 planes {x,y} {z,h0} {h1,h2} {R00,R10} {R20,R01} {R11,R21}   (frame columns 0 and 1; column 2 is
+// (grid order for box meshes), so one warp-wide LDG.128 of chunk k touches a few cache lines instead of one line per
+// lane as 96-byte-strided records would (the L1 data pipe, not HBM, is what these kernels saturate first), and all K
+// chunks of a vertex sit at compile-time offsets from one address (one address computation per vertex, one DRAM page).
+// Arrays are padded to a whole number of blocks (vpad()).
+//   d_vedge  Aniso   K=6 {x,y} {z,h0} {h1,h2} {R00,R10} {R20,R01} {R11,R21}   (frame columns 0 and 1; column 2 is
 //                    overwritten by orthogonalizeR before use, maSize.cc:94-121)
-//            LogAniso 6 planes {x,y} {z,M00} {M01,M02} {M10,M11} {M12,M20} {M21,M22}
-//            Iso / Identity 2 planes {x,y} {z,s}
-//   d_vpos   2 planes {x,y} {z,det Q_v}
-//   d_vq     5 planes {Q00,Q01} {Q02,Q10} {Q11,Q12} {Q20,Q21} {Q22,det Q_v}
-__device__ __forceinline__ const double2* chunk_ptr(const double* __restrict__ base, int64_t nv, int k, int64_t v)
+//            LogAniso K=6 {x,y} {z,M00} {M01,M02} {M10,M11} {M12,M20} {M21,M22}
+//            Iso / Identity K=2 {x,y} {z,s}
+//   d_vpos   K=2 {x,y} {z,det Q_v}
+//   d_vq     K=5 {Q00,Q01} {Q02,Q10} {Q11,Q12} {Q20,Q21} {Q22,det Q_v}
+constexpr int kVB = MAG_VBLOCK;
+template <int K>
+__device__ __forceinline__ const double2* chunk_ptr(const double* __restrict__ base, int k, int64_t v)
 {
-  return reinterpret_cast<const double2*>(base) + (size_t)k * (size_t)nv + (size_t)v;
+  return reinterpret_cast<const double2*>(base) + ((size_t)(v / kVB) * (size_t)(K * kVB) + (size_t)(k * kVB) + (size_t)(v % kVB));
 }
-__device__ __forceinline__ double2* chunk_ptr_w(double* __restrict__ base, int64_t nv, int k, int64_t v)
+// hot loops: vertex ids are non-negative int32, so the block offset is one 32x32->64 multiply-add
+template <int K>
+__device__ __forceinline__ const double2* chunk_ptr(const double* __restrict__ base, int k, int32_t v)
 {
-  return reinterpret_cast<double2*>(base) + (size_t)k * (size_t)nv + (size_t)v;
+  const unsigned u = (unsigned)v;
+  return reinterpret_cast<const double2*>(base) + ((size_t)(u / kVB) * (size_t)(K * kVB) + (size_t)(k * kVB + (int)(u % kVB)));
+}
+template <int K>
+__device__ __forceinline__ double2* chunk_ptr_w(double* __restrict__ base, int k, int64_t v)
+{
+  return reinterpret_cast<double2*>(base) + ((size_t)(v / kVB) * (size_t)(K * kVB) + (size_t)(k * kVB) + (size_t)(v % kVB));
 }
 struct Rec12 { double v[12]; };
-__device__ __forceinline__ Rec12 load_rec12(const double* __restrict__ base, int64_t nv, int32_t vid)
+__device__ __forceinline__ Rec12 load_rec12(const double* __restrict__ base, int32_t vid)
 {
   Rec12 r;
 #pragma unroll
-  for (int i = 0; i < 6; ++i) { double2 t = __ldg(chunk_ptr(base, nv, i, vid)); r.v[2 * i] = t.x; r.v[2 * i + 1] = t.y; }
+  for (int i = 0; i < 6; ++i) { double2 t = __ldg(chunk_ptr<6>(base, i, vid)); r.v[2 * i] = t.x; r.v[2 * i + 1] = t.y; }
   return r;
 }
-__device__ __forceinline__ void load_rec4(const double* __restrict__ base, int64_t nv, int32_t vid, double out[4])
+__device__ __forceinline__ void load_rec4(const double* __restrict__ base, int32_t vid, double out[4])
 {
-  double2 a = __ldg(chunk_ptr(base, nv, 0, vid)), b = __ldg(chunk_ptr(base, nv, 1, vid));
+  double2 a = __ldg(chunk_ptr<2>(base, 0, vid)), b = __ldg(chunk_ptr<2>(base, 1, vid));
   out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
 }
 
@@ -98,8 +112,8 @@ __global__ void k_pack4(int64_t nv, const double* __restrict__ xyz, const double
 {
   int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (v >= nv) return;
-  *chunk_ptr_w(rec, nv, 0, v) = make_double2(xyz[3 * v], xyz[3 * v + 1]);
-  *chunk_ptr_w(rec, nv, 1, v) = make_double2(xyz[3 * v + 2], s ? s[v] : 0.0);
+  *chunk_ptr_w<2>(rec, 0, v) = make_double2(xyz[3 * v], xyz[3 * v + 1]);
+  *chunk_ptr_w<2>(rec, 1, v) = make_double2(xyz[3 * v + 2], s ? s[v] : 0.0);
 }
 __global__ void k_pack12_aniso(int64_t nv, const double* __restrict__ xyz, const double* __restrict__ h,
                                const double* __restrict__ R, double* __restrict__ rec)
@@ -107,24 +121,24 @@ __global__ void k_pack12_aniso(int64_t nv, const double* __restrict__ xyz, const
   int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (v >= nv) return;
   const double* r = R + 9 * v;
-  *chunk_ptr_w(rec, nv, 0, v) = make_double2(xyz[3 * v], xyz[3 * v + 1]);
-  *chunk_ptr_w(rec, nv, 1, v) = make_double2(xyz[3 * v + 2], h[3 * v]);
-  *chunk_ptr_w(rec, nv, 2, v) = make_double2(h[3 * v + 1], h[3 * v + 2]);
-  *chunk_ptr_w(rec, nv, 3, v) = make_double2(r[0], r[3]);
-  *chunk_ptr_w(rec, nv, 4, v) = make_double2(r[6], r[1]);
-  *chunk_ptr_w(rec, nv, 5, v) = make_double2(r[4], r[7]);
+  *chunk_ptr_w<6>(rec, 0, v) = make_double2(xyz[3 * v], xyz[3 * v + 1]);
+  *chunk_ptr_w<6>(rec, 1, v) = make_double2(xyz[3 * v + 2], h[3 * v]);
+  *chunk_ptr_w<6>(rec, 2, v) = make_double2(h[3 * v + 1], h[3 * v + 2]);
+  *chunk_ptr_w<6>(rec, 3, v) = make_double2(r[0], r[3]);
+  *chunk_ptr_w<6>(rec, 4, v) = make_double2(r[6], r[1]);
+  *chunk_ptr_w<6>(rec, 5, v) = make_double2(r[4], r[7]);
 }
 __global__ void k_pack12_logm(int64_t nv, const double* __restrict__ xyz, const double* __restrict__ M, double* __restrict__ rec)
 {
   int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (v >= nv) return;
   const double* m = M + 9 * v;
-  *chunk_ptr_w(rec, nv, 0, v) = make_double2(xyz[3 * v], xyz[3 * v + 1]);
-  *chunk_ptr_w(rec, nv, 1, v) = make_double2(xyz[3 * v + 2], m[0]);
-  *chunk_ptr_w(rec, nv, 2, v) = make_double2(m[1], m[2]);
-  *chunk_ptr_w(rec, nv, 3, v) = make_double2(m[3], m[4]);
-  *chunk_ptr_w(rec, nv, 4, v) = make_double2(m[5], m[6]);
-  *chunk_ptr_w(rec, nv, 5, v) = make_double2(m[7], m[8]);
+  *chunk_ptr_w<6>(rec, 0, v) = make_double2(xyz[3 * v], xyz[3 * v + 1]);
+  *chunk_ptr_w<6>(rec, 1, v) = make_double2(xyz[3 * v + 2], m[0]);
+  *chunk_ptr_w<6>(rec, 2, v) = make_double2(m[1], m[2]);
+  *chunk_ptr_w<6>(rec, 3, v) = make_double2(m[3], m[4]);
+  *chunk_ptr_w<6>(rec, 4, v) = make_double2(m[5], m[6]);
+  *chunk_ptr_w<6>(rec, 5, v) = make_double2(m[7], m[8]);
 }
 
 // ------------------------------------------------------------------ per-vertex pass
@@ -140,7 +154,7 @@ __global__ void k_vertex_pass(int64_t nv, int dim, const double* __restrict__ ve
   double x, y, z;
   if (KIND == MAG_KIND_IDENTITY || KIND == MAG_KIND_ISO) {
     double r[4];
-    load_rec4(vedge, nv, (int32_t)v, r);
+    load_rec4(vedge, (int32_t)v, r);
     x = r[0]; y = r[1]; z = r[2];
     magst::identity(Q);
     if (KIND == MAG_KIND_ISO) {
@@ -149,7 +163,7 @@ __global__ void k_vertex_pass(int64_t nv, int dim, const double* __restrict__ ve
       Q.m[0][0] = ih; Q.m[1][1] = ih; Q.m[2][2] = ih;
     }
   } else {
-    Rec12 r = load_rec12(vedge, nv, (int32_t)v);
+    Rec12 r = load_rec12(vedge, (int32_t)v);
     x = r.v[0]; y = r.v[1]; z = r.v[2];
     if (KIND == MAG_KIND_ANISO) {
       magst::transform_aniso(V3{r.v[6], r.v[7], r.v[8]}, V3{r.v[9], r.v[10], r.v[11]}, r.v[3], r.v[4], r.v[5], Q);
@@ -164,13 +178,13 @@ __global__ void k_vertex_pass(int64_t nv, int dim, const double* __restrict__ ve
   // apf::getJacobianDeterminant(Q, mesh dimension) (apfVectorElement.cc:68-91): det in 3-D, |row0 x row1| in 2-D
   double det = dim == 3 ? magst::det3(Q)
                         : magst::length(magst::cross(V3{Q.m[0][0], Q.m[0][1], Q.m[0][2]}, V3{Q.m[1][0], Q.m[1][1], Q.m[1][2]}));
-  *chunk_ptr_w(vpos, nv, 0, v) = make_double2(x, y);
-  *chunk_ptr_w(vpos, nv, 1, v) = make_double2(z, det);
-  *chunk_ptr_w(vq, nv, 0, v) = make_double2(Q.m[0][0], Q.m[0][1]);
-  *chunk_ptr_w(vq, nv, 1, v) = make_double2(Q.m[0][2], Q.m[1][0]);
-  *chunk_ptr_w(vq, nv, 2, v) = make_double2(Q.m[1][1], Q.m[1][2]);
-  *chunk_ptr_w(vq, nv, 3, v) = make_double2(Q.m[2][0], Q.m[2][1]);
-  *chunk_ptr_w(vq, nv, 4, v) = make_double2(Q.m[2][2], det);
+  *chunk_ptr_w<2>(vpos, 0, v) = make_double2(x, y);
+  *chunk_ptr_w<2>(vpos, 1, v) = make_double2(z, det);
+  *chunk_ptr_w<5>(vq, 0, v) = make_double2(Q.m[0][0], Q.m[0][1]);
+  *chunk_ptr_w<5>(vq, 1, v) = make_double2(Q.m[0][2], Q.m[1][0]);
+  *chunk_ptr_w<5>(vq, 2, v) = make_double2(Q.m[1][1], Q.m[1][2]);
+  *chunk_ptr_w<5>(vq, 3, v) = make_double2(Q.m[2][0], Q.m[2][1]);
+  *chunk_ptr_w<5>(vq, 4, v) = make_double2(Q.m[2][2], det);
 }
 
 // ------------------------------------------------------------------ edge metric length
@@ -181,13 +195,15 @@ struct EdgeRecs {
   double a[N], b[N];
 };
 template <int KIND>
-__device__ __forceinline__ void load_edge_recs(const double* __restrict__ vedge, int64_t nv, int2 ev, EdgeRecs<KIND>& R)
+__device__ __forceinline__ void load_edge_recs(const double* __restrict__ vedge, int2 ev, EdgeRecs<KIND>& R)
 {
   constexpr int N = EdgeRecs<KIND>::N;
+  const double2* pa = chunk_ptr<N / 2>(vedge, 0, ev.x);
+  const double2* pb = chunk_ptr<N / 2>(vedge, 0, ev.y);
 #pragma unroll
-  for (int i = 0; i < N / 2; ++i) { double2 t = __ldg(chunk_ptr(vedge, nv, i, ev.x)); R.a[2 * i] = t.x; R.a[2 * i + 1] = t.y; }
+  for (int i = 0; i < N / 2; ++i) { double2 t = __ldg(pa + i * kVB); R.a[2 * i] = t.x; R.a[2 * i + 1] = t.y; }
 #pragma unroll
-  for (int i = 0; i < N / 2; ++i) { double2 t = __ldg(chunk_ptr(vedge, nv, i, ev.y)); R.b[2 * i] = t.x; R.b[2 * i + 1] = t.y; }
+  for (int i = 0; i < N / 2; ++i) { double2 t = __ldg(pb + i * kVB); R.b[2 * i] = t.x; R.b[2 * i + 1] = t.y; }
 }
 
 // MetricSizeField::measure: order 2 -> EdgeIntegration::N2, points +-0.577350269189626, weights 1
@@ -337,22 +353,23 @@ __device__ __forceinline__ long long next_chunk(unsigned long long* counter, lon
   __syncthreads();
   return *slot;
 }
-__device__ __forceinline__ void prefetch_l1(const void* p)
-{
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-}
-// both cache lines a 96-byte (12-double) record can touch
-__device__ __forceinline__ void prefetch_rec12(const double* __restrict__ base, int32_t vid)
-{
-  const char* p = reinterpret_cast<const char*>(base + 12 * (size_t)vid);
-  prefetch_l1(p);
-  prefetch_l1(p + 80);
-}
+// What the edge kernel needs of the sweep parameters, decoded once on the host so that the per-edge flag logic is a
+// handful of integer operations:
+//   off_bits  OR-ed into the flag word before the skip tests: the skip bit of every mark that was NOT requested
+//   err_mask  true flags of the requested marks; markEntities asserts they are clear on every entity (maAdapt.cc:308)
+//   tol_*     MAG_NEAR_REL * |threshold|, or -1 for an infinite threshold (nothing is ever near it)
+struct EdgeParams {
+  int32_t off_bits, err_mask;
+  int want_len;
+  uint32_t ops;
+  double max_len, min_len, tol_max, tol_min;
+};
+constexpr int32_t kSkipSplit = MAG_DONT_SPLIT | MAG_NEED_NOT_SPLIT, kSkipColl = MAG_DONT_COLLAPSE | MAG_NEED_NOT_COLLAPSE;
 
 // drain n (<= 32) queued edges: entry i is handled by lane i.  Returns bit 0: evaluated, bit 1: counted SPLIT, bit 2: counted COLLAPSE
-template <int KIND, bool FAST>
+template <int KIND, bool FAST, bool OWNED>
 __device__ __noinline__ unsigned drain_edges(NearQueue& q, int first, int n, const int2* __restrict__ edge_v,
-                                             const double* __restrict__ vedge, int64_t nv, const uint8_t* __restrict__ owned_arr,
+                                             const double* __restrict__ vedge, const uint8_t* __restrict__ owned_arr,
                                              int32_t* __restrict__ flags, double* __restrict__ lengths, uint32_t ops,
                                              double max_len, double min_len,
                                              MagDevStats* st, int32_t* __restrict__ near_list)
@@ -366,13 +383,13 @@ __device__ __noinline__ unsigned drain_edges(NearQueue& q, int first, int n, con
     near_list[base + lane] = e;
     if (FAST) {
       int32_t f = q.f[w][first + lane];
-      const bool need_split = (P.ops & MAG_OP_MARK_SPLIT) && !(f & (MAG_DONT_SPLIT | MAG_NEED_NOT_SPLIT));
-      const bool need_coll = (P.ops & MAG_OP_MARK_COLLAPSE) && !(f & (MAG_DONT_COLLAPSE | MAG_NEED_NOT_COLLAPSE));
+      const bool need_split = (P.ops & MAG_OP_MARK_SPLIT) && !(f & kSkipSplit);
+      const bool need_coll = (P.ops & MAG_OP_MARK_COLLAPSE) && !(f & kSkipColl);
       EdgeRecs<KIND> R;
-      load_edge_recs<KIND>(vedge, nv, __ldg(edge_v + e), R);
+      load_edge_recs<KIND>(vedge, __ldg(edge_v + e), R);
       int eig = 0;
       const double len = edge_length_strict<KIND>(R, &eig);
-      const bool owned = owned_arr ? (owned_arr[e] != 0) : true;
+      const bool owned = OWNED ? (owned_arr[e] != 0) : true;
       unsigned cs = 0, cc = 0;
       mark_edge(len, f, need_split, need_coll, owned, P, cs, cc);
       out = 1u | (cs << 1) | (cc << 2);
@@ -384,119 +401,81 @@ __device__ __noinline__ unsigned drain_edges(NearQueue& q, int first, int n, con
   return out;
 }
 
-// Software pipeline of the edge kernel, per thread and tile k:
-//   flag word + end vertices are loaded two tiles ahead, the two vertex records one tile ahead (straight into
-//   registers, only when the flag word says the edge has to be evaluated at all), so the gather latency of tile
-//   k+1 is covered by the arithmetic of tile k.
-template <int KIND, bool FAST>
+// Persistent edge kernel.  Per thread and tile: the flag word and the end vertices are loaded one tile ahead; the two
+// vertex records are gathered only when the flag word says the edge has to be evaluated at all (skipped edges cost 12
+// bytes).  Everything is indexed with int32 (mag_set_mesh rejects meshes with 2^31 or more entities of one dimension).
+template <int KIND, bool FAST, bool OWNED>
 __global__ void __launch_bounds__(kEdgeThreads, FAST ? MAG_EDGE_BLOCKS : MAG_EDGE_BLOCKS_STRICT)
-k_edges(int64_t ne, int64_t nv, const int2* __restrict__ edge_v, const double* __restrict__ vedge,
+k_edges(int32_t ne, const int2* __restrict__ edge_v, const double* __restrict__ vedge,
         const uint8_t* __restrict__ owned_arr, int32_t* __restrict__ flags, double* __restrict__ lengths,
-        SweepParams P, MagDevStats* st, int32_t* __restrict__ near_list, const int32_t* __restrict__ chunk_order)
+        EdgeParams P, MagDevStats* st, int32_t* __restrict__ near_list, const int32_t* __restrict__ chunk_order)
 {
   __shared__ NearQueue q;
   __shared__ long long chunk_slot;
   unsigned c_split = 0, c_coll = 0, c_eval = 0, c_err = 0;
-  unsigned long long maxbits = 0;
+  double maxlen = 0.0;                  // getMaximumEdgeLength starts at 0 and ignores NaN (maSize.cc:673-691)
   int qn = 0, eig_any = 0;
-  const bool do_split = P.ops & MAG_OP_MARK_SPLIT, do_coll = P.ops & MAG_OP_MARK_COLLAPSE;
-  const bool want_len = P.ops & MAG_OP_LENGTHS;
-  constexpr int32_t skip_split = MAG_DONT_SPLIT | MAG_NEED_NOT_SPLIT, skip_coll = MAG_DONT_COLLAPSE | MAG_NEED_NOT_COLLAPSE;
-  auto has_work = [&](int32_t f) { return want_len || (do_split && !(f & skip_split)) || (do_coll && !(f & skip_coll)); };
-  const int64_t ntiles = (ne + kEdgeThreads - 1) / kEdgeThreads;
-  const int64_t nchunks = (ntiles + kChunkTiles - 1) / kChunkTiles;
+  constexpr int kChunkEdges = kChunkTiles * kEdgeThreads;
+  const int nchunks = (ne + kChunkEdges - 1) / kChunkEdges;
   for (;;) {
     const long long ticket = next_chunk(&st->edge_chunk, &chunk_slot);
     if (ticket >= nchunks) break;
-    const long long chunk = chunk_order[ticket];
-    const int64_t t0 = chunk * kChunkTiles;
-    const int64_t t1 = (t0 + kChunkTiles < ntiles) ? t0 + kChunkTiles : ntiles;
-    const int64_t e_end = (t1 * kEdgeThreads < ne) ? t1 * kEdgeThreads : ne;   // first edge past this chunk
-    int64_t e = t0 * kEdgeThreads + threadIdx.x;
-    // prologue: tile t0 fully loaded, (flag, ends) of tile t0+1 in flight
-    int32_t f_cur = 0, f_nx = 0;
-    int2 ev_nx = make_int2(0, 0);
-    EdgeRecs<KIND> R;
-    bool work_cur = false;
-    int2 ev_cur = make_int2(0, 0);
-    if (e < e_end) {
-      f_cur = flags[e];
-      work_cur = has_work(f_cur);
-      ev_cur = __ldg(edge_v + e);
-#ifdef MAG_EDGE_PREFETCH
-      if (work_cur) load_edge_recs<KIND>(vedge, nv, ev_cur, R);
-#endif
-    }
-    if (e + kEdgeThreads < e_end) { f_nx = flags[e + kEdgeThreads]; ev_nx = __ldg(edge_v + e + kEdgeThreads); }
-    // one pipeline step: issue the loads of tile k+1 (records into Rn; only with MAG_EDGE_PREFETCH) and k+2 (flag, ends),
-    // then compute tile k from Rc.  With record prefetch the loop is unrolled by two with the roles of the two register
-    // sets swapped, so no register copies stand between a load and its (much later) first use.
-    auto step = [&](EdgeRecs<KIND>& Rc, int32_t f_c, bool work_c, EdgeRecs<KIND>& Rn, int32_t& f_n, bool& work_n) {
-      f_n = f_nx;
-      work_n = false;
-      const int2 ev_n = ev_nx;
-      if (e + kEdgeThreads < e_end) {
-        work_n = has_work(f_n);
-#ifdef MAG_EDGE_PREFETCH
-        if (work_n) load_edge_recs<KIND>(vedge, nv, ev_n, Rn);
-#endif
-      }
-      if (e + 2 * kEdgeThreads < e_end) { f_nx = flags[e + 2 * kEdgeThreads]; ev_nx = __ldg(edge_v + e + 2 * kEdgeThreads); }
+    const int e0 = chunk_order[ticket] * kChunkEdges;
+    const int e_end = (ne - e0 < kChunkEdges) ? ne : e0 + kChunkEdges;   // first edge past this chunk
+    const int tiles = (e_end - e0 + kEdgeThreads - 1) / kEdgeThreads;
+    int e = e0 + (int)threadIdx.x;
+    int32_t f = 0;
+    int2 ev = make_int2(0, 0);
+    if (e < e_end) { f = flags[e]; ev = __ldg(edge_v + e); }
+    for (int tile = 0; tile < tiles; ++tile, e += kEdgeThreads) {
+      int32_t f_nx = 0;
+      int2 ev_nx = make_int2(0, 0);
+      if (e + kEdgeThreads < e_end) { f_nx = flags[e + kEdgeThreads]; ev_nx = __ldg(edge_v + e + kEdgeThreads); }
       bool nr = false;
       if (e < e_end) {
-        int32_t f = f_c;
-        // markEntities asserts the true flag is clear on every entity it visits (maAdapt.cc:308)
-        if ((do_split && (f & MAG_SPLIT)) || (do_coll && (f & MAG_COLLAPSE))) ++c_err;
-        if (work_c) {
-#ifndef MAG_EDGE_PREFETCH
-          load_edge_recs<KIND>(vedge, nv, ev_cur, Rc);   // plain version: this tile's records are gathered here
-#endif
-          const bool need_split = do_split && !(f & skip_split), need_coll = do_coll && !(f & skip_coll);
-          const double len = FAST ? edge_length_fast<KIND>(Rc, &eig_any) : edge_length_strict<KIND>(Rc, &eig_any);
-          const bool owned = owned_arr ? (owned_arr[e] != 0) : true;
-          if (want_len) {
+        const int32_t fe = f | P.off_bits;
+        const bool need_split = !(fe & kSkipSplit), need_coll = !(fe & kSkipColl);
+        if (f & P.err_mask) ++c_err;
+        if (P.want_len || need_split || need_coll) {
+          EdgeRecs<KIND> R;
+          load_edge_recs<KIND>(vedge, ev, R);
+          const double len = FAST ? edge_length_fast<KIND>(R, &eig_any) : edge_length_strict<KIND>(R, &eig_any);
+          const bool owned = OWNED ? (owned_arr[e] != 0) : true;
+          if (P.want_len) {
             lengths[e] = len;
-            if (owned && len > 0) {
-              const unsigned long long b = (unsigned long long)__double_as_longlong(len);
-              maxbits = b > maxbits ? b : maxbits;
-            }
+            if (owned && len > maxlen) maxlen = len;
           }
-          nr = (need_split && near_thr(len, P.max_len)) || (need_coll && near_thr(len, P.min_len));
-          if ((need_split || need_coll) && !(FAST && nr)) {
-            ++c_eval;
-            mark_edge(len, f, need_split, need_coll, owned, P, c_split, c_coll);
-            if (f != f_c) flags[e] = f;
+          if (need_split || need_coll) {
+            nr = (need_split && fabs(len - P.max_len) <= P.tol_max) || (need_coll && fabs(len - P.min_len) <= P.tol_min);
+            if (!(FAST && nr)) {
+              ++c_eval;
+              int32_t g = f;
+              if (need_split) {
+                const bool t = len > P.max_len;
+                g |= t ? MAG_SPLIT : MAG_NEED_NOT_SPLIT;
+                c_split += (t && owned) ? 1u : 0u;
+              }
+              if (need_coll) {
+                const bool t = len < P.min_len;
+                g |= t ? MAG_COLLAPSE : MAG_NEED_NOT_COLLAPSE;
+                c_coll += (t && owned) ? 1u : 0u;
+              }
+              flags[e] = g;
+            }
           }
         }
       }
-      if (queue_push(q, qn, nr, (int32_t)e, f_c)) {
+      if (queue_push(q, qn, nr, (int32_t)e, f)) {
         qn -= 32;
-        const unsigned r = drain_edges<KIND, FAST>(q, qn, 32, edge_v, vedge, nv, owned_arr, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list);
+        const unsigned r = drain_edges<KIND, FAST, OWNED>(q, qn, 32, edge_v, vedge, owned_arr, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list);
         c_eval += r & 1u; c_split += (r >> 1) & 1u; c_coll += (r >> 2) & 1u;
       }
-      e += kEdgeThreads;
-      ev_cur = ev_n;
-    };
-#ifdef MAG_EDGE_PREFETCH
-    EdgeRecs<KIND> R2;
-    int32_t f_2 = 0;
-    bool work_2 = false;
-    for (int64_t tile = t0; tile < t1; tile += 2) {
-      step(R, f_cur, work_cur, R2, f_2, work_2);
-      if (tile + 1 < t1) step(R2, f_2, work_2, R, f_cur, work_cur);
+      f = f_nx;
+      ev = ev_nx;
     }
-#else
-    for (int64_t tile = t0; tile < t1; ++tile) {
-      int32_t f_n;
-      bool work_n;
-      step(R, f_cur, work_cur, R, f_n, work_n);
-      f_cur = f_n;
-      work_cur = work_n;
-    }
-#endif
   }
   if (qn) {
-    const unsigned r = drain_edges<KIND, FAST>(q, 0, qn, edge_v, vedge, nv, owned_arr, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list);
+    const unsigned r = drain_edges<KIND, FAST, OWNED>(q, 0, qn, edge_v, vedge, owned_arr, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list);
     c_eval += r & 1u; c_split += (r >> 1) & 1u; c_coll += (r >> 2) & 1u;
   }
   if (eig_any) atomicAdd(&st->n_eigen_fail, 1ull);
@@ -504,8 +483,9 @@ k_edges(int64_t ne, int64_t nv, const int2* __restrict__ edge_v, const double* _
   warp_count_to(c_coll, &st->n_collapse);
   warp_count_to(c_eval, &st->n_edges_eval);
   warp_count_to(c_err, &st->n_flag_err);
-  if (want_len) {
-    const unsigned long long m = warp_max_u64(maxbits);
+  if (P.want_len) {
+    // a non-negative double orders like its bit pattern
+    const unsigned long long m = warp_max_u64((unsigned long long)__double_as_longlong(maxlen));
     if ((threadIdx.x & 31) == 0 && m) atomicMax(&st->max_len_bits, m);
   }
 }
@@ -542,7 +522,7 @@ __device__ __forceinline__ void centroid_transform(const double* __restrict__ ve
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
       double r[4];
-      load_rec4(vedge, nv, vid[n], r);
+      load_rec4(vedge, vid[n], r);
       h = magst::add(h, magst::mul(r[3], n ? 0.25 : N0));
     }
     magst::identity(Q);
@@ -555,7 +535,7 @@ __device__ __forceinline__ void centroid_transform(const double* __restrict__ ve
   for (int i = 0; i < 9; ++i) c[i] = 0;
 #pragma unroll
   for (int n = 0; n < 4; ++n) {
-    Rec12 r = load_rec12(vedge, nv, vid[n]);
+    Rec12 r = load_rec12(vedge, vid[n]);
 #pragma unroll
     for (int i = 0; i < 9; ++i) c[i] = magst::add(c[i], magst::mul(r.v[3 + i], n ? 0.25 : N0));
   }
@@ -580,10 +560,10 @@ __device__ __forceinline__ int32_t best_vertex(const int4& tv, double d0, double
   if (d3 > maxJ) { maxJ = d3; vb = tv.w; }
   return vb;
 }
-__device__ __forceinline__ void load_q(const double* __restrict__ vq, int64_t nv, int32_t vb, M3& Q, double& detQ)
+__device__ __forceinline__ void load_q(const double* __restrict__ vq, int32_t vb, M3& Q, double& detQ)
 {
-  double2 q0 = __ldg(chunk_ptr(vq, nv, 0, vb)), q1 = __ldg(chunk_ptr(vq, nv, 1, vb)), q2 = __ldg(chunk_ptr(vq, nv, 2, vb)),
-          q3 = __ldg(chunk_ptr(vq, nv, 3, vb)), q4 = __ldg(chunk_ptr(vq, nv, 4, vb));
+  double2 q0 = __ldg(chunk_ptr<5>(vq, 0, vb)), q1 = __ldg(chunk_ptr<5>(vq, 1, vb)), q2 = __ldg(chunk_ptr<5>(vq, 2, vb)),
+          q3 = __ldg(chunk_ptr<5>(vq, 3, vb)), q4 = __ldg(chunk_ptr<5>(vq, 4, vb));
   Q.m[0][0] = q0.x; Q.m[0][1] = q0.y; Q.m[0][2] = q1.x;
   Q.m[1][0] = q1.y; Q.m[1][1] = q2.x; Q.m[1][2] = q2.y;
   Q.m[2][0] = q3.x; Q.m[2][1] = q3.y; Q.m[2][2] = q4.x;
@@ -599,14 +579,14 @@ __device__ __forceinline__ double tet_quality_eval(const int4& tv, int64_t nv, c
 {
   M3 Q;
   double detQ = 0.0;
-  if (HAVE_DETS && use_max) load_q(vq, nv, best_vertex(tv, dets[0], dets[1], dets[2], dets[3]), Q, detQ);
+  if (HAVE_DETS && use_max) load_q(vq, best_vertex(tv, dets[0], dets[1], dets[2], dets[3]), Q, detQ);
   double p[4][4];
-  load_rec4(vpos, nv, tv.x, p[0]);
-  load_rec4(vpos, nv, tv.y, p[1]);
-  load_rec4(vpos, nv, tv.z, p[2]);
-  load_rec4(vpos, nv, tv.w, p[3]);
+  load_rec4(vpos, tv.x, p[0]);
+  load_rec4(vpos, tv.y, p[1]);
+  load_rec4(vpos, tv.z, p[2]);
+  load_rec4(vpos, tv.w, p[3]);
   if (use_max) {
-    if (!HAVE_DETS) load_q(vq, nv, best_vertex(tv, p[0][3], p[1][3], p[2][3], p[3][3]), Q, detQ);
+    if (!HAVE_DETS) load_q(vq, best_vertex(tv, p[0][3], p[1][3], p[2][3], p[3][3]), Q, detQ);
   } else {
     centroid_transform<KIND>(vedge, nv, tv, Q, eig);
     detQ = FAST ? magst::det3(Q) : 0.0;
@@ -687,8 +667,8 @@ k_tets(int64_t nt, int64_t elem_off, int64_t nv, const int4* __restrict__ tet_v,
     int4 tv_cur = make_int4(0, 0, 0, 0), tv_nx = tv_cur;
     double dets[4] = {0, 0, 0, 0};
     auto load_dets = [&](const int4& tv, double* d) {
-      d[0] = __ldg(&chunk_ptr(vpos, nv, 1, tv.x)->y); d[1] = __ldg(&chunk_ptr(vpos, nv, 1, tv.y)->y);
-      d[2] = __ldg(&chunk_ptr(vpos, nv, 1, tv.z)->y); d[3] = __ldg(&chunk_ptr(vpos, nv, 1, tv.w)->y);
+      d[0] = __ldg(&chunk_ptr<2>(vpos, 1, tv.x)->y); d[1] = __ldg(&chunk_ptr<2>(vpos, 1, tv.y)->y);
+      d[2] = __ldg(&chunk_ptr<2>(vpos, 1, tv.z)->y); d[3] = __ldg(&chunk_ptr<2>(vpos, 1, tv.w)->y);
     };
     if (t < t_end) {
       f_cur = flags[elem_off + t];
@@ -763,7 +743,7 @@ __device__ __forceinline__ void centroid_transform_tri(const double* __restrict_
 #pragma unroll
     for (int n = 0; n < 3; ++n) {
       double r[4];
-      load_rec4(vedge, nv, vid[n], r);
+      load_rec4(vedge, vid[n], r);
       h = magst::add(h, magst::mul(r[3], n ? N1 : N0));
     }
     magst::identity(Q);
@@ -776,7 +756,7 @@ __device__ __forceinline__ void centroid_transform_tri(const double* __restrict_
   for (int i = 0; i < 9; ++i) c[i] = 0;
 #pragma unroll
   for (int n = 0; n < 3; ++n) {
-    Rec12 r = load_rec12(vedge, nv, vid[n]);
+    Rec12 r = load_rec12(vedge, vid[n]);
 #pragma unroll
     for (int i = 0; i < 9; ++i) c[i] = magst::add(c[i], magst::mul(r.v[3 + i], n ? N1 : N0));
   }
@@ -797,7 +777,7 @@ __device__ __forceinline__ double tri_quality_eval(const int32_t vid[3], int64_t
 {
   double p[3][4];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) load_rec4(vpos, nv, vid[i], p[i]);
+  for (int i = 0; i < 3; ++i) load_rec4(vpos, vid[i], p[i]);
   M3 Q;
   double detQ;
   if (use_max) {
@@ -806,7 +786,7 @@ __device__ __forceinline__ double tri_quality_eval(const int32_t vid[3], int64_t
 #pragma unroll
     for (int i = 0; i < 3; ++i)
       if (p[i][3] > maxJ) { maxJ = p[i][3]; vb = vid[i]; }
-    load_q(vq, nv, vb, Q, detQ);
+    load_q(vq, vb, Q, detQ);
   } else {
     centroid_transform_tri<KIND>(vedge, nv, vid, Q, eig);
   }
@@ -908,10 +888,10 @@ __device__ __forceinline__ int unrotate_code(int code, int rot)
     if (code & (1 << i)) out |= (1 << ((i + c_shift_table[rot]) % 3));
   return out;
 }
-__device__ __forceinline__ V3 load_pos(const double* __restrict__ vpos, int64_t nv, int32_t v)
+__device__ __forceinline__ V3 load_pos(const double* __restrict__ vpos, int32_t v)
 {
   double r[4];
-  load_rec4(vpos, nv, v, r);
+  load_rec4(vpos, v, r);
   return V3{r[0], r[1], r[2]};
 }
 // isPrismOk (maQuality.cc:490-530) / isPyramidOk (:532-560)
@@ -924,7 +904,7 @@ __global__ void k_layer(int64_t np, int64_t npy, int64_t nv, const int32_t* __re
   if (i < np) {
     V3 p[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) p[k] = load_pos(vpos, nv, prism_v[6 * i + k]);
+    for (int k = 0; k < 6; ++k) p[k] = load_pos(vpos, prism_v[6 * i + k]);
     code = 0xFF;
     for (int r = 0; r < 6; ++r) {
       const int* n2o = c_prism_rotation[r];
@@ -941,7 +921,7 @@ __global__ void k_layer(int64_t np, int64_t npy, int64_t nv, const int32_t* __re
     int64_t j = i - np;
     V3 p[5];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) p[k] = load_pos(vpos, nv, pyr_v[5 * j + k]);
+    for (int k = 0; k < 5; ++k) p[k] = load_pos(vpos, pyr_v[5 * j + k]);
     code = -1;
     for (int r = 0; r < 2; ++r) {
       const int* n2o = c_pyramid_rotation[r];
@@ -1071,22 +1051,39 @@ static unsigned persistent_grid(mag_ctx* c, int& per_sm, const void* kernel, int
   return (unsigned)(g < 1 ? 1 : g);
 }
 
-template <int KIND>
-static int launch_edges(mag_ctx* c, const SweepParams& P, bool fast)
+static EdgeParams edge_params(const SweepParams& P)
 {
-  const int2* ev = reinterpret_cast<const int2*>(c->d_edge_v);
-  if (fast) {
-    static int per_sm = 0;
-    const unsigned g = persistent_grid(c, per_sm, (const void*)k_edges<KIND, true>, c->ne, kEdgeThreads);
-    k_edges<KIND, true><<<g, kEdgeThreads, 0, c->stream>>>(c->ne, c->nv, ev, c->d_vedge, c->d_edge_owned, c->d_edge_flags, c->d_len, P, c->d_stats, c->d_near_edge, c->d_edge_order);
-  } else {
-    static int per_sm = 0;
-    const unsigned g = persistent_grid(c, per_sm, (const void*)k_edges<KIND, false>, c->ne, kEdgeThreads);
-    k_edges<KIND, false><<<g, kEdgeThreads, 0, c->stream>>>(c->ne, c->nv, ev, c->d_vedge, c->d_edge_owned, c->d_edge_flags, c->d_len, P, c->d_stats, c->d_near_edge, c->d_edge_order);
-  }
+  EdgeParams E;
+  const bool do_split = P.ops & MAG_OP_MARK_SPLIT, do_coll = P.ops & MAG_OP_MARK_COLLAPSE;
+  E.off_bits = (do_split ? 0 : MAG_DONT_SPLIT) | (do_coll ? 0 : MAG_DONT_COLLAPSE);
+  E.err_mask = (do_split ? MAG_SPLIT : 0) | (do_coll ? MAG_COLLAPSE : 0);
+  E.want_len = (P.ops & MAG_OP_LENGTHS) ? 1 : 0;
+  E.ops = P.ops;
+  E.max_len = P.max_len;
+  E.min_len = P.min_len;
+  E.tol_max = std::isfinite(P.max_len) ? MAG_NEAR_REL * std::fabs(P.max_len) : -1.0;
+  E.tol_min = std::isfinite(P.min_len) ? MAG_NEAR_REL * std::fabs(P.min_len) : -1.0;
+  return E;
+}
+
+template <int KIND, bool FAST, bool OWNED>
+static int launch_edges_t(mag_ctx* c, const SweepParams& P)
+{
+  static int per_sm = 0;
+  const unsigned g = persistent_grid(c, per_sm, (const void*)k_edges<KIND, FAST, OWNED>, c->ne, kEdgeThreads);
+  k_edges<KIND, FAST, OWNED><<<g, kEdgeThreads, 0, c->stream>>>((int32_t)c->ne, reinterpret_cast<const int2*>(c->d_edge_v), c->d_vedge,
+                                                                c->d_edge_owned, c->d_edge_flags, c->d_len, edge_params(P), c->d_stats,
+                                                                c->d_near_edge, c->d_edge_order);
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;
   return MAG_OK;
+}
+template <int KIND>
+static int launch_edges(mag_ctx* c, const SweepParams& P, bool fast)
+{
+  const bool owned = c->d_edge_owned != nullptr;
+  if (fast) return owned ? launch_edges_t<KIND, true, true>(c, P) : launch_edges_t<KIND, true, false>(c, P);
+  return owned ? launch_edges_t<KIND, false, true>(c, P) : launch_edges_t<KIND, false, false>(c, P);
 }
 
 template <int KIND>
