@@ -10,6 +10,7 @@ int magk_pack(mag_ctx* c);
 int magk_init_stats(mag_ctx* c);
 int magk_vertex_pass(mag_ctx* c);
 int magk_build_schedule(mag_ctx* c);
+int magk_fold_owned(mag_ctx* c);
 int magk_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double good_q, int use_max, int fp_mode);
 double magk_key_to_double(unsigned long long k);
 void magc_destroy(mag_ctx* c);
@@ -88,6 +89,29 @@ int repack(mag_ctx* c)
 
 } // namespace
 
+// device accumulators -> the public struct; the reference's assertions on this path become return codes
+int mag_stats_from_dev(mag_ctx* c, const MagDevStats& s, mag_stats* out)
+{
+  out->n_split = (int64_t)s.n_split;
+  out->n_collapse = (int64_t)s.n_collapse;
+  out->n_bad = (int64_t)s.n_bad;
+  out->n_edges_evaluated = (int64_t)s.n_edges_eval;
+  out->n_elems_evaluated = (int64_t)s.n_elems_eval;
+  out->n_near_threshold = (int64_t)(s.n_near_edge + s.n_near_elem);
+  out->n_layer_unsafe = (int64_t)s.n_layer_unsafe;
+  out->n_flag_mismatch = (int64_t)s.n_flag_mismatch;
+  out->min_quality = magk_key_to_double(s.min_q_key);
+  memcpy(&out->max_length, &s.max_len_bits, 8);
+  out->sum_length = s.sum_len;
+  if (s.n_flag_err)
+    return mag_fail(c, MAG_ERR_FLAG_STATE, "%llu entities already carried the flag being marked (ma::markEntities asserts, maAdapt.cc:308)", s.n_flag_err);
+  if (s.n_eigen_fail)
+    return mag_fail(c, MAG_ERR_EIGEN, "eigenQR failed on %llu evaluations (apf::eigen asserts convergence, apfMatrix.cc:76)", s.n_eigen_fail);
+  if (s.n_nonsimplex)
+    return mag_fail(c, MAG_ERR_NONSIMPLEX, "%llu prisms/pyramids reached markBadQuality without OK_QUALITY (maQuality.cc:169-182 has no entry for them)", s.n_nonsimplex);
+  return MAG_OK;
+}
+
 extern "C" {
 
 const char* mag_last_error(const mag_ctx* c) { return c ? c->err.c_str() : g_create_err.c_str(); }
@@ -121,7 +145,7 @@ int mag_create(mag_ctx** out, int device)
   c->d_near_edge = c->d_near_elem = nullptr;
   c->cap_vedge = c->cap_ma = c->cap_mb = 0;
   c->last_ops = 0; c->last_fp_mode = 0;
-  c->nccl_comm = nullptr; c->nranks = 1; c->rank = 0;
+  c->nccl_comm = nullptr; c->nranks = 1; c->rank = 0; c->d_gather = nullptr; c->h_gather = nullptr;
   c->t_slots = c->t_used = 0; c->n_launches = 0;
   auto fail = [&](cudaError_t err, const char* what) {
     int rc = mag_fail(nullptr, MAG_ERR_CUDA, "mag_create: %s: %s", what, cudaGetErrorString(err));
@@ -220,7 +244,7 @@ static int set_mesh_impl(mag_ctx* c, int dim, int64_t nv, const double* xyz, int
     return rc;
   if (edge_owned && (rc = upload(c, c->d_edge_owned, edge_owned, (size_t)ne))) return rc;
   if (elem_owned && (rc = upload(c, c->d_elem_owned, elem_owned, (size_t)nel))) return rc;
-  if ((rc = magk_build_schedule(c))) return rc;
+  if ((rc = magk_fold_owned(c)) || (rc = magk_build_schedule(c))) return rc;
   return repack(c);
 }
 
@@ -335,25 +359,7 @@ int mag_get_stats(mag_ctx* c, mag_stats* out)
   if (!out) return mag_fail(c, MAG_ERR_ARG, "mag_get_stats: null out");
   MAG_CUDA(c, cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(MagDevStats), cudaMemcpyDeviceToHost, c->stream));
   MAG_CUDA(c, cudaStreamSynchronize(c->stream));
-  const MagDevStats& s = *c->h_stats;
-  out->n_split = (int64_t)s.n_split;
-  out->n_collapse = (int64_t)s.n_collapse;
-  out->n_bad = (int64_t)s.n_bad;
-  out->n_edges_evaluated = (int64_t)s.n_edges_eval;
-  out->n_elems_evaluated = (int64_t)s.n_elems_eval;
-  out->n_near_threshold = (int64_t)(s.n_near_edge + s.n_near_elem);
-  out->n_layer_unsafe = (int64_t)s.n_layer_unsafe;
-  out->n_flag_mismatch = (int64_t)s.n_flag_mismatch;
-  out->min_quality = magk_key_to_double(s.min_q_key);
-  memcpy(&out->max_length, &s.max_len_bits, 8);
-  out->sum_length = s.sum_len;
-  if (s.n_flag_err)
-    return mag_fail(c, MAG_ERR_FLAG_STATE, "%llu entities already carried the flag being marked (ma::markEntities asserts, maAdapt.cc:308)", s.n_flag_err);
-  if (s.n_eigen_fail)
-    return mag_fail(c, MAG_ERR_EIGEN, "eigenQR failed on %llu evaluations (apf::eigen asserts convergence, apfMatrix.cc:76)", s.n_eigen_fail);
-  if (s.n_nonsimplex)
-    return mag_fail(c, MAG_ERR_NONSIMPLEX, "%llu prisms/pyramids reached markBadQuality without OK_QUALITY (maQuality.cc:169-182 has no entry for them)", s.n_nonsimplex);
-  return MAG_OK;
+  return mag_stats_from_dev(c, *c->h_stats, out);
 }
 
 int mag_timing_begin(mag_ctx* c, int max_sweeps)

@@ -108,6 +108,8 @@ void free_links(mag_ctx* c)
 void magc_destroy(mag_ctx* c)
 {
   free_links(c);
+  cudaFree(c->d_gather); c->d_gather = nullptr;
+  cudaFreeHost(c->h_gather); c->h_gather = nullptr;
   if (c->nccl_comm && g_nccl.h) g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
   c->nccl_comm = nullptr;
 }
@@ -141,6 +143,10 @@ int mag_comm_init(mag_ctx* c, int nranks, int rank, const void* unique_id)
   c->nccl_comm = comm;
   c->nranks = nranks;
   c->rank = rank;
+  if (c->d_gather) { cudaFree(c->d_gather); c->d_gather = nullptr; }
+  if (c->h_gather) { cudaFreeHost(c->h_gather); c->h_gather = nullptr; }
+  MAG_CUDA(c, cudaMalloc((void**)&c->d_gather, sizeof(MagDevStats) * (size_t)nranks));
+  MAG_CUDA(c, cudaMallocHost((void**)&c->h_gather, sizeof(MagDevStats) * (size_t)nranks));
   return MAG_OK;
 }
 
@@ -190,34 +196,26 @@ int mag_allreduce_stats(mag_ctx* c, mag_stats* global)
 {
   if (!c || !global) return MAG_ERR_ARG;
   MAG_CUDA(c, cudaSetDevice(c->device));
-  mag_stats mine;
-  int rc = mag_get_stats(c, &mine);
-  if (rc) return rc;
-  if (c->nranks == 1 || !c->nccl_comm) { *global = mine; return MAG_OK; }
-  // one all-gather of the whole struct (sum / min / max are different operators, so a single
-  // allreduce cannot carry them), reduced locally
-  const size_t sz = sizeof(mag_stats);
-  char* d_buf = nullptr;
-  MAG_CUDA(c, cudaMalloc((void**)&d_buf, sz * (size_t)(c->nranks + 1)));
-  MAG_CUDA(c, cudaMemcpyAsync(d_buf, &mine, sz, cudaMemcpyHostToDevice, c->stream));
-  MAG_NCCL(c, g_nccl.AllGather(d_buf, d_buf + sz, sz, ncclChar, (ncclComm_t)c->nccl_comm, c->stream));
-  std::vector<mag_stats> all((size_t)c->nranks);
-  MAG_CUDA(c, cudaMemcpyAsync(all.data(), d_buf + sz, sz * (size_t)c->nranks, cudaMemcpyDeviceToHost, c->stream));
+  if (c->nranks == 1 || !c->nccl_comm) return mag_get_stats(c, global);
+  // one all-gather of the device accumulators (sum / min / max are different operators, so a single allreduce cannot
+  // carry them), one copy to pinned memory, one host synchronisation; reduced locally, identically on every rank
+  const size_t sz = sizeof(MagDevStats);
+  MAG_NCCL(c, g_nccl.AllGather(c->d_stats, c->d_gather, sz, ncclChar, (ncclComm_t)c->nccl_comm, c->stream));
+  MAG_CUDA(c, cudaMemcpyAsync(c->h_gather, c->d_gather, sz * (size_t)c->nranks, cudaMemcpyDeviceToHost, c->stream));
   MAG_CUDA(c, cudaStreamSynchronize(c->stream));
-  MAG_CUDA(c, cudaFree(d_buf));
-  mag_stats g = all[0];
+  MagDevStats g = c->h_gather[0];
   for (int r = 1; r < c->nranks; ++r) {
-    const mag_stats& s = all[(size_t)r];
+    const MagDevStats& s = c->h_gather[r];
     g.n_split += s.n_split; g.n_collapse += s.n_collapse; g.n_bad += s.n_bad;
-    g.n_edges_evaluated += s.n_edges_evaluated; g.n_elems_evaluated += s.n_elems_evaluated;
-    g.n_near_threshold += s.n_near_threshold; g.n_layer_unsafe += s.n_layer_unsafe;
+    g.n_edges_eval += s.n_edges_eval; g.n_elems_eval += s.n_elems_eval;
+    g.n_near_edge += s.n_near_edge; g.n_near_elem += s.n_near_elem; g.n_layer_unsafe += s.n_layer_unsafe;
+    g.n_flag_err += s.n_flag_err; g.n_eigen_fail += s.n_eigen_fail; g.n_nonsimplex += s.n_nonsimplex;
     g.n_flag_mismatch += s.n_flag_mismatch;
-    if (s.min_quality < g.min_quality) g.min_quality = s.min_quality;
-    if (s.max_length > g.max_length) g.max_length = s.max_length;
-    g.sum_length += s.sum_length;
+    if (s.min_q_key < g.min_q_key) g.min_q_key = s.min_q_key;
+    if (s.max_len_bits > g.max_len_bits) g.max_len_bits = s.max_len_bits;
+    g.sum_len += s.sum_len;
   }
-  *global = g;
-  return MAG_OK;
+  return mag_stats_from_dev(c, g, global);
 }
 
 } // extern "C"

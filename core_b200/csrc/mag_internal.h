@@ -96,9 +96,12 @@ struct mag_ctx {
   void* nccl_comm;
   int nranks, rank;
   std::vector<MagLinks> links;
+  MagDevStats* d_gather; // [nranks] all-gathered accumulators (mag_allreduce_stats)
+  MagDevStats* h_gather; // pinned
 };
 
 int mag_fail(mag_ctx* c, int code, const char* fmt, ...);
+int mag_stats_from_dev(mag_ctx* c, const MagDevStats& s, mag_stats* out);
 #define MAG_CUDA(c, call)                                                                      \
   do {                                                                                         \
     cudaError_t e_ = (call);                                                                   \

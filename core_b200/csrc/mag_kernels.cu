@@ -76,6 +76,9 @@ __device__ __forceinline__ double warp_sum(double v)
 //   d_vpos   K=2 {x,y} {z,det Q_v}
 //   d_vq     K=5 {Q00,Q01} {Q02,Q10} {Q11,Q12} {Q20,Q21} {Q22,det Q_v}
 constexpr int kVB = MAG_VBLOCK;
+// Ownership rides in the connectivity: the sign bit of an entity's FIRST vertex id means "not owned by this part"
+// (k_fold_owned, at export time), so the owned-only counters of markEntities (maAdapt.cc:316) cost no extra load.
+constexpr int32_t kVidMask = 0x7fffffff;
 template <int K>
 __device__ __forceinline__ const double2* chunk_ptr(const double* __restrict__ base, int k, int64_t v)
 {
@@ -139,6 +142,13 @@ __global__ void k_pack12_logm(int64_t nv, const double* __restrict__ xyz, const 
   *chunk_ptr_w<6>(rec, 3, v) = make_double2(m[3], m[4]);
   *chunk_ptr_w<6>(rec, 4, v) = make_double2(m[5], m[6]);
   *chunk_ptr_w<6>(rec, 5, v) = make_double2(m[7], m[8]);
+}
+
+// sets the sign bit of the first vertex id of every entity this part does not own (stride = vertices per entity)
+__global__ void k_fold_owned(int64_t n, int stride, const uint8_t* __restrict__ owned, int32_t* __restrict__ conn)
+{
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n && !owned[i]) conn[i * stride] |= (int32_t)0x80000000;
 }
 
 // ------------------------------------------------------------------ per-vertex pass
@@ -367,9 +377,9 @@ struct EdgeParams {
 constexpr int32_t kSkipSplit = MAG_DONT_SPLIT | MAG_NEED_NOT_SPLIT, kSkipColl = MAG_DONT_COLLAPSE | MAG_NEED_NOT_COLLAPSE;
 
 // drain n (<= 32) queued edges: entry i is handled by lane i.  Returns bit 0: evaluated, bit 1: counted SPLIT, bit 2: counted COLLAPSE
-template <int KIND, bool FAST, bool OWNED>
+template <int KIND, bool FAST>
 __device__ __noinline__ unsigned drain_edges(NearQueue& q, int first, int n, const int2* __restrict__ edge_v,
-                                             const double* __restrict__ vedge, const uint8_t* __restrict__ owned_arr,
+                                             const double* __restrict__ vedge,
                                              int32_t* __restrict__ flags, double* __restrict__ lengths, uint32_t ops,
                                              double max_len, double min_len,
                                              MagDevStats* st, int32_t* __restrict__ near_list)
@@ -386,10 +396,12 @@ __device__ __noinline__ unsigned drain_edges(NearQueue& q, int first, int n, con
       const bool need_split = (P.ops & MAG_OP_MARK_SPLIT) && !(f & kSkipSplit);
       const bool need_coll = (P.ops & MAG_OP_MARK_COLLAPSE) && !(f & kSkipColl);
       EdgeRecs<KIND> R;
-      load_edge_recs<KIND>(vedge, __ldg(edge_v + e), R);
+      int2 ev = __ldg(edge_v + e);
+      const bool owned = ev.x >= 0;
+      ev.x &= kVidMask;
+      load_edge_recs<KIND>(vedge, ev, R);
       int eig = 0;
       const double len = edge_length_strict<KIND>(R, &eig);
-      const bool owned = OWNED ? (owned_arr[e] != 0) : true;
       unsigned cs = 0, cc = 0;
       mark_edge(len, f, need_split, need_coll, owned, P, cs, cc);
       out = 1u | (cs << 1) | (cc << 2);
@@ -404,10 +416,10 @@ __device__ __noinline__ unsigned drain_edges(NearQueue& q, int first, int n, con
 // Persistent edge kernel.  Per thread and tile: the flag word and the end vertices are loaded one tile ahead; the two
 // vertex records are gathered only when the flag word says the edge has to be evaluated at all (skipped edges cost 12
 // bytes).  Everything is indexed with int32 (mag_set_mesh rejects meshes with 2^31 or more entities of one dimension).
-template <int KIND, bool FAST, bool OWNED>
+template <int KIND, bool FAST>
 __global__ void __launch_bounds__(kEdgeThreads, FAST ? MAG_EDGE_BLOCKS : MAG_EDGE_BLOCKS_STRICT)
 k_edges(int32_t ne, const int2* __restrict__ edge_v, const double* __restrict__ vedge,
-        const uint8_t* __restrict__ owned_arr, int32_t* __restrict__ flags, double* __restrict__ lengths,
+        int32_t* __restrict__ flags, double* __restrict__ lengths,
         EdgeParams P, MagDevStats* st, int32_t* __restrict__ near_list, const int32_t* __restrict__ chunk_order)
 {
   __shared__ NearQueue q;
@@ -438,9 +450,9 @@ k_edges(int32_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
         if (f & P.err_mask) ++c_err;
         if (P.want_len || need_split || need_coll) {
           EdgeRecs<KIND> R;
-          load_edge_recs<KIND>(vedge, ev, R);
+          const bool owned = ev.x >= 0;                 // sign bit of the first vertex id = "not owned" (k_fold_owned)
+          load_edge_recs<KIND>(vedge, make_int2(ev.x & kVidMask, ev.y), R);
           const double len = FAST ? edge_length_fast<KIND>(R, &eig_any) : edge_length_strict<KIND>(R, &eig_any);
-          const bool owned = OWNED ? (owned_arr[e] != 0) : true;
           if (P.want_len) {
             lengths[e] = len;
             if (owned && len > maxlen) maxlen = len;
@@ -467,7 +479,7 @@ k_edges(int32_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
       }
       if (queue_push(q, qn, nr, (int32_t)e, f)) {
         qn -= 32;
-        const unsigned r = drain_edges<KIND, FAST, OWNED>(q, qn, 32, edge_v, vedge, owned_arr, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list);
+        const unsigned r = drain_edges<KIND, FAST>(q, qn, 32, edge_v, vedge, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list);
         c_eval += r & 1u; c_split += (r >> 1) & 1u; c_coll += (r >> 2) & 1u;
       }
       f = f_nx;
@@ -475,7 +487,7 @@ k_edges(int32_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
     }
   }
   if (qn) {
-    const unsigned r = drain_edges<KIND, FAST, OWNED>(q, 0, qn, edge_v, vedge, owned_arr, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list);
+    const unsigned r = drain_edges<KIND, FAST>(q, 0, qn, edge_v, vedge, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list);
     c_eval += r & 1u; c_split += (r >> 1) & 1u; c_coll += (r >> 2) & 1u;
   }
   if (eig_any) atomicAdd(&st->n_eigen_fail, 1ull);
@@ -603,11 +615,18 @@ __device__ __forceinline__ void mark_tet(double q, int32_t& f, bool owned, const
   else f |= MAG_OK_QUALITY;
 }
 
+// What the tet kernel needs of the sweep parameters, decoded once on the host (see EdgeParams)
+struct TetParams {
+  uint32_t ops;
+  int do_bad, want_q, use_max;
+  double good_q, tol_q;   // tol_q = MAG_NEAR_REL * |good_q|, or -1 when good_q is not finite
+};
+
 // returns bit 0: evaluated, bit 1: counted BAD_QUALITY
 template <int KIND, bool FAST>
-__device__ __noinline__ unsigned drain_tets(NearQueue& q, int first, int n, int64_t elem_off, int64_t nv, const int4* __restrict__ tet_v,
+__device__ __noinline__ unsigned drain_tets(NearQueue& q, int first, int n, int32_t elem_off, int64_t nv, const int4* __restrict__ tet_v,
                                             const double* __restrict__ vpos, const double* __restrict__ vq,
-                                            const double* __restrict__ vedge, const uint8_t* __restrict__ owned_arr,
+                                            const double* __restrict__ vedge,
                                             int32_t* __restrict__ flags, double* __restrict__ qual, uint32_t ops,
                                             double good_q, int use_max,
                                             MagDevStats* st, int32_t* __restrict__ near_list)
@@ -618,14 +637,15 @@ __device__ __noinline__ unsigned drain_tets(NearQueue& q, int first, int n, int6
   unsigned out = 0;
   if (lane < n) {
     const int32_t t = q.e[w][first + lane];
-    const int64_t el = elem_off + t;
-    near_list[base + lane] = (int32_t)el;
+    const int32_t el = elem_off + t;
+    near_list[base + lane] = el;
     if (FAST) {
       int32_t f = q.f[w][first + lane];
-      const int4 tv = __ldg(tet_v + t);
+      int4 tv = __ldg(tet_v + t);
+      const bool owned = tv.x >= 0;
+      tv.x &= kVidMask;
       int eig = 0;
       const double qv = tet_quality_eval<KIND, false, false>(tv, nv, vpos, vq, vedge, P.use_max, &eig, nullptr);
-      const bool owned = owned_arr ? (owned_arr[el] != 0) : true;
       unsigned cb = 0;
       mark_tet(qv, f, owned, P, cb);
       out = 1u | (cb << 1);
@@ -637,14 +657,15 @@ __device__ __noinline__ unsigned drain_tets(NearQueue& q, int first, int n, int6
   return out;
 }
 
-// Software pipeline of the tet kernel, per thread and tile k: flag word + vertices two tiles ahead; the four det Q_v
-// (8-byte loads out of the {x,y,z,det} records, which also pulls those records towards L1) one tile ahead, so that the
-// choice of the max-Jacobian vertex does not sit between two dependent gathers.
+// Persistent tet kernel, int32 indexing throughout (mag_set_mesh rejects larger meshes).  Software pipeline per thread
+// and tile k: flag word + vertices two tiles ahead; the four {z, det Q_v} chunks one tile ahead, so that the choice of
+// the max-Jacobian vertex (getMetricWithMaxJacobean, maQuality.cc:83-108) does not sit between two dependent gathers and
+// no chunk is fetched twice: at the tile itself only the four {x,y} chunks and the winner's transform are loaded.
 template <int KIND, bool FAST>
 __global__ void __launch_bounds__(kTetThreads, FAST ? MAG_TET_BLOCKS : MAG_TET_BLOCKS_STRICT)
-k_tets(int64_t nt, int64_t elem_off, int64_t nv, const int4* __restrict__ tet_v, const double* __restrict__ vpos,
-       const double* __restrict__ vq, const double* __restrict__ vedge, const uint8_t* __restrict__ owned_arr,
-       int32_t* __restrict__ flags, double* __restrict__ qual, SweepParams P, MagDevStats* st,
+k_tets(int32_t nt, int32_t elem_off, int64_t nv, const int4* __restrict__ tet_v, const double* __restrict__ vpos,
+       const double* __restrict__ vq, const double* __restrict__ vedge,
+       int32_t* __restrict__ flags, double* __restrict__ qual, TetParams P, MagDevStats* st,
        int32_t* __restrict__ near_list, const int32_t* __restrict__ chunk_order)
 {
   __shared__ NearQueue q;
@@ -652,77 +673,90 @@ k_tets(int64_t nt, int64_t elem_off, int64_t nv, const int4* __restrict__ tet_v,
   unsigned c_bad = 0, c_eval = 0, c_err = 0;
   unsigned long long minkey = ~0ull;
   int qn = 0, eig_any = 0;
-  const bool do_bad = P.ops & MAG_OP_MARK_BAD, want_q = P.ops & MAG_OP_QUALITIES;
-  const int64_t ntiles = (nt + kTetThreads - 1) / kTetThreads;
-  const int64_t nchunks = (ntiles + kChunkTiles - 1) / kChunkTiles;
+  constexpr int kChunkTets = kChunkTiles * kTetThreads;
+  const int nchunks = (nt + kChunkTets - 1) / kChunkTets;
+  flags += elem_off;
+  qual += elem_off;
+  auto load_zd = [&](const int4& tv, double2* zd) {
+    zd[0] = __ldg(chunk_ptr<2>(vpos, 1, tv.x & kVidMask)); zd[1] = __ldg(chunk_ptr<2>(vpos, 1, tv.y));
+    zd[2] = __ldg(chunk_ptr<2>(vpos, 1, tv.z)); zd[3] = __ldg(chunk_ptr<2>(vpos, 1, tv.w));
+  };
   for (;;) {
     const long long ticket = next_chunk(&st->elem_chunk, &chunk_slot);
     if (ticket >= nchunks) break;
-    const long long chunk = chunk_order[ticket];
-    const int64_t t0 = chunk * kChunkTiles;
-    const int64_t t1 = (t0 + kChunkTiles < ntiles) ? t0 + kChunkTiles : ntiles;
-    const int64_t t_end = (t1 * kTetThreads < nt) ? t1 * kTetThreads : nt;
-    int64_t t = t0 * kTetThreads + threadIdx.x;
+    const int t0 = chunk_order[ticket] * kChunkTets;
+    const int t_end = (nt - t0 < kChunkTets) ? nt : t0 + kChunkTets;
+    const int tiles = (t_end - t0 + kTetThreads - 1) / kTetThreads;
+    int t = t0 + (int)threadIdx.x;
     int32_t f_cur = 0, f_nx = 0;
     int4 tv_cur = make_int4(0, 0, 0, 0), tv_nx = tv_cur;
-    double dets[4] = {0, 0, 0, 0};
-    auto load_dets = [&](const int4& tv, double* d) {
-      d[0] = __ldg(&chunk_ptr<2>(vpos, 1, tv.x)->y); d[1] = __ldg(&chunk_ptr<2>(vpos, 1, tv.y)->y);
-      d[2] = __ldg(&chunk_ptr<2>(vpos, 1, tv.z)->y); d[3] = __ldg(&chunk_ptr<2>(vpos, 1, tv.w)->y);
-    };
+    double2 zd[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) zd[i] = make_double2(0.0, 0.0);
     if (t < t_end) {
-      f_cur = flags[elem_off + t];
+      f_cur = flags[t];
       tv_cur = __ldg(tet_v + t);
-      if (want_q || (do_bad && !(f_cur & MAG_OK_QUALITY))) load_dets(tv_cur, dets);
+      if (P.want_q || (P.do_bad && !(f_cur & MAG_OK_QUALITY))) load_zd(tv_cur, zd);
     }
-    if (t + kTetThreads < t_end) { f_nx = flags[elem_off + t + kTetThreads]; tv_nx = __ldg(tet_v + t + kTetThreads); }
-    for (int64_t tile = t0; tile < t1; ++tile, t += kTetThreads) {
+    if (t + kTetThreads < t_end) { f_nx = flags[t + kTetThreads]; tv_nx = __ldg(tet_v + t + kTetThreads); }
+    for (int tile = 0; tile < tiles; ++tile, t += kTetThreads) {
       const int32_t f_in = f_cur;
-      const int4 tv = tv_cur;
-      double d_cur[4] = {dets[0], dets[1], dets[2], dets[3]};
-      // next tile: its dets; tile after: flag word + vertices
+      int4 tv = tv_cur;
+      const bool owned = tv.x >= 0;
+      tv.x &= kVidMask;
+      const double2 z0 = zd[0], z1 = zd[1], z2 = zd[2], z3 = zd[3];
+      // next tile: its {z,det} chunks; tile after: flag word + vertices
       f_cur = f_nx;
       tv_cur = tv_nx;
-      if (t + kTetThreads < t_end && (want_q || (do_bad && !(f_cur & MAG_OK_QUALITY)))) load_dets(tv_cur, dets);
-      if (t + 2 * kTetThreads < t_end) { f_nx = flags[elem_off + t + 2 * kTetThreads]; tv_nx = __ldg(tet_v + t + 2 * kTetThreads); }
+      if (t + kTetThreads < t_end && (P.want_q || (P.do_bad && !(f_cur & MAG_OK_QUALITY)))) load_zd(tv_cur, zd);
+      if (t + 2 * kTetThreads < t_end) { f_nx = flags[t + 2 * kTetThreads]; tv_nx = __ldg(tet_v + t + 2 * kTetThreads); }
       bool nr = false;
       if (t < t_end) {
-        const int64_t el = elem_off + t;
         int32_t f = f_in;
-        if (do_bad && (f & MAG_BAD_QUALITY)) ++c_err;
-        const bool need_bad = do_bad && !(f & MAG_OK_QUALITY);
-        if (want_q || need_bad) {
-          const double qv = tet_quality_eval<KIND, FAST, true>(tv, nv, vpos, vq, vedge, P.use_max, &eig_any, d_cur);
-          if (want_q) {
-            qual[el] = qv;
+        if (P.do_bad && (f & MAG_BAD_QUALITY)) ++c_err;
+        const bool need_bad = P.do_bad && !(f & MAG_OK_QUALITY);
+        if (P.want_q || need_bad) {
+          M3 Q;
+          double detQ = 0.0;
+          if (P.use_max) load_q(vq, best_vertex(tv, z0.y, z1.y, z2.y, z3.y), Q, detQ);
+          const double2 a0 = __ldg(chunk_ptr<2>(vpos, 0, tv.x)), a1 = __ldg(chunk_ptr<2>(vpos, 0, tv.y)),
+                        a2 = __ldg(chunk_ptr<2>(vpos, 0, tv.z)), a3 = __ldg(chunk_ptr<2>(vpos, 0, tv.w));
+          if (!P.use_max) {
+            centroid_transform<KIND>(vedge, nv, tv, Q, &eig_any);
+            detQ = FAST ? magst::det3(Q) : 0.0;
+          }
+          const V3 x[4] = {V3{a0.x, a0.y, z0.x}, V3{a1.x, a1.y, z1.x}, V3{a2.x, a2.y, z2.x}, V3{a3.x, a3.y, z3.x}};
+          const double qv = FAST ? magfa::tet_quality(x, Q, detQ) : magst::tet_quality(x, Q);
+          if (P.want_q) {
+            qual[t] = qv;
             const unsigned long long k = dkey(qv);
             minkey = k < minkey ? k : minkey;
           }
-          nr = need_bad && near_thr(qv, P.good_q);
+          nr = need_bad && fabs(qv - P.good_q) <= P.tol_q;
           if (need_bad && !(FAST && nr)) {
-            const bool owned = owned_arr ? (owned_arr[el] != 0) : true;
             ++c_eval;
-            mark_tet(qv, f, owned, P, c_bad);
-            if (f != f_in) flags[el] = f;
+            const bool bad = qv < P.good_q;
+            c_bad += (bad && owned) ? 1u : 0u;
+            flags[t] = f | (bad ? MAG_BAD_QUALITY : MAG_OK_QUALITY);
           }
         }
       }
       if (queue_push(q, qn, nr, (int32_t)t, f_in)) {
         qn -= 32;
-        const unsigned r = drain_tets<KIND, FAST>(q, qn, 32, elem_off, nv, tet_v, vpos, vq, vedge, owned_arr, flags, qual, P.ops, P.good_q, P.use_max, st, near_list);
+        const unsigned r = drain_tets<KIND, FAST>(q, qn, 32, elem_off, nv, tet_v, vpos, vq, vedge, flags - elem_off, qual - elem_off, P.ops, P.good_q, P.use_max, st, near_list);
         c_eval += r & 1u; c_bad += (r >> 1) & 1u;
       }
     }
   }
   if (qn) {
-    const unsigned r = drain_tets<KIND, FAST>(q, 0, qn, elem_off, nv, tet_v, vpos, vq, vedge, owned_arr, flags, qual, P.ops, P.good_q, P.use_max, st, near_list);
+    const unsigned r = drain_tets<KIND, FAST>(q, 0, qn, elem_off, nv, tet_v, vpos, vq, vedge, flags - elem_off, qual - elem_off, P.ops, P.good_q, P.use_max, st, near_list);
     c_eval += r & 1u; c_bad += (r >> 1) & 1u;
   }
   if (eig_any) atomicAdd(&st->n_eigen_fail, 1ull);
   warp_count_to(c_bad, &st->n_bad);
   warp_count_to(c_eval, &st->n_elems_eval);
   warp_count_to(c_err, &st->n_flag_err);
-  if (want_q) {
+  if (P.want_q) {
     const unsigned long long m = warp_min_u64(minkey);
     if ((threadIdx.x & 31) == 0 && m != ~0ull) atomicMin(&st->min_q_key, m);
   }
@@ -971,7 +1005,7 @@ k_chunk_keys(int64_t n, int64_t chunk_len, const int32_t* __restrict__ conn, int
   __shared__ int sh[kThreads / 32];
   const int64_t lo = blockIdx.x * chunk_len, hi = (lo + chunk_len < n) ? lo + chunk_len : n;
   int m = 0x7fffffff;
-  for (int64_t i = lo * NV + threadIdx.x; i < hi * NV; i += kThreads) { int v = conn[i]; m = v < m ? v : m; }
+  for (int64_t i = lo * NV + threadIdx.x; i < hi * NV; i += kThreads) { int v = conn[i] & kVidMask; m = v < m ? v : m; }
   m = __reduce_min_sync(0xffffffffu, m);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
   __syncthreads();
@@ -999,6 +1033,21 @@ int magk_pack(mag_ctx* c)
   }
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;
+  return MAG_OK;
+}
+
+// after the connectivity and owned arrays are uploaded (mag_set_mesh): fold ownership into the tet / edge vertex ids
+int magk_fold_owned(mag_ctx* c)
+{
+  if (c->d_edge_owned && c->ne) {
+    k_fold_owned<<<grid_for(c->ne), kThreads, 0, c->stream>>>(c->ne, 2, c->d_edge_owned, c->d_edge_v);
+    c->n_launches++;
+  }
+  if (c->d_elem_owned && c->nt) {
+    k_fold_owned<<<grid_for(c->nt), kThreads, 0, c->stream>>>(c->nt, 4, c->d_elem_owned + (c->np + c->npy), c->d_tet_v);
+    c->n_launches++;
+  }
+  MAG_CUDA(c, cudaGetLastError());
   return MAG_OK;
 }
 
@@ -1066,14 +1115,14 @@ static EdgeParams edge_params(const SweepParams& P)
   return E;
 }
 
-template <int KIND, bool FAST, bool OWNED>
+template <int KIND, bool FAST>
 static int launch_edges_t(mag_ctx* c, const SweepParams& P)
 {
   static int per_sm = 0;
-  const unsigned g = persistent_grid(c, per_sm, (const void*)k_edges<KIND, FAST, OWNED>, c->ne, kEdgeThreads);
-  k_edges<KIND, FAST, OWNED><<<g, kEdgeThreads, 0, c->stream>>>((int32_t)c->ne, reinterpret_cast<const int2*>(c->d_edge_v), c->d_vedge,
-                                                                c->d_edge_owned, c->d_edge_flags, c->d_len, edge_params(P), c->d_stats,
-                                                                c->d_near_edge, c->d_edge_order);
+  const unsigned g = persistent_grid(c, per_sm, (const void*)k_edges<KIND, FAST>, c->ne, kEdgeThreads);
+  k_edges<KIND, FAST><<<g, kEdgeThreads, 0, c->stream>>>((int32_t)c->ne, reinterpret_cast<const int2*>(c->d_edge_v), c->d_vedge,
+                                                         c->d_edge_flags, c->d_len, edge_params(P), c->d_stats,
+                                                         c->d_near_edge, c->d_edge_order);
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;
   return MAG_OK;
@@ -1081,28 +1130,37 @@ static int launch_edges_t(mag_ctx* c, const SweepParams& P)
 template <int KIND>
 static int launch_edges(mag_ctx* c, const SweepParams& P, bool fast)
 {
-  const bool owned = c->d_edge_owned != nullptr;
-  if (fast) return owned ? launch_edges_t<KIND, true, true>(c, P) : launch_edges_t<KIND, true, false>(c, P);
-  return owned ? launch_edges_t<KIND, false, true>(c, P) : launch_edges_t<KIND, false, false>(c, P);
+  return fast ? launch_edges_t<KIND, true>(c, P) : launch_edges_t<KIND, false>(c, P);
 }
 
-template <int KIND>
-static int launch_tets(mag_ctx* c, const SweepParams& P, bool fast)
+static TetParams tet_params(const SweepParams& P)
 {
-  const int4* tv = reinterpret_cast<const int4*>(c->d_tet_v);
-  const int64_t off = c->np + c->npy;
-  if (fast) {
-    static int per_sm = 0;
-    const unsigned g = persistent_grid(c, per_sm, (const void*)k_tets<KIND, true>, c->nt, kTetThreads);
-    k_tets<KIND, true><<<g, kTetThreads, 0, c->stream>>>(c->nt, off, c->nv, tv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_owned, c->d_elem_flags, c->d_qual, P, c->d_stats, c->d_near_elem, c->d_tet_order);
-  } else {
-    static int per_sm = 0;
-    const unsigned g = persistent_grid(c, per_sm, (const void*)k_tets<KIND, false>, c->nt, kTetThreads);
-    k_tets<KIND, false><<<g, kTetThreads, 0, c->stream>>>(c->nt, off, c->nv, tv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_owned, c->d_elem_flags, c->d_qual, P, c->d_stats, c->d_near_elem, c->d_tet_order);
-  }
+  TetParams T;
+  T.ops = P.ops;
+  T.do_bad = (P.ops & MAG_OP_MARK_BAD) ? 1 : 0;
+  T.want_q = (P.ops & MAG_OP_QUALITIES) ? 1 : 0;
+  T.use_max = P.use_max;
+  T.good_q = P.good_q;
+  T.tol_q = std::isfinite(P.good_q) ? MAG_NEAR_REL * std::fabs(P.good_q) : -1.0;
+  return T;
+}
+
+template <int KIND, bool FAST>
+static int launch_tets_t(mag_ctx* c, const SweepParams& P)
+{
+  static int per_sm = 0;
+  const unsigned g = persistent_grid(c, per_sm, (const void*)k_tets<KIND, FAST>, c->nt, kTetThreads);
+  k_tets<KIND, FAST><<<g, kTetThreads, 0, c->stream>>>((int32_t)c->nt, (int32_t)(c->np + c->npy), c->nv, reinterpret_cast<const int4*>(c->d_tet_v),
+                                                        c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_flags, c->d_qual, tet_params(P),
+                                                        c->d_stats, c->d_near_elem, c->d_tet_order);
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;
   return MAG_OK;
+}
+template <int KIND>
+static int launch_tets(mag_ctx* c, const SweepParams& P, bool fast)
+{
+  return fast ? launch_tets_t<KIND, true>(c, P) : launch_tets_t<KIND, false>(c, P);
 }
 
 #include <algorithm>
