@@ -325,37 +325,46 @@ __device__ __forceinline__ unsigned long long near_reserve(unsigned long long* c
   return __shfl_sync(0xffffffffu, base, 0);
 }
 
-// Work distribution of the persistent kernels: chunks of kChunkTiles consecutive tiles handed out through an atomic
-// counter.  Consecutive tiles on one SM keep the vertex records they share (the next grid row of a box mesh, the
-// neighbouring elements of any reasonably numbered mesh) in that SM's L1; dynamic hand-out evens out chunks made
-// expensive by near-threshold re-evaluations or cheap by skip flags.
-#ifndef MAG_FAST_BLOCKS
-#define MAG_FAST_BLOCKS 2
-#endif
-#ifndef MAG_CHUNK_TILES
-#define MAG_CHUNK_TILES 32
-#endif
-constexpr int kChunkTiles = MAG_CHUNK_TILES;
+// Work distribution of the persistent kernels: chunks of consecutive entities (kEdgeChunk / kTetChunk, a whole number
+// of tiles for every block size used) handed out through an atomic counter.  Consecutive tiles on one SM keep the vertex
+// records they share (the next grid row of a box mesh, the neighbouring elements of any reasonably numbered mesh) in
+// that SM's L1; dynamic hand-out evens out chunks made expensive by near-threshold re-evaluations or cheap by skip flags.
+//
+// Occupancy (measured on B200, n = 203 lattice, scripts/run_variants.sh): both kernels are latency-bound, so resident
+// warps matter more than registers per thread.  The fast edge kernel fits 80 registers without spilling: 3 x 256 threads
+// per SM (24 warps) runs 1.49 -> 1.33 ms against 2 x 256 at 120 registers; 2 x 320 (96 registers) 1.40; 4 x 256 (64
+// registers, spills) 1.64.  The fast tet kernel fits 96 registers: 2 x 320 threads 0.90 -> 0.79 ms; 3 x 256 (80
+// registers, spills) 0.90; without the {z,det} prefetch 0.86 at 3 x 256.  Strict kernels keep 2 x 256.
 #ifndef MAG_EDGE_THREADS
 #define MAG_EDGE_THREADS 256
 #endif
 #ifndef MAG_EDGE_BLOCKS
-#define MAG_EDGE_BLOCKS 2
+#define MAG_EDGE_BLOCKS 3
 #endif
 #ifndef MAG_TET_THREADS
-#define MAG_TET_THREADS 256
+#define MAG_TET_THREADS 320
 #endif
 #ifndef MAG_TET_BLOCKS
 #define MAG_TET_BLOCKS 2
 #endif
-#ifndef MAG_TET_BLOCKS_STRICT
-#define MAG_TET_BLOCKS_STRICT 2
+#ifndef MAG_TET_PIPE
+#define MAG_TET_PIPE 1   /* 1: {z,det} chunks of the next tile are prefetched; 0: everything is loaded at the tile */
 #endif
-constexpr int kTetThreads = MAG_TET_THREADS;
-#ifndef MAG_EDGE_BLOCKS_STRICT
-#define MAG_EDGE_BLOCKS_STRICT 2
+constexpr int kStrictThreads = 256, kStrictBlocks = 2;
+#ifndef MAG_EDGE_CHUNK
+#define MAG_EDGE_CHUNK 8192   /* 32 tiles of 256 */
 #endif
-constexpr int kEdgeThreads = MAG_EDGE_THREADS;
+#ifndef MAG_TET_CHUNK
+#define MAG_TET_CHUNK 7680    /* 24 tiles of 320 = 30 tiles of 256 */
+#endif
+constexpr int kEdgeChunk = MAG_EDGE_CHUNK;
+constexpr int kTetChunk = MAG_TET_CHUNK;
+// (the log-Euclidean edge kernel carries the eigen-solver and keeps 2 x 256 at 128 registers)
+template <int KIND, bool FAST> struct EdgeCfg {
+  static constexpr int T = FAST ? MAG_EDGE_THREADS : kStrictThreads;
+  static constexpr int B = (FAST && KIND != MAG_KIND_LOGM) ? MAG_EDGE_BLOCKS : kStrictBlocks;
+};
+template <bool FAST> struct TetCfg { static constexpr int T = FAST ? MAG_TET_THREADS : kStrictThreads, B = FAST ? MAG_TET_BLOCKS : kStrictBlocks; };
 __device__ __forceinline__ long long next_chunk(unsigned long long* counter, long long* slot)
 {
   __syncthreads();                       // everyone is done with the previous value of *slot
@@ -417,7 +426,7 @@ __device__ __noinline__ unsigned drain_edges(NearQueue& q, int first, int n, con
 // vertex records are gathered only when the flag word says the edge has to be evaluated at all (skipped edges cost 12
 // bytes).  Everything is indexed with int32 (mag_set_mesh rejects meshes with 2^31 or more entities of one dimension).
 template <int KIND, bool FAST>
-__global__ void __launch_bounds__(kEdgeThreads, FAST ? MAG_EDGE_BLOCKS : MAG_EDGE_BLOCKS_STRICT)
+__global__ void __launch_bounds__(EdgeCfg<KIND, FAST>::T, EdgeCfg<KIND, FAST>::B)
 k_edges(int32_t ne, const int2* __restrict__ edge_v, const double* __restrict__ vedge,
         int32_t* __restrict__ flags, double* __restrict__ lengths,
         EdgeParams P, MagDevStats* st, int32_t* __restrict__ near_list, const int32_t* __restrict__ chunk_order)
@@ -427,7 +436,7 @@ k_edges(int32_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
   unsigned c_split = 0, c_coll = 0, c_eval = 0, c_err = 0;
   double maxlen = 0.0;                  // getMaximumEdgeLength starts at 0 and ignores NaN (maSize.cc:673-691)
   int qn = 0, eig_any = 0;
-  constexpr int kChunkEdges = kChunkTiles * kEdgeThreads;
+  constexpr int kEdgeThreads = EdgeCfg<KIND, FAST>::T, kChunkEdges = kEdgeChunk;
   const int nchunks = (ne + kChunkEdges - 1) / kChunkEdges;
   for (;;) {
     const long long ticket = next_chunk(&st->edge_chunk, &chunk_slot);
@@ -661,8 +670,8 @@ __device__ __noinline__ unsigned drain_tets(NearQueue& q, int first, int n, int3
 // and tile k: flag word + vertices two tiles ahead; the four {z, det Q_v} chunks one tile ahead, so that the choice of
 // the max-Jacobian vertex (getMetricWithMaxJacobean, maQuality.cc:83-108) does not sit between two dependent gathers and
 // no chunk is fetched twice: at the tile itself only the four {x,y} chunks and the winner's transform are loaded.
-template <int KIND, bool FAST>
-__global__ void __launch_bounds__(kTetThreads, FAST ? MAG_TET_BLOCKS : MAG_TET_BLOCKS_STRICT)
+template <int KIND, bool FAST, bool USE_MAX>
+__global__ void __launch_bounds__(TetCfg<FAST>::T, TetCfg<FAST>::B)
 k_tets(int32_t nt, int32_t elem_off, int64_t nv, const int4* __restrict__ tet_v, const double* __restrict__ vpos,
        const double* __restrict__ vq, const double* __restrict__ vedge,
        int32_t* __restrict__ flags, double* __restrict__ qual, TetParams P, MagDevStats* st,
@@ -673,7 +682,7 @@ k_tets(int32_t nt, int32_t elem_off, int64_t nv, const int4* __restrict__ tet_v,
   unsigned c_bad = 0, c_eval = 0, c_err = 0;
   unsigned long long minkey = ~0ull;
   int qn = 0, eig_any = 0;
-  constexpr int kChunkTets = kChunkTiles * kTetThreads;
+  constexpr int kTetThreads = TetCfg<FAST>::T, kChunkTets = kTetChunk;
   const int nchunks = (nt + kChunkTets - 1) / kChunkTets;
   flags += elem_off;
   qual += elem_off;
@@ -696,7 +705,7 @@ k_tets(int32_t nt, int32_t elem_off, int64_t nv, const int4* __restrict__ tet_v,
     if (t < t_end) {
       f_cur = flags[t];
       tv_cur = __ldg(tet_v + t);
-      if (P.want_q || (P.do_bad && !(f_cur & MAG_OK_QUALITY))) load_zd(tv_cur, zd);
+      if (MAG_TET_PIPE && (P.want_q || (P.do_bad && !(f_cur & MAG_OK_QUALITY)))) load_zd(tv_cur, zd);
     }
     if (t + kTetThreads < t_end) { f_nx = flags[t + kTetThreads]; tv_nx = __ldg(tet_v + t + kTetThreads); }
     for (int tile = 0; tile < tiles; ++tile, t += kTetThreads) {
@@ -704,11 +713,12 @@ k_tets(int32_t nt, int32_t elem_off, int64_t nv, const int4* __restrict__ tet_v,
       int4 tv = tv_cur;
       const bool owned = tv.x >= 0;
       tv.x &= kVidMask;
+      if (!MAG_TET_PIPE && (P.want_q || (P.do_bad && !(f_in & MAG_OK_QUALITY)))) load_zd(tv, zd);
       const double2 z0 = zd[0], z1 = zd[1], z2 = zd[2], z3 = zd[3];
       // next tile: its {z,det} chunks; tile after: flag word + vertices
       f_cur = f_nx;
       tv_cur = tv_nx;
-      if (t + kTetThreads < t_end && (P.want_q || (P.do_bad && !(f_cur & MAG_OK_QUALITY)))) load_zd(tv_cur, zd);
+      if (MAG_TET_PIPE && t + kTetThreads < t_end && (P.want_q || (P.do_bad && !(f_cur & MAG_OK_QUALITY)))) load_zd(tv_cur, zd);
       if (t + 2 * kTetThreads < t_end) { f_nx = flags[t + 2 * kTetThreads]; tv_nx = __ldg(tet_v + t + 2 * kTetThreads); }
       bool nr = false;
       if (t < t_end) {
@@ -718,10 +728,10 @@ k_tets(int32_t nt, int32_t elem_off, int64_t nv, const int4* __restrict__ tet_v,
         if (P.want_q || need_bad) {
           M3 Q;
           double detQ = 0.0;
-          if (P.use_max) load_q(vq, best_vertex(tv, z0.y, z1.y, z2.y, z3.y), Q, detQ);
+          if (USE_MAX) load_q(vq, best_vertex(tv, z0.y, z1.y, z2.y, z3.y), Q, detQ);
           const double2 a0 = __ldg(chunk_ptr<2>(vpos, 0, tv.x)), a1 = __ldg(chunk_ptr<2>(vpos, 0, tv.y)),
                         a2 = __ldg(chunk_ptr<2>(vpos, 0, tv.z)), a3 = __ldg(chunk_ptr<2>(vpos, 0, tv.w));
-          if (!P.use_max) {
+          if (!USE_MAX) {   // centroid metric (maQuality.cc:148-153): a separate instantiation keeps its registers out of the default path
             centroid_transform<KIND>(vedge, nv, tv, Q, &eig_any);
             detQ = FAST ? magst::det3(Q) : 0.0;
           }
@@ -1089,14 +1099,14 @@ static int launch_tris(mag_ctx* c, const SweepParams& P, bool fast)
 }
 
 // persistent grids: resident blocks per SM x number of SMs (queried once per context)
-static unsigned persistent_grid(mag_ctx* c, int& per_sm, const void* kernel, int64_t n, int threads = kThreads)
+static unsigned persistent_grid(mag_ctx* c, int& per_sm, const void* kernel, int64_t n, int threads, int chunk)
 {
   if (per_sm < 1 &&
       (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1))
     per_sm = 1;
   int64_t g = (int64_t)per_sm * c->n_sms;
-  const int64_t tiles = (n + (int64_t)threads * kChunkTiles - 1) / ((int64_t)threads * kChunkTiles);
-  if (g > tiles) g = tiles;
+  const int64_t chunks = (n + chunk - 1) / chunk;
+  if (g > chunks) g = chunks;
   return (unsigned)(g < 1 ? 1 : g);
 }
 
@@ -1119,7 +1129,8 @@ template <int KIND, bool FAST>
 static int launch_edges_t(mag_ctx* c, const SweepParams& P)
 {
   static int per_sm = 0;
-  const unsigned g = persistent_grid(c, per_sm, (const void*)k_edges<KIND, FAST>, c->ne, kEdgeThreads);
+  constexpr int kEdgeThreads = EdgeCfg<KIND, FAST>::T;
+  const unsigned g = persistent_grid(c, per_sm, (const void*)k_edges<KIND, FAST>, c->ne, kEdgeThreads, kEdgeChunk);
   k_edges<KIND, FAST><<<g, kEdgeThreads, 0, c->stream>>>((int32_t)c->ne, reinterpret_cast<const int2*>(c->d_edge_v), c->d_vedge,
                                                          c->d_edge_flags, c->d_len, edge_params(P), c->d_stats,
                                                          c->d_near_edge, c->d_edge_order);
@@ -1145,12 +1156,13 @@ static TetParams tet_params(const SweepParams& P)
   return T;
 }
 
-template <int KIND, bool FAST>
+template <int KIND, bool FAST, bool USE_MAX>
 static int launch_tets_t(mag_ctx* c, const SweepParams& P)
 {
   static int per_sm = 0;
-  const unsigned g = persistent_grid(c, per_sm, (const void*)k_tets<KIND, FAST>, c->nt, kTetThreads);
-  k_tets<KIND, FAST><<<g, kTetThreads, 0, c->stream>>>((int32_t)c->nt, (int32_t)(c->np + c->npy), c->nv, reinterpret_cast<const int4*>(c->d_tet_v),
+  constexpr int kTetThreads = TetCfg<FAST>::T;
+  const unsigned g = persistent_grid(c, per_sm, (const void*)k_tets<KIND, FAST, USE_MAX>, c->nt, kTetThreads, kTetChunk);
+  k_tets<KIND, FAST, USE_MAX><<<g, kTetThreads, 0, c->stream>>>((int32_t)c->nt, (int32_t)(c->np + c->npy), c->nv, reinterpret_cast<const int4*>(c->d_tet_v),
                                                         c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_flags, c->d_qual, tet_params(P),
                                                         c->d_stats, c->d_near_elem, c->d_tet_order);
   MAG_CUDA(c, cudaGetLastError());
@@ -1160,7 +1172,8 @@ static int launch_tets_t(mag_ctx* c, const SweepParams& P)
 template <int KIND>
 static int launch_tets(mag_ctx* c, const SweepParams& P, bool fast)
 {
-  return fast ? launch_tets_t<KIND, true>(c, P) : launch_tets_t<KIND, false>(c, P);
+  if (P.use_max) return fast ? launch_tets_t<KIND, true, true>(c, P) : launch_tets_t<KIND, false, true>(c, P);
+  return fast ? launch_tets_t<KIND, true, false>(c, P) : launch_tets_t<KIND, false, false>(c, P);
 }
 
 #include <algorithm>
@@ -1192,8 +1205,8 @@ int magk_build_schedule(mag_ctx* c)
 {
   int rc;
   int64_t nch;
-  if ((rc = build_order(c, c->ne, (int64_t)kChunkTiles * kEdgeThreads, c->d_edge_v, 2, c->d_edge_order, nch))) return rc;
-  if ((rc = build_order(c, c->nt, (int64_t)kChunkTiles * kTetThreads, c->d_tet_v, 4, c->d_tet_order, nch))) return rc;
+  if ((rc = build_order(c, c->ne, (int64_t)kEdgeChunk, c->d_edge_v, 2, c->d_edge_order, nch))) return rc;
+  if ((rc = build_order(c, c->nt, (int64_t)kTetChunk, c->d_tet_v, 4, c->d_tet_order, nch))) return rc;
   return MAG_OK;
 }
 
