@@ -14,7 +14,7 @@ SYMBOLS = [
     "mag_create", "mag_destroy", "mag_last_error", "mag_set_stream", "mag_synchronize",
     "mag_set_mesh", "mag_set_mesh_2d", "mag_set_coords",
     "mag_set_metric_identity", "mag_set_metric_iso", "mag_set_metric_aniso", "mag_set_metric_logm",
-    "mag_set_flags", "mag_sweep",
+    "mag_set_flags", "mag_sweep", "mag_sweep_host",
     "mag_get_edge_lengths", "mag_get_qualities", "mag_get_flags", "mag_get_layer_ok", "mag_get_stats",
     "mag_get_near_threshold", "mag_set_metric_logm_from_frames",
     "mag_timing_begin", "mag_timing_read", "mag_launch_count",
@@ -32,6 +32,19 @@ class MagStats(C.Structure):
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class MagHostPart(C.Structure):
+    """mag_host_part of include/mag.h"""
+    _fields_ = [("nv", C.c_int64), ("xyz", C.c_void_p), ("ne", C.c_int64), ("edge_v", C.c_void_p),
+                ("nt", C.c_int64), ("tet_v", C.c_void_p), ("edge_owned", C.c_void_p), ("elem_owned", C.c_void_p),
+                ("kind", C.c_int), ("field_a", C.c_void_p), ("field_b", C.c_void_p),
+                ("edge_flags", C.c_void_p), ("elem_flags", C.c_void_p), ("slice_entities", C.c_int64)]
+
+
+class MagHostResult(C.Structure):
+    _fields_ = [("edge_lengths", C.c_void_p), ("qualities", C.c_void_p), ("edge_flags", C.c_void_p),
+                ("elem_flags", C.c_void_p)]
 
 
 _lib = None
@@ -63,6 +76,8 @@ def lib():
     L.mag_set_metric_logm.argtypes = [vp, vp]
     L.mag_set_flags.argtypes = [vp, vp, vp]
     L.mag_sweep.argtypes = [vp, u32, f64, f64, f64, C.c_int, C.c_int]
+    L.mag_sweep_host.argtypes = [vp, C.POINTER(MagHostPart), C.POINTER(MagHostResult), u32, f64, f64, f64, C.c_int, C.c_int,
+                                 C.POINTER(MagStats)]
     L.mag_get_edge_lengths.argtypes = [vp, vp]
     L.mag_get_qualities.argtypes = [vp, vp]
     L.mag_get_flags.argtypes = [vp, vp, vp]

@@ -132,7 +132,7 @@ int mag_create(mag_ctx** out, int device)
   c->nv = c->ne = c->nt = c->np = c->npy = c->ntri = 0;
   c->dim = 3;
   c->kind = MAG_KIND_NONE;
-  c->vertex_pass_valid = false;
+  c->vertex_pass_valid = false; c->schedule_valid = false; c->s_up = c->s_down = nullptr;
   c->d_xyz = c->d_ma = c->d_mb = c->d_vedge = c->d_vpos = c->d_vq = nullptr;
   c->d_edge_v = c->d_tet_v = c->d_prism_v = c->d_pyr_v = c->d_tri_v = nullptr;
   c->d_edge_owned = c->d_elem_owned = nullptr;
@@ -178,6 +178,9 @@ void mag_destroy(mag_ctx* c)
   cudaFree(c->d_stats); cudaFreeHost(c->h_stats); cudaFree(c->d_block_sums);
   cudaFree(c->d_near_edge); cudaFree(c->d_near_elem); cudaFree(c->d_edge_order); cudaFree(c->d_tet_order);
   for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->pipe_ev) cudaEventDestroy(e);
+  if (c->s_up) cudaStreamDestroy(c->s_up);
+  if (c->s_down) cudaStreamDestroy(c->s_down);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -197,44 +200,61 @@ int mag_synchronize(mag_ctx* c)
   return MAG_OK;
 }
 
+// validates the shape of a part and (re)allocates every per-entity device array for it; no data is moved
+int magi_reshape(mag_ctx* c, int dim, int64_t nv, int64_t ne, int64_t nt, int64_t np, int64_t npy, int64_t ntri,
+                 bool has_edge_owned, bool has_elem_owned)
+{
+  if (nv < 0 || ne < 0 || nt < 0 || np < 0 || npy < 0 || ntri < 0) return mag_fail(c, MAG_ERR_ARG, "mag_set_mesh: negative count");
+  if (nv > MAG_MAX_ENTITIES || ne > MAG_MAX_ENTITIES || np + npy + nt + ntri > MAG_MAX_ENTITIES)
+    return mag_fail(c, MAG_ERR_ARG, "mag_set_mesh: entity ids are int32 (MDS_ID_TYPE=int, mds/CMakeLists.txt:7)");
+  int rc;
+  const int64_t nel = np + npy + nt + ntri;
+  if (dim != c->dim) c->vertex_pass_valid = false;
+  c->dim = dim;
+  c->schedule_valid = false;
+  const bool same_shape = nv == c->nv && ne == c->ne && nt == c->nt && np == c->np && npy == c->npy && ntri == c->ntri &&
+                          has_edge_owned == (c->d_edge_owned != nullptr) && has_elem_owned == (c->d_elem_owned != nullptr);
+  if (same_shape) return MAG_OK;
+  if (nv != c->nv) { // size field arrays are per vertex: drop them
+    c->kind = MAG_KIND_NONE;
+    if ((rc = dev_free(c, c->d_ma)) || (rc = dev_free(c, c->d_mb)) || (rc = dev_free(c, c->d_vedge))) return rc;
+    c->cap_ma = c->cap_mb = c->cap_vedge = 0;
+  }
+  if ((rc = dev_alloc(c, c->d_xyz, (size_t)nv * 3)) || (rc = dev_alloc(c, c->d_vpos, (size_t)vpad(nv) * 4)) ||
+      (rc = dev_alloc(c, c->d_vq, (size_t)vpad(nv) * 10)) || (rc = dev_alloc(c, c->d_edge_v, (size_t)ne * 2)) ||
+      (rc = dev_alloc(c, c->d_tet_v, (size_t)nt * 4)) || (rc = dev_alloc(c, c->d_prism_v, (size_t)np * 6)) ||
+      (rc = dev_alloc(c, c->d_pyr_v, (size_t)npy * 5)) || (rc = dev_alloc(c, c->d_tri_v, (size_t)ntri * 3)) ||
+      (rc = dev_alloc(c, c->d_edge_owned, has_edge_owned ? (size_t)ne : 0)) ||
+      (rc = dev_alloc(c, c->d_elem_owned, has_elem_owned ? (size_t)nel : 0)) ||
+      (rc = dev_alloc(c, c->d_edge_flags, (size_t)ne)) || (rc = dev_alloc(c, c->d_elem_flags, (size_t)nel)) ||
+      (rc = dev_alloc(c, c->d_len, (size_t)ne)) || (rc = dev_alloc(c, c->d_qual, (size_t)nel)) ||
+      (rc = dev_alloc(c, c->d_layer_ok, (size_t)(np + npy))) || (rc = dev_alloc(c, c->d_layer_codes, (size_t)(np + npy))) ||
+      (rc = dev_alloc(c, c->d_near_edge, (size_t)ne)) || (rc = dev_alloc(c, c->d_near_elem, (size_t)nel)))
+    return rc;
+  c->nv = nv; c->ne = ne; c->nt = nt; c->np = np; c->npy = npy; c->ntri = ntri;
+  if (nel) MAG_CUDA(c, cudaMemsetAsync(c->d_qual, 0, (size_t)nel * 8, c->stream));
+  return MAG_OK;
+}
+
+// grows the raw size-field arrays and the packed gather records for `kind`
+int magi_reserve_metric(mag_ctx* c, int kind, size_t na, size_t nb)
+{
+  int rc;
+  if ((rc = dev_reserve(c, c->d_ma, c->cap_ma, na)) || (rc = dev_reserve(c, c->d_mb, c->cap_mb, nb))) return rc;
+  return dev_reserve(c, c->d_vedge, c->cap_vedge, (size_t)vpad(c->nv) * rec_doubles(kind));
+}
+
 static int set_mesh_impl(mag_ctx* c, int dim, int64_t nv, const double* xyz, int64_t ne, const int32_t* edge_v,
                          int64_t nt, const int32_t* tet_v, int64_t np, const int32_t* prism_v,
                          int64_t npy, const int32_t* pyr_v, int64_t ntri, const int32_t* tri_v,
                          const uint8_t* edge_owned, const uint8_t* elem_owned)
 {
   CHECK_CTX(c);
-  if (nv < 0 || ne < 0 || nt < 0 || np < 0 || npy < 0 || ntri < 0) return mag_fail(c, MAG_ERR_ARG, "mag_set_mesh: negative count");
-  if (nv > MAG_MAX_ENTITIES || ne > MAG_MAX_ENTITIES || np + npy + nt + ntri > MAG_MAX_ENTITIES)
-    return mag_fail(c, MAG_ERR_ARG, "mag_set_mesh: entity ids are int32 (MDS_ID_TYPE=int, mds/CMakeLists.txt:7)");
-  if ((nv && !xyz) || (ne && !edge_v) || (nt && !tet_v) || (np && !prism_v) || (npy && !pyr_v) || (ntri && !tri_v))
+  if ((nv > 0 && !xyz) || (ne > 0 && !edge_v) || (nt > 0 && !tet_v) || (np > 0 && !prism_v) || (npy > 0 && !pyr_v) || (ntri > 0 && !tri_v))
     return mag_fail(c, MAG_ERR_ARG, "mag_set_mesh: null array with non-zero count");
   int rc;
+  if ((rc = magi_reshape(c, dim, nv, ne, nt, np, npy, ntri, edge_owned != nullptr, elem_owned != nullptr))) return rc;
   const int64_t nel = np + npy + nt + ntri;
-  if (dim != c->dim) c->vertex_pass_valid = false;
-  c->dim = dim;
-  const bool same_shape = nv == c->nv && ne == c->ne && nt == c->nt && np == c->np && npy == c->npy && ntri == c->ntri &&
-                          (edge_owned != nullptr) == (c->d_edge_owned != nullptr) &&
-                          (elem_owned != nullptr) == (c->d_elem_owned != nullptr);
-  if (!same_shape) {
-    if (nv != c->nv) { // size field arrays are per vertex: drop them
-      c->kind = MAG_KIND_NONE;
-      if ((rc = dev_free(c, c->d_ma)) || (rc = dev_free(c, c->d_mb)) || (rc = dev_free(c, c->d_vedge))) return rc;
-      c->cap_ma = c->cap_mb = c->cap_vedge = 0;
-    }
-    if ((rc = dev_alloc(c, c->d_xyz, (size_t)nv * 3)) || (rc = dev_alloc(c, c->d_vpos, (size_t)vpad(nv) * 4)) ||
-        (rc = dev_alloc(c, c->d_vq, (size_t)vpad(nv) * 10)) || (rc = dev_alloc(c, c->d_edge_v, (size_t)ne * 2)) ||
-        (rc = dev_alloc(c, c->d_tet_v, (size_t)nt * 4)) || (rc = dev_alloc(c, c->d_prism_v, (size_t)np * 6)) ||
-        (rc = dev_alloc(c, c->d_pyr_v, (size_t)npy * 5)) || (rc = dev_alloc(c, c->d_tri_v, (size_t)ntri * 3)) ||
-        (rc = dev_alloc(c, c->d_edge_owned, edge_owned ? (size_t)ne : 0)) ||
-        (rc = dev_alloc(c, c->d_elem_owned, elem_owned ? (size_t)nel : 0)) ||
-        (rc = dev_alloc(c, c->d_edge_flags, (size_t)ne)) || (rc = dev_alloc(c, c->d_elem_flags, (size_t)nel)) ||
-        (rc = dev_alloc(c, c->d_len, (size_t)ne)) || (rc = dev_alloc(c, c->d_qual, (size_t)nel)) ||
-        (rc = dev_alloc(c, c->d_layer_ok, (size_t)(np + npy))) || (rc = dev_alloc(c, c->d_layer_codes, (size_t)(np + npy))) ||
-        (rc = dev_alloc(c, c->d_near_edge, (size_t)ne)) || (rc = dev_alloc(c, c->d_near_elem, (size_t)nel)))
-      return rc;
-    c->nv = nv; c->ne = ne; c->nt = nt; c->np = np; c->npy = npy; c->ntri = ntri;
-    if (nel) MAG_CUDA(c, cudaMemsetAsync(c->d_qual, 0, (size_t)nel * 8, c->stream));
-  }
   // a new mesh starts with no flags (ma::getFlags returns 0 when the tag is absent, maAdapt.cc:80-88)
   if (ne) MAG_CUDA(c, cudaMemsetAsync(c->d_edge_flags, 0, (size_t)ne * 4, c->stream));
   if (nel) MAG_CUDA(c, cudaMemsetAsync(c->d_elem_flags, 0, (size_t)nel * 4, c->stream));
@@ -245,6 +265,7 @@ static int set_mesh_impl(mag_ctx* c, int dim, int64_t nv, const double* xyz, int
   if (edge_owned && (rc = upload(c, c->d_edge_owned, edge_owned, (size_t)ne))) return rc;
   if (elem_owned && (rc = upload(c, c->d_elem_owned, elem_owned, (size_t)nel))) return rc;
   if ((rc = magk_fold_owned(c)) || (rc = magk_build_schedule(c))) return rc;
+  c->schedule_valid = true;
   return repack(c);
 }
 
@@ -312,6 +333,10 @@ int mag_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double g
   if (ops & ~(uint32_t)(MAG_OP_ALL | MAG_OP_LENGTH_SUM)) return mag_fail(c, MAG_ERR_ARG, "mag_sweep: unknown op bits 0x%x", ops);
   if ((ops & MAG_OP_LENGTH_SUM) && !(ops & MAG_OP_LENGTHS)) return mag_fail(c, MAG_ERR_ARG, "mag_sweep: MAG_OP_LENGTH_SUM needs MAG_OP_LENGTHS");
   int rc;
+  if (!c->schedule_valid) {   // the mesh came through mag_sweep_host, which defers the chunk schedule
+    if ((rc = magk_build_schedule(c))) return rc;
+    c->schedule_valid = true;
+  }
   if ((rc = magk_init_stats(c))) return rc;
   c->last_ops = ops;
   c->last_fp_mode = fp_mode;

@@ -1,0 +1,148 @@
+// mag_host.cu -- mag_sweep_host: export + sweep + results of one part in ONE call, streamed.
+//
+// What the drop-in adapter does once per MeshAdapt iteration -- export the (changed) mesh, the size field and the flag
+// words, sweep, read lengths / qualities / flags back -- is bound by the host link, not by the kernels (n = 203 part:
+// 2.7 GB up, 1.3 GB down at ~55 GB/s against 2.5 ms of kernels).  Done as separate calls the downloads can only start
+// after the last upload.  This entry point cuts the edges and the tets into slices and runs three streams:
+//     upload stream     vertex data | edge slice 0 | edge slice 1 | ... | tet slice 0 | tet slice 1 | ...
+//     compute stream                  pack, vertex pass | k_edges(slice 0) | ...        | k_tets(slice 0) | ...
+//     download stream                                     | lengths+flags(slice 0) | ...   | qualities+flags(slice 0) | ...
+// so the device->host traffic rides under the host->device traffic (PCIe is full duplex) and the call costs about the
+// upload time alone.  Results are bit-identical to mag_set_mesh + mag_set_metric_* + mag_set_flags + mag_sweep + getters
+// (the slices only change the order in which entities are visited); the part stays resident afterwards.
+#include "mag_internal.h"
+#include <algorithm>
+
+int magk_pack(mag_ctx* c);
+int magk_init_stats(mag_ctx* c);
+int magk_vertex_pass(mag_ctx* c);
+int magk_edges_range(mag_ctx* c, uint32_t ops, double max_len, double min_len, int fp_mode, int64_t first, int64_t n);
+int magk_tets_range(mag_ctx* c, uint32_t ops, double good_q, int use_max, int fp_mode, int64_t first, int64_t n);
+int magk_length_sum(mag_ctx* c);
+
+namespace {
+
+// event pool: events are reused across calls (cudaEventDisableTiming: ordering only)
+struct Events {
+  mag_ctx* c;
+  size_t next = 0;
+  int get(cudaEvent_t* e)
+  {
+    if (next == c->pipe_ev.size()) {
+      cudaEvent_t ev;
+      MAG_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      c->pipe_ev.push_back(ev);
+    }
+    *e = c->pipe_ev[next++];
+    return MAG_OK;
+  }
+};
+
+// `later` waits for everything enqueued on `earlier` so far
+int chain(mag_ctx* c, Events& ev, cudaStream_t earlier, cudaStream_t later)
+{
+  cudaEvent_t e;
+  int rc = ev.get(&e);
+  if (rc) return rc;
+  MAG_CUDA(c, cudaEventRecord(e, earlier));
+  MAG_CUDA(c, cudaStreamWaitEvent(later, e, 0));
+  return MAG_OK;
+}
+
+template <class T>
+int copy_async(mag_ctx* c, T* dst, const T* src, size_t count, cudaMemcpyKind kind, cudaStream_t s)
+{
+  if (count) MAG_CUDA(c, cudaMemcpyAsync(dst, src, count * sizeof(T), kind, s));
+  return MAG_OK;
+}
+
+} // namespace
+
+extern "C" int mag_sweep_host(mag_ctx* c, const mag_host_part* in, const mag_host_result* out, uint32_t ops, double max_len,
+                              double min_len, double good_quality, int use_max_metric, int fp_mode, mag_stats* stats)
+{
+  if (!c) return MAG_ERR_ARG;
+  MAG_CUDA(c, cudaSetDevice(c->device));
+  if (!in || !out) return mag_fail(c, MAG_ERR_ARG, "mag_sweep_host: null argument");
+  if (fp_mode != MAG_FP_STRICT && fp_mode != MAG_FP_FAST) return mag_fail(c, MAG_ERR_ARG, "mag_sweep_host: bad fp_mode %d", fp_mode);
+  if (ops & ~(uint32_t)((MAG_OP_ALL & ~MAG_OP_LAYER_CHECK) | MAG_OP_LENGTH_SUM))
+    return mag_fail(c, MAG_ERR_ARG, "mag_sweep_host: op bits 0x%x not supported here (tet parts; use the resident API for layer checks)", ops);
+  if ((ops & MAG_OP_LENGTH_SUM) && !(ops & MAG_OP_LENGTHS)) return mag_fail(c, MAG_ERR_ARG, "mag_sweep_host: MAG_OP_LENGTH_SUM needs MAG_OP_LENGTHS");
+  const int64_t nv = in->nv, ne = in->ne, nt = in->nt;
+  if ((nv > 0 && !in->xyz) || (ne > 0 && !in->edge_v) || (nt > 0 && !in->tet_v))
+    return mag_fail(c, MAG_ERR_ARG, "mag_sweep_host: null array with non-zero count");
+  size_t na = 0, nb = 0;
+  switch (in->kind) {
+    case MAG_KIND_IDENTITY: break;
+    case MAG_KIND_ISO: na = (size_t)nv; break;
+    case MAG_KIND_ANISO: na = (size_t)nv * 3; nb = (size_t)nv * 9; break;
+    case MAG_KIND_LOGM: nb = (size_t)nv * 9; break;
+    default: return mag_fail(c, MAG_ERR_ARG, "mag_sweep_host: bad size-field kind %d", in->kind);
+  }
+  if ((na && !in->field_a) || (nb && !in->field_b)) return mag_fail(c, MAG_ERR_ARG, "mag_sweep_host: null size-field array");
+  int rc;
+  if (!c->s_up) MAG_CUDA(c, cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking));
+  if (!c->s_down) MAG_CUDA(c, cudaStreamCreateWithFlags(&c->s_down, cudaStreamNonBlocking));
+  cudaStream_t s_cmp = c->stream, s_up = c->s_up, s_down = c->s_down;
+  Events ev{c};
+
+  if ((rc = magi_reshape(c, 3, nv, ne, nt, 0, 0, 0, in->edge_owned != nullptr, in->elem_owned != nullptr))) return rc;
+  if ((rc = magi_reserve_metric(c, in->kind, na, nb))) return rc;
+  c->kind = in->kind;
+  c->last_ops = ops;
+  c->last_fp_mode = fp_mode;
+  // the device arrays may still be read by work queued earlier on the compute stream
+  if ((rc = chain(c, ev, s_cmp, s_up))) return rc;
+
+  // ---- vertex data, then pack + per-vertex transforms
+  if ((rc = copy_async(c, c->d_xyz, in->xyz, (size_t)nv * 3, cudaMemcpyHostToDevice, s_up)) ||
+      (rc = copy_async(c, c->d_ma, in->field_a, na, cudaMemcpyHostToDevice, s_up)) ||
+      (rc = copy_async(c, c->d_mb, in->field_b, nb, cudaMemcpyHostToDevice, s_up)))
+    return rc;
+  if ((rc = chain(c, ev, s_up, s_cmp)) || (rc = magk_init_stats(c))) return rc;
+  if (nv && (rc = magk_pack(c))) return rc;
+  if (nv && (ops & (MAG_OP_QUALITIES | MAG_OP_MARK_BAD)) && (rc = magk_vertex_pass(c))) return rc;
+
+  const bool do_edges = ne && (ops & (MAG_OP_LENGTHS | MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE));
+  int64_t slice = in->slice_entities > 0 ? in->slice_entities : (int64_t)4 << 20;
+  slice = std::max<int64_t>(61440, (slice + 61439) / 61440 * 61440); // a whole number of edge chunks (8192) and tet chunks (7680)
+
+  // ---- edges
+  for (int64_t e0 = 0; e0 < ne; e0 += slice) {
+    const int64_t n = std::min(slice, ne - e0);
+    if ((rc = copy_async(c, c->d_edge_v + 2 * e0, in->edge_v + 2 * e0, (size_t)n * 2, cudaMemcpyHostToDevice, s_up))) return rc;
+    if (in->edge_flags && (rc = copy_async(c, c->d_edge_flags + e0, in->edge_flags + e0, (size_t)n, cudaMemcpyHostToDevice, s_up))) return rc;
+    if (in->edge_owned && (rc = copy_async(c, c->d_edge_owned + e0, in->edge_owned + e0, (size_t)n, cudaMemcpyHostToDevice, s_up))) return rc;
+    if ((rc = chain(c, ev, s_up, s_cmp))) return rc;
+    if (!in->edge_flags) MAG_CUDA(c, cudaMemsetAsync(c->d_edge_flags + e0, 0, (size_t)n * 4, s_cmp));
+    if ((rc = magk_edges_range(c, ops, max_len, min_len, fp_mode, e0, n))) return rc;
+    if ((rc = chain(c, ev, s_cmp, s_down))) return rc;
+    if (out->edge_lengths && (ops & MAG_OP_LENGTHS) &&
+        (rc = copy_async(c, out->edge_lengths + e0, c->d_len + e0, (size_t)n, cudaMemcpyDeviceToHost, s_down)))
+      return rc;
+    if (out->edge_flags && (rc = copy_async(c, out->edge_flags + e0, c->d_edge_flags + e0, (size_t)n, cudaMemcpyDeviceToHost, s_down))) return rc;
+  }
+  if (do_edges && (ops & MAG_OP_LENGTH_SUM) && (rc = magk_length_sum(c))) return rc;
+
+  // ---- tets
+  for (int64_t t0 = 0; t0 < nt; t0 += slice) {
+    const int64_t n = std::min(slice, nt - t0);
+    if ((rc = copy_async(c, c->d_tet_v + 4 * t0, in->tet_v + 4 * t0, (size_t)n * 4, cudaMemcpyHostToDevice, s_up))) return rc;
+    if (in->elem_flags && (rc = copy_async(c, c->d_elem_flags + t0, in->elem_flags + t0, (size_t)n, cudaMemcpyHostToDevice, s_up))) return rc;
+    if (in->elem_owned && (rc = copy_async(c, c->d_elem_owned + t0, in->elem_owned + t0, (size_t)n, cudaMemcpyHostToDevice, s_up))) return rc;
+    if ((rc = chain(c, ev, s_up, s_cmp))) return rc;
+    if (!in->elem_flags) MAG_CUDA(c, cudaMemsetAsync(c->d_elem_flags + t0, 0, (size_t)n * 4, s_cmp));
+    if ((rc = magk_tets_range(c, ops, good_quality, use_max_metric, fp_mode, t0, n))) return rc;
+    if ((rc = chain(c, ev, s_cmp, s_down))) return rc;
+    if (out->qualities && (ops & MAG_OP_QUALITIES) &&
+        (rc = copy_async(c, out->qualities + t0, c->d_qual + t0, (size_t)n, cudaMemcpyDeviceToHost, s_down)))
+      return rc;
+    if (out->elem_flags && (rc = copy_async(c, out->elem_flags + t0, c->d_elem_flags + t0, (size_t)n, cudaMemcpyDeviceToHost, s_down))) return rc;
+  }
+
+  // ---- statistics; everything has landed when both streams are idle
+  mag_stats local;
+  rc = mag_get_stats(c, stats ? stats : &local);      // synchronizes the compute stream
+  MAG_CUDA(c, cudaStreamSynchronize(s_down));
+  return rc;
+}

@@ -51,6 +51,7 @@ struct mag_ctx {
   int dim;      // mesh dimension (3, or 2 after mag_set_mesh_2d)
   int kind;
   bool vertex_pass_valid;
+  bool schedule_valid;   // d_edge_order / d_tet_order match the resident connectivity
 
   // raw uploads (kept so coordinates or metric can be replaced independently)
   double* d_xyz;   // [nv][3]
@@ -92,6 +93,10 @@ struct mag_ctx {
   int t_slots, t_used;
   int64_t n_launches;
 
+  // mag_sweep_host pipeline: upload / download streams and an event pool
+  cudaStream_t s_up, s_down;
+  std::vector<cudaEvent_t> pipe_ev;
+
   // multi-GPU
   void* nccl_comm;
   int nranks, rank;
@@ -101,6 +106,11 @@ struct mag_ctx {
 };
 
 int mag_fail(mag_ctx* c, int code, const char* fmt, ...);
+extern "C" {
+int magi_reshape(mag_ctx* c, int dim, int64_t nv, int64_t ne, int64_t nt, int64_t np, int64_t npy, int64_t ntri,
+                 bool has_edge_owned, bool has_elem_owned);
+int magi_reserve_metric(mag_ctx* c, int kind, size_t na, size_t nb);
+}
 int mag_stats_from_dev(mag_ctx* c, const MagDevStats& s, mag_stats* out);
 #define MAG_CUDA(c, call)                                                                      \
   do {                                                                                         \

@@ -391,7 +391,7 @@ __device__ __noinline__ unsigned drain_edges(NearQueue& q, int first, int n, con
                                              const double* __restrict__ vedge,
                                              int32_t* __restrict__ flags, double* __restrict__ lengths, uint32_t ops,
                                              double max_len, double min_len,
-                                             MagDevStats* st, int32_t* __restrict__ near_list)
+                                             MagDevStats* st, int32_t* __restrict__ near_list, int32_t id_base)
 {
   SweepParams P{ops, max_len, min_len, 0.0, 0};
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -399,7 +399,7 @@ __device__ __noinline__ unsigned drain_edges(NearQueue& q, int first, int n, con
   unsigned out = 0;
   if (lane < n) {
     const int32_t e = q.e[w][first + lane];
-    near_list[base + lane] = e;
+    near_list[base + lane] = e + id_base;
     if (FAST) {
       int32_t f = q.f[w][first + lane];
       const bool need_split = (P.ops & MAG_OP_MARK_SPLIT) && !(f & kSkipSplit);
@@ -429,7 +429,7 @@ template <int KIND, bool FAST>
 __global__ void __launch_bounds__(EdgeCfg<KIND, FAST>::T, EdgeCfg<KIND, FAST>::B)
 k_edges(int32_t ne, const int2* __restrict__ edge_v, const double* __restrict__ vedge,
         int32_t* __restrict__ flags, double* __restrict__ lengths,
-        EdgeParams P, MagDevStats* st, int32_t* __restrict__ near_list, const int32_t* __restrict__ chunk_order)
+        EdgeParams P, MagDevStats* st, int32_t* __restrict__ near_list, const int32_t* __restrict__ chunk_order, int32_t id_base)
 {
   __shared__ NearQueue q;
   __shared__ long long chunk_slot;
@@ -441,7 +441,7 @@ k_edges(int32_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
   for (;;) {
     const long long ticket = next_chunk(&st->edge_chunk, &chunk_slot);
     if (ticket >= nchunks) break;
-    const int e0 = chunk_order[ticket] * kChunkEdges;
+    const int e0 = (chunk_order ? chunk_order[ticket] : (int)ticket) * kChunkEdges;   // no schedule: a sub-range sweep (mag_sweep_host)
     const int e_end = (ne - e0 < kChunkEdges) ? ne : e0 + kChunkEdges;   // first edge past this chunk
     const int tiles = (e_end - e0 + kEdgeThreads - 1) / kEdgeThreads;
     int e = e0 + (int)threadIdx.x;
@@ -488,7 +488,7 @@ k_edges(int32_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
       }
       if (queue_push(q, qn, nr, (int32_t)e, f)) {
         qn -= 32;
-        const unsigned r = drain_edges<KIND, FAST>(q, qn, 32, edge_v, vedge, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list);
+        const unsigned r = drain_edges<KIND, FAST>(q, qn, 32, edge_v, vedge, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list, id_base);
         c_eval += r & 1u; c_split += (r >> 1) & 1u; c_coll += (r >> 2) & 1u;
       }
       f = f_nx;
@@ -496,7 +496,7 @@ k_edges(int32_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
     }
   }
   if (qn) {
-    const unsigned r = drain_edges<KIND, FAST>(q, 0, qn, edge_v, vedge, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list);
+    const unsigned r = drain_edges<KIND, FAST>(q, 0, qn, edge_v, vedge, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list, id_base);
     c_eval += r & 1u; c_split += (r >> 1) & 1u; c_coll += (r >> 2) & 1u;
   }
   if (eig_any) atomicAdd(&st->n_eigen_fail, 1ull);
@@ -693,7 +693,7 @@ k_tets(int32_t nt, int32_t elem_off, int64_t nv, const int4* __restrict__ tet_v,
   for (;;) {
     const long long ticket = next_chunk(&st->elem_chunk, &chunk_slot);
     if (ticket >= nchunks) break;
-    const int t0 = chunk_order[ticket] * kChunkTets;
+    const int t0 = (chunk_order ? chunk_order[ticket] : (int)ticket) * kChunkTets;
     const int t_end = (nt - t0 < kChunkTets) ? nt : t0 + kChunkTets;
     const int tiles = (t_end - t0 + kTetThreads - 1) / kTetThreads;
     int t = t0 + (int)threadIdx.x;
@@ -1125,23 +1125,26 @@ static EdgeParams edge_params(const SweepParams& P)
   return E;
 }
 
+// [first, first + n) = the whole part with the chunk schedule, or a sub-range in natural order (mag_sweep_host)
+struct Range { int64_t first, n; bool whole; };
+
 template <int KIND, bool FAST>
-static int launch_edges_t(mag_ctx* c, const SweepParams& P)
+static int launch_edges_t(mag_ctx* c, const SweepParams& P, const Range& r)
 {
   static int per_sm = 0;
   constexpr int kEdgeThreads = EdgeCfg<KIND, FAST>::T;
-  const unsigned g = persistent_grid(c, per_sm, (const void*)k_edges<KIND, FAST>, c->ne, kEdgeThreads, kEdgeChunk);
-  k_edges<KIND, FAST><<<g, kEdgeThreads, 0, c->stream>>>((int32_t)c->ne, reinterpret_cast<const int2*>(c->d_edge_v), c->d_vedge,
-                                                         c->d_edge_flags, c->d_len, edge_params(P), c->d_stats,
-                                                         c->d_near_edge, c->d_edge_order);
+  const unsigned g = persistent_grid(c, per_sm, (const void*)k_edges<KIND, FAST>, r.n, kEdgeThreads, kEdgeChunk);
+  k_edges<KIND, FAST><<<g, kEdgeThreads, 0, c->stream>>>((int32_t)r.n, reinterpret_cast<const int2*>(c->d_edge_v) + r.first, c->d_vedge,
+                                                         c->d_edge_flags + r.first, c->d_len + r.first, edge_params(P), c->d_stats,
+                                                         c->d_near_edge, r.whole ? c->d_edge_order : nullptr, (int32_t)r.first);
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;
   return MAG_OK;
 }
 template <int KIND>
-static int launch_edges(mag_ctx* c, const SweepParams& P, bool fast)
+static int launch_edges(mag_ctx* c, const SweepParams& P, bool fast, const Range& r)
 {
-  return fast ? launch_edges_t<KIND, true>(c, P) : launch_edges_t<KIND, false>(c, P);
+  return fast ? launch_edges_t<KIND, true>(c, P, r) : launch_edges_t<KIND, false>(c, P, r);
 }
 
 static TetParams tet_params(const SweepParams& P)
@@ -1157,23 +1160,86 @@ static TetParams tet_params(const SweepParams& P)
 }
 
 template <int KIND, bool FAST, bool USE_MAX>
-static int launch_tets_t(mag_ctx* c, const SweepParams& P)
+static int launch_tets_t(mag_ctx* c, const SweepParams& P, const Range& r)
 {
   static int per_sm = 0;
   constexpr int kTetThreads = TetCfg<FAST>::T;
-  const unsigned g = persistent_grid(c, per_sm, (const void*)k_tets<KIND, FAST, USE_MAX>, c->nt, kTetThreads, kTetChunk);
-  k_tets<KIND, FAST, USE_MAX><<<g, kTetThreads, 0, c->stream>>>((int32_t)c->nt, (int32_t)(c->np + c->npy), c->nv, reinterpret_cast<const int4*>(c->d_tet_v),
-                                                        c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_flags, c->d_qual, tet_params(P),
-                                                        c->d_stats, c->d_near_elem, c->d_tet_order);
+  const unsigned g = persistent_grid(c, per_sm, (const void*)k_tets<KIND, FAST, USE_MAX>, r.n, kTetThreads, kTetChunk);
+  k_tets<KIND, FAST, USE_MAX><<<g, kTetThreads, 0, c->stream>>>((int32_t)r.n, (int32_t)(c->np + c->npy + r.first), c->nv,
+                                                                 reinterpret_cast<const int4*>(c->d_tet_v) + r.first,
+                                                                 c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_flags, c->d_qual, tet_params(P),
+                                                                 c->d_stats, c->d_near_elem, r.whole ? c->d_tet_order : nullptr);
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;
   return MAG_OK;
 }
 template <int KIND>
-static int launch_tets(mag_ctx* c, const SweepParams& P, bool fast)
+static int launch_tets(mag_ctx* c, const SweepParams& P, bool fast, const Range& r)
 {
-  if (P.use_max) return fast ? launch_tets_t<KIND, true, true>(c, P) : launch_tets_t<KIND, false, true>(c, P);
-  return fast ? launch_tets_t<KIND, true, false>(c, P) : launch_tets_t<KIND, false, false>(c, P);
+  if (P.use_max) return fast ? launch_tets_t<KIND, true, true>(c, P, r) : launch_tets_t<KIND, false, true>(c, P, r);
+  return fast ? launch_tets_t<KIND, true, false>(c, P, r) : launch_tets_t<KIND, false, false>(c, P, r);
+}
+
+static int launch_edges_kind(mag_ctx* c, const SweepParams& P, bool fast, const Range& r)
+{
+  switch (c->kind) {
+    case MAG_KIND_IDENTITY: return launch_edges<MAG_KIND_IDENTITY>(c, P, fast, r);
+    case MAG_KIND_ISO: return launch_edges<MAG_KIND_ISO>(c, P, fast, r);
+    case MAG_KIND_ANISO: return launch_edges<MAG_KIND_ANISO>(c, P, fast, r);
+    default: return launch_edges<MAG_KIND_LOGM>(c, P, fast, r);
+  }
+}
+static int launch_tets_kind(mag_ctx* c, const SweepParams& P, bool fast, const Range& r)
+{
+  switch (c->kind) {
+    case MAG_KIND_IDENTITY: return launch_tets<MAG_KIND_IDENTITY>(c, P, fast, r);
+    case MAG_KIND_ISO: return launch_tets<MAG_KIND_ISO>(c, P, fast, r);
+    case MAG_KIND_ANISO: return launch_tets<MAG_KIND_ANISO>(c, P, fast, r);
+    default: return launch_tets<MAG_KIND_LOGM>(c, P, fast, r);
+  }
+}
+static SweepParams sweep_params(const mag_ctx* c, uint32_t ops, double max_len, double min_len, double good_q, int use_max)
+{
+  SweepParams P{ops, max_len, min_len, good_q, use_max};
+  if (c->kind == MAG_KIND_IDENTITY) {
+    // IdentitySizeField::shouldSplit / shouldCollapse are constant false (maSize.cc:64-72): no length exceeds +inf
+    P.max_len = INFINITY;
+    P.min_len = -INFINITY;
+  }
+  return P;
+}
+
+// sub-range sweeps of the streaming entry point (mag_sweep_host): the slice's connectivity and flag words are already on
+// the device; entities are taken in natural order; the work-distribution ticket is reset for every launch
+int magk_edges_range(mag_ctx* c, uint32_t ops, double max_len, double min_len, int fp_mode, int64_t first, int64_t n)
+{
+  if (n <= 0) return MAG_OK;
+  if (c->d_edge_owned) {
+    k_fold_owned<<<grid_for(n), kThreads, 0, c->stream>>>(n, 2, c->d_edge_owned + first, c->d_edge_v + 2 * first);
+    c->n_launches++;
+  }
+  if (!(ops & (MAG_OP_LENGTHS | MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE))) return MAG_OK;   // export only
+  MAG_CUDA(c, cudaMemsetAsync(&c->d_stats->edge_chunk, 0, sizeof(unsigned long long), c->stream));
+  return launch_edges_kind(c, sweep_params(c, ops, max_len, min_len, 0.0, 1), fp_mode == MAG_FP_FAST, Range{first, n, false});
+}
+int magk_tets_range(mag_ctx* c, uint32_t ops, double good_q, int use_max, int fp_mode, int64_t first, int64_t n)
+{
+  if (n <= 0) return MAG_OK;
+  if (c->d_elem_owned) {
+    k_fold_owned<<<grid_for(n), kThreads, 0, c->stream>>>(n, 4, c->d_elem_owned + (c->np + c->npy) + first, c->d_tet_v + 4 * first);
+    c->n_launches++;
+  }
+  if (!(ops & (MAG_OP_QUALITIES | MAG_OP_MARK_BAD))) return MAG_OK;
+  MAG_CUDA(c, cudaMemsetAsync(&c->d_stats->elem_chunk, 0, sizeof(unsigned long long), c->stream));
+  return launch_tets_kind(c, sweep_params(c, ops, 0.0, 0.0, good_q, use_max), fp_mode == MAG_FP_FAST, Range{first, n, false});
+}
+int magk_length_sum(mag_ctx* c)
+{
+  k_sum_lengths<<<MAG_SUM_BLOCKS, kThreads, 0, c->stream>>>(c->ne, c->d_len, c->d_edge_owned, c->d_block_sums);
+  k_finish_sum<<<1, kThreads, 0, c->stream>>>((int64_t)MAG_SUM_BLOCKS, c->d_block_sums, c->d_stats);
+  MAG_CUDA(c, cudaGetLastError());
+  c->n_launches += 2;
+  return MAG_OK;
 }
 
 #include <algorithm>
@@ -1212,12 +1278,7 @@ int magk_build_schedule(mag_ctx* c)
 
 int magk_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double good_q, int use_max, int fp_mode)
 {
-  SweepParams P{ops, max_len, min_len, good_q, use_max};
-  if (c->kind == MAG_KIND_IDENTITY) {
-    // IdentitySizeField::shouldSplit / shouldCollapse are constant false (maSize.cc:64-72): no length exceeds +inf
-    P.max_len = INFINITY;
-    P.min_len = -INFINITY;
-  }
+  const SweepParams P = sweep_params(c, ops, max_len, min_len, good_q, use_max);
   const bool fast = fp_mode == MAG_FP_FAST;
   int rc;
   cudaEvent_t* tev = (c->t_used < c->t_slots) ? &c->tev[(size_t)4 * c->t_used] : nullptr;
@@ -1228,30 +1289,13 @@ int magk_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double 
   }
   if (tev) MAG_CUDA(c, cudaEventRecord(tev[1], c->stream));
   if (c->ne && (ops & (MAG_OP_LENGTHS | MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE))) {
-    switch (c->kind) {
-      case MAG_KIND_IDENTITY: rc = launch_edges<MAG_KIND_IDENTITY>(c, P, fast); break;
-      case MAG_KIND_ISO: rc = launch_edges<MAG_KIND_ISO>(c, P, fast); break;
-      case MAG_KIND_ANISO: rc = launch_edges<MAG_KIND_ANISO>(c, P, fast); break;
-      default: rc = launch_edges<MAG_KIND_LOGM>(c, P, fast); break;
-    }
-    if (rc) return rc;
-    if (ops & MAG_OP_LENGTH_SUM) {
-      k_sum_lengths<<<MAG_SUM_BLOCKS, kThreads, 0, c->stream>>>(c->ne, c->d_len, c->d_edge_owned, c->d_block_sums);
-      k_finish_sum<<<1, kThreads, 0, c->stream>>>((int64_t)MAG_SUM_BLOCKS, c->d_block_sums, c->d_stats);
-      MAG_CUDA(c, cudaGetLastError());
-      c->n_launches += 2;
-    }
+    if ((rc = launch_edges_kind(c, P, fast, Range{0, c->ne, true}))) return rc;
+    if ((ops & MAG_OP_LENGTH_SUM) && (rc = magk_length_sum(c))) return rc;
   }
   if (tev) MAG_CUDA(c, cudaEventRecord(tev[2], c->stream));
   if (ops & (MAG_OP_QUALITIES | MAG_OP_MARK_BAD)) {
     if (c->nt) {
-      switch (c->kind) {
-        case MAG_KIND_IDENTITY: rc = launch_tets<MAG_KIND_IDENTITY>(c, P, fast); break;
-        case MAG_KIND_ISO: rc = launch_tets<MAG_KIND_ISO>(c, P, fast); break;
-        case MAG_KIND_ANISO: rc = launch_tets<MAG_KIND_ANISO>(c, P, fast); break;
-        default: rc = launch_tets<MAG_KIND_LOGM>(c, P, fast); break;
-      }
-      if (rc) return rc;
+      if ((rc = launch_tets_kind(c, P, fast, Range{0, c->nt, true}))) return rc;
     }
     if (c->ntri) {
       switch (c->kind) {

@@ -12,7 +12,7 @@ Everything runs through the C ABI (include/mag.h); there is no CPU fallback.
 import ctypes as C
 import numpy as np
 
-from ._lib import lib, MagStats
+from ._lib import lib, MagStats, MagHostPart, MagHostResult
 
 # ma/maSize.h:26-27, ma/maInput.cc:32-46
 MAXLENGTH = 1.5
@@ -169,6 +169,30 @@ class Part:
               use_max=True, fp_mode=FP_STRICT):
         self._ck(self._L.mag_sweep(self._h, int(ops), float(max_len), float(min_len), float(good_quality),
                                    int(bool(use_max)), int(fp_mode)))
+
+    def sweep_host(self, xyz, edge_v, tet_v, kind, field_a=None, field_b=None, edge_flags=None, elem_flags=None,
+                   edge_owned=None, elem_owned=None, out_lengths=None, out_qualities=None, out_edge_flags=None,
+                   out_elem_flags=None, ops=OP_ALL & ~OP_LAYER_CHECK, max_len=MAXLENGTH, min_len=MINLENGTH,
+                   good_quality=GOOD_QUALITY_3D, use_max=True, fp_mode=FP_STRICT, slice_entities=0):
+        """mag_sweep_host: export + sweep + results of a tet part in one streamed call (host buffers, ideally pinned).
+        kind: 0 identity, 1 iso (field_a = size), 2 aniso (field_a = h, field_b = R), 3 logm (field_b = logM).
+        Returns the statistics dict; outputs land in the out_* buffers that were given."""
+        xyz = _arr(xyz, np.float64)
+        edge_v, tet_v = _arr(edge_v, np.int32), _arr(tet_v, np.int32)
+        fa, fb = _arr(field_a, np.float64), _arr(field_b, np.float64)
+        ef, lf = _arr(edge_flags, np.int32), _arr(elem_flags, np.int32)
+        eo, lo = _arr(edge_owned, np.uint8), _arr(elem_owned, np.uint8)
+        n = lambda a, k: 0 if a is None else int(a.numel() if hasattr(a, "numel") else a.size) // k
+        self.nv, self.ne, self.nt = n(xyz, 3), n(edge_v, 2), n(tet_v, 4)
+        self.np_ = self.npy = self.ntri = 0
+        pv = lambda a: None if a is None else _ptr(a).value
+        part = MagHostPart(self.nv, pv(xyz), self.ne, pv(edge_v), self.nt, pv(tet_v), pv(eo), pv(lo), int(kind),
+                           pv(fa), pv(fb), pv(ef), pv(lf), int(slice_entities))
+        res = MagHostResult(pv(out_lengths), pv(out_qualities), pv(out_edge_flags), pv(out_elem_flags))
+        s = MagStats()
+        self._ck(self._L.mag_sweep_host(self._h, C.byref(part), C.byref(res), int(ops), float(max_len), float(min_len),
+                                        float(good_quality), int(bool(use_max)), int(fp_mode), C.byref(s)))
+        return s.as_dict()
 
     def stats(self):
         s = MagStats()

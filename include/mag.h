@@ -150,6 +150,35 @@ int mag_get_stats(mag_ctx* c, mag_stats* out); /* this part only; also reports d
    which: 0 = edges (vs max_len or min_len), 1 = elements (vs good_quality).  Writes up to cap indices, returns the total in *n. */
 int mag_get_near_threshold(mag_ctx* c, int which, int64_t* idx, int64_t cap, int64_t* n);
 
+/* ---- export + sweep + results of one tet part in ONE call, streamed (what the adapter does once per MeshAdapt
+   iteration, ma/maAdapt.cc:293-324 callers in maRefine.cc / maCoarsen.cc / maShape.cc).  Equivalent to
+   mag_set_mesh + mag_set_metric_* + mag_set_flags + mag_sweep + mag_get_edge_lengths / qualities / flags / stats, with
+   bit-identical results, but the edges and tets travel in slices so that the device->host copies of finished slices
+   overlap the host->device copies of the next ones; the call returns when every output has landed.  Host buffers should
+   be page-locked (cudaHostAlloc / cudaHostRegister) for the copies to be asynchronous.  The part stays resident: the
+   getters, mag_sweep, mag_reconcile_edge_flags ... work on it afterwards.  Prisms / pyramids are not supported here. */
+typedef struct mag_host_part {
+  int64_t nv; const double* xyz;           /* [nv][3] */
+  int64_t ne; const int32_t* edge_v;       /* [ne][2] */
+  int64_t nt; const int32_t* tet_v;        /* [nt][4] */
+  const uint8_t* edge_owned;               /* [ne] or NULL */
+  const uint8_t* elem_owned;               /* [nt] or NULL */
+  int kind;                                /* 0 identity, 1 iso, 2 aniso, 3 logm */
+  const double* field_a;                   /* iso: size[nv]; aniso: h[nv][3]; else NULL */
+  const double* field_b;                   /* aniso: R[nv][9]; logm: logM[nv][9]; else NULL */
+  const int32_t* edge_flags;               /* incoming ma_flags words, NULL = 0 */
+  const int32_t* elem_flags;
+  int64_t slice_entities;                  /* entities per slice, 0 = default (4 Mi); rounded up to whole work chunks */
+} mag_host_part;
+typedef struct mag_host_result {           /* any pointer may be NULL */
+  double* edge_lengths;                    /* [ne]  (MAG_OP_LENGTHS) */
+  double* qualities;                       /* [nt]  (MAG_OP_QUALITIES) */
+  int32_t* edge_flags;                     /* [ne] */
+  int32_t* elem_flags;                     /* [nt] */
+} mag_host_result;
+int mag_sweep_host(mag_ctx* c, const mag_host_part* in, const mag_host_result* out, uint32_t ops, double max_len,
+                   double min_len, double good_quality, int use_max_metric, int fp_mode, mag_stats* stats /* may be NULL */);
+
 /* the logM vertex field from sizes + frames, computed on the host exactly as the reference does (libm log):
    variant 0 = LogAnisoSizeField::init from fields, log(1/h/h)   (ma/maSize.cc:491-499)
    variant 1 = LogMEval from a user function, -2*log(h)          (ma/maSize.cc:343-346)

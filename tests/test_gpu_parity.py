@@ -300,6 +300,66 @@ def test_two_parts_one_gpu_partition_invariance(cb):
     assert abs(mx - want["max_length"]) <= TOL * mx and abs(mn - want["min_quality"]) <= TOL * abs(mn)
 
 
+@pytest.mark.parametrize("kindname", ["iso", "aniso", "logm"])
+def test_sweep_host_streamed_equals_resident(cb, kindname):
+    """mag_sweep_host (export + sweep + results in one streamed call, several slices) returns bit for bit what the
+    resident calls return, with incoming flag words and ownership, in both fp modes; the part stays resident."""
+    from oracle import mao
+    n = 24
+    rng = np.random.default_rng(5)
+    xyz, ev, tv = cb.boxmesh.kuhn_box(n, n, n)
+    xyz = cb.fields.jitter(xyz, 0.3 / n)
+    nv = len(xyz)
+    R = util.random_frames(nv, rng)
+    H = (1.0 / n) * np.exp(rng.uniform(-1.0, 1.0, (nv, 3)))
+    s = (1.0 / n) * np.exp(rng.uniform(-1, 1, nv))
+    kind, ma, mb = {"iso": (mao.ISO, s, None), "aniso": (mao.ANISO, H, R),
+                    "logm": (mao.LOGM, None, mao.logm_from_frames(H, R, 0))}[kindname]
+    ef = np.zeros(len(ev), np.int32)
+    lf = np.zeros(len(tv), np.int32)
+    ef[rng.random(len(ev)) < 0.2] |= cb.DONT_SPLIT
+    ef[rng.random(len(ev)) < 0.1] |= cb.NEED_NOT_COLLAPSE
+    lf[rng.random(len(tv)) < 0.3] |= cb.OK_QUALITY
+    eo = (rng.random(len(ev)) < 0.9).astype(np.uint8)
+    lo = (rng.random(len(tv)) < 0.9).astype(np.uint8)
+    ops = cb.OP_ALL & ~cb.OP_LAYER_CHECK
+    p = cb.Part(0)
+    q = cb.Part(0)
+    assert len(ev) > 61440 and len(tv) > 61440          # more than one slice each
+    for mode in (cb.FP_STRICT, cb.FP_FAST):
+        p.set_mesh(xyz, ev, tv, edge_owned=eo, elem_owned=lo)
+        util.set_part_metric(p, kind, ma, mb)
+        p.set_flags(ef, lf)
+        p.sweep(ops, good_quality=0.1, fp_mode=mode)
+        st0, L0, q0 = p.stats(), p.edge_lengths(), p.qualities()
+        ef0, lf0 = p.flags()
+        oL, oq = np.empty(len(ev)), np.empty(len(tv))
+        oef, olf = np.empty(len(ev), np.int32), np.empty(len(tv), np.int32)
+        st1 = q.sweep_host(xyz, ev, tv, kind, ma, mb, edge_flags=ef, elem_flags=lf, edge_owned=eo, elem_owned=lo,
+                           out_lengths=oL, out_qualities=oq, out_edge_flags=oef, out_elem_flags=olf, ops=ops,
+                           good_quality=0.1, fp_mode=mode, slice_entities=61440)
+        assert np.array_equal(oL, L0) and np.array_equal(oq, q0)
+        assert np.array_equal(oef, ef0) and np.array_equal(olf, lf0)
+        for k in ("n_split", "n_collapse", "n_bad", "n_edges_evaluated", "n_elems_evaluated", "n_near_threshold",
+                  "min_quality", "max_length"):
+            assert st0[k] == st1[k], k
+        assert sorted(q.near_threshold(0)[0].tolist()) == sorted(p.near_threshold(0)[0].tolist())
+        # the part is resident: the getters and a plain sweep work on it
+        assert np.array_equal(q.edge_lengths(), L0)
+        q.set_flags(ef, lf)
+        q.sweep(ops, good_quality=0.1, fp_mode=mode)
+        assert np.array_equal(q.flags()[0], ef0) and q.stats()["n_bad"] == st0["n_bad"]
+    # NULL flag words = zeros, no ownership arrays, outputs optional
+    st = q.sweep_host(xyz, ev, tv, kind, ma, mb, ops=cb.OP_MARK_SPLIT | cb.OP_MARK_BAD, good_quality=0.1, fp_mode=cb.FP_FAST)
+    p.set_mesh(xyz, ev, tv)
+    util.set_part_metric(p, kind, ma, mb)
+    p.sweep(cb.OP_MARK_SPLIT | cb.OP_MARK_BAD, good_quality=0.1, fp_mode=cb.FP_FAST)
+    assert (st["n_split"], st["n_bad"]) == (p.stats()["n_split"], p.stats()["n_bad"])
+    assert np.array_equal(q.flags()[0], p.flags()[0]) and np.array_equal(q.flags()[1], p.flags()[1])
+    p.close()
+    q.close()
+
+
 def test_full_size_properties(cb):
     """BASELINE config 3 size (n=203: 50.2 M tets, 58.9 M edges).  The oracle cannot sweep this in seconds, so:
     (1) a seeded random sample of 300k edges and 300k tets is checked against the oracle; (2) fast and strict flags
