@@ -137,7 +137,7 @@ int mag_create(mag_ctx** out, int device)
   c->d_edge_v = c->d_tet_v = c->d_prism_v = c->d_pyr_v = c->d_tri_v = nullptr;
   c->d_edge_owned = c->d_elem_owned = nullptr;
   c->d_edge_flags = c->d_elem_flags = nullptr;
-  c->d_len = c->d_qual = nullptr;
+  c->d_len = c->d_qual = nullptr; c->d_weight = nullptr;
   c->d_layer_ok = c->d_layer_codes = nullptr;
   c->d_stats = nullptr; c->h_stats = nullptr;
   c->d_block_sums = nullptr; c->n_sms = 148;
@@ -174,7 +174,7 @@ void mag_destroy(mag_ctx* c)
   cudaFree(c->d_xyz); cudaFree(c->d_ma); cudaFree(c->d_mb); cudaFree(c->d_vedge); cudaFree(c->d_vpos); cudaFree(c->d_vq);
   cudaFree(c->d_edge_v); cudaFree(c->d_tet_v); cudaFree(c->d_prism_v); cudaFree(c->d_pyr_v); cudaFree(c->d_tri_v);
   cudaFree(c->d_edge_owned); cudaFree(c->d_elem_owned); cudaFree(c->d_edge_flags); cudaFree(c->d_elem_flags);
-  cudaFree(c->d_len); cudaFree(c->d_qual); cudaFree(c->d_layer_ok); cudaFree(c->d_layer_codes);
+  cudaFree(c->d_len); cudaFree(c->d_qual); cudaFree(c->d_weight); cudaFree(c->d_layer_ok); cudaFree(c->d_layer_codes);
   cudaFree(c->d_stats); cudaFreeHost(c->h_stats); cudaFree(c->d_block_sums);
   cudaFree(c->d_near_edge); cudaFree(c->d_near_elem); cudaFree(c->d_edge_order); cudaFree(c->d_tet_order);
   for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
@@ -215,6 +215,7 @@ int magi_reshape(mag_ctx* c, int dim, int64_t nv, int64_t ne, int64_t nt, int64_
   const bool same_shape = nv == c->nv && ne == c->ne && nt == c->nt && np == c->np && npy == c->npy && ntri == c->ntri &&
                           has_edge_owned == (c->d_edge_owned != nullptr) && has_elem_owned == (c->d_elem_owned != nullptr);
   if (same_shape) return MAG_OK;
+  if ((rc = dev_free(c, c->d_weight))) return rc;
   if (nv != c->nv) { // size field arrays are per vertex: drop them
     c->kind = MAG_KIND_NONE;
     if ((rc = dev_free(c, c->d_ma)) || (rc = dev_free(c, c->d_mb)) || (rc = dev_free(c, c->d_vedge))) return rc;

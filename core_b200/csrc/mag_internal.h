@@ -72,6 +72,7 @@ struct mag_ctx {
   int32_t* d_elem_flags; // [np+npy+nt]
   double* d_len;         // [ne]
   double* d_qual;        // [np+npy+nt]
+  double* d_weight;      // [np+npy+nt] element weights of the last mag_element_weights (allocated on first use)
   int32_t* d_layer_ok;   // [np+npy]
   int32_t* d_layer_codes;
   MagDevStats* d_stats;

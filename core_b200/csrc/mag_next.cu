@@ -1,0 +1,335 @@
+// mag_next.cu -- the sweeps either side of the marking path, over the same device-resident part:
+//   mag_element_weights   predictive load-balance weight of every element
+//                         ma::getElementWeights / getElementWeight (ma/maBalance.cc:21-52,74-97),
+//                         SizeField::getWeight = measure(element) / parentMeasure (ma/maSize.cc:147-156,225-229)
+//   mag_split_vertices    position and size-field values of the vertex that will split every SPLIT-marked edge
+//                         ma::makeSplitVert (ma/maRefine.cc:129-151), SizeField::interpolate (ma/maSize.cc:414-429,523-534)
+// Both follow the reference's operation order through the arithmetic policies of mag_math.cuh (StrictOps: bit-identical;
+// FusedOps: FMA-contracted, within 1e-12).
+#include "mag_internal.h"
+#include "mag_layout.cuh"
+#include "mag_math.cuh"
+#include <cmath>
+
+using namespace maglay;
+
+namespace {
+
+constexpr int kWThreads = 128;
+
+// ------------------------------------------------------------------ element weights
+// measure(tet): SizeFieldIntegrator, order 2 -> TetrahedronIntegration::N2 (apf/apfIntegrate.cc:328-342): 4 points,
+// weights 0.25/6; at each point dV2 = det(J * Q(xi)), Q = getTransform at the point from the four vertex values
+// (tet shape values apf/apfShape.cc:203-210; interpolation c = 0; c += node_n * N_n in node order, apfElement.cc:106-114).
+template <int KIND, class OPS>
+__device__ __forceinline__ double tet_weight(const double* __restrict__ vedge, const int4& tv, int* eig_fail)
+{
+  typedef MagMath<OPS> MM;
+  if (KIND == MAG_KIND_IDENTITY) return 1.0;   // IdentitySizeField::getWeight (maSize.cc:89-92)
+  constexpr int N = (KIND == MAG_KIND_ISO) ? 4 : 12;
+  const int32_t vid[4] = {tv.x & kVidMask, tv.y, tv.z, tv.w};
+  double rec[4][N];
+#pragma unroll
+  for (int n = 0; n < 4; ++n) {
+    if (KIND == MAG_KIND_ISO) load_rec4(vedge, vid[n], rec[n]);
+    else {
+      Rec12 r = load_rec12(vedge, vid[n]);
+#pragma unroll
+      for (int i = 0; i < 12; ++i) rec[n][i] = r.v[i];
+    }
+  }
+  // J rows = -x0 + xn (apfVectorElement.cc:44-52 with grads (-1,-1,-1),(1,0,0),(0,1,0),(0,0,1); the x*0 terms add +-0)
+  M3 J;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) J.m[i][c] = MM::add(-rec[0][c], rec[i + 1][c]);
+  constexpr double A = 0.138196601125011, B = 0.585410196624969;
+  double measurement = 0.0;
+#pragma unroll 1
+  for (int p = 0; p < 4; ++p) {
+    const double xi0 = p == 1 ? B : A, xi1 = p == 2 ? B : A, xi2 = p == 3 ? B : A;
+    const double Ns[4] = {1 - xi0 - xi1 - xi2, xi0, xi1, xi2};
+    double c[N - 3];
+#pragma unroll
+    for (int i = 0; i < N - 3; ++i) {
+      double v = MM::mul(rec[0][3 + i], Ns[0]);
+#pragma unroll
+      for (int n = 1; n < 4; ++n) v = MM::add(v, MM::mul(rec[n][3 + i], Ns[n]));
+      c[i] = v;
+    }
+    M3 Q;
+    if (KIND == MAG_KIND_ISO) {
+      MM::identity(Q);
+      const double ih = MM::div(1.0, c[0]);
+      Q.m[0][0] = ih; Q.m[1][1] = ih; Q.m[2][2] = ih;
+    } else if (KIND == MAG_KIND_ANISO) {
+      MM::transform_aniso(V3{c[3], c[4], c[5]}, V3{c[6], c[7], c[8]}, c[0], c[1], c[2], Q);
+    } else {
+      M3 L;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) L.m[i / 3][i % 3] = c[i];
+      if (MM::transform_logm(L, Q) != 1) *eig_fail = 1;
+    }
+    M3 JQ;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        JQ.m[i][j] = MM::add(MM::add(MM::mul(J.m[i][0], Q.m[0][j]), MM::mul(J.m[i][1], Q.m[1][j])), MM::mul(J.m[i][2], Q.m[2][j]));
+    const double wdv = MM::mul(0.25 / 6.0, MM::det3(JQ));
+    measurement = p == 0 ? wdv : MM::add(measurement, wdv);
+  }
+  return MM::div(measurement, 1.0 / 6.0);   // parentMeasure[TET]
+}
+
+template <int KIND, class OPS>
+__global__ void __launch_bounds__(kWThreads)
+k_tet_weights(int32_t nt, int32_t elem_off, const int4* __restrict__ tet_v, const double* __restrict__ vedge,
+              double w_max, double w_min, double* __restrict__ weight, MagDevStats* st)
+{
+  int eig = 0;
+  for (int32_t t = blockIdx.x * kWThreads + threadIdx.x; t < nt; t += gridDim.x * kWThreads) {
+    double w = tet_weight<KIND, OPS>(vedge, __ldg(tet_v + t), &eig);
+    // clamp of maBalance.cc:14-19
+    if (w > w_max) w = w_max;
+    else if (w < w_min) w = w_min;
+    weight[elem_off + t] = w;
+  }
+  if (eig) atomicAdd(&st->n_eigen_fail, 1ull);
+}
+
+template <int KIND>
+int launch_weights(mag_ctx* c, double w_max, double w_min, bool fast, double* d_w)
+{
+  const int64_t blocks = (c->nt + kWThreads - 1) / kWThreads;
+  const unsigned g = (unsigned)(blocks < (int64_t)c->n_sms * 16 ? blocks : (int64_t)c->n_sms * 16);
+  const int4* tv = reinterpret_cast<const int4*>(c->d_tet_v);
+  const int32_t off = (int32_t)(c->np + c->npy);
+  if (fast) k_tet_weights<KIND, FusedOps><<<g, kWThreads, 0, c->stream>>>((int32_t)c->nt, off, tv, c->d_vedge, w_max, w_min, d_w, c->d_stats);
+  else k_tet_weights<KIND, StrictOps><<<g, kWThreads, 0, c->stream>>>((int32_t)c->nt, off, tv, c->d_vedge, w_max, w_min, d_w, c->d_stats);
+  MAG_CUDA(c, cudaGetLastError());
+  c->n_launches++;
+  return MAG_OK;
+}
+
+// ------------------------------------------------------------------ split vertices
+// ordered compaction of the SPLIT-marked edges: tiles of kSTile edges -> tile counts -> exclusive scan -> scatter
+constexpr int kSThreads = 256, kSPasses = 4, kSTile = kSThreads * kSPasses;
+
+__global__ void __launch_bounds__(kSThreads)
+k_split_count(int32_t ne, const int32_t* __restrict__ flags, int32_t* __restrict__ tile_count)
+{
+  __shared__ int sh[kSThreads / 32];
+  int n = 0;
+  const int32_t e0 = blockIdx.x * kSTile;
+#pragma unroll
+  for (int p = 0; p < kSPasses; ++p) {
+    const int32_t e = e0 + p * kSThreads + threadIdx.x;
+    if (e < ne && (flags[e] & MAG_SPLIT)) ++n;
+  }
+  n = __reduce_add_sync(0xffffffffu, n);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = n;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int i = 0; i < kSThreads / 32; ++i) t += sh[i];
+    tile_count[blockIdx.x] = t;
+  }
+}
+// single block: exclusive scan of the tile counts in place, total to *total
+__global__ void __launch_bounds__(1024)
+k_split_scan(int32_t ntiles, int32_t* __restrict__ tile_count, long long* __restrict__ total)
+{
+  __shared__ long long sh[1024];
+  __shared__ long long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int32_t base = 0; base < ntiles; base += 1024) {
+    const int32_t i = base + threadIdx.x;
+    const long long v = i < ntiles ? tile_count[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      long long t = threadIdx.x >= (unsigned)o ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < ntiles) tile_count[i] = (int32_t)(carry + sh[threadIdx.x] - v);
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += sh[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+// makeSplitVert at xi = 0: edge shape values ((1-xi)/2, (1+xi)/2) = (0.5, 0.5) (apfShape.cc:123-124)
+template <int KIND, class OPS>
+__device__ __forceinline__ void split_vertex(const double* __restrict__ vedge, const double* __restrict__ raw_b, int2 ev, long long k,
+                                             double* __restrict__ oxyz, double* __restrict__ oa, double* __restrict__ ob)
+{
+  typedef MagMath<OPS> MM;
+  constexpr double N0 = (1.0 - 0.0) / 2.0, N1 = (1.0 + 0.0) / 2.0;
+  ev.x &= kVidMask;
+  if (KIND == MAG_KIND_IDENTITY || KIND == MAG_KIND_ISO) {
+    double a[4], b[4];
+    load_rec4(vedge, ev.x, a);
+    load_rec4(vedge, ev.y, b);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) oxyz[3 * k + i] = MM::lerp2(a[i], N0, b[i], N1);
+    if (KIND == MAG_KIND_ISO) oa[k] = MM::lerp2(a[3], N0, b[3], N1);
+    return;
+  }
+  const Rec12 a = load_rec12(vedge, ev.x), b = load_rec12(vedge, ev.y);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) oxyz[3 * k + i] = MM::lerp2(a.v[i], N0, b.v[i], N1);
+  if (KIND == MAG_KIND_LOGM) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) ob[9 * k + i] = MM::lerp2(a.v[3 + i], N0, b.v[3 + i], N1);
+    return;
+  }
+  // AnisoSizeField::interpolate: h interpolated, R = orthogonalizeR(interpolated frame) (maSize.cc:414-429, 94-121);
+  // column 2 of the interpolated frame is discarded by orthogonalizeR, so columns 0 and 1 of the records suffice
+  (void)raw_b;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) oa[3 * k + i] = MM::lerp2(a.v[3 + i], N0, b.v[3 + i], N1);
+  V3 r0{MM::lerp2(a.v[6], N0, b.v[6], N1), MM::lerp2(a.v[7], N0, b.v[7], N1), MM::lerp2(a.v[8], N0, b.v[8], N1)};
+  V3 r1{MM::lerp2(a.v[9], N0, b.v[9], N1), MM::lerp2(a.v[10], N0, b.v[10], N1), MM::lerp2(a.v[11], N0, b.v[11], N1)};
+  V3 r2;
+  MM::gram_schmidt(r0, r1, r2);
+  double* R = ob + 9 * k;   // row-major, frame vectors in the columns
+  R[0] = r0.x; R[3] = r0.y; R[6] = r0.z;
+  R[1] = r1.x; R[4] = r1.y; R[7] = r1.z;
+  R[2] = r2.x; R[5] = r2.y; R[8] = r2.z;
+}
+
+template <int KIND, class OPS>
+__global__ void __launch_bounds__(kSThreads)
+k_split_fill(int32_t ne, const int32_t* __restrict__ flags, const int2* __restrict__ edge_v, const double* __restrict__ vedge,
+             const int32_t* __restrict__ tile_off, int32_t* __restrict__ oidx, double* __restrict__ oxyz,
+             double* __restrict__ oa, double* __restrict__ ob)
+{
+  __shared__ int sh[kSThreads / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  long long base = tile_off[blockIdx.x];
+  const int32_t e0 = blockIdx.x * kSTile;
+  for (int p = 0; p < kSPasses; ++p) {
+    const int32_t e = e0 + p * kSThreads + threadIdx.x;
+    const bool s = e < ne && (flags[e] & MAG_SPLIT);
+    const unsigned m = __ballot_sync(0xffffffffu, s);
+    __syncthreads();                       // sh is free again
+    if (lane == 0) sh[w] = __popc(m);
+    __syncthreads();
+    int before = 0, pass_total = 0;
+#pragma unroll
+    for (int i = 0; i < kSThreads / 32; ++i) { before += i < w ? sh[i] : 0; pass_total += sh[i]; }
+    if (s) {
+      const long long k = base + before + __popc(m & ((1u << lane) - 1u));
+      oidx[k] = e;
+      split_vertex<KIND, OPS>(vedge, nullptr, __ldg(edge_v + e), k, oxyz, oa, ob);
+    }
+    base += pass_total;
+  }
+}
+
+template <int KIND>
+int launch_split_fill(mag_ctx* c, bool fast, unsigned tiles, const int32_t* d_off, int32_t* d_idx, double* d_xyz, double* d_a, double* d_b)
+{
+  const int2* ev = reinterpret_cast<const int2*>(c->d_edge_v);
+  if (fast) k_split_fill<KIND, FusedOps><<<tiles, kSThreads, 0, c->stream>>>((int32_t)c->ne, c->d_edge_flags, ev, c->d_vedge, d_off, d_idx, d_xyz, d_a, d_b);
+  else k_split_fill<KIND, StrictOps><<<tiles, kSThreads, 0, c->stream>>>((int32_t)c->ne, c->d_edge_flags, ev, c->d_vedge, d_off, d_idx, d_xyz, d_a, d_b);
+  MAG_CUDA(c, cudaGetLastError());
+  c->n_launches++;
+  return MAG_OK;
+}
+
+struct DevBuf {   // frees on scope exit
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+};
+
+} // namespace
+
+extern "C" {
+
+int mag_element_weights(mag_ctx* c, double w_max, double w_min, int fp_mode, double* out)
+{
+  if (!c) return MAG_ERR_ARG;
+  MAG_CUDA(c, cudaSetDevice(c->device));
+  if (c->kind == MAG_KIND_NONE) return mag_fail(c, MAG_ERR_ARG, "mag_element_weights: no size field set");
+  if (fp_mode != MAG_FP_STRICT && fp_mode != MAG_FP_FAST) return mag_fail(c, MAG_ERR_ARG, "mag_element_weights: bad fp_mode %d", fp_mode);
+  if (c->ntri) return mag_fail(c, MAG_ERR_ARG, "mag_element_weights: 2-D parts are not supported yet");
+  const int64_t nel = c->np + c->npy + c->nt;
+  if (nel == 0) return MAG_OK;
+  if (!c->d_weight) MAG_CUDA(c, cudaMalloc((void**)&c->d_weight, (size_t)nel * sizeof(double)));
+  // layer elements: the reference weighs a prism by its base triangle (maBalance.cc:31-37), which needs the face's own
+  // vertex order; they get 0 here and stay with the reference
+  if (c->np + c->npy) MAG_CUDA(c, cudaMemsetAsync(c->d_weight, 0, (size_t)(c->np + c->npy) * sizeof(double), c->stream));
+  MAG_CUDA(c, cudaMemsetAsync(&c->d_stats->n_eigen_fail, 0, sizeof(unsigned long long), c->stream));
+  if (c->nt) {
+    const bool fast = fp_mode == MAG_FP_FAST;
+    int rc;
+    switch (c->kind) {
+      case MAG_KIND_IDENTITY: rc = launch_weights<MAG_KIND_IDENTITY>(c, w_max, w_min, fast, c->d_weight); break;
+      case MAG_KIND_ISO: rc = launch_weights<MAG_KIND_ISO>(c, w_max, w_min, fast, c->d_weight); break;
+      case MAG_KIND_ANISO: rc = launch_weights<MAG_KIND_ANISO>(c, w_max, w_min, fast, c->d_weight); break;
+      default: rc = launch_weights<MAG_KIND_LOGM>(c, w_max, w_min, fast, c->d_weight); break;
+    }
+    if (rc) return rc;
+  }
+  if (out) MAG_CUDA(c, cudaMemcpyAsync(out, c->d_weight, (size_t)nel * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  MAG_CUDA(c, cudaMemcpyAsync(&c->h_stats->n_eigen_fail, &c->d_stats->n_eigen_fail, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->h_stats->n_eigen_fail)
+    return mag_fail(c, MAG_ERR_EIGEN, "eigenQR failed in %llu blocks of the weight sweep (apf::eigen asserts convergence, apfMatrix.cc:76)", c->h_stats->n_eigen_fail);
+  return MAG_OK;
+}
+
+int mag_split_vertices(mag_ctx* c, int fp_mode, int64_t cap, int64_t* n, int32_t* edge_idx, double* xyz, double* field_a, double* field_b)
+{
+  if (!c) return MAG_ERR_ARG;
+  MAG_CUDA(c, cudaSetDevice(c->device));
+  if (!n) return mag_fail(c, MAG_ERR_ARG, "mag_split_vertices: null count pointer");
+  if (c->kind == MAG_KIND_NONE) return mag_fail(c, MAG_ERR_ARG, "mag_split_vertices: no size field set");
+  if (fp_mode != MAG_FP_STRICT && fp_mode != MAG_FP_FAST) return mag_fail(c, MAG_ERR_ARG, "mag_split_vertices: bad fp_mode %d", fp_mode);
+  *n = 0;
+  if (c->ne == 0) return MAG_OK;
+  const unsigned tiles = (unsigned)((c->ne + kSTile - 1) / kSTile);
+  DevBuf off, tot, didx, dxyz, da, db;
+  MAG_CUDA(c, cudaMalloc(&off.p, (size_t)tiles * 4));
+  MAG_CUDA(c, cudaMalloc(&tot.p, 8));
+  k_split_count<<<tiles, kSThreads, 0, c->stream>>>((int32_t)c->ne, c->d_edge_flags, (int32_t*)off.p);
+  k_split_scan<<<1, 1024, 0, c->stream>>>((int32_t)tiles, (int32_t*)off.p, (long long*)tot.p);
+  MAG_CUDA(c, cudaGetLastError());
+  c->n_launches += 2;
+  long long total = 0;
+  MAG_CUDA(c, cudaMemcpyAsync(&total, tot.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  *n = total;
+  if (total == 0 || (!edge_idx && !xyz && !field_a && !field_b)) return MAG_OK;   // count only
+  if (cap < total) return mag_fail(c, MAG_ERR_ARG, "mag_split_vertices: %lld edges carry SPLIT, buffers hold %lld", total, (long long)cap);
+  const size_t na = c->kind == MAG_KIND_ISO ? 1 : (c->kind == MAG_KIND_ANISO ? 3 : 0);
+  const size_t nb = (c->kind == MAG_KIND_ANISO || c->kind == MAG_KIND_LOGM) ? 9 : 0;
+  MAG_CUDA(c, cudaMalloc(&didx.p, (size_t)total * 4));
+  MAG_CUDA(c, cudaMalloc(&dxyz.p, (size_t)total * 24));
+  if (na) MAG_CUDA(c, cudaMalloc(&da.p, (size_t)total * na * 8));
+  if (nb) MAG_CUDA(c, cudaMalloc(&db.p, (size_t)total * nb * 8));
+  const bool fast = fp_mode == MAG_FP_FAST;
+  int rc;
+  switch (c->kind) {
+    case MAG_KIND_IDENTITY: rc = launch_split_fill<MAG_KIND_IDENTITY>(c, fast, tiles, (int32_t*)off.p, (int32_t*)didx.p, (double*)dxyz.p, (double*)da.p, (double*)db.p); break;
+    case MAG_KIND_ISO: rc = launch_split_fill<MAG_KIND_ISO>(c, fast, tiles, (int32_t*)off.p, (int32_t*)didx.p, (double*)dxyz.p, (double*)da.p, (double*)db.p); break;
+    case MAG_KIND_ANISO: rc = launch_split_fill<MAG_KIND_ANISO>(c, fast, tiles, (int32_t*)off.p, (int32_t*)didx.p, (double*)dxyz.p, (double*)da.p, (double*)db.p); break;
+    default: rc = launch_split_fill<MAG_KIND_LOGM>(c, fast, tiles, (int32_t*)off.p, (int32_t*)didx.p, (double*)dxyz.p, (double*)da.p, (double*)db.p); break;
+  }
+  if (rc) return rc;
+  if (edge_idx) MAG_CUDA(c, cudaMemcpyAsync(edge_idx, didx.p, (size_t)total * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (xyz) MAG_CUDA(c, cudaMemcpyAsync(xyz, dxyz.p, (size_t)total * 24, cudaMemcpyDeviceToHost, c->stream));
+  if (field_a && na) MAG_CUDA(c, cudaMemcpyAsync(field_a, da.p, (size_t)total * na * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (field_b && nb) MAG_CUDA(c, cudaMemcpyAsync(field_b, db.p, (size_t)total * nb * 8, cudaMemcpyDeviceToHost, c->stream));
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return MAG_OK;
+}
+
+} // extern "C"

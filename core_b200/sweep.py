@@ -69,6 +69,7 @@ class Part:
         self._h = h
         self.device = device
         self.nv = self.ne = self.nt = self.np_ = self.npy = self.ntri = 0
+        self._kind = -1
         self._keep = []
 
     # ---- plumbing
@@ -130,20 +131,24 @@ class Part:
         self.synchronize()
 
     def set_size_field_identity(self):
+        self._kind = 0
         self._ck(self._L.mag_set_metric_identity(self._h))
 
     def set_size_field_iso(self, size):
         size = _arr(size, np.float64)
+        self._kind = 1
         self._ck(self._L.mag_set_metric_iso(self._h, _ptr(size)))
         self.synchronize()
 
     def set_size_field_aniso(self, h, R):
         h, R = _arr(h, np.float64), _arr(R, np.float64)
+        self._kind = 2
         self._ck(self._L.mag_set_metric_aniso(self._h, _ptr(h), _ptr(R)))
         self.synchronize()
 
     def set_size_field_logm(self, logM):
         logM = _arr(logM, np.float64)
+        self._kind = 3
         self._ck(self._L.mag_set_metric_logm(self._h, _ptr(logM)))
         self.synchronize()
 
@@ -152,6 +157,7 @@ class Part:
         function (variant 1, maSize.cc:343-346); the log is the host libm's, as in the reference."""
         h, R = _arr(h, np.float64), _arr(R, np.float64)
         out = np.empty((self.nv, 9)) if want_logm else None
+        self._kind = 3
         self._ck(self._L.mag_set_metric_logm_from_frames(self._h, _ptr(h), _ptr(R), int(variant), _ptr(out)))
         return out
 
@@ -185,6 +191,7 @@ class Part:
         n = lambda a, k: 0 if a is None else int(a.numel() if hasattr(a, "numel") else a.size) // k
         self.nv, self.ne, self.nt = n(xyz, 3), n(edge_v, 2), n(tet_v, 4)
         self.np_ = self.npy = self.ntri = 0
+        self._kind = int(kind)
         pv = lambda a: None if a is None else _ptr(a).value
         part = MagHostPart(self.nv, pv(xyz), self.ne, pv(edge_v), self.nt, pv(tet_v), pv(eo), pv(lo), int(kind),
                            pv(fa), pv(fb), pv(ef), pv(lf), int(slice_entities))
@@ -193,6 +200,32 @@ class Part:
         self._ck(self._L.mag_sweep_host(self._h, C.byref(part), C.byref(res), int(ops), float(max_len), float(min_len),
                                         float(good_quality), int(bool(use_max)), int(fp_mode), C.byref(s)))
         return s.as_dict()
+
+    def element_weights(self, refines_left=None, coarsens_left=0, fp_mode=FP_STRICT, dim=3):
+        """ma::getElementWeights (maBalance.cc:83-97): refines_left None = raw SizeField::getWeight, otherwise clamped
+        like clampForIterations with the Adapt's refinesLeft / coarsensLeft."""
+        if refines_left is None:
+            w_max, w_min = float("inf"), float("-inf")
+        else:
+            w_max, w_min = 2.0 ** (dim * refines_left), 4.0 ** (-coarsens_left)
+        out = np.empty(self.nelem, dtype=np.float64)
+        self._ck(self._L.mag_element_weights(self._h, w_max, w_min, int(fp_mode), _ptr(out)))
+        return out
+
+    def split_vertices(self, fp_mode=FP_STRICT):
+        """ma::makeSplitVert for every SPLIT-marked edge, in edge order: (edge_idx, xyz, field_a, field_b) with
+        (field_a, field_b) in the layout of the resident size field (iso: size[n]; aniso: h[n][3], R[n][9];
+        logm: None, logM[n][9]; identity: None, None)."""
+        n = C.c_int64(0)
+        self._ck(self._L.mag_split_vertices(self._h, int(fp_mode), 0, C.byref(n), None, None, None, None))
+        k = n.value
+        idx = np.empty(k, dtype=np.int32)
+        xyz = np.empty((k, 3))
+        fa = {1: np.empty(k), 2: np.empty((k, 3))}.get(self._kind)
+        fb = np.empty((k, 9)) if self._kind in (2, 3) else None
+        if k:
+            self._ck(self._L.mag_split_vertices(self._h, int(fp_mode), k, C.byref(n), _ptr(idx), _ptr(xyz), _ptr(fa), _ptr(fb)))
+        return idx, xyz, fa, fb
 
     def stats(self):
         s = MagStats()

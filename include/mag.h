@@ -179,6 +179,23 @@ typedef struct mag_host_result {           /* any pointer may be NULL */
 int mag_sweep_host(mag_ctx* c, const mag_host_part* in, const mag_host_result* out, uint32_t ops, double max_len,
                    double min_len, double good_quality, int use_max_metric, int fp_mode, mag_stats* stats /* may be NULL */);
 
+/* ---- the sweeps either side of the marking path, over the same resident part ----
+   Predictive load-balance weight of every element, ma::getElementWeights (ma/maBalance.cc:83-97):
+   SizeField::getWeight = measure(element) / parentMeasure (ma/maSize.cc:147-156,225-229; tets: 4-point Gauss rule
+   apf/apfIntegrate.cc:328-342 with getTransform at every point), clamped to [w_min, w_max] as clampForIterations does
+   (w_max = 2^(dim * refinesLeft), w_min = 4^(-coarsensLeft), maBalance.cc:41-52; pass +-HUGE_VAL for the raw weight).
+   out [np+npy+nt] host (may be NULL: the weights stay on the device); prisms / pyramids get 0 (the reference weighs
+   a prism by its base triangle, which needs that face's own vertex order).  Synchronous. */
+int mag_element_weights(mag_ctx* c, double w_max, double w_min, int fp_mode, double* out);
+/* Size-field transfer to the vertices that will split the SPLIT-marked edges (ma::makeSplitVert, ma/maRefine.cc:129-151;
+   SizeField::interpolate, ma/maSize.cc:414-429,523-534): for every edge whose resident flag word carries MAG_SPLIT, in
+   edge order, the edge index, the position of the new vertex (xi = 0) and the size-field values it receives --
+   iso: field_a = size[n]; aniso: field_a = h[n][3], field_b = R[n][9] (orthogonalised frame); logm: field_b = logM[n][9].
+   *n receives the number of SPLIT edges; with all output pointers NULL the call only counts.  cap = capacity of the
+   output arrays in vertices. */
+int mag_split_vertices(mag_ctx* c, int fp_mode, int64_t cap, int64_t* n, int32_t* edge_idx, double* xyz,
+                       double* field_a, double* field_b);
+
 /* the logM vertex field from sizes + frames, computed on the host exactly as the reference does (libm log):
    variant 0 = LogAnisoSizeField::init from fields, log(1/h/h)   (ma/maSize.cc:491-499)
    variant 1 = LogMEval from a user function, -2*log(h)          (ma/maSize.cc:343-346)

@@ -542,6 +542,104 @@ int mao_pyramid_ok(const double* xyz, const int32_t* pv, int* good_rotation)
   return all_good;
 }
 
+/* ----------------------------------------------------- predictive element weight
+ * ma::getElementWeight, maBalance.cc:74-81: getSizeWeight (:21-39) -> SizeField::getWeight =
+ * measure(e) / parentMeasure[type] (maSize.cc:225-229, parentMeasure[TET] = 1.0/6.0 :147-156), then
+ * clampForIterations (:41-52).  measure(tet): SizeFieldIntegrator with order 2 -> TetrahedronIntegration::N2,
+ * 4 points, weights 0.25/6.0 (apfIntegrate.cc:328-342); at each point dV2 = det(J*Q(xi)) with Q from
+ * getTransform at the point (tet shape values apfShape.cc:203-210).  IdentitySizeField::getWeight = 1.0
+ * (maSize.cc:89-92). */
+double mao_tet_weight(int kind, const double* xyz, const double* ma, const double* mb,
+                      const int32_t* tv, int* status)
+{
+  if (kind == MAO_IDENTITY) return 1.0;
+  metric_t mt = {kind, ma, mb};
+  static const double P[4][3] = {
+    {0.138196601125011, 0.138196601125011, 0.138196601125011},
+    {0.585410196624969, 0.138196601125011, 0.138196601125011},
+    {0.138196601125011, 0.585410196624969, 0.138196601125011},
+    {0.138196601125011, 0.138196601125011, 0.585410196624969}};
+  static const double g[4][3] = {{-1, -1, -1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  const double* x[4];
+  for (int i = 0; i < 4; ++i) x[i] = xyz + 3 * (size_t)tv[i];
+  double measurement = 0;
+  for (int p = 0; p < 4; ++p) {
+    const double* xi = P[p];
+    double N[4] = {1 - xi[0] - xi[1] - xi[2], xi[0], xi[1], xi[2]};
+    double Q[3][3];
+    int rc = transform_at(&mt, tv, N, 4, Q);
+    if (rc != 1 && status) *status = rc;
+    /* apf::getJacobian at the point (constant for a linear tet, recomputed per point by the reference) */
+    double J[3][3];
+    for (int i = 0; i < 3; ++i) for (int c = 0; c < 3; ++c) J[i][c] = x[0][c] * g[0][i];
+    for (int n = 1; n < 4; ++n)
+      for (int i = 0; i < 3; ++i) for (int c = 0; c < 3; ++c) J[i][c] = J[i][c] + x[n][c] * g[n][i];
+    double JQ[3][3];
+    matmul3((const double(*)[3])J, (const double(*)[3])Q, JQ);
+    double dV2 = mao_det3((const double(*)[3])JQ);
+    measurement += (0.25 / 6.0) * dV2;
+  }
+  return measurement / (1.0 / 6.0);
+}
+/* clamp of maBalance.cc:14-19 */
+double mao_clamp(double x, double max, double min)
+{
+  if (x > max) return max;
+  if (x < min) return min;
+  return x;
+}
+/* weights of nt tets; w_max = pow(2, dim*refinesLeft), w_min = pow(4, -coarsensLeft) (maBalance.cc:41-52),
+   pass +-HUGE_VAL for the raw SizeField::getWeight */
+int mao_tet_weights(int kind, const double* xyz, const double* ma, const double* mb,
+                    int64_t nt, const int32_t* tet_v, double w_max, double w_min, double* out)
+{
+  int status = 1;
+  for (int64_t t = 0; t < nt; ++t)
+    out[t] = mao_clamp(mao_tet_weight(kind, xyz, ma, mb, tet_v + 4 * t, &status), w_max, w_min);
+  return status;
+}
+
+/* ----------------------------------------------------- size-field transfer to split vertices
+ * ma::makeSplitVert, maRefine.cc:129-151: the new vertex sits at xi = 0 of the edge:
+ * point = mapLocalToGlobal (coordinate interpolation, N = (0.5, 0.5), apfShape.cc:123-124), then
+ * SizeField::interpolate(edge element, xi, vert):
+ *   AnisoSizeField (maSize.cc:414-429): h = interpolated sizes, R = orthogonalizeR(interpolated frames), all 9 entries
+ *   LogAnisoSizeField (:523-534): logM = interpolated logM
+ *   Iso (IsoSizeField is an AnisoSizeField over h=(s,s,s), R=I): the interpolated scalar
+ * out_a / out_b follow the (ma, mb) layout of the kind. */
+void mao_split_vertex(int kind, const double* xyz, const double* ma, const double* mb, const int32_t* ev,
+                      double* out_xyz, double* out_a, double* out_b)
+{
+  const double N[2] = {(1.0 - 0.0) / 2.0, (1.0 + 0.0) / 2.0};
+  const double* node[2];
+  node[0] = xyz + 3 * (size_t)ev[0]; node[1] = xyz + 3 * (size_t)ev[1];
+  interp(node, N, 2, 3, out_xyz);
+  if (kind == MAO_ISO) {
+    node[0] = ma + ev[0]; node[1] = ma + ev[1];
+    interp(node, N, 2, 1, out_a);
+  } else if (kind == MAO_ANISO) {
+    node[0] = ma + 3 * (size_t)ev[0]; node[1] = ma + 3 * (size_t)ev[1];
+    interp(node, N, 2, 3, out_a);
+    double R[3][3], RT[3][3];
+    node[0] = mb + 9 * (size_t)ev[0]; node[1] = mb + 9 * (size_t)ev[1];
+    interp(node, N, 2, 9, &R[0][0]);
+    transpose3((const double(*)[3])R, RT);
+    gram_schmidt_rows(RT);
+    transpose3((const double(*)[3])RT, R);
+    memcpy(out_b, R, sizeof(R));
+  } else if (kind == MAO_LOGM) {
+    node[0] = mb + 9 * (size_t)ev[0]; node[1] = mb + 9 * (size_t)ev[1];
+    interp(node, N, 2, 9, out_b);
+  }
+}
+void mao_split_vertices(int kind, const double* xyz, const double* ma, const double* mb, int64_t n,
+                        const int32_t* edge_v, double* out_xyz, double* out_a, double* out_b)
+{
+  const int sa = kind == MAO_ISO ? 1 : 3;
+  for (int64_t i = 0; i < n; ++i)
+    mao_split_vertex(kind, xyz, ma, mb, edge_v + 2 * i, out_xyz + 3 * i, out_a ? out_a + sa * i : 0, out_b ? out_b + 9 * i : 0);
+}
+
 /* ----------------------------------------------------- sweeps over arrays */
 int mao_edge_lengths(int kind, const double* xyz, const double* ma, const double* mb,
                      int64_t ne, const int32_t* edge_v, double* out)

@@ -34,6 +34,15 @@ int mao_tri_qualities(int kind, const double* xyz, const double* ma, const doubl
 int mao_prism_ok(const double* xyz, const int32_t* pv, int* good_codes);
 int mao_pyramid_ok(const double* xyz, const int32_t* pv, int* good_rotation);
 
+double mao_tet_weight(int kind, const double* xyz, const double* ma, const double* mb, const int32_t* tv, int* status);
+double mao_clamp(double x, double max, double min);
+int mao_tet_weights(int kind, const double* xyz, const double* ma, const double* mb,
+                    int64_t nt, const int32_t* tet_v, double w_max, double w_min, double* out);
+void mao_split_vertex(int kind, const double* xyz, const double* ma, const double* mb, const int32_t* ev,
+                      double* out_xyz, double* out_a, double* out_b);
+void mao_split_vertices(int kind, const double* xyz, const double* ma, const double* mb, int64_t n,
+                        const int32_t* edge_v, double* out_xyz, double* out_a, double* out_b);
+
 int mao_edge_lengths(int kind, const double* xyz, const double* ma, const double* mb,
                      int64_t ne, const int32_t* edge_v, double* out);
 int mao_tet_qualities(int kind, const double* xyz, const double* ma, const double* mb,

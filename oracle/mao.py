@@ -46,6 +46,8 @@ def lib():
         L.mao_pyramid_ok.argtypes = [vp, vp, vp]
         L.mao_mark_entities.restype = i64
         L.mao_mark_entities.argtypes = [i64, vp, C.c_int, f64, vp, vp, i32, i32, i32]
+        L.mao_tet_weights.argtypes = [C.c_int, vp, vp, vp, i64, vp, f64, f64, vp]
+        L.mao_split_vertices.argtypes = [C.c_int, vp, vp, vp, i64, vp, vp, vp, vp]
         L.mao_min_quality.restype = f64
         L.mao_min_quality.argtypes = [i64, vp]
         L.mao_max_length.restype = f64
@@ -107,6 +109,35 @@ def tet_qualities(kind, xyz, ma, mb, tet_v, use_max=True):
     rc = lib().mao_tet_qualities(kind, _p(xyz), _p(ma), _p(mb), nt, _p(tet_v), int(use_max), _p(out))
     assert rc == 1
     return out
+
+
+def tet_weights(kind, xyz, ma, mb, tet_v, refines_left=None, coarsens_left=0, dim=3):
+    """ma::getElementWeight restated (maBalance.cc:21-52,74-81); refines_left None = raw SizeField::getWeight."""
+    xyz, ma, mb, tet_v = _f64(xyz), _f64(ma), _f64(mb), _i32(tet_v)
+    nt = tet_v.size // 4
+    out = np.zeros(nt)
+    w_max, w_min = weight_clamps(refines_left, coarsens_left, dim)
+    rc = lib().mao_tet_weights(kind, _p(xyz), _p(ma), _p(mb), nt, _p(tet_v), w_max, w_min, _p(out))
+    assert rc == 1
+    return out
+
+
+def weight_clamps(refines_left, coarsens_left, dim=3):
+    """clampForIterations bounds (maBalance.cc:41-52)."""
+    if refines_left is None:
+        return float("inf"), float("-inf")
+    return 2.0 ** (dim * refines_left), 4.0 ** (-coarsens_left)
+
+
+def split_vertices(kind, xyz, ma, mb, edge_v):
+    """ma::makeSplitVert restated: (xyz, a, b) of the vertex splitting each edge, (a, b) in the kind's (ma, mb) layout."""
+    xyz, ma, mb, edge_v = _f64(xyz), _f64(ma), _f64(mb), _i32(edge_v)
+    n = edge_v.size // 2
+    oxyz = np.zeros((n, 3))
+    oa = np.zeros(n) if kind == ISO else (np.zeros((n, 3)) if kind == ANISO else None)
+    ob = np.zeros((n, 9)) if kind in (ANISO, LOGM) else None
+    lib().mao_split_vertices(kind, _p(xyz), _p(ma), _p(mb), n, _p(edge_v), _p(oxyz), _p(oa), _p(ob))
+    return oxyz, oa, ob
 
 
 def tri_qualities(kind, xyz, ma, mb, tri_v, use_max=True):

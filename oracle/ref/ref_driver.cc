@@ -41,6 +41,8 @@ long markEdgesToCollapse(Adapt* a);
 int markBadQuality(Adapt* a);
 void unMarkBadQuality(Adapt* a);
 double getMinQuality(Adapt* a);
+/* maBalance.cc:74-81, external linkage, no header */
+double getElementWeight(Adapt* a, Entity* e);
 }
 
 namespace {
@@ -426,6 +428,69 @@ double refo_avg_edge_length(void* hd)
 {
   Ref* r = (Ref*)hd;
   return ma::getAverageEdgeLength(r->m);
+}
+
+/* ---- predictive element weights (maBalance.cc:74-97): raw[i] = SizeField::getWeight(element i) and
+   clamped[i] = ma::getElementWeight(a, element i) with the Adapt's refinesLeft / coarsensLeft set as given.
+   Simplex elements only; others get 0.  Either output may be null. */
+int refo_weights(void* hd, int refinesLeft, int coarsensLeft, double* raw, double* clamped)
+{
+  Ref* r = (Ref*)hd; apf::Mesh2* m = r->m;
+  if (!r->sf) return 1;
+  if (clamped) {
+    if (r->a) { delete r->a; r->a = 0; }
+    if (r->in) { delete r->in; r->in = 0; }
+    r->in = ma::makeAdvanced(ma::configureIdentity(m, r->sf));
+    r->a = new ma::Adapt(r->in);
+    r->a->refinesLeft = refinesLeft;
+    r->a->coarsensLeft = coarsensLeft;
+  }
+  apf::MeshIterator* it = m->begin(m->getDimension()); apf::MeshEntity* e; int64_t k = 0;
+  while ((e = m->iterate(it))) {
+    bool simplex = apf::isSimplex(m->getType(e));
+    if (raw) raw[k] = simplex ? r->sf->getWeight(e) : 0;
+    if (clamped) clamped[k] = simplex ? ma::getElementWeight(r->a, e) : 0;
+    ++k;
+  }
+  m->end(it);
+  return 0;
+}
+
+/* ---- what ma::makeSplitVert (maRefine.cc:129-151) gives the vertex that splits each listed edge: its position
+   (apf::mapLocalToGlobal at xi = 0) and the size-field values SizeField::interpolate writes on it.  A scratch vertex
+   is created for each edge, read back and destroyed again.  Size-field kinds 2 (fields "refo_sizes"/"refo_frames":
+   out_a = h[3], out_b = R[9]) and 3 / 5 (field "ma_logM": out_b = logM[9]). */
+int refo_split_vertices(void* hd, int64_t n, const int64_t* edges, double* out_xyz, double* out_a, double* out_b)
+{
+  Ref* r = (Ref*)hd; apf::Mesh2* m = r->m;
+  if (!r->sf) return 1;
+  apf::Field* fh = m->findField("refo_sizes");
+  apf::Field* fR = m->findField("refo_frames");
+  apf::Field* fM = m->findField("ma_logM");
+  if (!(fh && fR) && !fM) return 2;
+  ma::Vector xi(0, 0, 0);
+  for (int64_t i = 0; i < n; ++i) {
+    apf::MeshEntity* e = apf::getMdsEntity(m, 1, (int)edges[i]);
+    apf::MeshElement* me = apf::createMeshElement(m, e);
+    ma::Vector point;
+    apf::mapLocalToGlobal(me, xi, point);
+    apf::MeshEntity* v = m->createVert(m->toModel(e));
+    m->setPoint(v, 0, point);
+    r->sf->interpolate(me, xi, v);
+    for (int c = 0; c < 3; ++c) out_xyz[3*i+c] = point[c];
+    if (fM) {
+      apf::Matrix3x3 M; apf::getMatrix(fM, v, 0, M);
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) out_b[9*i+3*a+b] = M[a][b];
+    } else {
+      apf::Vector3 h; apf::getVector(fh, v, 0, h);
+      apf::Matrix3x3 M; apf::getMatrix(fR, v, 0, M);
+      for (int c = 0; c < 3; ++c) out_a[3*i+c] = h[c];
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) out_b[9*i+3*a+b] = M[a][b];
+    }
+    apf::destroyMeshElement(me);
+    m->destroy(v);
+  }
+  return 0;
 }
 
 /* apf::eigen on one 3x3 (mth::eigenQR), for the known-answer vectors of

@@ -55,6 +55,8 @@ def lib():
         L.refo_avg_edge_length.restype = C.c_double
         L.refo_avg_edge_length.argtypes = [C.c_void_p]
         L.refo_eigen.argtypes = [C.c_void_p] * 3
+        L.refo_weights.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.refo_split_vertices.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -170,6 +172,25 @@ class RefMesh:
         codes = np.zeros(self.nelem, dtype=np.int32)
         lib().refo_layer_ok(self.h, _p(ok), _p(codes))
         return ok, codes
+
+    def weights(self, refines_left=None, coarsens_left=0):
+        """SizeField::getWeight per element (refines_left None) or ma::getElementWeight with the given iteration
+        counts (maBalance.cc:41-52,74-81)."""
+        out = np.zeros(self.nelem)
+        if refines_left is None:
+            assert lib().refo_weights(self.h, 0, 0, _p(out), None) == 0
+        else:
+            assert lib().refo_weights(self.h, int(refines_left), int(coarsens_left), None, _p(out)) == 0
+        return out
+
+    def split_vertices(self, edges):
+        """Position and size-field values ma::makeSplitVert gives the vertex splitting each listed edge."""
+        edges = np.ascontiguousarray(edges, dtype=np.int64)
+        n = len(edges)
+        xyz, a, b = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 9))
+        rc = lib().refo_split_vertices(self.h, n, _p(edges), _p(xyz), _p(a), _p(b))
+        assert rc == 0, rc
+        return xyz, a, b
 
     def max_edge_length(self):
         return lib().refo_max_edge_length(self.h)

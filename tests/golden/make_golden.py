@@ -6,7 +6,8 @@ built from /root/reference by oracle/ref/Makefile).  Run in the build container 
 Every array below except the inputs (coordinates jitter, size fields) is an OUTPUT OF THE REFERENCE:
 apf::makeMdsBox / apf::buildElement entity order, ma::SizeField::measure, ma::measureElementQuality,
 ma::markEdgesToSplit / markEdgesToCollapse / markBadQuality / getMinQuality / getMaximumEdgeLength,
-ma::isPrismOk / isPyramidOk, the ma_logM field, apf::eigen.  The fixtures are small (a few 100 kB) and
+ma::isPrismOk / isPyramidOk, the ma_logM field, apf::eigen, ma::getElementWeight, ma::makeSplitVert's
+size-field transfer.  The fixtures are small (a few 100 kB) and
 committed, because /root/reference does not exist on the GPU box.
 """
 import os
@@ -52,6 +53,17 @@ def case(name, m, kind, h=None, R=None, good_quality=-1.0, edge_flags=None, elem
     out["counts"] = np.array([r["n_split"], r["n_collapse"], r["n_bad"]], dtype=np.int64)
     out["min_q"] = np.float64(r["min_q"])
     out["max_len"] = np.float64(m.max_edge_length())
+    if simplex_only and np.all(et == refo.TET):
+        # ma::getElementWeight (raw SizeField::getWeight, and clamped with refinesLeft = 0,
+        # coarsensLeft = 1 -> [0.25, 1]) and what ma::makeSplitVert gives the vertex splitting every SPLIT-marked edge
+        out["weights_raw"] = m.weights()
+        out["weights_r0_c1"] = m.weights(0, 1)
+        if kind in (refo.KIND_ANISO_FIELD, refo.KIND_LOG_FIELD):   # stored vertex fields (user-function fields hold no data)
+            se = np.nonzero(r["edge_flags"] & 1)[0]
+            sx, sa, sb = m.split_vertices(se)
+            out["split_edges"], out["split_xyz"], out["split_b"] = se.astype(np.int32), sx, sb
+            if kind == refo.KIND_ANISO_FIELD:
+                out["split_a"] = sa
     if not simplex_only:
         ok, codes = m.layer_ok()
         out["layer_ok"], out["layer_codes"] = ok, codes

@@ -102,6 +102,49 @@ def test_golden_reference_vectors(cb, name, mode):
     p.close()
 
 
+@pytest.mark.parametrize("name", [n for n in util.golden_cases() if "weights_raw" in util.load(n)])
+def test_weights_and_split_vertices_golden(cb, name):
+    """SURVEY 8f rows on the device against the compiled reference's outputs: ma::getElementWeight (raw and clamped)
+    and ma::makeSplitVert's transfer (position + size-field values of the vertex splitting every SPLIT edge)."""
+    from oracle import mao
+    g = util.load(name)
+    kind, ma, mb = util.metric_arrays(g)
+    _, _, tet_v = util.split_elements(g)
+    p = cb.Part(0)
+    p.set_mesh(g["xyz"], g["edge_v"], tet_v)
+    util.set_part_metric(p, kind, ma, mb)
+    exact = kind != mao.LOGM          # LogAniso: CUDA exp() vs glibc exp() (see MAG_FP_STRICT in mag.h)
+    for mode in (cb.FP_STRICT, cb.FP_FAST):
+        w = p.element_weights(fp_mode=mode)
+        wc = p.element_weights(0, 1, fp_mode=mode)
+        if exact and mode == cb.FP_STRICT:
+            assert np.array_equal(w, g["weights_raw"]) and np.array_equal(wc, g["weights_r0_c1"])
+        else:
+            assert util.rel_err(w, g["weights_raw"]) < TOL and util.rel_err(wc, g["weights_r0_c1"]) < TOL
+    if "split_edges" in g:
+        gq = float(g["good_quality"])
+        p.set_flags(g["edge_flags_in"], g["elem_flags_in"])
+        p.sweep(cb.OP_MARK_SPLIT | cb.OP_MARK_COLLAPSE, fp_mode=cb.FP_STRICT)
+        ef, _ = p.flags()
+        for mode in (cb.FP_STRICT, cb.FP_FAST):
+            idx, sx, sa, sb = p.split_vertices(fp_mode=mode)
+            assert np.array_equal(idx, np.nonzero(ef & cb.SPLIT)[0])        # edge order, every SPLIT edge once
+            if kind != mao.LOGM:
+                assert np.array_equal(idx, g["split_edges"])
+            sel = np.searchsorted(g["split_edges"], idx)
+            ok = (sel < len(g["split_edges"])) & (g["split_edges"][np.minimum(sel, len(g["split_edges"]) - 1)] == idx)
+            assert ok.mean() > 0.99                                            # LogAniso: flags may differ in the listed band
+            sel, keep = sel[ok], np.nonzero(ok)[0]
+            if mode == cb.FP_STRICT:
+                assert np.array_equal(sx[keep], g["split_xyz"][sel]) and np.array_equal(sb[keep], g["split_b"][sel])
+                if kind == mao.ANISO:
+                    assert np.array_equal(sa[keep], g["split_a"][sel])
+            else:
+                assert util.rel_err(sx[keep], g["split_xyz"][sel]) < TOL
+                assert np.max(np.abs(sb[keep] - g["split_b"][sel])) < TOL * max(1.0, np.max(np.abs(g["split_b"])))
+    p.close()
+
+
 def test_unsafe_prisms(cb):
     g = util.load("mixed5_unsafe_layer")
     prism_v, _, tet_v = util.split_elements(g)

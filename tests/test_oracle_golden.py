@@ -43,6 +43,19 @@ def test_oracle_matches_reference_golden(name, built):
     if "qualities" in g:
         assert mao.min_quality(q) == float(g["min_q"])
     assert mao.max_length(L) == float(g["max_len"])
+    # SURVEY 8f rows, pinned the same way: ma::getElementWeight and ma::makeSplitVert's size-field transfer
+    if "weights_raw" in g:
+        assert np.array_equal(mao.tet_weights(kind, g["xyz"], ma, mb, tet_v), g["weights_raw"])
+        assert np.array_equal(mao.tet_weights(kind, g["xyz"], ma, mb, tet_v, 0, 1), g["weights_r0_c1"])
+        if kind != mao.IDENTITY:
+            assert g["weights_r0_c1"].min() == 0.25 or g["weights_r0_c1"].max() == 1.0   # the clamp is exercised
+    if "split_edges" in g:
+        se = g["split_edges"]
+        assert np.array_equal(se, np.nonzero(g["edge_flags_out"] & mao.SPLIT)[0])
+        sx, sa, sb = mao.split_vertices(kind, g["xyz"], ma, mb, g["edge_v"][se])
+        assert np.array_equal(sx, g["split_xyz"]) and np.array_equal(sb, g["split_b"])
+        if kind == mao.ANISO:
+            assert np.array_equal(sa, g["split_a"])
     if nns:
         ok, codes = mao.prism_ok(g["xyz"], prism_v)
         assert np.array_equal(ok, g["layer_ok"][:len(prism_v)])
