@@ -16,6 +16,11 @@
 #include <cstdlib>
 #include <cmath>
 
+namespace ma {
+/* external linkage in the reference, declared in no installed header (maBalance.cc:74-81) */
+double getElementWeight(Adapt* a, Entity* e);
+}
+
 namespace mag {
 
 static void fail(mag_ctx* c, const char* what, int rc)
@@ -41,6 +46,9 @@ struct Access {
     g->fSizes = sizes; g->fFrames = frames; g->fIso = iso; g->fnAniso = fa; g->fnIso = fi;
   }
   static double lengthAt(GpuSizeField* g, size_t k) { return g->lengths[k]; }
+  static bool isDirty(GpuSizeField* g) { return g->dirty; }
+  static int fpMode(GpuSizeField* g) { return g->fpMode; }
+  static int tetSlotOf(GpuSizeField* g, ma::Entity* e) { return g->tetSlot[apf::getMdsIndex(g->mesh, e)]; }
   static double qualityOf(GpuSizeField* g, ma::Entity* e) { return g->qualities[g->tetSlot[apf::getMdsIndex(g->mesh, e)]]; }
   static bool serveQuality(GpuSizeField* g, ma::Entity* e, double goodQuality, double& q)
   {
@@ -393,6 +401,29 @@ void getLinearQualitiesInMetricSpace(ma::Mesh* m, ma::SizeField* sf, std::vector
     out.push_back(cbrt(Access::qualityOf(g, e)));
   }
   m->end(it);
+}
+
+/* ma::getElementWeights (maBalance.cc:83-97): the tag "ma_weight" on every element.  Tets come from one device sweep
+   (mag_element_weights, clamped like clampForIterations with the Adapt's iteration counters); layer elements go
+   through the reference's own per-entity path (their weight is a base-triangle measure, maBalance.cc:31-37). */
+ma::Tag* getElementWeights(ma::Adapt* a)
+{
+  GpuSizeField* g = gpuField(a->sizeField);
+  ma::Mesh* m = a->mesh;
+  if (Access::isDirty(g)) g->refresh(a->input->goodQuality);
+  const int dim = m->getDimension();
+  const double w_max = pow(2.0, dim * (a->refinesLeft)), w_min = pow(4.0, -(a->coarsensLeft));
+  std::vector<double> w(m->count(dim));
+  MAG_DO(g->ctx, mag_element_weights(g->ctx, w_max, w_min, Access::fpMode(g), w.data()));
+  ma::Tag* weights = m->createDoubleTag("ma_weight", 1);
+  apf::MeshIterator* it = m->begin(dim);
+  ma::Entity* e;
+  while ((e = m->iterate(it))) {
+    double weight = m->getType(e) == apf::Mesh::TET ? w[Access::tetSlotOf(g, e)] : ma::getElementWeight(a, e);
+    m->setDoubleTag(e, weights, &weight);
+  }
+  m->end(it);
+  return weights;
 }
 
 /* ------------------------------------------------------------------ shape handler */

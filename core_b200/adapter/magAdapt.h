@@ -10,6 +10,7 @@
 //   ma::getMinQuality(Adapt*)         ma/maShape.cc:152     ->  mag::getMinQuality(Adapt*)
 //   ma::getMaximumEdgeLength(m, sf)   ma/maSize.cc:673      ->  mag::getMaximumEdgeLength(m, sf)
 //   ma::getEdgeLengthsInMetricSpace / getLinearQualitiesInMetricSpace   ma/maStats.cc:12-45  ->  mag::... (same vectors)
+//   ma::getElementWeights(Adapt*)     ma/maBalance.cc:83    ->  mag::getElementWeights(Adapt*)  (same "ma_weight" tag)
 //   ma::getShapeHandler(Adapt*)       ma/maShapeHandler.cc  ->  mag::shapeHandler  (an ma::ShapeHandlerFunction for Input::shapeHandler)
 //
 // mag::GpuSizeField IS an ma::SizeField: it can be put in ma::Input::sizeField and the UNMODIFIED reference keeps
@@ -92,6 +93,9 @@ double getMinQuality(ma::Adapt* a);
 double getMaximumEdgeLength(ma::Mesh* m, ma::SizeField* sf);
 void getEdgeLengthsInMetricSpace(ma::Mesh* m, ma::SizeField* sf, std::vector<double>& lengths);
 void getLinearQualitiesInMetricSpace(ma::Mesh* m, ma::SizeField* sf, std::vector<double>& qualities);
+
+/* ma::getElementWeights (ma/maBalance.cc:83-97): creates and fills the "ma_weight" element tag; the caller destroys it */
+ma::Tag* getElementWeights(ma::Adapt* a);
 
 /* ma::ShapeHandlerFunction: in->shapeHandler = mag::shapeHandler; getQuality(e) is then served from the device sweep */
 ma::ShapeHandler* shapeHandler(ma::Adapt* a);

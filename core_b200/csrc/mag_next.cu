@@ -4,8 +4,8 @@
 //                         SizeField::getWeight = measure(element) / parentMeasure (ma/maSize.cc:147-156,225-229)
 //   mag_split_vertices    position and size-field values of the vertex that will split every SPLIT-marked edge
 //                         ma::makeSplitVert (ma/maRefine.cc:129-151), SizeField::interpolate (ma/maSize.cc:414-429,523-534)
-// Both follow the reference's operation order through the arithmetic policies of mag_math.cuh (StrictOps: bit-identical;
-// FusedOps: FMA-contracted, within 1e-12).
+// MAG_FP_STRICT follows the reference's operation order (StrictOps of mag_math.cuh: bit-identical); MAG_FP_FAST uses
+// algebraically equivalent, cheaper forms (within 1e-12 relative).
 #include "mag_internal.h"
 #include "mag_layout.cuh"
 #include "mag_math.cuh"
@@ -83,14 +83,60 @@ __device__ __forceinline__ double tet_weight(const double* __restrict__ vedge, c
   return MM::div(measurement, 1.0 / 6.0);   // parentMeasure[TET]
 }
 
-template <int KIND, class OPS>
-__global__ void __launch_bounds__(kWThreads)
+// MAG_FP_FAST: det(J Q) = det(J) det(Q), and det(Q) needs no frame at all: Gram-Schmidt yields a rotation (maSize.cc:116,
+// 138), so det Q = 1 / (h0 h1 h2) for AnisoSizeField, exp(trace(logM) / 2) for LogAnisoSizeField (the eigenvalues of the
+// interpolated logM sum to its trace, which interpolates linearly) and 1 / h^3 for an isotropic field:
+//     weight = 0.25 det(J) sum_p det Q(xi_p)
+// Only the chunks holding the positions and the sizes / the diagonal of logM are gathered.
+template <int KIND>
+__device__ __forceinline__ double tet_weight_fast(const double* __restrict__ vedge, const int4& tv)
+{
+  if (KIND == MAG_KIND_IDENTITY) return 1.0;
+  constexpr int K = (KIND == MAG_KIND_ISO) ? 2 : 6;
+  const int32_t vid[4] = {tv.x & kVidMask, tv.y, tv.z, tv.w};
+  double x[4][3], s[4][3];
+#pragma unroll
+  for (int n = 0; n < 4; ++n) {
+    const double2* p = chunk_ptr<K>(vedge, 0, vid[n]);
+    const double2 c0 = __ldg(p), c1 = __ldg(p + kVB);
+    x[n][0] = c0.x; x[n][1] = c0.y; x[n][2] = c1.x;
+    s[n][0] = c1.y;                                   // iso: s; aniso: h0; logm: M00
+    if (KIND == MAG_KIND_ANISO) { const double2 c2 = __ldg(p + 2 * kVB); s[n][1] = c2.x; s[n][2] = c2.y; }
+    if (KIND == MAG_KIND_LOGM) { s[n][0] += __ldg(p + 3 * kVB).y + __ldg(p + 5 * kVB).y; }   // trace: M00 + M11 + M22
+  }
+  double e[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) e[i][c] = x[i + 1][c] - x[0][c];
+  const double detJ = e[0][0] * (e[1][1] * e[2][2] - e[1][2] * e[2][1]) - e[0][1] * (e[1][0] * e[2][2] - e[1][2] * e[2][0]) +
+                      e[0][2] * (e[1][0] * e[2][1] - e[1][1] * e[2][0]);
+  constexpr double A = 0.138196601125011, B = 0.585410196624969;
+  double sum = 0.0;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const double xi0 = p == 1 ? B : A, xi1 = p == 2 ? B : A, xi2 = p == 3 ? B : A;
+    const double Ns[4] = {1 - xi0 - xi1 - xi2, xi0, xi1, xi2};
+    constexpr int NC = KIND == MAG_KIND_ANISO ? 3 : 1;
+    double c[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) c[i] = s[0][i] * Ns[0] + s[1][i] * Ns[1] + s[2][i] * Ns[2] + s[3][i] * Ns[3];
+    if (KIND == MAG_KIND_ISO) sum += 1.0 / (c[0] * c[0] * c[0]);
+    else if (KIND == MAG_KIND_ANISO) sum += 1.0 / (c[0] * c[1] * c[2]);
+    else sum += exp(0.5 * c[0]);
+  }
+  return 0.25 * detJ * sum;
+}
+
+template <int KIND, bool FAST>
+__global__ void __launch_bounds__(FAST ? 256 : kWThreads)
 k_tet_weights(int32_t nt, int32_t elem_off, const int4* __restrict__ tet_v, const double* __restrict__ vedge,
               double w_max, double w_min, double* __restrict__ weight, MagDevStats* st)
 {
   int eig = 0;
-  for (int32_t t = blockIdx.x * kWThreads + threadIdx.x; t < nt; t += gridDim.x * kWThreads) {
-    double w = tet_weight<KIND, OPS>(vedge, __ldg(tet_v + t), &eig);
+  constexpr int T = FAST ? 256 : kWThreads;
+  for (int32_t t = blockIdx.x * T + threadIdx.x; t < nt; t += gridDim.x * T) {
+    double w = FAST ? tet_weight_fast<KIND>(vedge, __ldg(tet_v + t)) : tet_weight<KIND, StrictOps>(vedge, __ldg(tet_v + t), &eig);
     // clamp of maBalance.cc:14-19
     if (w > w_max) w = w_max;
     else if (w < w_min) w = w_min;
@@ -102,12 +148,13 @@ k_tet_weights(int32_t nt, int32_t elem_off, const int4* __restrict__ tet_v, cons
 template <int KIND>
 int launch_weights(mag_ctx* c, double w_max, double w_min, bool fast, double* d_w)
 {
-  const int64_t blocks = (c->nt + kWThreads - 1) / kWThreads;
-  const unsigned g = (unsigned)(blocks < (int64_t)c->n_sms * 16 ? blocks : (int64_t)c->n_sms * 16);
+  const int T = fast ? 256 : kWThreads;
+  const int64_t blocks = (c->nt + T - 1) / T;
+  const unsigned g = (unsigned)(blocks < (int64_t)c->n_sms * 32 ? blocks : (int64_t)c->n_sms * 32);
   const int4* tv = reinterpret_cast<const int4*>(c->d_tet_v);
   const int32_t off = (int32_t)(c->np + c->npy);
-  if (fast) k_tet_weights<KIND, FusedOps><<<g, kWThreads, 0, c->stream>>>((int32_t)c->nt, off, tv, c->d_vedge, w_max, w_min, d_w, c->d_stats);
-  else k_tet_weights<KIND, StrictOps><<<g, kWThreads, 0, c->stream>>>((int32_t)c->nt, off, tv, c->d_vedge, w_max, w_min, d_w, c->d_stats);
+  if (fast) k_tet_weights<KIND, true><<<g, 256, 0, c->stream>>>((int32_t)c->nt, off, tv, c->d_vedge, w_max, w_min, d_w, c->d_stats);
+  else k_tet_weights<KIND, false><<<g, kWThreads, 0, c->stream>>>((int32_t)c->nt, off, tv, c->d_vedge, w_max, w_min, d_w, c->d_stats);
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;
   return MAG_OK;

@@ -29,6 +29,7 @@ namespace ma {
 long markEdgesToCollapse(Adapt* a);
 int markBadQuality(Adapt* a);
 double getMinQuality(Adapt* a);
+double getElementWeight(Adapt* a, Entity* e);   /* maBalance.cc:74-81 */
 }
 
 namespace {
@@ -122,6 +123,7 @@ extern "C" int mag_adapter_check(int n, int log_interp, int fp_mode, double jitt
   }
   const double hbar = 1.0 / n;
   Marks R, A, B;
+  long weight_diffs = 0;
   { /* (R) the unmodified reference */
     Fields f = make_fields(m, "ref", hbar);
     ma::SizeField* sf = ma::makeSizeField(m, f.sizes, f.frames, log_interp != 0);
@@ -152,6 +154,20 @@ extern "C" int mag_adapter_check(int n, int log_interp, int fp_mode, double jitt
       A.n_bad = mag::markBadQuality(&a);
       A.min_q = mag::getMinQuality(&a);
       collect_flags(&a, A);
+      /* ma::getElementWeights (maBalance.cc:83-97) against the reference's own per-entity loop on the same Adapt */
+      a.refinesLeft = 0; a.coarsensLeft = 1;
+      ma::Tag* wt = mag::getElementWeights(&a);
+      apf::MeshIterator* wit = m->begin(3);
+      ma::Entity* we;
+      while ((we = m->iterate(wit))) {
+        double wg, wr = ma::getElementWeight(&a, we);   /* a.sizeField is the adapter; its getWeight delegates to the wrapped reference field */
+        m->getDoubleTag(we, wt, &wg);
+        const double tol = (fp_mode == MAG_FP_STRICT && !log_interp) ? 0.0 : 1e-12;
+        if (fabs(wg - wr) > tol * fabs(wr)) ++weight_diffs;
+      }
+      m->end(wit);
+      apf::removeTagFromDimension(m, wt, 3);
+      m->destroyTag(wt);
     }
     A.max_len = mag::getMaximumEdgeLength(m, g);
     delete in;
@@ -190,5 +206,6 @@ extern "C" int mag_adapter_check(int n, int log_interp, int fp_mode, double jitt
     bad |= fabs(k[i]->min_q - R.min_q) > tol * fabs(R.min_q) || fabs(k[i]->max_len - R.max_len) > tol * R.max_len;
   }
   for (int i = 15; i < 19; ++i) bad |= report[i] != 0;
+  bad |= weight_diffs != 0;
   return bad;
 }
