@@ -726,6 +726,39 @@ k_tets(int32_t nt, int32_t elem_off, int64_t nv, const int4* __restrict__ tet_v,
   }
 }
 
+// ------------------------------------------------------------------ cavity batches
+// Batch form of ma::getWorstQuality (ma/maQuality.cc:184-210) for many candidate cavities at once: cavity k is the list
+// of tets [offsets[k], offsets[k+1]) given by their four vertex ids -- existing vertices of the resident part, but the tets
+// need not exist in the mesh (collapse / swap / snap evaluate would-be elements, maCollapse.cc:37-113,
+// maEdgeSwap.cc:598-740).  One warp per cavity, lanes stride over its tets, warp-wide minimum: no atomics, deterministic.
+template <int KIND, bool FAST>
+__global__ void __launch_bounds__(256)
+k_cavity_quality(int64_t ncav, const int64_t* __restrict__ offsets, const int4* __restrict__ tet_v, int64_t nv,
+                 const double* __restrict__ vpos, const double* __restrict__ vq, const double* __restrict__ vedge,
+                 int use_max, double* __restrict__ worst, double* __restrict__ qual, MagDevStats* st)
+{
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  int eig = 0;
+  for (int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < ncav; k += nwarps) {
+    const int64_t lo = offsets[k], hi = offsets[k + 1];
+    unsigned long long key = ~0ull;
+    for (int64_t t = lo + lane; t < hi; t += 32) {
+      const int4 tv = __ldg(tet_v + t);
+      const double q = tet_quality_eval<KIND, FAST, false>(tv, nv, vpos, vq, vedge, use_max, &eig, nullptr);
+      if (qual) qual[t] = q;
+      const unsigned long long kq = dkey(q);
+      key = kq < key ? kq : key;
+    }
+    key = warp_min_u64(key);
+    if (lane == 0) {
+      const unsigned long long b = (key >> 63) ? (key & 0x7fffffffffffffffull) : ~key;   // inverse of dkey()
+      worst[k] = __longlong_as_double((long long)b);
+    }
+  }
+  if (eig) atomicAdd(&st->n_eigen_fail, 1ull);
+}
+
 // ------------------------------------------------------------------ triangles (2-D meshes)
 // measureTriQuality (maQuality.cc:110-136): 48 A^2 / (sum l^2)^2 with the transform of the max-"Jacobian" vertex
 // (|row0 x row1| of Q_v on a 2-D mesh) or of the centroid (xi = 1/3, 1/3).  2-D meshes are small next to the 3-D
@@ -1240,6 +1273,7 @@ int magk_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double 
   if (ops & (MAG_OP_QUALITIES | MAG_OP_MARK_BAD | MAG_OP_LAYER_CHECK)) {
     // per-vertex transforms are part of every quality sweep (never cached across sweeps)
     if ((rc = magk_vertex_pass(c))) return rc;
+    c->vertex_pass_valid = true;   // cavity batches between two exports reuse them (mag_cavity_quality)
   }
   if (tev) MAG_CUDA(c, cudaEventRecord(tev[1], c->stream));
   if (c->ne && (ops & (MAG_OP_LENGTHS | MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE))) {
@@ -1273,6 +1307,29 @@ int magk_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double 
   }
   if (tev) { MAG_CUDA(c, cudaEventRecord(tev[3], c->stream)); c->t_used++; }
   return MAG_OK;
+}
+
+template <int KIND>
+static int launch_cavities(mag_ctx* c, bool fast, int64_t ncav, const int64_t* d_off, const int32_t* d_tv, int use_max, double* d_worst, double* d_qual)
+{
+  const int64_t blocks = (ncav + 7) / 8;
+  const unsigned g = (unsigned)(blocks < (int64_t)c->n_sms * 16 ? (blocks < 1 ? 1 : blocks) : (int64_t)c->n_sms * 16);
+  const int4* tv = reinterpret_cast<const int4*>(d_tv);
+  if (fast) k_cavity_quality<KIND, true><<<g, 256, 0, c->stream>>>(ncav, d_off, tv, c->nv, c->d_vpos, c->d_vq, c->d_vedge, use_max, d_worst, d_qual, c->d_stats);
+  else k_cavity_quality<KIND, false><<<g, 256, 0, c->stream>>>(ncav, d_off, tv, c->nv, c->d_vpos, c->d_vq, c->d_vedge, use_max, d_worst, d_qual, c->d_stats);
+  MAG_CUDA(c, cudaGetLastError());
+  c->n_launches++;
+  return MAG_OK;
+}
+int magk_cavity_quality(mag_ctx* c, int fp_mode, int64_t ncav, const int64_t* d_off, const int32_t* d_tv, int use_max, double* d_worst, double* d_qual)
+{
+  const bool fast = fp_mode == MAG_FP_FAST;
+  switch (c->kind) {
+    case MAG_KIND_IDENTITY: return launch_cavities<MAG_KIND_IDENTITY>(c, fast, ncav, d_off, d_tv, use_max, d_worst, d_qual);
+    case MAG_KIND_ISO: return launch_cavities<MAG_KIND_ISO>(c, fast, ncav, d_off, d_tv, use_max, d_worst, d_qual);
+    case MAG_KIND_ANISO: return launch_cavities<MAG_KIND_ANISO>(c, fast, ncav, d_off, d_tv, use_max, d_worst, d_qual);
+    default: return launch_cavities<MAG_KIND_LOGM>(c, fast, ncav, d_off, d_tv, use_max, d_worst, d_qual);
+  }
 }
 
 double magk_key_to_double(unsigned long long k)

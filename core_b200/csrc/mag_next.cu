@@ -13,6 +13,9 @@
 
 using namespace maglay;
 
+int magk_vertex_pass(mag_ctx* c);
+int magk_cavity_quality(mag_ctx* c, int fp_mode, int64_t ncav, const int64_t* d_off, const int32_t* d_tv, int use_max, double* d_worst, double* d_qual);
+
 namespace {
 
 constexpr int kWThreads = 128;
@@ -330,6 +333,45 @@ int mag_element_weights(mag_ctx* c, double w_max, double w_min, int fp_mode, dou
   MAG_CUDA(c, cudaStreamSynchronize(c->stream));
   if (c->h_stats->n_eigen_fail)
     return mag_fail(c, MAG_ERR_EIGEN, "eigenQR failed in %llu blocks of the weight sweep (apf::eigen asserts convergence, apfMatrix.cc:76)", c->h_stats->n_eigen_fail);
+  return MAG_OK;
+}
+
+int mag_cavity_quality(mag_ctx* c, int64_t ncav, const int64_t* offsets, const int32_t* tet_v, int use_max_metric, int fp_mode,
+                       double* worst, double* qualities)
+{
+  if (!c) return MAG_ERR_ARG;
+  MAG_CUDA(c, cudaSetDevice(c->device));
+  if (c->kind == MAG_KIND_NONE) return mag_fail(c, MAG_ERR_ARG, "mag_cavity_quality: no size field set");
+  if (c->dim != 3) return mag_fail(c, MAG_ERR_ARG, "mag_cavity_quality: 3-D parts only");
+  if (fp_mode != MAG_FP_STRICT && fp_mode != MAG_FP_FAST) return mag_fail(c, MAG_ERR_ARG, "mag_cavity_quality: bad fp_mode %d", fp_mode);
+  if (ncav < 0 || (ncav && (!offsets || !worst))) return mag_fail(c, MAG_ERR_ARG, "mag_cavity_quality: bad arguments");
+  if (ncav == 0) return MAG_OK;
+  const int64_t ntet = offsets[ncav];
+  if (offsets[0] != 0 || ntet < ncav || (ntet && !tet_v)) return mag_fail(c, MAG_ERR_ARG, "mag_cavity_quality: bad offsets");
+  for (int64_t k = 0; k < ncav; ++k)   // getWorstQuality asserts n > 0 (maQuality.cc:186)
+    if (offsets[k + 1] <= offsets[k]) return mag_fail(c, MAG_ERR_ARG, "mag_cavity_quality: cavity %lld is empty", (long long)k);
+  for (int64_t i = 0; i < 4 * ntet; ++i)
+    if (tet_v[i] < 0 || tet_v[i] >= c->nv) return mag_fail(c, MAG_ERR_ARG, "mag_cavity_quality: vertex id %d out of range", tet_v[i]);
+  int rc;
+  if (!c->vertex_pass_valid) {
+    if ((rc = magk_vertex_pass(c))) return rc;
+    c->vertex_pass_valid = true;
+  }
+  DevBuf off, tv, dw, dq;
+  MAG_CUDA(c, cudaMalloc(&off.p, (size_t)(ncav + 1) * 8));
+  MAG_CUDA(c, cudaMalloc(&tv.p, (size_t)ntet * 16));
+  MAG_CUDA(c, cudaMalloc(&dw.p, (size_t)ncav * 8));
+  if (qualities) MAG_CUDA(c, cudaMalloc(&dq.p, (size_t)ntet * 8));
+  MAG_CUDA(c, cudaMemcpyAsync(off.p, offsets, (size_t)(ncav + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  MAG_CUDA(c, cudaMemcpyAsync(tv.p, tet_v, (size_t)ntet * 16, cudaMemcpyHostToDevice, c->stream));
+  MAG_CUDA(c, cudaMemsetAsync(&c->d_stats->n_eigen_fail, 0, sizeof(unsigned long long), c->stream));
+  if ((rc = magk_cavity_quality(c, fp_mode, ncav, (const int64_t*)off.p, (const int32_t*)tv.p, use_max_metric, (double*)dw.p, (double*)dq.p))) return rc;
+  MAG_CUDA(c, cudaMemcpyAsync(worst, dw.p, (size_t)ncav * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (qualities) MAG_CUDA(c, cudaMemcpyAsync(qualities, dq.p, (size_t)ntet * 8, cudaMemcpyDeviceToHost, c->stream));
+  MAG_CUDA(c, cudaMemcpyAsync(&c->h_stats->n_eigen_fail, &c->d_stats->n_eigen_fail, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->h_stats->n_eigen_fail)
+    return mag_fail(c, MAG_ERR_EIGEN, "eigenQR failed in %llu blocks of the cavity sweep (apf::eigen asserts convergence, apfMatrix.cc:76)", c->h_stats->n_eigen_fail);
   return MAG_OK;
 }
 

@@ -212,6 +212,18 @@ class Part:
         self._ck(self._L.mag_element_weights(self._h, w_max, w_min, int(fp_mode), _ptr(out)))
         return out
 
+    def cavity_quality(self, offsets, tet_v, use_max=True, fp_mode=FP_STRICT, want_qualities=False):
+        """Batch ma::getWorstQuality (maQuality.cc:184-210): worst[k] = min quality over the candidate tets
+        tet_v[offsets[k]:offsets[k+1]] (vertex quadruples; the tets need not exist in the mesh)."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        tet_v = np.ascontiguousarray(tet_v, dtype=np.int32)
+        ncav = len(offsets) - 1
+        worst = np.empty(ncav)
+        q = np.empty(len(tet_v)) if want_qualities else None
+        self._ck(self._L.mag_cavity_quality(self._h, ncav, _ptr(offsets), _ptr(tet_v), int(bool(use_max)), int(fp_mode),
+                                            _ptr(worst), _ptr(q)))
+        return (worst, q) if want_qualities else worst
+
     def split_vertices(self, fp_mode=FP_STRICT):
         """ma::makeSplitVert for every SPLIT-marked edge, in edge order: (edge_idx, xyz, field_a, field_b) with
         (field_a, field_b) in the layout of the resident size field (iso: size[n]; aniso: h[n][3], R[n][9];

@@ -187,6 +187,15 @@ int mag_sweep_host(mag_ctx* c, const mag_host_part* in, const mag_host_result* o
    out [np+npy+nt] host (may be NULL: the weights stay on the device); prisms / pyramids get 0 (the reference weighs
    a prism by its base triangle, which needs that face's own vertex order).  Synchronous. */
 int mag_element_weights(mag_ctx* c, double w_max, double w_min, int fp_mode, double* out);
+/* Batch form of ma::getWorstQuality / hasWorseQuality (ma/maQuality.cc:184-226) for many candidate cavities at once
+   (collapse / swap / snap operators: ma/maCollapse.cc:37-113, ma/maEdgeSwap.cc:598-740, ma/maSnapper.cc:407,573).
+   Cavity k = the tets tet_v[offsets[k] .. offsets[k+1]) given by their four vertex ids: existing vertices of the resident
+   part, but the tets need not exist in the mesh (operators evaluate would-be elements).  offsets [ncav+1], offsets[0] = 0,
+   no empty cavity (the reference asserts n > 0).  worst [ncav] = smallest measureElementQuality of the cavity;
+   qualities [offsets[ncav]] (may be NULL) = every element's quality; hasWorseQuality(cavity, q) == worst < q.
+   The per-vertex transforms of the last sweep are reused while mesh and size field are unchanged.  Synchronous. */
+int mag_cavity_quality(mag_ctx* c, int64_t ncav, const int64_t* offsets, const int32_t* tet_v /*[.][4]*/,
+                       int use_max_metric, int fp_mode, double* worst, double* qualities);
 /* Size-field transfer to the vertices that will split the SPLIT-marked edges (ma::makeSplitVert, ma/maRefine.cc:129-151;
    SizeField::interpolate, ma/maSize.cc:414-429,523-534): for every edge whose resident flag word carries MAG_SPLIT, in
    edge order, the edge index, the position of the new vertex (xi = 0) and the size-field values it receives --

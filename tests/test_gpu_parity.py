@@ -145,6 +145,87 @@ def test_weights_and_split_vertices_golden(cb, name):
     p.close()
 
 
+def edge_cavities(edge_v, tet_v):
+    """CSR of the tets around every edge (the cavity of an edge collapse / swap), built from the connectivity alone."""
+    pairs = [(0, 1), (1, 2), (2, 0), (0, 3), (1, 3), (2, 3)]
+    key = lambda a, b: np.minimum(a, b).astype(np.int64) * (1 << 32) + np.maximum(a, b)
+    ek = key(edge_v[:, 0], edge_v[:, 1])
+    order = np.argsort(ek)
+    tk = np.concatenate([key(tet_v[:, a], tet_v[:, b]) for a, b in pairs])
+    tid = np.tile(np.arange(len(tet_v)), 6)
+    pos = order[np.searchsorted(ek[order], tk)]          # edge index of every (tet, local edge)
+    o = np.argsort(pos, kind="stable")
+    counts = np.bincount(pos, minlength=len(edge_v))
+    offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    return offsets, tid[o]
+
+
+@pytest.mark.parametrize("name", [n for n in util.golden_cases() if "weights_raw" in util.load(n)])
+def test_cavity_quality_golden(cb, name):
+    """SURVEY 8f row 1: batch ma::getWorstQuality.  Cavities = the tets around every edge of the golden mesh; the worst
+    quality of each must equal the minimum of the compiled reference's own per-tet qualities."""
+    from oracle import mao
+    g = util.load(name)
+    kind, ma, mb = util.metric_arrays(g)
+    _, _, tet_v = util.split_elements(g)
+    offsets, members = edge_cavities(g["edge_v"], tet_v)
+    assert offsets[-1] == 6 * len(tet_v) and np.all(np.diff(offsets) > 0)
+    want = np.minimum.reduceat(g["qualities"][members], offsets[:-1])
+    want_c = np.minimum.reduceat(g["qualities_centroid"][members], offsets[:-1])
+    p = cb.Part(0)
+    p.set_mesh(g["xyz"], g["edge_v"], tet_v)
+    util.set_part_metric(p, kind, ma, mb)
+    for mode in (cb.FP_STRICT, cb.FP_FAST):
+        worst, q = p.cavity_quality(offsets, tet_v[members], fp_mode=mode, want_qualities=True)
+        worst_c = p.cavity_quality(offsets, tet_v[members], use_max=False, fp_mode=mode)
+        if mode == cb.FP_STRICT and kind != mao.LOGM:
+            assert np.array_equal(worst, want) and np.array_equal(q, g["qualities"][members])
+            assert np.array_equal(worst_c, want_c)
+        else:
+            assert util.rel_err(worst, want) < TOL and util.rel_err(worst_c, want_c) < TOL
+    p.close()
+
+
+def test_cavity_quality_candidate_tets_vs_oracle(cb):
+    """Would-be elements: random vertex quadruples (many inverted -> negative qualities) that are not mesh entities,
+    ragged cavities of 1..40 tets, against the restated oracle; error paths of the batch call."""
+    from oracle import mao
+    n = 10
+    rng = np.random.default_rng(11)
+    xyz, ev, tv = cb.boxmesh.kuhn_box(n, n, n)
+    xyz = cb.fields.jitter(xyz, 0.3 / n)
+    h, R = cb.fields.shock_rotating(xyz, 1.0 / n)
+    p = cb.Part(0)
+    p.set_mesh(xyz, ev, tv)
+    p.set_size_field_aniso(h, R)
+    sizes = rng.integers(1, 41, 3000)
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    base = rng.integers(0, len(xyz) - 150, offsets[-1])
+    cand = (base[:, None] + rng.integers(0, 150, (offsets[-1], 4))).astype(np.int32)     # nearby, arbitrary orientation
+    q0 = mao.tet_qualities(mao.ANISO, xyz, h, R, cand)
+    assert (q0 < 0).mean() > 0.2
+    want = np.minimum.reduceat(q0, offsets[:-1])
+    worst, q = p.cavity_quality(offsets, cand, fp_mode=cb.FP_STRICT, want_qualities=True)
+    assert np.array_equal(q, q0) and np.array_equal(worst, want)
+    worst_f = p.cavity_quality(offsets, cand, fp_mode=cb.FP_FAST)
+    # degenerate candidates (repeated / coplanar vertices) have |V| ~ 0 by cancellation: relative error is meaningless
+    # there, so the bound is 1e-12 relative plus an absolute floor far below any quality threshold
+    assert np.all(np.abs(worst_f - want) <= TOL * np.abs(want) + 1e-15)
+    # a sweep in between (new vertex pass) changes nothing; a new size field does
+    p.sweep(cb.OP_QUALITIES, fp_mode=cb.FP_FAST)
+    assert np.array_equal(p.cavity_quality(offsets, cand), want)
+    p.set_size_field_iso(h[:, 1].copy())
+    want_iso = np.minimum.reduceat(mao.tet_qualities(mao.ISO, xyz, h[:, 1].copy(), None, cand), offsets[:-1])
+    assert np.array_equal(p.cavity_quality(offsets, cand), want_iso)
+    with pytest.raises(cb.sweep.MagError):
+        p.cavity_quality(np.array([0, 2, 2], np.int64), cand[:2])          # empty cavity: the reference asserts n > 0
+    bad = cand[:4].copy()
+    bad[1, 2] = len(xyz)
+    with pytest.raises(cb.sweep.MagError):
+        p.cavity_quality(np.array([0, 4], np.int64), bad)                   # vertex id out of range
+    p.close()
+
+
 def test_unsafe_prisms(cb):
     g = util.load("mixed5_unsafe_layer")
     prism_v, _, tet_v = util.split_elements(g)
