@@ -484,6 +484,34 @@ def test_sweep_host_streamed_equals_resident(cb, kindname):
     q.close()
 
 
+def test_baseline_configs_1_and_2_reference_values(cb):
+    """BASELINE configs[0] (n = 20, isotropic h = hbar (1 + 2x)) and configs[1] (n = 55, 998,250 tets, planar shock
+    layer AnisoSizeField) on the device against the values the compiled reference printed at survey time
+    (SURVEY.md 8c): counts exact in both fp modes, min quality / max length bit-exact in strict mode."""
+    cases = [(20, "iso", (800, 15710, 0), 0.43199999999999933, 1.6508199830081591),
+             (20, "aniso", (26732, 0, 9600), 0.00064551397077518649, 7.0712523453038738),
+             (55, "aniso", (528471, None, 151250), 0.0012373498034575676, 8.5789062902035695)]
+    p = cb.Part(0)
+    for n, field, counts, minq, maxlen in cases:
+        xyz, ev, tv = cb.boxmesh.kuhn_box(n, n, n)
+        p.set_mesh(xyz, ev, tv)
+        if field == "iso":
+            p.set_size_field_iso(cb.fields.iso_linear(xyz, 1.0 / n))
+        else:
+            p.set_size_field_aniso(*cb.fields.shock_planar(xyz, 1.0 / n))
+        for mode in (cb.FP_STRICT, cb.FP_FAST):
+            p.clear_flags()
+            p.sweep(cb.OP_ALL & ~cb.OP_LAYER_CHECK, fp_mode=mode)
+            st = p.stats()
+            got = (st["n_split"], st["n_collapse"], st["n_bad"])
+            assert all(w is None or g == w for g, w in zip(got, counts)), (n, field, got)
+            if mode == cb.FP_STRICT:
+                assert st["min_quality"] == minq and st["max_length"] == maxlen
+            else:
+                assert abs(st["min_quality"] - minq) <= TOL * minq and abs(st["max_length"] - maxlen) <= TOL * maxlen
+    p.close()
+
+
 def test_full_size_properties(cb):
     """BASELINE config 3 size (n=203: 50.2 M tets, 58.9 M edges).  The oracle cannot sweep this in seconds, so:
     (1) a seeded random sample of 300k edges and 300k tets is checked against the oracle; (2) fast and strict flags
