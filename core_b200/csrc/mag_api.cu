@@ -132,7 +132,7 @@ int mag_create(mag_ctx** out, int device)
   c->nv = c->ne = c->nt = c->np = c->npy = c->ntri = 0;
   c->dim = 3;
   c->kind = MAG_KIND_NONE;
-  c->vertex_pass_valid = false; c->schedule_valid = false; c->s_up = c->s_down = nullptr;
+  c->vertex_pass_valid = false; c->schedule_valid = false; c->edge_flags_zero = c->elem_flags_zero = false; c->s_up = c->s_down = nullptr;
   c->d_xyz = c->d_ma = c->d_mb = c->d_vedge = c->d_vpos = c->d_vq = nullptr;
   c->d_edge_v = c->d_tet_v = c->d_prism_v = c->d_pyr_v = c->d_tri_v = nullptr;
   c->d_edge_owned = c->d_elem_owned = nullptr;
@@ -237,6 +237,15 @@ int magi_reshape(mag_ctx* c, int dim, int64_t nv, int64_t ne, int64_t nt, int64_
   return MAG_OK;
 }
 
+int magi_materialize_flags(mag_ctx* c)
+{
+  if (c->edge_flags_zero && c->ne) MAG_CUDA(c, cudaMemsetAsync(c->d_edge_flags, 0, (size_t)c->ne * 4, c->stream));
+  const int64_t nel = c->np + c->npy + c->nt + c->ntri;
+  if (c->elem_flags_zero && nel) MAG_CUDA(c, cudaMemsetAsync(c->d_elem_flags, 0, (size_t)nel * 4, c->stream));
+  c->edge_flags_zero = c->elem_flags_zero = false;
+  return MAG_OK;
+}
+
 // grows the raw size-field arrays and the packed gather records for `kind`
 int magi_reserve_metric(mag_ctx* c, int kind, size_t na, size_t nb)
 {
@@ -257,8 +266,7 @@ static int set_mesh_impl(mag_ctx* c, int dim, int64_t nv, const double* xyz, int
   if ((rc = magi_reshape(c, dim, nv, ne, nt, np, npy, ntri, edge_owned != nullptr, elem_owned != nullptr))) return rc;
   const int64_t nel = np + npy + nt + ntri;
   // a new mesh starts with no flags (ma::getFlags returns 0 when the tag is absent, maAdapt.cc:80-88)
-  if (ne) MAG_CUDA(c, cudaMemsetAsync(c->d_edge_flags, 0, (size_t)ne * 4, c->stream));
-  if (nel) MAG_CUDA(c, cudaMemsetAsync(c->d_elem_flags, 0, (size_t)nel * 4, c->stream));
+  c->edge_flags_zero = c->elem_flags_zero = true;
   if ((rc = upload(c, c->d_xyz, xyz, (size_t)nv * 3)) || (rc = upload(c, c->d_edge_v, edge_v, (size_t)ne * 2)) ||
       (rc = upload(c, c->d_tet_v, tet_v, (size_t)nt * 4)) || (rc = upload(c, c->d_prism_v, prism_v, (size_t)np * 6)) ||
       (rc = upload(c, c->d_pyr_v, pyr_v, (size_t)npy * 5)) || (rc = upload(c, c->d_tri_v, tri_v, (size_t)ntri * 3)))
@@ -315,14 +323,13 @@ int mag_set_flags(mag_ctx* c, const int32_t* edge_flags, const int32_t* elem_fla
 {
   CHECK_CTX(c);
   const int64_t nel = c->np + c->npy + c->nt + c->ntri;
-  if (c->ne) {
-    if (edge_flags) { int rc = upload(c, c->d_edge_flags, edge_flags, (size_t)c->ne); if (rc) return rc; }
-    else MAG_CUDA(c, cudaMemsetAsync(c->d_edge_flags, 0, (size_t)c->ne * 4, c->stream));
-  }
-  if (nel) {
-    if (elem_flags) { int rc = upload(c, c->d_elem_flags, elem_flags, (size_t)nel); if (rc) return rc; }
-    else MAG_CUDA(c, cudaMemsetAsync(c->d_elem_flags, 0, (size_t)nel * 4, c->stream));
-  }
+  // NULL = all zero: nothing is written now; the kernels of the next sweep skip the reads, anything else that looks
+  // at the words materialises them first (magi_materialize_flags)
+  if (edge_flags) { int rc = upload(c, c->d_edge_flags, edge_flags, (size_t)c->ne); if (rc) return rc; }
+  c->edge_flags_zero = edge_flags == nullptr;
+  if (elem_flags) { int rc = upload(c, c->d_elem_flags, elem_flags, (size_t)nel); if (rc) return rc; }
+  c->elem_flags_zero = elem_flags == nullptr;
+  (void)nel;
   return MAG_OK;
 }
 
@@ -364,6 +371,7 @@ int mag_get_flags(mag_ctx* c, int32_t* edge_flags, int32_t* elem_flags)
 {
   CHECK_CTX(c);
   int rc;
+  if ((rc = magi_materialize_flags(c))) return rc;
   if (edge_flags && (rc = download(c, edge_flags, c->d_edge_flags, (size_t)c->ne))) return rc;
   if (elem_flags && (rc = download(c, elem_flags, c->d_elem_flags, (size_t)(c->np + c->npy + c->nt + c->ntri)))) return rc;
   MAG_CUDA(c, cudaStreamSynchronize(c->stream));

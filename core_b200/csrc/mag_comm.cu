@@ -81,6 +81,7 @@ int exchange(mag_ctx* c, int32_t mask, int mode)
   if (c->links.empty()) return MAG_OK;
   if (!c->nccl_comm) return mag_fail(c, MAG_ERR_ARG, "flag exchange: call mag_comm_init first");
   ncclComm_t comm = (ncclComm_t)c->nccl_comm;
+  { int rc = magi_materialize_flags(c); if (rc) return rc; }
   for (auto& L : c->links)
     if (L.n) k_gather_flags<<<(unsigned)((L.n + 255) / 256), 256, 0, c->stream>>>(L.n, L.d_idx, c->d_edge_flags, mask, L.d_send);
   MAG_CUDA(c, cudaGetLastError());

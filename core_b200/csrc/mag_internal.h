@@ -51,6 +51,10 @@ struct mag_ctx {
   int dim;      // mesh dimension (3, or 2 after mag_set_mesh_2d)
   int kind;
   bool vertex_pass_valid;
+  // "ma_flags" words are logically all zero (ma::getFlags returns 0 when the tag is absent, maAdapt.cc:80-88) but the
+  // device arrays have not been zeroed: the whole-part edge / tet kernels then skip reading them; every other consumer
+  // calls magi_materialize_flags first
+  bool edge_flags_zero, elem_flags_zero;
   bool schedule_valid;   // d_edge_order / d_tet_order match the resident connectivity
 
   // raw uploads (kept so coordinates or metric can be replaced independently)
@@ -110,6 +114,7 @@ int mag_fail(mag_ctx* c, int code, const char* fmt, ...);
 extern "C" {
 int magi_reshape(mag_ctx* c, int dim, int64_t nv, int64_t ne, int64_t nt, int64_t np, int64_t npy, int64_t ntri,
                  bool has_edge_owned, bool has_elem_owned);
+int magi_materialize_flags(mag_ctx* c);
 int magi_reserve_metric(mag_ctx* c, int kind, size_t na, size_t nb);
 }
 int mag_stats_from_dev(mag_ctx* c, const MagDevStats& s, mag_stats* out);

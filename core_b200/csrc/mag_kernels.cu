@@ -334,6 +334,7 @@ __device__ __forceinline__ long long next_chunk(unsigned long long* counter, lon
 struct EdgeParams {
   int32_t off_bits, err_mask;
   int want_len;
+  int zero_in;   // the incoming flag words are all zero and the array was not materialised: do not read it
   uint32_t ops;
   double max_len, min_len, tol_max, tol_min;
 };
@@ -401,11 +402,11 @@ k_edges(int32_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
     int e = e0 + (int)threadIdx.x;
     int32_t f = 0;
     int2 ev = make_int2(0, 0);
-    if (e < e_end) { f = flags[e]; ev = __ldg(edge_v + e); }
+    if (e < e_end) { f = P.zero_in ? 0 : flags[e]; ev = __ldg(edge_v + e); }
     for (int tile = 0; tile < tiles; ++tile, e += kEdgeThreads) {
       int32_t f_nx = 0;
       int2 ev_nx = make_int2(0, 0);
-      if (e + kEdgeThreads < e_end) { f_nx = flags[e + kEdgeThreads]; ev_nx = __ldg(edge_v + e + kEdgeThreads); }
+      if (e + kEdgeThreads < e_end) { f_nx = P.zero_in ? 0 : flags[e + kEdgeThreads]; ev_nx = __ldg(edge_v + e + kEdgeThreads); }
       bool nr = false;
       if (e < e_end) {
         const int32_t fe = f | P.off_bits;
@@ -582,6 +583,7 @@ __device__ __forceinline__ void mark_tet(double q, int32_t& f, bool owned, const
 struct TetParams {
   uint32_t ops;
   int do_bad, want_q, use_max;
+  int zero_in;   // see EdgeParams
   double good_q, tol_q;   // tol_q = MAG_NEAR_REL * |good_q|, or -1 when good_q is not finite
 };
 
@@ -657,11 +659,11 @@ k_tets(int32_t nt, int32_t elem_off, int64_t nv, const int4* __restrict__ tet_v,
 #pragma unroll
     for (int i = 0; i < 4; ++i) zd[i] = make_double2(0.0, 0.0);
     if (t < t_end) {
-      f_cur = flags[t];
+      f_cur = P.zero_in ? 0 : flags[t];
       tv_cur = __ldg(tet_v + t);
       if (MAG_TET_PIPE && (P.want_q || (P.do_bad && !(f_cur & MAG_OK_QUALITY)))) load_zd(tv_cur, zd);
     }
-    if (t + kTetThreads < t_end) { f_nx = flags[t + kTetThreads]; tv_nx = __ldg(tet_v + t + kTetThreads); }
+    if (t + kTetThreads < t_end) { f_nx = P.zero_in ? 0 : flags[t + kTetThreads]; tv_nx = __ldg(tet_v + t + kTetThreads); }
     for (int tile = 0; tile < tiles; ++tile, t += kTetThreads) {
       const int32_t f_in = f_cur;
       int4 tv = tv_cur;
@@ -673,7 +675,7 @@ k_tets(int32_t nt, int32_t elem_off, int64_t nv, const int4* __restrict__ tet_v,
       f_cur = f_nx;
       tv_cur = tv_nx;
       if (MAG_TET_PIPE && t + kTetThreads < t_end && (P.want_q || (P.do_bad && !(f_cur & MAG_OK_QUALITY)))) load_zd(tv_cur, zd);
-      if (t + 2 * kTetThreads < t_end) { f_nx = flags[t + 2 * kTetThreads]; tv_nx = __ldg(tet_v + t + 2 * kTetThreads); }
+      if (t + 2 * kTetThreads < t_end) { f_nx = P.zero_in ? 0 : flags[t + 2 * kTetThreads]; tv_nx = __ldg(tet_v + t + 2 * kTetThreads); }
       bool nr = false;
       if (t < t_end) {
         int32_t f = f_in;
@@ -1097,9 +1099,10 @@ static unsigned persistent_grid(mag_ctx* c, int& per_sm, const void* kernel, int
   return (unsigned)(g < 1 ? 1 : g);
 }
 
-static EdgeParams edge_params(const SweepParams& P)
+static EdgeParams edge_params(const SweepParams& P, bool zero_in)
 {
   EdgeParams E;
+  E.zero_in = zero_in ? 1 : 0;
   const bool do_split = P.ops & MAG_OP_MARK_SPLIT, do_coll = P.ops & MAG_OP_MARK_COLLAPSE;
   E.off_bits = (do_split ? 0 : MAG_DONT_SPLIT) | (do_coll ? 0 : MAG_DONT_COLLAPSE);
   E.err_mask = (do_split ? MAG_SPLIT : 0) | (do_coll ? MAG_COLLAPSE : 0);
@@ -1122,7 +1125,7 @@ static int launch_edges_t(mag_ctx* c, const SweepParams& P, const Range& r)
   constexpr int kEdgeThreads = EdgeCfg<KIND, FAST>::T;
   const unsigned g = persistent_grid(c, per_sm, (const void*)k_edges<KIND, FAST>, r.n, kEdgeThreads, kEdgeChunk);
   k_edges<KIND, FAST><<<g, kEdgeThreads, 0, c->stream>>>((int32_t)r.n, reinterpret_cast<const int2*>(c->d_edge_v) + r.first, c->d_vedge,
-                                                         c->d_edge_flags + r.first, c->d_len + r.first, edge_params(P), c->d_stats,
+                                                         c->d_edge_flags + r.first, c->d_len + r.first, edge_params(P, r.whole && c->edge_flags_zero), c->d_stats,
                                                          c->d_near_edge, r.whole ? c->d_edge_order : nullptr, (int32_t)r.first);
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;
@@ -1134,9 +1137,10 @@ static int launch_edges(mag_ctx* c, const SweepParams& P, bool fast, const Range
   return fast ? launch_edges_t<KIND, true>(c, P, r) : launch_edges_t<KIND, false>(c, P, r);
 }
 
-static TetParams tet_params(const SweepParams& P)
+static TetParams tet_params(const SweepParams& P, bool zero_in)
 {
   TetParams T;
+  T.zero_in = zero_in ? 1 : 0;
   T.ops = P.ops;
   T.do_bad = (P.ops & MAG_OP_MARK_BAD) ? 1 : 0;
   T.want_q = (P.ops & MAG_OP_QUALITIES) ? 1 : 0;
@@ -1154,7 +1158,7 @@ static int launch_tets_t(mag_ctx* c, const SweepParams& P, const Range& r)
   const unsigned g = persistent_grid(c, per_sm, (const void*)k_tets<KIND, FAST, USE_MAX>, r.n, kTetThreads, kTetChunk);
   k_tets<KIND, FAST, USE_MAX><<<g, kTetThreads, 0, c->stream>>>((int32_t)r.n, (int32_t)(c->np + c->npy + r.first), c->nv,
                                                                  reinterpret_cast<const int4*>(c->d_tet_v) + r.first,
-                                                                 c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_flags, c->d_qual, tet_params(P),
+                                                                 c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_flags, c->d_qual, tet_params(P, r.whole && c->elem_flags_zero),
                                                                  c->d_stats, c->d_near_elem, r.whole ? c->d_tet_order : nullptr);
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;
@@ -1278,12 +1282,17 @@ int magk_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double 
   if (tev) MAG_CUDA(c, cudaEventRecord(tev[1], c->stream));
   if (c->ne && (ops & (MAG_OP_LENGTHS | MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE))) {
     if ((rc = launch_edges_kind(c, P, fast, Range{0, c->ne, true}))) return rc;
+    // a requested mark writes the flag word of EVERY edge when the incoming words are zero (nothing is skipped)
+    if (ops & (MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE)) c->edge_flags_zero = false;
     if ((ops & MAG_OP_LENGTH_SUM) && (rc = magk_length_sum(c))) return rc;
   }
   if (tev) MAG_CUDA(c, cudaEventRecord(tev[2], c->stream));
   if (ops & (MAG_OP_QUALITIES | MAG_OP_MARK_BAD)) {
+    // only the tet kernel understands "all zero, not materialised" (it then writes every word it marks)
+    if ((c->ntri || c->np + c->npy) && (rc = magi_materialize_flags(c))) return rc;
     if (c->nt) {
       if ((rc = launch_tets_kind(c, P, fast, Range{0, c->nt, true}))) return rc;
+      if (ops & MAG_OP_MARK_BAD) c->elem_flags_zero = false;
     }
     if (c->ntri) {
       switch (c->kind) {

@@ -385,6 +385,7 @@ int mag_split_vertices(mag_ctx* c, int fp_mode, int64_t cap, int64_t* n, int32_t
   *n = 0;
   if (c->ne == 0) return MAG_OK;
   const unsigned tiles = (unsigned)((c->ne + kSTile - 1) / kSTile);
+  { int rc = magi_materialize_flags(c); if (rc) return rc; }
   DevBuf off, tot, didx, dxyz, da, db;
   MAG_CUDA(c, cudaMalloc(&off.p, (size_t)tiles * 4));
   MAG_CUDA(c, cudaMalloc(&tot.p, 8));
