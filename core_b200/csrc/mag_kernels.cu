@@ -109,11 +109,9 @@ __global__ void k_fold_owned(int64_t n, int stride, const uint8_t* __restrict__ 
 // Q_v = SizeField::getTransform(vertex, xi=0) and det Q_v (apf::getJacobianDeterminant(Q,3)).
 // The vertex shape value is exactly 1.0 so "interpolation" returns the node value.
 template <int KIND>
-__global__ void k_vertex_pass(int64_t nv, int dim, const double* __restrict__ vedge, double* __restrict__ vpos,
-                              double* __restrict__ vq, MagDevStats* st)
+__device__ __forceinline__ void vertex_pass_one(int64_t v, int dim, const double* __restrict__ vedge, double* __restrict__ vpos,
+                                                double* __restrict__ vq, int* eig_fail)
 {
-  int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (v >= nv) return;
   M3 Q;
   double x, y, z;
   if (KIND == MAG_KIND_IDENTITY || KIND == MAG_KIND_ISO) {
@@ -136,7 +134,7 @@ __global__ void k_vertex_pass(int64_t nv, int dim, const double* __restrict__ ve
 #pragma unroll
       for (int i = 0; i < 9; ++i) A.m[i / 3][i % 3] = r.v[3 + i];
       int rc = magst::transform_logm(A, Q);
-      if (rc != 1) atomicAdd(&st->n_eigen_fail, 1ull);
+      if (rc != 1) *eig_fail = 1;
     }
   }
   // apf::getJacobianDeterminant(Q, mesh dimension) (apfVectorElement.cc:68-91): det in 3-D, |row0 x row1| in 2-D
@@ -149,6 +147,16 @@ __global__ void k_vertex_pass(int64_t nv, int dim, const double* __restrict__ ve
   *chunk_ptr_w<5>(vq, 2, v) = make_double2(Q.m[1][1], Q.m[1][2]);
   *chunk_ptr_w<5>(vq, 3, v) = make_double2(Q.m[2][0], Q.m[2][1]);
   *chunk_ptr_w<5>(vq, 4, v) = make_double2(Q.m[2][2], det);
+}
+template <int KIND>
+__global__ void k_vertex_pass(int64_t nv, int dim, const double* __restrict__ vedge, double* __restrict__ vpos,
+                              double* __restrict__ vq, MagDevStats* st)
+{
+  int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  int eig = 0;
+  vertex_pass_one<KIND>(v, dim, vedge, vpos, vq, &eig);
+  if (eig) atomicAdd(&st->n_eigen_fail, 1ull);
 }
 
 // ------------------------------------------------------------------ edge metric length
@@ -305,6 +313,15 @@ __device__ __forceinline__ unsigned long long near_reserve(unsigned long long* c
 #define MAG_TET_PIPE 1   /* 1: {z,det} chunks of the next tile are prefetched; 0: everything is loaded at the tile */
 #endif
 constexpr int kStrictThreads = 256, kStrictBlocks = 2;
+#ifndef MAG_FUSE_VERTEX
+#define MAG_FUSE_VERTEX 0   /* 1: in fast sweeps the per-vertex pass rides in the edge kernel's launch (k_edges<..,VERT>).
+                               Measured on B200 (n = 203): 2.428 -> 2.386 ms lattice, 1.95 -> 1.91 ms jittered with a vertex
+                               chunk every 8th ticket -- the vertex work costs the same warp-time inside the persistent
+                               kernel as alone (both are latency-bound per warp), so it stays a separate launch by default */
+#endif
+#ifndef MAG_VERT_EVERY
+#define MAG_VERT_EVERY 8
+#endif
 #ifndef MAG_EDGE_CHUNK
 #define MAG_EDGE_CHUNK 8192   /* 32 tiles of 256 */
 #endif
@@ -380,11 +397,18 @@ __device__ __noinline__ unsigned drain_edges(NearQueue& q, int first, int n, con
 // Persistent edge kernel.  Per thread and tile: the flag word and the end vertices are loaded one tile ahead; the two
 // vertex records are gathered only when the flag word says the edge has to be evaluated at all (skipped edges cost 12
 // bytes).  Everything is indexed with int32 (mag_set_mesh rejects meshes with 2^31 or more entities of one dimension).
-template <int KIND, bool FAST>
+// VERT: the per-vertex pass rides in the same launch.  Every kVertEvery-th ticket is a chunk of vertices instead of a
+// chunk of edges, so the HBM-bound streaming of the vertex pass (96 B in, 112 B out per vertex) overlaps the
+// latency-bound edge work of the other resident CTAs instead of preceding it, and both sweep the vertex array in step
+// (the vertex pass finds the gather records in L2).  The tet kernel of the same sweep is launched after this one.
+struct VertArgs { int32_t nv; int dim; double* vpos; double* vq; };
+constexpr int kVertChunk = 8192, kVertEvery = MAG_VERT_EVERY;
+template <int KIND, bool FAST, bool VERT>
 __global__ void __launch_bounds__(EdgeCfg<KIND, FAST>::T, EdgeCfg<KIND, FAST>::B)
 k_edges(int32_t ne, const int2* __restrict__ edge_v, const double* __restrict__ vedge,
         int32_t* __restrict__ flags, double* __restrict__ lengths,
-        EdgeParams P, MagDevStats* st, int32_t* __restrict__ near_list, const int32_t* __restrict__ chunk_order, int32_t id_base)
+        EdgeParams P, MagDevStats* st, int32_t* __restrict__ near_list, const int32_t* __restrict__ chunk_order, int32_t id_base,
+        VertArgs V)
 {
   __shared__ NearQueue q;
   __shared__ long long chunk_slot;
@@ -393,9 +417,23 @@ k_edges(int32_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
   int qn = 0, eig_any = 0;
   constexpr int kEdgeThreads = EdgeCfg<KIND, FAST>::T, kChunkEdges = kEdgeChunk;
   const int nchunks = (ne + kChunkEdges - 1) / kChunkEdges;
+  const int nvchunks = VERT ? (V.nv + kVertChunk - 1) / kVertChunk : 0;
   for (;;) {
-    const long long ticket = next_chunk(&st->edge_chunk, &chunk_slot);
-    if (ticket >= nchunks) break;
+    long long ticket = next_chunk(&st->edge_chunk, &chunk_slot);
+    if (VERT) {
+      // tickets 0, kVertEvery, 2 kVertEvery, ... are the vertex chunks; the others are edge chunks in schedule order
+      const long long nint = (long long)nvchunks * kVertEvery;      // tickets of the interleaved stretch
+      const long long ntickets = nint > (long long)nchunks + nvchunks ? nint : (long long)nchunks + nvchunks;
+      if (ticket >= ntickets) break;
+      if (ticket < nint && ticket % kVertEvery == 0) {
+        const int v0 = (int)(ticket / kVertEvery) * kVertChunk;
+        const int v_end = (V.nv - v0 < kVertChunk) ? V.nv : v0 + kVertChunk;
+        for (int v = v0 + (int)threadIdx.x; v < v_end; v += kEdgeThreads) vertex_pass_one<KIND>(v, V.dim, vedge, V.vpos, V.vq, &eig_any);
+        continue;
+      }
+      ticket = ticket < nint ? ticket - ticket / kVertEvery - 1 : ticket - nvchunks;
+      if (ticket >= nchunks) continue;                                // fewer edge chunks than slots between vertex chunks
+    } else if (ticket >= nchunks) break;
     const int e0 = (chunk_order ? chunk_order[ticket] : (int)ticket) * kChunkEdges;   // no schedule: a sub-range sweep (mag_sweep_host)
     const int e_end = (ne - e0 < kChunkEdges) ? ne : e0 + kChunkEdges;   // first edge past this chunk
     const int tiles = (e_end - e0 + kEdgeThreads - 1) / kEdgeThreads;
@@ -1118,23 +1156,30 @@ static EdgeParams edge_params(const SweepParams& P, bool zero_in)
 // [first, first + n) = the whole part with the chunk schedule, or a sub-range in natural order (mag_sweep_host)
 struct Range { int64_t first, n; bool whole; };
 
-template <int KIND, bool FAST>
+template <int KIND, bool FAST, bool VERT>
 static int launch_edges_t(mag_ctx* c, const SweepParams& P, const Range& r)
 {
   static int per_sm = 0;
   constexpr int kEdgeThreads = EdgeCfg<KIND, FAST>::T;
-  const unsigned g = persistent_grid(c, per_sm, (const void*)k_edges<KIND, FAST>, r.n, kEdgeThreads, kEdgeChunk);
-  k_edges<KIND, FAST><<<g, kEdgeThreads, 0, c->stream>>>((int32_t)r.n, reinterpret_cast<const int2*>(c->d_edge_v) + r.first, c->d_vedge,
-                                                         c->d_edge_flags + r.first, c->d_len + r.first, edge_params(P, r.whole && c->edge_flags_zero), c->d_stats,
-                                                         c->d_near_edge, r.whole ? c->d_edge_order : nullptr, (int32_t)r.first);
+  // the grid is sized for the edge chunks plus, with VERT, the vertex chunks that ride along
+  const int64_t work = r.n + (VERT ? (c->nv + kVertChunk - 1) / kVertChunk * (int64_t)kEdgeChunk : 0);
+  const unsigned g = persistent_grid(c, per_sm, (const void*)k_edges<KIND, FAST, VERT>, work, kEdgeThreads, kEdgeChunk);
+  const VertArgs V{(int32_t)c->nv, c->dim, c->d_vpos, c->d_vq};
+  k_edges<KIND, FAST, VERT><<<g, kEdgeThreads, 0, c->stream>>>((int32_t)r.n, reinterpret_cast<const int2*>(c->d_edge_v) + r.first, c->d_vedge,
+                                                               c->d_edge_flags + r.first, c->d_len + r.first, edge_params(P, r.whole && c->edge_flags_zero), c->d_stats,
+                                                               c->d_near_edge, r.whole ? c->d_edge_order : nullptr, (int32_t)r.first, V);
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;
   return MAG_OK;
 }
 template <int KIND>
-static int launch_edges(mag_ctx* c, const SweepParams& P, bool fast, const Range& r)
+static int launch_edges(mag_ctx* c, const SweepParams& P, bool fast, const Range& r, bool with_vertex_pass)
 {
-  return fast ? launch_edges_t<KIND, true>(c, P, r) : launch_edges_t<KIND, false>(c, P, r);
+#if MAG_FUSE_VERTEX
+  if (fast && with_vertex_pass) return launch_edges_t<KIND, true, true>(c, P, r);
+#endif
+  (void)with_vertex_pass;
+  return fast ? launch_edges_t<KIND, true, false>(c, P, r) : launch_edges_t<KIND, false, false>(c, P, r);
 }
 
 static TetParams tet_params(const SweepParams& P, bool zero_in)
@@ -1171,13 +1216,13 @@ static int launch_tets(mag_ctx* c, const SweepParams& P, bool fast, const Range&
   return fast ? launch_tets_t<KIND, true, false>(c, P, r) : launch_tets_t<KIND, false, false>(c, P, r);
 }
 
-static int launch_edges_kind(mag_ctx* c, const SweepParams& P, bool fast, const Range& r)
+static int launch_edges_kind(mag_ctx* c, const SweepParams& P, bool fast, const Range& r, bool with_vertex_pass = false)
 {
   switch (c->kind) {
-    case MAG_KIND_IDENTITY: return launch_edges<MAG_KIND_IDENTITY>(c, P, fast, r);
-    case MAG_KIND_ISO: return launch_edges<MAG_KIND_ISO>(c, P, fast, r);
-    case MAG_KIND_ANISO: return launch_edges<MAG_KIND_ANISO>(c, P, fast, r);
-    default: return launch_edges<MAG_KIND_LOGM>(c, P, fast, r);
+    case MAG_KIND_IDENTITY: return launch_edges<MAG_KIND_IDENTITY>(c, P, fast, r, with_vertex_pass);
+    case MAG_KIND_ISO: return launch_edges<MAG_KIND_ISO>(c, P, fast, r, with_vertex_pass);
+    case MAG_KIND_ANISO: return launch_edges<MAG_KIND_ANISO>(c, P, fast, r, with_vertex_pass);
+    default: return launch_edges<MAG_KIND_LOGM>(c, P, fast, r, false);   // the eigen-solver twice in one kernel does not fit
   }
 }
 static int launch_tets_kind(mag_ctx* c, const SweepParams& P, bool fast, const Range& r)
@@ -1274,14 +1319,18 @@ int magk_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double 
   int rc;
   cudaEvent_t* tev = (c->t_used < c->t_slots) ? &c->tev[(size_t)4 * c->t_used] : nullptr;
   if (tev) MAG_CUDA(c, cudaEventRecord(tev[0], c->stream));
-  if (ops & (MAG_OP_QUALITIES | MAG_OP_MARK_BAD | MAG_OP_LAYER_CHECK)) {
-    // per-vertex transforms are part of every quality sweep (never cached across sweeps)
-    if ((rc = magk_vertex_pass(c))) return rc;
+  const bool need_vertex = ops & (MAG_OP_QUALITIES | MAG_OP_MARK_BAD | MAG_OP_LAYER_CHECK);
+  const bool do_edges = c->ne && (ops & (MAG_OP_LENGTHS | MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE));
+  // per-vertex transforms are part of every quality sweep (never cached across sweeps); in a fast sweep that also
+  // measures the edges they ride in the edge kernel's launch (k_edges<.., VERT>)
+  const bool fuse_vertex = MAG_FUSE_VERTEX && need_vertex && do_edges && fast && c->nv && c->kind != MAG_KIND_LOGM;
+  if (need_vertex) {
+    if (!fuse_vertex && (rc = magk_vertex_pass(c))) return rc;
     c->vertex_pass_valid = true;   // cavity batches between two exports reuse them (mag_cavity_quality)
   }
   if (tev) MAG_CUDA(c, cudaEventRecord(tev[1], c->stream));
   if (c->ne && (ops & (MAG_OP_LENGTHS | MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE))) {
-    if ((rc = launch_edges_kind(c, P, fast, Range{0, c->ne, true}))) return rc;
+    if ((rc = launch_edges_kind(c, P, fast, Range{0, c->ne, true}, fuse_vertex))) return rc;
     // a requested mark writes the flag word of EVERY edge when the incoming words are zero (nothing is skipped)
     if (ops & (MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE)) c->edge_flags_zero = false;
     if ((ops & MAG_OP_LENGTH_SUM) && (rc = magk_length_sum(c))) return rc;
