@@ -438,7 +438,8 @@ def run_b200(a):
         try:
             if n == 203 and a.field == "aniso" and world == 1 and a.jitter == 0:
                 tj = json.load(open(os.path.join(HERE, "profiles", "traffic.json")))
-                key = "%s<2, %d>" % (dom, 1 if a.fp == "fast" else 0)
+                # template arguments as ncu prints them: k_edges<KIND, FAST, VERT>, k_tets<KIND, FAST, USE_MAX>
+                key = "%s<2, %d, %d>" % (dom, 1 if a.fp == "fast" else 0, 0 if dom == "k_edges" else 1)
                 traffic = float(tj[key]["dram_bytes_per_launch"])
         except Exception:
             traffic = None
