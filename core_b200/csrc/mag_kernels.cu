@@ -313,6 +313,9 @@ __device__ __forceinline__ unsigned long long near_reserve(unsigned long long* c
 #define MAG_TET_PIPE 1   /* 1: {z,det} chunks of the next tile are prefetched; 0: everything is loaded at the tile */
 #endif
 constexpr int kStrictThreads = 256, kStrictBlocks = 2;
+#ifndef MAG_EDGE_TILE_SCHED
+#define MAG_EDGE_TILE_SCHED 1   /* 1: the edge schedule orders tiles (256 edges); 0: chunks of MAG_EDGE_CHUNK edges */
+#endif
 #ifndef MAG_FUSE_VERTEX
 #define MAG_FUSE_VERTEX 0   /* 1: in fast sweeps the per-vertex pass rides in the edge kernel's launch (k_edges<..,VERT>).
                                Measured on B200 (n = 203): 2.428 -> 2.386 ms lattice, 1.95 -> 1.91 ms jittered with a vertex
@@ -434,17 +437,34 @@ k_edges(int32_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
       ticket = ticket < nint ? ticket - ticket / kVertEvery - 1 : ticket - nvchunks;
       if (ticket >= nchunks) continue;                                // fewer edge chunks than slots between vertex chunks
     } else if (ticket >= nchunks) break;
+#if MAG_EDGE_TILE_SCHED
+    // tile-granular schedule: the ticket is a group of kChunkEdges / T consecutive SCHEDULE positions; position p holds
+    // the index of a tile of T consecutive edges.  The schedule is sorted by the smallest vertex id a tile touches, so
+    // the tiles a CTA works through back to back belong to different edge families over the same window of vertices
+    // (box mesh: x, y, z, three face diagonals, body diagonal) and find each other's records in L1.
+    static_assert(kEdgeThreads == kStrictThreads, "the tile schedule is built for tiles of kStrictThreads edges");
+    constexpr int kGroup = kChunkEdges / kEdgeThreads;
+    const int ntiles = (ne + kEdgeThreads - 1) / kEdgeThreads;
+    const int k0 = (int)ticket * kGroup;
+    const int tiles = (ntiles - k0 < kGroup) ? ntiles - k0 : kGroup;
+    const int e_end = ne;
+    auto tile_base = [&](int p) { return (chunk_order ? __ldg(chunk_order + k0 + p) : k0 + p) * kEdgeThreads + (int)threadIdx.x; };
+#else
     const int e0 = (chunk_order ? chunk_order[ticket] : (int)ticket) * kChunkEdges;   // no schedule: a sub-range sweep (mag_sweep_host)
     const int e_end = (ne - e0 < kChunkEdges) ? ne : e0 + kChunkEdges;   // first edge past this chunk
     const int tiles = (e_end - e0 + kEdgeThreads - 1) / kEdgeThreads;
-    int e = e0 + (int)threadIdx.x;
+    auto tile_base = [&](int p) { return e0 + p * kEdgeThreads + (int)threadIdx.x; };
+#endif
+    int e = tile_base(0);
+    int e_nx = tiles > 1 ? tile_base(1) : e_end;
     int32_t f = 0;
     int2 ev = make_int2(0, 0);
     if (e < e_end) { f = P.zero_in ? 0 : flags[e]; ev = __ldg(edge_v + e); }
-    for (int tile = 0; tile < tiles; ++tile, e += kEdgeThreads) {
+    for (int tile = 0; tile < tiles; ++tile) {
+      const int e_nx2 = tile + 2 < tiles ? tile_base(tile + 2) : e_end;
       int32_t f_nx = 0;
       int2 ev_nx = make_int2(0, 0);
-      if (e + kEdgeThreads < e_end) { f_nx = P.zero_in ? 0 : flags[e + kEdgeThreads]; ev_nx = __ldg(edge_v + e + kEdgeThreads); }
+      if (e_nx < e_end) { f_nx = P.zero_in ? 0 : flags[e_nx]; ev_nx = __ldg(edge_v + e_nx); }
       bool nr = false;
       if (e < e_end) {
         const int32_t fe = f | P.off_bits;
@@ -486,6 +506,8 @@ k_edges(int32_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
       }
       f = f_nx;
       ev = ev_nx;
+      e = e_nx;
+      e_nx = e_nx2;
     }
   }
   if (qn) {
@@ -1278,28 +1300,40 @@ int magk_length_sum(mag_ctx* c)
   return MAG_OK;
 }
 
-#include <algorithm>
-#include <numeric>
-// builds c->d_edge_order / c->d_tet_order: chunk indices sorted by key (stable, so equal keys keep the caller's order)
+#include <cub/device/device_radix_sort.cuh>
+namespace {
+__global__ void k_iota(int64_t n, int32_t* __restrict__ out)
+{
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int32_t)i;
+}
+} // namespace
+// builds c->d_edge_order / c->d_tet_order: chunk (tile) indices sorted by key on the device (LSD radix sort is stable, so
+// equal keys keep the caller's order); nothing travels to the host
 static int build_order(mag_ctx* c, int64_t n, int64_t chunk_len, const int32_t* d_conn, int nv_per, int32_t*& d_order, int64_t& n_chunks)
 {
   n_chunks = (n + chunk_len - 1) / chunk_len;
   if (d_order) { MAG_CUDA(c, cudaFree(d_order)); d_order = nullptr; }
   if (n_chunks == 0) return MAG_OK;
-  int32_t* d_keys = nullptr;
+  int32_t *d_keys = nullptr, *d_keys_out = nullptr, *d_idx = nullptr;
+  void* d_tmp = nullptr;
+  size_t tmp_bytes = 0;
   MAG_CUDA(c, cudaMalloc((void**)&d_keys, (size_t)n_chunks * 4));
+  MAG_CUDA(c, cudaMalloc((void**)&d_keys_out, (size_t)n_chunks * 4));
+  MAG_CUDA(c, cudaMalloc((void**)&d_idx, (size_t)n_chunks * 4));
   MAG_CUDA(c, cudaMalloc((void**)&d_order, (size_t)n_chunks * 4));
   if (nv_per == 2) k_chunk_keys<2><<<(unsigned)n_chunks, kThreads, 0, c->stream>>>(n, chunk_len, d_conn, d_keys);
   else k_chunk_keys<4><<<(unsigned)n_chunks, kThreads, 0, c->stream>>>(n, chunk_len, d_conn, d_keys);
+  k_iota<<<grid_for(n_chunks), kThreads, 0, c->stream>>>(n_chunks, d_idx);
   MAG_CUDA(c, cudaGetLastError());
-  c->n_launches++;
-  std::vector<int32_t> keys((size_t)n_chunks), order((size_t)n_chunks);
-  MAG_CUDA(c, cudaMemcpyAsync(keys.data(), d_keys, (size_t)n_chunks * 4, cudaMemcpyDeviceToHost, c->stream));
+  c->n_launches += 2;
+  MAG_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys_out, d_idx, d_order, (int)n_chunks, 0, 31, c->stream));
+  MAG_CUDA(c, cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
+  MAG_CUDA(c, cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys_out, d_idx, d_order, (int)n_chunks, 0, 31, c->stream));
   MAG_CUDA(c, cudaStreamSynchronize(c->stream));
-  std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return keys[(size_t)a] < keys[(size_t)b]; });
-  MAG_CUDA(c, cudaMemcpyAsync(d_order, order.data(), (size_t)n_chunks * 4, cudaMemcpyHostToDevice, c->stream));
-  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  MAG_CUDA(c, cudaFree(d_tmp));
+  MAG_CUDA(c, cudaFree(d_idx));
+  MAG_CUDA(c, cudaFree(d_keys_out));
   MAG_CUDA(c, cudaFree(d_keys));
   return MAG_OK;
 }
@@ -1307,7 +1341,7 @@ int magk_build_schedule(mag_ctx* c)
 {
   int rc;
   int64_t nch;
-  if ((rc = build_order(c, c->ne, (int64_t)kEdgeChunk, c->d_edge_v, 2, c->d_edge_order, nch))) return rc;
+  if ((rc = build_order(c, c->ne, MAG_EDGE_TILE_SCHED ? (int64_t)kStrictThreads : (int64_t)kEdgeChunk, c->d_edge_v, 2, c->d_edge_order, nch))) return rc;
   if ((rc = build_order(c, c->nt, (int64_t)kTetChunk, c->d_tet_v, 4, c->d_tet_order, nch))) return rc;
   return MAG_OK;
 }
