@@ -254,6 +254,23 @@ def run_reference_arm(a):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Runs this rank on the CPUs nearest to its GPU (NVML's ideal CPU affinity), so that the pinned host buffers of the
+    end-to-end leg are allocated on that NUMA node and their copies do not cross the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 # --------------------------------------------------------------------------- B200 arm
 def run_b200(a):
     import torch
@@ -266,6 +283,7 @@ def run_b200(a):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
     torch.cuda.set_device(local)
+    bind_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
