@@ -493,6 +493,30 @@ int refo_split_vertices(void* hd, int64_t n, const int64_t* edges, double* out_x
   return 0;
 }
 
+/* writes the mesh in the reference's native format (mds_write_smb, mds/mds_smb.c:640-690); with one part the file is
+   <path minus ".smb">0.smb.  Fields present on the mesh travel as tags. */
+void refo_write_smb(void* hd, const char* path)
+{
+  Ref* r = (Ref*)hd;
+  r->m->writeNative(path);
+}
+/* vertex fields "sizes" (VECTOR) and "frames" (MATRIX) stored on the mesh without building a size field */
+void refo_store_fields(void* hd, const double* h, const double* R)
+{
+  Ref* r = (Ref*)hd; apf::Mesh2* m = r->m;
+  apf::Field* fh = apf::createFieldOn(m, "sizes", apf::VECTOR);
+  apf::Field* fR = apf::createFieldOn(m, "frames", apf::MATRIX);
+  apf::MeshIterator* it = m->begin(0); apf::MeshEntity* e;
+  while ((e = m->iterate(it))) {
+    int i = apf::getMdsIndex(m, e);
+    apf::setVector(fh, e, 0, apf::Vector3(h + 3*i));
+    apf::Matrix3x3 M;
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) M[a][b] = R[9*i+3*a+b];
+    apf::setMatrix(fR, e, 0, M);
+  }
+  m->end(it);
+}
+
 /* apf::eigen on one 3x3 (mth::eigenQR), for the known-answer vectors of
    test/eigen_test.cc.  vecs: eigenvector j in row j. returns 3 */
 int refo_eigen(const double* A, double* vals, double* vecs)

@@ -55,6 +55,8 @@ def lib():
         L.refo_avg_edge_length.restype = C.c_double
         L.refo_avg_edge_length.argtypes = [C.c_void_p]
         L.refo_eigen.argtypes = [C.c_void_p] * 3
+        L.refo_write_smb.argtypes = [C.c_void_p, C.c_char_p]
+        L.refo_store_fields.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.refo_weights.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.refo_split_vertices.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
@@ -172,6 +174,14 @@ class RefMesh:
         codes = np.zeros(self.nelem, dtype=np.int32)
         lib().refo_layer_ok(self.h, _p(ok), _p(codes))
         return ok, codes
+
+    def write_smb(self, path):
+        """mds_write_smb; a serial mesh lands in <path minus .smb>0.smb."""
+        lib().refo_write_smb(self.h, path.encode())
+
+    def store_fields(self, h, R):
+        h, R = _f64(h), _f64(R)
+        lib().refo_store_fields(self.h, _p(h), _p(R))
 
     def weights(self, refines_left=None, coarsens_left=0):
         """SizeField::getWeight per element (refines_left None) or ma::getElementWeight with the given iteration

@@ -169,6 +169,33 @@ def main():
     print("mixed5_unsafe_layer          unsafe prisms: %d of %d" % (int((ok == 0).sum()), len(prisms)))
     m.close()
 
+    # native-format fixtures written by the reference itself (mds_write_smb) with the arrays its own API exports from the
+    # same meshes: pins core_b200/smb.py
+    import shutil
+    import tempfile
+    tmp = tempfile.mkdtemp()
+    m = refo.RefMesh.box(3, 2, 2)
+    xyz = fields.jitter(m.export()[0], 0.2 / 3)
+    m.set_coords(xyz)
+    h, R = fields.shock_rotating(xyz, 1.0 / 3)
+    m.store_fields(h, R)                       # vertex fields "sizes" / "frames" travel as tags
+    m.write_smb(os.path.join(tmp, "kbox322.smb"))
+    shutil.copy(os.path.join(tmp, "kbox3220.smb"), os.path.join(HERE, "kbox322_0.smb"))
+    _, ev, et, elv = m.export()
+    m.set_sizefield(refo.KIND_ANISO_FIELD, h, R)
+    np.savez_compressed(os.path.join(HERE, "smb_kbox322.npz"), xyz=xyz, edge_v=ev, elem_type=et, elem_v=elv, h=h, R=R,
+                        lengths=m.lengths(), qualities=m.qualities(True))
+    m.close()
+    xyz, tets, prisms = mixed_box(3, 1)
+    m = refo.RefMesh.build(xyz, tets=tets, prisms=prisms)
+    m.write_smb(os.path.join(tmp, "mixed3.smb"))
+    shutil.copy(os.path.join(tmp, "mixed30.smb"), os.path.join(HERE, "mixed3_0.smb"))
+    _, ev, et, elv = m.export()
+    np.savez_compressed(os.path.join(HERE, "smb_mixed3.npz"), xyz=xyz, edge_v=ev, elem_type=et, elem_v=elv)
+    m.close()
+    shutil.rmtree(tmp)
+    print("smb fixtures: kbox322_0.smb, mixed3_0.smb")
+
     # apf::eigen on the six matrices of test/eigen_test.cc:13-56 plus random symmetric ones
     A6 = np.array([
         [[1.001575e+00, -3.138397e-01, 8.107355e-01], [-3.138397e-01, 4.946182e-01, -1.860431e+00], [8.107355e-01, -1.860431e+00, 7.582283e+00]],
