@@ -469,7 +469,7 @@ def run_b200(a):
                     "step_frac": ab["total"] / (step_ms * 1e-3) / 1e9 / peak}
         cpu = None
         if not a.no_cpu:
-            cpu = cpu_baseline(a.cpu_n or 44)
+            cpu = cpu_baseline(a.cpu_n or 55)   # BASELINE configs[1] size: 998,250 tets, ~11 s on one core
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",

