@@ -125,7 +125,7 @@ __device__ __forceinline__ void apply_refl2(const Refl2& r, double& x, double& y
 }
 // returns w^T V exp(Lambda) V^T w through the reference's iteration; *fail is set if the reference would assert
 #ifndef MAG_QR_INLINE
-#define MAG_QR_INLINE __noinline__
+#define MAG_QR_INLINE __forceinline__
 #endif
 __device__ MAG_QR_INLINE double quad_expm_qr3(double m00, double m01, double m02, double m11, double m12, double m22,
                                              double w0, double w1, double w2, int* fail)
