@@ -39,7 +39,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=203, help="cells per side of each part's box")
+    # "--cells" is the spelling to use under torchrun, whose own parser rejects "--n" as an ambiguous abbreviation
+    ap.add_argument("--n", "--cells", dest="n", type=int, default=203, help="cells per side of each part's box")
     ap.add_argument("--fp", default=os.environ.get("MAG_BENCH_FP", "fast"), choices=["strict", "fast"])
     ap.add_argument("--field", default="aniso", choices=["aniso", "logm", "iso"])
     ap.add_argument("--e2e-steps", type=int, default=3)

@@ -567,7 +567,7 @@ def test_nccl_two_gpus(cb):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(root, "bench.py"),
-                          "--gpus", "2", "--steps", "2", "--warmup", "1", "--n", "40", "--no-cpu", "--e2e-steps", "1"],
+                          "--gpus", "2", "--steps", "2", "--warmup", "1", "--cells", "40", "--no-cpu", "--e2e-steps", "1"],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     import json
