@@ -312,7 +312,10 @@ __device__ __forceinline__ unsigned long long near_reserve(unsigned long long* c
 #ifndef MAG_TET_PIPE
 #define MAG_TET_PIPE 1   /* 1: {z,det} chunks of the next tile are prefetched; 0: everything is loaded at the tile */
 #endif
-constexpr int kStrictThreads = 256, kStrictBlocks = 2;
+#ifndef MAG_STRICT_BLOCKS
+#define MAG_STRICT_BLOCKS 2
+#endif
+constexpr int kStrictThreads = 256, kStrictBlocks = MAG_STRICT_BLOCKS;
 #ifndef MAG_EDGE_TILE_SCHED
 #define MAG_EDGE_TILE_SCHED 1   /* 1: the edge schedule orders tiles (256 edges); 0: chunks of MAG_EDGE_CHUNK edges */
 #endif

@@ -1,0 +1,45 @@
+"""Small end-to-end exercise of every kernel family for compute-sanitizer (memcheck): all kinds, both fp modes, ownership,
+incoming flags, mixed mesh with layer check, 2-D part, streamed host call, weights, split vertices, cavity batches."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import core_b200 as cb
+rng = np.random.default_rng(3)
+n = 9
+xyz, ev, tv = cb.boxmesh.kuhn_box(n, n + 1, n - 1)
+xyz = cb.fields.jitter(xyz, 0.3 / n)
+h, R = cb.fields.shock_rotating(xyz, 1.0 / n)
+eo = (rng.random(len(ev)) < 0.9).astype(np.uint8)
+lo = (rng.random(len(tv)) < 0.9).astype(np.uint8)
+ef = np.zeros(len(ev), np.int32); ef[rng.random(len(ev)) < 0.2] |= cb.DONT_SPLIT
+lf = np.zeros(len(tv), np.int32); lf[rng.random(len(tv)) < 0.3] |= cb.OK_QUALITY
+p = cb.Part(0)
+p.set_mesh(xyz, ev, tv, edge_owned=eo, elem_owned=lo)
+for kind in ("identity", "iso", "aniso", "logm"):
+    if kind == "identity": p.set_size_field_identity()
+    elif kind == "iso": p.set_size_field_iso(h[:, 1].copy())
+    elif kind == "aniso": p.set_size_field_aniso(h, R)
+    else: p.set_size_field_logm_from_frames(h, R, 0)
+    for mode in (cb.FP_STRICT, cb.FP_FAST):
+        p.set_flags(ef, lf); p.sweep(cb.OP_ALL & ~cb.OP_LAYER_CHECK | cb.OP_LENGTH_SUM, fp_mode=mode); p.stats(); p.flags()
+        p.clear_flags(); p.sweep(cb.OP_ALL & ~cb.OP_LAYER_CHECK, use_max=False, fp_mode=mode); p.stats()
+        p.element_weights(fp_mode=mode); p.element_weights(0, 1, fp_mode=mode)
+        p.split_vertices(fp_mode=mode); p.near_threshold(0); p.near_threshold(1)
+        off = np.arange(0, len(tv) + 1, 3, dtype=np.int64); off[-1] = len(tv)
+        p.cavity_quality(off, tv, fp_mode=mode)
+oL, oq = np.empty(len(ev)), np.empty(len(tv))
+oe, ol = np.empty(len(ev), np.int32), np.empty(len(tv), np.int32)
+p.sweep_host(xyz, ev, tv, 2, h, R, edge_flags=ef, elem_flags=lf, edge_owned=eo, elem_owned=lo, out_lengths=oL, out_qualities=oq,
+             out_edge_flags=oe, out_elem_flags=ol, fp_mode=cb.FP_FAST, slice_entities=61440)
+p.clear_flags(); p.sweep(cb.OP_ALL & ~cb.OP_LAYER_CHECK, fp_mode=cb.FP_FAST); p.stats()
+x2, e2, t2, pr2 = cb.boxmesh.mixed_box(5, 2)
+ef2, lf2 = cb.boxmesh.layer_closure_flags(e2, pr2, None, len(t2))
+h2, R2 = cb.fields.shock_rotating(x2, 0.2)
+p.set_mesh(x2, e2, t2, prism_v=pr2); p.set_size_field_aniso(h2, R2); p.set_flags(ef2, lf2); p.sweep(cb.OP_ALL, fp_mode=cb.FP_FAST); p.stats(); p.layer_ok()
+x3, e3, tr3 = cb.boxmesh.tri_box(9, 7)
+h3, R3 = cb.fields.shock_rotating(x3, 1.0 / 8)
+p.set_mesh_2d(x3, e3, tr3); p.set_size_field_aniso(h3, R3)
+for mode in (cb.FP_STRICT, cb.FP_FAST):
+    p.clear_flags(); p.sweep(cb.OP_ALL & ~cb.OP_LAYER_CHECK, good_quality=0.2, fp_mode=mode); p.stats()
+p.close()
+print("sanitize_small: done")
