@@ -148,6 +148,50 @@ k_tet_weights(int32_t nt, int32_t elem_off, const int4* __restrict__ tet_v, cons
   if (eig) atomicAdd(&st->n_eigen_fail, 1ull);
 }
 
+// ------------------------------------------------------------------ short-edge classification
+// ShortEdgeFixer::shouldApply (ma/maShape.cc:188-219), the sweep fixElementShapes runs right after markBadQuality: for
+// every element carrying BAD_QUALITY, the measured lengths of its six edges in getDownward(tet, 1) order; if
+// max / min < maximumEdgeRatio the element is not a short-edge case and BAD_QUALITY is cleared, otherwise the FIRST
+// shortest edge is the one to remove.  The lengths are the resident results of the last MAG_OP_LENGTHS sweep.
+__global__ void __launch_bounds__(256)
+k_short_edges(int32_t nt, int32_t elem_off, const int32_t* __restrict__ tet_e, const double* __restrict__ len, double max_ratio,
+              int32_t* __restrict__ flags, int32_t* __restrict__ short_edge, unsigned long long* __restrict__ counts)
+{
+  unsigned cleared = 0, kept = 0;
+  const int32_t nloop = (nt + 255) / 256 * 256;
+  for (int32_t t = blockIdx.x * 256 + threadIdx.x; t < nloop; t += gridDim.x * 256) {
+    if (t < nt) {
+      const int32_t f = flags[elem_off + t];
+      int32_t pick = -1;
+      if (f & MAG_BAD_QUALITY) {
+        int32_t e[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) e[i] = __ldg(tet_e + 6 * (int64_t)t + i);
+        double lmax = __ldg(len + e[0]), lmin = lmax;
+        pick = e[0];
+#pragma unroll
+        for (int i = 1; i < 6; ++i) {
+          const double l = __ldg(len + e[i]);
+          if (l > lmax) lmax = l;
+          if (l < lmin) { lmin = l; pick = e[i]; }
+        }
+        if (__ddiv_rn(lmax, lmin) < max_ratio) {
+          flags[elem_off + t] = f & ~MAG_BAD_QUALITY;
+          pick = -1;
+          ++cleared;
+        } else ++kept;
+      }
+      short_edge[elem_off + t] = pick;
+    }
+  }
+  cleared = __reduce_add_sync(0xffffffffu, cleared);
+  kept = __reduce_add_sync(0xffffffffu, kept);
+  if ((threadIdx.x & 31) == 0) {
+    if (cleared) atomicAdd(&counts[0], (unsigned long long)cleared);
+    if (kept) atomicAdd(&counts[1], (unsigned long long)kept);
+  }
+}
+
 template <int KIND>
 int launch_weights(mag_ctx* c, double w_max, double w_min, bool fast, double* d_w)
 {
@@ -372,6 +416,44 @@ int mag_cavity_quality(mag_ctx* c, int64_t ncav, const int64_t* offsets, const i
   MAG_CUDA(c, cudaStreamSynchronize(c->stream));
   if (c->h_stats->n_eigen_fail)
     return mag_fail(c, MAG_ERR_EIGEN, "eigenQR failed in %llu blocks of the cavity sweep (apf::eigen asserts convergence, apfMatrix.cc:76)", c->h_stats->n_eigen_fail);
+  return MAG_OK;
+}
+
+int mag_short_edge_test(mag_ctx* c, const int32_t* tet_edges, double max_edge_ratio, int32_t* short_edge,
+                        int64_t* n_cleared, int64_t* n_short)
+{
+  if (!c) return MAG_ERR_ARG;
+  MAG_CUDA(c, cudaSetDevice(c->device));
+  if (c->dim != 3) return mag_fail(c, MAG_ERR_ARG, "mag_short_edge_test: 3-D parts only");
+  if (c->nt && !tet_edges) return mag_fail(c, MAG_ERR_ARG, "mag_short_edge_test: null tet_edges");
+  if (!(c->last_ops & MAG_OP_LENGTHS)) return mag_fail(c, MAG_ERR_ARG, "mag_short_edge_test: the last sweep did not measure the edges (MAG_OP_LENGTHS)");
+  for (int64_t i = 0; i < 6 * c->nt; ++i)
+    if (tet_edges[i] < 0 || tet_edges[i] >= c->ne) return mag_fail(c, MAG_ERR_ARG, "mag_short_edge_test: edge index %d out of range", tet_edges[i]);
+  int rc;
+  if ((rc = magi_materialize_flags(c))) return rc;
+  const int64_t nel = c->np + c->npy + c->nt;
+  if (n_cleared) *n_cleared = 0;
+  if (n_short) *n_short = 0;
+  if (c->nt == 0) return MAG_OK;
+  DevBuf te, se, cnt;
+  MAG_CUDA(c, cudaMalloc(&te.p, (size_t)c->nt * 24));
+  MAG_CUDA(c, cudaMalloc(&se.p, (size_t)nel * 4));
+  MAG_CUDA(c, cudaMalloc(&cnt.p, 16));
+  MAG_CUDA(c, cudaMemcpyAsync(te.p, tet_edges, (size_t)c->nt * 24, cudaMemcpyHostToDevice, c->stream));
+  MAG_CUDA(c, cudaMemsetAsync(se.p, 0xff, (size_t)nel * 4, c->stream));      // -1 on layer elements
+  MAG_CUDA(c, cudaMemsetAsync(cnt.p, 0, 16, c->stream));
+  const int64_t blocks = (c->nt + 255) / 256;
+  const unsigned g = (unsigned)(blocks < (int64_t)c->n_sms * 16 ? blocks : (int64_t)c->n_sms * 16);
+  k_short_edges<<<g, 256, 0, c->stream>>>((int32_t)c->nt, (int32_t)(c->np + c->npy), (const int32_t*)te.p, c->d_len, max_edge_ratio,
+                                          c->d_elem_flags, (int32_t*)se.p, (unsigned long long*)cnt.p);
+  MAG_CUDA(c, cudaGetLastError());
+  c->n_launches++;
+  unsigned long long h[2] = {0, 0};
+  if (short_edge) MAG_CUDA(c, cudaMemcpyAsync(short_edge, se.p, (size_t)nel * 4, cudaMemcpyDeviceToHost, c->stream));
+  MAG_CUDA(c, cudaMemcpyAsync(h, cnt.p, 16, cudaMemcpyDeviceToHost, c->stream));
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (n_cleared) *n_cleared = (int64_t)h[0];
+  if (n_short) *n_short = (int64_t)h[1];
   return MAG_OK;
 }
 

@@ -224,6 +224,16 @@ class Part:
                                             _ptr(worst), _ptr(q)))
         return (worst, q) if want_qualities else worst
 
+    def short_edge_test(self, tet_edges, max_edge_ratio):
+        """ShortEdgeFixer::shouldApply over every BAD_QUALITY tet (maShape.cc:188-219): returns (short_edge [nelem] with
+        -1 where nothing is to be removed, n_cleared, n_short); BAD_QUALITY is cleared on the resident flags where the
+        edge ratio is below max_edge_ratio."""
+        te = np.ascontiguousarray(tet_edges, dtype=np.int32)
+        out = np.empty(self.nelem, dtype=np.int32)
+        nc, ns = C.c_int64(0), C.c_int64(0)
+        self._ck(self._L.mag_short_edge_test(self._h, _ptr(te), float(max_edge_ratio), _ptr(out), C.byref(nc), C.byref(ns)))
+        return out, nc.value, ns.value
+
     def split_vertices(self, fp_mode=FP_STRICT):
         """ma::makeSplitVert for every SPLIT-marked edge, in edge order: (edge_idx, xyz, field_a, field_b) with
         (field_a, field_b) in the layout of the resident size field (iso: size[n]; aniso: h[n][3], R[n][9];

@@ -196,6 +196,14 @@ int mag_element_weights(mag_ctx* c, double w_max, double w_min, int fp_mode, dou
    The per-vertex transforms of the last sweep are reused while mesh and size field are unchanged.  Synchronous. */
 int mag_cavity_quality(mag_ctx* c, int64_t ncav, const int64_t* offsets, const int32_t* tet_v /*[.][4]*/,
                        int use_max_metric, int fp_mode, double* worst, double* qualities);
+/* ShortEdgeFixer::shouldApply (ma/maShape.cc:188-219), the classification sweep ma::fixElementShapes runs over the
+   BAD_QUALITY elements right after markBadQuality: tet_edges [nt][6] = the edge indices of every tet in
+   getDownward(tet, 1) order; the lengths are those of the last MAG_OP_LENGTHS sweep (resident).  For every tet carrying
+   BAD_QUALITY: if max / min edge length < max_edge_ratio (ma::Input::maximumEdgeRatio) the resident BAD_QUALITY bit is
+   cleared (not a short-edge case), otherwise short_edge[element] = the first shortest edge (the one ShortEdgeRemover is
+   given).  short_edge [np+npy+nt] (may be NULL), -1 where nothing is to be removed.  Synchronous. */
+int mag_short_edge_test(mag_ctx* c, const int32_t* tet_edges, double max_edge_ratio, int32_t* short_edge,
+                        int64_t* n_cleared, int64_t* n_short);
 /* Size-field transfer to the vertices that will split the SPLIT-marked edges (ma::makeSplitVert, ma/maRefine.cc:129-151;
    SizeField::interpolate, ma/maSize.cc:414-429,523-534): for every edge whose resident flag word carries MAG_SPLIT, in
    edge order, the edge index, the position of the new vertex (xi = 0) and the size-field values it receives --

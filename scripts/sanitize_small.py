@@ -27,6 +27,10 @@ for kind in ("identity", "iso", "aniso", "logm"):
         p.split_vertices(fp_mode=mode); p.near_threshold(0); p.near_threshold(1)
         off = np.arange(0, len(tv) + 1, 3, dtype=np.int64); off[-1] = len(tv)
         p.cavity_quality(off, tv, fp_mode=mode)
+key = lambda a, b: np.minimum(a, b).astype(np.int64) * (1 << 32) + np.maximum(a, b)
+ek = key(ev[:, 0], ev[:, 1]); order = np.argsort(ek)
+te = np.stack([order[np.searchsorted(ek[order], key(tv[:, a], tv[:, b]))] for a, b in ((0, 1), (1, 2), (2, 0), (0, 3), (1, 3), (2, 3))], axis=1).astype(np.int32)
+p.short_edge_test(te, 2.0)
 oL, oq = np.empty(len(ev)), np.empty(len(tv))
 oe, ol = np.empty(len(ev), np.int32), np.empty(len(tv), np.int32)
 p.sweep_host(xyz, ev, tv, 2, h, R, edge_flags=ef, elem_flags=lf, edge_owned=eo, elem_owned=lo, out_lengths=oL, out_qualities=oq,

@@ -186,6 +186,45 @@ def test_cavity_quality_golden(cb, name):
     p.close()
 
 
+def tet_edge_table(edge_v, tet_v):
+    """[nt,6] edge indices of every tet in getDownward(tet, 1) order = tet_edge_verts {01,12,20,03,13,23} (apfMesh.cc:53-60)."""
+    key = lambda a, b: np.minimum(a, b).astype(np.int64) * (1 << 32) + np.maximum(a, b)
+    ek = key(edge_v[:, 0], edge_v[:, 1])
+    order = np.argsort(ek)
+    cols = [order[np.searchsorted(ek[order], key(tet_v[:, a], tet_v[:, b]))] for a, b in ((0, 1), (1, 2), (2, 0), (0, 3), (1, 3), (2, 3))]
+    return np.ascontiguousarray(np.stack(cols, axis=1), dtype=np.int32)
+
+
+@pytest.mark.parametrize("name", ["jbox7_shock_rot_aniso", "jbox7_random_aniso_flags", "box6_shock_planar_aniso"])
+def test_short_edge_classification(cb, name):
+    """ShortEdgeFixer::shouldApply (maShape.cc:188-219) over the BAD_QUALITY tets.  The class is local to maShape.cc, so it
+    cannot be called in the compiled reference; the expectation is its few lines restated with numpy on the REFERENCE's
+    own lengths and flags (golden vectors): ratio test max/min < maximumEdgeRatio, first shortest edge otherwise."""
+    g = util.load(name)
+    kind, ma, mb = util.metric_arrays(g)
+    _, _, tet_v = util.split_elements(g)
+    te = tet_edge_table(g["edge_v"], tet_v)
+    gq = float(g["good_quality"])
+    gq = 0.027 if gq < 0 else gq
+    p = cb.Part(0)
+    p.set_mesh(g["xyz"], g["edge_v"], tet_v)
+    util.set_part_metric(p, kind, ma, mb)
+    for ratio in (2.0, 100.0, 1.0):            # maInput.cc:35,43 defaults; 1.0 clears nothing
+        p.set_flags(g["edge_flags_in"], g["elem_flags_in"])
+        p.sweep(cb.OP_ALL & ~cb.OP_LAYER_CHECK, good_quality=gq, fp_mode=cb.FP_STRICT)
+        short, n_cleared, n_short = p.short_edge_test(te, ratio)
+        bad = (g["elem_flags_out"] & cb.BAD_QUALITY) != 0
+        l = g["lengths"][te]
+        cleared = bad & (l.max(axis=1) / l.min(axis=1) < ratio)
+        want = np.where(bad & ~cleared, te[np.arange(len(te)), l.argmin(axis=1)], -1)
+        assert np.array_equal(short, want)
+        assert (n_cleared, n_short) == (int(cleared.sum()), int((bad & ~cleared).sum()))
+        lf = p.flags()[1]
+        assert np.array_equal(lf, np.where(cleared, g["elem_flags_out"] & ~cb.BAD_QUALITY, g["elem_flags_out"]))
+    assert bad.sum() > 0
+    p.close()
+
+
 def test_cavity_quality_candidate_tets_vs_oracle(cb):
     """Would-be elements: random vertex quadruples (many inverted -> negative qualities) that are not mesh entities,
     ragged cavities of 1..40 tets, against the restated oracle; error paths of the batch call."""
