@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--n", "--cells", dest="n", type=int, default=203, help="cells per side of each part's box")
     ap.add_argument("--fp", default=os.environ.get("MAG_BENCH_FP", "fast"), choices=["strict", "fast"])
     ap.add_argument("--field", default="aniso", choices=["aniso", "logm", "iso"])
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-n", type=int, default=0, help="box size of the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--jitter", type=float, default=0.0,
@@ -258,6 +258,8 @@ def run_reference_arm(a):
 def bind_to_gpu_numa_node(gpu_index):
     """Runs this rank on the CPUs nearest to its GPU (NVML's ideal CPU affinity), so that the pinned host buffers of the
     end-to-end leg are allocated on that NUMA node and their copies do not cross the socket interconnect."""
+    if os.environ.get("MAG_BENCH_NO_BIND"):
+        return
     try:
         import pynvml
         pynvml.nvmlInit()
