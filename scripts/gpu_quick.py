@@ -28,7 +28,7 @@ for name, kind, ma, mb, setter in (("identity", mao.IDENTITY, None, None, lambda
     L0 = mao.edge_lengths(kind, xyz, ma, mb, ev)
     q0 = mao.tet_qualities(kind, xyz, ma, mb, tv)
     ef0 = np.zeros(len(ev), np.int32); lf0 = np.zeros(len(tv), np.int32)
-    ns = mao.mark_edges_to_split(L0, ef0); nc = mao.mark_edges_to_collapse(L0, ef0); nb = mao.mark_bad_quality(q0, lf0, 0.027)
+    ns = mao.mark_edges_to_split(L0, ef0, None, kind); nc = mao.mark_edges_to_collapse(L0, ef0, None, kind); nb = mao.mark_bad_quality(q0, lf0, 0.027)
     for mode in (cb.FP_STRICT, cb.FP_FAST):
         p.set_flags(None, None)
         p.sweep(cb.OP_ALL & ~cb.OP_LAYER_CHECK, fp_mode=mode)
