@@ -585,6 +585,22 @@ def test_full_size_properties(cb):
     stt = rng.choice(len(tv), 300000, replace=False)
     assert np.array_equal(mao.edge_lengths(mao.ANISO, xyz, h, R, ev[se]), L0[se])
     assert np.array_equal(mao.tet_qualities(mao.ANISO, xyz, h, R, tv[stt]), q0[stt])
+    # the rows either side of the path at full size: fast weights agree with the reference-order ones, every SPLIT edge
+    # gets exactly one split vertex in edge order, and the streamed one-call path returns what the resident calls returned
+    w_strict, w_fast = p.element_weights(fp_mode=cb.FP_STRICT), p.element_weights(fp_mode=cb.FP_FAST)
+    assert util.rel_err(w_fast, w_strict) < TOL
+    assert np.array_equal(mao.tet_weights(mao.ANISO, xyz, h, R, tv[stt[:50000]]), w_strict[stt[:50000]])
+    idx, sx, sa, sb = p.split_vertices()
+    assert len(idx) == s1["n_split"] and np.array_equal(idx, np.nonzero(ef1 & cb.SPLIT)[0])
+    assert np.array_equal(sx[:1000], 0.5 * xyz[ev[idx[:1000], 0]] + 0.5 * xyz[ev[idx[:1000], 1]])
+    del sx, sa, sb
+    oL, oq = np.empty(len(ev)), np.empty(len(tv))
+    oef, olf = np.empty(len(ev), np.int32), np.empty(len(tv), np.int32)
+    sth = p.sweep_host(xyz, ev, tv, 2, h, R, out_lengths=oL, out_qualities=oq, out_edge_flags=oef, out_elem_flags=olf,
+                       ops=cb.OP_ALL & ~cb.OP_LAYER_CHECK, fp_mode=cb.FP_FAST)
+    assert np.array_equal(oL, L1) and np.array_equal(oq, q1) and np.array_equal(oef, ef1) and np.array_equal(olf, lf1)
+    assert all(sth[k] == s1[k] for k in ("n_split", "n_collapse", "n_bad", "min_quality", "max_length", "n_near_threshold"))
+    del oL, oq, oef, olf
     # entity-order invariance
     p.set_mesh(xyz, ev[::-1].copy(), tv[::-1].copy())   # a new mesh starts with zero flag words
     p.set_size_field_aniso(h, R)
