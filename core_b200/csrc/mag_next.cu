@@ -148,6 +148,246 @@ k_tet_weights(int32_t nt, int32_t elem_off, const int4* __restrict__ tet_v, cons
   if (eig) atomicAdd(&st->n_eigen_fail, 1ull);
 }
 
+// measure(triangle) on a 2-D part: TriangleIntegration::N2 (apf/apfIntegrate.cc:146-159), three points of weight 1/3/2;
+// dV2 = |row0(J Q) x row1(J Q)| (getJacobianDeterminant(., 2), apf/apfVectorElement.cc:75-84); triangle shape values
+// apf/apfShape.cc:141-160; parentMeasure[TRIANGLE] = 1/2 (ma/maSize.cc:150).  MAG_FP_FAST runs the same steps with
+// contracted arithmetic (a 2-D part is never large enough for the gathers to matter).
+template <int KIND, class OPS>
+__device__ __forceinline__ double tri_weight(const double* __restrict__ vedge, const int32_t* __restrict__ tv, int* eig_fail)
+{
+  typedef MagMath<OPS> MM;
+  if (KIND == MAG_KIND_IDENTITY) return 1.0;
+  constexpr int N = (KIND == MAG_KIND_ISO) ? 4 : 12;
+  double rec[3][N];
+#pragma unroll
+  for (int n = 0; n < 3; ++n) {
+    const int32_t v = __ldg(tv + n) & kVidMask;
+    if (KIND == MAG_KIND_ISO) load_rec4(vedge, v, rec[n]);
+    else {
+      Rec12 r = load_rec12(vedge, v);
+#pragma unroll
+      for (int i = 0; i < 12; ++i) rec[n][i] = r.v[i];
+    }
+  }
+  double J[2][3];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) J[i][c] = MM::add(-rec[0][c], rec[i + 1][c]);
+  constexpr double A = 0.666666666666667, B = 0.166666666666667;
+  double measurement = 0.0;
+#pragma unroll 1
+  for (int p = 0; p < 3; ++p) {
+    const double xi0 = p == 0 ? A : B, xi1 = p == 1 ? A : B;
+    const double Ns[3] = {1 - xi0 - xi1, xi0, xi1};
+    double c[N - 3];
+#pragma unroll
+    for (int i = 0; i < N - 3; ++i) {
+      double v = MM::mul(rec[0][3 + i], Ns[0]);
+#pragma unroll
+      for (int n = 1; n < 3; ++n) v = MM::add(v, MM::mul(rec[n][3 + i], Ns[n]));
+      c[i] = v;
+    }
+    M3 Q;
+    if (KIND == MAG_KIND_ISO) {
+      MM::identity(Q);
+      const double ih = MM::div(1.0, c[0]);
+      Q.m[0][0] = ih; Q.m[1][1] = ih; Q.m[2][2] = ih;
+    } else if (KIND == MAG_KIND_ANISO) {
+      MM::transform_aniso(V3{c[3], c[4], c[5]}, V3{c[6], c[7], c[8]}, c[0], c[1], c[2], Q);
+    } else {
+      M3 L;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) L.m[i / 3][i % 3] = c[i];
+      if (MM::transform_logm(L, Q) != 1) *eig_fail = 1;
+    }
+    V3 jq[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      jq[i].x = MM::add(MM::add(MM::mul(J[i][0], Q.m[0][0]), MM::mul(J[i][1], Q.m[1][0])), MM::mul(J[i][2], Q.m[2][0]));
+      jq[i].y = MM::add(MM::add(MM::mul(J[i][0], Q.m[0][1]), MM::mul(J[i][1], Q.m[1][1])), MM::mul(J[i][2], Q.m[2][1]));
+      jq[i].z = MM::add(MM::add(MM::mul(J[i][0], Q.m[0][2]), MM::mul(J[i][1], Q.m[1][2])), MM::mul(J[i][2], Q.m[2][2]));
+    }
+    const double wdv = MM::mul(1. / 3. / 2.0, MM::length(MM::cross(jq[0], jq[1])));
+    measurement = p == 0 ? wdv : MM::add(measurement, wdv);
+  }
+  return MM::div(measurement, 1.0 / 2.0);   // parentMeasure[TRIANGLE]
+}
+
+template <int KIND, bool FAST>
+__global__ void __launch_bounds__(kWThreads)
+k_tri_weights(int32_t nt, const int32_t* __restrict__ tri_v, const double* __restrict__ vedge, double w_max, double w_min,
+              double* __restrict__ weight, MagDevStats* st)
+{
+  int eig = 0;
+  for (int32_t t = blockIdx.x * kWThreads + threadIdx.x; t < nt; t += gridDim.x * kWThreads) {
+    double w = FAST ? tri_weight<KIND, FusedOps>(vedge, tri_v + 3 * (int64_t)t, &eig)
+                    : tri_weight<KIND, StrictOps>(vedge, tri_v + 3 * (int64_t)t, &eig);
+    if (w > w_max) w = w_max;
+    else if (w < w_min) w = w_min;
+    weight[t] = w;
+  }
+  if (eig) atomicAdd(&st->n_eigen_fail, 1ull);
+}
+
+// ------------------------------------------------------------------ sliver classification
+// ma::getSliverCode / matchSliver (ma/maShape.cc:35-120), the classification LargeAngleTetFixer runs over the BAD_QUALITY
+// tets: J (apfVectorElement.cc:44-52) and Q = getTransform at the centroid, J = J Q; the quality of the tet's FIRST face
+// (measureTriQuality with the transform of its largest-determinant vertex -- m->getDimension() is 3, maQuality.cc:86-100 --
+// walking the FACE's own vertex order) against goodQuality^2 decides between projecting vertex 3 onto the face and
+// projecting edge 0-2 onto edge 0-1.  apf::project apfVector.h:134-137; apf::invert apfMatrix.h:165-173.  Always in the
+// reference's operation order (StrictOps): the outputs are bit codes decided by comparisons.
+__constant__ signed char c_sliver_table2d[4][4][2] =
+  {{{-1,-1}, {-1,-1}, {-1,-1}, {-1,-1}},
+   {{ 7, 2}, {-1,-1}, { 3, 3}, {-1,-1}},
+   {{ 1, 2}, { 2, 3}, {-1,-1}, {-1,-1}},
+   {{ 3, 2}, { 2, 3}, { 3, 3}, {-1,-1}}};
+__constant__ signed char c_sliver_table[8][8][2] =
+  {{{-1,-1}, {-1,-1}, {-1,-1}, {-1,-1}, {-1,-1}, {-1,-1}, {-1,-1}, {-1,-1}},
+   {{ 4, 1}, {-1,-1}, {10, 2}, { 6, 3}, { 4, 2}, { 5, 3}, { 0, 3}, {-1,-1}},
+   {{ 1, 1}, { 8, 2}, {-1,-1}, { 6, 3}, { 9, 2}, { 5, 3}, { 0, 3}, {-1,-1}},
+   {{ 2, 0}, { 8, 2}, {10, 2}, {-1,-1}, { 0, 2}, { 5, 3}, { 0, 3}, {-1,-1}},
+   {{ 2, 1}, {11, 2}, { 2, 2}, { 6, 3}, {-1,-1}, { 5, 3}, { 0, 3}, {-1,-1}},
+   {{ 0, 0}, {11, 2}, { 6, 2}, { 6, 3}, { 4, 2}, {-1,-1}, { 0, 3}, {-1,-1}},
+   {{ 1, 0}, { 5, 2}, { 2, 2}, { 6, 3}, { 9, 2}, { 5, 3}, {-1,-1}, {-1,-1}},
+   {{ 0, 1}, { 5, 2}, { 6, 2}, { 6, 3}, { 0, 2}, { 5, 3}, { 0, 3}, {-1,-1}}};
+
+__device__ __forceinline__ V3 project_onto(const V3& a, const V3& b)
+{
+  const double s = magst::div(magst::dot(a, b), magst::dot(b, b));
+  return V3{magst::mul(b.x, s), magst::mul(b.y, s), magst::mul(b.z, s)};
+}
+// basisPoint = invert(transpose(J)) * p with J rows j0, j1, j2: rows of the inverse = cross products of J's rows over det(J^T)
+__device__ __forceinline__ void area_point(const V3& j0, const V3& j1, const V3& j2, const V3& p, double area[3])
+{
+  M3 JT;
+  JT.m[0][0] = j0.x; JT.m[1][0] = j0.y; JT.m[2][0] = j0.z;
+  JT.m[0][1] = j1.x; JT.m[1][1] = j1.y; JT.m[2][1] = j1.z;
+  JT.m[0][2] = j2.x; JT.m[1][2] = j2.y; JT.m[2][2] = j2.z;
+  const double d = magst::det3(JT);
+  const V3 r0 = magst::cross(j1, j2), r1 = magst::cross(j2, j0);
+  const double b0 = magst::dot(V3{magst::div(r0.x, d), magst::div(r0.y, d), magst::div(r0.z, d)}, p);
+  const double b1 = magst::dot(V3{magst::div(r1.x, d), magst::div(r1.y, d), magst::div(r1.z, d)}, p);
+  area[0] = magst::sub(magst::sub(1.0, b0), b1);
+  area[1] = b0;
+  area[2] = b1;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kWThreads)
+k_sliver_codes(int32_t nt, int32_t elem_off, const int4* __restrict__ tet_v, const int32_t* __restrict__ face0_v,
+               const double* __restrict__ vedge, const double* __restrict__ vpos, const double* __restrict__ vq,
+               const int32_t* __restrict__ flags, int only_bad, double good_quality, int32_t* __restrict__ codes,
+               int32_t* __restrict__ match, MagDevStats* st)
+{
+  int eig = 0;
+  for (int32_t t = blockIdx.x * kWThreads + threadIdx.x; t < nt; t += gridDim.x * kWThreads) {
+    int code = 0, rot = -1, idx = -1;
+    if (!only_bad || (flags[elem_off + t] & MAG_BAD_QUALITY)) {
+      const int4 tv = __ldg(tet_v + t);
+      const int32_t vid[4] = {tv.x & kVidMask, tv.y, tv.z, tv.w};
+      // centroid transform: N = (1 - .25 - .25 - .25, .25, .25, .25)
+      constexpr int N = (KIND == MAG_KIND_ISO || KIND == MAG_KIND_IDENTITY) ? 4 : 12;
+      double rec[4][N];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        if (N == 4) load_rec4(vedge, vid[n], rec[n]);
+        else {
+          Rec12 r = load_rec12(vedge, vid[n]);
+#pragma unroll
+          for (int i = 0; i < 12; ++i) rec[n][i] = r.v[i];
+        }
+      }
+      M3 Q;
+      if (KIND == MAG_KIND_IDENTITY) magst::identity(Q);
+      else {
+        const double Ns[4] = {1 - .25 - .25 - .25, .25, .25, .25};
+        double cf[N - 3];
+#pragma unroll
+        for (int i = 0; i < N - 3; ++i) {
+          double v = magst::mul(rec[0][3 + i], Ns[0]);
+#pragma unroll
+          for (int n = 1; n < 4; ++n) v = magst::add(v, magst::mul(rec[n][3 + i], Ns[n]));
+          cf[i] = v;
+        }
+        if (KIND == MAG_KIND_ISO) {
+          magst::identity(Q);
+          const double ih = magst::div(1.0, cf[0]);
+          Q.m[0][0] = ih; Q.m[1][1] = ih; Q.m[2][2] = ih;
+        } else if (KIND == MAG_KIND_ANISO) {
+          magst::transform_aniso(V3{cf[3], cf[4], cf[5]}, V3{cf[6], cf[7], cf[8]}, cf[0], cf[1], cf[2], Q);
+        } else {
+          M3 L;
+#pragma unroll
+          for (int i = 0; i < 9; ++i) L.m[i / 3][i % 3] = cf[i];
+          if (magst::transform_logm(L, Q) != 1) eig = 1;
+        }
+      }
+      V3 j[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const double a = magst::add(-rec[0][0], rec[i + 1][0]), b = magst::add(-rec[0][1], rec[i + 1][1]),
+                     cz = magst::add(-rec[0][2], rec[i + 1][2]);
+        j[i].x = magst::add(magst::add(magst::mul(a, Q.m[0][0]), magst::mul(b, Q.m[1][0])), magst::mul(cz, Q.m[2][0]));
+        j[i].y = magst::add(magst::add(magst::mul(a, Q.m[0][1]), magst::mul(b, Q.m[1][1])), magst::mul(cz, Q.m[2][1]));
+        j[i].z = magst::add(magst::add(magst::mul(a, Q.m[0][2]), magst::mul(b, Q.m[1][2])), magst::mul(cz, Q.m[2][2]));
+      }
+      // quality of the first face with the transform of its largest-determinant vertex (strict >, first maximum wins)
+      int32_t fv[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) fv[i] = face0_v ? __ldg(face0_v + 3 * (int64_t)t + i) : vid[i];
+      V3 fx[3];
+      int32_t vb = fv[0];
+      double maxJ = -1.0;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        double p[4];
+        load_rec4(vpos, fv[i], p);
+        fx[i] = V3{p[0], p[1], p[2]};
+        if (p[3] > maxJ) { maxJ = p[3]; vb = fv[i]; }
+      }
+      M3 Qf;
+      {
+        const double2 q0 = __ldg(chunk_ptr<5>(vq, 0, vb)), q1 = __ldg(chunk_ptr<5>(vq, 1, vb)), q2 = __ldg(chunk_ptr<5>(vq, 2, vb)),
+                      q3 = __ldg(chunk_ptr<5>(vq, 3, vb)), q4 = __ldg(chunk_ptr<5>(vq, 4, vb));
+        Qf.m[0][0] = q0.x; Qf.m[0][1] = q0.y; Qf.m[0][2] = q1.x;
+        Qf.m[1][0] = q1.y; Qf.m[1][1] = q2.x; Qf.m[1][2] = q2.y;
+        Qf.m[2][0] = q3.x; Qf.m[2][1] = q3.y; Qf.m[2][2] = q4.x;
+      }
+      const double f0 = magst::tri_quality(fx, Qf);
+      double area[3];
+      if (magst::mul(magst::mul(f0, f0), f0) > magst::mul(good_quality, good_quality)) {
+        const V3 v03 = j[2];
+        const V3 nrm = magst::cross(j[0], j[1]);
+        const V3 pr = project_onto(v03, nrm);
+        const V3 projected = V3{magst::sub(v03.x, pr.x), magst::sub(v03.y, pr.y), magst::sub(v03.z, pr.z)};
+        area_point(j[0], j[1], nrm, projected, area);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) if (area[i] > 0) code |= (1 << i);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) if (area[i] > -0.10 && area[i] < 0.10) code |= ((1 << i) << 3);
+        rot = c_sliver_table[code & 7][(code >> 3) & 7][0];
+        idx = c_sliver_table[code & 7][(code >> 3) & 7][1];
+      } else {
+        code |= (1 << 6);
+        const V3 projected = project_onto(j[1], j[0]);
+        const V3 nrm = magst::cross(j[0], j[1]);
+        area_point(j[0], j[1], nrm, projected, area);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) if (area[i] > 0) code |= ((1 << i) << 7);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) if (area[i] > -0.20 && area[i] < 0.20) code |= ((1 << i) << 9);
+        rot = c_sliver_table2d[(code >> 7) & 3][(code >> 9) & 3][0];
+        idx = c_sliver_table2d[(code >> 7) & 3][(code >> 9) & 3][1];
+      }
+    }
+    codes[elem_off + t] = code;
+    match[2 * (int64_t)(elem_off + t)] = rot;
+    match[2 * (int64_t)(elem_off + t) + 1] = idx;
+  }
+  if (eig) atomicAdd(&st->n_eigen_fail, 1ull);
+}
+
 // ------------------------------------------------------------------ short-edge classification
 // ShortEdgeFixer::shouldApply (ma/maShape.cc:188-219), the sweep fixElementShapes runs right after markBadQuality: for
 // every element carrying BAD_QUALITY, the measured lengths of its six edges in getDownward(tet, 1) order; if
@@ -202,6 +442,18 @@ int launch_weights(mag_ctx* c, double w_max, double w_min, bool fast, double* d_
   const int32_t off = (int32_t)(c->np + c->npy);
   if (fast) k_tet_weights<KIND, true><<<g, 256, 0, c->stream>>>((int32_t)c->nt, off, tv, c->d_vedge, w_max, w_min, d_w, c->d_stats);
   else k_tet_weights<KIND, false><<<g, kWThreads, 0, c->stream>>>((int32_t)c->nt, off, tv, c->d_vedge, w_max, w_min, d_w, c->d_stats);
+  MAG_CUDA(c, cudaGetLastError());
+  c->n_launches++;
+  return MAG_OK;
+}
+
+template <int KIND>
+int launch_tri_weights(mag_ctx* c, double w_max, double w_min, bool fast, double* d_w)
+{
+  const int64_t blocks = (c->ntri + kWThreads - 1) / kWThreads;
+  const unsigned g = (unsigned)(blocks < (int64_t)c->n_sms * 32 ? blocks : (int64_t)c->n_sms * 32);
+  if (fast) k_tri_weights<KIND, true><<<g, kWThreads, 0, c->stream>>>((int32_t)c->ntri, c->d_tri_v, c->d_vedge, w_max, w_min, d_w, c->d_stats);
+  else k_tri_weights<KIND, false><<<g, kWThreads, 0, c->stream>>>((int32_t)c->ntri, c->d_tri_v, c->d_vedge, w_max, w_min, d_w, c->d_stats);
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;
   return MAG_OK;
@@ -353,8 +605,7 @@ int mag_element_weights(mag_ctx* c, double w_max, double w_min, int fp_mode, dou
   MAG_CUDA(c, cudaSetDevice(c->device));
   if (c->kind == MAG_KIND_NONE) return mag_fail(c, MAG_ERR_ARG, "mag_element_weights: no size field set");
   if (fp_mode != MAG_FP_STRICT && fp_mode != MAG_FP_FAST) return mag_fail(c, MAG_ERR_ARG, "mag_element_weights: bad fp_mode %d", fp_mode);
-  if (c->ntri) return mag_fail(c, MAG_ERR_ARG, "mag_element_weights: 2-D parts are not supported yet");
-  const int64_t nel = c->np + c->npy + c->nt;
+  const int64_t nel = c->np + c->npy + c->nt + c->ntri;
   if (nel == 0) return MAG_OK;
   if (!c->d_weight) MAG_CUDA(c, cudaMalloc((void**)&c->d_weight, (size_t)nel * sizeof(double)));
   // layer elements: the reference weighs a prism by its base triangle (maBalance.cc:31-37), which needs the face's own
@@ -369,6 +620,17 @@ int mag_element_weights(mag_ctx* c, double w_max, double w_min, int fp_mode, dou
       case MAG_KIND_ISO: rc = launch_weights<MAG_KIND_ISO>(c, w_max, w_min, fast, c->d_weight); break;
       case MAG_KIND_ANISO: rc = launch_weights<MAG_KIND_ANISO>(c, w_max, w_min, fast, c->d_weight); break;
       default: rc = launch_weights<MAG_KIND_LOGM>(c, w_max, w_min, fast, c->d_weight); break;
+    }
+    if (rc) return rc;
+  }
+  if (c->ntri) {
+    const bool fast = fp_mode == MAG_FP_FAST;
+    int rc;
+    switch (c->kind) {
+      case MAG_KIND_IDENTITY: rc = launch_tri_weights<MAG_KIND_IDENTITY>(c, w_max, w_min, fast, c->d_weight); break;
+      case MAG_KIND_ISO: rc = launch_tri_weights<MAG_KIND_ISO>(c, w_max, w_min, fast, c->d_weight); break;
+      case MAG_KIND_ANISO: rc = launch_tri_weights<MAG_KIND_ANISO>(c, w_max, w_min, fast, c->d_weight); break;
+      default: rc = launch_tri_weights<MAG_KIND_LOGM>(c, w_max, w_min, fast, c->d_weight); break;
     }
     if (rc) return rc;
   }
@@ -416,6 +678,61 @@ int mag_cavity_quality(mag_ctx* c, int64_t ncav, const int64_t* offsets, const i
   MAG_CUDA(c, cudaStreamSynchronize(c->stream));
   if (c->h_stats->n_eigen_fail)
     return mag_fail(c, MAG_ERR_EIGEN, "eigenQR failed in %llu blocks of the cavity sweep (apf::eigen asserts convergence, apfMatrix.cc:76)", c->h_stats->n_eigen_fail);
+  return MAG_OK;
+}
+
+int mag_sliver_codes(mag_ctx* c, const int32_t* face0_v, double good_quality, int only_bad, int32_t* codes, int32_t* match)
+{
+  if (!c) return MAG_ERR_ARG;
+  MAG_CUDA(c, cudaSetDevice(c->device));
+  if (c->kind == MAG_KIND_NONE) return mag_fail(c, MAG_ERR_ARG, "mag_sliver_codes: no size field set");
+  if (c->dim != 3) return mag_fail(c, MAG_ERR_ARG, "mag_sliver_codes: 3-D parts only");
+  if (!codes || !match) return mag_fail(c, MAG_ERR_ARG, "mag_sliver_codes: null output");
+  if (face0_v)
+    for (int64_t i = 0; i < 3 * c->nt; ++i)
+      if (face0_v[i] < 0 || face0_v[i] >= c->nv) return mag_fail(c, MAG_ERR_ARG, "mag_sliver_codes: vertex id %d out of range", face0_v[i]);
+  const int64_t nel = c->np + c->npy + c->nt;
+  if (nel == 0) return MAG_OK;
+  int rc;
+  if (only_bad && (rc = magi_materialize_flags(c))) return rc;
+  if (!c->vertex_pass_valid) {
+    if ((rc = magk_vertex_pass(c))) return rc;
+    c->vertex_pass_valid = true;
+  }
+  DevBuf f0, dc, dm;
+  if (face0_v && c->nt) {
+    MAG_CUDA(c, cudaMalloc(&f0.p, (size_t)c->nt * 12));
+    MAG_CUDA(c, cudaMemcpyAsync(f0.p, face0_v, (size_t)c->nt * 12, cudaMemcpyHostToDevice, c->stream));
+  }
+  MAG_CUDA(c, cudaMalloc(&dc.p, (size_t)nel * 4));
+  MAG_CUDA(c, cudaMalloc(&dm.p, (size_t)nel * 8));
+  // layer elements: code 0, no match
+  MAG_CUDA(c, cudaMemsetAsync(dc.p, 0, (size_t)nel * 4, c->stream));
+  MAG_CUDA(c, cudaMemsetAsync(dm.p, 0xff, (size_t)nel * 8, c->stream));
+  MAG_CUDA(c, cudaMemsetAsync(&c->d_stats->n_eigen_fail, 0, sizeof(unsigned long long), c->stream));
+  if (c->nt) {
+    const int64_t blocks = (c->nt + kWThreads - 1) / kWThreads;
+    const unsigned g = (unsigned)(blocks < (int64_t)c->n_sms * 32 ? blocks : (int64_t)c->n_sms * 32);
+    const int4* tv = reinterpret_cast<const int4*>(c->d_tet_v);
+    const int32_t off = (int32_t)(c->np + c->npy);
+#define MAG_SLIVER(K) k_sliver_codes<K><<<g, kWThreads, 0, c->stream>>>((int32_t)c->nt, off, tv, (const int32_t*)f0.p, c->d_vedge, \
+      c->d_vpos, c->d_vq, c->d_elem_flags, only_bad, good_quality, (int32_t*)dc.p, (int32_t*)dm.p, c->d_stats)
+    switch (c->kind) {
+      case MAG_KIND_IDENTITY: MAG_SLIVER(MAG_KIND_IDENTITY); break;
+      case MAG_KIND_ISO: MAG_SLIVER(MAG_KIND_ISO); break;
+      case MAG_KIND_ANISO: MAG_SLIVER(MAG_KIND_ANISO); break;
+      default: MAG_SLIVER(MAG_KIND_LOGM); break;
+    }
+#undef MAG_SLIVER
+    MAG_CUDA(c, cudaGetLastError());
+    c->n_launches++;
+  }
+  MAG_CUDA(c, cudaMemcpyAsync(codes, dc.p, (size_t)nel * 4, cudaMemcpyDeviceToHost, c->stream));
+  MAG_CUDA(c, cudaMemcpyAsync(match, dm.p, (size_t)nel * 8, cudaMemcpyDeviceToHost, c->stream));
+  MAG_CUDA(c, cudaMemcpyAsync(&c->h_stats->n_eigen_fail, &c->d_stats->n_eigen_fail, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->h_stats->n_eigen_fail)
+    return mag_fail(c, MAG_ERR_EIGEN, "eigenQR failed in %llu blocks of the sliver sweep (apf::eigen asserts convergence, apfMatrix.cc:76)", c->h_stats->n_eigen_fail);
   return MAG_OK;
 }
 

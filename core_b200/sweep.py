@@ -234,6 +234,16 @@ class Part:
         self._ck(self._L.mag_short_edge_test(self._h, _ptr(te), float(max_edge_ratio), _ptr(out), C.byref(nc), C.byref(ns)))
         return out, nc.value, ns.value
 
+    def sliver_codes(self, face0_v=None, good_quality=0.027, only_bad=False):
+        """ma::getSliverCode / matchSliver (maShape.cc:35-120) of every tet (or every BAD_QUALITY tet): (codes [nelem],
+        match [nelem][2] = {rotation, code_index}, -1 = no match).  face0_v [nt][3] = the first face's vertices in the
+        face's own order (None: the tet's v0, v1, v2)."""
+        f0 = None if face0_v is None else np.ascontiguousarray(face0_v, dtype=np.int32)
+        codes = np.empty(self.nelem, dtype=np.int32)
+        match = np.empty((self.nelem, 2), dtype=np.int32)
+        self._ck(self._L.mag_sliver_codes(self._h, _ptr(f0), float(good_quality), int(bool(only_bad)), _ptr(codes), _ptr(match)))
+        return codes, match
+
     def split_vertices(self, fp_mode=FP_STRICT):
         """ma::makeSplitVert for every SPLIT-marked edge, in edge order: (edge_idx, xyz, field_a, field_b) with
         (field_a, field_b) in the layout of the resident size field (iso: size[n]; aniso: h[n][3], R[n][9];

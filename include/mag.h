@@ -185,7 +185,9 @@ int mag_sweep_host(mag_ctx* c, const mag_host_part* in, const mag_host_result* o
    apf/apfIntegrate.cc:328-342 with getTransform at every point), clamped to [w_min, w_max] as clampForIterations does
    (w_max = 2^(dim * refinesLeft), w_min = 4^(-coarsensLeft), maBalance.cc:41-52; pass +-HUGE_VAL for the raw weight).
    out [np+npy+nt] host (may be NULL: the weights stay on the device); prisms / pyramids get 0 (the reference weighs
-   a prism by its base triangle, which needs that face's own vertex order).  Synchronous. */
+   a prism by its base triangle, which needs that face's own vertex order).  On a 2-D part (mag_set_mesh_2d) the elements
+   are triangles: 3-point rule apf/apfIntegrate.cc:146-159, dV = |row0(J Q) x row1(J Q)|, parent measure 1/2, out [ntri].
+   Synchronous. */
 int mag_element_weights(mag_ctx* c, double w_max, double w_min, int fp_mode, double* out);
 /* Batch form of ma::getWorstQuality / hasWorseQuality (ma/maQuality.cc:184-226) for many candidate cavities at once
    (collapse / swap / snap operators: ma/maCollapse.cc:37-113, ma/maEdgeSwap.cc:598-740, ma/maSnapper.cc:407,573).
@@ -204,6 +206,16 @@ int mag_cavity_quality(mag_ctx* c, int64_t ncav, const int64_t* offsets, const i
    given).  short_edge [np+npy+nt] (may be NULL), -1 where nothing is to be removed.  Synchronous. */
 int mag_short_edge_test(mag_ctx* c, const int32_t* tet_edges, double max_edge_ratio, int32_t* short_edge,
                         int64_t* n_cleared, int64_t* n_short);
+/* ma::getSliverCode / ma::matchSliver (ma/maShape.cc:35-120), the classification LargeAngleTetFixer applies to the
+   BAD_QUALITY tets after markBadQuality: codes[element] = the bit code (bits 0-2 / 3-5: signs and near-zero area
+   coordinates of vertex 3 projected onto the first face; bit 6 + bits 7-8 / 9-11: the edge projection used when the first
+   face is itself worse than good_quality^2), match[element] = {rotation, code_index} of matchSliver's tables, {-1,-1} = no
+   match.  face0_v [nt][3] = the vertices of getDownward(tet, 2)[0] in THAT FACE's own order (measureTriQuality walks the
+   face entity; NULL = the tet's own (v0, v1, v2), which can differ from the reference in the last bit of the face quality).
+   only_bad != 0: only tets whose resident flag word carries BAD_QUALITY are classified.  codes [np+npy+nt], match
+   [np+npy+nt][2]; unclassified and layer elements get 0 and {-1,-1}.  Always evaluated in the reference's operation
+   order.  Synchronous. */
+int mag_sliver_codes(mag_ctx* c, const int32_t* face0_v, double good_quality, int only_bad, int32_t* codes, int32_t* match);
 /* Size-field transfer to the vertices that will split the SPLIT-marked edges (ma::makeSplitVert, ma/maRefine.cc:129-151;
    SizeField::interpolate, ma/maSize.cc:414-429,523-534): for every edge whose resident flag word carries MAG_SPLIT, in
    edge order, the edge index, the position of the new vertex (xi = 0) and the size-field values it receives --

@@ -418,9 +418,11 @@ static double gen_det2(const double A[3][3])
   cross3(A[0], A[1], c);
   return len3(c);
 }
-double mao_tri_quality(int kind, const double* xyz, const double* ma, const double* mb,
-                       const int32_t* tv, int use_max, int* status)
+static double tri_quality_dim(int kind, const double* xyz, const double* ma, const double* mb,
+                              const int32_t* tv, int use_max, int mesh_dim, int* status)
 {
+  /* mesh_dim = m->getDimension() (maQuality.cc:86,100): on a 3-D mesh the "largest Jacobian" vertex of a FACE is still
+     chosen by the 3x3 determinant of its transform */
   metric_t mt = {kind, ma, mb};
   double Q[3][3];
   if (use_max) {
@@ -430,7 +432,7 @@ double mao_tri_quality(int kind, const double* xyz, const double* ma, const doub
       double N[1] = {1.0};
       int rc = transform_at(&mt, tv + i, N, 1, cq);
       if (rc != 1 && status) *status = rc;
-      double cj = gen_det2((const double(*)[3])cq);
+      double cj = mesh_dim == 3 ? mao_det3((const double(*)[3])cq) : gen_det2((const double(*)[3])cq);
       if (cj > maxJ) { maxJ = cj; memcpy(Q, cq, sizeof(Q)); }
     }
     if (maxJ == -1.0) memset(Q, 0, sizeof(Q));
@@ -462,12 +464,116 @@ double mao_tri_quality(int kind, const double* xyz, const double* ma, const doub
   for (int i = 0; i < 3; ++i) s += l[i] * l[i];
   return 48 * (A * A) / (s * s);
 }
+double mao_tri_quality(int kind, const double* xyz, const double* ma, const double* mb,
+                       const int32_t* tv, int use_max, int* status)
+{
+  return tri_quality_dim(kind, xyz, ma, mb, tv, use_max, 2, status);
+}
 int mao_tri_qualities(int kind, const double* xyz, const double* ma, const double* mb,
                       int64_t nt, const int32_t* tri_v, int use_max, double* out)
 {
   int status = 1;
   for (int64_t t = 0; t < nt; ++t)
     out[t] = mao_tri_quality(kind, xyz, ma, mb, tri_v + 3 * t, use_max, &status);
+  return status;
+}
+
+/* ----------------------------------------------------- sliver classification
+ * getSliverCode / matchSliver, maShape.cc:35-120 (the sweep fixElementShapes' LargeAngleTetFixer runs over the
+ * BAD_QUALITY tets).  J and Q at the centroid; the quality of the tet's FIRST face decides which projection is used.
+ * face0_v = the vertices of getDownward(tet, 2)[0] in that face's OWN order (measureTriQuality walks the face entity).
+ * apf::project apfVector.h:134-137, apf::invert apfMatrix.h:165-173 (rows = cross products of the columns, divided by the
+ * cofactor determinant), matrix * vector = row dot products. */
+static void project3(const double* a, const double* b, double* r)
+{
+  double s = dot3(a, b) / dot3(b, b);
+  for (int i = 0; i < 3; ++i) r[i] = b[i] * s;
+}
+static void invert3(const double m[3][3], double r[3][3])
+{
+  double x[3][3];
+  transpose3(m, x);
+  cross3(x[1], x[2], r[0]);
+  cross3(x[2], x[0], r[1]);
+  cross3(x[0], x[1], r[2]);
+  double d = mao_det3(m);
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r[i][j] = r[i][j] / d;
+}
+int mao_sliver_code(int kind, const double* xyz, const double* ma, const double* mb, const int32_t* tv,
+                    const int32_t* face0_v, double good_quality, int* status)
+{
+  metric_t mt = {kind, ma, mb};
+  const double* x[4];
+  for (int i = 0; i < 4; ++i) x[i] = xyz + 3 * (size_t)tv[i];
+  static const double g[4][3] = {{-1, -1, -1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  double J0[3][3], Q[3][3], J[3][3];
+  for (int i = 0; i < 3; ++i) for (int c = 0; c < 3; ++c) J0[i][c] = x[0][c] * g[0][i];
+  for (int n = 1; n < 4; ++n)
+    for (int i = 0; i < 3; ++i) for (int c = 0; c < 3; ++c) J0[i][c] = J0[i][c] + x[n][c] * g[n][i];
+  double N[4] = {1 - .25 - .25 - .25, .25, .25, .25};
+  int rc = transform_at(&mt, tv, N, 4, Q);
+  if (rc != 1 && status) *status = rc;
+  matmul3((const double(*)[3])J0, (const double(*)[3])Q, J);
+  int code = 0;
+  double f0 = tri_quality_dim(kind, xyz, ma, mb, face0_v, 1, 3, status);
+  double JT[3][3], inv[3][3], projected[3], basis[3];
+  if (f0 * f0 * f0 > good_quality * good_quality) {
+    double v03[3] = {J[2][0], J[2][1], J[2][2]};
+    cross3(J[0], J[1], J[2]);
+    double pr[3];
+    project3(v03, J[2], pr);
+    for (int i = 0; i < 3; ++i) projected[i] = v03[i] - pr[i];
+    transpose3((const double(*)[3])J, JT);
+    invert3((const double(*)[3])JT, inv);
+    for (int i = 0; i < 3; ++i) basis[i] = dot3(inv[i], projected);
+    double area[3] = {1 - basis[0] - basis[1], basis[0], basis[1]};
+    for (int i = 0; i < 3; ++i) if (area[i] > 0) code |= (1 << i);
+    for (int i = 0; i < 3; ++i) if (area[i] > -0.10 && area[i] < 0.10) code |= ((1 << i) << 3);
+  } else {
+    code |= (1 << 6);
+    double v02[3] = {J[1][0], J[1][1], J[1][2]};
+    project3(v02, J[0], projected);
+    cross3(J[0], J[1], J[2]);
+    transpose3((const double(*)[3])J, JT);
+    invert3((const double(*)[3])JT, inv);
+    for (int i = 0; i < 3; ++i) basis[i] = dot3(inv[i], projected);
+    double area[3] = {1 - basis[0] - basis[1], basis[0], basis[1]};
+    for (int i = 0; i < 2; ++i) if (area[i] > 0) code |= ((1 << i) << 7);
+    for (int i = 0; i < 3; ++i) if (area[i] > -0.20 && area[i] < 0.20) code |= ((1 << i) << 9);
+  }
+  return code;
+}
+/* matchSliver's two tables (maShape.cc:93-119): {rotation, code_index}, {-1,-1} = no match */
+static const signed char sliver_table2d[4][4][2] =
+  {{{-1,-1}, {-1,-1}, {-1,-1}, {-1,-1}},
+   {{ 7, 2}, {-1,-1}, { 3, 3}, {-1,-1}},
+   {{ 1, 2}, { 2, 3}, {-1,-1}, {-1,-1}},
+   {{ 3, 2}, { 2, 3}, { 3, 3}, {-1,-1}}};
+static const signed char sliver_table[8][8][2] =
+  {{{-1,-1}, {-1,-1}, {-1,-1}, {-1,-1}, {-1,-1}, {-1,-1}, {-1,-1}, {-1,-1}},
+   {{ 4, 1}, {-1,-1}, {10, 2}, { 6, 3}, { 4, 2}, { 5, 3}, { 0, 3}, {-1,-1}},
+   {{ 1, 1}, { 8, 2}, {-1,-1}, { 6, 3}, { 9, 2}, { 5, 3}, { 0, 3}, {-1,-1}},
+   {{ 2, 0}, { 8, 2}, {10, 2}, {-1,-1}, { 0, 2}, { 5, 3}, { 0, 3}, {-1,-1}},
+   {{ 2, 1}, {11, 2}, { 2, 2}, { 6, 3}, {-1,-1}, { 5, 3}, { 0, 3}, {-1,-1}},
+   {{ 0, 0}, {11, 2}, { 6, 2}, { 6, 3}, { 4, 2}, {-1,-1}, { 0, 3}, {-1,-1}},
+   {{ 1, 0}, { 5, 2}, { 2, 2}, { 6, 3}, { 9, 2}, { 5, 3}, {-1,-1}, {-1,-1}},
+   {{ 0, 1}, { 5, 2}, { 6, 2}, { 6, 3}, { 0, 2}, { 5, 3}, { 0, 3}, {-1,-1}}};
+void mao_match_sliver(int code, int* rotation, int* code_index)
+{
+  const signed char* m = ((code >> 6) & 1) ? sliver_table2d[(code >> 7) & 3][(code >> 9) & 3]
+                                           : sliver_table[code & 7][(code >> 3) & 7];
+  *rotation = m[0];
+  *code_index = m[1];
+}
+int mao_sliver_codes(int kind, const double* xyz, const double* ma, const double* mb, int64_t nt, const int32_t* tet_v,
+                     const int32_t* face0_v, double good_quality, int32_t* codes, int32_t* match /*[nt][2]*/)
+{
+  int status = 1;
+  for (int64_t t = 0; t < nt; ++t) {
+    int c = mao_sliver_code(kind, xyz, ma, mb, tet_v + 4 * t, face0_v + 3 * t, good_quality, &status);
+    codes[t] = c;
+    if (match) { int r, k; mao_match_sliver(c, &r, &k); match[2 * t] = r; match[2 * t + 1] = k; }
+  }
   return status;
 }
 
@@ -580,6 +686,45 @@ double mao_tet_weight(int kind, const double* xyz, const double* ma, const doubl
     measurement += (0.25 / 6.0) * dV2;
   }
   return measurement / (1.0 / 6.0);
+}
+/* measure(triangle) on a 2-D mesh: TriangleIntegration::N2 (apfIntegrate.cc:146-159), 3 points, weights 1/3/2;
+ * dV2 = |row0(J Q) x row1(J Q)| (getJacobianDeterminant(., 2), apfVectorElement.cc:75-84); triangle shape values and
+ * gradients apfShape.cc:141-160; parentMeasure[TRIANGLE] = 1.0/2.0 (maSize.cc:150). */
+double mao_tri_weight(int kind, const double* xyz, const double* ma, const double* mb,
+                      const int32_t* tv, int* status)
+{
+  if (kind == MAO_IDENTITY) return 1.0;
+  metric_t mt = {kind, ma, mb};
+  static const double P[3][2] = {{0.666666666666667, 0.166666666666667}, {0.166666666666667, 0.666666666666667},
+                                 {0.166666666666667, 0.166666666666667}};
+  static const double g[3][3] = {{-1, -1, 0}, {1, 0, 0}, {0, 1, 0}};
+  const double* x[3];
+  for (int i = 0; i < 3; ++i) x[i] = xyz + 3 * (size_t)tv[i];
+  double measurement = 0;
+  for (int p = 0; p < 3; ++p) {
+    double N[3] = {1 - P[p][0] - P[p][1], P[p][0], P[p][1]};
+    double Q[3][3];
+    int rc = transform_at(&mt, tv, N, 3, Q);
+    if (rc != 1 && status) *status = rc;
+    double J[3][3];
+    for (int i = 0; i < 3; ++i) for (int c = 0; c < 3; ++c) J[i][c] = x[0][c] * g[0][i];
+    for (int n = 1; n < 3; ++n)
+      for (int i = 0; i < 3; ++i) for (int c = 0; c < 3; ++c) J[i][c] = J[i][c] + x[n][c] * g[n][i];
+    double JQ[3][3];
+    matmul3((const double(*)[3])J, (const double(*)[3])Q, JQ);
+    measurement += (1. / 3. / 2.0) * gen_det2((const double(*)[3])JQ);
+  }
+  return measurement / (1.0 / 2.0);
+}
+int mao_tri_weights(int kind, const double* xyz, const double* ma, const double* mb,
+                    int64_t nt, const int32_t* tri_v, double w_max, double w_min, double* out)
+{
+  int status = 1;
+  for (int64_t t = 0; t < nt; ++t) {
+    double w = mao_tri_weight(kind, xyz, ma, mb, tri_v + 3 * t, &status);
+    out[t] = (w > w_max) ? w_max : ((w < w_min) ? w_min : w);
+  }
+  return status;
 }
 /* clamp of maBalance.cc:14-19 */
 double mao_clamp(double x, double max, double min)

@@ -36,6 +36,14 @@ int mao_pyramid_ok(const double* xyz, const int32_t* pv, int* good_rotation);
 
 double mao_tet_weight(int kind, const double* xyz, const double* ma, const double* mb, const int32_t* tv, int* status);
 double mao_clamp(double x, double max, double min);
+int mao_sliver_code(int kind, const double* xyz, const double* ma, const double* mb, const int32_t* tv,
+                    const int32_t* face0_v, double good_quality, int* status);
+void mao_match_sliver(int code, int* rotation, int* code_index);
+int mao_sliver_codes(int kind, const double* xyz, const double* ma, const double* mb, int64_t nt, const int32_t* tet_v,
+                     const int32_t* face0_v, double good_quality, int32_t* codes, int32_t* match);
+double mao_tri_weight(int kind, const double* xyz, const double* ma, const double* mb, const int32_t* tv, int* status);
+int mao_tri_weights(int kind, const double* xyz, const double* ma, const double* mb,
+                    int64_t nt, const int32_t* tri_v, double w_max, double w_min, double* out);
 int mao_tet_weights(int kind, const double* xyz, const double* ma, const double* mb,
                     int64_t nt, const int32_t* tet_v, double w_max, double w_min, double* out);
 void mao_split_vertex(int kind, const double* xyz, const double* ma, const double* mb, const int32_t* ev,

@@ -27,7 +27,8 @@ def build():
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        src = [os.path.join(_HERE, f) for f in ("ma_oracle.c", "ma_oracle.h")]
+        if not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(f) for f in src):
             build()
         L = C.CDLL(LIB_PATH)
         vp, i64, i32, f64 = C.c_void_p, C.c_int64, C.c_int32, C.c_double
@@ -47,6 +48,8 @@ def lib():
         L.mao_mark_entities.restype = i64
         L.mao_mark_entities.argtypes = [i64, vp, C.c_int, f64, vp, vp, i32, i32, i32]
         L.mao_tet_weights.argtypes = [C.c_int, vp, vp, vp, i64, vp, f64, f64, vp]
+        L.mao_tri_weights.argtypes = [C.c_int, vp, vp, vp, i64, vp, f64, f64, vp]
+        L.mao_sliver_codes.argtypes = [C.c_int, vp, vp, vp, i64, vp, vp, f64, vp, vp]
         L.mao_split_vertices.argtypes = [C.c_int, vp, vp, vp, i64, vp, vp, vp, vp]
         L.mao_min_quality.restype = f64
         L.mao_min_quality.argtypes = [i64, vp]
@@ -118,6 +121,28 @@ def tet_weights(kind, xyz, ma, mb, tet_v, refines_left=None, coarsens_left=0, di
     out = np.zeros(nt)
     w_max, w_min = weight_clamps(refines_left, coarsens_left, dim)
     rc = lib().mao_tet_weights(kind, _p(xyz), _p(ma), _p(mb), nt, _p(tet_v), w_max, w_min, _p(out))
+    assert rc == 1
+    return out
+
+
+def sliver_codes(kind, xyz, ma, mb, tet_v, face0_v, good_quality=0.027):
+    """ma::getSliverCode / matchSliver (maShape.cc:35-120) of every tet; face0_v = vertices of each tet's first face in
+    the face's own order.  Returns (codes [nt], match [nt][2] = {rotation, code_index})."""
+    xyz, ma, mb, tet_v, face0_v = _f64(xyz), _f64(ma), _f64(mb), _i32(tet_v), _i32(face0_v)
+    nt = tet_v.size // 4
+    codes, match = np.zeros(nt, np.int32), np.zeros((nt, 2), np.int32)
+    rc = lib().mao_sliver_codes(kind, _p(xyz), _p(ma), _p(mb), nt, _p(tet_v), _p(face0_v), float(good_quality), _p(codes), _p(match))
+    assert rc == 1
+    return codes, match
+
+
+def tri_weights(kind, xyz, ma, mb, tri_v, refines_left=None, coarsens_left=0):
+    """ma::getElementWeight on a 2-D mesh (triangle measure / (1/2), clampForIterations with dimension 2)."""
+    xyz, ma, mb, tri_v = _f64(xyz), _f64(ma), _f64(mb), _i32(tri_v)
+    nt = tri_v.size // 3
+    out = np.zeros(nt)
+    w_max, w_min = weight_clamps(refines_left, coarsens_left, 2)
+    rc = lib().mao_tri_weights(kind, _p(xyz), _p(ma), _p(mb), nt, _p(tri_v), w_max, w_min, _p(out))
     assert rc == 1
     return out
 

@@ -43,6 +43,9 @@ void unMarkBadQuality(Adapt* a);
 double getMinQuality(Adapt* a);
 /* maBalance.cc:74-81, external linkage, no header */
 double getElementWeight(Adapt* a, Entity* e);
+/* maShape.cc:35-120, external linkage; maShape.h:66 declares matchSliver with a Mesh* first argument that no definition has */
+int getSliverCode(Adapt* a, Entity* tet);
+CodeMatch matchSliver(Adapt* a, Entity* tet);
 }
 
 namespace {
@@ -450,6 +453,38 @@ int refo_weights(void* hd, int refinesLeft, int coarsensLeft, double* raw, doubl
     bool simplex = apf::isSimplex(m->getType(e));
     if (raw) raw[k] = simplex ? r->sf->getWeight(e) : 0;
     if (clamped) clamped[k] = simplex ? ma::getElementWeight(r->a, e) : 0;
+    ++k;
+  }
+  m->end(it);
+  return 0;
+}
+
+/* ---- ma::getSliverCode / ma::matchSliver (maShape.cc:35-120) of every tet, with goodQuality as given (< 0: default), and the
+   vertices of each tet's first face (getDownward(tet, 2)[0]) in the FACE's own order, which is what measureTriQuality
+   walks.  Non-tet elements get code 0 / match -1,-1 / face -1. */
+int refo_sliver_codes(void* hd, double goodQuality, int32_t* codes, int32_t* match, int32_t* face0_v)
+{
+  Ref* r = (Ref*)hd; apf::Mesh2* m = r->m;
+  if (!r->sf) return 1;
+  if (r->a) { delete r->a; r->a = 0; }
+  if (r->in) { delete r->in; r->in = 0; }
+  r->in = ma::makeAdvanced(ma::configureIdentity(m, r->sf));
+  if (goodQuality >= 0) r->in->goodQuality = goodQuality;
+  r->a = new ma::Adapt(r->in);
+  apf::MeshIterator* it = m->begin(m->getDimension()); apf::MeshEntity* e; int64_t k = 0;
+  while ((e = m->iterate(it))) {
+    if (m->getType(e) == apf::Mesh::TET) {
+      codes[k] = ma::getSliverCode(r->a, e);
+      ma::CodeMatch cm = ma::matchSliver(r->a, e);
+      match[2 * k] = cm.rotation; match[2 * k + 1] = cm.code_index;
+      apf::Downward fs, fv;
+      m->getDownward(e, 2, fs);
+      m->getDownward(fs[0], 0, fv);
+      for (int i = 0; i < 3; ++i) face0_v[3 * k + i] = (int32_t)apf::getMdsIndex(m, fv[i]);
+    } else {
+      codes[k] = 0; match[2 * k] = match[2 * k + 1] = -1;
+      for (int i = 0; i < 3; ++i) face0_v[3 * k + i] = -1;
+    }
     ++k;
   }
   m->end(it);

@@ -58,6 +58,7 @@ def lib():
         L.refo_write_smb.argtypes = [C.c_void_p, C.c_char_p]
         L.refo_store_fields.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.refo_weights.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.refo_sliver_codes.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
         L.refo_split_vertices.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
@@ -192,6 +193,14 @@ class RefMesh:
         else:
             assert lib().refo_weights(self.h, int(refines_left), int(coarsens_left), None, _p(out)) == 0
         return out
+
+    def sliver_codes(self, good_quality=-1.0):
+        """ma::getSliverCode / matchSliver of every tet, and the first face's vertices in the face's own order."""
+        codes = np.zeros(self.nelem, np.int32)
+        match = np.zeros((self.nelem, 2), np.int32)
+        f0 = np.zeros((self.nelem, 3), np.int32)
+        assert lib().refo_sliver_codes(self.h, float(good_quality), _p(codes), _p(match), _p(f0)) == 0
+        return codes, match, f0
 
     def split_vertices(self, edges):
         """Position and size-field values ma::makeSplitVert gives the vertex splitting each listed edge."""

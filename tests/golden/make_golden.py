@@ -7,7 +7,7 @@ Every array below except the inputs (coordinates jitter, size fields) is an OUTP
 apf::makeMdsBox / apf::buildElement entity order, ma::SizeField::measure, ma::measureElementQuality,
 ma::markEdgesToSplit / markEdgesToCollapse / markBadQuality / getMinQuality / getMaximumEdgeLength,
 ma::isPrismOk / isPyramidOk, the ma_logM field, apf::eigen, ma::getElementWeight, ma::makeSplitVert's
-size-field transfer.  The fixtures are small (a few 100 kB) and
+size-field transfer, ma::getSliverCode / matchSliver.  The fixtures are small (a few 100 kB) and
 committed, because /root/reference does not exist on the GPU box.
 """
 import os
@@ -53,7 +53,7 @@ def case(name, m, kind, h=None, R=None, good_quality=-1.0, edge_flags=None, elem
     out["counts"] = np.array([r["n_split"], r["n_collapse"], r["n_bad"]], dtype=np.int64)
     out["min_q"] = np.float64(r["min_q"])
     out["max_len"] = np.float64(m.max_edge_length())
-    if simplex_only and np.all(et == refo.TET):
+    if simplex_only and (np.all(et == refo.TET) or np.all(et == refo.TRIANGLE)):   # 2-D: measure(triangle) / (1/2)
         # ma::getElementWeight (raw SizeField::getWeight, and clamped with refinesLeft = 0,
         # coarsensLeft = 1 -> [0.25, 1]) and what ma::makeSplitVert gives the vertex splitting every SPLIT-marked edge
         out["weights_raw"] = m.weights()
@@ -64,6 +64,9 @@ def case(name, m, kind, h=None, R=None, good_quality=-1.0, edge_flags=None, elem
             out["split_edges"], out["split_xyz"], out["split_b"] = se.astype(np.int32), sx, sb
             if kind == refo.KIND_ANISO_FIELD:
                 out["split_a"] = sa
+    if simplex_only and np.all(et == refo.TET):
+        # ma::getSliverCode / matchSliver of every tet (maShape.cc:35-120) + the first face's own vertex order
+        out["sliver_codes"], out["sliver_match"], out["face0_v"] = m.sliver_codes(good_quality)
     if not simplex_only:
         ok, codes = m.layer_ok()
         out["layer_ok"], out["layer_codes"] = ok, codes

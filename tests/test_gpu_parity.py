@@ -109,14 +109,17 @@ def test_weights_and_split_vertices_golden(cb, name):
     from oracle import mao
     g = util.load(name)
     kind, ma, mb = util.metric_arrays(g)
-    _, _, tet_v = util.split_elements(g)
     p = cb.Part(0)
-    p.set_mesh(g["xyz"], g["edge_v"], tet_v)
+    two_d = util.is_2d(g)
+    if two_d:   # triangles are the elements: measure(triangle) / (1/2), clampForIterations with dimension 2
+        p.set_mesh_2d(g["xyz"], g["edge_v"], np.ascontiguousarray(g["elem_v"][:, :3]))
+    else:
+        p.set_mesh(g["xyz"], g["edge_v"], util.split_elements(g)[2])
     util.set_part_metric(p, kind, ma, mb)
     exact = kind != mao.LOGM          # LogAniso: CUDA exp() vs glibc exp() (see MAG_FP_STRICT in mag.h)
     for mode in (cb.FP_STRICT, cb.FP_FAST):
         w = p.element_weights(fp_mode=mode)
-        wc = p.element_weights(0, 1, fp_mode=mode)
+        wc = p.element_weights(0, 1, fp_mode=mode, dim=2 if two_d else 3)
         if exact and mode == cb.FP_STRICT:
             assert np.array_equal(w, g["weights_raw"]) and np.array_equal(wc, g["weights_r0_c1"])
         else:
@@ -142,6 +145,40 @@ def test_weights_and_split_vertices_golden(cb, name):
             else:
                 assert util.rel_err(sx[keep], g["split_xyz"][sel]) < TOL
                 assert np.max(np.abs(sb[keep] - g["split_b"][sel])) < TOL * max(1.0, np.max(np.abs(g["split_b"])))
+    p.close()
+
+
+@pytest.mark.parametrize("name", [n for n in util.golden_cases() if "sliver_codes" in util.load(n)])
+def test_sliver_codes_golden(cb, name):
+    """SURVEY 8f row 1, second classification sweep: ma::getSliverCode / matchSliver on the device against the compiled
+    reference's own codes (every tet; then only the BAD_QUALITY ones after a marking sweep)."""
+    from oracle import mao
+    g = util.load(name)
+    kind, ma, mb = util.metric_arrays(g)
+    tet_v = util.split_elements(g)[2]
+    gq = float(g["good_quality"])
+    gq = 0.027 if gq < 0 else gq
+    p = cb.Part(0)
+    p.set_mesh(g["xyz"], g["edge_v"], tet_v)
+    util.set_part_metric(p, kind, ma, mb)
+    codes, match = p.sliver_codes(g["face0_v"], gq)
+    if kind != mao.LOGM:
+        assert np.array_equal(codes, g["sliver_codes"]) and np.array_equal(match, g["sliver_match"])
+    else:   # CUDA exp() vs glibc exp(): a tet whose area coordinate sits within rounding of a cut may flip a bit
+        assert (codes == g["sliver_codes"]).mean() > 0.995
+        same = codes == g["sliver_codes"]
+        assert np.array_equal(match[same], g["sliver_match"][same])
+    # the tet's own (v0, v1, v2) instead of the face's order: same face, same code unless the face quality ties the cut
+    c2, _ = p.sliver_codes(None, gq)
+    assert (c2 == codes).mean() > 0.995
+    # only the BAD_QUALITY tets of the resident flags
+    p.set_flags(g["edge_flags_in"], g["elem_flags_in"])
+    p.sweep(cb.OP_MARK_BAD, good_quality=gq, fp_mode=cb.FP_STRICT)
+    _, lf = p.flags()
+    bad = (lf & cb.BAD_QUALITY) != 0
+    c3, m3 = p.sliver_codes(g["face0_v"], gq, only_bad=True)
+    assert np.array_equal(c3[bad], codes[bad]) and np.array_equal(m3[bad], match[bad])
+    assert np.all(c3[~bad] == 0) and np.all(m3[~bad] == -1)
     p.close()
 
 

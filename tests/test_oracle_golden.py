@@ -56,6 +56,10 @@ def test_oracle_matches_reference_golden(name, built):
         assert np.array_equal(sx, g["split_xyz"]) and np.array_equal(sb, g["split_b"])
         if kind == mao.ANISO:
             assert np.array_equal(sa, g["split_a"])
+    if "sliver_codes" in g:   # ma::getSliverCode / matchSliver, both projections exercised across the fixtures
+        codes, match = mao.sliver_codes(kind, g["xyz"], ma, mb, tet_v, g["face0_v"], gq)
+        assert np.array_equal(codes, g["sliver_codes"]) and np.array_equal(match, g["sliver_match"])
+        assert np.all(codes != 0)                                   # the reference asserts a non-zero code
     if nns:
         ok, codes = mao.prism_ok(g["xyz"], prism_v)
         assert np.array_equal(ok, g["layer_ok"][:len(prism_v)])
@@ -76,6 +80,16 @@ def check_2d(g, kind, ma, mb):
     assert counts == g["counts"].tolist()
     assert np.array_equal(ef, g["edge_flags_out"]) and np.array_equal(lf, g["elem_flags_out"])
     assert mao.min_quality(q) == float(g["min_q"]) and mao.max_length(L) == float(g["max_len"])
+    # ma::getElementWeight of a triangle (3-point rule, parent measure 1/2) and the split-vertex transfer
+    assert np.array_equal(mao.tri_weights(kind, g["xyz"], ma, mb, tri_v), g["weights_raw"])
+    assert np.array_equal(mao.tri_weights(kind, g["xyz"], ma, mb, tri_v, 0, 1), g["weights_r0_c1"])
+    if "split_edges" in g:
+        se = g["split_edges"]
+        assert np.array_equal(se, np.nonzero(g["edge_flags_out"] & mao.SPLIT)[0])
+        sx, sa, sb = mao.split_vertices(kind, g["xyz"], ma, mb, g["edge_v"][se])
+        assert np.array_equal(sx, g["split_xyz"]) and np.array_equal(sb, g["split_b"])
+        if kind == mao.ANISO:
+            assert np.array_equal(sa, g["split_a"])
 
 
 def test_layer_closure_flags_golden():
