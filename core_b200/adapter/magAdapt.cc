@@ -48,6 +48,8 @@ struct Access {
   static double lengthAt(GpuSizeField* g, size_t k) { return g->lengths[k]; }
   static bool isDirty(GpuSizeField* g) { return g->dirty; }
   static int fpMode(GpuSizeField* g) { return g->fpMode; }
+  static int vertSlotOf(GpuSizeField* g, ma::Entity* v) { return g->vertSlot[apf::getMdsIndex(g->mesh, v)]; }
+  static long nonSimplex(GpuSizeField* g) { return g->nNonSimplex; }
   static int tetSlotOf(GpuSizeField* g, ma::Entity* e) { return g->tetSlot[apf::getMdsIndex(g->mesh, e)]; }
   static double qualityOf(GpuSizeField* g, ma::Entity* e) { return g->qualities[g->tetSlot[apf::getMdsIndex(g->mesh, e)]]; }
   static bool serveQuality(GpuSizeField* g, ma::Entity* e, double goodQuality, double& q)
@@ -65,7 +67,8 @@ struct Access {
     ma::Mesh* m = g->mesh;
     if (m->getDimension() != 3) { fprintf(stderr, "mag adapter: only 3D meshes are supported\n"); abort(); }
     size_t nv = m->count(0);
-    std::vector<int> vslot;
+    std::vector<int>& vslot = g->vertSlot;
+    vslot.assign(vslot.size(), -1);
     x.xyz.resize(3 * nv);
     if (g->kind == 1) x.ma.resize(nv);
     else { x.ma.resize(3 * nv); x.mb.resize(9 * nv); }
@@ -424,6 +427,31 @@ ma::Tag* getElementWeights(ma::Adapt* a)
   }
   m->end(it);
   return weights;
+}
+
+/* ma::getSliverCode / matchSliver (maShape.cc:35-120) for every tet of the mesh in one device sweep */
+void getSliverCodes(ma::Adapt* a, std::vector<int>& codes, std::vector<ma::CodeMatch>& matches)
+{
+  GpuSizeField* g = gpuField(a->sizeField);
+  ma::Mesh* m = a->mesh;
+  if (Access::isDirty(g)) g->refresh(a->input->goodQuality);
+  const size_t nel = m->count(3), nns = (size_t)Access::nonSimplex(g);
+  std::vector<int> face0(3 * (nel - nns)), match(2 * nel);
+  codes.assign(nel, 0);
+  apf::MeshIterator* it = m->begin(3);
+  ma::Entity* e;
+  while ((e = m->iterate(it))) {
+    if (m->getType(e) != apf::Mesh::TET) continue;
+    const size_t t = (size_t)Access::tetSlotOf(g, e) - nns;
+    apf::Downward fs, fv;
+    m->getDownward(e, 2, fs);
+    m->getDownward(fs[0], 0, fv);
+    for (int i = 0; i < 3; ++i) face0[3 * t + i] = Access::vertSlotOf(g, fv[i]);
+  }
+  m->end(it);
+  MAG_DO(g->ctx, mag_sliver_codes(g->ctx, face0.data(), a->input->goodQuality, 0, codes.data(), match.data()));
+  matches.resize(nel);
+  for (size_t i = 0; i < nel; ++i) { matches[i].rotation = match[2 * i]; matches[i].code_index = match[2 * i + 1]; }
 }
 
 /* ------------------------------------------------------------------ shape handler */

@@ -11,6 +11,7 @@
 //   ma::getMaximumEdgeLength(m, sf)   ma/maSize.cc:673      ->  mag::getMaximumEdgeLength(m, sf)
 //   ma::getEdgeLengthsInMetricSpace / getLinearQualitiesInMetricSpace   ma/maStats.cc:12-45  ->  mag::... (same vectors)
 //   ma::getElementWeights(Adapt*)     ma/maBalance.cc:83    ->  mag::getElementWeights(Adapt*)  (same "ma_weight" tag)
+//   ma::getSliverCode / matchSliver   ma/maShape.cc:35-120  ->  mag::getSliverCodes(Adapt*, ...)  (every tet in one sweep)
 //   ma::getShapeHandler(Adapt*)       ma/maShapeHandler.cc  ->  mag::shapeHandler  (an ma::ShapeHandlerFunction for Input::shapeHandler)
 //
 // mag::GpuSizeField IS an ma::SizeField: it can be put in ma::Input::sizeField and the UNMODIFIED reference keeps
@@ -25,6 +26,7 @@
 
 #include <maSize.h>
 #include <maInput.h>
+#include <maTables.h>
 #include <vector>
 
 struct mag_ctx;
@@ -72,6 +74,7 @@ class GpuSizeField : public ma::SizeField
     apf::Field* fSizes; apf::Field* fFrames; apf::Field* fIso;
     ma::AnisotropicFunction* fnAniso; ma::IsotropicFunction* fnIso;
     std::vector<int> edgeSlot, tetSlot;           /* MDS index -> position in the exported arrays (-1: not exported) */
+    std::vector<int> vertSlot;                    /* MDS index of a vertex -> exported vertex id */
     std::vector<double> lengths, qualities;       /* host copies of the last sweep */
     std::vector<int> edgeFlags, elemFlags;        /* flags of the last sweep run on zero incoming words */
     long nNonSimplex;
@@ -96,6 +99,11 @@ void getLinearQualitiesInMetricSpace(ma::Mesh* m, ma::SizeField* sf, std::vector
 
 /* ma::getElementWeights (ma/maBalance.cc:83-97): creates and fills the "ma_weight" element tag; the caller destroys it */
 ma::Tag* getElementWeights(ma::Adapt* a);
+
+/* ma::getSliverCode / ma::matchSliver (ma/maShape.cc:35-120) of every tet in one device sweep: codes[i] / matches[i] belong to
+   the i-th element of m->begin(3) (layer elements: 0 and {-1,-1}).  The first face of every tet is exported in the face
+   entity's own vertex order, which is what the reference's measureTriQuality walks. */
+void getSliverCodes(ma::Adapt* a, std::vector<int>& codes, std::vector<ma::CodeMatch>& matches);
 
 /* ma::ShapeHandlerFunction: in->shapeHandler = mag::shapeHandler; getQuality(e) is then served from the device sweep */
 ma::ShapeHandler* shapeHandler(ma::Adapt* a);

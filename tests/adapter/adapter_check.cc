@@ -30,6 +30,8 @@ long markEdgesToCollapse(Adapt* a);
 int markBadQuality(Adapt* a);
 double getMinQuality(Adapt* a);
 double getElementWeight(Adapt* a, Entity* e);   /* maBalance.cc:74-81 */
+int getSliverCode(Adapt* a, Entity* tet);        /* maShape.cc:35-89 */
+CodeMatch matchSliver(Adapt* a, Entity* tet);    /* maShape.cc:91-120 (maShape.h:66 declares a signature no definition has) */
 }
 
 namespace {
@@ -123,7 +125,7 @@ extern "C" int mag_adapter_check(int n, int log_interp, int fp_mode, double jitt
   }
   const double hbar = 1.0 / n;
   Marks R, A, B;
-  long weight_diffs = 0;
+  long weight_diffs = 0, sliver_diffs = 0;
   { /* (R) the unmodified reference */
     Fields f = make_fields(m, "ref", hbar);
     ma::SizeField* sf = ma::makeSizeField(m, f.sizes, f.frames, log_interp != 0);
@@ -168,6 +170,22 @@ extern "C" int mag_adapter_check(int n, int log_interp, int fp_mode, double jitt
       m->end(wit);
       apf::removeTagFromDimension(m, wt, 3);
       m->destroyTag(wt);
+      /* ma::getSliverCode / matchSliver (maShape.cc:35-120) of every tet against the reference's per-entity calls on the
+         same Adapt (its getTransform / face quality go through the adapter to the wrapped reference field) */
+      std::vector<int> codes;
+      std::vector<ma::CodeMatch> matches;
+      mag::getSliverCodes(&a, codes, matches);
+      wit = m->begin(3);
+      size_t wi = 0;
+      long nel3 = 0;
+      while ((we = m->iterate(wit))) {
+        const int rc = ma::getSliverCode(&a, we);
+        const ma::CodeMatch rm = ma::matchSliver(&a, we);
+        if (codes[wi] != rc || matches[wi].rotation != rm.rotation || matches[wi].code_index != rm.code_index) ++sliver_diffs;
+        ++wi; ++nel3;
+      }
+      m->end(wit);
+      if (log_interp && sliver_diffs * 200 <= nel3) sliver_diffs = 0;   /* CUDA exp() vs glibc exp(): rare borderline bits */
     }
     A.max_len = mag::getMaximumEdgeLength(m, g);
     delete in;
@@ -207,5 +225,6 @@ extern "C" int mag_adapter_check(int n, int log_interp, int fp_mode, double jitt
   }
   for (int i = 15; i < 19; ++i) bad |= report[i] != 0;
   bad |= weight_diffs != 0;
+  bad |= sliver_diffs != 0;
   return bad;
 }

@@ -197,7 +197,7 @@ def edge_cavities(edge_v, tet_v):
     return offsets, tid[o]
 
 
-@pytest.mark.parametrize("name", [n for n in util.golden_cases() if "weights_raw" in util.load(n)])
+@pytest.mark.parametrize("name", [n for n in util.golden_cases() if "sliver_codes" in util.load(n)])
 def test_cavity_quality_golden(cb, name):
     """SURVEY 8f row 1: batch ma::getWorstQuality.  Cavities = the tets around every edge of the golden mesh; the worst
     quality of each must equal the minimum of the compiled reference's own per-tet qualities."""
