@@ -15,7 +15,7 @@ SYMBOLS = [
     "mag_set_mesh", "mag_set_mesh_2d", "mag_set_coords",
     "mag_set_metric_identity", "mag_set_metric_iso", "mag_set_metric_aniso", "mag_set_metric_logm",
     "mag_set_flags", "mag_sweep", "mag_sweep_host", "mag_element_weights", "mag_split_vertices", "mag_cavity_quality", "mag_short_edge_test",
-    "mag_sliver_codes",
+    "mag_sliver_codes", "mag_linear_qualities",
     "mag_get_edge_lengths", "mag_get_qualities", "mag_get_flags", "mag_get_layer_ok", "mag_get_stats",
     "mag_get_near_threshold", "mag_set_metric_logm_from_frames",
     "mag_timing_begin", "mag_timing_read", "mag_launch_count",
@@ -83,6 +83,7 @@ def lib():
     L.mag_cavity_quality.argtypes = [vp, i64, vp, vp, C.c_int, C.c_int, vp, vp]
     L.mag_short_edge_test.argtypes = [vp, vp, f64, vp, C.POINTER(i64), C.POINTER(i64)]
     L.mag_sliver_codes.argtypes = [vp, vp, f64, C.c_int, vp, vp]
+    L.mag_linear_qualities.argtypes = [C.c_int, i64, vp, vp, vp, C.POINTER(i64)]
     L.mag_split_vertices.argtypes = [vp, C.c_int, i64, C.POINTER(i64), vp, vp, vp, vp]
     L.mag_get_edge_lengths.argtypes = [vp, vp]
     L.mag_get_qualities.argtypes = [vp, vp]

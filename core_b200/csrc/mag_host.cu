@@ -12,6 +12,7 @@
 // (the slices only change the order in which entities are visited); the part stays resident afterwards.
 #include "mag_internal.h"
 #include <algorithm>
+#include <cmath>
 
 int magk_pack(mag_ctx* c);
 int magk_init_stats(mag_ctx* c);
@@ -150,4 +151,19 @@ extern "C" int mag_sweep_host(mag_ctx* c, const mag_host_part* in, const mag_hos
   rc = mag_get_stats(c, stats ? stats : &local);      // synchronizes the compute stream
   MAG_CUDA(c, cudaStreamSynchronize(s_down));
   return rc;
+}
+
+// ma::getLinearQualitiesInMetricSpace's selection and post-processing (ma/maStats.cc:12-31) on the host, with the host's
+// libm exactly as the reference: owned simplex elements in iteration order, cbrt of the quality (2-D: signed sqrt).
+extern "C" int mag_linear_qualities(int dim, int64_t n, const double* qualities, const uint8_t* keep, double* out, int64_t* n_out)
+{
+  if ((dim != 2 && dim != 3) || n < 0 || (n && (!qualities || !out)) || !n_out) return MAG_ERR_ARG;
+  int64_t k = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    if (keep && !keep[i]) continue;
+    const double lq = qualities[i];
+    out[k++] = dim == 2 ? ((lq > 0) ? std::sqrt(lq) : -std::sqrt(-lq)) : cbrt(lq);
+  }
+  *n_out = k;
+  return MAG_OK;
 }

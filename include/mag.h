@@ -225,6 +225,12 @@ int mag_sliver_codes(mag_ctx* c, const int32_t* face0_v, double good_quality, in
 int mag_split_vertices(mag_ctx* c, int fp_mode, int64_t cap, int64_t* n, int32_t* edge_idx, double* xyz,
                        double* field_a, double* field_b);
 
+/* Host-side post-processing of ma::getLinearQualitiesInMetricSpace (ma/maStats.cc:12-31), the vector ma::stats returns and
+   measureAnisoStats tabulates (test/measureAnisoStats.cc:217-243): for every element with keep[i] != 0 (owned and simplex;
+   NULL = all), in order, cbrt(quality) on a 3-D mesh, the signed square root on a 2-D one, through the host's libm as the
+   reference does.  out holds up to n values; *n_out = how many were written.  No context, no device work. */
+int mag_linear_qualities(int dim, int64_t n, const double* qualities, const uint8_t* keep, double* out, int64_t* n_out);
+
 /* the logM vertex field from sizes + frames, computed on the host exactly as the reference does (libm log):
    variant 0 = LogAnisoSizeField::init from fields, log(1/h/h)   (ma/maSize.cc:491-499)
    variant 1 = LogMEval from a user function, -2*log(h)          (ma/maSize.cc:343-346)

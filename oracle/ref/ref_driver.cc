@@ -459,6 +459,20 @@ int refo_weights(void* hd, int refinesLeft, int coarsensLeft, double* raw, doubl
   return 0;
 }
 
+/* ---- ma::stats(m, sf, edgeLengths, linearQualities, true) (maStats.cc:115-134): the two vectors measureAnisoStats writes
+   to its tables.  The caller sizes the outputs for every edge / element; the counts come back in n[2]. */
+int refo_stats(void* hd, double* el, double* lq, int64_t* n)
+{
+  Ref* r = (Ref*)hd;
+  if (!r->sf) return 1;
+  std::vector<double> e, q;
+  ma::stats(r->m, r->sf, e, q, true);
+  n[0] = (int64_t)e.size(); n[1] = (int64_t)q.size();
+  for (size_t i = 0; i < e.size(); ++i) el[i] = e[i];
+  for (size_t i = 0; i < q.size(); ++i) lq[i] = q[i];
+  return 0;
+}
+
 /* ---- ma::getSliverCode / ma::matchSliver (maShape.cc:35-120) of every tet, with goodQuality as given (< 0: default), and the
    vertices of each tet's first face (getDownward(tet, 2)[0]) in the FACE's own order, which is what measureTriQuality
    walks.  Non-tet elements get code 0 / match -1,-1 / face -1. */

@@ -58,6 +58,7 @@ def lib():
         L.refo_write_smb.argtypes = [C.c_void_p, C.c_char_p]
         L.refo_store_fields.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.refo_weights.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.refo_stats.argtypes = [C.c_void_p] * 4
         L.refo_sliver_codes.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
         L.refo_split_vertices.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
@@ -193,6 +194,13 @@ class RefMesh:
         else:
             assert lib().refo_weights(self.h, int(refines_left), int(coarsens_left), None, _p(out)) == 0
         return out
+
+    def stats(self):
+        """ma::stats in metric space: (edge lengths of owned edges, cbrt / signed sqrt of owned simplex qualities)."""
+        el, lq = np.zeros(self.ne), np.zeros(self.nelem)
+        n = np.zeros(2, np.int64)
+        assert lib().refo_stats(self.h, _p(el), _p(lq), _p(n)) == 0
+        return el[:n[0]].copy(), lq[:n[1]].copy()
 
     def sliver_codes(self, good_quality=-1.0):
         """ma::getSliverCode / matchSliver of every tet, and the first face's vertices in the face's own order."""

@@ -44,6 +44,7 @@ def case(name, m, kind, h=None, R=None, good_quality=-1.0, edge_flags=None, elem
         out["qualities"] = m.qualities(use_max)
         out["qualities_centroid"] = m.qualities(False)
         out["vertex_Q"] = m.vertex_transforms()
+    out["stats_el"], out["stats_lq"] = m.stats()   # ma::stats (maStats.cc:115-134): the tables of measureAnisoStats
     which = 15 if simplex_only else 3 + 4  # markBadQuality works on mixed meshes because layer elements carry OK_QUALITY
     r = m.mark(which=which, good_quality=good_quality, edge_flags=edge_flags, elem_flags=elem_flags)
     out["edge_flags_in"] = np.zeros(m.ne, np.int32) if edge_flags is None else np.asarray(edge_flags, np.int32)

@@ -157,3 +157,28 @@ def test_survey_smoke_values(built):
     assert (r["n_split"], r["n_collapse"], r["n_bad"]) == (26732, 0, 9600)
     assert r["min_quality"] == 0.00064551397077518649
     assert r["max_length"] == 7.0712523453038738
+
+
+@pytest.mark.parametrize("name", util.golden_cases())
+def test_stats_tables_match_ma_stats(name, built, tmp_path):
+    """SURVEY 8f row 4: the vectors of ma::stats (maStats.cc:12-45,115-134) rebuilt from per-entity lengths and qualities by
+    core_b200.stats, bit for bit, and the table files in measureAnisoStats' format (one `ostream << double` per line)."""
+    from core_b200 import stats
+    g = util.load(name)
+    kind, ma, mb = util.metric_arrays(g)
+    two_d = util.is_2d(g)
+    simplex = (g["elem_type"] == util.TRIANGLE) | (g["elem_type"] == util.TET)
+    if "qualities" in g:
+        q = g["qualities"]
+    else:
+        q = np.zeros(len(simplex))
+        q[simplex] = mao.tet_qualities(kind, g["xyz"], ma, mb, util.split_elements(g)[2])
+    el = stats.edge_lengths(g["lengths"])
+    lq = stats.linear_qualities(q, simplex=simplex, dim=2 if two_d else 3)
+    assert np.array_equal(el, g["stats_el"]) and np.array_equal(lq, g["stats_lq"])
+    pe, pq = stats.write_linear_tables(str(tmp_path), 0, g["lengths"], q, simplex=simplex, dim=2 if two_d else 3)
+    assert pe.endswith("linear_tables/linearETable_0.dat") and pq.endswith("linear_tables/linearQTable_0.dat")
+    rows = open(pe).read().split("\n")
+    assert len(rows) == len(el) + 1 and rows[-1] == ""
+    assert rows[0] == "%g" % el[0] and np.allclose(np.array(rows[:-1], float), el, rtol=1e-5)
+    assert np.allclose(np.loadtxt(pq), lq, rtol=1e-5, atol=1e-300)
