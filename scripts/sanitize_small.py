@@ -1,5 +1,5 @@
 """Small end-to-end exercise of every kernel family for compute-sanitizer (memcheck): all kinds, both fp modes, ownership,
-incoming flags, mixed mesh with layer check, 2-D part, streamed host call, weights, split vertices, cavity batches."""
+incoming flags, mixed mesh with layer check, 2-D part, streamed host call, weights (3-D and 2-D), split vertices, cavity batches, sliver codes."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -27,6 +27,7 @@ for kind in ("identity", "iso", "aniso", "logm"):
         p.split_vertices(fp_mode=mode); p.near_threshold(0); p.near_threshold(1)
         off = np.arange(0, len(tv) + 1, 3, dtype=np.int64); off[-1] = len(tv)
         p.cavity_quality(off, tv, fp_mode=mode)
+    p.sliver_codes(None, 0.3); p.sliver_codes(np.ascontiguousarray(tv[:, [1, 2, 0]]), 0.027, only_bad=True)
 key = lambda a, b: np.minimum(a, b).astype(np.int64) * (1 << 32) + np.maximum(a, b)
 ek = key(ev[:, 0], ev[:, 1]); order = np.argsort(ek)
 te = np.stack([order[np.searchsorted(ek[order], key(tv[:, a], tv[:, b]))] for a, b in ((0, 1), (1, 2), (2, 0), (0, 3), (1, 3), (2, 3))], axis=1).astype(np.int32)
@@ -45,5 +46,8 @@ h3, R3 = cb.fields.shock_rotating(x3, 1.0 / 8)
 p.set_mesh_2d(x3, e3, tr3); p.set_size_field_aniso(h3, R3)
 for mode in (cb.FP_STRICT, cb.FP_FAST):
     p.clear_flags(); p.sweep(cb.OP_ALL & ~cb.OP_LAYER_CHECK, good_quality=0.2, fp_mode=mode); p.stats()
+    p.element_weights(fp_mode=mode); p.element_weights(0, 1, fp_mode=mode, dim=2); p.split_vertices(fp_mode=mode)
+for setter in (p.set_size_field_identity, lambda: p.set_size_field_iso(h3[:, 1].copy()), lambda: p.set_size_field_logm_from_frames(h3, R3, 0)):
+    setter(); p.element_weights(fp_mode=cb.FP_STRICT); p.element_weights(fp_mode=cb.FP_FAST)
 p.close()
 print("sanitize_small: done")
