@@ -388,6 +388,16 @@ k_sliver_codes(int32_t nt, int32_t elem_off, const int4* __restrict__ tet_v, con
   if (eig) atomicAdd(&st->n_eigen_fail, 1ull);
 }
 
+// ma::clearFlagFromDimension (ma/maAdapt.cc:139-147) / ma::unMarkBadQuality (ma/maShape.cc:138-150) on the resident words
+__global__ void __launch_bounds__(256)
+k_clear_bits(int64_t n, int32_t mask, int32_t* __restrict__ flags)
+{
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const int32_t f = flags[i];
+    if (f & mask) flags[i] = f & ~mask;
+  }
+}
+
 // ------------------------------------------------------------------ short-edge classification
 // ShortEdgeFixer::shouldApply (ma/maShape.cc:188-219), the sweep fixElementShapes runs right after markBadQuality: for
 // every element carrying BAD_QUALITY, the measured lengths of its six edges in getDownward(tet, 1) order; if
@@ -733,6 +743,23 @@ int mag_sliver_codes(mag_ctx* c, const int32_t* face0_v, double good_quality, in
   MAG_CUDA(c, cudaStreamSynchronize(c->stream));
   if (c->h_stats->n_eigen_fail)
     return mag_fail(c, MAG_ERR_EIGEN, "eigenQR failed in %llu blocks of the sliver sweep (apf::eigen asserts convergence, apfMatrix.cc:76)", c->h_stats->n_eigen_fail);
+  return MAG_OK;
+}
+
+int mag_clear_flag(mag_ctx* c, int dimension, int32_t flag)
+{
+  if (!c) return MAG_ERR_ARG;
+  MAG_CUDA(c, cudaSetDevice(c->device));
+  if (dimension != 1 && dimension != c->dim) return mag_fail(c, MAG_ERR_ARG, "mag_clear_flag: dimension %d holds no resident flag words (edges = 1, elements = %d)", dimension, c->dim);
+  const bool edges = dimension == 1;
+  if (edges ? c->edge_flags_zero : c->elem_flags_zero) return MAG_OK;   // all words are zero: nothing to clear
+  const int64_t n = edges ? c->ne : c->np + c->npy + c->nt + c->ntri;
+  if (n == 0) return MAG_OK;
+  const int64_t blocks = (n + 255) / 256;
+  const unsigned g = (unsigned)(blocks < (int64_t)c->n_sms * 16 ? blocks : (int64_t)c->n_sms * 16);
+  k_clear_bits<<<g, 256, 0, c->stream>>>(n, flag, edges ? c->d_edge_flags : c->d_elem_flags);
+  MAG_CUDA(c, cudaGetLastError());
+  c->n_launches++;
   return MAG_OK;
 }
 

@@ -333,7 +333,14 @@ class Part:
 
     def getLinearQualitiesInMetricSpace(self, fp_mode=FP_STRICT):   # ma/maStats.cc:12-31 (cbrt in 3D)
         self.sweep(OP_QUALITIES, fp_mode=fp_mode)
-        return np.cbrt(self.qualities()[self.np_ + self.npy:])
+        from . import stats   # the host's libm cbrt, as the reference (numpy's own differs in the last bit)
+        return stats.linear_qualities(self.qualities()[self.np_ + self.npy:], dim=2 if self.ntri else 3)
+
+    def clearFlagFromDimension(self, flag, dimension):          # ma/maAdapt.cc:139-147
+        self._ck(self._L.mag_clear_flag(self._h, int(dimension), int(flag)))
+
+    def unMarkBadQuality(self):                                 # ma/maShape.cc:138-150
+        self.clearFlagFromDimension(BAD_QUALITY, 2 if self.ntri else 3)
 
     # ---- multi-GPU (NCCL)
     @staticmethod

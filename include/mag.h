@@ -134,6 +134,11 @@ int mag_set_metric_logm(mag_ctx* c, const double* logM /*[nv][9] row-major*/);  
 /* ---- incoming "ma_flags" words; NULL = all zero (maAdapt.cc:80-88 getFlags default) ---- */
 int mag_set_flags(mag_ctx* c, const int32_t* edge_flags /*[ne]*/, const int32_t* elem_flags /*[np+npy+nt]*/);
 
+/* ma::clearFlagFromDimension (ma/maAdapt.cc:139-147) on the resident "ma_flags" words: clears the bits of flag on every
+   edge (dimension 1) or every element (dimension = the mesh dimension).  ma::unMarkBadQuality (ma/maShape.cc:138-150) is
+   mag_clear_flag(c, 3, MAG_BAD_QUALITY).  Asynchronous on the context's stream. */
+int mag_clear_flag(mag_ctx* c, int dimension, int32_t flag);
+
 /* ---- the sweep.  max_len / min_len = ma::MAXLENGTH / MINLENGTH (1.5 / 0.5, maSize.h:26-27);
    good_quality = ma::Input::goodQuality; use_max_metric = measureElementQuality's useMax (default true, maShape.h:26).
    Asynchronous on the context's stream; results are read with the getters below (which synchronize). ---- */

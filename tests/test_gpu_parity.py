@@ -373,15 +373,22 @@ def test_reference_named_entry_points(cb):
     assert p.getMinQuality() == want["min_quality"]
     assert p.getMaximumEdgeLength() == want["max_length"]
     assert np.array_equal(p.getEdgeLengthsInMetricSpace(), want["lengths"])
-    assert np.array_equal(p.getLinearQualitiesInMetricSpace(), np.cbrt(want["qualities"]))
+    import ctypes
+    libm = ctypes.CDLL("libm.so.6")
+    libm.cbrt.restype, libm.cbrt.argtypes = ctypes.c_double, [ctypes.c_double]
+    assert np.array_equal(p.getLinearQualitiesInMetricSpace(), np.array([libm.cbrt(float(q)) for q in want["qualities"]]))
     # a second markEdgesToSplit on the marked mesh: the reference asserts because SPLIT is still set
     with pytest.raises(cb.MagError) as ei:
         p.markEdgesToSplit()
     assert ei.value.code == 3
     # clear only the true flags (what ma::refine / unMarkBadQuality do) and re-mark: only un-decided entities are evaluated
-    ef &= ~(cb.SPLIT | cb.COLLAPSE)
-    lf &= ~cb.BAD_QUALITY
     p.set_flags(ef, lf)
+    p.clearFlagFromDimension(cb.SPLIT | cb.COLLAPSE, 1)      # ma::clearFlagFromDimension (maAdapt.cc:139-147)
+    p.unMarkBadQuality()                                      # maShape.cc:138-150
+    ef2, lf2 = p.flags()
+    assert np.array_equal(ef2, ef & ~(cb.SPLIT | cb.COLLAPSE)) and np.array_equal(lf2, lf & ~cb.BAD_QUALITY)
+    with pytest.raises(cb.MagError):
+        p.clearFlagFromDimension(cb.SPLIT, 2)                 # a 3-D part holds words on edges and elements only
     p.sweep(cb.OP_MARK_SPLIT | cb.OP_MARK_COLLAPSE | cb.OP_MARK_BAD)
     st = p.stats()
     assert (st["n_split"], st["n_collapse"], st["n_bad"]) == (want["n_split"], want["n_collapse"], want["n_bad"])
