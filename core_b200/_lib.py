@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmag.so")
 SYMBOLS = [
     "mag_create", "mag_destroy", "mag_last_error", "mag_set_stream", "mag_synchronize",
     "mag_set_mesh", "mag_set_mesh_2d", "mag_set_coords",
-    "mag_set_metric_identity", "mag_set_metric_iso", "mag_set_metric_aniso", "mag_set_metric_logm",
+    "mag_set_metric_identity", "mag_set_metric_uniform_refiner", "mag_set_metric_iso", "mag_set_metric_aniso", "mag_set_metric_logm",
     "mag_set_flags", "mag_clear_flag", "mag_sweep", "mag_sweep_host", "mag_element_weights", "mag_split_vertices", "mag_cavity_quality", "mag_short_edge_test",
     "mag_sliver_codes", "mag_linear_qualities",
     "mag_get_edge_lengths", "mag_get_qualities", "mag_get_flags", "mag_get_layer_ok", "mag_get_stats",
@@ -72,6 +72,7 @@ def lib():
     L.mag_set_mesh_2d.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, vp]
     L.mag_set_coords.argtypes = [vp, vp]
     L.mag_set_metric_identity.argtypes = [vp]
+    L.mag_set_metric_uniform_refiner.argtypes = [vp]
     L.mag_set_metric_iso.argtypes = [vp, vp]
     L.mag_set_metric_aniso.argtypes = [vp, vp, vp]
     L.mag_set_metric_logm.argtypes = [vp, vp]

@@ -132,6 +132,7 @@ int mag_create(mag_ctx** out, int device)
   c->nv = c->ne = c->nt = c->np = c->npy = c->ntri = 0;
   c->dim = 3;
   c->kind = MAG_KIND_NONE;
+  c->uniform_refiner = false;
   c->vertex_pass_valid = false; c->schedule_valid = false; c->edge_flags_zero = c->elem_flags_zero = false; c->s_up = c->s_down = nullptr;
   c->d_xyz = c->d_ma = c->d_mb = c->d_vedge = c->d_vpos = c->d_vq = nullptr;
   c->d_edge_v = c->d_tet_v = c->d_prism_v = c->d_pyr_v = c->d_tri_v = nullptr;
@@ -309,9 +310,16 @@ static int set_metric(mag_ctx* c, int kind, const double* a, size_t na, const do
   if ((rc = dev_reserve(c, c->d_ma, c->cap_ma, na)) || (rc = dev_reserve(c, c->d_mb, c->cap_mb, nb))) return rc;
   if ((rc = upload(c, c->d_ma, a, na)) || (rc = upload(c, c->d_mb, b, nb))) return rc;
   c->kind = kind;
+  c->uniform_refiner = false;
   return repack(c);
 }
 int mag_set_metric_identity(mag_ctx* c) { return set_metric(c, MAG_KIND_IDENTITY, nullptr, 0, nullptr, 0); }
+int mag_set_metric_uniform_refiner(mag_ctx* c)
+{
+  int rc = set_metric(c, MAG_KIND_IDENTITY, nullptr, 0, nullptr, 0);
+  if (rc == MAG_OK) c->uniform_refiner = true;
+  return rc;
+}
 int mag_set_metric_iso(mag_ctx* c, const double* size) { return c ? set_metric(c, MAG_KIND_ISO, size, (size_t)c->nv, nullptr, 0) : MAG_ERR_ARG; }
 int mag_set_metric_aniso(mag_ctx* c, const double* h, const double* R)
 {

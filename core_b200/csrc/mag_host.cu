@@ -90,6 +90,7 @@ extern "C" int mag_sweep_host(mag_ctx* c, const mag_host_part* in, const mag_hos
   if ((rc = magi_reshape(c, 3, nv, ne, nt, 0, 0, 0, in->edge_owned != nullptr, in->elem_owned != nullptr))) return rc;
   if ((rc = magi_reserve_metric(c, in->kind, na, nb))) return rc;
   c->kind = in->kind;
+  c->uniform_refiner = false;
   c->edge_flags_zero = c->elem_flags_zero = false;   // every slice below is uploaded or zeroed explicitly
   c->last_ops = ops;
   c->last_fp_mode = fp_mode;

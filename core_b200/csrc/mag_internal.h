@@ -50,6 +50,7 @@ struct mag_ctx {
   int64_t ntri; // 2-D meshes: the elements are triangles (nt = np = npy = 0)
   int dim;      // mesh dimension (3, or 2 after mag_set_mesh_2d)
   int kind;
+  bool uniform_refiner; // identity kind only: ma::UniformRefiner, shouldSplit constant true (maSize.h:75-85)
   bool vertex_pass_valid;
   // "ma_flags" words are logically all zero (ma::getFlags returns 0 when the tag is absent, maAdapt.cc:80-88) but the
   // device arrays have not been zeroed: the whole-part edge / tet kernels then skip reading them; every other consumer

@@ -1266,7 +1266,8 @@ static SweepParams sweep_params(const mag_ctx* c, uint32_t ops, double max_len, 
   SweepParams P{ops, max_len, min_len, good_q, use_max};
   if (c->kind == MAG_KIND_IDENTITY) {
     // IdentitySizeField::shouldSplit / shouldCollapse are constant false (maSize.cc:64-72): no length exceeds +inf
-    P.max_len = INFINITY;
+    // ma::UniformRefiner (maSize.h:75-85) answers shouldSplit with a constant true: every length exceeds -inf
+    P.max_len = c->uniform_refiner ? -INFINITY : INFINITY;
     P.min_len = -INFINITY;
   }
   return P;

@@ -134,6 +134,11 @@ class Part:
         self._kind = 0
         self._ck(self._L.mag_set_metric_identity(self._h))
 
+    def set_size_field_uniform_refiner(self):
+        """ma::UniformRefiner (maSize.h:75-85), what ma::runUniformRefinement configures: every edge that may be split is."""
+        self._kind = 0
+        self._ck(self._L.mag_set_metric_uniform_refiner(self._h))
+
     def set_size_field_iso(self, size):
         size = _arr(size, np.float64)
         self._kind = 1

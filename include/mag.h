@@ -126,6 +126,8 @@ int mag_set_coords(mag_ctx* c, const double* xyz);
 
 /* ---- size field (vertex nodes, linear Lagrange) ---- */
 int mag_set_metric_identity(mag_ctx* c);                                   /* ma::IdentitySizeField */
+int mag_set_metric_uniform_refiner(mag_ctx* c);                            /* ma::UniformRefiner (ma/maSize.h:75-85): identity measure,
+                                                                              shouldSplit constant true, shouldCollapse false */
 int mag_set_metric_iso(mag_ctx* c, const double* size /*[nv]*/);           /* IsoSizeField / IsoUserField */
 int mag_set_metric_aniso(mag_ctx* c, const double* h /*[nv][3]*/,
                          const double* R /*[nv][9] row-major, frame vectors in columns*/); /* AnisoSizeField */

@@ -11,6 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_build", "libma_oracle.so")
 IDENTITY, ISO, ANISO, LOGM = range(4)
+UNIFORM = 100   # ma::UniformRefiner: IdentitySizeField arithmetic, shouldSplit constant true (maSize.h:75-85); marks only
 
 # ma flag bits, ma/maAdapt.h:17-37
 SPLIT, DONT_SPLIT, COLLAPSE, DONT_COLLAPSE, CHECKED, BAD_QUALITY, OK_QUALITY = (1 << i for i in range(7))
@@ -18,6 +19,11 @@ DONT_SWAP, LAYER = 1 << 9, 1 << 10
 NEED_NOT_SPLIT, NEED_NOT_COLLAPSE = 1 << 17, 1 << 18
 
 _lib = None
+
+
+def _arith(kind):
+    """UniformRefiner measures, transforms and weighs like IdentitySizeField (maSize.h:75-85)."""
+    return IDENTITY if kind == UNIFORM else kind
 
 
 def build():
@@ -97,6 +103,7 @@ def logm_from_frames(h, R, variant=0):
 
 
 def edge_lengths(kind, xyz, ma, mb, edge_v):
+    kind = _arith(kind)
     xyz, ma, mb, edge_v = _f64(xyz), _f64(ma), _f64(mb), _i32(edge_v)
     ne = edge_v.size // 2
     out = np.zeros(ne)
@@ -106,6 +113,7 @@ def edge_lengths(kind, xyz, ma, mb, edge_v):
 
 
 def tet_qualities(kind, xyz, ma, mb, tet_v, use_max=True):
+    kind = _arith(kind)
     xyz, ma, mb, tet_v = _f64(xyz), _f64(ma), _f64(mb), _i32(tet_v)
     nt = tet_v.size // 4
     out = np.zeros(nt)
@@ -116,6 +124,7 @@ def tet_qualities(kind, xyz, ma, mb, tet_v, use_max=True):
 
 def tet_weights(kind, xyz, ma, mb, tet_v, refines_left=None, coarsens_left=0, dim=3):
     """ma::getElementWeight restated (maBalance.cc:21-52,74-81); refines_left None = raw SizeField::getWeight."""
+    kind = _arith(kind)
     xyz, ma, mb, tet_v = _f64(xyz), _f64(ma), _f64(mb), _i32(tet_v)
     nt = tet_v.size // 4
     out = np.zeros(nt)
@@ -128,6 +137,7 @@ def tet_weights(kind, xyz, ma, mb, tet_v, refines_left=None, coarsens_left=0, di
 def sliver_codes(kind, xyz, ma, mb, tet_v, face0_v, good_quality=0.027):
     """ma::getSliverCode / matchSliver (maShape.cc:35-120) of every tet; face0_v = vertices of each tet's first face in
     the face's own order.  Returns (codes [nt], match [nt][2] = {rotation, code_index})."""
+    kind = _arith(kind)
     xyz, ma, mb, tet_v, face0_v = _f64(xyz), _f64(ma), _f64(mb), _i32(tet_v), _i32(face0_v)
     nt = tet_v.size // 4
     codes, match = np.zeros(nt, np.int32), np.zeros((nt, 2), np.int32)
@@ -138,6 +148,7 @@ def sliver_codes(kind, xyz, ma, mb, tet_v, face0_v, good_quality=0.027):
 
 def tri_weights(kind, xyz, ma, mb, tri_v, refines_left=None, coarsens_left=0):
     """ma::getElementWeight on a 2-D mesh (triangle measure / (1/2), clampForIterations with dimension 2)."""
+    kind = _arith(kind)
     xyz, ma, mb, tri_v = _f64(xyz), _f64(ma), _f64(mb), _i32(tri_v)
     nt = tri_v.size // 3
     out = np.zeros(nt)
@@ -156,6 +167,7 @@ def weight_clamps(refines_left, coarsens_left, dim=3):
 
 def split_vertices(kind, xyz, ma, mb, edge_v):
     """ma::makeSplitVert restated: (xyz, a, b) of the vertex splitting each edge, (a, b) in the kind's (ma, mb) layout."""
+    kind = _arith(kind)
     xyz, ma, mb, edge_v = _f64(xyz), _f64(ma), _f64(mb), _i32(edge_v)
     n = edge_v.size // 2
     oxyz = np.zeros((n, 3))
@@ -167,6 +179,7 @@ def split_vertices(kind, xyz, ma, mb, edge_v):
 
 def tri_qualities(kind, xyz, ma, mb, tri_v, use_max=True):
     """measureTriQuality on a 2-D mesh (maQuality.cc:110-136)."""
+    kind = _arith(kind)
     xyz, ma, mb, tri_v = _f64(xyz), _f64(ma), _f64(mb), _i32(tri_v)
     nt = tri_v.size // 3
     out = np.zeros(nt)
@@ -176,6 +189,7 @@ def tri_qualities(kind, xyz, ma, mb, tri_v, use_max=True):
 
 
 def vertex_transforms(kind, ma, mb, nv):
+    kind = _arith(kind)
     ma, mb = _f64(ma), _f64(mb)
     out = np.zeros((nv, 9))
     lib().mao_vertex_transforms(kind, _p(ma), _p(mb), nv, _p(out))
@@ -215,12 +229,12 @@ def mark_entities(value, cmp, thr, flags, owned, true_flag, set_false_flag, all_
 
 def mark_edges_to_split(lengths, flags, owned=None, kind=None):      # maRefine.cc:395-400
     # IdentitySizeField::shouldSplit / shouldCollapse are constant false (maSize.cc:64-72)
-    thr = float("inf") if kind == IDENTITY else 1.5
+    thr = float("inf") if kind == IDENTITY else (float("-inf") if kind == UNIFORM else 1.5)
     return mark_entities(lengths, 0, thr, flags, owned, SPLIT, NEED_NOT_SPLIT, DONT_SPLIT | NEED_NOT_SPLIT)
 
 
 def mark_edges_to_collapse(lengths, flags, owned=None, kind=None):   # maCoarsen.cc:287-292
-    thr = float("-inf") if kind == IDENTITY else 0.5
+    thr = float("-inf") if kind in (IDENTITY, UNIFORM) else 0.5
     return mark_entities(lengths, 1, thr, flags, owned, COLLAPSE, NEED_NOT_COLLAPSE,
                          DONT_COLLAPSE | NEED_NOT_COLLAPSE)
 

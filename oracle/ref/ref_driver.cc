@@ -238,7 +238,8 @@ void refo_set_coords(void* h, const double* xyz)
 /* ---- size fields.  kind: 0 identity, 1 iso scalar field (IsoUserField),
    2 sizes+frames fields linear (AnisoSizeField::init), 3 sizes+frames fields
    log (LogAnisoSizeField::init), 4 anisotropic user function linear,
-   5 anisotropic user function log (LogMEval), 6 isotropic user function. */
+   5 anisotropic user function log (LogMEval), 6 isotropic user function,
+   7 ma::UniformRefiner (maSize.h:75-85: identity measure, shouldSplit constant true). */
 int refo_set_sizefield(void* hd, int kind, const double* hs, const double* R)
 {
   Ref* r = (Ref*)hd; apf::Mesh2* m = r->m;
@@ -278,6 +279,8 @@ int refo_set_sizefield(void* hd, int kind, const double* hs, const double* R)
     r->fn_s.assign(hs, hs + nv);
     r->fi.m = m; r->fi.s = r->fn_s.data();
     r->sf = ma::makeSizeField(m, &r->fi);
+  } else if (kind == 7) {
+    r->sf = new ma::UniformRefiner(m);
   } else return 1;
   return 0;
 }

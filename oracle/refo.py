@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libref_oracle.so")
 
 KIND_IDENTITY, KIND_ISO_FIELD, KIND_ANISO_FIELD, KIND_LOG_FIELD, \
-    KIND_ANISO_FN, KIND_LOG_FN, KIND_ISO_FN = range(7)
+    KIND_ANISO_FN, KIND_LOG_FN, KIND_ISO_FN, KIND_UNIFORM = range(8)
 
 # apf::Mesh::Type (apf/apfMesh.h:149-167)
 VERTEX, EDGE, TRIANGLE, QUAD, TET, HEX, PRISM, PYRAMID = range(8)

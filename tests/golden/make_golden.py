@@ -112,6 +112,10 @@ def main():
     case("box6_iso_fn", m, refo.KIND_ISO_FN, fields.iso_linear(xyz, 1.0 / n))
     case("box6_iso_field", m, refo.KIND_ISO_FIELD, fields.iso_linear(xyz, 1.0 / n))
     case("box6_identity", m, refo.KIND_IDENTITY)
+    # ma::UniformRefiner (what ma::runUniformRefinement configures): every edge not carrying DONT_SPLIT is marked
+    ef = np.zeros(m.ne, np.int32)
+    ef[::7] |= 1 << 1
+    case("box6_uniform_refiner", m, refo.KIND_UNIFORM, edge_flags=ef)
     h, R = fields.shock_planar(xyz, 1.0 / n)
     case("box6_shock_planar_aniso", m, refo.KIND_ANISO_FN, h, R)
     case("box6_shock_planar_logfn", m, refo.KIND_LOG_FN, h, R)

@@ -9,7 +9,7 @@ from oracle import mao
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 # reference driver kinds (oracle/refo.py) -> restated-oracle kinds
-REF_KIND_TO_MAO = {0: mao.IDENTITY, 1: mao.ISO, 2: mao.ANISO, 3: mao.LOGM, 4: mao.ANISO, 5: mao.LOGM, 6: mao.ISO}
+REF_KIND_TO_MAO = {0: mao.IDENTITY, 1: mao.ISO, 2: mao.ANISO, 3: mao.LOGM, 4: mao.ANISO, 5: mao.LOGM, 6: mao.ISO, 7: mao.UNIFORM}
 # apf::Mesh::Type
 TRIANGLE, TET, PRISM, PYRAMID = 2, 4, 6, 7
 
@@ -40,7 +40,7 @@ def split_elements(g):
 def metric_arrays(g):
     """(mao kind, ma, mb) as the restated oracle / mag_set_metric_* take them."""
     kind = REF_KIND_TO_MAO[int(g["kind"])]
-    if kind == mao.IDENTITY:
+    if kind in (mao.IDENTITY, mao.UNIFORM):
         return kind, None, None
     if kind == mao.ISO:
         return kind, g["h"], None
@@ -57,6 +57,8 @@ def logm_variant(g):
 def set_part_metric(p, kind, ma, mb):
     if kind == mao.IDENTITY:
         p.set_size_field_identity()
+    elif kind == mao.UNIFORM:
+        p.set_size_field_uniform_refiner()
     elif kind == mao.ISO:
         p.set_size_field_iso(ma)
     elif kind == mao.ANISO:
