@@ -82,7 +82,7 @@ struct mag_ctx {
   int32_t* d_layer_codes;
   MagDevStats* d_stats;
   MagDevStats* h_stats;  // pinned
-  double* d_block_sums;  // [MAG_SUM_BLOCKS] partial sums of owned edge lengths (MAG_OP_LENGTH_SUM)
+  double* d_block_sums;  // [MAG_SUM_BLOCKS] partial sums of the edge lengths (MAG_OP_LENGTH_SUM)
   int32_t* d_near_edge;  // [ne]  near-threshold edge indices of the last sweep (an entity is listed at most once)
   int32_t* d_near_elem;  // [np+npy+nt]
   int n_sms;

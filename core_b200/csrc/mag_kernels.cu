@@ -531,7 +531,7 @@ k_edges(int32_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
   }
 }
 
-// ma::getAverageEdgeLength-style sum of the stored lengths over owned edges (MAG_OP_LENGTH_SUM): a fixed-shape
+// ma::getAverageEdgeLength's sum of the stored lengths over all edges of the part (MAG_OP_LENGTH_SUM): a fixed-shape
 // two-level tree (per-thread strided partial -> warp -> block -> k_finish_sum), deterministic for a given ne
 __global__ void __launch_bounds__(kThreads)
 k_sum_lengths(int64_t ne, const double* __restrict__ lengths, const uint8_t* __restrict__ owned_arr, double* __restrict__ block_sums)
@@ -545,7 +545,7 @@ k_sum_lengths(int64_t ne, const double* __restrict__ lengths, const uint8_t* __r
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0;
-    for (int i = 0; i < kWarps; ++i) t += sh[i];
+    for (int i = 0; i < kThreads / 32; ++i) t += sh[i];   // the block's warps (sh is sized for the largest block)
     block_sums[blockIdx.x] = t;
   }
 }
@@ -1299,7 +1299,8 @@ int magk_tets_range(mag_ctx* c, uint32_t ops, double good_q, int use_max, int fp
 }
 int magk_length_sum(mag_ctx* c)
 {
-  k_sum_lengths<<<MAG_SUM_BLOCKS, kThreads, 0, c->stream>>>(c->ne, c->d_len, c->d_edge_owned, c->d_block_sums);
+  // ma::getAverageEdgeLength (maSize.cc:654-671) adds up EVERY edge a part holds, owned or not, before the PCU Add
+  k_sum_lengths<<<MAG_SUM_BLOCKS, kThreads, 0, c->stream>>>(c->ne, c->d_len, nullptr, c->d_block_sums);
   k_finish_sum<<<1, kThreads, 0, c->stream>>>((int64_t)MAG_SUM_BLOCKS, c->d_block_sums, c->d_stats);
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches += 2;

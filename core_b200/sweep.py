@@ -332,6 +332,14 @@ class Part:
         self.sweep(OP_LENGTHS, fp_mode=fp_mode)
         return self.stats()["max_length"]
 
+    def getAverageEdgeLength(self, fp_mode=FP_STRICT):      # ma/maSize.cc:654-671
+        """Mean PHYSICAL edge length over every edge of the part (the reference measures with an IdentitySizeField whatever
+        the adapt's size field is): call with the identity size field set."""
+        if self._kind != 0:
+            raise MagError(2, "getAverageEdgeLength measures with ma::IdentitySizeField: set_size_field_identity() first")
+        self.sweep(OP_LENGTHS | OP_LENGTH_SUM, fp_mode=fp_mode)
+        return self.stats()["sum_length"] / self.ne
+
     def getEdgeLengthsInMetricSpace(self, fp_mode=FP_STRICT):   # ma/maStats.cc:33-45
         self.sweep(OP_LENGTHS, fp_mode=fp_mode)
         return self.edge_lengths()

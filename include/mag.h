@@ -70,8 +70,10 @@ enum {
   MAG_OP_MARK_BAD = 1 << 4,      /* ma::markBadQuality */
   MAG_OP_LAYER_CHECK = 1 << 5,   /* ma::isPrismOk / isPyramidOk on every prism / pyramid (ma::checkLayerShape, maLayer.cc:166-192) */
   MAG_OP_ALL = 63,
-  MAG_OP_LENGTH_SUM = 1 << 6     /* additionally reduce the sum of the measured lengths over owned edges into mag_stats.sum_length
-                                    (needs MAG_OP_LENGTHS; not part of MAG_OP_ALL: no reference mark needs it) */
+  MAG_OP_LENGTH_SUM = 1 << 6     /* additionally reduce the sum of the measured lengths over EVERY edge of the part (owned or not, as
+                                    ma::getAverageEdgeLength does, ma/maSize.cc:654-671) into mag_stats.sum_length; the average is
+                                    sum_length / ne, or the two summed over the parts (needs MAG_OP_LENGTHS; not part of MAG_OP_ALL:
+                                    no reference mark needs it) */
 };
 
 /* arithmetic mode */
@@ -94,7 +96,8 @@ typedef struct mag_stats {
   int64_t n_flag_mismatch;  /* part-boundary copies that disagreed before owner reconciliation (must be 0) */
   double min_quality;       /* ma::getMinQuality: min over all tets, initial value 1.0 (valid after MAG_OP_QUALITIES) */
   double max_length;        /* ma::getMaximumEdgeLength: max over owned edges, initial 0.0 (valid after MAG_OP_LENGTHS) */
-  double sum_length;        /* MAG_OP_LENGTH_SUM: sum over owned edges (fixed tree order, not the reference's serial order); else 0 */
+  double sum_length;        /* MAG_OP_LENGTH_SUM: sum over all edges of the part (fixed tree order, not the reference's serial order:
+                               equal to 1e-13 relative, not bit for bit); else 0 */
 } mag_stats;
 
 /* ---- lifetime ---- */

@@ -377,6 +377,19 @@ def test_reference_named_entry_points(cb):
     libm = ctypes.CDLL("libm.so.6")
     libm.cbrt.restype, libm.cbrt.argtypes = ctypes.c_double, [ctypes.c_double]
     assert np.array_equal(p.getLinearQualitiesInMetricSpace(), np.array([libm.cbrt(float(q)) for q in want["qualities"]]))
+    # ma::getAverageEdgeLength (maSize.cc:654-671): identity measure, every edge of the part whether owned or not
+    with pytest.raises(cb.MagError):
+        p.getAverageEdgeLength()
+    eo = (np.arange(len(ev)) % 3 != 0).astype(np.uint8)
+    p2 = cb.Part(0)
+    p2.set_mesh(xyz, ev, tv, edge_owned=eo)
+    p2.set_size_field_identity()
+    L_id = mao.edge_lengths(mao.IDENTITY, xyz, None, None, ev)
+    serial = 0.0
+    for v in L_id:
+        serial += float(v)
+    assert abs(p2.getAverageEdgeLength() - serial / len(ev)) <= 1e-13 * serial / len(ev)
+    p2.close()
     # a second markEdgesToSplit on the marked mesh: the reference asserts because SPLIT is still set
     with pytest.raises(cb.MagError) as ei:
         p.markEdgesToSplit()
