@@ -685,3 +685,17 @@ def test_nccl_two_gpus(cb):
     import json
     line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert line["n_gpus"] == 2 and line["stats"]["n_flag_mismatch"] == 0
+
+
+def test_nccl_two_part_device(cb):
+    """Two slab parts on two GPUs through mag_comm_* (tests/nccl_two_part.py): consistent copies and global statistics
+    equal to the serial oracle, injected disagreements counted and resolved by the owner, syncFlag's OR."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29613", os.path.join(root, "tests", "nccl_two_part.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "NCCL_TWO_PART_OK" in out.stdout, (out.stdout[-1500:], out.stderr[-3000:])
