@@ -455,21 +455,25 @@ def run_b200(a):
         step_ms = ms_total / a.steps
         # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/traffic.json,
         # written by scripts/profile_summary.py); only meaningful for the configuration that was profiled
-        traffic = None
+        traffic, units = None, None
         try:
             if n == 203 and a.field == "aniso" and world == 1 and a.jitter == 0:
                 tj = json.load(open(os.path.join(HERE, "profiles", "traffic.json")))
                 # template arguments as ncu prints them: k_edges<KIND, FAST, VERT>, k_tets<KIND, FAST, USE_MAX>
                 key = "%s<2, %d, %d>" % (dom, 1 if a.fp == "fast" else 0, 0 if dom == "k_edges" else 1)
                 traffic = float(tj[key]["dram_bytes_per_launch"])
+                # the path is not purely HBM-bound: utilisation of the other units under ncu
+                units = {k: tj[key].get(k) for k in ("fp64_pipe_pct", "l1_data_pipe_pct", "dram_pct", "warps_active_pct")}
+                units["source"] = tj[key].get("source")
         except Exception:
-            traffic = None
+            traffic, units = None, None
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": int(dom_bytes), "kernel_ms": dom_ms,
                     "kernel_ms_all": {"vertex_pass": vert_ms, "edges": edge_ms, "elements": elem_ms},
                     "step_algorithmic_bytes": int(ab["total"]),
-                    "step_frac": ab["total"] / (step_ms * 1e-3) / 1e9 / peak}
+                    "step_frac": ab["total"] / (step_ms * 1e-3) / 1e9 / peak,
+                    "unit_utilisation_ncu": units}
         cpu = None
         if not a.no_cpu:
             cpu = cpu_baseline(a.cpu_n or 55)   # BASELINE configs[1] size: 998,250 tets, ~11 s on one core

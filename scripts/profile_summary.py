@@ -46,7 +46,17 @@ for r in rows[2:]:
                 pass
     stalls.sort(reverse=True)
     lines.append("%s\n    %s\n    stalls per issue: %s" % (short, ", ".join(vals), ", ".join("%s %.2f" % (h, v) for v, h in stalls[:6])))
-    traffic[short] = {"dram_bytes_per_launch": dram, "source": "profiles/%s_ncu_summary.txt" % tag}
+    def pct(key):
+        try:
+            return float(r[hdr.index(key)].replace(",", ""))
+        except (ValueError, IndexError):
+            return None
+    # the units that bound these kernels besides HBM: reported by bench.py next to the HBM fraction
+    traffic[short] = {"dram_bytes_per_launch": dram, "source": "profiles/%s_ncu_summary.txt" % tag,
+                      "fp64_pipe_pct": pct("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                      "l1_data_pipe_pct": pct("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+                      "dram_pct": pct("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                      "warps_active_pct": pct("sm__warps_active.avg.pct_of_peak_sustained_active")}
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
 launch_src = os.path.join(ROOT, "gpurun_out", tag + "_launches.csv")
 if os.path.exists(launch_src):
