@@ -101,6 +101,27 @@ def mixed_box(n, k):
     return xyz, np.array(tets, np.int32), np.array(prisms, np.int32)
 
 
+def prism_pyramid_slab(nx, ny):
+    """One layer of nx x ny cells: cell (x, y) with x + y even = 2 prisms, odd = 6 pyramids around the cell centre (every
+    face between neighbouring cells is a quad, so the mesh conforms).  Returns xyz, prisms [.,6], pyramids [.,5]."""
+    s = nx + 1
+    vid = lambda x, y, z: x + s * (y + (ny + 1) * z)
+    xyz = [[x / nx, y / ny, z / max(nx, ny)] for z in (0, 1) for y in range(ny + 1) for x in range(s)]
+    prisms, pyrs = [], []
+    for y in range(ny):
+        for x in range(nx):
+            c = [vid(x, y, 0), vid(x + 1, y, 0), vid(x + 1, y + 1, 0), vid(x, y + 1, 0),
+                 vid(x, y, 1), vid(x + 1, y, 1), vid(x + 1, y + 1, 1), vid(x, y + 1, 1)]
+            if (x + y) % 2 == 0:
+                prisms += [[c[0], c[1], c[2], c[4], c[5], c[6]], [c[0], c[2], c[3], c[4], c[6], c[7]]]
+            else:
+                a = len(xyz)
+                xyz.append(np.mean([xyz[i] for i in c], axis=0).tolist())
+                for q in ([0, 1, 2, 3], [4, 7, 6, 5], [0, 4, 5, 1], [1, 5, 6, 2], [2, 6, 7, 3], [3, 7, 4, 0]):   # bases seen from the apex
+                    pyrs.append([c[q[0]], c[q[1]], c[q[2]], c[q[3]], a])
+    return np.array(xyz), np.array(prisms, np.int32), np.array(pyrs, np.int32)
+
+
 def main():
     assert refo.available(), "build oracle/_ref first (make -C oracle/ref)"
     rng = np.random.default_rng(20261017)
@@ -175,6 +196,32 @@ def main():
     np.savez_compressed(os.path.join(HERE, "mixed5_unsafe_layer.npz"), xyz=xyz, edge_v=ev, elem_type=et, elem_v=elv,
                         layer_ok=ok, layer_codes=codes)
     print("mixed5_unsafe_layer          unsafe prisms: %d of %d" % (int((ok == 0).sum()), len(prisms)))
+    m.close()
+
+    # prisms + pyramids (ma::isPyramidOk, LAYER closure over pyramid edges): a mildly jittered slab through a real ma::Adapt,
+    # and the same slab with the apexes and corners thrown far enough that pyramids become unsafe (isPyramidOk only)
+    rng2 = np.random.default_rng(20261018)          # its own stream: the fixtures generated after it keep their values
+    xyz, prisms, pyrs = prism_pyramid_slab(4, 3)
+    nc = 2 * 5 * 4                                   # corner vertices; the rest are pyramid apexes
+    x1 = xyz.copy()
+    x1[nc:] += 0.05 * (rng2.random((len(xyz) - nc, 3)) - 0.5)
+    m = refo.RefMesh.build(x1, prisms=prisms, pyramids=pyrs)
+    h, R = fields.shock_rotating(x1, 1.0 / 4)
+    case("pyrslab_shock_rot_aniso", m, refo.KIND_ANISO_FIELD, h, R)
+    m.close()
+    xyz, prisms, pyrs = prism_pyramid_slab(6, 5)
+    nc = 2 * 7 * 6
+    x2 = xyz.copy()
+    x2 += 0.2 * (rng2.random(xyz.shape) - 0.5) * np.array([1.0, 1.0, 0.5])
+    x2[nc:] += 0.3 * (rng2.random((len(xyz) - nc, 3)) - 0.5)
+    m = refo.RefMesh.build(x2, prisms=prisms, pyramids=pyrs)
+    _, ev, et, elv = m.export()
+    ok, codes = m.layer_ok()
+    np.savez_compressed(os.path.join(HERE, "pyrslab_unsafe_layer.npz"), xyz=x2, edge_v=ev, elem_type=et, elem_v=elv,
+                        layer_ok=ok, layer_codes=codes)
+    py = et == refo.PYRAMID
+    print("pyrslab_unsafe_layer         unsafe pyramids: %d of %d, good rotations %s; unsafe prisms %d" % (
+        int((ok[py] == 0).sum()), int(py.sum()), np.bincount(codes[py] + 1, minlength=3).tolist(), int((ok[~py] == 0).sum())))
     m.close()
 
     # native-format fixtures written by the reference itself (mds_write_smb) with the arrays its own API exports from the

@@ -315,6 +315,20 @@ def test_unsafe_prisms(cb):
     p.close()
 
 
+def test_unsafe_pyramids(cb):
+    """ma::isPyramidOk on the device against the compiled reference (good rotations -1 / 0 / 1), prisms of the same mesh too."""
+    g = util.load("pyrslab_unsafe_layer")
+    prism_v, pyr_v, tet_v = util.split_elements(g)
+    p = cb.Part(0)
+    p.set_mesh(g["xyz"], g["edge_v"], None, prism_v, pyr_v)
+    p.set_size_field_identity()
+    p.sweep(cb.OP_LAYER_CHECK)
+    ok, codes = p.layer_ok()
+    assert np.array_equal(ok, g["layer_ok"]) and np.array_equal(codes, g["layer_codes"])
+    assert p.stats()["n_layer_unsafe"] == int((g["layer_ok"] == 0).sum())
+    p.close()
+
+
 @pytest.mark.parametrize("kindname", ["identity", "iso", "aniso", "logm"])
 def test_random_box_vs_oracle(cb, kindname):
     """Seeded jittered box, random frames / sizes, random incoming flag words and ownership, both fp modes."""

@@ -64,6 +64,9 @@ def test_oracle_matches_reference_golden(name, built):
         ok, codes = mao.prism_ok(g["xyz"], prism_v)
         assert np.array_equal(ok, g["layer_ok"][:len(prism_v)])
         assert np.array_equal(codes, g["layer_codes"][:len(prism_v)])
+        ok, codes = mao.pyramid_ok(g["xyz"], pyr_v)        # ma::isPyramidOk: the good rotation (maQuality.cc:533-560)
+        assert np.array_equal(ok, g["layer_ok"][len(prism_v):nns])
+        assert np.array_equal(codes, g["layer_codes"][len(prism_v):nns])
 
 
 def check_2d(g, kind, ma, mb):
@@ -102,6 +105,24 @@ def test_layer_closure_flags_golden():
     ef, lf = boxmesh.layer_closure_flags(g["edge_v"], prism_v, None, len(tet_v))
     assert np.array_equal(ef, g["edge_flags_ctor"])
     assert np.array_equal(lf, g["elem_flags_ctor"])
+    g = util.load("pyrslab_shock_rot_aniso")             # pyramids too: their eight edges join the closure
+    prism_v, pyr_v, tet_v = util.split_elements(g)
+    assert len(pyr_v) == 36 and len(tet_v) == 0
+    ef, lf = boxmesh.layer_closure_flags(g["edge_v"], prism_v, pyr_v, 0)
+    assert np.array_equal(ef, g["edge_flags_ctor"])
+    assert np.array_equal(lf, g["elem_flags_ctor"])
+
+
+def test_unsafe_pyramids_golden(built):
+    """ma::isPyramidOk on a prism + pyramid slab thrown about until half of the pyramids are unsafe: all three good-rotation
+    values (-1, 0, 1) occur; also the unsafe prisms of the same mesh."""
+    g = util.load("pyrslab_unsafe_layer")
+    prism_v, pyr_v, _ = util.split_elements(g)
+    ok, codes = mao.pyramid_ok(g["xyz"], pyr_v)
+    assert set(codes.tolist()) == {-1, 0, 1} and 0 < (ok == 0).sum() < len(ok)
+    assert np.array_equal(ok, g["layer_ok"][len(prism_v):]) and np.array_equal(codes, g["layer_codes"][len(prism_v):])
+    ok, codes = mao.prism_ok(g["xyz"], prism_v)
+    assert np.array_equal(ok, g["layer_ok"][:len(prism_v)]) and np.array_equal(codes, g["layer_codes"][:len(prism_v)])
 
 
 def test_unsafe_prisms_golden(built):
@@ -181,4 +202,5 @@ def test_stats_tables_match_ma_stats(name, built, tmp_path):
     rows = open(pe).read().split("\n")
     assert len(rows) == len(el) + 1 and rows[-1] == ""
     assert rows[0] == "%g" % el[0] and np.allclose(np.array(rows[:-1], float), el, rtol=1e-5)
-    assert np.allclose(np.loadtxt(pq), lq, rtol=1e-5, atol=1e-300)
+    got = np.array([float(x) for x in open(pq).read().split()])   # empty on a mesh without simplex elements
+    assert len(got) == len(lq) and np.allclose(got, lq, rtol=1e-5, atol=1e-300)
