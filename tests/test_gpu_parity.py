@@ -425,6 +425,50 @@ def test_reference_named_entry_points(cb):
     p.close()
 
 
+def test_set_coords_stream_and_reshape(cb):
+    """Coordinates replaced under a resident mesh (vertex motion: the packed records, the per-vertex pass and cached
+    cavity transforms must follow), a caller-owned CUDA stream, and a context re-used for a part of another shape."""
+    import torch
+    from oracle import mao
+    n = 7
+    xyz, ev, tv = cb.boxmesh.kuhn_box(n, n, n)
+    x0 = cb.fields.jitter(xyz, 0.2 / n, seed=3)
+    x1 = cb.fields.jitter(xyz, 0.3 / n, seed=4)
+    h, R = cb.fields.shock_rotating(xyz, 1.0 / n)
+    p = cb.Part(0)
+    p.set_mesh(x0, ev, tv)
+    p.set_size_field_aniso(h, R)
+    p.sweep(cb.OP_ALL & ~cb.OP_LAYER_CHECK)
+    check_against(cb, p, util.oracle_sweep(mao.ANISO, x0, h, R, ev, tv), mao.ANISO, cb.FP_STRICT)
+    off = np.arange(0, len(tv) + 1, 2, dtype=np.int64)
+    w0 = p.cavity_quality(off, tv)                       # caches the per-vertex transforms of x0
+    p.set_coords(x1)
+    p.clear_flags()
+    p.sweep(cb.OP_ALL & ~cb.OP_LAYER_CHECK)
+    want1 = util.oracle_sweep(mao.ANISO, x1, h, R, ev, tv)
+    check_against(cb, p, want1, mao.ANISO, cb.FP_STRICT)
+    w1 = p.cavity_quality(off, tv)
+    assert np.array_equal(w1, np.minimum.reduceat(want1["qualities"], off[:-1])) and not np.array_equal(w0, w1)
+    # the same sweep on a stream the caller owns
+    s = torch.cuda.Stream()
+    p.set_stream(s.cuda_stream)
+    for mode in (cb.FP_STRICT, cb.FP_FAST):
+        p.clear_flags()
+        p.sweep(cb.OP_ALL & ~cb.OP_LAYER_CHECK, fp_mode=mode)
+        check_against(cb, p, want1, mao.ANISO, mode)
+    p.set_stream(None)
+    # another shape on the same context: smaller mesh, other size-field kind
+    xs, es, ts = cb.boxmesh.kuhn_box(3, 4, 2)
+    siz = cb.fields.iso_linear(xs, 0.3)
+    p.set_mesh(xs, es, ts)
+    with pytest.raises(cb.MagError):
+        p.sweep()                                        # the size field went with the old mesh
+    p.set_size_field_iso(siz)
+    p.sweep(cb.OP_ALL & ~cb.OP_LAYER_CHECK)
+    check_against(cb, p, util.oracle_sweep(mao.ISO, xs, siz, None, es, ts), mao.ISO, cb.FP_STRICT)
+    p.close()
+
+
 def test_near_threshold_listing(cb):
     """An edge whose metric length is exactly the threshold: listed, and marked as the reference's strict
     comparison decides (1.5 > 1.5 is false) in both modes."""
