@@ -32,7 +32,7 @@ static void fail(mag_ctx* c, const char* what, int rc)
 
 struct Export {
   std::vector<double> xyz, ma, mb;
-  std::vector<int> edge_v, tet_v, prism_v, pyr_v;
+  std::vector<int> edge_v, tet_v, prism_v, pyr_v, tri_v;   /* tri_v: the elements of a 2-D mesh */
   std::vector<unsigned char> edge_owned, elem_owned;
   std::vector<ma::Entity*> edges, elems; /* iteration order; elems = prisms | pyramids | tets */
 };
@@ -56,7 +56,7 @@ struct Access {
   {
     int slot;
     g->lastGoodQuality = goodQuality;
-    if (!g->serve(e, 3, slot)) return false;
+    if (!g->serve(e, g->mesh->getDimension(), slot)) return false;
     q = g->qualities[slot];
     return true;
   }
@@ -65,7 +65,8 @@ struct Access {
   static void exportMesh(GpuSizeField* g, Export& x)
   {
     ma::Mesh* m = g->mesh;
-    if (m->getDimension() != 3) { fprintf(stderr, "mag adapter: only 3D meshes are supported\n"); abort(); }
+    const int mdim = m->getDimension();
+    if (mdim != 3 && mdim != 2) { fprintf(stderr, "mag adapter: only 2D and 3D meshes are supported\n"); abort(); }
     size_t nv = m->count(0);
     std::vector<int>& vslot = g->vertSlot;
     vslot.assign(vslot.size(), -1);
@@ -111,14 +112,15 @@ struct Access {
       ++k;
     }
     m->end(it);
-    /* dimension 3 iterates prisms, pyramids, tets (MDS type order, mds.h:16-26) */
+    /* dimension 3 iterates prisms, pyramids, tets (MDS type order, mds.h:16-26); on a 2-D mesh the elements are the
+       triangles (ma::measureTriQuality), kept in the same "te" list and slot table */
     std::vector<ma::Entity*> pr, py, te;
-    it = m->begin(3);
+    it = m->begin(mdim);
     while ((e = m->iterate(it))) {
       int t = m->getType(e);
-      if (t == apf::Mesh::PRISM) pr.push_back(e);
-      else if (t == apf::Mesh::PYRAMID) py.push_back(e);
-      else if (t == apf::Mesh::TET) te.push_back(e);
+      if (mdim == 3 && t == apf::Mesh::PRISM) pr.push_back(e);
+      else if (mdim == 3 && t == apf::Mesh::PYRAMID) py.push_back(e);
+      else if (t == (mdim == 3 ? apf::Mesh::TET : apf::Mesh::TRIANGLE)) te.push_back(e);
       else { fprintf(stderr, "mag adapter: element type %d is not supported\n", t); abort(); }
     }
     m->end(it);
@@ -136,7 +138,8 @@ struct Access {
         for (int j = 0; j < n; ++j) out[i * n + j] = vslot[apf::getMdsIndex(m, dv[j])];
       }
     };
-    conn(pr, 6, x.prism_v); conn(py, 5, x.pyr_v); conn(te, 4, x.tet_v);
+    conn(pr, 6, x.prism_v); conn(py, 5, x.pyr_v);
+    if (mdim == 3) conn(te, 4, x.tet_v); else conn(te, 3, x.tri_v);
     g->tetSlot.assign(g->tetSlot.size(), -1);
     for (size_t i = 0; i < te.size(); ++i) {
       int id = apf::getMdsIndex(m, te[i]);
@@ -149,6 +152,10 @@ struct Access {
   static void upload(GpuSizeField* g, Export& x)
   {
     mag_ctx* c = g->ctx;
+    if (g->mesh->getDimension() == 2)
+      MAG_DO(c, mag_set_mesh_2d(c, (int64_t)(x.xyz.size() / 3), x.xyz.data(), (int64_t)x.edges.size(), x.edge_v.data(),
+                                (int64_t)(x.tri_v.size() / 3), x.tri_v.data(), x.edge_owned.data(), x.elem_owned.data()));
+    else
     MAG_DO(c, mag_set_mesh(c, (int64_t)(x.xyz.size() / 3), x.xyz.data(), (int64_t)x.edges.size(), x.edge_v.data(),
                            (int64_t)(x.tet_v.size() / 4), x.tet_v.data(), (int64_t)(x.prism_v.size() / 6), x.prism_v.data(),
                            (int64_t)(x.pyr_v.size() / 5), x.pyr_v.data(), x.edge_owned.data(), x.elem_owned.data()));
@@ -222,7 +229,7 @@ bool GpuSizeField::serve(ma::Entity* e, int dim, int& slot)
   lastDim = dim;
   lastId = id;
   if (!in_order) { dirty = true; streak = 0; return false; }
-  if (!dirty && ((long)mesh->count(1) != (long)lengths.size() || (long)mesh->count(3) != (long)qualities.size())) dirty = true;
+  if (!dirty && ((long)mesh->count(1) != (long)lengths.size() || (long)mesh->count(mesh->getDimension()) != (long)qualities.size())) dirty = true;
   if (dirty) {
     if (++streak < kSweepDetect) return false;
     refresh(lastGoodQuality);
@@ -397,11 +404,13 @@ void getLinearQualitiesInMetricSpace(ma::Mesh* m, ma::SizeField* sf, std::vector
   g->refresh(-1);
   /* owned simplex elements, cbrt of the mean ratio cubed (maStats.cc:12-31) */
   out.clear();
-  apf::MeshIterator* it = m->begin(3);
+  const int dim = m->getDimension();
+  apf::MeshIterator* it = m->begin(dim);
   ma::Entity* e;
   while ((e = m->iterate(it))) {
-    if (m->getType(e) != apf::Mesh::TET || !m->isOwned(e)) continue;
-    out.push_back(cbrt(Access::qualityOf(g, e)));
+    if (m->getType(e) != (dim == 3 ? apf::Mesh::TET : apf::Mesh::TRIANGLE) || !m->isOwned(e)) continue;
+    const double lq = Access::qualityOf(g, e);
+    out.push_back(dim == 2 ? ((lq > 0) ? sqrt(lq) : -sqrt(-lq)) : cbrt(lq));   /* maStats.cc:24-28 */
   }
   m->end(it);
 }
@@ -422,7 +431,8 @@ ma::Tag* getElementWeights(ma::Adapt* a)
   apf::MeshIterator* it = m->begin(dim);
   ma::Entity* e;
   while ((e = m->iterate(it))) {
-    double weight = m->getType(e) == apf::Mesh::TET ? w[Access::tetSlotOf(g, e)] : ma::getElementWeight(a, e);
+    const int t = m->getType(e);
+    double weight = (t == apf::Mesh::TET || (dim == 2 && t == apf::Mesh::TRIANGLE)) ? w[Access::tetSlotOf(g, e)] : ma::getElementWeight(a, e);
     m->setDoubleTag(e, weights, &weight);
   }
   m->end(it);
@@ -464,7 +474,8 @@ class GpuShapeHandler : public ma::ShapeHandler
     {
       GpuSizeField* g = dynamic_cast<GpuSizeField*>(a->sizeField);
       double q;
-      if (g && a->mesh->getType(e) == apf::Mesh::TET) {
+      const int t = a->mesh->getType(e);
+      if (g && (t == apf::Mesh::TET || (t == apf::Mesh::TRIANGLE && a->mesh->getDimension() == 2))) {
         if (Access::serveQuality(g, e, a->input->goodQuality, q)) return q;
         /* LinearHandler::getQuality (maShapeHandler.cc:27-30) on the wrapped reference field */
         if (a->mesh->getShape()->getOrder() == 1) return ma::measureElementQuality(a->mesh, g->wrapped, e);

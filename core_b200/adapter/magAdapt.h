@@ -14,6 +14,7 @@
 //   ma::getSliverCode / matchSliver   ma/maShape.cc:35-120  ->  mag::getSliverCodes(Adapt*, ...)  (every tet in one sweep)
 //   ma::getShapeHandler(Adapt*)       ma/maShapeHandler.cc  ->  mag::shapeHandler  (an ma::ShapeHandlerFunction for Input::shapeHandler)
 //
+// 3-D meshes (tets, with prisms / pyramids as layer elements) and 2-D meshes (triangles: ma::measureTriQuality).
 // mag::GpuSizeField IS an ma::SizeField: it can be put in ma::Input::sizeField and the UNMODIFIED reference keeps
 // working -- the per-entity virtuals (measure / shouldSplit / shouldCollapse) are answered from the last device sweep
 // while the mesh is unchanged, and delegated to the wrapped reference size field (the rest of the reference running as

@@ -84,7 +84,7 @@ void collect_flags(ma::Adapt* a, Marks& k)
   k.ef.clear(); k.lf.clear();
   while ((e = m->iterate(it))) k.ef.push_back(ma::getFlags(a, e));
   m->end(it);
-  it = m->begin(3);
+  it = m->begin(m->getDimension());
   while ((e = m->iterate(it))) k.lf.push_back(ma::getFlags(a, e));
   m->end(it);
 }
@@ -103,18 +103,29 @@ long diff(const std::vector<int>& a, const std::vector<int>& b)
    report[5..9]  adapter bulk (A), report[10..14] unmodified reference loops over the adapter (B)
    report[15..18] flag words differing: A edges, A elems, B edges, B elems;  report[19] sweeps the adapter ran for B
    returns 0 when A and B reproduce the reference exactly (fp_mode strict) / flags+counts exactly, values 1e-12 (fast). */
+static int adapter_check(int n, int nz, int log_interp, int fp_mode, double jitter, double* report);
 extern "C" int mag_adapter_check(int n, int log_interp, int fp_mode, double jitter, double* report)
 {
+  return adapter_check(n, n, log_interp, fp_mode, jitter, report);
+}
+/* the same on a 2-D box (triangles are the elements: ma::measureTriQuality, goodQuality 0.2 as ma::configure picks in 2-D) */
+extern "C" int mag_adapter_check_2d(int n, int log_interp, int fp_mode, double jitter, double* report)
+{
+  return adapter_check(n, 0, log_interp, fp_mode, jitter, report);
+}
+static int adapter_check(int n, int nz, int log_interp, int fp_mode, double jitter, double* report)
+{
   ensure_pcu();
-  apf::Mesh2* m = apf::makeMdsBox(n, n, n, 1, 1, 1, true, g_pcu);
+  apf::Mesh2* m = apf::makeMdsBox(n, n, nz, 1, 1, nz ? 1 : 0, true, g_pcu);
+  const int dim = m->getDimension();
   if (jitter > 0) {
     unsigned long long s = 12345;
     apf::MeshIterator* it = m->begin(0); apf::MeshEntity* v;
     while ((v = m->iterate(it))) {
       apf::Vector3 p; m->getPoint(v, 0, p);
       bool interior = true;
-      for (int i = 0; i < 3; ++i) interior = interior && p[i] > 1e-9 && p[i] < 1 - 1e-9;
-      for (int i = 0; i < 3; ++i) {
+      for (int i = 0; i < dim; ++i) interior = interior && p[i] > 1e-9 && p[i] < 1 - 1e-9;
+      for (int i = 0; i < dim; ++i) {
         s = s * 6364136223846793005ULL + 1442695040888963407ULL;
         double u = (double)(s >> 11) / 9007199254740992.0;
         if (interior) p[i] += jitter / n * (u - 0.5);
@@ -159,7 +170,7 @@ extern "C" int mag_adapter_check(int n, int log_interp, int fp_mode, double jitt
       /* ma::getElementWeights (maBalance.cc:83-97) against the reference's own per-entity loop on the same Adapt */
       a.refinesLeft = 0; a.coarsensLeft = 1;
       ma::Tag* wt = mag::getElementWeights(&a);
-      apf::MeshIterator* wit = m->begin(3);
+      apf::MeshIterator* wit = m->begin(dim);
       ma::Entity* we;
       while ((we = m->iterate(wit))) {
         double wg, wr = ma::getElementWeight(&a, we);   /* a.sizeField is the adapter; its getWeight delegates to the wrapped reference field */
@@ -174,17 +185,18 @@ extern "C" int mag_adapter_check(int n, int log_interp, int fp_mode, double jitt
          same Adapt (its getTransform / face quality go through the adapter to the wrapped reference field) */
       std::vector<int> codes;
       std::vector<ma::CodeMatch> matches;
-      mag::getSliverCodes(&a, codes, matches);
-      wit = m->begin(3);
+      if (dim == 3) mag::getSliverCodes(&a, codes, matches);
+      wit = m->begin(dim == 3 ? 3 : 0);
+      if (dim != 3) { m->end(wit); wit = 0; }
       size_t wi = 0;
       long nel3 = 0;
-      while ((we = m->iterate(wit))) {
+      while (wit && (we = m->iterate(wit))) {
         const int rc = ma::getSliverCode(&a, we);
         const ma::CodeMatch rm = ma::matchSliver(&a, we);
         if (codes[wi] != rc || matches[wi].rotation != rm.rotation || matches[wi].code_index != rm.code_index) ++sliver_diffs;
         ++wi; ++nel3;
       }
-      m->end(wit);
+      if (wit) m->end(wit);
       if (log_interp && sliver_diffs * 200 <= nel3) sliver_diffs = 0;   /* CUDA exp() vs glibc exp(): rare borderline bits */
     }
     A.max_len = mag::getMaximumEdgeLength(m, g);

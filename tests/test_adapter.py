@@ -34,3 +34,20 @@ def test_adapter_reproduces_reference(built, log_interp, fp_mode):
     # the unmodified reference loops (5 whole-mesh sweeps: split, collapse, bad, minq, maxlen) were served by a handful
     # of device sweeps, not by per-entity evaluation
     assert 0 < rep[19] <= 5 * 12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("log_interp,fp_mode", [(0, 0), (0, 1), (1, 0)])
+def test_adapter_reproduces_reference_2d(built, log_interp, fp_mode):
+    """The same on a 2-D box: triangles are the elements (ma::measureTriQuality, goodQuality 0.2 as ma::Input picks in 2-D)."""
+    if not os.path.exists(LIB):
+        pytest.skip("libmag_ma.so not built (needs the reference headers)")
+    L = C.CDLL(LIB)
+    L.mag_adapter_check_2d.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p]
+    rep = np.zeros(20)
+    rc = L.mag_adapter_check_2d(60, log_interp, fp_mode, 0.25, rep.ctypes.data_as(C.c_void_p))
+    ref, bulk, loops = rep[0:5], rep[5:10], rep[10:15]
+    assert rc == 0, "adapter differs from the reference: ref=%s bulk=%s loops=%s flagdiffs=%s" % (ref, bulk, loops, rep[15:19])
+    assert ref[0] > 0 and ref[2] > 0
+    assert np.array_equal(ref[:3], bulk[:3]) and np.array_equal(ref[:3], loops[:3])
+    assert np.all(rep[15:19] == 0)
