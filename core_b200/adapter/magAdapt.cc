@@ -165,6 +165,22 @@ struct Access {
     MAG_DO(c, mag_synchronize(c));
   }
 
+  /* the export of the mesh as it is now, on the host (entity lists) and on the device: reused while topoValid holds */
+  static Export& ensureExported(GpuSizeField* g)
+  {
+    ma::Mesh* m = g->mesh;
+    const int dim = m->getDimension();
+    if (g->exported && g->topoValid && g->exported->edges.size() == m->count(1) && g->exported->elems.size() == m->count(dim) &&
+        g->exported->xyz.size() == 3 * m->count(0))
+      return *g->exported;
+    if (!g->exported) g->exported = new Export;
+    *g->exported = Export();
+    exportMesh(g, *g->exported);
+    upload(g, *g->exported);
+    g->topoValid = true;
+    return *g->exported;
+  }
+
   static int readFlags(ma::Mesh* m, ma::Tag* tag, ma::Entity* e)
   {
     /* ma::getFlags (maAdapt.cc:80-88): 0 when the entity has no tag */
@@ -177,29 +193,31 @@ struct Access {
   /* one device sweep with the incoming "ma_flags" words of the Adapt; writes the changed words back.  Returns stats. */
   static mag_stats sweepWithAdaptFlags(GpuSizeField* g, ma::Adapt* a, unsigned ops)
   {
-    Export x;
-    exportMesh(g, x);
-    upload(g, x);
+    Export& x = ensureExported(g);
     ma::Mesh* m = g->mesh;
-    std::vector<int> ef(x.edges.size()), lf(x.elems.size());
-    for (size_t i = 0; i < x.edges.size(); ++i) ef[i] = readFlags(m, a->flagsTag, x.edges[i]);
-    for (size_t i = 0; i < x.elems.size(); ++i) lf[i] = readFlags(m, a->flagsTag, x.elems[i]);
+    /* only the dimension the sweep works on has its flag words read, sent and written back */
+    const bool on_edges = ops & (MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE), on_elems = ops & MAG_OP_MARK_BAD;
+    std::vector<int> ef(on_edges ? x.edges.size() : 0), lf(on_elems ? x.elems.size() : 0);
+    for (size_t i = 0; i < ef.size(); ++i) ef[i] = readFlags(m, a->flagsTag, x.edges[i]);
+    for (size_t i = 0; i < lf.size(); ++i) lf[i] = readFlags(m, a->flagsTag, x.elems[i]);
     mag_ctx* c = g->ctx;
-    MAG_DO(c, mag_set_flags(c, ef.data(), lf.data()));
+    MAG_DO(c, mag_set_flags(c, on_edges ? ef.data() : 0, on_elems ? lf.data() : 0));
     MAG_DO(c, mag_sweep(c, ops, ma::MAXLENGTH, ma::MINLENGTH, a->input->goodQuality, 1, g->fpMode));
     mag_stats st;
     MAG_DO(c, mag_get_stats(c, &st)); /* MAG_ERR_FLAG_STATE here == the reference's assert at maAdapt.cc:308 */
-    std::vector<int> ef2(ef.size()), lf2(lf.size());
-    MAG_DO(c, mag_get_flags(c, ef2.data(), lf2.data()));
-    for (size_t i = 0; i < ef.size(); ++i) if (ef2[i] != ef[i]) ma::setFlags(a, x.edges[i], ef2[i]);
-    for (size_t i = 0; i < lf.size(); ++i) if (lf2[i] != lf[i]) ma::setFlags(a, x.elems[i], lf2[i]);
+    if (on_edges || on_elems) {
+      std::vector<int> ef2(ef.size()), lf2(lf.size());
+      MAG_DO(c, mag_get_flags(c, on_edges ? ef2.data() : 0, on_elems ? lf2.data() : 0));
+      for (size_t i = 0; i < ef.size(); ++i) if (ef2[i] != ef[i]) ma::setFlags(a, x.edges[i], ef2[i]);
+      for (size_t i = 0; i < lf.size(); ++i) if (lf2[i] != lf[i]) ma::setFlags(a, x.elems[i], lf2[i]);
+    }
     g->dirty = true; /* the per-entity snapshot (zero incoming flags) was not refreshed by this sweep */
     return st;
   }
 };
 
 GpuSizeField::GpuSizeField()
-  : mesh(0), wrapped(0), ctx(0), kind(0), logVariant(0), fpMode(MAG_FP_STRICT), dirty(true), streak(0), lastGoodQuality(-1),
+  : mesh(0), wrapped(0), ctx(0), kind(0), logVariant(0), fpMode(MAG_FP_STRICT), dirty(true), topoValid(false), exported(0), streak(0), lastGoodQuality(-1),
     fSizes(0), fFrames(0), fIso(0), fnAniso(0), fnIso(0), nNonSimplex(0), lastDim(-1), lastId(-1)
 {
 }
@@ -207,6 +225,7 @@ GpuSizeField::GpuSizeField()
 GpuSizeField::~GpuSizeField()
 {
   if (ctx) mag_destroy(ctx);
+  delete exported;
   delete wrapped; /* like the reference: an AnisoSizeField destroys the fields it was built from (maSize.cc:385-389) */
 }
 
@@ -228,7 +247,7 @@ bool GpuSizeField::serve(ma::Entity* e, int dim, int& slot)
   const bool in_order = (dim == lastDim && id > lastId);
   lastDim = dim;
   lastId = id;
-  if (!in_order) { dirty = true; streak = 0; return false; }
+  if (!in_order) { dirty = true; streak = 0; topoValid = false; return false; }
   if (!dirty && ((long)mesh->count(1) != (long)lengths.size() || (long)mesh->count(mesh->getDimension()) != (long)qualities.size())) dirty = true;
   if (dirty) {
     if (++streak < kSweepDetect) return false;
@@ -242,9 +261,7 @@ bool GpuSizeField::serve(ma::Entity* e, int dim, int& slot)
 
 void GpuSizeField::refresh(double goodQuality)
 {
-  Export x;
-  Access::exportMesh(this, x);
-  Access::upload(this, x);
+  Export& x = Access::ensureExported(this);
   mag_ctx* c = ctx;
   MAG_DO(c, mag_set_flags(c, 0, 0));
   unsigned ops = MAG_OP_LENGTHS | MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE | MAG_OP_QUALITIES;
@@ -285,27 +302,27 @@ bool GpuSizeField::shouldCollapse(ma::Entity* edge)
 /* everything below is a mesh-modification-time call: the snapshot is no longer trusted afterwards */
 void GpuSizeField::interpolate(apf::MeshElement* parent, ma::Vector const& xi, ma::Entity* newVert)
 {
-  dirty = true; streak = 0;
+  dirty = true; streak = 0; topoValid = false;
   wrapped->interpolate(parent, xi, newVert);
 }
 void GpuSizeField::getTransform(apf::MeshElement* e, ma::Vector const& xi, ma::Matrix& t)
 {
-  dirty = true; streak = 0;
+  dirty = true; streak = 0; topoValid = false;
   wrapped->getTransform(e, xi, t);
 }
 double GpuSizeField::getWeight(ma::Entity* e)
 {
-  dirty = true; streak = 0;
+  dirty = true; streak = 0; topoValid = false;
   return wrapped->getWeight(e);
 }
 void GpuSizeField::onRefine(ma::Entity* parent, ma::EntityArray& newEntities)
 {
-  dirty = true; streak = 0;
+  dirty = true; streak = 0; topoValid = false;
   wrapped->onRefine(parent, newEntities);
 }
 void GpuSizeField::onCavity(ma::EntityArray& oldElements, ma::EntityArray& newEntities)
 {
-  dirty = true; streak = 0;
+  dirty = true; streak = 0; topoValid = false;
   wrapped->onCavity(oldElements, newEntities);
 }
 int GpuSizeField::getTransferDimension() { return wrapped->getTransferDimension(); }

@@ -35,6 +35,8 @@ namespace ma { class Adapt; class ShapeHandler; }
 
 namespace mag {
 
+struct Export;   /* the arrays of one MDS export (magAdapt.cc) */
+
 class GpuSizeField : public ma::SizeField
 {
   public:
@@ -52,7 +54,7 @@ class GpuSizeField : public ma::SizeField
     bool hasNodesOn(int dimension);
 
     /* the mesh or the field changed behind our back (e.g. coordinates moved by the caller) */
-    void invalidate() { dirty = true; }
+    void invalidate() { dirty = true; topoValid = false; }
     /* MAG_FP_STRICT (default) or MAG_FP_FAST, see include/mag.h */
     void setArithmetic(int fp_mode) { fpMode = fp_mode; invalidate(); }
     /* re-export the mesh + field and run one full device sweep now */
@@ -70,6 +72,12 @@ class GpuSizeField : public ma::SizeField
     int logVariant;  /* 0 fields (maSize.cc:491-499), 1 user function (maSize.cc:343-346) */
     int fpMode;
     bool dirty;
+    /* the device holds the export of the mesh as it is now: set by an export, cleared by every callback a mesh-modifying
+       operator makes (interpolate / getTransform / getWeight / onRefine / onCavity), by any out-of-order per-entity query,
+       by a change of the entity counts and by invalidate().  While it holds, consecutive bulk sweeps (split, collapse, bad
+       quality ... of one MeshAdapt iteration) share ONE export instead of walking MDS again. */
+    bool topoValid;
+    Export* exported;
     long streak;     /* consecutive per-entity sweep-like queries since the last mesh change */
     double lastGoodQuality;
     apf::Field* fSizes; apf::Field* fFrames; apf::Field* fIso;

@@ -1,8 +1,18 @@
+"""The C++ adapter against the unmodified reference in one process on the GPU box (libmag_ma.so is prebuilt where the
+reference tree exists): parity report and wall-clock of the five whole-mesh sweeps (split, collapse, bad quality, min quality,
+max length) done by the reference alone, by the adapter's bulk entry points (MDS export + upload + device sweep + flag
+write-back, five times) and by the unmodified reference loops with the adapter plugged into ma::Input.
+usage: adapter_run.py [cells per side, default 16]"""
 import ctypes as C, numpy as np, sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-L = C.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "core_b200/lib/libmag_ma.so"))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+L = C.CDLL(os.path.join(ROOT, "core_b200/lib/libmag_ma.so"))
 L.mag_adapter_check.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p]
+L.mag_adapter_times.argtypes = [C.c_void_p]
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 for log_interp, fp in ((0, 0), (0, 1), (1, 0), (1, 1)):
-    rep = np.zeros(20)
-    rc = L.mag_adapter_check(int(sys.argv[1]) if len(sys.argv) > 1 else 16, log_interp, fp, 0.25, rep.ctypes.data_as(C.c_void_p))
-    print("log=%d fp=%d rc=%d" % (log_interp, fp, rc), rep.tolist(), flush=True)
+    rep, t = np.zeros(20), np.zeros(3)
+    rc = L.mag_adapter_check(n, log_interp, fp, 0.25, rep.ctypes.data_as(C.c_void_p))
+    L.mag_adapter_times(t.ctypes.data_as(C.c_void_p))
+    print("n=%d log=%d fp=%d rc=%d counts=%s  reference %.3f s | adapter bulk %.3f s (%.1fx) | reference loops over the adapter %.3f s (%.1fx)"
+          % (n, log_interp, fp, rc, rep[:3].astype(np.int64).tolist(), t[0], t[1], t[0] / t[1], t[2], t[0] / t[2]), flush=True)

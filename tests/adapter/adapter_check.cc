@@ -23,6 +23,7 @@
 #include <PCU.h>
 #include <cmath>
 #include <vector>
+#include <chrono>
 
 namespace ma {
 /* external linkage, no header in the reference (maCoarsen.cc:287, maShape.cc:132,152) */
@@ -47,6 +48,12 @@ void ensure_pcu()
   gmi_register_null();
   gmi_register_mesh();
 }
+
+/* wall-clock seconds of the last check: [0] the reference's five sweeps (split, collapse, bad, min quality, max length),
+   [1] the adapter's bulk entry points for the same five (each one exports the mesh from MDS, uploads, sweeps, writes the
+   flag words back), [2] the unmodified reference loops served through the adapter */
+double g_times[3] = {0, 0, 0};
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 struct Fields { apf::Field* sizes; apf::Field* frames; };
 
@@ -104,6 +111,7 @@ long diff(const std::vector<int>& a, const std::vector<int>& b)
    report[15..18] flag words differing: A edges, A elems, B edges, B elems;  report[19] sweeps the adapter ran for B
    returns 0 when A and B reproduce the reference exactly (fp_mode strict) / flags+counts exactly, values 1e-12 (fast). */
 static int adapter_check(int n, int nz, int log_interp, int fp_mode, double jitter, double* report);
+extern "C" void mag_adapter_times(double* t) { for (int i = 0; i < 3; ++i) t[i] = g_times[i]; }
 extern "C" int mag_adapter_check(int n, int log_interp, int fp_mode, double jitter, double* report)
 {
   return adapter_check(n, n, log_interp, fp_mode, jitter, report);
@@ -143,13 +151,15 @@ static int adapter_check(int n, int nz, int log_interp, int fp_mode, double jitt
     ma::Input* in = ma::makeAdvanced(ma::configureIdentity(m, sf));
     {
       ma::Adapt a(in);
+      const double t0 = now_s();
       R.n_split = ma::markEdgesToSplit(&a);
       R.n_collapse = ma::markEdgesToCollapse(&a);
       R.n_bad = ma::markBadQuality(&a);
       R.min_q = ma::getMinQuality(&a);
+      g_times[0] = now_s() - t0;
       collect_flags(&a, R);
     }
-    R.max_len = ma::getMaximumEdgeLength(m, sf);
+    { const double t0 = now_s(); R.max_len = ma::getMaximumEdgeLength(m, sf); g_times[0] += now_s() - t0; }
     delete in;
     delete sf; /* destroys (Aniso) or leaves (LogAniso) the input fields */
     if (log_interp) { apf::destroyField(f.sizes); apf::destroyField(f.frames); }
@@ -162,10 +172,12 @@ static int adapter_check(int n, int nz, int log_interp, int fp_mode, double jitt
     in->shapeHandler = mag::shapeHandler;
     {
       ma::Adapt a(in);
+      const double t0 = now_s();
       A.n_split = mag::markEdgesToSplit(&a);
       A.n_collapse = mag::markEdgesToCollapse(&a);
       A.n_bad = mag::markBadQuality(&a);
       A.min_q = mag::getMinQuality(&a);
+      g_times[1] = now_s() - t0;
       collect_flags(&a, A);
       /* ma::getElementWeights (maBalance.cc:83-97) against the reference's own per-entity loop on the same Adapt */
       a.refinesLeft = 0; a.coarsensLeft = 1;
@@ -199,7 +211,7 @@ static int adapter_check(int n, int nz, int log_interp, int fp_mode, double jitt
       if (wit) m->end(wit);
       if (log_interp && sliver_diffs * 200 <= nel3) sliver_diffs = 0;   /* CUDA exp() vs glibc exp(): rare borderline bits */
     }
-    A.max_len = mag::getMaximumEdgeLength(m, g);
+    { const double t0 = now_s(); A.max_len = mag::getMaximumEdgeLength(m, g); g_times[1] += now_s() - t0; }
     delete in;
   }
   long sweeps0 = mag_launch_count(g->ctx);
@@ -208,13 +220,15 @@ static int adapter_check(int n, int nz, int log_interp, int fp_mode, double jitt
     in->shapeHandler = mag::shapeHandler;
     {
       ma::Adapt a(in);
+      const double t0 = now_s();
       B.n_split = ma::markEdgesToSplit(&a);
       B.n_collapse = ma::markEdgesToCollapse(&a);
       B.n_bad = ma::markBadQuality(&a);
       B.min_q = ma::getMinQuality(&a);
+      g_times[2] = now_s() - t0;
       collect_flags(&a, B);
     }
-    B.max_len = ma::getMaximumEdgeLength(m, g);
+    { const double t0 = now_s(); B.max_len = ma::getMaximumEdgeLength(m, g); g_times[2] += now_s() - t0; }
     delete in;
   }
   report[19] = (double)(mag_launch_count(g->ctx) - sweeps0);
