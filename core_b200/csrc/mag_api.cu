@@ -11,6 +11,9 @@ int magk_init_stats(mag_ctx* c);
 int magk_vertex_pass(mag_ctx* c);
 int magk_build_schedule(mag_ctx* c);
 int magk_fold_owned(mag_ctx* c);
+int magk_check_conn(mag_ctx* c, int32_t* d_conn, int64_t n);
+int magk_conn_begin(mag_ctx* c);
+int magk_conn_result(mag_ctx* c, unsigned long long* bad);
 int magk_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double good_q, int use_max, int fp_mode);
 double magk_key_to_double(unsigned long long k);
 void magc_destroy(mag_ctx* c);
@@ -103,6 +106,8 @@ int mag_stats_from_dev(mag_ctx* c, const MagDevStats& s, mag_stats* out)
   out->min_quality = magk_key_to_double(s.min_q_key);
   memcpy(&out->max_length, &s.max_len_bits, 8);
   out->sum_length = s.sum_len;
+  if (s.n_bad_conn)
+    return mag_fail(c, MAG_ERR_ARG, "%llu vertex ids of the connectivity lie outside [0, nv); the results of this call are void", s.n_bad_conn);
   if (s.n_flag_err)
     return mag_fail(c, MAG_ERR_FLAG_STATE, "%llu entities already carried the flag being marked (ma::markEntities asserts, maAdapt.cc:308)", s.n_flag_err);
   if (s.n_eigen_fail)
@@ -263,6 +268,7 @@ static int set_mesh_impl(mag_ctx* c, int dim, int64_t nv, const double* xyz, int
   CHECK_CTX(c);
   if ((nv > 0 && !xyz) || (ne > 0 && !edge_v) || (nt > 0 && !tet_v) || (np > 0 && !prism_v) || (npy > 0 && !pyr_v) || (ntri > 0 && !tri_v))
     return mag_fail(c, MAG_ERR_ARG, "mag_set_mesh: null array with non-zero count");
+  if (nv == 0 && (ne > 0 || nt > 0 || np > 0 || npy > 0 || ntri > 0)) return mag_fail(c, MAG_ERR_ARG, "mag_set_mesh: entities without vertices");
   int rc;
   if ((rc = magi_reshape(c, dim, nv, ne, nt, np, npy, ntri, edge_owned != nullptr, elem_owned != nullptr))) return rc;
   const int64_t nel = np + npy + nt + ntri;
@@ -274,6 +280,17 @@ static int set_mesh_impl(mag_ctx* c, int dim, int64_t nv, const double* xyz, int
     return rc;
   if (edge_owned && (rc = upload(c, c->d_edge_owned, edge_owned, (size_t)ne))) return rc;
   if (elem_owned && (rc = upload(c, c->d_elem_owned, elem_owned, (size_t)nel))) return rc;
+  // every vertex id must address a vertex: checked on the device before anything gathers through it
+  unsigned long long bad = 0;
+  if ((rc = magk_conn_begin(c)) || (rc = magk_check_conn(c, c->d_edge_v, ne * 2)) || (rc = magk_check_conn(c, c->d_tet_v, nt * 4)) ||
+      (rc = magk_check_conn(c, c->d_prism_v, np * 6)) || (rc = magk_check_conn(c, c->d_pyr_v, npy * 5)) ||
+      (rc = magk_check_conn(c, c->d_tri_v, ntri * 3)) || (rc = magk_conn_result(c, &bad)))
+    return rc;
+  if (bad) {
+    c->nv = c->ne = c->nt = c->np = c->npy = c->ntri = 0;   // the part is unusable: leave the context empty
+    c->kind = MAG_KIND_NONE;
+    return mag_fail(c, MAG_ERR_ARG, "mag_set_mesh: %llu vertex ids outside [0, %lld)", bad, (long long)nv);
+  }
   if ((rc = magk_fold_owned(c)) || (rc = magk_build_schedule(c))) return rc;
   c->schedule_valid = true;
   return repack(c);

@@ -20,6 +20,7 @@ int magk_vertex_pass(mag_ctx* c);
 int magk_edges_range(mag_ctx* c, uint32_t ops, double max_len, double min_len, int fp_mode, int64_t first, int64_t n);
 int magk_tets_range(mag_ctx* c, uint32_t ops, double good_q, int use_max, int fp_mode, int64_t first, int64_t n);
 int magk_length_sum(mag_ctx* c);
+int magk_check_conn(mag_ctx* c, int32_t* d_conn, int64_t n);
 
 namespace {
 
@@ -72,6 +73,7 @@ extern "C" int mag_sweep_host(mag_ctx* c, const mag_host_part* in, const mag_hos
   const int64_t nv = in->nv, ne = in->ne, nt = in->nt;
   if ((nv > 0 && !in->xyz) || (ne > 0 && !in->edge_v) || (nt > 0 && !in->tet_v))
     return mag_fail(c, MAG_ERR_ARG, "mag_sweep_host: null array with non-zero count");
+  if (nv == 0 && (ne > 0 || nt > 0)) return mag_fail(c, MAG_ERR_ARG, "mag_sweep_host: entities without vertices");
   size_t na = 0, nb = 0;
   switch (in->kind) {
     case MAG_KIND_IDENTITY: break;
@@ -122,6 +124,7 @@ extern "C" int mag_sweep_host(mag_ctx* c, const mag_host_part* in, const mag_hos
     if (in->edge_owned && (rc = copy_async(c, c->d_edge_owned + e0, in->edge_owned + e0, (size_t)n, cudaMemcpyHostToDevice, s_up))) return rc;
     if ((rc = chain(c, ev, s_up, s_cmp))) return rc;
     if (!in->edge_flags) MAG_CUDA(c, cudaMemsetAsync(c->d_edge_flags + e0, 0, (size_t)n * 4, s_cmp));
+    if ((rc = magk_check_conn(c, c->d_edge_v + 2 * e0, 2 * n))) return rc;   // out-of-range ids: counted, made harmless, reported with the statistics
     if ((rc = magk_edges_range(c, ops, max_len, min_len, fp_mode, e0, n))) return rc;
     if ((rc = chain(c, ev, s_cmp, s_down))) return rc;
     if (out->edge_lengths && (ops & MAG_OP_LENGTHS) &&
@@ -139,6 +142,7 @@ extern "C" int mag_sweep_host(mag_ctx* c, const mag_host_part* in, const mag_hos
     if (in->elem_owned && (rc = copy_async(c, c->d_elem_owned + t0, in->elem_owned + t0, (size_t)n, cudaMemcpyHostToDevice, s_up))) return rc;
     if ((rc = chain(c, ev, s_up, s_cmp))) return rc;
     if (!in->elem_flags) MAG_CUDA(c, cudaMemsetAsync(c->d_elem_flags + t0, 0, (size_t)n * 4, s_cmp));
+    if ((rc = magk_check_conn(c, c->d_tet_v + 4 * t0, 4 * n))) return rc;
     if ((rc = magk_tets_range(c, ops, good_quality, use_max_metric, fp_mode, t0, n))) return rc;
     if ((rc = chain(c, ev, s_cmp, s_down))) return rc;
     if (out->qualities && (ops & MAG_OP_QUALITIES) &&

@@ -16,6 +16,7 @@ struct MagDevStats {
   unsigned long long n_layer_unsafe;
   unsigned long long n_flag_err, n_eigen_fail, n_nonsimplex;
   unsigned long long n_flag_mismatch;
+  unsigned long long n_bad_conn;   // vertex ids outside [0, nv) met by the export-time check (and replaced by 0)
   unsigned long long edge_chunk, elem_chunk; // work-distribution counters of the persistent kernels
   unsigned long long max_len_bits; // bits of a non-negative double: integer order == fp order
   unsigned long long min_q_key;    // order-preserving key of a double (see dkey())

@@ -499,6 +499,21 @@ def test_edge_cases_and_errors(cb):
     with pytest.raises(cb.MagError) as ei:
         p.sweep()
     assert ei.value.code == 2
+    # a vertex id outside [0, nv): rejected at export (device-side check), the context stays usable
+    with pytest.raises(cb.MagError) as ei:
+        p.set_mesh(np.zeros((3, 3)), np.array([[0, 1], [1, 3]], np.int32))
+    assert ei.value.code == 2 and "vertex ids" in str(ei.value)
+    with pytest.raises(cb.MagError):
+        p.set_mesh(np.zeros((4, 3)), np.array([[0, 1]], np.int32), np.array([[0, 1, 2, -1]], np.int32))
+    with pytest.raises(cb.MagError):
+        p.set_mesh(np.zeros((0, 3)), np.array([[0, 1]], np.int32))
+    # ... and in the streamed one-call path (the ids are made harmless on the device, the call reports MAG_ERR_ARG)
+    xb, eb, tb = cb.boxmesh.kuhn_box(2, 2, 2)
+    tb_bad = tb.copy()
+    tb_bad[5, 2] = len(xb)
+    with pytest.raises(cb.MagError) as ei:
+        p.sweep_host(xb, eb, tb_bad, 1, cb.fields.iso_linear(xb, 0.5), None, out_lengths=np.empty(len(eb)), out_qualities=np.empty(len(tb)))
+    assert ei.value.code == 2
     # empty mesh: every count zero, statistics at their initial values (getMinQuality 1, getMaximumEdgeLength 0)
     p.set_mesh(np.zeros((0, 3)), np.zeros((0, 2), np.int32), np.zeros((0, 4), np.int32))
     p.set_size_field_identity()
