@@ -157,6 +157,13 @@ int mag_set_edge_links(mag_ctx* c, int npeers, const int32_t* peer, const int64_
   if (!c) return MAG_ERR_ARG;
   MAG_CUDA(c, cudaSetDevice(c->device));
   if (npeers < 0 || (npeers && (!peer || !n || !idx))) return mag_fail(c, MAG_ERR_ARG, "mag_set_edge_links: bad arguments");
+  for (int k = 0; k < npeers; ++k) {   // the lists are boundary-sized: checked on the host
+    if (n[k] < 0 || (n[k] && !idx[k])) return mag_fail(c, MAG_ERR_ARG, "mag_set_edge_links: bad list for peer %d", peer[k]);
+    for (int64_t i = 0; i < n[k]; ++i)
+      if (idx[k][i] < 0 || idx[k][i] >= c->ne)
+        return mag_fail(c, MAG_ERR_ARG, "mag_set_edge_links: edge index %d (peer %d, entry %lld) outside [0, %lld)", idx[k][i], peer[k],
+                        (long long)i, (long long)c->ne);
+  }
   free_links(c);
   for (int k = 0; k < npeers; ++k) {
     MagLinks L;

@@ -34,6 +34,11 @@ def main():
     uid = [cb.Part.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     p.comm_init(world, rank, uid[0])
+    try:   # an index past the part's edges is refused on the host
+        p.set_edge_links([(1 - rank, np.array([len(part["edge_v"])], np.int32), None)])
+        raise AssertionError("out-of-range link index accepted")
+    except cb.MagError as e:
+        assert e.code == 2
     p.set_edge_links(part["links"])
     mask = cb.SPLIT | cb.COLLAPSE | cb.NEED_NOT_SPLIT | cb.NEED_NOT_COLLAPSE
     # 1. consistent copies, global statistics
