@@ -514,6 +514,14 @@ def test_edge_cases_and_errors(cb):
     with pytest.raises(cb.MagError) as ei:
         p.sweep_host(xb, eb, tb_bad, 1, cb.fields.iso_linear(xb, 0.5), None, out_lengths=np.empty(len(eb)), out_qualities=np.empty(len(tb)))
     assert ei.value.code == 2
+    # maximum sizes: entity ids are int32 (MDS_ID_TYPE = int); a count the kernels could not index is refused before
+    # anything is allocated or read (the arrays behind these pointers are tiny)
+    import ctypes as C
+    tiny = np.zeros(8, np.int32)
+    for ne_big, nt_big in ((2 ** 31 - 1, 0), (0, 2 ** 31 - 1), (2 ** 33, 0)):
+        rc = p._L.mag_set_mesh(p._h, 4, np.zeros(12).ctypes.data, ne_big, tiny.ctypes.data, nt_big, tiny.ctypes.data, 0, None, 0, None, None, None)
+        assert rc == 2 and b"int32" in p._L.mag_last_error(p._h)
+    assert p._L.mag_set_mesh(p._h, -1, None, 0, None, 0, None, 0, None, 0, None, None, None) == 2
     # empty mesh: every count zero, statistics at their initial values (getMinQuality 1, getMaximumEdgeLength 0)
     p.set_mesh(np.zeros((0, 3)), np.zeros((0, 2), np.int32), np.zeros((0, 4), np.int32))
     p.set_size_field_identity()
@@ -740,6 +748,35 @@ def test_full_size_properties(cb):
     efr, lfr = p.flags()
     assert np.array_equal(efr[::-1], ef0) and np.array_equal(lfr[::-1], lf0)
     assert (st["n_split"], st["n_bad"]) == (s0["n_split"], s0["n_bad"])
+    p.close()
+
+
+def test_full_size_loganiso(cb):
+    """BASELINE config 3, log-Euclidean variant (makeSizeField(m, sizes, frames, true)) at n=203: the fast path (the
+    reference's QR iteration in its second form) against the strict path on every entity -- flags and counts identical,
+    lengths and qualities within 1e-12 -- and against the oracle on a seeded sample."""
+    from oracle import mao
+    n = 203
+    xyz, ev, tv = cb.boxmesh.kuhn_box(n, n, n)
+    xyz = cb.fields.jitter(xyz, 0.2 / n)
+    h, R = cb.fields.shock_rotating(xyz, 1.0 / n)
+    p = cb.Part(0)
+    p.set_mesh(xyz, ev, tv)
+    lm = p.set_size_field_logm_from_frames(h, R, 0, want_logm=True)
+    res = {}
+    for mode in (cb.FP_STRICT, cb.FP_FAST):
+        p.clear_flags()
+        p.sweep(cb.OP_ALL & ~cb.OP_LAYER_CHECK, fp_mode=mode)
+        res[mode] = (p.stats(), p.edge_lengths(), p.qualities(), *p.flags())
+    (s0, L0, q0, ef0, lf0), (s1, L1, q1, ef1, lf1) = res[cb.FP_STRICT], res[cb.FP_FAST]
+    assert np.array_equal(ef0, ef1) and np.array_equal(lf0, lf1)
+    assert all(s0[k] == s1[k] for k in ("n_split", "n_collapse", "n_bad"))
+    assert util.rel_err(L1, L0) < TOL and util.rel_err(q1, q0) < TOL
+    rng = np.random.default_rng(11)
+    se = rng.choice(len(ev), 100000, replace=False)
+    stt = rng.choice(len(tv), 100000, replace=False)
+    assert util.rel_err(L1[se], mao.edge_lengths(mao.LOGM, xyz, None, lm, ev[se])) < TOL
+    assert util.rel_err(q1[stt], mao.tet_qualities(mao.LOGM, xyz, None, lm, tv[stt])) < TOL
     p.close()
 
 
