@@ -7,6 +7,7 @@
 #include <maAdapt.h>
 #include <maShapeHandler.h>
 #include <maShape.h>
+#include <maStats.h>
 #include <apfMDS.h>
 #include <apfMesh2.h>
 #include <apfShape.h>
@@ -429,6 +430,28 @@ void getLinearQualitiesInMetricSpace(ma::Mesh* m, ma::SizeField* sf, std::vector
     const double lq = Access::qualityOf(g, e);
     out.push_back(dim == 2 ? ((lq > 0) ? sqrt(lq) : -sqrt(-lq)) : cbrt(lq));   /* maStats.cc:24-28 */
   }
+  m->end(it);
+}
+
+void stats(ma::Mesh* m, ma::SizeField* sf, std::vector<double>& edgeLengths, std::vector<double>& linearQualities, bool inMetric)
+{
+  edgeLengths.clear();
+  linearQualities.clear();
+  if (!inMetric) { ma::stats(m, sf, edgeLengths, linearQualities, false); return; }
+  GpuSizeField* g = gpuField(sf);
+  g->refresh(-1);                                   /* one export + one sweep serve both vectors */
+  const int dim = m->getDimension();
+  apf::MeshIterator* it = m->begin(dim);            /* qualities first, as getStatsInMetricSpace does (maStats.cc:95-103) */
+  ma::Entity* e;
+  while ((e = m->iterate(it))) {
+    if (m->getType(e) != (dim == 3 ? apf::Mesh::TET : apf::Mesh::TRIANGLE) || !m->isOwned(e)) continue;
+    const double lq = Access::qualityOf(g, e);
+    linearQualities.push_back(dim == 2 ? ((lq > 0) ? sqrt(lq) : -sqrt(-lq)) : cbrt(lq));
+  }
+  m->end(it);
+  it = m->begin(1);
+  size_t k = 0;
+  while ((e = m->iterate(it))) { if (m->isOwned(e)) edgeLengths.push_back(Access::lengthAt(g, k)); ++k; }
   m->end(it);
 }
 

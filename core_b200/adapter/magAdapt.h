@@ -105,6 +105,9 @@ double getMinQuality(ma::Adapt* a);
 double getMaximumEdgeLength(ma::Mesh* m, ma::SizeField* sf);
 void getEdgeLengthsInMetricSpace(ma::Mesh* m, ma::SizeField* sf, std::vector<double>& lengths);
 void getLinearQualitiesInMetricSpace(ma::Mesh* m, ma::SizeField* sf, std::vector<double>& qualities);
+/* ma::stats (ma/maStats.cc:115-134): both vectors from ONE device sweep when inMetric, the reference's own physical-space
+   loops otherwise */
+void stats(ma::Mesh* m, ma::SizeField* sf, std::vector<double>& edgeLengths, std::vector<double>& linearQualities, bool inMetric);
 
 /* ma::getElementWeights (ma/maBalance.cc:83-97): creates and fills the "ma_weight" element tag; the caller destroys it */
 ma::Tag* getElementWeights(ma::Adapt* a);

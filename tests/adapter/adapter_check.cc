@@ -13,6 +13,7 @@
 #include <maAdapt.h>
 #include <maRefine.h>
 #include <maShape.h>
+#include <maStats.h>
 #include <apfMDS.h>
 #include <apfBox.h>
 #include <apfMesh2.h>
@@ -144,7 +145,8 @@ static int adapter_check(int n, int nz, int log_interp, int fp_mode, double jitt
   }
   const double hbar = 1.0 / n;
   Marks R, A, B;
-  long weight_diffs = 0, sliver_diffs = 0;
+  long weight_diffs = 0, sliver_diffs = 0, stats_diffs = 0;
+  std::vector<double> ref_el, ref_lq;
   { /* (R) the unmodified reference */
     Fields f = make_fields(m, "ref", hbar);
     ma::SizeField* sf = ma::makeSizeField(m, f.sizes, f.frames, log_interp != 0);
@@ -160,6 +162,7 @@ static int adapter_check(int n, int nz, int log_interp, int fp_mode, double jitt
       collect_flags(&a, R);
     }
     { const double t0 = now_s(); R.max_len = ma::getMaximumEdgeLength(m, sf); g_times[0] += now_s() - t0; }
+    ma::stats(m, sf, ref_el, ref_lq, true);
     delete in;
     delete sf; /* destroys (Aniso) or leaves (LogAniso) the input fields */
     if (log_interp) { apf::destroyField(f.sizes); apf::destroyField(f.frames); }
@@ -212,6 +215,16 @@ static int adapter_check(int n, int nz, int log_interp, int fp_mode, double jitt
       if (log_interp && sliver_diffs * 200 <= nel3) sliver_diffs = 0;   /* CUDA exp() vs glibc exp(): rare borderline bits */
     }
     { const double t0 = now_s(); A.max_len = mag::getMaximumEdgeLength(m, g); g_times[1] += now_s() - t0; }
+    { /* ma::stats through the adapter against the reference's vectors */
+      std::vector<double> el, lq;
+      mag::stats(m, g, el, lq, true);
+      const double tol = (fp_mode == MAG_FP_STRICT && !log_interp) ? 0.0 : 1e-12;
+      if (el.size() != ref_el.size() || lq.size() != ref_lq.size()) stats_diffs = -1;
+      else {
+        for (size_t i = 0; i < el.size(); ++i) if (fabs(el[i] - ref_el[i]) > tol * fabs(ref_el[i])) ++stats_diffs;
+        for (size_t i = 0; i < lq.size(); ++i) if (fabs(lq[i] - ref_lq[i]) > tol * fabs(ref_lq[i])) ++stats_diffs;
+      }
+    }
     delete in;
   }
   long sweeps0 = mag_launch_count(g->ctx);
@@ -252,5 +265,6 @@ static int adapter_check(int n, int nz, int log_interp, int fp_mode, double jitt
   for (int i = 15; i < 19; ++i) bad |= report[i] != 0;
   bad |= weight_diffs != 0;
   bad |= sliver_diffs != 0;
+  bad |= stats_diffs != 0;
   return bad;
 }
