@@ -10,6 +10,7 @@
 //   ma::getMinQuality(Adapt*)         ma/maShape.cc:152     ->  mag::getMinQuality(Adapt*)
 //   ma::getMaximumEdgeLength(m, sf)   ma/maSize.cc:673      ->  mag::getMaximumEdgeLength(m, sf)
 //   ma::getEdgeLengthsInMetricSpace / getLinearQualitiesInMetricSpace   ma/maStats.cc:12-45  ->  mag::... (same vectors)
+//   ma::stats(m, sf, el, lq, inMetric)  ma/maStats.cc:115-134  ->  mag::stats (both vectors from one sweep)
 //   ma::getElementWeights(Adapt*)     ma/maBalance.cc:83    ->  mag::getElementWeights(Adapt*)  (same "ma_weight" tag)
 //   ma::getSliverCode / matchSliver   ma/maShape.cc:35-120  ->  mag::getSliverCodes(Adapt*, ...)  (every tet in one sweep)
 //   ma::getShapeHandler(Adapt*)       ma/maShapeHandler.cc  ->  mag::shapeHandler  (an ma::ShapeHandlerFunction for Input::shapeHandler)
