@@ -16,6 +16,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
+#include <thread>
+#include <functional>
 
 namespace ma {
 /* external linkage in the reference, declared in no installed header (maBalance.cc:74-81) */
@@ -30,6 +32,20 @@ static void fail(mag_ctx* c, const char* what, int rc)
   abort(); /* the reference's convention: PCU_ALWAYS_ASSERT -> abort (pcu_util.h:44-69) */
 }
 #define MAG_DO(c, call) do { int rc_ = (call); if (rc_) fail((c), #call, rc_); } while (0)
+
+/* static chunks of [0, n) over nthreads host threads (the calling thread takes the first chunk) */
+static void parallelFor(size_t n, int nthreads, const std::function<void(size_t, size_t)>& body)
+{
+  if (nthreads <= 1 || n < 4096) { body(0, n); return; }
+  std::vector<std::thread> pool;
+  const size_t per = (n + (size_t)nthreads - 1) / (size_t)nthreads;
+  for (int t = 1; t < nthreads; ++t) {
+    const size_t b = per * (size_t)t, e = b + per < n ? b + per : n;
+    if (b < e) pool.push_back(std::thread(body, b, e));
+  }
+  body(0, per < n ? per : n);
+  for (size_t i = 0; i < pool.size(); ++i) pool[i].join();
+}
 
 struct Export {
   std::vector<double> xyz, ma, mb;
@@ -100,12 +116,7 @@ struct Access {
     x.edge_v.resize(2 * ne); x.edge_owned.resize(ne); x.edges.resize(ne);
     g->edgeSlot.assign(g->edgeSlot.size(), -1);
     it = m->begin(1); k = 0;
-    while ((e = m->iterate(it))) {
-      apf::Downward dv;
-      m->getDownward(e, 0, dv);
-      x.edge_v[2 * k] = vslot[apf::getMdsIndex(m, dv[0])];
-      x.edge_v[2 * k + 1] = vslot[apf::getMdsIndex(m, dv[1])];
-      x.edge_owned[k] = m->isOwned(e) ? 1 : 0;
+    while ((e = m->iterate(it))) {    /* the iteration itself stays on one thread; the adjacency queries below do not */
       x.edges[k] = e;
       int id = apf::getMdsIndex(m, e);
       if ((size_t)id >= g->edgeSlot.size()) g->edgeSlot.resize((size_t)id + 1 + g->edgeSlot.size() / 2, -1);
@@ -113,6 +124,15 @@ struct Access {
       ++k;
     }
     m->end(it);
+    parallelFor(ne, g->exportThreads, [&](size_t b, size_t en) {
+      for (size_t i = b; i < en; ++i) {
+        apf::Downward dv;
+        m->getDownward(x.edges[i], 0, dv);
+        x.edge_v[2 * i] = vslot[apf::getMdsIndex(m, dv[0])];
+        x.edge_v[2 * i + 1] = vslot[apf::getMdsIndex(m, dv[1])];
+        x.edge_owned[i] = m->isOwned(x.edges[i]) ? 1 : 0;
+      }
+    });
     /* dimension 3 iterates prisms, pyramids, tets (MDS type order, mds.h:16-26); on a 2-D mesh the elements are the
        triangles (ma::measureTriQuality), kept in the same "te" list and slot table */
     std::vector<ma::Entity*> pr, py, te;
@@ -133,11 +153,13 @@ struct Access {
     x.elem_owned.resize(x.elems.size());
     auto conn = [&](std::vector<ma::Entity*>& v, int n, std::vector<int>& out) {
       out.resize(v.size() * n);
-      for (size_t i = 0; i < v.size(); ++i) {
-        apf::Downward dv;
-        m->getDownward(v[i], 0, dv);
-        for (int j = 0; j < n; ++j) out[i * n + j] = vslot[apf::getMdsIndex(m, dv[j])];
-      }
+      parallelFor(v.size(), g->exportThreads, [&](size_t b, size_t en) {
+        for (size_t i = b; i < en; ++i) {
+          apf::Downward dv;
+          m->getDownward(v[i], 0, dv);
+          for (int j = 0; j < n; ++j) out[i * n + j] = vslot[apf::getMdsIndex(m, dv[j])];
+        }
+      });
     };
     conn(pr, 6, x.prism_v); conn(py, 5, x.pyr_v);
     if (mdim == 3) conn(te, 4, x.tet_v); else conn(te, 3, x.tri_v);
@@ -147,7 +169,9 @@ struct Access {
       if ((size_t)id >= g->tetSlot.size()) g->tetSlot.resize((size_t)id + 1 + g->tetSlot.size() / 2, -1);
       g->tetSlot[id] = (int)(g->nNonSimplex + i);
     }
-    for (size_t i = 0; i < x.elems.size(); ++i) x.elem_owned[i] = m->isOwned(x.elems[i]) ? 1 : 0;
+    parallelFor(x.elems.size(), g->exportThreads, [&](size_t b, size_t en) {
+      for (size_t i = b; i < en; ++i) x.elem_owned[i] = m->isOwned(x.elems[i]) ? 1 : 0;
+    });
   }
 
   static void upload(GpuSizeField* g, Export& x)
@@ -199,8 +223,12 @@ struct Access {
     /* only the dimension the sweep works on has its flag words read, sent and written back */
     const bool on_edges = ops & (MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE), on_elems = ops & MAG_OP_MARK_BAD;
     std::vector<int> ef(on_edges ? x.edges.size() : 0), lf(on_elems ? x.elems.size() : 0);
-    for (size_t i = 0; i < ef.size(); ++i) ef[i] = readFlags(m, a->flagsTag, x.edges[i]);
-    for (size_t i = 0; i < lf.size(); ++i) lf[i] = readFlags(m, a->flagsTag, x.elems[i]);
+    parallelFor(ef.size(), g->exportThreads, [&](size_t b, size_t en) {
+      for (size_t i = b; i < en; ++i) ef[i] = readFlags(m, a->flagsTag, x.edges[i]);
+    });
+    parallelFor(lf.size(), g->exportThreads, [&](size_t b, size_t en) {
+      for (size_t i = b; i < en; ++i) lf[i] = readFlags(m, a->flagsTag, x.elems[i]);
+    });
     mag_ctx* c = g->ctx;
     MAG_DO(c, mag_set_flags(c, on_edges ? ef.data() : 0, on_elems ? lf.data() : 0));
     MAG_DO(c, mag_sweep(c, ops, ma::MAXLENGTH, ma::MINLENGTH, a->input->goodQuality, 1, g->fpMode));
@@ -218,7 +246,7 @@ struct Access {
 };
 
 GpuSizeField::GpuSizeField()
-  : mesh(0), wrapped(0), ctx(0), kind(0), logVariant(0), fpMode(MAG_FP_STRICT), dirty(true), topoValid(false), exported(0), streak(0), lastGoodQuality(-1),
+  : mesh(0), wrapped(0), ctx(0), kind(0), logVariant(0), fpMode(MAG_FP_STRICT), dirty(true), topoValid(false), exported(0), exportThreads(1), streak(0), lastGoodQuality(-1),
     fSizes(0), fFrames(0), fIso(0), fnAniso(0), fnIso(0), nNonSimplex(0), lastDim(-1), lastId(-1)
 {
 }

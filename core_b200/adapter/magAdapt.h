@@ -58,6 +58,11 @@ class GpuSizeField : public ma::SizeField
     void invalidate() { dirty = true; topoValid = false; }
     /* MAG_FP_STRICT (default) or MAG_FP_FAST, see include/mag.h */
     void setArithmetic(int fp_mode) { fpMode = fp_mode; invalidate(); }
+    /* host threads for the read-only part of the MDS walk of an export (getDownward / isOwned of every edge and element, the
+       "ma_flags" tag reads); default 1 = the reference's own single-threaded access pattern.  MDS adjacency queries do not
+       write, so more threads are safe while nothing else touches the mesh (no other thread of the caller does during a
+       MeshAdapt call); opt-in because the reference makes no such promise in writing. */
+    void setExportThreads(int n) { exportThreads = n < 1 ? 1 : n; }
     /* re-export the mesh + field and run one full device sweep now */
     void refresh(double goodQuality = -1);
 
@@ -79,6 +84,7 @@ class GpuSizeField : public ma::SizeField
        quality ... of one MeshAdapt iteration) share ONE export instead of walking MDS again. */
     bool topoValid;
     Export* exported;
+    int exportThreads;
     long streak;     /* consecutive per-entity sweep-like queries since the last mesh change */
     double lastGoodQuality;
     apf::Field* fSizes; apf::Field* fFrames; apf::Field* fIso;

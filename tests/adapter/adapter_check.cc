@@ -54,6 +54,7 @@ void ensure_pcu()
    [1] the adapter's bulk entry points for the same five (each one exports the mesh from MDS, uploads, sweeps, writes the
    flag words back), [2] the unmodified reference loops served through the adapter */
 double g_times[3] = {0, 0, 0};
+int g_export_threads = 1;   /* mag_adapter_set_threads: host threads of the adapter's MDS walk in the next checks */
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 struct Fields { apf::Field* sizes; apf::Field* frames; };
@@ -112,6 +113,7 @@ long diff(const std::vector<int>& a, const std::vector<int>& b)
    report[15..18] flag words differing: A edges, A elems, B edges, B elems;  report[19] sweeps the adapter ran for B
    returns 0 when A and B reproduce the reference exactly (fp_mode strict) / flags+counts exactly, values 1e-12 (fast). */
 static int adapter_check(int n, int nz, int log_interp, int fp_mode, double jitter, double* report);
+extern "C" void mag_adapter_set_threads(int n) { g_export_threads = n; }
 extern "C" void mag_adapter_times(double* t) { for (int i = 0; i < 3; ++i) t[i] = g_times[i]; }
 extern "C" int mag_adapter_check(int n, int log_interp, int fp_mode, double jitter, double* report)
 {
@@ -170,6 +172,7 @@ static int adapter_check(int n, int nz, int log_interp, int fp_mode, double jitt
   Fields f = make_fields(m, "gpu", hbar);
   mag::GpuSizeField* g = mag::makeSizeField(m, f.sizes, f.frames, log_interp != 0, 0);
   g->setArithmetic(fp_mode);
+  g->setExportThreads(g_export_threads);
   { /* (A) the adapter's bulk entry points */
     ma::Input* in = ma::makeAdvanced(ma::configureIdentity(m, g));
     in->shapeHandler = mag::shapeHandler;

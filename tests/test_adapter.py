@@ -51,3 +51,21 @@ def test_adapter_reproduces_reference_2d(built, log_interp, fp_mode):
     assert ref[0] > 0 and ref[2] > 0
     assert np.array_equal(ref[:3], bulk[:3]) and np.array_equal(ref[:3], loops[:3])
     assert np.all(rep[15:19] == 0)
+
+
+@pytest.mark.gpu
+def test_adapter_threaded_export(built):
+    """The opt-in multi-threaded MDS walk of the export (setExportThreads) gives the same export: the whole self-check
+    passes with 8 host threads on a box large enough for the threads to start (n = 24: 83 k tets)."""
+    if not os.path.exists(LIB):
+        pytest.skip("libmag_ma.so not built (needs the reference headers)")
+    L = C.CDLL(LIB)
+    L.mag_adapter_check.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p]
+    L.mag_adapter_set_threads.argtypes = [C.c_int]
+    L.mag_adapter_set_threads(8)
+    try:
+        rep = np.zeros(20)
+        rc = L.mag_adapter_check(24, 0, 0, 0.25, rep.ctypes.data_as(C.c_void_p))
+        assert rc == 0 and np.all(rep[15:19] == 0) and np.array_equal(rep[0:3], rep[5:8])
+    finally:
+        L.mag_adapter_set_threads(1)
