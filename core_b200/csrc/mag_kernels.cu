@@ -567,8 +567,8 @@ __device__ __forceinline__ void centroid_transform(const double* __restrict__ ve
 {
   constexpr double N0 = 1 - 0.25 - 0.25 - 0.25;
   const int32_t vid[4] = {tv.x, tv.y, tv.z, tv.w};
-  if (KIND == MAG_KIND_IDENTITY) { magst::identity(Q); return; }
-  if (KIND == MAG_KIND_ISO) {
+  if constexpr (KIND == MAG_KIND_IDENTITY) { magst::identity(Q); return; }
+  else if constexpr (KIND == MAG_KIND_ISO) {
     double h = 0;
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
@@ -580,23 +580,24 @@ __device__ __forceinline__ void centroid_transform(const double* __restrict__ ve
     double ih = magst::div(1.0, h);
     Q.m[0][0] = ih; Q.m[1][1] = ih; Q.m[2][2] = ih;
     return;
-  }
-  double c[9];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) c[i] = 0;
-#pragma unroll
-  for (int n = 0; n < 4; ++n) {
-    Rec12 r = load_rec12(vedge, vid[n]);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) c[i] = magst::add(c[i], magst::mul(r.v[3 + i], n ? 0.25 : N0));
-  }
-  if (KIND == MAG_KIND_ANISO) {
-    magst::transform_aniso(V3{c[3], c[4], c[5]}, V3{c[6], c[7], c[8]}, c[0], c[1], c[2], Q);
   } else {
-    M3 A;
+    double c[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) A.m[i / 3][i % 3] = c[i];
-    if (magst::transform_logm(A, Q) != 1) *eig = 1;
+    for (int i = 0; i < 9; ++i) c[i] = 0;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      Rec12 r = load_rec12(vedge, vid[n]);
+#pragma unroll
+      for (int i = 0; i < 9; ++i) c[i] = magst::add(c[i], magst::mul(r.v[3 + i], n ? 0.25 : N0));
+    }
+    if (KIND == MAG_KIND_ANISO) {
+      magst::transform_aniso(V3{c[3], c[4], c[5]}, V3{c[6], c[7], c[8]}, c[0], c[1], c[2], Q);
+    } else {
+      M3 A;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) A.m[i / 3][i % 3] = c[i];
+      if (magst::transform_logm(A, Q) != 1) *eig = 1;
+    }
   }
 }
 
@@ -845,8 +846,8 @@ template <int KIND>
 __device__ __forceinline__ void centroid_transform_tri(const double* __restrict__ vedge, int64_t nv, const int32_t vid[3], M3& Q, int* eig)
 {
   constexpr double N1 = 1. / 3., N0 = 1 - 1. / 3. - 1. / 3.;
-  if (KIND == MAG_KIND_IDENTITY) { magst::identity(Q); return; }
-  if (KIND == MAG_KIND_ISO) {
+  if constexpr (KIND == MAG_KIND_IDENTITY) { magst::identity(Q); return; }
+  else if constexpr (KIND == MAG_KIND_ISO) {
     double h = 0;
 #pragma unroll
     for (int n = 0; n < 3; ++n) {
@@ -858,23 +859,24 @@ __device__ __forceinline__ void centroid_transform_tri(const double* __restrict_
     double ih = magst::div(1.0, h);
     Q.m[0][0] = ih; Q.m[1][1] = ih; Q.m[2][2] = ih;
     return;
-  }
-  double c[9];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) c[i] = 0;
-#pragma unroll
-  for (int n = 0; n < 3; ++n) {
-    Rec12 r = load_rec12(vedge, vid[n]);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) c[i] = magst::add(c[i], magst::mul(r.v[3 + i], n ? N1 : N0));
-  }
-  if (KIND == MAG_KIND_ANISO) {
-    magst::transform_aniso(V3{c[3], c[4], c[5]}, V3{c[6], c[7], c[8]}, c[0], c[1], c[2], Q);
   } else {
-    M3 A;
+    double c[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) A.m[i / 3][i % 3] = c[i];
-    if (magst::transform_logm(A, Q) != 1) *eig = 1;
+    for (int i = 0; i < 9; ++i) c[i] = 0;
+#pragma unroll
+    for (int n = 0; n < 3; ++n) {
+      Rec12 r = load_rec12(vedge, vid[n]);
+#pragma unroll
+      for (int i = 0; i < 9; ++i) c[i] = magst::add(c[i], magst::mul(r.v[3 + i], n ? N1 : N0));
+    }
+    if (KIND == MAG_KIND_ANISO) {
+      magst::transform_aniso(V3{c[3], c[4], c[5]}, V3{c[6], c[7], c[8]}, c[0], c[1], c[2], Q);
+    } else {
+      M3 A;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) A.m[i / 3][i % 3] = c[i];
+      if (magst::transform_logm(A, Q) != 1) *eig = 1;
+    }
   }
 }
 
