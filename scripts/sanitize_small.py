@@ -32,6 +32,16 @@ key = lambda a, b: np.minimum(a, b).astype(np.int64) * (1 << 32) + np.maximum(a,
 ek = key(ev[:, 0], ev[:, 1]); order = np.argsort(ek)
 te = np.stack([order[np.searchsorted(ek[order], key(tv[:, a], tv[:, b]))] for a, b in ((0, 1), (1, 2), (2, 0), (0, 3), (1, 3), (2, 3))], axis=1).astype(np.int32)
 p.short_edge_test(te, 2.0)
+p.clearFlagFromDimension(cb.SPLIT | cb.COLLAPSE, 1); p.unMarkBadQuality()
+p.set_size_field_uniform_refiner(); p.clear_flags(); p.sweep(cb.OP_MARK_SPLIT | cb.OP_MARK_COLLAPSE); p.stats()
+p.set_size_field_identity(); p.getAverageEdgeLength()
+bad = tv.copy(); bad[3, 1] = len(xyz) + 5
+try:
+    p.set_mesh(xyz, ev, bad)          # the export-time range check must stop this before anything gathers through it
+    raise SystemExit("bad connectivity accepted")
+except cb.MagError:
+    pass
+p.set_mesh(xyz, ev, tv, edge_owned=eo, elem_owned=lo); p.set_size_field_aniso(h, R)
 oL, oq = np.empty(len(ev)), np.empty(len(tv))
 oe, ol = np.empty(len(ev), np.int32), np.empty(len(tv), np.int32)
 p.sweep_host(xyz, ev, tv, 2, h, R, edge_flags=ef, elem_flags=lf, edge_owned=eo, elem_owned=lo, out_lengths=oL, out_qualities=oq,
