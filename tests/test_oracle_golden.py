@@ -153,6 +153,18 @@ def test_eigen_golden_and_reference_kat(built):
             assert np.allclose(A @ E[j], v[j] * E[j], atol=1e-9)
 
 
+def test_qr_kat(built):
+    """test/qr.cc:84-109 (testEigenQR) and :57-82 (the all-ones matrix of testHessenberg): the restated iteration
+    converges, its eigenvector matrix is orthogonal and Q L Q^T reproduces A, both to the reference test's 1e-10."""
+    for A in (np.array([[1, 5, 4], [5, 6, 3], [4, 3, 2]], dtype=np.float64), np.ones((3, 3))):
+        vals, vecs, rc = mao.eigen(A)
+        assert rc in (1, 3)
+        Q = vecs.T                                   # eigenvectors are returned as rows (apfMatrix.cc:68-83)
+        assert np.max(np.abs(Q @ Q.T - np.eye(3))) < 1e-10
+        assert np.max(np.abs(Q @ np.diag(vals) @ Q.T - A)) < 1e-10
+    assert np.allclose(sorted(mao.eigen(np.ones((3, 3)))[0]), [0, 0, 3], atol=1e-10)
+
+
 def test_det_kat(built):
     """test/ma_insphere.cc:13-29: exact integer determinants of the 3x3 minors of the test's 4x4 matrix."""
     M = np.array([[2, 5, 3, 5], [14, 9, 6, 7], [4, 9, 3, 2], [3, 7, 8, 6]], dtype=np.float64)
