@@ -271,3 +271,75 @@ static int adapter_check(int n, int nz, int log_interp, int fp_mode, double jitt
   bad |= stats_diffs != 0;
   return bad;
 }
+
+/* The drop-in claim end to end: ma::adapt (refine, coarsen, shape correction -- the UNMODIFIED reference driver) on two
+   identical jittered boxes, once with the reference's own AnisoSizeField and once with the mag::GpuSizeField /
+   mag::shapeHandler plugged into ma::Input (MAG_FP_STRICT: every length and quality the reference sees is bit-identical, so
+   every operator decision is the same).  The two adapted meshes must be the same mesh: same entity counts, same
+   coordinates and connectivity in iteration order, and the same longest metric edge (the quantity test/aniso_adapt.h:65-74
+   checks against MAXLENGTH once the adaptation has converged).
+   which: 1 = reference only (no device), 3 = both.  out[0..2] counts of the reference run (verts, edges, tets), out[3..5] of
+   the adapter run, out[6] differing coordinates / connectivity entries, out[7] longest metric edge after the adapter run,
+   out[8] device kernel launches made during the adapter run, out[9] / out[10] wall-clock seconds of the two runs. */
+extern "C" int mag_adapter_adapt_check(int n, int which, double size_scale, int iterations, double* out)
+{
+  ensure_pcu();
+  for (int i = 0; i < 11; ++i) out[i] = 0;
+  apf::Mesh2* mesh[2] = {0, 0};
+  double ref_max_len = 0;
+  for (int run = 0; run < 2; ++run) {
+    if (!(which & (1 << run))) continue;
+    apf::Mesh2* m = apf::makeMdsBox(n, n, n, 1, 1, 1, true, g_pcu);
+    mesh[run] = m;
+    Fields f = make_fields(m, run ? "gpu" : "ref", size_scale / n);
+    ma::SizeField* sf;
+    mag::GpuSizeField* g = 0;
+    if (run == 0) sf = ma::makeSizeField(m, f.sizes, f.frames, false);
+    else { g = mag::makeSizeField(m, f.sizes, f.frames, false, 0); sf = g; }
+    ma::Input* in = ma::makeAdvanced(ma::configureIdentity(m, sf));
+    in->maximumIterations = iterations;
+    in->shouldSnap = false;              /* the box has a null model */
+    if (run == 1) in->shapeHandler = mag::shapeHandler;
+    const long l0 = g ? mag_launch_count(g->ctx) : 0;
+    const double t0 = now_s();
+    ma::adapt(in);                       /* deletes the Input; the size field is ours (ownsSizeField = false) */
+    out[9 + run] = now_s() - t0;
+    out[3 * run] = (double)m->count(0); out[3 * run + 1] = (double)m->count(1); out[3 * run + 2] = (double)m->count(3);
+    if (run == 1) {
+      out[8] = (double)(mag_launch_count(g->ctx) - l0);
+      out[7] = ma::getMaximumEdgeLength(m, g->wrapped);
+    } else ref_max_len = ma::getMaximumEdgeLength(m, sf);
+    delete sf;
+  }
+  int bad = 0;
+  if (which == 3) {
+    apf::Mesh2 *a = mesh[0], *b = mesh[1];
+    long diffs = 0;
+    for (int d = 0; d <= 3; ++d) if (a->count(d) != b->count(d)) diffs += 1000000;
+    if (!diffs) {
+      apf::MeshIterator *ia = a->begin(0), *ib = b->begin(0);
+      apf::MeshEntity *ea, *eb;
+      while ((ea = a->iterate(ia)) && (eb = b->iterate(ib))) {
+        apf::Vector3 pa, pb;
+        a->getPoint(ea, 0, pa); b->getPoint(eb, 0, pb);
+        if (!(pa[0] == pb[0] && pa[1] == pb[1] && pa[2] == pb[2]) || apf::getMdsIndex(a, ea) != apf::getMdsIndex(b, eb)) ++diffs;
+      }
+      a->end(ia); b->end(ib);
+      for (int d = 1; d <= 3; d += 2) {
+        ia = a->begin(d); ib = b->begin(d);
+        while ((ea = a->iterate(ia)) && (eb = b->iterate(ib))) {
+          apf::Downward va, vb;
+          const int na = a->getDownward(ea, 0, va), nb = b->getDownward(eb, 0, vb);
+          if (na != nb) { ++diffs; continue; }
+          for (int i = 0; i < na; ++i) if (apf::getMdsIndex(a, va[i]) != apf::getMdsIndex(b, vb[i])) ++diffs;
+        }
+        a->end(ia); b->end(ib);
+      }
+    }
+    out[6] = (double)diffs;
+    bad = diffs != 0 || out[7] != ref_max_len;   /* the longest metric edge left (test/aniso_adapt.h:65-74 asks <= MAXLENGTH once converged) */
+  }
+  for (int run = 0; run < 2; ++run)
+    if (mesh[run]) { mesh[run]->destroyNative(); apf::destroyMesh(mesh[run]); }
+  return bad;
+}

@@ -69,3 +69,22 @@ def test_adapter_threaded_export(built):
         assert rc == 0 and np.all(rep[15:19] == 0) and np.array_equal(rep[0:3], rep[5:8])
     finally:
         L.mag_adapter_set_threads(1)
+
+
+@pytest.mark.gpu
+def test_ma_adapt_through_the_adapter_gives_the_same_mesh(built):
+    """The drop-in claim end to end: the UNMODIFIED ma::adapt driver (refine / coarsen / shape correction, two iterations) on
+    a jittered 10^3 box with the rotating shock-layer fields, once with the reference's AnisoSizeField and once with
+    mag::GpuSizeField + mag::shapeHandler plugged into ma::Input (strict arithmetic).  Same adapted mesh: counts,
+    coordinates and connectivity in iteration order, same longest metric edge (the quantity test/aniso_adapt.h:65-74
+    checks); and the device did serve whole-mesh sweeps on the way."""
+    if not os.path.exists(LIB):
+        pytest.skip("libmag_ma.so not built (needs the reference headers)")
+    L = C.CDLL(LIB)
+    L.mag_adapter_adapt_check.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p]
+    out = np.zeros(11)
+    rc = L.mag_adapter_adapt_check(10, 3, 1.0, 2, out.ctypes.data_as(C.c_void_p))
+    assert rc == 0, out.tolist()
+    assert np.array_equal(out[0:3], out[3:6]) and out[6] == 0
+    assert out[2] > 4 * 6000                      # the mesh was really adapted (6000 tets before)
+    assert out[8] > 0                             # device sweeps happened
