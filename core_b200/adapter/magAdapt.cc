@@ -52,6 +52,7 @@ struct Export {
   std::vector<int> edge_v, tet_v, prism_v, pyr_v, tri_v;   /* tri_v: the elements of a 2-D mesh */
   std::vector<unsigned char> edge_owned, elem_owned;
   std::vector<ma::Entity*> edges, elems; /* iteration order; elems = prisms | pyramids | tets */
+  bool logm_direct;                       /* mb holds the reference's ma_logM field, not frames */
 };
 
 struct Access {
@@ -88,7 +89,14 @@ struct Access {
     std::vector<int>& vslot = g->vertSlot;
     vslot.assign(vslot.size(), -1);
     x.xyz.resize(3 * nv);
+    /* LogAnisoSizeField built from fields keeps its own "ma_logM" vertex field and is the only thing it updates when
+       vertices are created (interpolate / onRefine / onCavity, maSize.cc:523-561): the sizes and frames it was built from go
+       stale for new vertices, so the export reads the logM field itself */
+    apf::Field* logM = (g->kind == 3 && !g->fnAniso) ? m->findField("ma_logM") : 0;
+    if (g->kind == 3 && !g->fnAniso && !logM) { fprintf(stderr, "mag adapter: the wrapped LogAnisoSizeField has no ma_logM field\n"); abort(); }
+    x.logm_direct = logM != 0;
     if (g->kind == 1) x.ma.resize(nv);
+    else if (logM) x.mb.resize(9 * nv);
     else { x.ma.resize(3 * nv); x.mb.resize(9 * nv); }
     apf::MeshIterator* it = m->begin(0);
     ma::Entity* e;
@@ -102,6 +110,10 @@ struct Access {
       x.xyz[3 * k] = p[0]; x.xyz[3 * k + 1] = p[1]; x.xyz[3 * k + 2] = p[2];
       if (g->kind == 1) {
         x.ma[k] = g->fnIso ? g->fnIso->getValue(e) : apf::getScalar(g->fIso, e, 0);
+      } else if (logM) {
+        ma::Matrix M;
+        apf::getMatrix(logM, e, 0, M);
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) x.mb[9 * k + 3 * i + j] = M[i][j];
       } else {
         ma::Matrix R; ma::Vector h;
         if (g->fnAniso) g->fnAniso->getValue(e, R, h);
@@ -186,6 +198,7 @@ struct Access {
                            (int64_t)(x.pyr_v.size() / 5), x.pyr_v.data(), x.edge_owned.data(), x.elem_owned.data()));
     if (g->kind == 1) MAG_DO(c, mag_set_metric_iso(c, x.ma.data()));
     else if (g->kind == 2) MAG_DO(c, mag_set_metric_aniso(c, x.ma.data(), x.mb.data()));
+    else if (x.logm_direct) MAG_DO(c, mag_set_metric_logm(c, x.mb.data()));
     else MAG_DO(c, mag_set_metric_logm_from_frames(c, x.ma.data(), x.mb.data(), g->logVariant, 0));
     MAG_DO(c, mag_synchronize(c));
   }

@@ -72,18 +72,26 @@ def test_adapter_threaded_export(built):
 
 
 @pytest.mark.gpu
-def test_ma_adapt_through_the_adapter_gives_the_same_mesh(built):
+@pytest.mark.parametrize("log_interp,fp_mode,jitter", [(0, 0, 0.0), (0, 1, 0.25), (1, 0, 0.25), (1, 1, 0.0)])
+def test_ma_adapt_through_the_adapter_gives_the_same_mesh(built, log_interp, fp_mode, jitter):
     """The drop-in claim end to end: the UNMODIFIED ma::adapt driver (refine / coarsen / shape correction, two iterations) on
-    a jittered 10^3 box with the rotating shock-layer fields, once with the reference's AnisoSizeField and once with
-    mag::GpuSizeField + mag::shapeHandler plugged into ma::Input (strict arithmetic).  Same adapted mesh: counts,
-    coordinates and connectivity in iteration order, same longest metric edge (the quantity test/aniso_adapt.h:65-74
-    checks); and the device did serve whole-mesh sweeps on the way."""
+    a 10^3 box (lattice or jittered) with the rotating shock-layer fields, once with the reference's own size field
+    (AnisoSizeField or LogAnisoSizeField) and once with mag::GpuSizeField + mag::shapeHandler plugged into ma::Input.
+    Same adapted mesh: counts, coordinates and connectivity in iteration order, same longest metric edge (the quantity
+    test/aniso_adapt.h:65-74 checks); and the device did serve whole-mesh sweeps on the way.  (The log-Euclidean case is
+    what exposed that the export has to read the size field's own ma_logM field: the sizes / frames it was built from go
+    stale for vertices created by refinement.)"""
     if not os.path.exists(LIB):
         pytest.skip("libmag_ma.so not built (needs the reference headers)")
     L = C.CDLL(LIB)
-    L.mag_adapter_adapt_check.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p]
-    out = np.zeros(11)
-    rc = L.mag_adapter_adapt_check(10, 3, 1.0, 2, out.ctypes.data_as(C.c_void_p))
+    L.mag_adapter_adapt_check2.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.mag_adapter_set_adapt_jitter.argtypes = [C.c_double]
+    L.mag_adapter_set_adapt_jitter(jitter)
+    try:
+        out = np.zeros(11)
+        rc = L.mag_adapter_adapt_check2(10, 3, 1.0, 2, log_interp, fp_mode, out.ctypes.data_as(C.c_void_p))
+    finally:
+        L.mag_adapter_set_adapt_jitter(0.0)
     assert rc == 0, out.tolist()
     assert np.array_equal(out[0:3], out[3:6]) and out[6] == 0
     assert out[2] > 4 * 6000                      # the mesh was really adapted (6000 tets before)
