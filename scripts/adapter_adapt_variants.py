@@ -1,3 +1,5 @@
+"""ma::adapt through the adapter against ma::adapt with the reference's own size field (tests/adapter/adapter_check.cc:
+mag_adapter_adapt_check2) for LogAniso strict / fast and Aniso fast; prints the report rows.  usage: adapter_adapt_variants.py [jitter]"""
 import ctypes as C, numpy as np
 L=C.CDLL("core_b200/lib/libmag_ma.so")
 L.mag_adapter_adapt_check2.argtypes=[C.c_int,C.c_int,C.c_double,C.c_int,C.c_int,C.c_int,C.c_void_p]
