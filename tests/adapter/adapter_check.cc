@@ -55,6 +55,7 @@ void ensure_pcu()
    flag words back), [2] the unmodified reference loops served through the adapter */
 double g_times[3] = {0, 0, 0};
 int g_export_threads = 1;
+int g_adapt_dim = 3;         /* mag_adapter_set_adapt_dim: 3 = n^3 box of tets, 2 = n^2 box of triangles */
 double g_adapt_jitter = 0;   /* mag_adapter_set_adapt_jitter: vertex jitter of the boxes of the ma::adapt checks */   /* mag_adapter_set_threads: host threads of the adapter's MDS walk in the next checks */
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -137,6 +138,7 @@ static void jitter_mesh(apf::Mesh2* m, int n, double jitter)
 static int adapter_check(int n, int nz, int log_interp, int fp_mode, double jitter, double* report);
 extern "C" void mag_adapter_set_threads(int n) { g_export_threads = n; }
 extern "C" void mag_adapter_set_adapt_jitter(double j) { g_adapt_jitter = j; }
+extern "C" void mag_adapter_set_adapt_dim(int d) { g_adapt_dim = d == 2 ? 2 : 3; }
 extern "C" void mag_adapter_times(double* t) { for (int i = 0; i < 3; ++i) t[i] = g_times[i]; }
 extern "C" int mag_adapter_check(int n, int log_interp, int fp_mode, double jitter, double* report)
 {
@@ -309,7 +311,7 @@ static int adapt_check(int n, int which, double size_scale, int iterations, int 
   double ref_max_len = 0;
   for (int run = 0; run < 2; ++run) {
     if (!(which & (1 << run))) continue;
-    apf::Mesh2* m = apf::makeMdsBox(n, n, n, 1, 1, 1, true, g_pcu);
+    apf::Mesh2* m = g_adapt_dim == 2 ? apf::makeMdsBox(n, n, 0, 1, 1, 0, true, g_pcu) : apf::makeMdsBox(n, n, n, 1, 1, 1, true, g_pcu);
     mesh[run] = m;
     jitter_mesh(m, n, g_adapt_jitter);
     Fields f = make_fields(m, run ? "gpu" : "ref", size_scale / n);
@@ -325,7 +327,7 @@ static int adapt_check(int n, int which, double size_scale, int iterations, int 
     const double t0 = now_s();
     ma::adapt(in);                       /* deletes the Input; the size field is ours (ownsSizeField = false) */
     out[9 + run] = now_s() - t0;
-    out[3 * run] = (double)m->count(0); out[3 * run + 1] = (double)m->count(1); out[3 * run + 2] = (double)m->count(3);
+    out[3 * run] = (double)m->count(0); out[3 * run + 1] = (double)m->count(1); out[3 * run + 2] = (double)m->count(m->getDimension());
     if (run == 1) {
       out[8] = (double)(mag_launch_count(g->ctx) - l0);
       out[7] = ma::getMaximumEdgeLength(m, g->wrapped);
@@ -336,7 +338,8 @@ static int adapt_check(int n, int which, double size_scale, int iterations, int 
   if (which == 3) {
     apf::Mesh2 *a = mesh[0], *b = mesh[1];
     long diffs = 0;
-    for (int d = 0; d <= 3; ++d) if (a->count(d) != b->count(d)) diffs += 1000000;
+    const int mdim = a->getDimension();
+    for (int d = 0; d <= mdim; ++d) if (a->count(d) != b->count(d)) diffs += 1000000;
     if (!diffs) {
       apf::MeshIterator *ia = a->begin(0), *ib = b->begin(0);
       apf::MeshEntity *ea, *eb;
@@ -346,7 +349,7 @@ static int adapt_check(int n, int which, double size_scale, int iterations, int 
         if (!(pa[0] == pb[0] && pa[1] == pb[1] && pa[2] == pb[2]) || apf::getMdsIndex(a, ea) != apf::getMdsIndex(b, eb)) ++diffs;
       }
       a->end(ia); b->end(ib);
-      for (int d = 1; d <= 3; d += 2) {
+      for (int d = 1; d <= mdim; d += mdim - 1) {
         ia = a->begin(d); ib = b->begin(d);
         while ((ea = a->iterate(ia)) && (eb = b->iterate(ib))) {
           apf::Downward va, vb;

@@ -72,10 +72,11 @@ def test_adapter_threaded_export(built):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("log_interp,fp_mode,jitter", [(0, 0, 0.0), (0, 1, 0.25), (1, 0, 0.25), (1, 1, 0.0)])
-def test_ma_adapt_through_the_adapter_gives_the_same_mesh(built, log_interp, fp_mode, jitter):
+@pytest.mark.parametrize("dim,log_interp,fp_mode,jitter", [(3, 0, 0, 0.0), (3, 0, 1, 0.25), (3, 1, 0, 0.25), (3, 1, 1, 0.0),
+                                                           (2, 0, 0, 0.0), (2, 1, 1, 0.25)])
+def test_ma_adapt_through_the_adapter_gives_the_same_mesh(built, dim, log_interp, fp_mode, jitter):
     """The drop-in claim end to end: the UNMODIFIED ma::adapt driver (refine / coarsen / shape correction, two iterations) on
-    a 10^3 box (lattice or jittered) with the rotating shock-layer fields, once with the reference's own size field
+    a 10^3 box of tets or a 60^2 box of triangles (lattice or jittered) with the rotating shock-layer fields, once with the reference's own size field
     (AnisoSizeField or LogAnisoSizeField) and once with mag::GpuSizeField + mag::shapeHandler plugged into ma::Input.
     Same adapted mesh: counts, coordinates and connectivity in iteration order, same longest metric edge (the quantity
     test/aniso_adapt.h:65-74 checks); and the device did serve whole-mesh sweeps on the way.  (The log-Euclidean case is
@@ -86,13 +87,16 @@ def test_ma_adapt_through_the_adapter_gives_the_same_mesh(built, log_interp, fp_
     L = C.CDLL(LIB)
     L.mag_adapter_adapt_check2.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.mag_adapter_set_adapt_jitter.argtypes = [C.c_double]
+    L.mag_adapter_set_adapt_dim.argtypes = [C.c_int]
     L.mag_adapter_set_adapt_jitter(jitter)
+    L.mag_adapter_set_adapt_dim(dim)
     try:
         out = np.zeros(11)
-        rc = L.mag_adapter_adapt_check2(10, 3, 1.0, 2, log_interp, fp_mode, out.ctypes.data_as(C.c_void_p))
+        rc = L.mag_adapter_adapt_check2(10 if dim == 3 else 60, 3, 1.0, 2, log_interp, fp_mode, out.ctypes.data_as(C.c_void_p))
     finally:
         L.mag_adapter_set_adapt_jitter(0.0)
+        L.mag_adapter_set_adapt_dim(3)
     assert rc == 0, out.tolist()
     assert np.array_equal(out[0:3], out[3:6]) and out[6] == 0
-    assert out[2] > 4 * 6000                      # the mesh was really adapted (6000 tets before)
+    assert out[2] > 3 * (6000 if dim == 3 else 7200)   # the mesh was really adapted (6000 tets / 7200 triangles before)
     assert out[8] > 0                             # device sweeps happened
