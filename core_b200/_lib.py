@@ -18,7 +18,7 @@ SYMBOLS = [
     "mag_sliver_codes", "mag_linear_qualities",
     "mag_get_edge_lengths", "mag_get_qualities", "mag_get_flags", "mag_get_layer_ok", "mag_get_stats",
     "mag_get_near_threshold", "mag_set_metric_logm_from_frames",
-    "mag_timing_begin", "mag_timing_read", "mag_launch_count",
+    "mag_timing_begin", "mag_timing_read", "mag_launch_count", "mag_get_row_layout",
     "mag_comm_unique_id", "mag_comm_init", "mag_set_edge_links", "mag_reconcile_edge_flags",
     "mag_sync_edge_flags", "mag_allreduce_stats",
 ]
@@ -98,6 +98,7 @@ def lib():
     L.mag_timing_read.argtypes = [vp, vp, C.POINTER(C.c_int)]
     L.mag_launch_count.argtypes = [vp]
     L.mag_launch_count.restype = i64
+    L.mag_get_row_layout.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     L.mag_comm_unique_id.argtypes = [vp]
     L.mag_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.mag_set_edge_links.argtypes = [vp, C.c_int, vp, vp, vp, vp]

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cmath>
+#include <cstdlib>
 
 int magk_pack(mag_ctx* c);
 int magk_init_stats(mag_ctx* c);
@@ -17,6 +18,7 @@ int magk_conn_result(mag_ctx* c, unsigned long long* bad);
 int magk_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double good_q, int use_max, int fp_mode);
 double magk_key_to_double(unsigned long long k);
 void magc_destroy(mag_ctx* c);
+void magk_free_rows(mag_ctx* c);
 
 static thread_local std::string g_create_err;
 
@@ -85,7 +87,10 @@ int repack(mag_ctx* c)
   int rc = dev_reserve(c, c->d_vedge, c->cap_vedge, (size_t)vpad(c->nv) * rec_doubles(c->kind));
   if (rc) return rc;
   c->vertex_pass_valid = false;
-  return magk_pack(c);
+  if ((rc = magk_pack(c))) return rc;
+  // Q_v and det Q_v depend on the coordinates and the size field only: computed here, reused by every sweep until either
+  // changes again (ma/maQuality.cc:83-108 evaluates them per tet; round 1 recomputed them per sweep)
+  return magk_vertex_pass(c);
 }
 
 #define CHECK_CTX(c) do { if (!(c)) return MAG_ERR_ARG; int rc_ = use_device(c); if (rc_) return rc_; } while (0)
@@ -148,6 +153,10 @@ int mag_create(mag_ctx** out, int device)
   c->d_stats = nullptr; c->h_stats = nullptr;
   c->d_block_sums = nullptr; c->n_sms = 148;
   c->d_edge_order = c->d_tet_order = nullptr;
+  c->erows = MagRows{0, 0, 0, nullptr, nullptr, nullptr, false};
+  c->trows = c->erows;
+  { const char* e = getenv("MAG_LEGACY_SWEEP"); c->legacy_sweep = e && e[0] == '1'; }
+  c->d_vstat = nullptr;
   c->d_near_edge = c->d_near_elem = nullptr;
   c->cap_vedge = c->cap_ma = c->cap_mb = 0;
   c->last_ops = 0; c->last_fp_mode = 0;
@@ -164,6 +173,8 @@ int mag_create(mag_ctx** out, int device)
   if ((e = cudaMalloc((void**)&c->d_stats, sizeof(MagDevStats))) != cudaSuccess) return fail(e, "cudaMalloc stats");
   if ((e = cudaMallocHost((void**)&c->h_stats, sizeof(MagDevStats))) != cudaSuccess) return fail(e, "cudaMallocHost stats");
   if ((e = cudaMalloc((void**)&c->d_block_sums, sizeof(double) * MAG_SUM_BLOCKS)) != cudaSuccess) return fail(e, "cudaMalloc block sums");
+  if ((e = cudaMalloc((void**)&c->d_vstat, sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc vertex-pass counter");
+  if ((e = cudaMemset(c->d_vstat, 0, sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMemset vertex-pass counter");
   if ((e = cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return fail(e, "SM count");
   int rc = magk_init_stats(c);
   if (rc) { g_create_err = c->err; delete c; return rc; }
@@ -183,6 +194,7 @@ void mag_destroy(mag_ctx* c)
   cudaFree(c->d_len); cudaFree(c->d_qual); cudaFree(c->d_weight); cudaFree(c->d_layer_ok); cudaFree(c->d_layer_codes);
   cudaFree(c->d_stats); cudaFreeHost(c->h_stats); cudaFree(c->d_block_sums);
   cudaFree(c->d_near_edge); cudaFree(c->d_near_elem); cudaFree(c->d_edge_order); cudaFree(c->d_tet_order);
+  magk_free_rows(c); cudaFree(c->d_vstat);
   for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
   for (cudaEvent_t e : c->pipe_ev) cudaEventDestroy(e);
   if (c->s_up) cudaStreamDestroy(c->s_up);
@@ -221,12 +233,19 @@ int magi_reshape(mag_ctx* c, int dim, int64_t nv, int64_t ne, int64_t nt, int64_
   const bool same_shape = nv == c->nv && ne == c->ne && nt == c->nt && np == c->np && npy == c->npy && ntri == c->ntri &&
                           has_edge_owned == (c->d_edge_owned != nullptr) && has_elem_owned == (c->d_elem_owned != nullptr);
   if (same_shape) return MAG_OK;
+  // the context holds NO part while its arrays are replaced: a failed allocation below (a 50 M-tet part needs ~10 GB)
+  // leaves it empty, so that later calls report MAG_ERR_ARG instead of running over half-allocated arrays
+  const bool keep_field = nv == c->nv;
+  c->nv = c->ne = c->nt = c->np = c->npy = c->ntri = 0;
+  c->vertex_pass_valid = false;
+  magk_free_rows(c);
   if ((rc = dev_free(c, c->d_weight))) return rc;
-  if (nv != c->nv) { // size field arrays are per vertex: drop them
+  if (!keep_field) { // size field arrays are per vertex: drop them
     c->kind = MAG_KIND_NONE;
     if ((rc = dev_free(c, c->d_ma)) || (rc = dev_free(c, c->d_mb)) || (rc = dev_free(c, c->d_vedge))) return rc;
     c->cap_ma = c->cap_mb = c->cap_vedge = 0;
   }
+  auto fail_empty = [&](int code) { c->kind = MAG_KIND_NONE; return code; };
   if ((rc = dev_alloc(c, c->d_xyz, (size_t)nv * 3)) || (rc = dev_alloc(c, c->d_vpos, (size_t)vpad(nv) * 4)) ||
       (rc = dev_alloc(c, c->d_vq, (size_t)vpad(nv) * 10)) || (rc = dev_alloc(c, c->d_edge_v, (size_t)ne * 2)) ||
       (rc = dev_alloc(c, c->d_tet_v, (size_t)nt * 4)) || (rc = dev_alloc(c, c->d_prism_v, (size_t)np * 6)) ||
@@ -237,7 +256,7 @@ int magi_reshape(mag_ctx* c, int dim, int64_t nv, int64_t ne, int64_t nt, int64_
       (rc = dev_alloc(c, c->d_len, (size_t)ne)) || (rc = dev_alloc(c, c->d_qual, (size_t)nel)) ||
       (rc = dev_alloc(c, c->d_layer_ok, (size_t)(np + npy))) || (rc = dev_alloc(c, c->d_layer_codes, (size_t)(np + npy))) ||
       (rc = dev_alloc(c, c->d_near_edge, (size_t)ne)) || (rc = dev_alloc(c, c->d_near_elem, (size_t)nel)))
-    return rc;
+    return fail_empty(rc);
   c->nv = nv; c->ne = ne; c->nt = nt; c->np = np; c->npy = npy; c->ntri = ntri;
   if (nel) MAG_CUDA(c, cudaMemsetAsync(c->d_qual, 0, (size_t)nel * 8, c->stream));
   return MAG_OK;
@@ -447,6 +466,25 @@ int mag_timing_read(mag_ctx* c, float* ms, int* n_out)
   return MAG_OK;
 }
 int64_t mag_launch_count(const mag_ctx* c) { return c ? c->n_launches : -1; }
+
+int mag_get_row_layout(mag_ctx* c, int which, int64_t* counts, int32_t* anchor, int32_t* slice_off, int32_t* slots)
+{
+  CHECK_CTX(c);
+  if (!counts || (which != 0 && which != 1)) return mag_fail(c, MAG_ERR_ARG, "mag_get_row_layout: bad argument");
+  if (c->legacy_sweep) return mag_fail(c, MAG_ERR_ARG, "mag_get_row_layout: MAG_LEGACY_SWEEP=1 runs without the row layout");
+  int rc;
+  if (!c->schedule_valid) {
+    if ((rc = magk_build_schedule(c))) return rc;
+    c->schedule_valid = true;
+  }
+  const MagRows& r = which ? c->trows : c->erows;
+  counts[0] = r.n_rows; counts[1] = r.n_slices; counts[2] = r.n_slots;
+  if (anchor && (rc = download(c, anchor, r.d_anchor, (size_t)r.n_slices * 32))) return rc;
+  if (slice_off && r.n_slices && (rc = download(c, slice_off, r.d_slice_off, (size_t)r.n_slices + 1))) return rc;
+  if (slots && (rc = download(c, slots, r.d_slots, (size_t)r.n_slots * (which ? 4 : 2)))) return rc;
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return MAG_OK;
+}
 
 // host-side construction of the logM field, operation for operation as the reference
 // (apf::Matrix product order, apfMatrix.h:94-106; libm log)

@@ -104,13 +104,11 @@ extern "C" int mag_sweep_host(mag_ctx* c, const mag_host_part* in, const mag_hos
       (rc = copy_async(c, c->d_ma, in->field_a, na, cudaMemcpyHostToDevice, s_up)) ||
       (rc = copy_async(c, c->d_mb, in->field_b, nb, cudaMemcpyHostToDevice, s_up)))
     return rc;
-  if ((rc = chain(c, ev, s_up, s_cmp)) || (rc = magk_init_stats(c))) return rc;
+  if ((rc = chain(c, ev, s_up, s_cmp))) return rc;
   if (nv && (rc = magk_pack(c))) return rc;
   c->vertex_pass_valid = false;
-  if (nv && (ops & (MAG_OP_QUALITIES | MAG_OP_MARK_BAD))) {
-    if ((rc = magk_vertex_pass(c))) return rc;
-    c->vertex_pass_valid = true;
-  }
+  if (nv && (ops & (MAG_OP_QUALITIES | MAG_OP_MARK_BAD)) && (rc = magk_vertex_pass(c))) return rc;
+  if ((rc = magk_init_stats(c))) return rc;   // after the vertex pass: its eigen-solver failures are folded in
 
   const bool do_edges = ne && (ops & (MAG_OP_LENGTHS | MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE));
   int64_t slice = in->slice_entities > 0 ? in->slice_entities : (int64_t)4 << 20;

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <string>
 #include <vector>
+#include <map>
 #include "../../include/mag.h"
 
 enum MagKind { MAG_KIND_NONE = -1, MAG_KIND_IDENTITY = 0, MAG_KIND_ISO = 1, MAG_KIND_ANISO = 2, MAG_KIND_LOGM = 3 };
@@ -32,6 +33,18 @@ static inline int64_t vpad(int64_t nv) { return (nv + MAG_VBLOCK - 1) / MAG_VBLO
 #define MAG_MAX_ENTITIES (0x7fffffffLL - (1LL << 20))
 // transient bit (never visible to the caller): entity awaits strict re-evaluation
 #define MAG_PENDING_BIT (1 << 30)
+
+// Anchor-row layout of one entity dimension (mag_rows.cuh): every entity is filed under its FIRST vertex (the anchor); the
+// rows are cut into slices of 32 (one per warp), stored slot-major inside a slice (sliced ELLPACK).  Built at export.
+struct MagRows {
+  int64_t n_rows;        // rows holding at least one entity
+  int64_t n_slices;      // ceil(n_rows / 32)
+  int64_t n_slots;       // 32 * sum of the slice widths
+  int32_t* d_anchor;     // [32 n_slices] anchor vertex of row position p, -1 = padding
+  int32_t* d_slice_off;  // [n_slices + 1] first slot of every slice
+  int32_t* d_slots;      // edges: int2 {other vertex | not-owned << 31, edge id}; tets: int4 {o1 | not-owned << 31, o2, o3, tet id}; id -1 = empty
+  bool valid;
+};
 
 struct MagLinks {
   int peer;
@@ -87,9 +100,14 @@ struct mag_ctx {
   int32_t* d_near_edge;  // [ne]  near-threshold edge indices of the last sweep (an entity is listed at most once)
   int32_t* d_near_elem;  // [np+npy+nt]
   int n_sms;
-  int32_t* d_edge_order; // chunk schedule of the edge kernel (chunk indices sorted by smallest vertex id)
+  int32_t* d_edge_order; // chunk schedule of the legacy edge kernel (tile indices sorted by smallest vertex id)
   int32_t* d_tet_order;
+  MagRows erows, trows;  // anchor-row layout of the edges / tets (whole-part sweeps)
+  bool legacy_sweep;     // MAG_LEGACY_SWEEP=1: whole-part sweeps run the round-1 tile kernels (A/B measurements)
+  unsigned long long* d_vstat; // [1] eigen-solver failures of the cached per-vertex pass (folded into every sweep's statistics)
   size_t cap_vedge, cap_ma, cap_mb;
+
+  std::map<const void*, int> occupancy; // resident blocks per SM of the persistent kernels (queried once per context)
 
   // last sweep parameters (for the near-threshold fix-up and getters)
   uint32_t last_ops;

@@ -160,13 +160,13 @@ __device__ __forceinline__ void vertex_pass_one(int64_t v, int dim, const double
 }
 template <int KIND>
 __global__ void k_vertex_pass(int64_t nv, int dim, const double* __restrict__ vedge, double* __restrict__ vpos,
-                              double* __restrict__ vq, MagDevStats* st)
+                              double* __restrict__ vq, unsigned long long* eig_fail)
 {
   int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (v >= nv) return;
   int eig = 0;
   vertex_pass_one<KIND>(v, dim, vedge, vpos, vq, &eig);
-  if (eig) atomicAdd(&st->n_eigen_fail, 1ull);
+  if (eig) atomicAdd(eig_fail, 1ull);
 }
 
 // ------------------------------------------------------------------ edge metric length
@@ -1047,12 +1047,14 @@ __global__ void k_layer(int64_t np, int64_t npy, int64_t nv, const int32_t* __re
 }
 
 // ------------------------------------------------------------------ misc
-__global__ void k_init_stats(MagDevStats* st)
+// vstat: eigen-solver failures of the cached per-vertex pass; they belong to every sweep that uses those transforms
+__global__ void k_init_stats(MagDevStats* st, const unsigned long long* vstat)
 {
   MagDevStats z;
   memset(&z, 0, sizeof(z));
   z.max_len_bits = 0;                 // bits of +0.0 : getMaximumEdgeLength starts at 0.0
   z.min_q_key = dkey(1.0);            // getMinQuality starts at 1
+  z.n_eigen_fail = vstat ? *vstat : 0ull;
   *st = z;
 }
 // fixed-order tree sum of the per-block partials (deterministic for a given grid)
@@ -1104,6 +1106,8 @@ k_check_conn(int64_t n, int32_t* __restrict__ conn, int32_t nv, unsigned long lo
 }
 
 inline unsigned grid_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
+
+#include "mag_rows.cuh"
 
 } // namespace
 
@@ -1168,25 +1172,30 @@ int magk_fold_owned(mag_ctx* c)
 
 int magk_init_stats(mag_ctx* c)
 {
-  k_init_stats<<<1, 1, 0, c->stream>>>(c->d_stats);
+  k_init_stats<<<1, 1, 0, c->stream>>>(c->d_stats, c->vertex_pass_valid ? c->d_vstat : nullptr);
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;
   return MAG_OK;
 }
 
+// Q_v and det Q_v of every vertex (strict arithmetic in both modes).  They depend on the coordinates and the size field
+// only, so they are computed when either changes (repack in mag_api.cu, mag_sweep_host) and reused by every sweep,
+// cavity batch and sliver classification until the next change; eigen-solver failures are kept in c->d_vstat.
 int magk_vertex_pass(mag_ctx* c)
 {
   if (c->nv == 0) return MAG_OK;
+  MAG_CUDA(c, cudaMemsetAsync(c->d_vstat, 0, sizeof(unsigned long long), c->stream));
   unsigned g = grid_for(c->nv);
   switch (c->kind) {
-    case MAG_KIND_IDENTITY: k_vertex_pass<MAG_KIND_IDENTITY><<<g, kThreads, 0, c->stream>>>(c->nv, c->dim, c->d_vedge, c->d_vpos, c->d_vq, c->d_stats); break;
-    case MAG_KIND_ISO: k_vertex_pass<MAG_KIND_ISO><<<g, kThreads, 0, c->stream>>>(c->nv, c->dim, c->d_vedge, c->d_vpos, c->d_vq, c->d_stats); break;
-    case MAG_KIND_ANISO: k_vertex_pass<MAG_KIND_ANISO><<<g, kThreads, 0, c->stream>>>(c->nv, c->dim, c->d_vedge, c->d_vpos, c->d_vq, c->d_stats); break;
-    case MAG_KIND_LOGM: k_vertex_pass<MAG_KIND_LOGM><<<g, kThreads, 0, c->stream>>>(c->nv, c->dim, c->d_vedge, c->d_vpos, c->d_vq, c->d_stats); break;
+    case MAG_KIND_IDENTITY: k_vertex_pass<MAG_KIND_IDENTITY><<<g, kThreads, 0, c->stream>>>(c->nv, c->dim, c->d_vedge, c->d_vpos, c->d_vq, c->d_vstat); break;
+    case MAG_KIND_ISO: k_vertex_pass<MAG_KIND_ISO><<<g, kThreads, 0, c->stream>>>(c->nv, c->dim, c->d_vedge, c->d_vpos, c->d_vq, c->d_vstat); break;
+    case MAG_KIND_ANISO: k_vertex_pass<MAG_KIND_ANISO><<<g, kThreads, 0, c->stream>>>(c->nv, c->dim, c->d_vedge, c->d_vpos, c->d_vq, c->d_vstat); break;
+    case MAG_KIND_LOGM: k_vertex_pass<MAG_KIND_LOGM><<<g, kThreads, 0, c->stream>>>(c->nv, c->dim, c->d_vedge, c->d_vpos, c->d_vq, c->d_vstat); break;
     default: return mag_fail(c, MAG_ERR_ARG, "no size field set");
   }
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;
+  c->vertex_pass_valid = true;
   return MAG_OK;
 }
 
@@ -1204,11 +1213,18 @@ static int launch_tris(mag_ctx* c, const SweepParams& P, bool fast)
 }
 
 // persistent grids: resident blocks per SM x number of SMs (queried once per context)
-static unsigned persistent_grid(mag_ctx* c, int& per_sm, const void* kernel, int64_t n, int threads, int chunk)
+static int blocks_per_sm(mag_ctx* c, const void* kernel, int threads)
 {
-  if (per_sm < 1 &&
-      (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1))
-    per_sm = 1;
+  auto it = c->occupancy.find(kernel);
+  if (it != c->occupancy.end()) return it->second;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  c->occupancy[kernel] = per_sm;
+  return per_sm;
+}
+static unsigned persistent_grid(mag_ctx* c, const void* kernel, int64_t n, int threads, int chunk)
+{
+  const int per_sm = blocks_per_sm(c, kernel, threads);
   int64_t g = (int64_t)per_sm * c->n_sms;
   const int64_t chunks = (n + chunk - 1) / chunk;
   if (g > chunks) g = chunks;
@@ -1237,11 +1253,10 @@ struct Range { int64_t first, n; bool whole; };
 template <int KIND, bool FAST, bool VERT>
 static int launch_edges_t(mag_ctx* c, const SweepParams& P, const Range& r)
 {
-  static int per_sm = 0;
   constexpr int kEdgeThreads = EdgeCfg<KIND, FAST>::T;
   // the grid is sized for the edge chunks plus, with VERT, the vertex chunks that ride along
   const int64_t work = r.n + (VERT ? (c->nv + kVertChunk - 1) / kVertChunk * (int64_t)kEdgeChunk : 0);
-  const unsigned g = persistent_grid(c, per_sm, (const void*)k_edges<KIND, FAST, VERT>, work, kEdgeThreads, kEdgeChunk);
+  const unsigned g = persistent_grid(c, (const void*)k_edges<KIND, FAST, VERT>, work, kEdgeThreads, kEdgeChunk);
   const VertArgs V{(int32_t)c->nv, c->dim, c->d_vpos, c->d_vq};
   k_edges<KIND, FAST, VERT><<<g, kEdgeThreads, 0, c->stream>>>((int32_t)r.n, reinterpret_cast<const int2*>(c->d_edge_v) + r.first, c->d_vedge,
                                                                c->d_edge_flags + r.first, c->d_len + r.first, edge_params(P, r.whole && c->edge_flags_zero), c->d_stats,
@@ -1276,9 +1291,8 @@ static TetParams tet_params(const SweepParams& P, bool zero_in)
 template <int KIND, bool FAST, bool USE_MAX>
 static int launch_tets_t(mag_ctx* c, const SweepParams& P, const Range& r)
 {
-  static int per_sm = 0;
   constexpr int kTetThreads = TetCfg<FAST>::T;
-  const unsigned g = persistent_grid(c, per_sm, (const void*)k_tets<KIND, FAST, USE_MAX>, r.n, kTetThreads, kTetChunk);
+  const unsigned g = persistent_grid(c, (const void*)k_tets<KIND, FAST, USE_MAX>, r.n, kTetThreads, kTetChunk);
   k_tets<KIND, FAST, USE_MAX><<<g, kTetThreads, 0, c->stream>>>((int32_t)r.n, (int32_t)(c->np + c->npy + r.first), c->nv,
                                                                  reinterpret_cast<const int4*>(c->d_tet_v) + r.first,
                                                                  c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_flags, c->d_qual, tet_params(P, r.whole && c->elem_flags_zero),
@@ -1359,49 +1373,219 @@ int magk_length_sum(mag_ctx* c)
 }
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 namespace {
 __global__ void k_iota(int64_t n, int32_t* __restrict__ out)
 {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) out[i] = (int32_t)i;
 }
+// export-time temporaries: freed on every exit path
+struct Scratch {
+  std::vector<void*> ptrs;
+  ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+  template <class T> cudaError_t get(T*& p, size_t count)
+  {
+    p = nullptr;
+    cudaError_t e = cudaMalloc((void**)&p, (count ? count : 1) * sizeof(T));
+    if (e == cudaSuccess) ptrs.push_back(p);
+    return e;
+  }
+};
+int bits_for(int64_t n) { int b = 1; while (b < 31 && ((int64_t)1 << b) <= n) ++b; return b; }
+int sort_pairs(mag_ctx* c, Scratch& S, const int32_t* k_in, int32_t* k_out, const int32_t* v_in, int32_t* v_out, int64_t n, int end_bit)
+{
+  size_t tmp_bytes = 0;
+  void* d_tmp = nullptr;
+  MAG_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, v_out, (int)n, 0, end_bit, c->stream));
+  MAG_CUDA(c, S.get(reinterpret_cast<char*&>(d_tmp), tmp_bytes));
+  MAG_CUDA(c, cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, k_in, k_out, v_in, v_out, (int)n, 0, end_bit, c->stream));
+  return MAG_OK;
+}
+int exclusive_scan(mag_ctx* c, Scratch& S, const int32_t* in, int32_t* out, int64_t n)
+{
+  size_t tmp_bytes = 0;
+  void* d_tmp = nullptr;
+  MAG_CUDA(c, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, (int)n, c->stream));
+  MAG_CUDA(c, S.get(reinterpret_cast<char*&>(d_tmp), tmp_bytes));
+  MAG_CUDA(c, cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, in, out, (int)n, c->stream));
+  return MAG_OK;
+}
+void free_rows(MagRows& r)
+{
+  cudaFree(r.d_anchor); cudaFree(r.d_slice_off); cudaFree(r.d_slots);
+  r.d_anchor = r.d_slice_off = r.d_slots = nullptr;
+  r.n_rows = r.n_slices = r.n_slots = 0;
+  r.valid = false;
+}
 } // namespace
-// builds c->d_edge_order / c->d_tet_order: chunk (tile) indices sorted by key on the device (LSD radix sort is stable, so
-// equal keys keep the caller's order); nothing travels to the host
+// builds c->d_edge_order / c->d_tet_order (legacy tile kernels): chunk (tile) indices sorted by key on the device (LSD radix
+// sort is stable, so equal keys keep the caller's order); nothing travels to the host
 static int build_order(mag_ctx* c, int64_t n, int64_t chunk_len, const int32_t* d_conn, int nv_per, int32_t*& d_order, int64_t& n_chunks)
 {
   n_chunks = (n + chunk_len - 1) / chunk_len;
   if (d_order) { MAG_CUDA(c, cudaFree(d_order)); d_order = nullptr; }
   if (n_chunks == 0) return MAG_OK;
+  Scratch S;
   int32_t *d_keys = nullptr, *d_keys_out = nullptr, *d_idx = nullptr;
-  void* d_tmp = nullptr;
-  size_t tmp_bytes = 0;
-  MAG_CUDA(c, cudaMalloc((void**)&d_keys, (size_t)n_chunks * 4));
-  MAG_CUDA(c, cudaMalloc((void**)&d_keys_out, (size_t)n_chunks * 4));
-  MAG_CUDA(c, cudaMalloc((void**)&d_idx, (size_t)n_chunks * 4));
+  MAG_CUDA(c, S.get(d_keys, (size_t)n_chunks));
+  MAG_CUDA(c, S.get(d_keys_out, (size_t)n_chunks));
+  MAG_CUDA(c, S.get(d_idx, (size_t)n_chunks));
   MAG_CUDA(c, cudaMalloc((void**)&d_order, (size_t)n_chunks * 4));
   if (nv_per == 2) k_chunk_keys<2><<<(unsigned)n_chunks, kThreads, 0, c->stream>>>(n, chunk_len, d_conn, d_keys);
   else k_chunk_keys<4><<<(unsigned)n_chunks, kThreads, 0, c->stream>>>(n, chunk_len, d_conn, d_keys);
   k_iota<<<grid_for(n_chunks), kThreads, 0, c->stream>>>(n_chunks, d_idx);
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches += 2;
-  MAG_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys_out, d_idx, d_order, (int)n_chunks, 0, 31, c->stream));
-  MAG_CUDA(c, cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
-  MAG_CUDA(c, cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys_out, d_idx, d_order, (int)n_chunks, 0, 31, c->stream));
+  int rc = sort_pairs(c, S, d_keys, d_keys_out, d_idx, d_order, n_chunks, 31);
+  if (rc) return rc;
   MAG_CUDA(c, cudaStreamSynchronize(c->stream));
-  MAG_CUDA(c, cudaFree(d_tmp));
-  MAG_CUDA(c, cudaFree(d_idx));
-  MAG_CUDA(c, cudaFree(d_keys_out));
-  MAG_CUDA(c, cudaFree(d_keys));
   return MAG_OK;
 }
+
+// the anchor-row layout of one entity dimension (mag_rows.cuh), built on the device from the resident connectivity
+// (ownership already folded into the sign bit of the first vertex id)
+template <int NV>
+static int build_rows(mag_ctx* c, int64_t n, const int32_t* d_conn, MagRows& rows)
+{
+  free_rows(rows);
+  if (n == 0 || c->nv == 0) { rows.valid = true; return MAG_OK; }
+  const int64_t nv = c->nv;
+  Scratch S;
+  int32_t *key = nullptr, *val = nullptr, *key2 = nullptr, *sorted_e = nullptr, *deg = nullptr, *start = nullptr, *nrows = nullptr, *rowstart = nullptr;
+  MAG_CUDA(c, S.get(key, (size_t)n));
+  MAG_CUDA(c, S.get(val, (size_t)n));
+  MAG_CUDA(c, S.get(key2, (size_t)n));
+  MAG_CUDA(c, S.get(sorted_e, (size_t)n));
+  MAG_CUDA(c, S.get(deg, (size_t)nv + 1));
+  MAG_CUDA(c, S.get(start, (size_t)nv + 1));
+  MAG_CUDA(c, S.get(nrows, (size_t)nv + 1));
+  MAG_CUDA(c, S.get(rowstart, (size_t)nv + 1));
+  MAG_CUDA(c, cudaMemsetAsync(deg, 0, ((size_t)nv + 1) * 4, c->stream));
+  k_row_keys<NV><<<grid_for(n), kThreads, 0, c->stream>>>(n, d_conn, key, val, deg);
+  MAG_CUDA(c, cudaGetLastError());
+  int rc;
+  if ((rc = sort_pairs(c, S, key, key2, val, sorted_e, n, bits_for(nv)))) return rc;
+  if ((rc = exclusive_scan(c, S, deg, start, nv + 1))) return rc;
+  k_row_counts<<<grid_for(nv + 1), kThreads, 0, c->stream>>>(nv, deg, nrows);
+  MAG_CUDA(c, cudaGetLastError());
+  if ((rc = exclusive_scan(c, S, nrows, rowstart, nv + 1))) return rc;
+  int32_t n_rows32 = 0;
+  MAG_CUDA(c, cudaMemcpyAsync(&n_rows32, rowstart + nv, 4, cudaMemcpyDeviceToHost, c->stream));
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  const int64_t R = n_rows32, nslices = (R + 31) / 32, Rpad = nslices * 32;
+  int32_t *row_anchor = nullptr, *row_len = nullptr, *row_first = nullptr, *rkey = nullptr, *ridx = nullptr, *rkey2 = nullptr, *order = nullptr;
+  MAG_CUDA(c, S.get(row_anchor, (size_t)R));
+  MAG_CUDA(c, S.get(row_len, (size_t)R));
+  MAG_CUDA(c, S.get(row_first, (size_t)R));
+  MAG_CUDA(c, S.get(rkey, (size_t)R));
+  MAG_CUDA(c, S.get(ridx, (size_t)R));
+  MAG_CUDA(c, S.get(rkey2, (size_t)R));
+  MAG_CUDA(c, S.get(order, (size_t)R));
+  k_row_records<<<grid_for(nv), kThreads, 0, c->stream>>>(nv, deg, start, rowstart, row_anchor, row_len, row_first, rkey, ridx);
+  MAG_CUDA(c, cudaGetLastError());
+  if ((rc = sort_pairs(c, S, rkey, rkey2, ridx, order, R, bits_for(nv >> kRowWindowLog2) + 6))) return rc;
+  MAG_CUDA(c, cudaMalloc((void**)&rows.d_slice_off, ((size_t)nslices + 1) * 4));
+  MAG_CUDA(c, cudaMalloc((void**)&rows.d_anchor, (size_t)Rpad * 4));
+  int32_t* width32 = nullptr;
+  MAG_CUDA(c, S.get(width32, (size_t)nslices + 1));
+  k_slice_width<<<grid_for((nslices + 1) * 32), kThreads, 0, c->stream>>>(R, nslices, order, row_len, width32);
+  MAG_CUDA(c, cudaGetLastError());
+  if ((rc = exclusive_scan(c, S, width32, rows.d_slice_off, nslices + 1))) return rc;
+  // the scan runs in int32: check the total in 64 bits on the host side of the widths (each <= 32 * kRowMax)
+  int32_t n_slots32 = 0;
+  MAG_CUDA(c, cudaMemcpyAsync(&n_slots32, rows.d_slice_off + nslices, 4, cudaMemcpyDeviceToHost, c->stream));
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (n_slots32 < 0 || (int64_t)n_slots32 < n) {
+    free_rows(rows);
+    return mag_fail(c, MAG_ERR_ARG, "row layout: slot count overflows int32 (%lld entities)", (long long)n);
+  }
+  const int64_t n_slots = n_slots32;
+  MAG_CUDA(c, cudaMalloc((void**)&rows.d_slots, (size_t)n_slots * NV * 4));
+  MAG_CUDA(c, cudaMemsetAsync(rows.d_slots, 0xFF, (size_t)n_slots * NV * 4, c->stream));
+  k_slots_fill<NV><<<grid_for(Rpad), kThreads, 0, c->stream>>>(R, Rpad, order, row_anchor, row_len, row_first, sorted_e, d_conn,
+                                                               rows.d_slice_off, rows.d_anchor, rows.d_slots);
+  MAG_CUDA(c, cudaGetLastError());
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->n_launches += 5;
+  rows.n_rows = R;
+  rows.n_slices = nslices;
+  rows.n_slots = n_slots;
+  rows.valid = true;
+  return MAG_OK;
+}
+
+void magk_free_rows(mag_ctx* c) { free_rows(c->erows); free_rows(c->trows); }
+
 int magk_build_schedule(mag_ctx* c)
 {
   int rc;
-  int64_t nch;
-  if ((rc = build_order(c, c->ne, MAG_EDGE_TILE_SCHED ? (int64_t)kStrictThreads : (int64_t)kEdgeChunk, c->d_edge_v, 2, c->d_edge_order, nch))) return rc;
-  if ((rc = build_order(c, c->nt, (int64_t)kTetChunk, c->d_tet_v, 4, c->d_tet_order, nch))) return rc;
+  if (c->legacy_sweep) {
+    int64_t nch;
+    if ((rc = build_order(c, c->ne, MAG_EDGE_TILE_SCHED ? (int64_t)kStrictThreads : (int64_t)kEdgeChunk, c->d_edge_v, 2, c->d_edge_order, nch))) return rc;
+    if ((rc = build_order(c, c->nt, (int64_t)kTetChunk, c->d_tet_v, 4, c->d_tet_order, nch))) return rc;
+    return MAG_OK;
+  }
+  if ((rc = build_rows<2>(c, c->ne, c->d_edge_v, c->erows))) return rc;
+  if ((rc = build_rows<4>(c, c->nt, c->d_tet_v, c->trows))) return rc;
   return MAG_OK;
+}
+
+// ---- whole-part sweeps over the anchor rows
+template <int KIND, bool FAST>
+static int launch_edge_rows_t(mag_ctx* c, const SweepParams& P)
+{
+  constexpr int T = EdgeRowCfg<KIND, FAST>::T;
+  const int per_sm = blocks_per_sm(c, (const void*)k_edge_rows<KIND, FAST>, T);
+  int64_t g = (int64_t)per_sm * c->n_sms;
+  const int64_t need = (c->erows.n_slices + T / 32 - 1) / (T / 32);
+  if (g > need) g = need;
+  k_edge_rows<KIND, FAST><<<(unsigned)(g < 1 ? 1 : g), T, 0, c->stream>>>(
+      (int32_t)c->erows.n_slices, c->erows.d_anchor, c->erows.d_slice_off, reinterpret_cast<const int2*>(c->erows.d_slots), c->d_vedge,
+      c->d_edge_flags, c->d_len, edge_params(P, c->edge_flags_zero), c->d_stats, c->d_near_edge);
+  MAG_CUDA(c, cudaGetLastError());
+  c->n_launches++;
+  return MAG_OK;
+}
+static int launch_edge_rows(mag_ctx* c, const SweepParams& P, bool fast)
+{
+  switch (c->kind) {
+    case MAG_KIND_IDENTITY: return fast ? launch_edge_rows_t<MAG_KIND_IDENTITY, true>(c, P) : launch_edge_rows_t<MAG_KIND_IDENTITY, false>(c, P);
+    case MAG_KIND_ISO: return fast ? launch_edge_rows_t<MAG_KIND_ISO, true>(c, P) : launch_edge_rows_t<MAG_KIND_ISO, false>(c, P);
+    case MAG_KIND_ANISO: return fast ? launch_edge_rows_t<MAG_KIND_ANISO, true>(c, P) : launch_edge_rows_t<MAG_KIND_ANISO, false>(c, P);
+    default: return fast ? launch_edge_rows_t<MAG_KIND_LOGM, true>(c, P) : launch_edge_rows_t<MAG_KIND_LOGM, false>(c, P);
+  }
+}
+template <int KIND, bool FAST, bool USE_MAX>
+static int launch_tet_rows_t(mag_ctx* c, const SweepParams& P)
+{
+  constexpr int T = TetRowCfg<FAST>::T;
+  const int per_sm = blocks_per_sm(c, (const void*)k_tet_rows<KIND, FAST, USE_MAX>, T);
+  int64_t g = (int64_t)per_sm * c->n_sms;
+  const int64_t need = (c->trows.n_slices + T / 32 - 1) / (T / 32);
+  if (g > need) g = need;
+  k_tet_rows<KIND, FAST, USE_MAX><<<(unsigned)(g < 1 ? 1 : g), T, 0, c->stream>>>(
+      (int32_t)c->trows.n_slices, c->trows.d_anchor, c->trows.d_slice_off, reinterpret_cast<const int4*>(c->trows.d_slots),
+      (int32_t)(c->np + c->npy), c->nv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_flags, c->d_qual, tet_params(P, c->elem_flags_zero),
+      c->d_stats, c->d_near_elem);
+  MAG_CUDA(c, cudaGetLastError());
+  c->n_launches++;
+  return MAG_OK;
+}
+template <int KIND>
+static int launch_tet_rows_k(mag_ctx* c, const SweepParams& P, bool fast)
+{
+  if (P.use_max) return fast ? launch_tet_rows_t<KIND, true, true>(c, P) : launch_tet_rows_t<KIND, false, true>(c, P);
+  return fast ? launch_tet_rows_t<KIND, true, false>(c, P) : launch_tet_rows_t<KIND, false, false>(c, P);
+}
+static int launch_tet_rows(mag_ctx* c, const SweepParams& P, bool fast)
+{
+  switch (c->kind) {
+    case MAG_KIND_IDENTITY: return launch_tet_rows_k<MAG_KIND_IDENTITY>(c, P, fast);
+    case MAG_KIND_ISO: return launch_tet_rows_k<MAG_KIND_ISO>(c, P, fast);
+    case MAG_KIND_ANISO: return launch_tet_rows_k<MAG_KIND_ANISO>(c, P, fast);
+    default: return launch_tet_rows_k<MAG_KIND_LOGM>(c, P, fast);
+  }
 }
 
 int magk_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double good_q, int use_max, int fp_mode)
@@ -1412,17 +1596,11 @@ int magk_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double 
   cudaEvent_t* tev = (c->t_used < c->t_slots) ? &c->tev[(size_t)4 * c->t_used] : nullptr;
   if (tev) MAG_CUDA(c, cudaEventRecord(tev[0], c->stream));
   const bool need_vertex = ops & (MAG_OP_QUALITIES | MAG_OP_MARK_BAD | MAG_OP_LAYER_CHECK);
-  const bool do_edges = c->ne && (ops & (MAG_OP_LENGTHS | MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE));
-  // per-vertex transforms are part of every quality sweep (never cached across sweeps); in a fast sweep that also
-  // measures the edges they ride in the edge kernel's launch (k_edges<.., VERT>)
-  const bool fuse_vertex = MAG_FUSE_VERTEX && need_vertex && do_edges && fast && c->nv && c->kind != MAG_KIND_LOGM;
-  if (need_vertex) {
-    if (!fuse_vertex && (rc = magk_vertex_pass(c))) return rc;
-    c->vertex_pass_valid = true;   // cavity batches between two exports reuse them (mag_cavity_quality)
-  }
+  // the per-vertex transforms are normally in place (computed when the coordinates or the size field were set)
+  if (need_vertex && !c->vertex_pass_valid && (rc = magk_vertex_pass(c))) return rc;
   if (tev) MAG_CUDA(c, cudaEventRecord(tev[1], c->stream));
   if (c->ne && (ops & (MAG_OP_LENGTHS | MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE))) {
-    if ((rc = launch_edges_kind(c, P, fast, Range{0, c->ne, true}, fuse_vertex))) return rc;
+    if ((rc = c->legacy_sweep ? launch_edges_kind(c, P, fast, Range{0, c->ne, true}, false) : launch_edge_rows(c, P, fast))) return rc;
     // a requested mark writes the flag word of EVERY edge when the incoming words are zero (nothing is skipped)
     if (ops & (MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE)) c->edge_flags_zero = false;
     if ((ops & MAG_OP_LENGTH_SUM) && (rc = magk_length_sum(c))) return rc;
@@ -1432,7 +1610,7 @@ int magk_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double 
     // only the tet kernel understands "all zero, not materialised" (it then writes every word it marks)
     if ((c->ntri || c->np + c->npy) && (rc = magi_materialize_flags(c))) return rc;
     if (c->nt) {
-      if ((rc = launch_tets_kind(c, P, fast, Range{0, c->nt, true}))) return rc;
+      if ((rc = c->legacy_sweep ? launch_tets_kind(c, P, fast, Range{0, c->nt, true}) : launch_tet_rows(c, P, fast))) return rc;
       if (ops & MAG_OP_MARK_BAD) c->elem_flags_zero = false;
     }
     if (c->ntri) {

@@ -311,6 +311,18 @@ class Part:
     def launch_count(self):
         return int(self._L.mag_launch_count(self._h))
 
+    def row_layout(self, which):
+        """The anchor-row device layout of the edges (which = 0) or tets (1): dict(rows, slices, slots, anchor [32*slices],
+        slice_off [slices+1], slot [slots, 2 or 4]) -- see mag_get_row_layout / core_b200/csrc/mag_rows.cuh."""
+        counts = np.zeros(3, np.int64)
+        self._ck(self._L.mag_get_row_layout(self._h, int(which), _ptr(counts), None, None, None))
+        rows, slices, slots = (int(x) for x in counts)
+        anchor = np.empty(32 * slices, np.int32)
+        off = np.empty(slices + 1 if slices else 0, np.int32)
+        sl = np.empty((slots, 4 if which else 2), np.int32)
+        self._ck(self._L.mag_get_row_layout(self._h, int(which), _ptr(counts), _ptr(anchor), _ptr(off), _ptr(sl)))
+        return dict(rows=rows, slices=slices, slots=slots, anchor=anchor, slice_off=off, slot=sl)
+
     # ---- the reference's entry points, same names and meaning
     def markEdgesToSplit(self, fp_mode=FP_STRICT):          # ma/maRefine.cc:395-400
         self.sweep(OP_MARK_SPLIT, fp_mode=fp_mode)

@@ -254,6 +254,13 @@ int mag_timing_begin(mag_ctx* c, int max_sweeps);
 int mag_timing_read(mag_ctx* c, float* ms /*[max_sweeps][3]*/, int* n_out);
 /* number of CUDA kernels this context has launched so far */
 int64_t mag_launch_count(const mag_ctx* c);
+/* The device layout the whole-part sweeps run over (diagnostics and tests; built by mag_set_mesh, or by the first mag_sweep
+   after mag_sweep_host): every edge (which = 0) / tet (which = 1) is filed under its first vertex, the anchor; rows of one
+   anchor's entities are cut into slices of 32 rows stored slot-major (see core_b200/csrc/mag_rows.cuh).
+   counts[3] = {rows, slices, slots}; anchor [32 * slices] (-1 = padding row); slice_off [slices + 1];
+   slots [slots][2] = {other vertex | not-owned << 31, edge index} or [slots][4] = {v1 | not-owned << 31, v2, v3, tet index},
+   index -1 = empty slot.  Array pointers may be NULL (counts only). */
+int mag_get_row_layout(mag_ctx* c, int which, int64_t* counts, int32_t* anchor, int32_t* slice_off, int32_t* slots);
 
 /* ---- multi-GPU: one part per GPU, NCCL over NVLink (replaces PCU on this path only) ---- */
 #define MAG_UNIQUE_ID_BYTES 128

@@ -366,6 +366,99 @@ def test_random_box_vs_oracle(cb, kindname):
     p.close()
 
 
+def _shuffled_hub_mesh(cb, rng, n=9):
+    """A jittered box whose entities arrive in an order and orientation unrelated to the vertex numbering (what an
+    unstructured mesh looks like to the row layout), plus a hub: vertex 0 is made the FIRST vertex of 100 extra edges and 70
+    extra tets, so its rows must be cut (kRowMax = 32 in mag_rows.cuh)."""
+    xyz, ev, tv = cb.boxmesh.kuhn_box(n, n, n + 1)
+    xyz = cb.fields.jitter(xyz, 0.3 / n)
+    nv = len(xyz)
+    hub_e = np.stack([np.zeros(100, np.int64), rng.choice(np.arange(1, nv), 100, replace=False)], axis=1)
+    hub_t = np.concatenate([np.zeros((70, 1), np.int64), np.stack([rng.choice(np.arange(1, nv), 3, replace=False) for _ in range(70)])], axis=1)
+    flip = rng.random(len(ev)) < 0.5                       # box entities: random first vertex; hub entities keep vertex 0 first
+    ev[flip] = ev[flip][:, ::-1]
+    rot = rng.integers(0, 3, len(tv))                      # even permutations keep the orientation
+    even = np.array([[0, 1, 2, 3], [1, 2, 0, 3], [3, 0, 2, 1]])
+    tv = np.take_along_axis(tv, even[rot], axis=1)
+    ev = np.concatenate([ev, hub_e]).astype(np.int32)
+    tv = np.concatenate([tv, hub_t]).astype(np.int32)
+    ev = np.ascontiguousarray(ev[rng.permutation(len(ev))])
+    tv = np.ascontiguousarray(tv[rng.permutation(len(tv))])
+    return xyz, ev, tv
+
+
+def test_row_layout_invariants(cb):
+    """mag_get_row_layout: every entity sits in exactly one slot, under its first vertex, with its other vertices in the
+    caller's order and its ownership bit; slices are as wide as their longest row; no row is longer than 32."""
+    rng = np.random.default_rng(5)
+    xyz, ev, tv = _shuffled_hub_mesh(cb, rng)
+    eo = (rng.random(len(ev)) < 0.8).astype(np.uint8)
+    lo = (rng.random(len(tv)) < 0.8).astype(np.uint8)
+    p = cb.Part(0)
+    p.set_mesh(xyz, ev, tv, edge_owned=eo, elem_owned=lo)
+    for which, conn, owned in ((0, ev, eo), (1, tv, lo)):
+        lay = p.row_layout(which)
+        sl, off, anchor = lay["slot"], lay["slice_off"], lay["anchor"]
+        assert lay["slots"] == off[-1] and lay["slices"] == (lay["rows"] + 31) // 32
+        ids = sl[:, -1]
+        used = np.nonzero(ids >= 0)[0]
+        assert np.array_equal(np.sort(ids[used]), np.arange(len(conn))), "every entity exactly once"
+        slice_of = np.searchsorted(off, used, side="right") - 1
+        lane = (used - off[slice_of]) % 32
+        a = anchor[32 * slice_of + lane]
+        e = ids[used]
+        assert np.array_equal(a, conn[e, 0]), "filed under the first vertex"
+        assert np.array_equal(sl[used, 0] & 0x7fffffff, conn[e, 1])
+        assert np.array_equal((sl[used, 0] >= 0).astype(np.uint8), owned[e])
+        if which:
+            assert np.array_equal(sl[used, 1], conn[e, 2]) and np.array_equal(sl[used, 2], conn[e, 3])
+        width = np.diff(off) // 32
+        assert width.min() >= 1 and width.max() <= 32
+        k = (used - off[slice_of]) // 32
+        assert np.array_equal(np.bincount(slice_of, minlength=lay["slices"]) > 0, np.ones(lay["slices"], bool))
+        assert np.array_equal(np.maximum.reduceat(k[np.argsort(slice_of, kind="stable")],
+                                                  np.searchsorted(np.sort(slice_of), np.arange(lay["slices"]))) + 1, width)
+        # an anchor's entities keep the caller's order along its row(s)
+        hub = np.nonzero(a == 0)[0]
+        assert len(hub) >= (100 if which == 0 else 70)
+        rows_hub = len(set(zip(slice_of[hub].tolist(), lane[hub].tolist())))
+        assert rows_hub >= (4 if which == 0 else 3)
+    p.close()
+
+
+@pytest.mark.parametrize("kindname", ["iso", "aniso", "logm"])
+def test_shuffled_hub_mesh_vs_oracle(cb, kindname):
+    """The whole sweep on a mesh whose entity order and orientation are unrelated to the vertex numbering."""
+    from oracle import mao
+    rng = np.random.default_rng(6)
+    xyz, ev, tv = _shuffled_hub_mesh(cb, rng)
+    nv = len(xyz)
+    R = util.random_frames(nv, rng)
+    H = (1.0 / 9) * np.exp(rng.uniform(-1.0, 1.0, (nv, 3)))
+    s = (1.0 / 9) * np.exp(rng.uniform(-1, 1, nv))
+    kind, ma, mb = {"iso": (mao.ISO, s, None), "aniso": (mao.ANISO, H, R), "logm": (mao.LOGM, None, mao.logm_from_frames(H, R, 0))}[kindname]
+    ef = np.zeros(len(ev), np.int32)
+    lf = np.zeros(len(tv), np.int32)
+    ef[rng.random(len(ev)) < 0.2] |= cb.DONT_SPLIT
+    ef[rng.random(len(ev)) < 0.2] |= cb.NEED_NOT_COLLAPSE
+    lf[rng.random(len(tv)) < 0.3] |= cb.OK_QUALITY
+    eo = (rng.random(len(ev)) < 0.9).astype(np.uint8)
+    lo = (rng.random(len(tv)) < 0.9).astype(np.uint8)
+    want = util.oracle_sweep(kind, xyz, ma, mb, ev, tv, ef, lf, eo, lo, good_quality=0.1)
+    p = cb.Part(0)
+    p.set_mesh(xyz, ev, tv, edge_owned=eo, elem_owned=lo)
+    util.set_part_metric(p, kind, ma, mb)
+    for mode in (cb.FP_STRICT, cb.FP_FAST):
+        p.set_flags(ef, lf)
+        p.sweep(cb.OP_ALL & ~cb.OP_LAYER_CHECK, good_quality=0.1, fp_mode=mode)
+        check_against(cb, p, want, kind, mode)
+        p.clear_flags()                                   # and with the incoming words all zero (not materialised)
+        p.sweep(cb.OP_ALL & ~cb.OP_LAYER_CHECK, good_quality=0.1, fp_mode=mode)
+        want0 = util.oracle_sweep(kind, xyz, ma, mb, ev, tv, None, None, eo, lo, good_quality=0.1)
+        check_against(cb, p, want0, kind, mode)
+    p.close()
+
+
 def test_reference_named_entry_points(cb):
     """The host mirror's reference-named calls (markEdgesToSplit ... getMaximumEdgeLength) one at a time, and the
     second-sweep behaviour: NEED_NOT_* / OK_QUALITY set by the first sweep make the second one skip (maAdapt.cc:311)."""
