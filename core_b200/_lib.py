@@ -14,7 +14,7 @@ SYMBOLS = [
     "mag_create", "mag_destroy", "mag_last_error", "mag_set_stream", "mag_synchronize",
     "mag_set_mesh", "mag_set_mesh_2d", "mag_set_coords",
     "mag_set_metric_identity", "mag_set_metric_uniform_refiner", "mag_set_metric_iso", "mag_set_metric_aniso", "mag_set_metric_logm",
-    "mag_set_flags", "mag_clear_flag", "mag_sweep", "mag_sweep_host", "mag_element_weights", "mag_split_vertices", "mag_cavity_quality", "mag_short_edge_test",
+    "mag_set_flags", "mag_clear_flag", "mag_reset_layer", "mag_sweep", "mag_sweep_host", "mag_element_weights", "mag_split_vertices", "mag_cavity_quality", "mag_short_edge_test",
     "mag_sliver_codes", "mag_linear_qualities",
     "mag_get_edge_lengths", "mag_get_qualities", "mag_get_flags", "mag_get_layer_ok", "mag_get_stats",
     "mag_get_near_threshold", "mag_set_metric_logm_from_frames",
@@ -78,6 +78,7 @@ def lib():
     L.mag_set_metric_logm.argtypes = [vp, vp]
     L.mag_set_flags.argtypes = [vp, vp, vp]
     L.mag_clear_flag.argtypes = [vp, C.c_int, i32]
+    L.mag_reset_layer.argtypes = [vp, vp, C.POINTER(i64)]
     L.mag_sweep.argtypes = [vp, u32, f64, f64, f64, C.c_int, C.c_int]
     L.mag_sweep_host.argtypes = [vp, C.POINTER(MagHostPart), C.POINTER(MagHostResult), u32, f64, f64, f64, C.c_int, C.c_int,
                                  C.POINTER(MagStats)]

@@ -173,19 +173,28 @@ def slab_part(gnx, ny, nz, nparts, part, wx=1.0, wy=1.0, wz=1.0):
 
 
 # ---------------------------------------------------------------------------- mixed prism / tet boxes (config 5)
-def mixed_box(n, k, index_dtype=np.int32):
-    """n^3 cells: the bottom k cell layers are 2 prisms per cell, (0,1,2|4,5,6) and (0,2,3|4,6,7) -- conforming to
-    the 0-2 bottom diagonal of the Kuhn tets (apfBox.cc:250-256) -- and Kuhn tets above.  Returns
+def mixed_box(n, k, index_dtype=np.int32, ny=None, nz=None, x0=0, gnx=None, wx=1.0):
+    """n x ny x nz cells (default a cube): the bottom k cell layers are 2 prisms per cell, (0,1,2|4,5,6) and (0,2,3|4,6,7)
+    -- conforming to the 0-2 bottom diagonal of the Kuhn tets (apfBox.cc:250-256) -- and Kuhn tets above.  Returns
     (xyz, edge_v, tet_v, prism_v); edges are the unique vertex pairs of all elements sorted by (min, max) vertex
     (a mixed mesh cannot come from makeMdsBox, so there is no reference creation order to follow; the parity
-    fixtures of tests/golden use the order apf::buildElement produced)."""
-    s = n + 1
-    g = np.arange(s) / n
-    xyz = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).transpose(2, 1, 0, 3).reshape(-1, 3).copy()
-    cx, cy, cz = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
-    c0 = (cx + s * (cy + s * cz)).transpose(2, 1, 0).reshape(-1)
-    zc = cz.transpose(2, 1, 0).reshape(-1)
-    stride = np.array([1, s, s * s], dtype=np.int64)
+    fixtures of tests/golden use the order apf::buildElement produced).
+    x0 / gnx / wx: this box is the x-slab [x0, x0 + n] of a global box with gnx cells of total width wx along x (shared
+    vertices of neighbouring slabs get bit-identical coordinates, as in kuhn_box)."""
+    nx = n
+    ny = n if ny is None else ny
+    nz = n if nz is None else nz
+    gnx = nx if gnx is None else gnx
+    sx, sy, sz = nx + 1, ny + 1, nz + 1
+    xyz = np.empty((sz, sy, sx, 3), dtype=np.float64)
+    xyz[..., 0] = ((wx / gnx) * (np.arange(sx) + x0))[None, None, :]
+    xyz[..., 1] = (np.arange(sy) / ny)[None, :, None]
+    xyz[..., 2] = (np.arange(sz) / nz)[:, None, None]
+    xyz = xyz.reshape(-1, 3)
+    cz, cy, cx = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    c0 = (cx + sx * (cy + sy * cz)).reshape(-1)
+    zc = cz.reshape(-1)
+    stride = np.array([1, sx, sx * sy], dtype=np.int64)
     corner = c0[:, None] + (_CORNER @ stride)[None, :]
     lay = zc < k
     pc = corner[lay]
@@ -194,9 +203,41 @@ def mixed_box(n, k, index_dtype=np.int32):
     pairs = [tet_v[:, [a, b]] for a, b in ((0, 1), (1, 2), (2, 0), (0, 3), (1, 3), (2, 3))]
     pairs += [prism_v[:, [a, b]] for a, b in _PRISM_EDGES]
     e = np.sort(np.concatenate(pairs, axis=0), axis=1)
-    edge_v = np.unique(e, axis=0)
+    nv = sx * sy * sz
+    key = np.unique(e[:, 0].astype(np.int64) * nv + e[:, 1])     # sorted by (min, max)
+    edge_v = np.stack([key // nv, key % nv], axis=1)
     return (xyz, np.ascontiguousarray(edge_v.astype(index_dtype)), np.ascontiguousarray(tet_v.astype(index_dtype)),
             np.ascontiguousarray(prism_v.astype(index_dtype)))
+
+
+def mixed_slab_part(gnx, ny, nz, k, nparts, part, wx=1.0):
+    """One x-slab part of the global gnx x ny x nz mixed prism / tet box (BASELINE configs[4] on several GPUs).  Same contract
+    as slab_part: full copies of the entities in the cut planes, per-peer shared-edge lists in the same order on both sides
+    (sorted by the (y, z) grid ids of the two end vertices, which both parts see identically), owner = the part with the
+    fewest elements, ties -> lowest part id (apfPM.cc:109-126).
+    Returns dict(xyz, edge_v, tet_v, prism_v, edge_owned, links, x0, nx)."""
+    bounds = slab_bounds(gnx, nparts)
+    lo, hi = bounds[part]
+    nx = hi - lo
+    xyz, edge_v, tet_v, prism_v = mixed_box(nx, k, ny=ny, nz=nz, x0=lo, gnx=gnx, wx=wx)
+    sx = nx + 1
+    nelem = [(b[1] - b[0]) * ny * (2 * min(k, nz) + 6 * max(nz - k, 0)) for b in bounds]
+    a, b = edge_v[:, 0].astype(np.int64), edge_v[:, 1].astype(np.int64)
+    edge_owned = np.ones(len(edge_v), dtype=np.uint8)
+    links = []
+    for peer, plane in ((part - 1, 0), (part + 1, nx)):
+        if peer < 0 or peer >= nparts:
+            continue
+        idx = np.nonzero(((a % sx) == plane) & ((b % sx) == plane))[0]
+        ka, kb = a[idx] // sx, b[idx] // sx                    # y + (ny+1) z of each end: the same numbers on the peer
+        kmin, kmax = np.minimum(ka, kb), np.maximum(ka, kb)
+        idx = idx[np.lexsort((kmax, kmin))]
+        owner = part if (nelem[part], part) < (nelem[peer], peer) else peer
+        peer_owns = np.full(len(idx), 1 if owner == peer else 0, dtype=np.uint8)
+        if owner == peer:
+            edge_owned[idx] = 0
+        links.append((peer, np.ascontiguousarray(idx.astype(np.int32)), peer_owns))
+    return dict(xyz=xyz, edge_v=edge_v, tet_v=tet_v, prism_v=prism_v, edge_owned=edge_owned, links=links, x0=lo, nx=nx)
 
 
 # apf prism_edge_verts / pyramid_edge_verts (apf/apfMesh.cc:62-78)

@@ -157,6 +157,7 @@ int mag_create(mag_ctx** out, int device)
   c->trows = c->erows;
   { const char* e = getenv("MAG_LEGACY_SWEEP"); c->legacy_sweep = e && e[0] == '1'; }
   c->d_vstat = nullptr;
+  c->d_pair_keys = nullptr; c->d_pair_vals = nullptr; c->pair_bits = 0; c->d_layer_count = nullptr;
   c->d_near_edge = c->d_near_elem = nullptr;
   c->cap_vedge = c->cap_ma = c->cap_mb = 0;
   c->last_ops = 0; c->last_fp_mode = 0;
@@ -175,6 +176,7 @@ int mag_create(mag_ctx** out, int device)
   if ((e = cudaMalloc((void**)&c->d_block_sums, sizeof(double) * MAG_SUM_BLOCKS)) != cudaSuccess) return fail(e, "cudaMalloc block sums");
   if ((e = cudaMalloc((void**)&c->d_vstat, sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc vertex-pass counter");
   if ((e = cudaMemset(c->d_vstat, 0, sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMemset vertex-pass counter");
+  if ((e = cudaMalloc((void**)&c->d_layer_count, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc layer counters");
   if ((e = cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return fail(e, "SM count");
   int rc = magk_init_stats(c);
   if (rc) { g_create_err = c->err; delete c; return rc; }
@@ -194,7 +196,7 @@ void mag_destroy(mag_ctx* c)
   cudaFree(c->d_len); cudaFree(c->d_qual); cudaFree(c->d_weight); cudaFree(c->d_layer_ok); cudaFree(c->d_layer_codes);
   cudaFree(c->d_stats); cudaFreeHost(c->h_stats); cudaFree(c->d_block_sums);
   cudaFree(c->d_near_edge); cudaFree(c->d_near_elem); cudaFree(c->d_edge_order); cudaFree(c->d_tet_order);
-  magk_free_rows(c); cudaFree(c->d_vstat);
+  magk_free_rows(c); cudaFree(c->d_vstat); magl_free_pairs(c); cudaFree(c->d_layer_count);
   for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
   for (cudaEvent_t e : c->pipe_ev) cudaEventDestroy(e);
   if (c->s_up) cudaStreamDestroy(c->s_up);
@@ -230,6 +232,7 @@ int magi_reshape(mag_ctx* c, int dim, int64_t nv, int64_t ne, int64_t nt, int64_
   if (dim != c->dim) c->vertex_pass_valid = false;
   c->dim = dim;
   c->schedule_valid = false;
+  magl_free_pairs(c);   // new connectivity follows
   const bool same_shape = nv == c->nv && ne == c->ne && nt == c->nt && np == c->np && npy == c->npy && ntri == c->ntri &&
                           has_edge_owned == (c->d_edge_owned != nullptr) && has_elem_owned == (c->d_elem_owned != nullptr);
   if (same_shape) return MAG_OK;

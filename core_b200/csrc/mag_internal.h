@@ -104,6 +104,11 @@ struct mag_ctx {
   int32_t* d_tet_order;
   MagRows erows, trows;  // anchor-row layout of the edges / tets (whole-part sweeps)
   bool legacy_sweep;     // MAG_LEGACY_SWEEP=1: whole-part sweeps run the round-1 tile kernels (A/B measurements)
+  // (vertex pair) -> edge index hash table of mag_reset_layer (mag_layer.cu); pair_bits = 0: not built
+  unsigned long long* d_pair_keys;
+  int32_t* d_pair_vals;
+  int pair_bits;
+  unsigned long long* d_layer_count; // [2]
   unsigned long long* d_vstat; // [1] eigen-solver failures of the cached per-vertex pass (folded into every sweep's statistics)
   size_t cap_vedge, cap_ma, cap_mb;
 
@@ -137,6 +142,7 @@ int magi_reshape(mag_ctx* c, int dim, int64_t nv, int64_t ne, int64_t nt, int64_
 int magi_materialize_flags(mag_ctx* c);
 int magi_reserve_metric(mag_ctx* c, int kind, size_t na, size_t nb);
 }
+void magl_free_pairs(mag_ctx* c);
 int mag_stats_from_dev(mag_ctx* c, const MagDevStats& s, mag_stats* out);
 #define MAG_CUDA(c, call)                                                                      \
   do {                                                                                         \

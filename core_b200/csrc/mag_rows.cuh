@@ -52,14 +52,46 @@ template <bool FAST> struct TetRowCfg {
   static constexpr int T = FAST ? MAG_TROW_THREADS : kStrictThreads, B = FAST ? MAG_TROW_BLOCKS : kStrictBlocks;
 };
 
-// lane 0 draws the warp's next slice; the value is broadcast (and thereby waited for) only when it is needed
-__device__ __forceinline__ int ticket_issue(unsigned long long* counter)
-{
-  unsigned long long t = 0;
-  if ((threadIdx.x & 31) == 0) t = atomicAdd(counter, 1ull);
-  return (int)t;
-}
-__device__ __forceinline__ int ticket_take(int raw) { return __shfl_sync(0xffffffffu, raw, 0); }
+#ifndef MAG_ROW_STATIC
+#define MAG_ROW_STATIC 1   /* 1: slice s goes to warp s mod (warps of the grid); 0: atomic ticket per slice */
+#endif
+#ifndef MAG_EROW_PF
+#define MAG_EROW_PF 0      /* 1: the other end's record of the NEXT slot row is requested before this one is evaluated (24 registers) */
+#endif
+// Slice hand-out.  Static: all warps of the grid stride through the slices together (so they sweep the vertex array
+// together) and a warp knows its next slice at once -- its header is requested a slice ahead.  Ticket: lane 0 draws the
+// warp's next slice from an atomic counter; the value is broadcast (and thereby waited for) only when it is needed.
+struct SliceWalk {
+  int s, raw, step;
+  __device__ __forceinline__ void begin(unsigned long long* counter)
+  {
+    if (MAG_ROW_STATIC) {
+      const int wpb = blockDim.x >> 5;
+      s = blockIdx.x * wpb + (threadIdx.x >> 5);
+      step = gridDim.x * wpb;
+    } else {
+      raw = issue(counter);
+      s = __shfl_sync(0xffffffffu, raw, 0);
+    }
+  }
+  // call at the top of a slice: returns the slice after this one when it is already known (static), else -1
+  __device__ __forceinline__ int peek(unsigned long long* counter)
+  {
+    if (MAG_ROW_STATIC) return s + step;
+    raw = issue(counter);
+    return -1;
+  }
+  __device__ __forceinline__ void next()
+  {
+    if (MAG_ROW_STATIC) s += step; else s = __shfl_sync(0xffffffffu, raw, 0);
+  }
+  static __device__ __forceinline__ int issue(unsigned long long* counter)
+  {
+    unsigned long long t = 0;
+    if ((threadIdx.x & 31) == 0) t = atomicAdd(counter, 1ull);
+    return (int)t;
+  }
+};
 
 template <int KIND>
 __device__ __forceinline__ void load_half_rec(const double* __restrict__ vedge, int32_t v, double* r)
@@ -116,13 +148,13 @@ k_edge_rows(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t* 
   unsigned c_split = 0, c_coll = 0, c_eval = 0, c_err = 0;
   double maxlen = 0.0;                  // getMaximumEdgeLength starts at 0 and ignores NaN (maSize.cc:673-691)
   int eig_any = 0;
-  int raw = ticket_issue(&st->edge_chunk);
-  int s = ticket_take(raw);
-  while (s < nslices) {
-    raw = ticket_issue(&st->edge_chunk);          // the next slice's ticket travels while this one is worked on
-    const int off = __ldg(slice_off + s);
-    const int K = (__ldg(slice_off + s + 1) - off) >> 5;
-    const int va = __ldg(anchor + (s << 5) + lane);
+  SliceWalk w;
+  w.begin(&st->edge_chunk);
+  int off = 0, off1 = 0, va = -1;
+  if (w.s < nslices) { off = __ldg(slice_off + w.s); off1 = __ldg(slice_off + w.s + 1); va = __ldg(anchor + (w.s << 5) + lane); }
+  while (w.s < nslices) {
+    const int s_nx = w.peek(&st->edge_chunk);
+    const int K = (off1 - off) >> 5;
     const int2* sp = slots + off + lane;
     int2 sl = ld_stream(sp);                      // every slice is at least one slot wide
     int2 sl1 = make_int2(0, -1);
@@ -131,20 +163,36 @@ k_edge_rows(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t* 
 #pragma unroll
     for (int i = 0; i < N; ++i) R.a[i] = 0.0;
     if (va >= 0) load_half_rec<KIND>(vedge, va, R.a);
+    // header of the next slice (static hand-out: known now; ticket hand-out: read when the ticket has arrived, below)
+    int off_nx = 0, off1_nx = 0, va_nx = -1;
+    if (MAG_ROW_STATIC && s_nx < nslices) { off_nx = __ldg(slice_off + s_nx); off1_nx = __ldg(slice_off + s_nx + 1); va_nx = __ldg(anchor + (s_nx << 5) + lane); }
     int32_t f = (!P.zero_in && sl.y >= 0) ? ld_stream_rw(flags + sl.y) : 0;
+#if MAG_EROW_PF
+    double bn[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) bn[i] = 0.0;
+    if (sl.y >= 0) load_half_rec<KIND>(vedge, sl.x & kVidMask, bn);
+#endif
     unsigned nearmask = 0;                        // bit k: this lane's k-th entity landed within 1e-12 of a threshold
     for (int k = 0; k < K; ++k) {
       int2 sl2 = make_int2(0, -1);
       if (k + 2 < K) sl2 = ld_stream(sp + (k + 2) * 32);
       const int32_t f1 = (!P.zero_in && sl1.y >= 0) ? ld_stream_rw(flags + sl1.y) : 0;
       const int e = sl.y;
+#if MAG_EROW_PF
+#pragma unroll
+      for (int i = 0; i < N; ++i) R.b[i] = bn[i];
+      if (sl1.y >= 0) load_half_rec<KIND>(vedge, sl1.x & kVidMask, bn);   // the next slot row's records travel during this evaluation
+#endif
       if (e >= 0) {
         const int32_t fe = f | P.off_bits;
         const bool need_split = !(fe & kSkipSplit), need_coll = !(fe & kSkipColl);
         if (f & P.err_mask) ++c_err;
         if (P.want_len || need_split || need_coll) {
           const bool owned = sl.x >= 0;           // sign bit of the other vertex id = "not owned"
+#if !MAG_EROW_PF
           load_half_rec<KIND>(vedge, sl.x & kVidMask, R.b);
+#endif
           const double len = FAST ? edge_length_fast<KIND>(R, &eig_any) : edge_length_strict<KIND>(R, &eig_any);
           if (P.want_len) {
             st_stream(lengths + e, len);
@@ -185,7 +233,9 @@ k_edge_rows(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t* 
       const unsigned r = near_edges<KIND, FAST>(nr, w.y, va, w.x, fw, vedge, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list);
       c_eval += r & 1u; c_split += (r >> 1) & 1u; c_coll += (r >> 2) & 1u; eig_any |= (int)(r >> 3);
     }
-    s = ticket_take(raw);
+    w.next();
+    if (MAG_ROW_STATIC) { off = off_nx; off1 = off1_nx; va = va_nx; }
+    else if (w.s < nslices) { off = __ldg(slice_off + w.s); off1 = __ldg(slice_off + w.s + 1); va = __ldg(anchor + (w.s << 5) + lane); }
   }
   if (eig_any) atomicAdd(&st->n_eigen_fail, 1ull);
   warp_count_to(c_split, &st->n_split);
@@ -253,13 +303,15 @@ k_tet_rows(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t* _
   auto load_zd = [&](const int4& w, double2* zd) {
     zd[0] = __ldg(chunk_ptr<2>(vpos, 1, w.x & kVidMask)); zd[1] = __ldg(chunk_ptr<2>(vpos, 1, w.y)); zd[2] = __ldg(chunk_ptr<2>(vpos, 1, w.z));
   };
-  int raw = ticket_issue(&st->elem_chunk);
-  int s = ticket_take(raw);
-  while (s < nslices) {
-    raw = ticket_issue(&st->elem_chunk);
-    const int off = __ldg(slice_off + s);
-    const int K = (__ldg(slice_off + s + 1) - off) >> 5;
-    const int va = __ldg(anchor + (s << 5) + lane);
+  SliceWalk w;
+  w.begin(&st->elem_chunk);
+  int off = 0, off1 = 0, va = -1;
+  if (w.s < nslices) { off = __ldg(slice_off + w.s); off1 = __ldg(slice_off + w.s + 1); va = __ldg(anchor + (w.s << 5) + lane); }
+  while (w.s < nslices) {
+    const int s_nx = w.peek(&st->elem_chunk);
+    const int K = (off1 - off) >> 5;
+    int off_nx = 0, off1_nx = 0, va_nx = -1;
+    if (MAG_ROW_STATIC && s_nx < nslices) { off_nx = __ldg(slice_off + s_nx); off1_nx = __ldg(slice_off + s_nx + 1); va_nx = __ldg(anchor + (s_nx << 5) + lane); }
     const int4* sp = slots + off + lane;
     int4 sl = ld_stream(sp);
     int4 sl1 = make_int4(0, 0, 0, -1);
@@ -323,7 +375,9 @@ k_tet_rows(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t* _
                                                qual - elem_off, P.ops, P.good_q, P.use_max, st, near_list);
       c_eval += r & 1u; c_bad += (r >> 1) & 1u; eig_any |= (int)(r >> 2);
     }
-    s = ticket_take(raw);
+    w.next();
+    if (MAG_ROW_STATIC) { off = off_nx; off1 = off1_nx; va = va_nx; }
+    else if (w.s < nslices) { off = __ldg(slice_off + w.s); off1 = __ldg(slice_off + w.s + 1); va = __ldg(anchor + (w.s << 5) + lane); }
   }
   if (eig_any) atomicAdd(&st->n_eigen_fail, 1ull);
   warp_count_to(c_bad, &st->n_bad);

@@ -175,6 +175,15 @@ class Part:
         """Incoming flag words = 0 on every entity (asynchronous device memset)."""
         self._ck(self._L.mag_set_flags(self._h, None, None))
 
+    def reset_layer(self, user_layer_tag=None):
+        """ma::resetLayer (ma/maLayer.cc:94-103) on the resident flag words: LAYER on the closure of every prism / pyramid (and
+        of every element with a non-zero user tag), synchronised across parts, then the freeze (DONT_* on LAYER edges,
+        OK_QUALITY on LAYER elements).  Returns this part's number of layer elements."""
+        tag = _arr(user_layer_tag, np.int32)
+        n = C.c_int64(0)
+        self._ck(self._L.mag_reset_layer(self._h, _ptr(tag), C.byref(n)))
+        return int(n.value)
+
     # ---- sweep + results
     def sweep(self, ops=OP_ALL, max_len=MAXLENGTH, min_len=MINLENGTH, good_quality=GOOD_QUALITY_3D,
               use_max=True, fp_mode=FP_STRICT):

@@ -144,6 +144,16 @@ int mag_set_flags(mag_ctx* c, const int32_t* edge_flags /*[ne]*/, const int32_t*
    mag_clear_flag(c, 3, MAG_BAD_QUALITY).  Asynchronous on the context's stream. */
 int mag_clear_flag(mag_ctx* c, int dimension, int32_t flag);
 
+/* ma::resetLayer (ma/maLayer.cc:94-103) on the resident flag words, what ma::Adapt's constructor does before any mark:
+   markLayerElements (:11-48) -- every prism / pyramid, and every element i with user_layer_tag[i] != 0
+   (Input::userDefinedLayerTagName; [np+npy+nt] host array or NULL), puts MAG_LAYER on itself and on the edges of its
+   closure; with part-boundary links set (mag_set_edge_links) LAYER is then OR-ed across the copies of shared edges
+   (syncFlag, :45-46) -- and freezeLayer (:51-71): LAYER edges get DONT_COLLAPSE | DONT_SPLIT | DONT_SWAP, LAYER elements
+   OK_QUALITY, so that the three marks skip the boundary layer.  Bits are OR-ed into the resident words (mag_set_flags /
+   mag_clear_flag first for a fresh start).  *n_layer_elements (may be NULL) = this part's count (the reference sums it
+   over the parts).  Vertex and face flag words are not held by the library.  Synchronous. */
+int mag_reset_layer(mag_ctx* c, const int32_t* user_layer_tag, int64_t* n_layer_elements);
+
 /* ---- the sweep.  max_len / min_len = ma::MAXLENGTH / MINLENGTH (1.5 / 0.5, maSize.h:26-27);
    good_quality = ma::Input::goodQuality; use_max_metric = measureElementQuality's useMax (default true, maShape.h:26).
    Asynchronous on the context's stream; results are read with the getters below (which synchronize). ---- */

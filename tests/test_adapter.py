@@ -33,7 +33,7 @@ def test_adapter_reproduces_reference(built, log_interp, fp_mode):
     assert np.all(rep[15:19] == 0)
     # the unmodified reference loops (5 whole-mesh sweeps: split, collapse, bad, minq, maxlen) were served by a handful
     # of device sweeps, not by per-entity evaluation
-    assert 0 < rep[19] <= 5 * 16
+    assert 0 < rep[19] <= 5 * 40      # export (row layout, per-vertex pass) + sweeps; per-entity evaluation would be ~1e5
 
 
 @pytest.mark.gpu

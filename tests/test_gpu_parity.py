@@ -302,6 +302,77 @@ def test_cavity_quality_candidate_tets_vs_oracle(cb):
     p.close()
 
 
+@pytest.mark.parametrize("name", ["mixed5_shock_rot_aniso", "pyrslab_shock_rot_aniso"])
+def test_reset_layer_golden(cb, name):
+    """mag_reset_layer = ma::resetLayer (maLayer.cc:94-103): the edge / element flag words the reference's Adapt constructor
+    leaves on a mesh with prisms / pyramids (golden edge_flags_ctor / elem_flags_ctor), bit for bit; then the full sweep on
+    top of them equals the reference's."""
+    g = util.load(name)
+    pr, py, te = util.split_elements(g)
+    kind, ma, mb = util.metric_arrays(g)
+    p = cb.Part(0)
+    p.set_mesh(g["xyz"], g["edge_v"], te, prism_v=pr, pyr_v=py)
+    util.set_part_metric(p, kind, ma, mb)
+    p.clear_flags()
+    n = p.reset_layer()
+    assert n == len(pr) + len(py)
+    ef, lf = p.flags()
+    assert np.array_equal(ef, g["edge_flags_ctor"]) and np.array_equal(lf, g["elem_flags_ctor"])
+    assert p.reset_layer() == n                                  # idempotent
+    ef2, lf2 = p.flags()
+    assert np.array_equal(ef2, ef) and np.array_equal(lf2, lf)
+    p.sweep(cb.OP_ALL, good_quality=float(g["good_quality"]) if float(g["good_quality"]) > 0 else cb.GOOD_QUALITY_3D, fp_mode=cb.FP_STRICT)
+    st = p.stats()
+    ef3, lf3 = p.flags()
+    if np.array_equal(g["edge_flags_in"], g["edge_flags_ctor"]) or not g["edge_flags_in"].any():
+        assert np.array_equal(ef3, g["edge_flags_out"]) and np.array_equal(lf3, g["elem_flags_out"])
+        assert (st["n_split"], st["n_collapse"], st["n_bad"]) == tuple(int(x) for x in g["counts"])
+    p.close()
+
+
+def test_reset_layer_user_tag_and_errors(cb):
+    """Input::userDefinedLayerTagName (maLayer.cc:24-39): tagged elements -- tets included -- join the layer; a layer element
+    whose edges the part does not hold is refused; a 2-D part is refused."""
+    rng = np.random.default_rng(11)
+    xyz, ev, tv, pv = cb.boxmesh.mixed_box(6, 2)
+    nel = len(pv) + len(tv)
+    tag = np.zeros(nel, np.int32)
+    tagged = rng.choice(np.arange(len(pv), nel), 40, replace=False)
+    tag[tagged] = 3
+    p = cb.Part(0)
+    p.set_mesh(xyz, ev, tv, prism_v=pv)
+    p.clear_flags()
+    assert p.reset_layer(tag) == len(pv) + 40
+    ef, lf = p.flags()
+    # numpy model: closure edges of the prisms and of the tagged tets
+    want_e, want_l = cb.boxmesh.layer_closure_flags(ev, pv, None, len(tv))
+    tt = tv[tagged - len(pv)].astype(np.int64)
+    pairs = np.sort(np.concatenate([tt[:, [a, b]] for a, b in ((0, 1), (1, 2), (2, 0), (0, 3), (1, 3), (2, 3))]), axis=1)
+    nvmax = len(xyz)
+    hit = np.isin(np.sort(ev.astype(np.int64), axis=1) @ np.array([nvmax, 1]), pairs @ np.array([nvmax, 1]))
+    want_e[hit] = cb.LAYER | cb.DONT_COLLAPSE | cb.DONT_SPLIT | cb.DONT_SWAP
+    want_l[tagged] = cb.LAYER | cb.OK_QUALITY
+    assert np.array_equal(ef, want_e) and np.array_equal(lf, want_l)
+    # incoming bits survive (the call ORs)
+    ef_in = np.zeros(len(ev), np.int32)
+    ef_in[::7] = cb.CHECKED
+    p.set_flags(ef_in, np.zeros(nel, np.int32))
+    p.reset_layer()
+    ef2, _ = p.flags()
+    assert np.array_equal(ef2, cb.boxmesh.layer_closure_flags(ev, pv, None, len(tv))[0] | ef_in)
+    # a part that misses an edge of a prism
+    p.set_mesh(xyz, ev[1:], tv, prism_v=pv)
+    p.clear_flags()
+    with pytest.raises(cb.MagError) as e:
+        p.reset_layer()
+    assert e.value.code == 2
+    x2, e2, t2 = cb.boxmesh.tri_box(4, 3)
+    p.set_mesh_2d(x2, e2, t2)
+    with pytest.raises(cb.MagError):
+        p.reset_layer()
+    p.close()
+
+
 def test_unsafe_prisms(cb):
     g = util.load("mixed5_unsafe_layer")
     prism_v, _, tet_v = util.split_elements(g)
