@@ -14,7 +14,7 @@ SYMBOLS = [
     "mag_create", "mag_destroy", "mag_last_error", "mag_set_stream", "mag_synchronize",
     "mag_set_mesh", "mag_set_mesh_2d", "mag_set_coords",
     "mag_set_metric_identity", "mag_set_metric_uniform_refiner", "mag_set_metric_iso", "mag_set_metric_aniso", "mag_set_metric_logm",
-    "mag_set_flags", "mag_clear_flag", "mag_reset_layer", "mag_sweep", "mag_sweep_host", "mag_element_weights", "mag_split_vertices", "mag_cavity_quality", "mag_short_edge_test",
+    "mag_set_flags", "mag_clear_flag", "mag_reset_layer", "mag_sweep", "mag_sweep_host", "mag_resweep_host", "mag_set_mark_bytes", "mag_get_mark_bytes", "mag_element_weights", "mag_split_vertices", "mag_cavity_quality", "mag_short_edge_test",
     "mag_sliver_codes", "mag_linear_qualities",
     "mag_get_edge_lengths", "mag_get_qualities", "mag_get_flags", "mag_get_layer_ok", "mag_get_stats",
     "mag_get_near_threshold", "mag_set_metric_logm_from_frames",
@@ -41,6 +41,16 @@ class MagHostPart(C.Structure):
                 ("nt", C.c_int64), ("tet_v", C.c_void_p), ("edge_owned", C.c_void_p), ("elem_owned", C.c_void_p),
                 ("kind", C.c_int), ("field_a", C.c_void_p), ("field_b", C.c_void_p),
                 ("edge_flags", C.c_void_p), ("elem_flags", C.c_void_p), ("slice_entities", C.c_int64)]
+
+
+class MagHostUpdate(C.Structure):
+    """mag_host_update of include/mag.h"""
+    _fields_ = [("xyz", C.c_void_p), ("kind", C.c_int), ("field_a", C.c_void_p), ("field_b", C.c_void_p),
+                ("edge_marks", C.c_void_p), ("elem_marks", C.c_void_p)]
+
+
+class MagHostMarks(C.Structure):
+    _fields_ = [("edge_marks", C.c_void_p), ("elem_marks", C.c_void_p), ("edge_lengths", C.c_void_p), ("qualities", C.c_void_p)]
 
 
 class MagHostResult(C.Structure):
@@ -82,6 +92,10 @@ def lib():
     L.mag_sweep.argtypes = [vp, u32, f64, f64, f64, C.c_int, C.c_int]
     L.mag_sweep_host.argtypes = [vp, C.POINTER(MagHostPart), C.POINTER(MagHostResult), u32, f64, f64, f64, C.c_int, C.c_int,
                                  C.POINTER(MagStats)]
+    L.mag_resweep_host.argtypes = [vp, C.POINTER(MagHostUpdate), C.POINTER(MagHostMarks), u32, f64, f64, f64, C.c_int, C.c_int,
+                                   C.POINTER(MagStats)]
+    L.mag_set_mark_bytes.argtypes = [vp, vp, vp]
+    L.mag_get_mark_bytes.argtypes = [vp, vp, vp]
     L.mag_element_weights.argtypes = [vp, f64, f64, C.c_int, vp]
     L.mag_cavity_quality.argtypes = [vp, i64, vp, vp, C.c_int, C.c_int, vp, vp]
     L.mag_short_edge_test.argtypes = [vp, vp, f64, vp, C.POINTER(i64), C.POINTER(i64)]

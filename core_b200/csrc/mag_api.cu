@@ -157,6 +157,7 @@ int mag_create(mag_ctx** out, int device)
   c->trows = c->erows;
   { const char* e = getenv("MAG_LEGACY_SWEEP"); c->legacy_sweep = e && e[0] == '1'; }
   c->d_vstat = nullptr;
+  c->d_edge_bytes = c->d_elem_bytes = nullptr;
   c->d_pair_keys = nullptr; c->d_pair_vals = nullptr; c->pair_bits = 0; c->d_layer_count = nullptr;
   c->d_near_edge = c->d_near_elem = nullptr;
   c->cap_vedge = c->cap_ma = c->cap_mb = 0;
@@ -196,6 +197,7 @@ void mag_destroy(mag_ctx* c)
   cudaFree(c->d_len); cudaFree(c->d_qual); cudaFree(c->d_weight); cudaFree(c->d_layer_ok); cudaFree(c->d_layer_codes);
   cudaFree(c->d_stats); cudaFreeHost(c->h_stats); cudaFree(c->d_block_sums);
   cudaFree(c->d_near_edge); cudaFree(c->d_near_elem); cudaFree(c->d_edge_order); cudaFree(c->d_tet_order);
+  cudaFree(c->d_edge_bytes); cudaFree(c->d_elem_bytes);
   magk_free_rows(c); cudaFree(c->d_vstat); magl_free_pairs(c); cudaFree(c->d_layer_count);
   for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
   for (cudaEvent_t e : c->pipe_ev) cudaEventDestroy(e);
@@ -242,7 +244,7 @@ int magi_reshape(mag_ctx* c, int dim, int64_t nv, int64_t ne, int64_t nt, int64_
   c->nv = c->ne = c->nt = c->np = c->npy = c->ntri = 0;
   c->vertex_pass_valid = false;
   magk_free_rows(c);
-  if ((rc = dev_free(c, c->d_weight))) return rc;
+  if ((rc = dev_free(c, c->d_weight)) || (rc = dev_free(c, c->d_edge_bytes)) || (rc = dev_free(c, c->d_elem_bytes))) return rc;
   if (!keep_field) { // size field arrays are per vertex: drop them
     c->kind = MAG_KIND_NONE;
     if ((rc = dev_free(c, c->d_ma)) || (rc = dev_free(c, c->d_mb)) || (rc = dev_free(c, c->d_vedge))) return rc;

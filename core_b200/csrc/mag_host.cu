@@ -21,6 +21,10 @@ int magk_edges_range(mag_ctx* c, uint32_t ops, double max_len, double min_len, i
 int magk_tets_range(mag_ctx* c, uint32_t ops, double good_q, int use_max, int fp_mode, int64_t first, int64_t n);
 int magk_length_sum(mag_ctx* c);
 int magk_check_conn(mag_ctx* c, int32_t* d_conn, int64_t n);
+int magk_build_schedule(mag_ctx* c);
+int magk_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double good_q, int use_max, int fp_mode);
+int magk_marks_expand(mag_ctx* c, cudaStream_t s, const uint8_t* d_bytes, int32_t* d_words, int64_t n);
+int magk_marks_compress(mag_ctx* c, cudaStream_t s, const int32_t* d_words, uint8_t* d_bytes, int64_t n);
 
 namespace {
 
@@ -48,6 +52,26 @@ int chain(mag_ctx* c, Events& ev, cudaStream_t earlier, cudaStream_t later)
   if (rc) return rc;
   MAG_CUDA(c, cudaEventRecord(e, earlier));
   MAG_CUDA(c, cudaStreamWaitEvent(later, e, 0));
+  return MAG_OK;
+}
+
+int reserve_mark_bytes(mag_ctx* c)
+{
+  const int64_t nel = c->np + c->npy + c->nt + c->ntri;
+  if (!c->d_edge_bytes && c->ne) MAG_CUDA(c, cudaMalloc((void**)&c->d_edge_bytes, (size_t)c->ne));
+  if (!c->d_elem_bytes && nel) MAG_CUDA(c, cudaMalloc((void**)&c->d_elem_bytes, (size_t)nel));
+  return MAG_OK;
+}
+// every stream of the pipeline is idle when an entry point returns, also on the error paths: the caller may free or
+// unpin its host buffers right away
+int drain(mag_ctx* c, int rc)
+{
+  cudaError_t e1 = c->s_up ? cudaStreamSynchronize(c->s_up) : cudaSuccess;
+  cudaError_t e2 = cudaStreamSynchronize(c->stream);
+  cudaError_t e3 = c->s_down ? cudaStreamSynchronize(c->s_down) : cudaSuccess;
+  if (rc) return rc;
+  cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+  if (e != cudaSuccess) return mag_fail(c, MAG_ERR_CUDA, "pipeline drain: %s", cudaGetErrorString(e));
   return MAG_OK;
 }
 
@@ -96,6 +120,10 @@ extern "C" int mag_sweep_host(mag_ctx* c, const mag_host_part* in, const mag_hos
   c->edge_flags_zero = c->elem_flags_zero = false;   // every slice below is uploaded or zeroed explicitly
   c->last_ops = ops;
   c->last_fp_mode = fp_mode;
+  // everything queued from here on is drained before the call returns, also when a step fails (the caller may free or
+  // unpin its buffers right after an error)
+  auto run = [&]() -> int {
+  int rc;
   // the device arrays may still be read by work queued earlier on the compute stream
   if ((rc = chain(c, ev, s_cmp, s_up))) return rc;
 
@@ -149,11 +177,144 @@ extern "C" int mag_sweep_host(mag_ctx* c, const mag_host_part* in, const mag_hos
     if (out->elem_flags && (rc = copy_async(c, out->elem_flags + t0, c->d_elem_flags + t0, (size_t)n, cudaMemcpyDeviceToHost, s_down))) return rc;
   }
 
-  // ---- statistics; everything has landed when both streams are idle
+  // ---- statistics; everything has landed when the three streams are idle
   mag_stats local;
-  rc = mag_get_stats(c, stats ? stats : &local);      // synchronizes the compute stream
-  MAG_CUDA(c, cudaStreamSynchronize(s_down));
-  return rc;
+  return mag_get_stats(c, stats ? stats : &local);      // synchronizes the compute stream
+  };
+  return drain(c, run());
+}
+
+
+extern "C" int mag_set_mark_bytes(mag_ctx* c, const uint8_t* edge_marks, const uint8_t* elem_marks)
+{
+  if (!c) return MAG_ERR_ARG;
+  MAG_CUDA(c, cudaSetDevice(c->device));
+  const int64_t nel = c->np + c->npy + c->nt + c->ntri;
+  int rc;
+  if ((rc = reserve_mark_bytes(c))) return rc;
+  if (edge_marks && c->ne) {
+    MAG_CUDA(c, cudaMemcpyAsync(c->d_edge_bytes, edge_marks, (size_t)c->ne, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = magk_marks_expand(c, c->stream, c->d_edge_bytes, c->d_edge_flags, c->ne))) return rc;
+  }
+  c->edge_flags_zero = edge_marks == nullptr;
+  if (elem_marks && nel) {
+    MAG_CUDA(c, cudaMemcpyAsync(c->d_elem_bytes, elem_marks, (size_t)nel, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = magk_marks_expand(c, c->stream, c->d_elem_bytes, c->d_elem_flags, nel))) return rc;
+  }
+  c->elem_flags_zero = elem_marks == nullptr;
+  return MAG_OK;
+}
+
+extern "C" int mag_get_mark_bytes(mag_ctx* c, uint8_t* edge_marks, uint8_t* elem_marks)
+{
+  if (!c) return MAG_ERR_ARG;
+  MAG_CUDA(c, cudaSetDevice(c->device));
+  const int64_t nel = c->np + c->npy + c->nt + c->ntri;
+  int rc;
+  if ((rc = reserve_mark_bytes(c)) || (rc = magi_materialize_flags(c))) return rc;
+  if (edge_marks && c->ne) {
+    if ((rc = magk_marks_compress(c, c->stream, c->d_edge_flags, c->d_edge_bytes, c->ne))) return rc;
+    MAG_CUDA(c, cudaMemcpyAsync(edge_marks, c->d_edge_bytes, (size_t)c->ne, cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (elem_marks && nel) {
+    if ((rc = magk_marks_compress(c, c->stream, c->d_elem_flags, c->d_elem_bytes, nel))) return rc;
+    MAG_CUDA(c, cudaMemcpyAsync(elem_marks, c->d_elem_bytes, (size_t)nel, cudaMemcpyDeviceToHost, c->stream));
+  }
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return MAG_OK;
+}
+
+// One sweep of a part whose CONNECTIVITY is already resident (mag_set_mesh / mag_sweep_host earlier): what changes between the
+// sweeps of one MeshAdapt iteration, or between the time steps of a solver that re-evaluates its size field on a fixed
+// mesh, is the vertex data and the flag words -- 120 B / vertex + 1 B / entity up and 1 B / entity down instead of the
+// 2.7 GB + 1.3 GB of the full export (n = 203 part: 1.13 GB + 0.11 GB).
+//     upload stream     xyz | size field | mark bytes
+//     compute stream                      pack, vertex pass | expand | edge sweep | compress | element sweep | compress
+//     download stream                                                               edge bytes (+ lengths) | element bytes (+ qualities)
+extern "C" int mag_resweep_host(mag_ctx* c, const mag_host_update* in, const mag_host_marks* out, uint32_t ops, double max_len,
+                                double min_len, double good_quality, int use_max_metric, int fp_mode, mag_stats* stats)
+{
+  if (!c) return MAG_ERR_ARG;
+  MAG_CUDA(c, cudaSetDevice(c->device));
+  if (!in || !out) return mag_fail(c, MAG_ERR_ARG, "mag_resweep_host: null argument");
+  if (fp_mode != MAG_FP_STRICT && fp_mode != MAG_FP_FAST) return mag_fail(c, MAG_ERR_ARG, "mag_resweep_host: bad fp_mode %d", fp_mode);
+  if (ops & ~(uint32_t)(MAG_OP_ALL | MAG_OP_LENGTH_SUM)) return mag_fail(c, MAG_ERR_ARG, "mag_resweep_host: unknown op bits 0x%x", ops);
+  if ((ops & MAG_OP_LENGTH_SUM) && !(ops & MAG_OP_LENGTHS)) return mag_fail(c, MAG_ERR_ARG, "mag_resweep_host: MAG_OP_LENGTH_SUM needs MAG_OP_LENGTHS");
+  if (c->nv == 0 || !c->d_xyz) return mag_fail(c, MAG_ERR_ARG, "mag_resweep_host: no part is resident (mag_set_mesh / mag_sweep_host first)");
+  const int64_t nv = c->nv, ne = c->ne, nel = c->np + c->npy + c->nt + c->ntri;
+  size_t na = 0, nb = 0;
+  if (in->kind >= 0) {
+    switch (in->kind) {
+      case MAG_KIND_IDENTITY: break;
+      case MAG_KIND_ISO: na = (size_t)nv; break;
+      case MAG_KIND_ANISO: na = (size_t)nv * 3; nb = (size_t)nv * 9; break;
+      case MAG_KIND_LOGM: nb = (size_t)nv * 9; break;
+      default: return mag_fail(c, MAG_ERR_ARG, "mag_resweep_host: bad size-field kind %d", in->kind);
+    }
+    if ((na && !in->field_a) || (nb && !in->field_b)) return mag_fail(c, MAG_ERR_ARG, "mag_resweep_host: null size-field array");
+  } else if (c->kind == MAG_KIND_NONE) return mag_fail(c, MAG_ERR_ARG, "mag_resweep_host: no size field is resident and none was given");
+  int rc;
+  if (!c->s_up) MAG_CUDA(c, cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking));
+  if (!c->s_down) MAG_CUDA(c, cudaStreamCreateWithFlags(&c->s_down, cudaStreamNonBlocking));
+  cudaStream_t s_cmp = c->stream, s_up = c->s_up, s_down = c->s_down;
+  Events ev{c};
+  if ((rc = reserve_mark_bytes(c))) return rc;
+  if (in->kind >= 0 && (rc = magi_reserve_metric(c, in->kind, na, nb))) return rc;
+  if (!c->schedule_valid) {   // the part came through mag_sweep_host, which defers the device layout of the whole-part sweeps
+    if ((rc = magk_build_schedule(c))) return rc;
+    c->schedule_valid = true;
+  }
+  c->last_ops = ops;
+  c->last_fp_mode = fp_mode;
+  auto run = [&]() -> int {
+    int rc;
+    if ((rc = chain(c, ev, s_cmp, s_up))) return rc;   // earlier work on the compute stream may still read these arrays
+    const bool new_vertex_data = in->xyz || in->kind >= 0;
+    if (in->xyz && (rc = copy_async(c, c->d_xyz, in->xyz, (size_t)nv * 3, cudaMemcpyHostToDevice, s_up))) return rc;
+    if (in->kind >= 0) {
+      if ((rc = copy_async(c, c->d_ma, in->field_a, na, cudaMemcpyHostToDevice, s_up)) ||
+          (rc = copy_async(c, c->d_mb, in->field_b, nb, cudaMemcpyHostToDevice, s_up)))
+        return rc;
+      c->kind = in->kind;
+      c->uniform_refiner = false;
+    }
+    if ((rc = chain(c, ev, s_up, s_cmp))) return rc;
+    if (in->edge_marks && (rc = copy_async(c, c->d_edge_bytes, in->edge_marks, (size_t)ne, cudaMemcpyHostToDevice, s_up))) return rc;
+    if (in->elem_marks && (rc = copy_async(c, c->d_elem_bytes, in->elem_marks, (size_t)nel, cudaMemcpyHostToDevice, s_up))) return rc;
+    if (new_vertex_data) {
+      c->vertex_pass_valid = false;
+      if ((rc = magk_pack(c))) return rc;
+      if ((ops & (MAG_OP_QUALITIES | MAG_OP_MARK_BAD | MAG_OP_LAYER_CHECK)) && (rc = magk_vertex_pass(c))) return rc;
+    }
+    if ((rc = chain(c, ev, s_up, s_cmp))) return rc;
+    if (in->edge_marks && (rc = magk_marks_expand(c, s_cmp, c->d_edge_bytes, c->d_edge_flags, ne))) return rc;
+    if (in->elem_marks && (rc = magk_marks_expand(c, s_cmp, c->d_elem_bytes, c->d_elem_flags, nel))) return rc;
+    c->edge_flags_zero = in->edge_marks == nullptr;
+    c->elem_flags_zero = in->elem_marks == nullptr;
+    if ((rc = magk_init_stats(c))) return rc;
+    const uint32_t edge_ops = ops & (MAG_OP_LENGTHS | MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE | MAG_OP_LENGTH_SUM);
+    const uint32_t elem_ops = ops & (MAG_OP_QUALITIES | MAG_OP_MARK_BAD | MAG_OP_LAYER_CHECK);
+    // edges first: their bytes (and lengths) travel back while the elements are evaluated
+    if (edge_ops && (rc = magk_sweep(c, edge_ops, max_len, min_len, good_quality, use_max_metric, fp_mode))) return rc;
+    if (out->edge_marks && ne) {
+      if ((rc = magi_materialize_flags(c))) return rc;
+      if ((rc = magk_marks_compress(c, s_cmp, c->d_edge_flags, c->d_edge_bytes, ne))) return rc;
+    }
+    if ((rc = chain(c, ev, s_cmp, s_down))) return rc;
+    if (out->edge_marks && (rc = copy_async(c, out->edge_marks, c->d_edge_bytes, (size_t)ne, cudaMemcpyDeviceToHost, s_down))) return rc;
+    if (out->edge_lengths && (ops & MAG_OP_LENGTHS) && (rc = copy_async(c, out->edge_lengths, c->d_len, (size_t)ne, cudaMemcpyDeviceToHost, s_down))) return rc;
+    if (elem_ops && (rc = magk_sweep(c, elem_ops, max_len, min_len, good_quality, use_max_metric, fp_mode))) return rc;
+    if (out->elem_marks && nel) {
+      if ((rc = magi_materialize_flags(c))) return rc;
+      if ((rc = magk_marks_compress(c, s_cmp, c->d_elem_flags, c->d_elem_bytes, nel))) return rc;
+    }
+    if ((rc = chain(c, ev, s_cmp, s_down))) return rc;
+    if (out->elem_marks && (rc = copy_async(c, out->elem_marks, c->d_elem_bytes, (size_t)nel, cudaMemcpyDeviceToHost, s_down))) return rc;
+    if (out->qualities && (ops & MAG_OP_QUALITIES) && (rc = copy_async(c, out->qualities, c->d_qual, (size_t)nel, cudaMemcpyDeviceToHost, s_down))) return rc;
+    mag_stats local;
+    return mag_get_stats(c, stats ? stats : &local);      // synchronizes the compute stream
+  };
+  return drain(c, run());
 }
 
 // ma::getLinearQualitiesInMetricSpace's selection and post-processing (ma/maStats.cc:12-31) on the host, with the host's

@@ -109,6 +109,8 @@ struct mag_ctx {
   int32_t* d_pair_vals;
   int pair_bits;
   unsigned long long* d_layer_count; // [2]
+  uint8_t* d_edge_bytes;  // [ne] mark bytes in transit (mag_set/get_mark_bytes, mag_resweep_host); allocated on first use
+  uint8_t* d_elem_bytes;  // [np+npy+nt+ntri]
   unsigned long long* d_vstat; // [1] eigen-solver failures of the cached per-vertex pass (folded into every sweep's statistics)
   size_t cap_vedge, cap_ma, cap_mb;
 

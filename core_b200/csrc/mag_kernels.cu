@@ -1105,6 +1105,43 @@ k_check_conn(int64_t n, int32_t* __restrict__ conn, int32_t nv, unsigned long lo
   if ((threadIdx.x & 31) == 0 && b) atomicAdd(bad, (unsigned long long)b);
 }
 
+// ------------------------------------------------------------------ mark bytes (mag_set_mark_bytes / mag_get_mark_bytes)
+// the eight bits of an "ma_flags" word the sweep reads or writes, packed into one byte for the host link:
+//   bits 0-3 = SPLIT, DONT_SPLIT, COLLAPSE, DONT_COLLAPSE (word bits 0-3); 4 = NEED_NOT_SPLIT (17); 5 = NEED_NOT_COLLAPSE (18);
+//   6 = BAD_QUALITY (5); 7 = OK_QUALITY (6)
+__device__ __forceinline__ int32_t mark_expand(unsigned b)
+{
+  return (int32_t)((b & 0xFu) | ((b & 0x10u) << 13) | ((b & 0x20u) << 13) | ((b & 0x40u) >> 1) | ((b & 0x80u) >> 1));
+}
+__device__ __forceinline__ unsigned mark_compress(int32_t f)
+{
+  const unsigned u = (unsigned)f;
+  return (u & 0xFu) | ((u >> 13) & 0x10u) | ((u >> 13) & 0x20u) | ((u << 1) & 0x40u) | ((u << 1) & 0x80u);
+}
+// four entities per thread: one 32-bit load of bytes <-> one 128-bit store of words
+__global__ void __launch_bounds__(kThreads)
+k_marks_expand(int64_t n, const uint8_t* __restrict__ bytes, int32_t* __restrict__ words)
+{
+  const int64_t i = (blockIdx.x * (int64_t)kThreads + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const unsigned b = *reinterpret_cast<const unsigned*>(bytes + i);
+    *reinterpret_cast<int4*>(words + i) = make_int4(mark_expand(b & 0xFF), mark_expand((b >> 8) & 0xFF), mark_expand((b >> 16) & 0xFF), mark_expand(b >> 24));
+  } else {
+    for (int64_t j = i; j < n; ++j) words[j] = mark_expand(bytes[j]);
+  }
+}
+__global__ void __launch_bounds__(kThreads)
+k_marks_compress(int64_t n, const int32_t* __restrict__ words, uint8_t* __restrict__ bytes)
+{
+  const int64_t i = (blockIdx.x * (int64_t)kThreads + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const int4 w = *reinterpret_cast<const int4*>(words + i);
+    *reinterpret_cast<unsigned*>(bytes + i) = mark_compress(w.x) | (mark_compress(w.y) << 8) | (mark_compress(w.z) << 16) | (mark_compress(w.w) << 24);
+  } else {
+    for (int64_t j = i; j < n; ++j) bytes[j] = (uint8_t)mark_compress(words[j]);
+  }
+}
+
 inline unsigned grid_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
 #include "mag_rows.cuh"
@@ -1167,6 +1204,24 @@ int magk_fold_owned(mag_ctx* c)
     c->n_launches++;
   }
   MAG_CUDA(c, cudaGetLastError());
+  return MAG_OK;
+}
+
+// words[first .. first+n) <-> bytes[0 .. n) on the given stream (first must be a multiple of 4: cudaMalloc alignment + int4 access)
+int magk_marks_expand(mag_ctx* c, cudaStream_t s, const uint8_t* d_bytes, int32_t* d_words, int64_t n)
+{
+  if (n <= 0) return MAG_OK;
+  k_marks_expand<<<grid_for((n + 3) / 4), kThreads, 0, s>>>(n, d_bytes, d_words);
+  MAG_CUDA(c, cudaGetLastError());
+  c->n_launches++;
+  return MAG_OK;
+}
+int magk_marks_compress(mag_ctx* c, cudaStream_t s, const int32_t* d_words, uint8_t* d_bytes, int64_t n)
+{
+  if (n <= 0) return MAG_OK;
+  k_marks_compress<<<grid_for((n + 3) / 4), kThreads, 0, s>>>(n, d_words, d_bytes);
+  MAG_CUDA(c, cudaGetLastError());
+  c->n_launches++;
   return MAG_OK;
 }
 

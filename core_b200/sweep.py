@@ -12,7 +12,7 @@ Everything runs through the C ABI (include/mag.h); there is no CPU fallback.
 import ctypes as C
 import numpy as np
 
-from ._lib import lib, MagStats, MagHostPart, MagHostResult
+from ._lib import lib, MagStats, MagHostPart, MagHostResult, MagHostUpdate, MagHostMarks
 
 # ma/maSize.h:26-27, ma/maInput.cc:32-46
 MAXLENGTH = 1.5
@@ -213,6 +213,50 @@ class Part:
         s = MagStats()
         self._ck(self._L.mag_sweep_host(self._h, C.byref(part), C.byref(res), int(ops), float(max_len), float(min_len),
                                         float(good_quality), int(bool(use_max)), int(fp_mode), C.byref(s)))
+        return s.as_dict()
+
+    # ---- mark bytes: the 8 bits of a flag word the sweep reads or writes (include/mag.h MAG_MARK_*)
+    MARK_WORD_MASK = SPLIT | DONT_SPLIT | COLLAPSE | DONT_COLLAPSE | NEED_NOT_SPLIT | NEED_NOT_COLLAPSE | BAD_QUALITY | OK_QUALITY
+
+    @staticmethod
+    def word_to_mark(w):
+        u = np.asarray(w).astype(np.uint32)
+        return ((u & 0xF) | ((u >> 13) & 0x30) | ((u << 1) & 0xC0)).astype(np.uint8)
+
+    @staticmethod
+    def mark_to_word(b):
+        u = np.asarray(b).astype(np.uint32)
+        return ((u & 0xF) | ((u & 0x30) << 13) | ((u & 0xC0) >> 1)).astype(np.int32)
+
+    def set_mark_bytes(self, edge_marks=None, elem_marks=None):
+        e, l = _arr(edge_marks, np.uint8), _arr(elem_marks, np.uint8)
+        self._ck(self._L.mag_set_mark_bytes(self._h, _ptr(e), _ptr(l)))
+        self.synchronize()
+
+    def mark_bytes(self, edge_out=None, elem_out=None):
+        ef = edge_out if edge_out is not None else np.empty(self.ne, dtype=np.uint8)
+        lf = elem_out if elem_out is not None else np.empty(self.nelem, dtype=np.uint8)
+        self._ck(self._L.mag_get_mark_bytes(self._h, _ptr(ef), _ptr(lf)))
+        return ef, lf
+
+    def resweep_host(self, xyz=None, kind=-1, field_a=None, field_b=None, edge_marks=None, elem_marks=None,
+                     out_edge_marks=None, out_elem_marks=None, out_lengths=None, out_qualities=None,
+                     ops=OP_ALL & ~OP_LAYER_CHECK, max_len=MAXLENGTH, min_len=MINLENGTH,
+                     good_quality=GOOD_QUALITY_3D, use_max=True, fp_mode=FP_STRICT):
+        """mag_resweep_host: the connectivity stays resident; coordinates (xyz), the size field (kind >= 0 with field_a /
+        field_b as in sweep_host) and the incoming mark bytes go up, the outgoing mark bytes (and, opt-in, lengths /
+        qualities) come back, in one streamed call.  Returns the statistics dict."""
+        xyz = _arr(xyz, np.float64)
+        fa, fb = _arr(field_a, np.float64), _arr(field_b, np.float64)
+        em, lm = _arr(edge_marks, np.uint8), _arr(elem_marks, np.uint8)
+        pv = lambda a: None if a is None else _ptr(a).value
+        if int(kind) >= 0:
+            self._kind = int(kind)
+        upd = MagHostUpdate(pv(xyz), int(kind), pv(fa), pv(fb), pv(em), pv(lm))
+        res = MagHostMarks(pv(out_edge_marks), pv(out_elem_marks), pv(out_lengths), pv(out_qualities))
+        s = MagStats()
+        self._ck(self._L.mag_resweep_host(self._h, C.byref(upd), C.byref(res), int(ops), float(max_len), float(min_len),
+                                          float(good_quality), int(bool(use_max)), int(fp_mode), C.byref(s)))
         return s.as_dict()
 
     def element_weights(self, refines_left=None, coarsens_left=0, fp_mode=FP_STRICT, dim=3):

@@ -199,6 +199,46 @@ typedef struct mag_host_result {           /* any pointer may be NULL */
 int mag_sweep_host(mag_ctx* c, const mag_host_part* in, const mag_host_result* out, uint32_t ops, double max_len,
                    double min_len, double good_quality, int use_max_metric, int fp_mode, mag_stats* stats /* may be NULL */);
 
+/* ---- the same for a part whose connectivity is ALREADY resident: only what changes between the sweeps of one MeshAdapt
+   iteration (or between the time steps of a solver that re-evaluates its size field on a fixed mesh) crosses the host
+   link -- vertex coordinates, the size field, and the flag words as one MARK BYTE per entity:
+     bit 0 SPLIT, 1 DONT_SPLIT, 2 COLLAPSE, 3 DONT_COLLAPSE (= bits 0-3 of the ma_flags word, ma/maAdapt.h:17-37),
+     bit 4 NEED_NOT_SPLIT, 5 NEED_NOT_COLLAPSE, 6 BAD_QUALITY, 7 OK_QUALITY
+   i.e. exactly the bits markEntities reads (its allFalseFlags / the true-flag assertion) or writes for the three marks
+   (ma/maAdapt.cc:293-324, maRefine.cc:385-400, maCoarsen.cc:277-292, maShape.cc:122-136); the caller keeps the other bits
+   of its words and merges:  word = (word & ~MAG_MARK_WORD_MASK) | MAG_MARK_TO_WORD(byte). ---- */
+enum {
+  MAG_MARK_SPLIT = 1, MAG_MARK_DONT_SPLIT = 2, MAG_MARK_COLLAPSE = 4, MAG_MARK_DONT_COLLAPSE = 8,
+  MAG_MARK_NEED_NOT_SPLIT = 16, MAG_MARK_NEED_NOT_COLLAPSE = 32, MAG_MARK_BAD_QUALITY = 64, MAG_MARK_OK_QUALITY = 128
+};
+#define MAG_MARK_WORD_MASK (MAG_SPLIT | MAG_DONT_SPLIT | MAG_COLLAPSE | MAG_DONT_COLLAPSE | MAG_NEED_NOT_SPLIT | MAG_NEED_NOT_COLLAPSE | MAG_BAD_QUALITY | MAG_OK_QUALITY)
+#define MAG_MARK_TO_WORD(b) ((int32_t)(((uint32_t)(b) & 0xFu) | (((uint32_t)(b) & 0x30u) << 13) | (((uint32_t)(b) & 0xC0u) >> 1)))
+#define MAG_WORD_TO_MARK(w) ((uint8_t)(((uint32_t)(w) & 0xFu) | (((uint32_t)(w) >> 13) & 0x30u) | (((uint32_t)(w) << 1) & 0xC0u)))
+/* resident flag words := MAG_MARK_TO_WORD(byte) (all other bits zero); NULL = all zero, like mag_set_flags */
+int mag_set_mark_bytes(mag_ctx* c, const uint8_t* edge_marks /*[ne]*/, const uint8_t* elem_marks /*[np+npy+nt]*/);
+/* MAG_WORD_TO_MARK of the resident flag words; either pointer may be NULL.  Synchronous. */
+int mag_get_mark_bytes(mag_ctx* c, uint8_t* edge_marks, uint8_t* elem_marks);
+typedef struct mag_host_update {
+  const double* xyz;                       /* [nv][3] moved vertices (apf::Mesh2::setPoint), NULL = unchanged */
+  int kind;                                /* size field given here: 0 identity, 1 iso, 2 aniso, 3 logm; -1 = unchanged */
+  const double* field_a;                   /* as in mag_host_part */
+  const double* field_b;
+  const uint8_t* edge_marks;               /* incoming mark bytes [ne], NULL = all zero */
+  const uint8_t* elem_marks;               /* [np+npy+nt], NULL = all zero */
+} mag_host_update;
+typedef struct mag_host_marks {            /* any pointer may be NULL */
+  uint8_t* edge_marks;                     /* [ne] outgoing mark bytes */
+  uint8_t* elem_marks;                     /* [np+npy+nt] */
+  double* edge_lengths;                    /* [ne], opt-in (MAG_OP_LENGTHS) */
+  double* qualities;                       /* [np+npy+nt], opt-in (MAG_OP_QUALITIES) */
+} mag_host_marks;
+/* update + sweep + marks of the resident part in one streamed call (uploads | kernels | downloads on three streams; the
+   edge bytes travel back while the elements are evaluated).  All of MAG_OP_ALL is supported (prisms / pyramids included).
+   Results are bit-identical to mag_set_coords + mag_set_metric_* + mag_set_mark_bytes + mag_sweep + mag_get_mark_bytes.
+   Returns when every output has landed and every stream is idle, also on errors. */
+int mag_resweep_host(mag_ctx* c, const mag_host_update* in, const mag_host_marks* out, uint32_t ops, double max_len,
+                     double min_len, double good_quality, int use_max_metric, int fp_mode, mag_stats* stats /* may be NULL */);
+
 /* ---- the sweeps either side of the marking path, over the same resident part ----
    Predictive load-balance weight of every element, ma::getElementWeights (ma/maBalance.cc:83-97):
    SizeField::getWeight = measure(element) / parentMeasure (ma/maSize.cc:147-156,225-229; tets: 4-point Gauss rule

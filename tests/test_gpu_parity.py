@@ -825,6 +825,71 @@ def test_sweep_host_streamed_equals_resident(cb, kindname):
     q.close()
 
 
+@pytest.mark.parametrize("kindname", ["iso", "aniso", "logm"])
+def test_resweep_host_equals_resident(cb, kindname):
+    """mag_resweep_host (connectivity resident; coordinates + size field + mark bytes up, mark bytes down) returns what
+    mag_set_coords + mag_set_metric_* + mag_set_flags + mag_sweep + mag_get_flags return, restricted to the eight mark
+    bits; moved vertices and a changed field are picked up (the cached per-vertex pass is invalidated)."""
+    from oracle import mao
+    n = 14
+    rng = np.random.default_rng(11)
+    xyz, ev, tv = cb.boxmesh.kuhn_box(n, n, n)
+    xyz = cb.fields.jitter(xyz, 0.3 / n)
+    nv = len(xyz)
+    ops = cb.OP_ALL & ~cb.OP_LAYER_CHECK
+    p, q = cb.Part(0), cb.Part(0)
+    p.set_mesh(xyz, ev, tv)
+    q.set_mesh(xyz, ev, tv)
+    mask = np.int32(cb.Part.MARK_WORD_MASK)
+    w = rng.integers(0, 2**31 - 1, 1000).astype(np.int32)
+    assert np.array_equal(cb.Part.mark_to_word(cb.Part.word_to_mark(w)), w & mask)
+    for it, mode in enumerate((cb.FP_STRICT, cb.FP_FAST, cb.FP_FAST)):
+        xyz_i = cb.fields.jitter(xyz, 0.05 / n, seed=100 + it) if it else xyz
+        R = util.random_frames(nv, rng)
+        H = (1.0 / n) * np.exp(rng.uniform(-1.0, 1.0, (nv, 3)))
+        s = (1.0 / n) * np.exp(rng.uniform(-1, 1, nv))
+        kind, ma, mb = {"iso": (mao.ISO, s, None), "aniso": (mao.ANISO, H, R),
+                        "logm": (mao.LOGM, None, mao.logm_from_frames(H, R, 0))}[kindname]
+        ef = np.zeros(len(ev), np.int32)
+        lf = np.zeros(len(tv), np.int32)
+        ef[rng.random(len(ev)) < 0.2] |= cb.DONT_SPLIT
+        ef[rng.random(len(ev)) < 0.1] |= cb.NEED_NOT_COLLAPSE
+        lf[rng.random(len(tv)) < 0.3] |= cb.OK_QUALITY
+        p.set_coords(xyz_i)
+        util.set_part_metric(p, kind, ma, mb)
+        p.set_flags(ef, lf)
+        p.sweep(ops, good_quality=0.1, fp_mode=mode)
+        st0, L0, q0 = p.stats(), p.edge_lengths(), p.qualities()
+        ef0, lf0 = p.flags()
+        oem, olm = np.empty(len(ev), np.uint8), np.empty(len(tv), np.uint8)
+        oL, oq = np.empty(len(ev)), np.empty(len(tv))
+        st1 = q.resweep_host(xyz=xyz_i, kind=kind, field_a=ma, field_b=mb, edge_marks=cb.Part.word_to_mark(ef),
+                             elem_marks=cb.Part.word_to_mark(lf), out_edge_marks=oem, out_elem_marks=olm,
+                             out_lengths=oL, out_qualities=oq, ops=ops, good_quality=0.1, fp_mode=mode)
+        assert np.array_equal(oem, cb.Part.word_to_mark(ef0)) and np.array_equal(olm, cb.Part.word_to_mark(lf0))
+        assert np.array_equal(oL, L0) and np.array_equal(oq, q0)
+        for k in ("n_split", "n_collapse", "n_bad", "n_edges_evaluated", "n_elems_evaluated", "n_near_threshold",
+                  "min_quality", "max_length"):
+            assert st0[k] == st1[k], k
+        # getters on the resident part agree as well
+        em, lm = q.mark_bytes()
+        assert np.array_equal(em, oem) and np.array_equal(lm, olm)
+    # nothing new uploaded: same field, all-zero marks, marks only
+    st2 = q.resweep_host(out_edge_marks=oem, out_elem_marks=olm, ops=cb.OP_MARK_SPLIT | cb.OP_MARK_COLLAPSE | cb.OP_MARK_BAD,
+                         good_quality=0.1, fp_mode=cb.FP_FAST)
+    p.set_flags(None, None)
+    p.sweep(cb.OP_MARK_SPLIT | cb.OP_MARK_COLLAPSE | cb.OP_MARK_BAD, good_quality=0.1, fp_mode=cb.FP_FAST)
+    assert np.array_equal(oem, cb.Part.word_to_mark(p.flags()[0])) and np.array_equal(olm, cb.Part.word_to_mark(p.flags()[1]))
+    assert (st2["n_split"], st2["n_collapse"], st2["n_bad"]) == tuple(p.stats()[k] for k in ("n_split", "n_collapse", "n_bad"))
+    # set / get of mark bytes alone
+    b = rng.integers(0, 256, len(ev)).astype(np.uint8)
+    q.set_mark_bytes(b, None)
+    assert np.array_equal(q.mark_bytes()[0], b) and not q.mark_bytes()[1].any()
+    assert np.array_equal(q.flags()[0], cb.Part.mark_to_word(b))
+    p.close()
+    q.close()
+
+
 def test_baseline_configs_1_and_2_reference_values(cb):
     """BASELINE configs[0] (n = 20, isotropic h = hbar (1 + 2x)) and configs[1] (n = 55, 998,250 tets, planar shock
     layer AnisoSizeField) on the device against the values the compiled reference printed at survey time
