@@ -20,20 +20,21 @@ namespace magfa {
 __device__ constexpr double kXI = 0.577350269189626;
 __device__ constexpr double kNP0 = (1.0 - kXI) / 2.0, kNP1 = (1.0 + kXI) / 2.0;
 
+// (contractions written out: the whole-part and the sub-range kernels must return the same bits, whatever nvcc would fuse)
 __device__ __forceinline__ double edge_identity(const double ra[4], const double rb[4])
 {
   double dx = rb[0] - ra[0], dy = rb[1] - ra[1], dz = rb[2] - ra[2];
-  return sqrt(dx * dx + dy * dy + dz * dz);
+  return sqrt(fma(dz, dz, fma(dy, dy, __dmul_rn(dx, dx))));
 }
 
 // iso: Q = I/h  ->  len = |d| (1/h+ + 1/h-) = |x1-x0| (h+ + h-) / (2 h+ h-)
 __device__ __forceinline__ double edge_iso(const double ra[4], const double rb[4])
 {
   double dx = rb[0] - ra[0], dy = rb[1] - ra[1], dz = rb[2] - ra[2];
-  double l = sqrt(dx * dx + dy * dy + dz * dz);
-  double hp = ra[3] * kNP0 + rb[3] * kNP1;
-  double hm = ra[3] * kNP1 + rb[3] * kNP0;
-  return l * (hp + hm) / (2.0 * hp * hm);
+  double l = sqrt(fma(dz, dz, fma(dy, dy, __dmul_rn(dx, dx))));
+  double hp = fma(ra[3], kNP0, __dmul_rn(rb[3], kNP1));
+  double hm = fma(ra[3], kNP1, __dmul_rn(rb[3], kNP0));
+  return __dmul_rn(l, hp + hm) / __dmul_rn(__dmul_rn(2.0, hp), hm);
 }
 
 // Unnormalised Gram-Schmidt at one Gauss point, t = interpolation weight of vertex b (c = a + t (b - a)):

@@ -53,7 +53,9 @@ template <bool FAST> struct TetRowCfg {
 };
 
 #ifndef MAG_ROW_STATIC
-#define MAG_ROW_STATIC 1   /* 1: slice s goes to warp s mod (warps of the grid); 0: atomic ticket per slice */
+#define MAG_ROW_STATIC 0   /* 1: slice s goes to warp s mod (warps of the grid); 0: atomic ticket per slice.  Measured (B200, n = 203,
+                              r2b): static 1.94 / 1.77 ms (lattice / jittered) with the SMs idle 45 % of the launch -- warps that fall behind lose
+                              the L2 window the others share and fall further behind; ticket 1.42 / 1.02 ms */
 #endif
 #ifndef MAG_EROW_PF
 #define MAG_EROW_PF 0      /* 1: the other end's record of the NEXT slot row is requested before this one is evaluated (24 registers) */
@@ -141,7 +143,7 @@ template <int KIND, bool FAST>
 __global__ void __launch_bounds__(EdgeRowCfg<KIND, FAST>::T, EdgeRowCfg<KIND, FAST>::B)
 k_edge_rows(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t* __restrict__ slice_off, const int2* __restrict__ slots,
             const double* __restrict__ vedge, int32_t* __restrict__ flags, double* __restrict__ lengths, EdgeParams P,
-            MagDevStats* st, int32_t* __restrict__ near_list)
+            MagDevStats* st, int32_t* __restrict__ near_list, PfArgs pf)
 {
   constexpr int N = EdgeRecs<KIND>::N;
   const int lane = threadIdx.x & 31;
@@ -155,6 +157,8 @@ k_edge_rows(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t* 
   while (w.s < nslices) {
     const int s_nx = w.peek(&st->edge_chunk);
     const int K = (off1 - off) >> 5;
+    int pf_b0 = 0, pf_b1 = 0;                      // lane 0: the vertex blocks slice s + dist adds (requested at the end of this slice)
+    if (pf.blk && lane == 0 && w.s + pf.dist < pf.n) { pf_b0 = __ldg(pf.blk + w.s + pf.dist - 1); pf_b1 = __ldg(pf.blk + w.s + pf.dist); }
     const int2* sp = slots + off + lane;
     int2 sl = ld_stream(sp);                      // every slice is at least one slot wide
     int2 sl1 = make_int2(0, -1);
@@ -233,6 +237,7 @@ k_edge_rows(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t* 
       const unsigned r = near_edges<KIND, FAST>(nr, w.y, va, w.x, fw, vedge, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list);
       c_eval += r & 1u; c_split += (r >> 1) & 1u; c_coll += (r >> 2) & 1u; eig_any |= (int)(r >> 3);
     }
+    if (pf_b1 > pf_b0) l2_prefetch_blocks<N / 2>(vedge, pf_b0, pf_b1);
     w.next();
     if (MAG_ROW_STATIC) { off = off_nx; off1 = off1_nx; va = va_nx; }
     else if (w.s < nslices) { off = __ldg(slice_off + w.s); off1 = __ldg(slice_off + w.s + 1); va = __ldg(anchor + (w.s << 5) + lane); }
@@ -291,7 +296,7 @@ template <int KIND, bool FAST, bool USE_MAX>
 __global__ void __launch_bounds__(TetRowCfg<FAST>::T, TetRowCfg<FAST>::B)
 k_tet_rows(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t* __restrict__ slice_off, const int4* __restrict__ slots,
            int32_t elem_off, int64_t nv, const double* __restrict__ vpos, const double* __restrict__ vq, const double* __restrict__ vedge,
-           int32_t* __restrict__ flags, double* __restrict__ qual, TetParams P, MagDevStats* st, int32_t* __restrict__ near_list)
+           int32_t* __restrict__ flags, double* __restrict__ qual, TetParams P, MagDevStats* st, int32_t* __restrict__ near_list, PfArgs pf)
 {
   const int lane = threadIdx.x & 31;
   unsigned c_bad = 0, c_eval = 0, c_err = 0;
@@ -310,6 +315,8 @@ k_tet_rows(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t* _
   while (w.s < nslices) {
     const int s_nx = w.peek(&st->elem_chunk);
     const int K = (off1 - off) >> 5;
+    int pf_b0 = 0, pf_b1 = 0;
+    if (pf.blk && lane == 0 && w.s + pf.dist < pf.n) { pf_b0 = __ldg(pf.blk + w.s + pf.dist - 1); pf_b1 = __ldg(pf.blk + w.s + pf.dist); }
     int off_nx = 0, off1_nx = 0, va_nx = -1;
     if (MAG_ROW_STATIC && s_nx < nslices) { off_nx = __ldg(slice_off + s_nx); off1_nx = __ldg(slice_off + s_nx + 1); va_nx = __ldg(anchor + (s_nx << 5) + lane); }
     const int4* sp = slots + off + lane;
@@ -374,6 +381,11 @@ k_tet_rows(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t* _
       const unsigned r = near_tets<KIND, FAST>(nr, w.w, elem_off, make_int4(va, w.x, w.y, w.z), fw, nv, vpos, vq, vedge, flags - elem_off,
                                                qual - elem_off, P.ops, P.good_q, P.use_max, st, near_list);
       c_eval += r & 1u; c_bad += (r >> 1) & 1u; eig_any |= (int)(r >> 2);
+    }
+    if (pf_b1 > pf_b0) {
+      l2_prefetch_blocks<2>(vpos, pf_b0, pf_b1);
+      if (USE_MAX) l2_prefetch_blocks<5>(vq, pf_b0, pf_b1);
+      else l2_prefetch_blocks<EdgeRecs<KIND>::N / 2>(vedge, pf_b0, pf_b1);
     }
     w.next();
     if (MAG_ROW_STATIC) { off = off_nx; off1 = off1_nx; va = va_nx; }
@@ -446,24 +458,39 @@ __global__ void __launch_bounds__(kThreads)
 k_slots_fill(int64_t nrows, int64_t nrows_pad, const int32_t* __restrict__ order, const int32_t* __restrict__ row_anchor,
              const int32_t* __restrict__ row_len, const int32_t* __restrict__ row_first, const int32_t* __restrict__ sorted_e,
              const int32_t* __restrict__ conn, const int32_t* __restrict__ slice_off, int32_t* __restrict__ anchor_out,
-             int32_t* __restrict__ slots)
+             int32_t* __restrict__ slots, int32_t* __restrict__ slice_vmax)
 {
   const int64_t p = blockIdx.x * (int64_t)kThreads + threadIdx.x;
-  if (p >= nrows_pad) return;
-  if (p >= nrows) { anchor_out[p] = -1; return; }
-  const int r = order[p];
-  anchor_out[p] = row_anchor[r];
-  const int len = row_len[r], first = row_first[r];
-  const int64_t base = (int64_t)slice_off[p >> 5] + (p & 31);
-  for (int k = 0; k < len; ++k) {
-    const int32_t e = sorted_e[first + k];
-    const int32_t* cv = conn + (int64_t)e * NV;
-    const int32_t notowned = cv[0] & (int32_t)0x80000000;
-    const int64_t d = base + 32 * k;
-    if (NV == 2) {
-      reinterpret_cast<int2*>(slots)[d] = make_int2(cv[1] | notowned, e);
-    } else {
-      reinterpret_cast<int4*>(slots)[d] = make_int4(cv[1] | notowned, cv[2], cv[3], e);
+  if (p >= nrows_pad) return;                     // nrows_pad is a multiple of 32: whole warps leave together
+  int vmax = 0;                                   // largest vertex id this row touches (-> L2 prefetch table)
+  if (p >= nrows) anchor_out[p] = -1;
+  else {
+    const int r = order[p];
+    vmax = anchor_out[p] = row_anchor[r];
+    const int len = row_len[r], first = row_first[r];
+    const int64_t base = (int64_t)slice_off[p >> 5] + (p & 31);
+    for (int k = 0; k < len; ++k) {
+      const int32_t e = sorted_e[first + k];
+      const int32_t* cv = conn + (int64_t)e * NV;
+      const int32_t notowned = cv[0] & (int32_t)0x80000000;
+      const int64_t d = base + 32 * k;
+      vmax = cv[1] > vmax ? cv[1] : vmax;
+      if (NV == 2) {
+        reinterpret_cast<int2*>(slots)[d] = make_int2(cv[1] | notowned, e);
+      } else {
+        reinterpret_cast<int4*>(slots)[d] = make_int4(cv[1] | notowned, cv[2], cv[3], e);
+        vmax = cv[2] > vmax ? cv[2] : vmax;
+        vmax = cv[3] > vmax ? cv[3] : vmax;
+      }
     }
   }
+  vmax = __reduce_max_sync(0xffffffffu, vmax);
+  if ((p & 31) == 0) slice_vmax[p >> 5] = vmax;
+}
+// running maximum of vertex ids -> number of kVB-vertex blocks covering [0, vmax]
+__global__ void __launch_bounds__(kThreads)
+k_vmax_to_blocks(int64_t n, int32_t* __restrict__ a)
+{
+  const int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x;
+  if (i < n) a[i] = a[i] / kVB + 1;
 }
