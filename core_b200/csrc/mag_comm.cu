@@ -72,7 +72,7 @@ __global__ void k_merge_flags(int64_t n, const int32_t* __restrict__ idx, const 
   }
   if ((mine & mask) != theirs) {
     atomicAdd(&st->n_flag_mismatch, 1ull);
-    if (peer_owns && peer_owns[i]) flags[e] = (mine & ~mask) | theirs;
+    if (mode == 0 && peer_owns && peer_owns[i]) flags[e] = (mine & ~mask) | theirs;   // mode 2: count only
   }
 }
 
@@ -171,17 +171,24 @@ int mag_set_edge_links(mag_ctx* c, int npeers, const int32_t* peer, const int64_
     L.n = n[k];
     L.d_idx = L.d_send = L.d_recv = nullptr;
     L.d_peer_owns = nullptr;
-    if (L.n) {
-      MAG_CUDA(c, cudaMalloc((void**)&L.d_idx, (size_t)L.n * 4));
-      MAG_CUDA(c, cudaMalloc((void**)&L.d_send, (size_t)L.n * 4));
-      MAG_CUDA(c, cudaMalloc((void**)&L.d_recv, (size_t)L.n * 4));
-      MAG_CUDA(c, cudaMemcpyAsync(L.d_idx, idx[k], (size_t)L.n * 4, cudaMemcpyHostToDevice, c->stream));
-      if (peer_owns && peer_owns[k]) {
-        MAG_CUDA(c, cudaMalloc((void**)&L.d_peer_owns, (size_t)L.n));
-        MAG_CUDA(c, cudaMemcpyAsync(L.d_peer_owns, peer_owns[k], (size_t)L.n, cudaMemcpyHostToDevice, c->stream));
+    c->links.push_back(L);               // registered first: free_links releases whatever was allocated if a step below fails
+    MagLinks& R = c->links.back();
+    cudaError_t e = cudaSuccess;
+    if (R.n) {
+      if (e == cudaSuccess) e = cudaMalloc((void**)&R.d_idx, (size_t)R.n * 4);
+      if (e == cudaSuccess) e = cudaMalloc((void**)&R.d_send, (size_t)R.n * 4);
+      if (e == cudaSuccess) e = cudaMalloc((void**)&R.d_recv, (size_t)R.n * 4);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(R.d_idx, idx[k], (size_t)R.n * 4, cudaMemcpyHostToDevice, c->stream);
+      if (e == cudaSuccess && peer_owns && peer_owns[k]) {
+        e = cudaMalloc((void**)&R.d_peer_owns, (size_t)R.n);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(R.d_peer_owns, peer_owns[k], (size_t)R.n, cudaMemcpyHostToDevice, c->stream);
       }
     }
-    c->links.push_back(L);
+    if (e != cudaSuccess) {
+      cudaStreamSynchronize(c->stream);
+      free_links(c);
+      return mag_fail(c, MAG_ERR_CUDA, "mag_set_edge_links: %s", cudaGetErrorString(e));
+    }
   }
   MAG_CUDA(c, cudaStreamSynchronize(c->stream));
   return MAG_OK;
@@ -192,6 +199,23 @@ int mag_reconcile_edge_flags(mag_ctx* c, int32_t flag_mask)
   if (!c) return MAG_ERR_ARG;
   MAG_CUDA(c, cudaSetDevice(c->device));
   return exchange(c, flag_mask, 0);
+}
+/* ma::checkFlagConsistency (maAdapt.cc:226-256): the reference asserts that every copy of a shared edge carries the same
+   bits; here the copies are compared (nothing is repaired) and a disagreement is MAG_ERR_INCONSISTENT */
+int mag_check_edge_flag_consistency(mag_ctx* c, int32_t flag_mask, int64_t* n_mismatch)
+{
+  if (!c) return MAG_ERR_ARG;
+  MAG_CUDA(c, cudaSetDevice(c->device));
+  unsigned long long before = 0, after = 0;
+  MAG_CUDA(c, cudaMemcpyAsync(&before, &c->d_stats->n_flag_mismatch, sizeof(before), cudaMemcpyDeviceToHost, c->stream));
+  int rc = exchange(c, flag_mask, 2);
+  if (rc) return rc;
+  MAG_CUDA(c, cudaMemcpyAsync(&after, &c->d_stats->n_flag_mismatch, sizeof(after), cudaMemcpyDeviceToHost, c->stream));
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (n_mismatch) *n_mismatch = (int64_t)(after - before);
+  if (after != before)
+    return mag_fail(c, MAG_ERR_INCONSISTENT, "%llu copies of shared edges disagree with their peer's copy under mask 0x%x", after - before, flag_mask);
+  return MAG_OK;
 }
 int mag_sync_edge_flags(mag_ctx* c, int32_t flag_mask)
 {
@@ -219,6 +243,7 @@ int mag_allreduce_stats(mag_ctx* c, mag_stats* global)
     g.n_near_edge += s.n_near_edge; g.n_near_elem += s.n_near_elem; g.n_layer_unsafe += s.n_layer_unsafe;
     g.n_flag_err += s.n_flag_err; g.n_eigen_fail += s.n_eigen_fail; g.n_nonsimplex += s.n_nonsimplex;
     g.n_flag_mismatch += s.n_flag_mismatch;
+    g.n_bad_conn += s.n_bad_conn;
     if (s.min_q_key < g.min_q_key) g.min_q_key = s.min_q_key;
     if (s.max_len_bits > g.max_len_bits) g.max_len_bits = s.max_len_bits;
     g.sum_len += s.sum_len;

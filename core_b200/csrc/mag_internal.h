@@ -22,6 +22,8 @@ struct MagDevStats {
   unsigned long long max_len_bits; // bits of a non-negative double: integer order == fp order
   unsigned long long min_q_key;    // order-preserving key of a double (see dkey())
   double sum_len;
+  unsigned long long n_eigen_aux;  // eigen-solver failures of the auxiliary sweeps (weights, cavities, sliver codes): their own
+                                   // counter, so a deferred MAG_ERR_EIGEN of the last mag_sweep survives them
 };
 
 #define MAG_SUM_BLOCKS 1184 /* 8 x 148: fixed shape of the length-sum tree */
@@ -106,6 +108,7 @@ struct mag_ctx {
   int32_t* d_edge_pf;    // legacy kernels: L2 prefetch table per ticket (see PfArgs in mag_rows.cuh)
   int32_t* d_tet_pf;
   int64_t n_edge_pf, n_tet_pf;
+  bool lean_sweep;       // MAG_LEAN_SWEEP=0: never use the lean kernels of mag_lean.cuh (A/B measurements, tests)
   bool l2_prefetch;      // MAG_L2_PREFETCH=0 switches the L2 prefetch of the vertex arrays off (A/B measurements)
   MagRows erows, trows;  // anchor-row layout of the edges / tets (whole-part sweeps)
   bool legacy_sweep;     // MAG_LEGACY_SWEEP=1: whole-part sweeps run the round-1 tile kernels (A/B measurements)

@@ -1195,6 +1195,7 @@ k_marks_compress(int64_t n, const int32_t* __restrict__ words, uint8_t* __restri
 inline unsigned grid_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
 #include "mag_rows.cuh"
+#include "mag_lean.cuh"
 
 } // namespace
 
@@ -1689,8 +1690,52 @@ static int launch_edge_rows_t(mag_ctx* c, const SweepParams& P)
   c->n_launches++;
   return MAG_OK;
 }
+// the lean kernels (mag_lean.cuh): MAG_FP_FAST sweeps over all-zero incoming flag words
+template <int KIND>
+static int launch_edge_rows_z(mag_ctx* c, const SweepParams& P)
+{
+  constexpr int T = EdgeLeanCfg<KIND>::T;
+  const int per_sm = blocks_per_sm(c, (const void*)k_edge_rows_z<KIND>, T);
+  int64_t g = (int64_t)per_sm * c->n_sms;
+  const int64_t groups = (c->erows.n_slices + kZGroup - 1) / kZGroup;
+  const int64_t need = (groups + T / 32 - 1) / (T / 32);
+  if (g > need) g = need;
+  k_edge_rows_z<KIND><<<(unsigned)(g < 1 ? 1 : g), T, 0, c->stream>>>(
+      (int32_t)c->erows.n_slices, c->erows.d_anchor, c->erows.d_slice_off, reinterpret_cast<const int2*>(c->erows.d_slots), c->d_vedge,
+      c->d_edge_flags, c->d_len, edge_params(P, true), c->d_stats, c->d_near_edge);
+  MAG_CUDA(c, cudaGetLastError());
+  c->n_launches++;
+  return MAG_OK;
+}
+template <int KIND>
+static int launch_tet_rows_z(mag_ctx* c, const SweepParams& P)
+{
+  constexpr int T = MAG_TZ_THREADS;
+  const int per_sm = blocks_per_sm(c, (const void*)k_tet_rows_z<KIND>, T);
+  int64_t g = (int64_t)per_sm * c->n_sms;
+  const int64_t groups = (c->trows.n_slices + kZGroup - 1) / kZGroup;
+  const int64_t need = (groups + T / 32 - 1) / (T / 32);
+  if (g > need) g = need;
+  k_tet_rows_z<KIND><<<(unsigned)(g < 1 ? 1 : g), T, 0, c->stream>>>(
+      (int32_t)c->trows.n_slices, c->trows.d_anchor, c->trows.d_slice_off, reinterpret_cast<const int4*>(c->trows.d_slots),
+      (int32_t)(c->np + c->npy), c->nv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_flags, c->d_qual, tet_params(P, true),
+      c->d_stats, c->d_near_elem);
+  MAG_CUDA(c, cudaGetLastError());
+  c->n_launches++;
+  return MAG_OK;
+}
+
 static int launch_edge_rows(mag_ctx* c, const SweepParams& P, bool fast)
 {
+  constexpr uint32_t kEdgeFull = MAG_OP_LENGTHS | MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE;
+  if (fast && c->edge_flags_zero && c->lean_sweep && (P.ops & kEdgeFull) == kEdgeFull) {
+    switch (c->kind) {
+      case MAG_KIND_IDENTITY: return launch_edge_rows_z<MAG_KIND_IDENTITY>(c, P);
+      case MAG_KIND_ISO: return launch_edge_rows_z<MAG_KIND_ISO>(c, P);
+      case MAG_KIND_ANISO: return launch_edge_rows_z<MAG_KIND_ANISO>(c, P);
+      default: return launch_edge_rows_z<MAG_KIND_LOGM>(c, P);
+    }
+  }
   switch (c->kind) {
     case MAG_KIND_IDENTITY: return fast ? launch_edge_rows_t<MAG_KIND_IDENTITY, true>(c, P) : launch_edge_rows_t<MAG_KIND_IDENTITY, false>(c, P);
     case MAG_KIND_ISO: return fast ? launch_edge_rows_t<MAG_KIND_ISO, true>(c, P) : launch_edge_rows_t<MAG_KIND_ISO, false>(c, P);
@@ -1722,6 +1767,15 @@ static int launch_tet_rows_k(mag_ctx* c, const SweepParams& P, bool fast)
 }
 static int launch_tet_rows(mag_ctx* c, const SweepParams& P, bool fast)
 {
+  constexpr uint32_t kElemFull = MAG_OP_QUALITIES | MAG_OP_MARK_BAD;
+  if (fast && c->elem_flags_zero && P.use_max && c->lean_sweep && (P.ops & kElemFull) == kElemFull) {
+    switch (c->kind) {
+      case MAG_KIND_IDENTITY: return launch_tet_rows_z<MAG_KIND_IDENTITY>(c, P);
+      case MAG_KIND_ISO: return launch_tet_rows_z<MAG_KIND_ISO>(c, P);
+      case MAG_KIND_ANISO: return launch_tet_rows_z<MAG_KIND_ANISO>(c, P);
+      default: return launch_tet_rows_z<MAG_KIND_LOGM>(c, P);
+    }
+  }
   switch (c->kind) {
     case MAG_KIND_IDENTITY: return launch_tet_rows_k<MAG_KIND_IDENTITY>(c, P, fast);
     case MAG_KIND_ISO: return launch_tet_rows_k<MAG_KIND_ISO>(c, P, fast);

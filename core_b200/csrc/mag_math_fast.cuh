@@ -43,56 +43,79 @@ __device__ __forceinline__ double edge_iso(const double ra[4], const double rb[4
 //   d^T M d = A0^2/(N0 h0^2) + (N0 A1 - G A0)^2/(N0 E h1^2) + D^2/(E h2^2)
 // brought to the common denominator N0 E (h0 h1 h2)^2.  Returns numerator and denominator (both >= 0);
 // the metric length is sqrt(num/den) = num * rsqrt(num * den).
-__device__ __forceinline__ void aniso_point_nd(const double* __restrict__ a, const double* __restrict__ dl, double t,
-                                               double dx, double dy, double dz, double& num, double& den)
+// Every contraction is written out (fma / __dmul_rn / __dadd_rn): the same edge must get the same bits from every kernel
+// that evaluates it (whole-part rows, lean rows, sub-range tiles), whatever nvcc would choose to fuse in each context.
+__device__ __forceinline__ double dot3(double ax, double ay, double az, double bx, double by, double bz)
 {
-  const double h0 = fma(t, dl[0], a[3]), h1 = fma(t, dl[1], a[4]), h2 = fma(t, dl[2], a[5]);
-  const double c0x = fma(t, dl[3], a[6]), c0y = fma(t, dl[4], a[7]), c0z = fma(t, dl[5], a[8]);
-  const double c1x = fma(t, dl[6], a[9]), c1y = fma(t, dl[7], a[10]), c1z = fma(t, dl[8], a[11]);
-  const double Xx = c0y * c1z - c0z * c1y, Xy = c0z * c1x - c0x * c1z, Xz = c0x * c1y - c0y * c1x;
-  const double N0 = c0x * c0x + c0y * c0y + c0z * c0z;
-  const double E = Xx * Xx + Xy * Xy + Xz * Xz;
-  const double G = c0x * c1x + c0y * c1y + c0z * c1z;
-  const double A0 = dx * c0x + dy * c0y + dz * c0z;
-  const double A1 = dx * c1x + dy * c1y + dz * c1z;
-  const double D = dx * Xx + dy * Xy + dz * Xz;
-  const double a1 = N0 * A1 - G * A0;
-  const double q0 = h1 * h2, q1 = h0 * h2, q2 = h0 * h1, pp = q0 * h0;
-  const double t0 = A0 * q0, t1 = a1 * q1, t2 = D * q2;
-  num = (t0 * t0) * E + t1 * t1 + (t2 * t2) * N0;
-  den = (N0 * E) * (pp * pp);
+  return fma(az, bz, fma(ay, by, __dmul_rn(ax, bx)));
+}
+// a b - c d
+__device__ __forceinline__ double diffprod(double a, double b, double c, double d) { return fma(a, b, -__dmul_rn(c, d)); }
+
+// one Gauss point: c = interpolated {h0, h1, h2, c0x, c0y, c0z, c1x, c1y, c1z}, (dx, dy, dz) = x1 - x0
+__device__ __forceinline__ void aniso_point_nd(const double* __restrict__ c, double dx, double dy, double dz, double& num, double& den)
+{
+  const double h0 = c[0], h1 = c[1], h2 = c[2];
+  const double c0x = c[3], c0y = c[4], c0z = c[5], c1x = c[6], c1y = c[7], c1z = c[8];
+  const double Xx = diffprod(c0y, c1z, c0z, c1y), Xy = diffprod(c0z, c1x, c0x, c1z), Xz = diffprod(c0x, c1y, c0y, c1x);
+  const double N0 = dot3(c0x, c0y, c0z, c0x, c0y, c0z);
+  const double E = dot3(Xx, Xy, Xz, Xx, Xy, Xz);
+  const double G = dot3(c0x, c0y, c0z, c1x, c1y, c1z);
+  const double A0 = dot3(dx, dy, dz, c0x, c0y, c0z);
+  const double A1 = dot3(dx, dy, dz, c1x, c1y, c1z);
+  const double D = dot3(dx, dy, dz, Xx, Xy, Xz);
+  const double a1 = diffprod(N0, A1, G, A0);
+  const double q0 = __dmul_rn(h1, h2), q1 = __dmul_rn(h0, h2), q2 = __dmul_rn(h0, h1), pp = __dmul_rn(q0, h0);
+  const double t0 = __dmul_rn(A0, q0), t1 = __dmul_rn(a1, q1), t2 = __dmul_rn(D, q2);
+  num = fma(__dmul_rn(t2, t2), N0, fma(t1, t1, __dmul_rn(__dmul_rn(t0, t0), E)));
+  den = __dmul_rn(__dmul_rn(N0, E), __dmul_rn(pp, pp));
 }
 
-// sqrt(num/den) with one reciprocal square root (no IEEE divide / sqrt sequences); exact zero for a zero-length edge
-__device__ __forceinline__ double sqrt_ratio(double num, double den)
+// 1 / sqrt(x) for a positive normal x: MUFU.RSQ64H (2^-22) + one cubic step, as CUDA's rsqrt() does it, without the
+// special-case branch (the caller tests the range once for both Gauss points)
+__device__ __forceinline__ double rsqrt_core(double x)
 {
-  const double x = num * den;
-  const double r = rsqrt(x);
-  return x > 0.0 ? num * r : 0.0;
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x, __dmul_rn(y, y), 1.0);          // 1 - x y^2
+  const double p = fma(e, 0.375, 0.5);
+  return fma(__dmul_rn(y, e), p, y);                       // y (1 + e/2 + 3 e^2/8)
 }
 
+// 0.5 (sqrt(np/dp) + sqrt(nm/dm)) with the square roots as n rsqrt(n d); exact zero for a zero-length edge
+__device__ __forceinline__ double half_sum_sqrt_ratios(double np, double dp, double nm, double dm)
+{
+  const double xp = __dmul_rn(np, dp), xm = __dmul_rn(nm, dm);
+  double sp, sm;
+  // both products positive, normal and far from the ends of the exponent range (2^-900 .. 2^+900): an integer test of the
+  // high words (negative values and NaN fail it through the sign bit / the top exponent)
+  const unsigned hp = (unsigned)__double2hiint(xp) - 0x07b00000u, hm = (unsigned)__double2hiint(xm) - 0x07b00000u;
+  if (hp < 0x70800000u && hm < 0x70800000u) {
+    sp = __dmul_rn(np, rsqrt_core(xp));
+    sm = __dmul_rn(nm, rsqrt_core(xm));
+  } else {                                                 // zero-length edges, sizes beyond 1e+-23: rare
+    sp = xp > 0.0 ? __dmul_rn(np, rsqrt(xp)) : 0.0;
+    sm = xm > 0.0 ? __dmul_rn(nm, rsqrt(xm)) : 0.0;
+  }
+  return __dmul_rn(0.5, __dadd_rn(sp, sm));
+}
+
+// The records are consumed first -- both Gauss points' interpolated values c = a + t (b - a) -- so a and b are dead
+// before the long part starts (the kernels keep other records in flight meanwhile: registers)
 __device__ __forceinline__ double edge_aniso(const double* __restrict__ a, const double* __restrict__ b)
 {
   const double dx = b[0] - a[0], dy = b[1] - a[1], dz = b[2] - a[2]; // 2d; the 1/2 is applied at the end
-  double dl[9];
+  double cp[9], cm[9];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) dl[i] = b[3 + i] - a[3 + i];
-#ifdef MAG_EDGE_SEQ
-  // one Gauss point after the other (not unrolled): fewer live registers, less instruction-level parallelism
-  double len = 0;
-#pragma unroll 1
-  for (int p = 0; p < 2; ++p) {
-    double n_, d_;
-    aniso_point_nd(a, dl, p ? kNP0 : kNP1, dx, dy, dz, n_, d_);
-    len += sqrt_ratio(n_, d_);
+  for (int i = 0; i < 9; ++i) {
+    const double dl = b[3 + i] - a[3 + i];
+    cp[i] = fma(kNP1, dl, a[3 + i]);   // xi = +XI: weights (kNP0, kNP1)
+    cm[i] = fma(kNP0, dl, a[3 + i]);   // xi = -XI: weights (kNP1, kNP0)
   }
-  return 0.5 * len;
-#else
   double np, dp, nm, dm;
-  aniso_point_nd(a, dl, kNP1, dx, dy, dz, np, dp);  // xi = +XI: weights (kNP0, kNP1)
-  aniso_point_nd(a, dl, kNP0, dx, dy, dz, nm, dm);  // xi = -XI: weights (kNP1, kNP0)
-  return 0.5 * (sqrt_ratio(np, dp) + sqrt_ratio(nm, dm));
-#endif
+  aniso_point_nd(cp, dx, dy, dz, np, dp);
+  aniso_point_nd(cm, dx, dy, dz, nm, dm);
+  return half_sum_sqrt_ratios(np, dp, nm, dm);
 }
 
 // log-Euclidean field.  The length at a Gauss point is sqrt(sum_k exp(lambda_k) (v_k . j)^2), j = (x1 - x0) / 2, with
@@ -226,21 +249,21 @@ __device__ __forceinline__ double tet_quality(const V3 x[4], const M3& Q, double
   for (int i = 0; i < 3; ++i) {
     const double ex = x[i + 1].x - x[0].x, ey = x[i + 1].y - x[0].y, ez = x[i + 1].z - x[0].z;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) y[i][k] = ex * Q.m[0][k] + ey * Q.m[1][k] + ez * Q.m[2][k];
+    for (int k = 0; k < 3; ++k) y[i][k] = fma(ez, Q.m[2][k], fma(ey, Q.m[1][k], __dmul_rn(ex, Q.m[0][k])));
   }
-  double s = 0;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) s += y[i][0] * y[i][0] + y[i][1] * y[i][1] + y[i][2] * y[i][2];
-  const int pa[3] = {0, 0, 1}, pb[3] = {1, 2, 2};
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const double u = y[pb[i]][0] - y[pa[i]][0], v = y[pb[i]][1] - y[pa[i]][1], w = y[pb[i]][2] - y[pa[i]][2];
-    s += u * u + v * v + w * w;
-  }
-  const double det = y[0][0] * (y[1][1] * y[2][2] - y[1][2] * y[2][1]) - y[0][1] * (y[1][0] * y[2][2] - y[1][2] * y[2][0]) +
-                     y[0][2] * (y[1][0] * y[2][1] - y[1][1] * y[2][0]);
-  const double V = det * (1.0 / 6.0);
-  const double q = 15552.0 * (V * V) / (s * s * s);
+  // sum of the six squared edge lengths of the points 0, y1, y2, y3:  4 sum |y_i|^2 - |sum y_i|^2  (every term of the
+  // difference is bounded by 4 s, so no accuracy is lost: s >= sum |y_i|^2)
+  const double n0 = dot3(y[0][0], y[0][1], y[0][2], y[0][0], y[0][1], y[0][2]);
+  const double n1 = dot3(y[1][0], y[1][1], y[1][2], y[1][0], y[1][1], y[1][2]);
+  const double n2 = dot3(y[2][0], y[2][1], y[2][2], y[2][0], y[2][1], y[2][2]);
+  const double Sx = __dadd_rn(__dadd_rn(y[0][0], y[1][0]), y[2][0]), Sy = __dadd_rn(__dadd_rn(y[0][1], y[1][1]), y[2][1]),
+               Sz = __dadd_rn(__dadd_rn(y[0][2], y[1][2]), y[2][2]);
+  const double s = fma(4.0, __dadd_rn(__dadd_rn(n0, n1), n2), -dot3(Sx, Sy, Sz, Sx, Sy, Sz));
+  const double m0 = diffprod(y[1][1], y[2][2], y[1][2], y[2][1]), m1 = diffprod(y[1][0], y[2][2], y[1][2], y[2][0]),
+               m2 = diffprod(y[1][0], y[2][1], y[1][1], y[2][0]);
+  const double det = fma(y[0][2], m2, fma(-y[0][1], m1, __dmul_rn(y[0][0], m0)));
+  const double V = __dmul_rn(det, 1.0 / 6.0);
+  const double q = __ddiv_rn(__dmul_rn(15552.0, __dmul_rn(V, V)), __dmul_rn(__dmul_rn(s, s), s));
   return V < 0 ? -q : q;
 }
 

@@ -145,7 +145,7 @@ k_tet_weights(int32_t nt, int32_t elem_off, const int4* __restrict__ tet_v, cons
     else if (w < w_min) w = w_min;
     weight[elem_off + t] = w;
   }
-  if (eig) atomicAdd(&st->n_eigen_fail, 1ull);
+  if (eig) atomicAdd(&st->n_eigen_aux, 1ull);
 }
 
 // measure(triangle) on a 2-D part: TriangleIntegration::N2 (apf/apfIntegrate.cc:146-159), three points of weight 1/3/2;
@@ -227,7 +227,7 @@ k_tri_weights(int32_t nt, const int32_t* __restrict__ tri_v, const double* __res
     else if (w < w_min) w = w_min;
     weight[t] = w;
   }
-  if (eig) atomicAdd(&st->n_eigen_fail, 1ull);
+  if (eig) atomicAdd(&st->n_eigen_aux, 1ull);
 }
 
 // ------------------------------------------------------------------ sliver classification
@@ -385,7 +385,7 @@ k_sliver_codes(int32_t nt, int32_t elem_off, const int4* __restrict__ tet_v, con
     match[2 * (int64_t)(elem_off + t)] = rot;
     match[2 * (int64_t)(elem_off + t) + 1] = idx;
   }
-  if (eig) atomicAdd(&st->n_eigen_fail, 1ull);
+  if (eig) atomicAdd(&st->n_eigen_aux, 1ull);
 }
 
 // ma::clearFlagFromDimension (ma/maAdapt.cc:139-147) / ma::unMarkBadQuality (ma/maShape.cc:138-150) on the resident words
@@ -621,7 +621,7 @@ int mag_element_weights(mag_ctx* c, double w_max, double w_min, int fp_mode, dou
   // layer elements: the reference weighs a prism by its base triangle (maBalance.cc:31-37), which needs the face's own
   // vertex order; they get 0 here and stay with the reference
   if (c->np + c->npy) MAG_CUDA(c, cudaMemsetAsync(c->d_weight, 0, (size_t)(c->np + c->npy) * sizeof(double), c->stream));
-  MAG_CUDA(c, cudaMemsetAsync(&c->d_stats->n_eigen_fail, 0, sizeof(unsigned long long), c->stream));
+  MAG_CUDA(c, cudaMemsetAsync(&c->d_stats->n_eigen_aux, 0, sizeof(unsigned long long), c->stream));
   if (c->nt) {
     const bool fast = fp_mode == MAG_FP_FAST;
     int rc;
@@ -645,10 +645,10 @@ int mag_element_weights(mag_ctx* c, double w_max, double w_min, int fp_mode, dou
     if (rc) return rc;
   }
   if (out) MAG_CUDA(c, cudaMemcpyAsync(out, c->d_weight, (size_t)nel * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  MAG_CUDA(c, cudaMemcpyAsync(&c->h_stats->n_eigen_fail, &c->d_stats->n_eigen_fail, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  MAG_CUDA(c, cudaMemcpyAsync(&c->h_stats->n_eigen_aux, &c->d_stats->n_eigen_aux, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   MAG_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (c->h_stats->n_eigen_fail)
-    return mag_fail(c, MAG_ERR_EIGEN, "eigenQR failed in %llu blocks of the weight sweep (apf::eigen asserts convergence, apfMatrix.cc:76)", c->h_stats->n_eigen_fail);
+  if (c->h_stats->n_eigen_aux)
+    return mag_fail(c, MAG_ERR_EIGEN, "eigenQR failed in %llu blocks of the weight sweep (apf::eigen asserts convergence, apfMatrix.cc:76)", c->h_stats->n_eigen_aux);
   return MAG_OK;
 }
 
@@ -680,14 +680,14 @@ int mag_cavity_quality(mag_ctx* c, int64_t ncav, const int64_t* offsets, const i
   if (qualities) MAG_CUDA(c, cudaMalloc(&dq.p, (size_t)ntet * 8));
   MAG_CUDA(c, cudaMemcpyAsync(off.p, offsets, (size_t)(ncav + 1) * 8, cudaMemcpyHostToDevice, c->stream));
   MAG_CUDA(c, cudaMemcpyAsync(tv.p, tet_v, (size_t)ntet * 16, cudaMemcpyHostToDevice, c->stream));
-  MAG_CUDA(c, cudaMemsetAsync(&c->d_stats->n_eigen_fail, 0, sizeof(unsigned long long), c->stream));
+  MAG_CUDA(c, cudaMemsetAsync(&c->d_stats->n_eigen_aux, 0, sizeof(unsigned long long), c->stream));
   if ((rc = magk_cavity_quality(c, fp_mode, ncav, (const int64_t*)off.p, (const int32_t*)tv.p, use_max_metric, (double*)dw.p, (double*)dq.p))) return rc;
   MAG_CUDA(c, cudaMemcpyAsync(worst, dw.p, (size_t)ncav * 8, cudaMemcpyDeviceToHost, c->stream));
   if (qualities) MAG_CUDA(c, cudaMemcpyAsync(qualities, dq.p, (size_t)ntet * 8, cudaMemcpyDeviceToHost, c->stream));
-  MAG_CUDA(c, cudaMemcpyAsync(&c->h_stats->n_eigen_fail, &c->d_stats->n_eigen_fail, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  MAG_CUDA(c, cudaMemcpyAsync(&c->h_stats->n_eigen_aux, &c->d_stats->n_eigen_aux, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   MAG_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (c->h_stats->n_eigen_fail)
-    return mag_fail(c, MAG_ERR_EIGEN, "eigenQR failed in %llu blocks of the cavity sweep (apf::eigen asserts convergence, apfMatrix.cc:76)", c->h_stats->n_eigen_fail);
+  if (c->h_stats->n_eigen_aux)
+    return mag_fail(c, MAG_ERR_EIGEN, "eigenQR failed in %llu blocks of the cavity sweep (apf::eigen asserts convergence, apfMatrix.cc:76)", c->h_stats->n_eigen_aux);
   return MAG_OK;
 }
 
@@ -719,7 +719,7 @@ int mag_sliver_codes(mag_ctx* c, const int32_t* face0_v, double good_quality, in
   // layer elements: code 0, no match
   MAG_CUDA(c, cudaMemsetAsync(dc.p, 0, (size_t)nel * 4, c->stream));
   MAG_CUDA(c, cudaMemsetAsync(dm.p, 0xff, (size_t)nel * 8, c->stream));
-  MAG_CUDA(c, cudaMemsetAsync(&c->d_stats->n_eigen_fail, 0, sizeof(unsigned long long), c->stream));
+  MAG_CUDA(c, cudaMemsetAsync(&c->d_stats->n_eigen_aux, 0, sizeof(unsigned long long), c->stream));
   if (c->nt) {
     const int64_t blocks = (c->nt + kWThreads - 1) / kWThreads;
     const unsigned g = (unsigned)(blocks < (int64_t)c->n_sms * 32 ? blocks : (int64_t)c->n_sms * 32);
@@ -739,10 +739,10 @@ int mag_sliver_codes(mag_ctx* c, const int32_t* face0_v, double good_quality, in
   }
   MAG_CUDA(c, cudaMemcpyAsync(codes, dc.p, (size_t)nel * 4, cudaMemcpyDeviceToHost, c->stream));
   MAG_CUDA(c, cudaMemcpyAsync(match, dm.p, (size_t)nel * 8, cudaMemcpyDeviceToHost, c->stream));
-  MAG_CUDA(c, cudaMemcpyAsync(&c->h_stats->n_eigen_fail, &c->d_stats->n_eigen_fail, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  MAG_CUDA(c, cudaMemcpyAsync(&c->h_stats->n_eigen_aux, &c->d_stats->n_eigen_aux, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   MAG_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (c->h_stats->n_eigen_fail)
-    return mag_fail(c, MAG_ERR_EIGEN, "eigenQR failed in %llu blocks of the sliver sweep (apf::eigen asserts convergence, apfMatrix.cc:76)", c->h_stats->n_eigen_fail);
+  if (c->h_stats->n_eigen_aux)
+    return mag_fail(c, MAG_ERR_EIGEN, "eigenQR failed in %llu blocks of the sliver sweep (apf::eigen asserts convergence, apfMatrix.cc:76)", c->h_stats->n_eigen_aux);
   return MAG_OK;
 }
 

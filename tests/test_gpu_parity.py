@@ -892,6 +892,72 @@ def test_resweep_host_equals_resident(cb, kindname):
     q.close()
 
 
+def _part_with_env(cb, env):
+    """A Part created under the given environment (the library reads its A/B switches in mag_create)."""
+    import os
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return cb.Part(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("kindname", ["iso", "aniso", "logm"])
+@pytest.mark.parametrize("mesh", ["lattice", "jittered", "hub"])
+def test_lean_kernels_equal_general(cb, kindname, mesh):
+    """The lean whole-part kernels (mag_lean.cuh: MAG_FP_FAST, zero incoming flag words, full marking sweep) return bit for
+    bit what the general row kernels and the tile kernels of the sub-range path return: lengths, qualities, flag words,
+    counts, min / max and the near-threshold lists (the lattice puts a whole edge family exactly on the collapse threshold)."""
+    from oracle import mao
+    rng = np.random.default_rng(21)
+    n = 13
+    if mesh == "hub":
+        xyz, ev, tv = _shuffled_hub_mesh(cb, rng)
+    else:
+        xyz, ev, tv = cb.boxmesh.kuhn_box(n, n, n + 2)
+        if mesh == "jittered":
+            xyz = cb.fields.jitter(xyz, 0.3 / n)
+    nv = len(xyz)
+    if mesh == "lattice":
+        H, R = cb.fields.shock_rotating(xyz, 1.0 / n)
+        s = cb.fields.iso_linear(xyz, 1.0 / n)
+    else:
+        R = util.random_frames(nv, rng)
+        H = (1.0 / n) * np.exp(rng.uniform(-1.0, 1.0, (nv, 3)))
+        s = (1.0 / n) * np.exp(rng.uniform(-1, 1, nv))
+    kind, ma, mb = {"iso": (mao.ISO, s, None), "aniso": (mao.ANISO, H, R),
+                    "logm": (mao.LOGM, None, mao.logm_from_frames(H, R, 0))}[kindname]
+    eo = (rng.random(len(ev)) < 0.9).astype(np.uint8)
+    lo = (rng.random(len(tv)) < 0.9).astype(np.uint8)
+    ops = cb.OP_ALL & ~cb.OP_LAYER_CHECK
+    res = []
+    for env in ({}, {"MAG_LEAN_SWEEP": "0"}, {"MAG_LEGACY_SWEEP": "1"}):
+        p = _part_with_env(cb, env)
+        p.set_mesh(xyz, ev, tv, edge_owned=eo, elem_owned=lo)
+        util.set_part_metric(p, kind, ma, mb)
+        p.clear_flags()
+        p.sweep(ops, good_quality=0.1, fp_mode=cb.FP_FAST)
+        st = p.stats()
+        res.append((p.edge_lengths(), p.qualities(), p.flags(), st, sorted(p.near_threshold(0)[0].tolist()),
+                    sorted(p.near_threshold(1)[0].tolist())))
+        p.close()
+    L0, q0, (ef0, lf0), st0, ne0, nl0 = res[0]
+    if mesh == "lattice" and kindname == "aniso":
+        assert st0["n_near_threshold"] > 1000          # the z edges measure exactly 0.5
+    for L, q, (ef, lf), st, ne_, nl in res[1:]:
+        assert np.array_equal(L, L0), "%d lengths differ, max rel %.3g" % (np.count_nonzero(L != L0), util.rel_err(L, L0))
+        assert np.array_equal(q, q0), "%d qualities differ" % np.count_nonzero(q != q0)
+        assert np.array_equal(ef, ef0) and np.array_equal(lf, lf0)
+        for k in ("n_split", "n_collapse", "n_bad", "n_edges_evaluated", "n_elems_evaluated", "n_near_threshold", "min_quality", "max_length"):
+            assert st[k] == st0[k], k
+        assert ne_ == ne0 and nl == nl0
+
+
 def test_baseline_configs_1_and_2_reference_values(cb):
     """BASELINE configs[0] (n = 20, isotropic h = hbar (1 + 2x)) and configs[1] (n = 55, 998,250 tets, planar shock
     layer AnisoSizeField) on the device against the values the compiled reference printed at survey time
