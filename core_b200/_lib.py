@@ -20,7 +20,7 @@ SYMBOLS = [
     "mag_get_near_threshold", "mag_set_metric_logm_from_frames",
     "mag_timing_begin", "mag_timing_read", "mag_launch_count", "mag_get_row_layout",
     "mag_comm_unique_id", "mag_comm_init", "mag_set_edge_links", "mag_reconcile_edge_flags",
-    "mag_sync_edge_flags", "mag_allreduce_stats",
+    "mag_sync_edge_flags", "mag_check_edge_flag_consistency", "mag_allreduce_stats",
 ]
 
 
@@ -119,6 +119,7 @@ def lib():
     L.mag_set_edge_links.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     L.mag_reconcile_edge_flags.argtypes = [vp, i32]
     L.mag_sync_edge_flags.argtypes = [vp, i32]
+    L.mag_check_edge_flag_consistency.argtypes = [vp, i32, C.POINTER(i64)]
     L.mag_allreduce_stats.argtypes = [vp, C.POINTER(MagStats)]
     _lib = L
     return L

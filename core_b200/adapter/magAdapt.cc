@@ -47,7 +47,16 @@ static void parallelFor(size_t n, int nthreads, const std::function<void(size_t,
   for (size_t i = 0; i < pool.size(); ++i) pool[i].join();
 }
 
+/* FNV-1a over the bytes of the per-vertex arrays: what the device holds of the coordinates and the size field */
+static unsigned long long hashBytes(unsigned long long h, const void* p, size_t n)
+{
+  const unsigned char* b = (const unsigned char*)p;
+  for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+  return h;
+}
+
 struct Export {
+  unsigned long long vertHash;            /* hash of xyz / ma / mb as uploaded */
   std::vector<double> xyz, ma, mb;
   std::vector<int> edge_v, tet_v, prism_v, pyr_v, tri_v;   /* tri_v: the elements of a 2-D mesh */
   std::vector<unsigned char> edge_owned, elem_owned;
@@ -64,6 +73,8 @@ struct Access {
     g->fSizes = sizes; g->fFrames = frames; g->fIso = iso; g->fnAniso = fa; g->fnIso = fi;
   }
   static double lengthAt(GpuSizeField* g, size_t k) { return g->lengths[k]; }
+  static void resetOrder(GpuSizeField* g) { g->lastDim = g->lastId = -1; }
+  static size_t exportedElems(GpuSizeField* g) { return g->exported ? g->exported->elems.size() : 0; }
   static bool isDirty(GpuSizeField* g) { return g->dirty; }
   static int fpMode(GpuSizeField* g) { return g->fpMode; }
   static int vertSlotOf(GpuSizeField* g, ma::Entity* v) { return g->vertSlot[apf::getMdsIndex(g->mesh, v)]; }
@@ -79,12 +90,18 @@ struct Access {
     return true;
   }
 
-  /* one pass over the mesh in m->begin(d) order (mds.c:745-777), vertex ids compacted to 0..nv-1 */
-  static void exportMesh(GpuSizeField* g, Export& x)
+  static unsigned long long vertexHash(const Export& x)
+  {
+    unsigned long long h = 1469598103934665603ull;
+    h = hashBytes(h, x.xyz.data(), x.xyz.size() * sizeof(double));
+    h = hashBytes(h, x.ma.data(), x.ma.size() * sizeof(double));
+    return hashBytes(h, x.mb.data(), x.mb.size() * sizeof(double));
+  }
+
+  /* the per-vertex part of an export: coordinates and size-field values in m->begin(0) order, vertex ids compacted to 0..nv-1 */
+  static void exportVertices(GpuSizeField* g, Export& x)
   {
     ma::Mesh* m = g->mesh;
-    const int mdim = m->getDimension();
-    if (mdim != 3 && mdim != 2) { fprintf(stderr, "mag adapter: only 2D and 3D meshes are supported\n"); abort(); }
     size_t nv = m->count(0);
     std::vector<int>& vslot = g->vertSlot;
     vslot.assign(vslot.size(), -1);
@@ -124,6 +141,20 @@ struct Access {
       ++k;
     }
     m->end(it);
+    x.vertHash = vertexHash(x);
+  }
+
+  /* one pass over the mesh in m->begin(d) order (mds.c:745-777) */
+  static void exportMesh(GpuSizeField* g, Export& x)
+  {
+    ma::Mesh* m = g->mesh;
+    const int mdim = m->getDimension();
+    if (mdim != 3 && mdim != 2) { fprintf(stderr, "mag adapter: only 2D and 3D meshes are supported\n"); abort(); }
+    exportVertices(g, x);
+    std::vector<int>& vslot = g->vertSlot;
+    apf::MeshIterator* it;
+    ma::Entity* e;
+    int k;
     size_t ne = m->count(1);
     x.edge_v.resize(2 * ne); x.edge_owned.resize(ne); x.edges.resize(ne);
     g->edgeSlot.assign(g->edgeSlot.size(), -1);
@@ -196,6 +227,11 @@ struct Access {
     MAG_DO(c, mag_set_mesh(c, (int64_t)(x.xyz.size() / 3), x.xyz.data(), (int64_t)x.edges.size(), x.edge_v.data(),
                            (int64_t)(x.tet_v.size() / 4), x.tet_v.data(), (int64_t)(x.prism_v.size() / 6), x.prism_v.data(),
                            (int64_t)(x.pyr_v.size() / 5), x.pyr_v.data(), x.edge_owned.data(), x.elem_owned.data()));
+    uploadField(g, x);
+  }
+  static void uploadField(GpuSizeField* g, Export& x)
+  {
+    mag_ctx* c = g->ctx;
     if (g->kind == 1) MAG_DO(c, mag_set_metric_iso(c, x.ma.data()));
     else if (g->kind == 2) MAG_DO(c, mag_set_metric_aniso(c, x.ma.data(), x.mb.data()));
     else if (x.logm_direct) MAG_DO(c, mag_set_metric_logm(c, x.mb.data()));
@@ -209,8 +245,20 @@ struct Access {
     ma::Mesh* m = g->mesh;
     const int dim = m->getDimension();
     if (g->exported && g->topoValid && g->exported->edges.size() == m->count(1) && g->exported->elems.size() == m->count(dim) &&
-        g->exported->xyz.size() == 3 * m->count(0))
-      return *g->exported;
+        g->exported->xyz.size() == 3 * m->count(0)) {
+      /* the connectivity is trusted (no callback, no out-of-order query, same counts); coordinates and field values are
+         not -- snapping (ma/ma.cc:37, setPoint) and in-place edits of the size fields reach no callback.  The vertex walk is a
+         fourteenth of an export: redo it, and if anything moved, send the per-vertex arrays again (connectivity stays) */
+      Export& x = *g->exported;
+      const unsigned long long before = x.vertHash;
+      exportVertices(g, x);
+      if (x.vertHash != before) {
+        MAG_DO(g->ctx, mag_set_coords(g->ctx, x.xyz.data()));
+        uploadField(g, x);
+        g->dirty = true;
+      }
+      return x;
+    }
     if (!g->exported) g->exported = new Export;
     *g->exported = Export();
     exportMesh(g, *g->exported);
@@ -254,13 +302,14 @@ struct Access {
       for (size_t i = 0; i < lf.size(); ++i) if (lf2[i] != lf[i]) ma::setFlags(a, x.elems[i], lf2[i]);
     }
     g->dirty = true; /* the per-entity snapshot (zero incoming flags) was not refreshed by this sweep */
+    g->lastDim = g->lastId = -1;
     return st;
   }
 };
 
 GpuSizeField::GpuSizeField()
   : mesh(0), wrapped(0), ctx(0), kind(0), logVariant(0), fpMode(MAG_FP_STRICT), dirty(true), topoValid(false), exported(0), exportThreads(1), streak(0), lastGoodQuality(-1),
-    fSizes(0), fFrames(0), fIso(0), fnAniso(0), fnIso(0), nNonSimplex(0), lastDim(-1), lastId(-1)
+    fSizes(0), fFrames(0), fIso(0), fnAniso(0), fnIso(0), nNonSimplex(0), lastDim(-1), lastId(-1), snapshotHash(0)
 {
 }
 
@@ -287,12 +336,32 @@ bool GpuSizeField::serve(ma::Entity* e, int dim, int& slot)
      out-of-order query, a callback, a changed count: a cavity operator at work -- goes to the wrapped reference field. */
   const int id = apf::getMdsIndex(mesh, e);
   const bool in_order = (dim == lastDim && id > lastId);
+  /* a whole-mesh loop of the reference starts at the first entity of m->begin(dim): a query for that entity opens a sweep at
+     once (meshes of any size; the first 4095 queries no longer go to the CPU).  A loop whose first entities are skipped by
+     their flags is still recognised by its length (kSweepDetect in-order queries). */
+  bool first = false;
+  if (!in_order) {
+    apf::MeshIterator* it = mesh->begin(dim);
+    ma::Entity* e0 = mesh->iterate(it);
+    mesh->end(it);
+    first = (e0 == e);
+  }
   lastDim = dim;
   lastId = id;
-  if (!in_order) { dirty = true; streak = 0; topoValid = false; return false; }
+  if (!in_order && !first) { dirty = true; streak = 0; topoValid = false; return false; }
   if (!dirty && ((long)mesh->count(1) != (long)lengths.size() || (long)mesh->count(mesh->getDimension()) != (long)qualities.size())) dirty = true;
-  if (dirty) {
-    if (++streak < kSweepDetect) return false;
+  if (first) {
+    /* sweep start: the snapshot is reused only if the mesh is still what it was taken from (ensureExported re-reads the
+       vertices and compares) */
+    if (!dirty) {
+      Export& x = Access::ensureExported(this);
+      if (x.vertHash != snapshotHash) dirty = true;
+    }
+    if (dirty) refresh(lastGoodQuality);
+  } else if (dirty) {
+    /* in order, but not (yet) known to be a sweep: the wrapped field answers, and the device export is no longer trusted
+       either -- a count-preserving operator (swap, snap) may be at work without a callback reaching us */
+    if (++streak < kSweepDetect) { topoValid = false; return false; }
     refresh(lastGoodQuality);
   }
   const std::vector<int>& map = dim == 1 ? edgeSlot : tetSlot;
@@ -321,6 +390,7 @@ void GpuSizeField::refresh(double goodQuality)
   lastGoodQuality = goodQuality;
   dirty = false;
   streak = 0;
+  snapshotHash = x.vertHash;
 }
 
 double GpuSizeField::measure(ma::Entity* e)
@@ -441,6 +511,7 @@ double getMaximumEdgeLength(ma::Mesh* m, ma::SizeField* sf)
 {
   GpuSizeField* g = gpuField(sf);
   g->refresh(-1);
+  Access::resetOrder(g);
   mag_stats st;
   MAG_DO(g->ctx, mag_get_stats(g->ctx, &st));
   return m->getPCU()->Max<double>(st.max_length); /* maSize.cc:689 */
@@ -449,6 +520,7 @@ void getEdgeLengthsInMetricSpace(ma::Mesh* m, ma::SizeField* sf, std::vector<dou
 {
   GpuSizeField* g = gpuField(sf);
   g->refresh(-1);
+  Access::resetOrder(g);
   /* ma::stats keeps owned edges only, iteration order (maStats.cc:33-45) */
   out.clear();
   apf::MeshIterator* it = m->begin(1);
@@ -461,6 +533,7 @@ void getLinearQualitiesInMetricSpace(ma::Mesh* m, ma::SizeField* sf, std::vector
 {
   GpuSizeField* g = gpuField(sf);
   g->refresh(-1);
+  Access::resetOrder(g);
   /* owned simplex elements, cbrt of the mean ratio cubed (maStats.cc:12-31) */
   out.clear();
   const int dim = m->getDimension();
@@ -481,6 +554,7 @@ void stats(ma::Mesh* m, ma::SizeField* sf, std::vector<double>& edgeLengths, std
   if (!inMetric) { ma::stats(m, sf, edgeLengths, linearQualities, false); return; }
   GpuSizeField* g = gpuField(sf);
   g->refresh(-1);                                   /* one export + one sweep serve both vectors */
+  Access::resetOrder(g);
   const int dim = m->getDimension();
   apf::MeshIterator* it = m->begin(dim);            /* qualities first, as getStatsInMetricSpace does (maStats.cc:95-103) */
   ma::Entity* e;
@@ -503,8 +577,10 @@ ma::Tag* getElementWeights(ma::Adapt* a)
 {
   GpuSizeField* g = gpuField(a->sizeField);
   ma::Mesh* m = a->mesh;
-  if (Access::isDirty(g)) g->refresh(a->input->goodQuality);
+  g->refresh(a->input->goodQuality);        /* re-validates (or redoes) the export: never a stale device copy */
+  Access::resetOrder(g);
   const int dim = m->getDimension();
+  if (Access::exportedElems(g) != m->count(dim)) { fprintf(stderr, "mag adapter: export out of step with the mesh\n"); abort(); }
   const double w_max = pow(2.0, dim * (a->refinesLeft)), w_min = pow(4.0, -(a->coarsensLeft));
   std::vector<double> w(m->count(dim));
   MAG_DO(g->ctx, mag_element_weights(g->ctx, w_max, w_min, Access::fpMode(g), w.data()));
@@ -525,7 +601,9 @@ void getSliverCodes(ma::Adapt* a, std::vector<int>& codes, std::vector<ma::CodeM
 {
   GpuSizeField* g = gpuField(a->sizeField);
   ma::Mesh* m = a->mesh;
-  if (Access::isDirty(g)) g->refresh(a->input->goodQuality);
+  g->refresh(a->input->goodQuality);
+  Access::resetOrder(g);
+  if (Access::exportedElems(g) != m->count(3)) { fprintf(stderr, "mag adapter: export out of step with the mesh\n"); abort(); }
   const size_t nel = m->count(3), nns = (size_t)Access::nonSimplex(g);
   std::vector<int> face0(3 * (nel - nns)), match(2 * nel);
   codes.assign(nel, 0);

@@ -54,7 +54,9 @@ class GpuSizeField : public ma::SizeField
     int getTransferDimension();
     bool hasNodesOn(int dimension);
 
-    /* the mesh or the field changed behind our back (e.g. coordinates moved by the caller) */
+    /* the CONNECTIVITY changed behind our back without any SizeField callback (a count-preserving edit made by the caller's own
+       code).  Moved vertices (apf::Mesh2::setPoint, snapping) and in-place edits of the size fields need no call: every
+       bulk sweep and every sweep start re-reads the vertices and compares a hash with what the device holds. */
     void invalidate() { dirty = true; topoValid = false; }
     /* MAG_FP_STRICT (default) or MAG_FP_FAST, see include/mag.h */
     void setArithmetic(int fp_mode) { fpMode = fp_mode; invalidate(); }
@@ -95,6 +97,7 @@ class GpuSizeField : public ma::SizeField
     std::vector<int> edgeFlags, elemFlags;        /* flags of the last sweep run on zero incoming words */
     long nNonSimplex;
     int lastDim, lastId;  /* last per-entity query: dimension and MDS index */
+  unsigned long long snapshotHash;   /* vertex hash (coordinates + field) of the export the snapshot was swept from */
     bool serve(ma::Entity* e, int dim, int& slot);
 };
 

@@ -158,6 +158,7 @@ int mag_create(mag_ctx** out, int device)
   { const char* e = getenv("MAG_LEGACY_SWEEP"); c->legacy_sweep = e && e[0] == '1'; }
   { const char* e = getenv("MAG_L2_PREFETCH"); c->l2_prefetch = !(e && e[0] == '0'); }
   { const char* e = getenv("MAG_LEAN_SWEEP"); c->lean_sweep = !(e && e[0] == '0'); }
+  { const char* e = getenv("MAG_GENERAL_ROWS"); c->general_rows = e && e[0] == '1'; }
   c->d_edge_pf = c->d_tet_pf = nullptr; c->n_edge_pf = c->n_tet_pf = 0;
   c->d_vstat = nullptr;
   c->d_edge_bytes = c->d_elem_bytes = nullptr;

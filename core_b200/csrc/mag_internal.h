@@ -108,6 +108,7 @@ struct mag_ctx {
   int32_t* d_edge_pf;    // legacy kernels: L2 prefetch table per ticket (see PfArgs in mag_rows.cuh)
   int32_t* d_tet_pf;
   int64_t n_edge_pf, n_tet_pf;
+  bool general_rows;     // MAG_GENERAL_ROWS=1: sweeps the lean kernels do not serve run the general row kernels instead of the tiles
   bool lean_sweep;       // MAG_LEAN_SWEEP=0: never use the lean kernels of mag_lean.cuh (A/B measurements, tests)
   bool l2_prefetch;      // MAG_L2_PREFETCH=0 switches the L2 prefetch of the vertex arrays off (A/B measurements)
   MagRows erows, trows;  // anchor-row layout of the edges / tets (whole-part sweeps)

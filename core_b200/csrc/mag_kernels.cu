@@ -1661,13 +1661,13 @@ void magk_free_rows(mag_ctx* c) { free_rows(c->erows); free_rows(c->trows); }
 int magk_build_schedule(mag_ctx* c)
 {
   int rc;
-  if (c->legacy_sweep) {
-    int64_t nch;
-    if ((rc = build_order(c, c->ne, MAG_EDGE_TILE_SCHED ? (int64_t)kStrictThreads : (int64_t)kEdgeChunk, c->d_edge_v, 2, c->d_edge_order, nch,
-                          MAG_EDGE_TILE_SCHED ? kEdgeChunk / kStrictThreads : 1, c->d_edge_pf, c->n_edge_pf))) return rc;
-    if ((rc = build_order(c, c->nt, (int64_t)kTetChunk, c->d_tet_v, 4, c->d_tet_order, nch, 1, c->d_tet_pf, c->n_tet_pf))) return rc;
-    return MAG_OK;
-  }
+  // the tile schedule of k_edges / k_tets (a few bytes per 256 entities) is always built: those kernels serve every sweep
+  // the lean row kernels do not (incoming flag words, single marks, strict arithmetic, the log-Euclidean field)
+  int64_t nch;
+  if ((rc = build_order(c, c->ne, MAG_EDGE_TILE_SCHED ? (int64_t)kStrictThreads : (int64_t)kEdgeChunk, c->d_edge_v, 2, c->d_edge_order, nch,
+                        MAG_EDGE_TILE_SCHED ? kEdgeChunk / kStrictThreads : 1, c->d_edge_pf, c->n_edge_pf))) return rc;
+  if ((rc = build_order(c, c->nt, (int64_t)kTetChunk, c->d_tet_v, 4, c->d_tet_order, nch, 1, c->d_tet_pf, c->n_tet_pf))) return rc;
+  if (c->legacy_sweep) return MAG_OK;
   if ((rc = build_rows<2>(c, c->ne, c->d_edge_v, c->erows))) return rc;
   if ((rc = build_rows<4>(c, c->nt, c->d_tet_v, c->trows))) return rc;
   return MAG_OK;
@@ -1690,6 +1690,31 @@ static int launch_edge_rows_t(mag_ctx* c, const SweepParams& P)
   c->n_launches++;
   return MAG_OK;
 }
+// Which kernel family serves a whole-part sweep (measured on B200, n = 203, r2c / r2d):
+//   lean row kernels (mag_lean.cuh)  MAG_FP_FAST over all-zero incoming flag words, every output of the dimension requested,
+//                                    max-Jacobian metric: 1.26 / 0.78 ms (edges / tets) against 1.35 / 0.80 for the tiles;
+//   tile kernels (k_edges / k_tets)  everything else.  The log-Euclidean edge kernel stays with the tiles as well (its QR
+//                                    iteration wants every register: 4.7 ms against 5.4 ms in a row kernel);
+//   general row kernels              only with MAG_GENERAL_ROWS=1 (A/B measurements): 1.43 / 0.82 ms, slower than the tiles.
+static bool lean_edges_ok(const mag_ctx* c, const SweepParams& P, bool fast)
+{
+  constexpr uint32_t kEdgeFull = MAG_OP_LENGTHS | MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE;
+  return fast && c->edge_flags_zero && c->lean_sweep && (P.ops & kEdgeFull) == kEdgeFull && c->kind != MAG_KIND_LOGM;
+}
+static bool lean_tets_ok(const mag_ctx* c, const SweepParams& P, bool fast)
+{
+  constexpr uint32_t kElemFull = MAG_OP_QUALITIES | MAG_OP_MARK_BAD;
+  return fast && c->elem_flags_zero && P.use_max && c->lean_sweep && (P.ops & kElemFull) == kElemFull;
+}
+static bool use_edge_rows(const mag_ctx* c, const SweepParams& P, bool fast)
+{
+  return !c->legacy_sweep && (c->general_rows || lean_edges_ok(c, P, fast));
+}
+static bool use_tet_rows(const mag_ctx* c, const SweepParams& P, bool fast)
+{
+  return !c->legacy_sweep && (c->general_rows || lean_tets_ok(c, P, fast));
+}
+
 // the lean kernels (mag_lean.cuh): MAG_FP_FAST sweeps over all-zero incoming flag words
 template <int KIND>
 static int launch_edge_rows_z(mag_ctx* c, const SweepParams& P)
@@ -1697,7 +1722,7 @@ static int launch_edge_rows_z(mag_ctx* c, const SweepParams& P)
   constexpr int T = EdgeLeanCfg<KIND>::T;
   const int per_sm = blocks_per_sm(c, (const void*)k_edge_rows_z<KIND>, T);
   int64_t g = (int64_t)per_sm * c->n_sms;
-  const int64_t groups = (c->erows.n_slices + kZGroup - 1) / kZGroup;
+  const int64_t groups = (c->erows.n_slices + kEZGroup - 1) / kEZGroup;
   const int64_t need = (groups + T / 32 - 1) / (T / 32);
   if (g > need) g = need;
   k_edge_rows_z<KIND><<<(unsigned)(g < 1 ? 1 : g), T, 0, c->stream>>>(
@@ -1710,10 +1735,10 @@ static int launch_edge_rows_z(mag_ctx* c, const SweepParams& P)
 template <int KIND>
 static int launch_tet_rows_z(mag_ctx* c, const SweepParams& P)
 {
-  constexpr int T = MAG_TZ_THREADS;
+  constexpr int T = MAG_TZ2_THREADS;
   const int per_sm = blocks_per_sm(c, (const void*)k_tet_rows_z<KIND>, T);
   int64_t g = (int64_t)per_sm * c->n_sms;
-  const int64_t groups = (c->trows.n_slices + kZGroup - 1) / kZGroup;
+  const int64_t groups = (c->trows.n_slices + kTZGroup - 1) / kTZGroup;
   const int64_t need = (groups + T / 32 - 1) / (T / 32);
   if (g > need) g = need;
   k_tet_rows_z<KIND><<<(unsigned)(g < 1 ? 1 : g), T, 0, c->stream>>>(
@@ -1727,8 +1752,7 @@ static int launch_tet_rows_z(mag_ctx* c, const SweepParams& P)
 
 static int launch_edge_rows(mag_ctx* c, const SweepParams& P, bool fast)
 {
-  constexpr uint32_t kEdgeFull = MAG_OP_LENGTHS | MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE;
-  if (fast && c->edge_flags_zero && c->lean_sweep && (P.ops & kEdgeFull) == kEdgeFull) {
+  if (lean_edges_ok(c, P, fast)) {
     switch (c->kind) {
       case MAG_KIND_IDENTITY: return launch_edge_rows_z<MAG_KIND_IDENTITY>(c, P);
       case MAG_KIND_ISO: return launch_edge_rows_z<MAG_KIND_ISO>(c, P);
@@ -1767,8 +1791,7 @@ static int launch_tet_rows_k(mag_ctx* c, const SweepParams& P, bool fast)
 }
 static int launch_tet_rows(mag_ctx* c, const SweepParams& P, bool fast)
 {
-  constexpr uint32_t kElemFull = MAG_OP_QUALITIES | MAG_OP_MARK_BAD;
-  if (fast && c->elem_flags_zero && P.use_max && c->lean_sweep && (P.ops & kElemFull) == kElemFull) {
+  if (lean_tets_ok(c, P, fast)) {
     switch (c->kind) {
       case MAG_KIND_IDENTITY: return launch_tet_rows_z<MAG_KIND_IDENTITY>(c, P);
       case MAG_KIND_ISO: return launch_tet_rows_z<MAG_KIND_ISO>(c, P);
@@ -1796,7 +1819,7 @@ int magk_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double 
   if (need_vertex && !c->vertex_pass_valid && (rc = magk_vertex_pass(c))) return rc;
   if (tev) MAG_CUDA(c, cudaEventRecord(tev[1], c->stream));
   if (c->ne && (ops & (MAG_OP_LENGTHS | MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE))) {
-    if ((rc = c->legacy_sweep ? launch_edges_kind(c, P, fast, Range{0, c->ne, true}, false) : launch_edge_rows(c, P, fast))) return rc;
+    if ((rc = use_edge_rows(c, P, fast) ? launch_edge_rows(c, P, fast) : launch_edges_kind(c, P, fast, Range{0, c->ne, true}, false))) return rc;
     // a requested mark writes the flag word of EVERY edge when the incoming words are zero (nothing is skipped)
     if (ops & (MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE)) c->edge_flags_zero = false;
     if ((ops & MAG_OP_LENGTH_SUM) && (rc = magk_length_sum(c))) return rc;
@@ -1806,7 +1829,7 @@ int magk_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double 
     // only the tet kernel understands "all zero, not materialised" (it then writes every word it marks)
     if ((c->ntri || c->np + c->npy) && (rc = magi_materialize_flags(c))) return rc;
     if (c->nt) {
-      if ((rc = c->legacy_sweep ? launch_tets_kind(c, P, fast, Range{0, c->nt, true}) : launch_tet_rows(c, P, fast))) return rc;
+      if ((rc = use_tet_rows(c, P, fast) ? launch_tet_rows(c, P, fast) : launch_tets_kind(c, P, fast, Range{0, c->nt, true}))) return rc;
       if (ops & MAG_OP_MARK_BAD) c->elem_flags_zero = false;
     }
     if (c->ntri) {

@@ -242,15 +242,9 @@ __device__ __forceinline__ double edge_logm(const double* __restrict__ a, const 
 // mean ratio cubed with fixed Q, evaluated in metric space: y_i = (x_i - x_0) Q, the six edges are
 // y1, y2, y3, y2-y1, y3-y1, y3-y2 (the reference's 01,12,20,03,13,23 up to sign), V = det[y1;y2;y3] / 6
 // (= det(J) det(Q) / 6).  Differences are taken in physical space first so no accuracy is lost far from the origin.
-__device__ __forceinline__ double tet_quality(const V3 x[4], const M3& Q, double /*detQ*/)
+// quality from the metric-space edge vectors y_i = (x_i - x_0) Q, i = 1..3
+__device__ __forceinline__ double tet_quality_y(const double y[3][3])
 {
-  double y[3][3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const double ex = x[i + 1].x - x[0].x, ey = x[i + 1].y - x[0].y, ez = x[i + 1].z - x[0].z;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) y[i][k] = fma(ez, Q.m[2][k], fma(ey, Q.m[1][k], __dmul_rn(ex, Q.m[0][k])));
-  }
   // sum of the six squared edge lengths of the points 0, y1, y2, y3:  4 sum |y_i|^2 - |sum y_i|^2  (every term of the
   // difference is bounded by 4 s, so no accuracy is lost: s >= sum |y_i|^2)
   const double n0 = dot3(y[0][0], y[0][1], y[0][2], y[0][0], y[0][1], y[0][2]);
@@ -265,6 +259,17 @@ __device__ __forceinline__ double tet_quality(const V3 x[4], const M3& Q, double
   const double V = __dmul_rn(det, 1.0 / 6.0);
   const double q = __ddiv_rn(__dmul_rn(15552.0, __dmul_rn(V, V)), __dmul_rn(__dmul_rn(s, s), s));
   return V < 0 ? -q : q;
+}
+__device__ __forceinline__ double tet_quality(const V3 x[4], const M3& Q, double /*detQ*/)
+{
+  double y[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double ex = x[i + 1].x - x[0].x, ey = x[i + 1].y - x[0].y, ez = x[i + 1].z - x[0].z;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) y[i][k] = fma(ez, Q.m[2][k], fma(ey, Q.m[1][k], __dmul_rn(ex, Q.m[0][k])));
+  }
+  return tet_quality_y(y);
 }
 
 // triangle mean ratio in metric space: y_i = (x_i - x_0) Q, edges y1, y2 - y1, y2; A = |y1 x y2| / 2

@@ -447,6 +447,13 @@ class Part:
     def reconcile_edge_flags(self, mask):
         self._ck(self._L.mag_reconcile_edge_flags(self._h, int(mask)))
 
+    def check_edge_flag_consistency(self, mask):
+        """ma::checkFlagConsistency: raises MagError(MAG_ERR_INCONSISTENT) when copies of a shared edge disagree; returns the
+        number of disagreeing local copies otherwise (0)."""
+        n = C.c_int64(0)
+        self._ck(self._L.mag_check_edge_flag_consistency(self._h, int(mask), C.byref(n)))
+        return int(n.value)
+
     def sync_edge_flags(self, mask):
         self._ck(self._L.mag_sync_edge_flags(self._h, int(mask)))
 

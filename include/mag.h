@@ -325,6 +325,10 @@ int mag_set_edge_links(mag_ctx* c, int npeers, const int32_t* peer, const int64_
    disagreeing copies goes to mag_stats.n_flag_mismatch (the reference asserts it is 0) and, where peer_owns says so, the
    owner's bits overwrite the local ones. */
 int mag_reconcile_edge_flags(mag_ctx* c, int32_t flag_mask);
+/* ma::checkFlagConsistency as the reference uses it (maRefine.cc:430, maCoarsen.cc:305): copies are compared, nothing is
+   repaired; any disagreement -> MAG_ERR_INCONSISTENT (the reference asserts).  *n_mismatch (may be NULL) = disagreeing local
+   copies.  Synchronous. */
+int mag_check_edge_flag_consistency(mag_ctx* c, int32_t flag_mask, int64_t* n_mismatch);
 /* ma::syncFlag semantics: OR the bits of flag_mask across all copies */
 int mag_sync_edge_flags(mag_ctx* c, int32_t flag_mask);
 /* global statistics: sums of counts, min of min_quality, max of max_length over all parts */

@@ -20,6 +20,7 @@
 #include <apf.h>
 #include <gmi_null.h>
 #include <gmi_mesh.h>
+#include <gmi_analytic.h>
 #include <lionPrint.h>
 #include <PCU.h>
 #include <cmath>
@@ -55,7 +56,8 @@ void ensure_pcu()
    flag words back), [2] the unmodified reference loops served through the adapter */
 double g_times[3] = {0, 0, 0};
 int g_export_threads = 1;
-int g_adapt_dim = 3;         /* mag_adapter_set_adapt_dim: 3 = n^3 box of tets, 2 = n^2 box of triangles */
+int g_adapt_dim = 3;         /* mag_adapter_set_adapt_dim: 3 = n^3 box of tets, 2 = n^2 box of triangles, 4 = unit ball on an
+                                analytic sphere model (vertices created on the boundary are SNAPPED: ma/ma.cc:37) */
 double g_adapt_jitter = 0;   /* mag_adapter_set_adapt_jitter: vertex jitter of the boxes of the ma::adapt checks */   /* mag_adapter_set_threads: host threads of the adapter's MDS walk in the next checks */
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -81,6 +83,50 @@ Fields make_fields(apf::Mesh2* m, const char* tag, double hbar)
   }
   m->end(it);
   return f;
+}
+
+/* the unit sphere as a parametric model face: (longitude, latitude) -> point */
+void sphere_point(double const p[2], double x[3], void*)
+{
+  x[0] = cos(p[0]) * cos(p[1]);
+  x[1] = sin(p[0]) * cos(p[1]);
+  x[2] = sin(p[1]);
+}
+
+/* eight tets around the centre of an octahedron inscribed in the unit sphere; the six outer vertices, the twelve outer edges
+   and the eight outer triangles are classified on the analytic face (so refinement snaps what it creates there to the
+   sphere), everything else on the region.  The situation of test/ma_test_analytic_model.cc, with an interior vertex. */
+apf::Mesh2* make_ball()
+{
+  gmi_model* model = gmi_make_analytic();
+  int periodic[2] = {1, 0};
+  double ranges[2][2] = {{0.0, 2.0 * M_PI}, {-0.5 * M_PI, 0.5 * M_PI}};
+  gmi_add_analytic(model, 2, 0, sphere_point, periodic, ranges, 0);
+  gmi_add_analytic_region(model, 1);
+  apf::Mesh2* m = apf::makeEmptyMdsMesh(model, 3, false, g_pcu);
+  apf::ModelEntity* face = m->findModelEntity(2, 0);
+  apf::ModelEntity* region = m->findModelEntity(3, 1);
+  /* +x -x +y -y +z -z, centre */
+  const double lon[6] = {0.0, M_PI, 0.5 * M_PI, 1.5 * M_PI, 0.0, 0.0}, lat[6] = {0, 0, 0, 0, 0.5 * M_PI, -0.5 * M_PI};
+  apf::MeshEntity* v[7];
+  for (int i = 0; i < 6; ++i) {
+    double uv[2] = {lon[i], lat[i]}, x[3];
+    sphere_point(uv, x, 0);
+    v[i] = m->createVertex(face, apf::Vector3(x[0], x[1], x[2]), apf::Vector3(uv[0], uv[1], 0));
+  }
+  v[6] = m->createVertex(region, apf::Vector3(0, 0, 0), apf::Vector3(0, 0, 0));
+  for (int pass = 0; pass < 2; ++pass)          /* surface triangles first, then the tets that reuse them */
+    for (int oct = 0; oct < 8; ++oct) {
+      apf::MeshEntity* t[4] = {v[oct & 1], v[2 + ((oct >> 1) & 1)], v[4 + ((oct >> 2) & 1)], v[6]};
+      apf::Vector3 p[3];
+      for (int i = 0; i < 3; ++i) m->getPoint(t[i], 0, p[i]);
+      if (apf::cross(p[1] - p[0], p[2] - p[0]) * (apf::Vector3(0, 0, 0) - p[0]) < 0) std::swap(t[1], t[2]);   /* positive volume */
+      if (pass == 0) apf::buildElement(m, face, apf::Mesh::TRIANGLE, t);
+      else apf::buildElement(m, region, apf::Mesh::TET, t);
+    }
+  m->acceptChanges();
+  m->verify();
+  return m;
 }
 
 struct Marks {
@@ -138,7 +184,7 @@ static void jitter_mesh(apf::Mesh2* m, int n, double jitter)
 static int adapter_check(int n, int nz, int log_interp, int fp_mode, double jitter, double* report);
 extern "C" void mag_adapter_set_threads(int n) { g_export_threads = n; }
 extern "C" void mag_adapter_set_adapt_jitter(double j) { g_adapt_jitter = j; }
-extern "C" void mag_adapter_set_adapt_dim(int d) { g_adapt_dim = d == 2 ? 2 : 3; }
+extern "C" void mag_adapter_set_adapt_dim(int d) { g_adapt_dim = (d == 2 || d == 4) ? d : 3; }
 extern "C" void mag_adapter_times(double* t) { for (int i = 0; i < 3; ++i) t[i] = g_times[i]; }
 extern "C" int mag_adapter_check(int n, int log_interp, int fp_mode, double jitter, double* report)
 {
@@ -311,9 +357,11 @@ static int adapt_check(int n, int which, double size_scale, int iterations, int 
   double ref_max_len = 0;
   for (int run = 0; run < 2; ++run) {
     if (!(which & (1 << run))) continue;
-    apf::Mesh2* m = g_adapt_dim == 2 ? apf::makeMdsBox(n, n, 0, 1, 1, 0, true, g_pcu) : apf::makeMdsBox(n, n, n, 1, 1, 1, true, g_pcu);
+    const bool ball = g_adapt_dim == 4;
+    apf::Mesh2* m = ball ? make_ball()
+                         : (g_adapt_dim == 2 ? apf::makeMdsBox(n, n, 0, 1, 1, 0, true, g_pcu) : apf::makeMdsBox(n, n, n, 1, 1, 1, true, g_pcu));
     mesh[run] = m;
-    jitter_mesh(m, n, g_adapt_jitter);
+    if (!ball) jitter_mesh(m, n, g_adapt_jitter);
     Fields f = make_fields(m, run ? "gpu" : "ref", size_scale / n);
     ma::SizeField* sf;
     mag::GpuSizeField* g = 0;
@@ -321,7 +369,8 @@ static int adapt_check(int n, int which, double size_scale, int iterations, int 
     else { g = mag::makeSizeField(m, f.sizes, f.frames, log_interp != 0, 0); g->setArithmetic(fp_mode); sf = g; }
     ma::Input* in = ma::makeAdvanced(ma::configureIdentity(m, sf));
     in->maximumIterations = iterations;
-    in->shouldSnap = false;              /* the box has a null model */
+    in->shouldSnap = ball;               /* the boxes have a null model; the ball's boundary is an analytic sphere */
+    in->shouldTransferParametric = ball;
     if (run == 1) in->shapeHandler = mag::shapeHandler;
     const long l0 = g ? mag_launch_count(g->ctx) : 0;
     const double t0 = now_s();

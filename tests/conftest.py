@@ -19,10 +19,16 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def built():
-    """Makes sure libmag.so and the restated oracle exist (builds them if nvcc / gcc are here)."""
+    """Makes sure libmag.so and the restated oracle exist AND that libmag.so was built from the sources as they are now
+    (a hash of the sources is stamped at build time: file times do not survive the copy to the GPU box, hashes do)."""
     import __graft_entry__ as g
     from core_b200._lib import LIB_PATH
     from oracle import mao
-    if not os.path.exists(LIB_PATH) or not os.path.exists(mao.LIB_PATH):
+    stale = True
+    try:
+        stale = open(g.STAMP).read().strip() != g.source_hash()
+    except OSError:
+        pass
+    if stale or not os.path.exists(LIB_PATH) or not os.path.exists(mao.LIB_PATH):
         g.build()
     return True

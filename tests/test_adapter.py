@@ -73,7 +73,7 @@ def test_adapter_threaded_export(built):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("dim,log_interp,fp_mode,jitter", [(3, 0, 0, 0.0), (3, 0, 1, 0.25), (3, 1, 0, 0.25), (3, 1, 1, 0.0),
-                                                           (2, 0, 0, 0.0), (2, 1, 1, 0.25)])
+                                                           (2, 0, 0, 0.0), (2, 1, 1, 0.25), (4, 0, 0, 0.0), (4, 1, 0, 0.0)])
 def test_ma_adapt_through_the_adapter_gives_the_same_mesh(built, dim, log_interp, fp_mode, jitter):
     """The drop-in claim end to end: the UNMODIFIED ma::adapt driver (refine / coarsen / shape correction, two iterations) on
     a 10^3 box of tets or a 60^2 box of triangles (lattice or jittered) with the rotating shock-layer fields, once with the reference's own size field
@@ -81,7 +81,11 @@ def test_ma_adapt_through_the_adapter_gives_the_same_mesh(built, dim, log_interp
     Same adapted mesh: counts, coordinates and connectivity in iteration order, same longest metric edge (the quantity
     test/aniso_adapt.h:65-74 checks); and the device did serve whole-mesh sweeps on the way.  (The log-Euclidean case is
     what exposed that the export has to read the size field's own ma_logM field: the sizes / frames it was built from go
-    stale for vertices created by refinement.)"""
+    stale for vertices created by refinement.)
+    dim = 4: a unit ball (8 tets around the centre of an octahedron) on an ANALYTIC sphere model with snapping on, three
+    iterations -- the situation of test/ma_test_analytic_model.cc: snap() (ma/ma.cc:37) moves the vertices refinement created on
+    the boundary with no size-field callback, so the adapter has to notice that its device copy of the coordinates is stale
+    (vertex hash, magAdapt.cc ensureExported) to keep producing the reference's mesh."""
     if not os.path.exists(LIB):
         pytest.skip("libmag_ma.so not built (needs the reference headers)")
     L = C.CDLL(LIB)
@@ -92,11 +96,11 @@ def test_ma_adapt_through_the_adapter_gives_the_same_mesh(built, dim, log_interp
     L.mag_adapter_set_adapt_dim(dim)
     try:
         out = np.zeros(11)
-        rc = L.mag_adapter_adapt_check2(10 if dim == 3 else 60, 3, 1.0, 2, log_interp, fp_mode, out.ctypes.data_as(C.c_void_p))
+        rc = L.mag_adapter_adapt_check2({3: 10, 2: 60, 4: 4}[dim], 3, 1.0, 2 if dim != 4 else 3, log_interp, fp_mode, out.ctypes.data_as(C.c_void_p))
     finally:
         L.mag_adapter_set_adapt_jitter(0.0)
         L.mag_adapter_set_adapt_dim(3)
     assert rc == 0, out.tolist()
     assert np.array_equal(out[0:3], out[3:6]) and out[6] == 0
-    assert out[2] > 3 * (6000 if dim == 3 else 7200)   # the mesh was really adapted (6000 tets / 7200 triangles before)
+    assert out[2] > 3 * {3: 6000, 2: 7200, 4: 8}[dim]   # the mesh was really adapted (6000 tets / 7200 triangles / 8 tets before)
     assert out[8] > 0                             # device sweeps happened

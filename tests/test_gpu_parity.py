@@ -919,7 +919,7 @@ def test_lean_kernels_equal_general(cb, kindname, mesh):
     if mesh == "hub":
         xyz, ev, tv = _shuffled_hub_mesh(cb, rng)
     else:
-        xyz, ev, tv = cb.boxmesh.kuhn_box(n, n, n + 2)
+        xyz, ev, tv = cb.boxmesh.kuhn_box(n, n, n)
         if mesh == "jittered":
             xyz = cb.fields.jitter(xyz, 0.3 / n)
     nv = len(xyz)
