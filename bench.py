@@ -595,6 +595,31 @@ def run_b200(a):
         per_part = [[int(x) for x in t.tolist()] for t in allp]
     else:
         per_part = None
+    # where the multi-part step spends what a single part does not (device events on the sweep stream; the statistics call
+    # ends in a host synchronisation, so it is timed on the host from the moment the device is idle)
+    multi = None
+    if world > 1:
+        acc = np.zeros(4)
+        reps = 5
+        for _ in range(reps):
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            T.barrier()
+            with torch.cuda.stream(stream):
+                p.clear_flags()
+                e[0].record(stream)
+                p.sweep(ops | (cb.OP_LAYER_CHECK if npr else 0), fp_mode=fp_mode)
+                e[1].record(stream)
+                p.reconcile_edge_flags(mark_mask)
+                e[2].record(stream)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            p.allreduce_stats()
+            acc += np.array([e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), 1e3 * (time.perf_counter() - t0), 0.0])
+        acc /= reps
+        multi = {"sweep_ms": T.max_over_ranks(float(acc[0])), "reconcile_flags_ms": T.max_over_ranks(float(acc[1])),
+                 "allreduce_stats_ms": T.max_over_ranks(float(acc[2])),
+                 "what": "per step, max over ranks: the sweep kernels; pack + grouped ncclSend/Recv + merge of the part-boundary "
+                         "flag words (device events); all-gather of the statistics + copy + host sync (host clock, device idle at start)"}
     ents_rank = ne + nt + npr
     ents_all = ents_rank * world
     step_ms = main["ms_per_step"]
@@ -762,6 +787,8 @@ def run_b200(a):
             odd = [c for i, c in enumerate(per_part) if i % 2 == 1]
             line["per_part_owned_counts"] = per_part
             line["parity_symmetry"] = "ok" if all(c == even[0] for c in even) and all(c == odd[0] for c in odd) else "FAILED"
+        if multi is not None:
+            line["multi_part_overhead"] = multi
         if pm is not None:
             line["parity_multi"] = pm["status"]
             line["parity_multi_detail"] = pm

@@ -18,6 +18,10 @@
 #include <cmath>
 #include <thread>
 #include <functional>
+#include <algorithm>
+#include <map>
+#include <stdint.h>
+#include <PCU.h>
 
 namespace ma {
 /* external linkage in the reference, declared in no installed header (maBalance.cc:74-81) */
@@ -53,6 +57,38 @@ static unsigned long long hashBytes(unsigned long long h, const void* p, size_t 
   const unsigned char* b = (const unsigned char*)p;
   for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
   return h;
+}
+
+void buildEdgeLinks(apf::Sharing* sh, int self, const std::vector<ma::Entity*>& edges, EdgeLinks& out)
+{
+  struct Item { uintptr_t key; int idx; unsigned char peerOwns; };
+  std::map<int, std::vector<Item> > lists;   /* peers in increasing order */
+  apf::CopyArray copies;
+  for (size_t i = 0; i < edges.size(); ++i) {
+    ma::Entity* e = edges[i];
+    if (!sh->isShared(e)) continue;
+    const int owner = sh->getOwner(e);
+    copies.setSize(0);
+    sh->getCopies(e, copies);
+    for (size_t k = 0; k < copies.getSize(); ++k) {
+      const int p = copies[k].peer;
+      if (p == self) continue;
+      Item it;
+      it.key = self < p ? (uintptr_t)e : (uintptr_t)copies[k].entity;
+      it.idx = (int)i;
+      it.peerOwns = owner == p ? 1 : 0;
+      lists[p].push_back(it);
+    }
+  }
+  out.peer.clear(); out.idx.clear(); out.peerOwns.clear();
+  for (std::map<int, std::vector<Item> >::iterator l = lists.begin(); l != lists.end(); ++l) {
+    std::vector<Item>& v = l->second;
+    std::sort(v.begin(), v.end(), [](const Item& a, const Item& b) { return a.key < b.key; });
+    out.peer.push_back(l->first);
+    out.idx.push_back(std::vector<int>(v.size()));
+    out.peerOwns.push_back(std::vector<unsigned char>(v.size()));
+    for (size_t i = 0; i < v.size(); ++i) { out.idx.back()[i] = v[i].idx; out.peerOwns.back()[i] = v[i].peerOwns; }
+  }
 }
 
 struct Export {
@@ -228,6 +264,38 @@ struct Access {
                            (int64_t)(x.tet_v.size() / 4), x.tet_v.data(), (int64_t)(x.prism_v.size() / 6), x.prism_v.data(),
                            (int64_t)(x.pyr_v.size() / 5), x.pyr_v.data(), x.edge_owned.data(), x.elem_owned.data()));
     uploadField(g, x);
+    uploadLinks(g, x);
+  }
+  /* several parts: NCCL communicator (once per context; the unique id goes from part 0 to the others over PCU) and the
+     part-boundary edge lists of this export */
+  static void uploadLinks(GpuSizeField* g, Export& x)
+  {
+    pcu::PCU* P = g->mesh->getPCU();
+    if (!P || P->Peers() <= 1) return;
+    mag_ctx* c = g->ctx;
+    if (!g->commReady) {
+      char id[MAG_UNIQUE_ID_BYTES];
+      if (P->Self() == 0) MAG_DO(c, mag_comm_unique_id(id));
+      P->Begin();
+      if (P->Self() == 0)
+        for (int r = 1; r < P->Peers(); ++r) P->Pack(r, id, sizeof(id));
+      P->Send();
+      while (P->Receive()) P->Unpack(id, sizeof(id));
+      MAG_DO(c, mag_comm_init(c, P->Peers(), P->Self(), id));
+      g->commReady = true;
+    }
+    apf::Sharing* sh = g->userSharing;
+    if (!sh) {
+      if (!g->ownSharing) g->ownSharing = apf::getSharing(g->mesh);
+      sh = g->ownSharing;
+    }
+    EdgeLinks L;
+    buildEdgeLinks(sh, P->Self(), x.edges, L);
+    std::vector<int64_t> n(L.peer.size());
+    std::vector<const int32_t*> idx(L.peer.size());
+    std::vector<const uint8_t*> own(L.peer.size());
+    for (size_t k = 0; k < L.peer.size(); ++k) { n[k] = (int64_t)L.idx[k].size(); idx[k] = L.idx[k].data(); own[k] = L.peerOwns[k].data(); }
+    MAG_DO(c, mag_set_edge_links(c, (int)L.peer.size(), L.peer.data(), n.data(), idx.data(), own.data()));
   }
   static void uploadField(GpuSizeField* g, Export& x)
   {
@@ -294,6 +362,12 @@ struct Access {
     MAG_DO(c, mag_set_flags(c, on_edges ? ef.data() : 0, on_elems ? lf.data() : 0));
     MAG_DO(c, mag_sweep(c, ops, ma::MAXLENGTH, ma::MINLENGTH, a->input->goodQuality, 1, g->fpMode));
     mag_stats st;
+    if (g->commReady) {
+      /* where the reference calls checkFlagConsistency (maRefine.cc:430, maCoarsen.cc:305; it asserts): every copy of a shared
+         edge must have come out with the same mark on every part */
+      if (on_edges) MAG_DO(c, mag_check_edge_flag_consistency(c, (ops & MAG_OP_MARK_SPLIT ? MAG_SPLIT : 0) | (ops & MAG_OP_MARK_COLLAPSE ? MAG_COLLAPSE : 0), 0));
+      MAG_DO(c, mag_allreduce_stats(c, &st));   /* owned counts summed, min / max reduced: PCU Add / Min / Max of the reference */
+    } else
     MAG_DO(c, mag_get_stats(c, &st)); /* MAG_ERR_FLAG_STATE here == the reference's assert at maAdapt.cc:308 */
     if (on_edges || on_elems) {
       std::vector<int> ef2(ef.size()), lf2(lf.size());
@@ -309,7 +383,7 @@ struct Access {
 
 GpuSizeField::GpuSizeField()
   : mesh(0), wrapped(0), ctx(0), kind(0), logVariant(0), fpMode(MAG_FP_STRICT), dirty(true), topoValid(false), exported(0), exportThreads(1), streak(0), lastGoodQuality(-1),
-    fSizes(0), fFrames(0), fIso(0), fnAniso(0), fnIso(0), nNonSimplex(0), lastDim(-1), lastId(-1), snapshotHash(0)
+    fSizes(0), fFrames(0), fIso(0), fnAniso(0), fnIso(0), nNonSimplex(0), lastDim(-1), lastId(-1), userSharing(0), ownSharing(0), commReady(false), snapshotHash(0)
 {
 }
 
@@ -317,6 +391,7 @@ GpuSizeField::~GpuSizeField()
 {
   if (ctx) mag_destroy(ctx);
   delete exported;
+  delete ownSharing;
   delete wrapped; /* like the reference: an AnisoSizeField destroys the fields it was built from (maSize.cc:385-389) */
 }
 
@@ -487,25 +562,25 @@ long markEdgesToSplit(ma::Adapt* a)
 {
   GpuSizeField* g = gpuField(a->sizeField);
   mag_stats st = Access::sweepWithAdaptFlags(g, a, MAG_OP_MARK_SPLIT);
-  return a->mesh->getPCU()->Add<long>((long)st.n_split); /* maAdapt.cc:323 */
+  return g->multiPart() ? (long)st.n_split : a->mesh->getPCU()->Add<long>((long)st.n_split); /* maAdapt.cc:323 */
 }
 long markEdgesToCollapse(ma::Adapt* a)
 {
   GpuSizeField* g = gpuField(a->sizeField);
   mag_stats st = Access::sweepWithAdaptFlags(g, a, MAG_OP_MARK_COLLAPSE);
-  return a->mesh->getPCU()->Add<long>((long)st.n_collapse);
+  return g->multiPart() ? (long)st.n_collapse : a->mesh->getPCU()->Add<long>((long)st.n_collapse);
 }
 int markBadQuality(ma::Adapt* a)
 {
   GpuSizeField* g = gpuField(a->sizeField);
   mag_stats st = Access::sweepWithAdaptFlags(g, a, MAG_OP_MARK_BAD);
-  return (int)a->mesh->getPCU()->Add<long>((long)st.n_bad);
+  return (int)(g->multiPart() ? (long)st.n_bad : a->mesh->getPCU()->Add<long>((long)st.n_bad));
 }
 double getMinQuality(ma::Adapt* a)
 {
   GpuSizeField* g = gpuField(a->sizeField);
   mag_stats st = Access::sweepWithAdaptFlags(g, a, MAG_OP_QUALITIES);
-  return a->mesh->getPCU()->Min<double>(st.min_quality); /* maShape.cc:168 */
+  return g->multiPart() ? st.min_quality : a->mesh->getPCU()->Min<double>(st.min_quality); /* maShape.cc:168 */
 }
 double getMaximumEdgeLength(ma::Mesh* m, ma::SizeField* sf)
 {
@@ -513,6 +588,7 @@ double getMaximumEdgeLength(ma::Mesh* m, ma::SizeField* sf)
   g->refresh(-1);
   Access::resetOrder(g);
   mag_stats st;
+  if (g->multiPart()) { MAG_DO(g->ctx, mag_allreduce_stats(g->ctx, &st)); return st.max_length; }
   MAG_DO(g->ctx, mag_get_stats(g->ctx, &st));
   return m->getPCU()->Max<double>(st.max_length); /* maSize.cc:689 */
 }

@@ -38,6 +38,20 @@ namespace mag {
 
 struct Export;   /* the arrays of one MDS export (magAdapt.cc) */
 
+/* Part-boundary edge lists in the layout mag_set_edge_links takes (struct mds_links, mds/mds_net.h:33-38): for every peer
+   part the export indices of the edges shared with it, in the SAME order on both sides, and whether the peer's copy is the
+   owner (apf::Sharing::getOwner -- apfPM.cc:109-126 for the default NormalSharing). */
+struct EdgeLinks {
+  std::vector<int> peer;
+  std::vector<std::vector<int> > idx;
+  std::vector<std::vector<unsigned char> > peerOwns;
+};
+/* Built from apf::Sharing alone, no communication: both sides sort a peer's list by the entity pointer of the copy that
+   lives on the LOWER-numbered part (its own pointer there, the remote pointer of apf::Copy on the other side; MDS pointers
+   grow with the entity index, mds/apfMDS.cc fromEnt/toEnt).  edges = the exported edges in export order; self = this
+   part's id (m->getPCU()->Self()). */
+void buildEdgeLinks(apf::Sharing* sh, int self, const std::vector<ma::Entity*>& edges, EdgeLinks& out);
+
 class GpuSizeField : public ma::SizeField
 {
   public:
@@ -67,6 +81,13 @@ class GpuSizeField : public ma::SizeField
     void setExportThreads(int n) { exportThreads = n < 1 ? 1 : n; }
     /* re-export the mesh + field and run one full device sweep now */
     void refresh(double goodQuality = -1);
+    /* Several parts (mesh->getPCU()->Peers() > 1): the flag words of part-boundary edges are compared across parts with NCCL
+       where the reference calls ma::checkFlagConsistency (maRefine.cc:430, maCoarsen.cc:305 -> mag_check_edge_flag_consistency)
+       and the counts / min / max are reduced with mag_allreduce_stats instead of PCU.  Set up on the first export: the NCCL
+       unique id travels from part 0 over PCU, the lists come from buildEdgeLinks.  sharing: whose view of ownership to use
+       (NULL = apf::getSharing(mesh), which the adapter then owns). */
+    void setSharing(apf::Sharing* sharing) { userSharing = sharing; }
+    bool multiPart() const { return commReady; }
 
     ma::Mesh* mesh;
     ma::SizeField* wrapped;  /* the reference size field built from the same inputs (owned) */
@@ -97,6 +118,9 @@ class GpuSizeField : public ma::SizeField
     std::vector<int> edgeFlags, elemFlags;        /* flags of the last sweep run on zero incoming words */
     long nNonSimplex;
     int lastDim, lastId;  /* last per-entity query: dimension and MDS index */
+  apf::Sharing* userSharing;   /* not owned */
+  apf::Sharing* ownSharing;    /* from apf::getSharing, owned */
+  bool commReady;              /* mag_comm_init done for this context */
   unsigned long long snapshotHash;   /* vertex hash (coordinates + field) of the export the snapshot was swept from */
     bool serve(ma::Entity* e, int dim, int& slot);
 };

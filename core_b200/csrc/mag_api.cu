@@ -153,13 +153,10 @@ int mag_create(mag_ctx** out, int device)
   c->d_stats = nullptr; c->h_stats = nullptr;
   c->d_block_sums = nullptr; c->n_sms = 148;
   c->d_edge_order = c->d_tet_order = nullptr;
-  c->erows = MagRows{0, 0, 0, nullptr, nullptr, nullptr, nullptr, false};
+  c->erows = MagRows{0, 0, 0, nullptr, nullptr, nullptr, false};
   c->trows = c->erows;
   { const char* e = getenv("MAG_LEGACY_SWEEP"); c->legacy_sweep = e && e[0] == '1'; }
-  { const char* e = getenv("MAG_L2_PREFETCH"); c->l2_prefetch = !(e && e[0] == '0'); }
   { const char* e = getenv("MAG_LEAN_SWEEP"); c->lean_sweep = !(e && e[0] == '0'); }
-  { const char* e = getenv("MAG_GENERAL_ROWS"); c->general_rows = e && e[0] == '1'; }
-  c->d_edge_pf = c->d_tet_pf = nullptr; c->n_edge_pf = c->n_tet_pf = 0;
   c->d_vstat = nullptr;
   c->d_edge_bytes = c->d_elem_bytes = nullptr;
   c->d_pair_keys = nullptr; c->d_pair_vals = nullptr; c->pair_bits = 0; c->d_layer_count = nullptr;
@@ -200,7 +197,7 @@ void mag_destroy(mag_ctx* c)
   cudaFree(c->d_edge_owned); cudaFree(c->d_elem_owned); cudaFree(c->d_edge_flags); cudaFree(c->d_elem_flags);
   cudaFree(c->d_len); cudaFree(c->d_qual); cudaFree(c->d_weight); cudaFree(c->d_layer_ok); cudaFree(c->d_layer_codes);
   cudaFree(c->d_stats); cudaFreeHost(c->h_stats); cudaFree(c->d_block_sums);
-  cudaFree(c->d_near_edge); cudaFree(c->d_near_elem); cudaFree(c->d_edge_order); cudaFree(c->d_tet_order); cudaFree(c->d_edge_pf); cudaFree(c->d_tet_pf);
+  cudaFree(c->d_near_edge); cudaFree(c->d_near_elem); cudaFree(c->d_edge_order); cudaFree(c->d_tet_order);
   cudaFree(c->d_edge_bytes); cudaFree(c->d_elem_bytes);
   magk_free_rows(c); cudaFree(c->d_vstat); magl_free_pairs(c); cudaFree(c->d_layer_count);
   for (cudaEvent_t e : c->tev) cudaEventDestroy(e);

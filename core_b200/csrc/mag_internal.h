@@ -44,7 +44,6 @@ struct MagRows {
   int64_t n_slots;       // 32 * sum of the slice widths
   int32_t* d_anchor;     // [32 n_slices] anchor vertex of row position p, -1 = padding
   int32_t* d_slice_off;  // [n_slices + 1] first slot of every slice
-  int32_t* d_pf;         // [n_slices] L2 prefetch table: vertex blocks covering everything slices 0..s touch
   int32_t* d_slots;      // edges: int2 {other vertex | not-owned << 31, edge id}; tets: int4 {o1 | not-owned << 31, o2, o3, tet id}; id -1 = empty
   bool valid;
 };
@@ -105,12 +104,7 @@ struct mag_ctx {
   int n_sms;
   int32_t* d_edge_order; // chunk schedule of the legacy edge kernel (tile indices sorted by smallest vertex id)
   int32_t* d_tet_order;
-  int32_t* d_edge_pf;    // legacy kernels: L2 prefetch table per ticket (see PfArgs in mag_rows.cuh)
-  int32_t* d_tet_pf;
-  int64_t n_edge_pf, n_tet_pf;
-  bool general_rows;     // MAG_GENERAL_ROWS=1: sweeps the lean kernels do not serve run the general row kernels instead of the tiles
   bool lean_sweep;       // MAG_LEAN_SWEEP=0: never use the lean kernels of mag_lean.cuh (A/B measurements, tests)
-  bool l2_prefetch;      // MAG_L2_PREFETCH=0 switches the L2 prefetch of the vertex arrays off (A/B measurements)
   MagRows erows, trows;  // anchor-row layout of the edges / tets (whole-part sweeps)
   bool legacy_sweep;     // MAG_LEGACY_SWEEP=1: whole-part sweeps run the round-1 tile kernels (A/B measurements)
   // (vertex pair) -> edge index hash table of mag_reset_layer (mag_layer.cu); pair_bits = 0: not built

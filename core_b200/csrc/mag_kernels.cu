@@ -74,30 +74,6 @@ __device__ __forceinline__ double warp_sum(double v)
 
 using namespace maglay;
 
-// L2 prefetch of the vertex arrays ahead of the sweep front.  The work units (slices of anchor rows; tickets of the tile kernels) are handed out in vertex order, so the FIRST touch
-// of a vertex record -- the only access that has to come from HBM; every later one finds it in L2 -- happens at the
-// leading edge of the window of vertex ids the sweep has reached (box mesh: the +z neighbour, one grid plane ahead).
-// blk[j] = number of 32-vertex blocks that cover every vertex units 0..j touch (running maximum, built at export).  The
-// warp that takes unit s asks the TMA unit to pull the blocks unit s + dist adds, [blk[s+dist-1], blk[s+dist]), into L2
-// (cp.async.bulk.prefetch.L2, SASS UBLKPF.L2: one instruction, no register, no shared memory, no L1 wavefront), dist = a
-// little more than the units in flight.  Every block is requested exactly once per sweep, in address order.
-struct PfArgs { const int32_t* blk; int32_t n; int32_t dist; };
-__device__ __forceinline__ void l2_prefetch(const void* p, unsigned bytes)
-{
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-// blocks [b0, b1) of a vertex array with K 16-byte chunks per vertex (512 K bytes per block), in pieces of at most 32 KB
-template <int K>
-__device__ __forceinline__ void l2_prefetch_blocks(const double* base, int b0, int b1)
-{
-  constexpr int kPiece = 64 / K > 0 ? 64 / K : 1;
-  for (int b = b0; b < b1; b += kPiece) {
-    const int nb = b1 - b < kPiece ? b1 - b : kPiece;
-    l2_prefetch(base + (size_t)b * (size_t)(64 * K), (unsigned)(nb * 512 * K));
-  }
-}
-
-
 // ------------------------------------------------------------------ pack kernels
 __global__ void k_pack4(int64_t nv, const double* __restrict__ xyz, const double* __restrict__ s, double* __restrict__ rec)
 {
@@ -450,7 +426,7 @@ __global__ void __launch_bounds__(EdgeCfg<KIND, FAST>::T, EdgeCfg<KIND, FAST>::B
 k_edges(int32_t ne, const int2* __restrict__ edge_v, const double* __restrict__ vedge,
         int32_t* __restrict__ flags, double* __restrict__ lengths,
         EdgeParams P, MagDevStats* st, int32_t* __restrict__ near_list, const int32_t* __restrict__ chunk_order, int32_t id_base,
-        VertArgs V, PfArgs pf)
+        VertArgs V)
 {
   __shared__ NearQueue q;
   __shared__ long long chunk_slot;
@@ -476,10 +452,6 @@ k_edges(int32_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
       ticket = ticket < nint ? ticket - ticket / kVertEvery - 1 : ticket - nvchunks;
       if (ticket >= nchunks) continue;                                // fewer edge chunks than slots between vertex chunks
     } else if (ticket >= nchunks) break;
-    if (pf.blk && threadIdx.x == 32 && ticket + pf.dist < pf.n) {   // one lane of warp 1 (warp 0 drew the ticket): see PfArgs
-      const int b0 = __ldg(pf.blk + ticket + pf.dist - 1), b1 = __ldg(pf.blk + ticket + pf.dist);
-      l2_prefetch_blocks<EdgeRecs<KIND>::N / 2>(vedge, b0, b1);
-    }
 #if MAG_EDGE_TILE_SCHED
     // tile-granular schedule: the ticket is a group of kChunkEdges / T consecutive SCHEDULE positions; position p holds
     // the index of a tile of T consecutive edges.  The schedule is sorted by the smallest vertex id a tile touches, so
@@ -735,7 +707,7 @@ __global__ void __launch_bounds__(TetCfg<FAST>::T, TetCfg<FAST>::B)
 k_tets(int32_t nt, int32_t elem_off, int64_t nv, const int4* __restrict__ tet_v, const double* __restrict__ vpos,
        const double* __restrict__ vq, const double* __restrict__ vedge,
        int32_t* __restrict__ flags, double* __restrict__ qual, TetParams P, MagDevStats* st,
-       int32_t* __restrict__ near_list, const int32_t* __restrict__ chunk_order, PfArgs pf)
+       int32_t* __restrict__ near_list, const int32_t* __restrict__ chunk_order)
 {
   __shared__ NearQueue q;
   __shared__ long long chunk_slot;
@@ -753,12 +725,6 @@ k_tets(int32_t nt, int32_t elem_off, int64_t nv, const int4* __restrict__ tet_v,
   for (;;) {
     const long long ticket = next_chunk(&st->elem_chunk, &chunk_slot);
     if (ticket >= nchunks) break;
-    if (pf.blk && threadIdx.x == 32 && ticket + pf.dist < pf.n) {
-      const int b0 = __ldg(pf.blk + ticket + pf.dist - 1), b1 = __ldg(pf.blk + ticket + pf.dist);
-      l2_prefetch_blocks<2>(vpos, b0, b1);
-      if (USE_MAX) l2_prefetch_blocks<5>(vq, b0, b1);
-      else l2_prefetch_blocks<EdgeRecs<KIND>::N / 2>(vedge, b0, b1);
-    }
     const int t0 = (chunk_order ? chunk_order[ticket] : (int)ticket) * kChunkTets;
     const int t_end = (nt - t0 < kChunkTets) ? nt : t0 + kChunkTets;
     const int tiles = (t_end - t0 + kTetThreads - 1) / kTetThreads;
@@ -1112,35 +1078,19 @@ __global__ void k_finish_sum(int64_t n, const double* __restrict__ part, MagDevS
 // the vertex array together, so a vertex record is fetched from HBM once per sweep instead of once per family.
 template <int NV>
 __global__ void __launch_bounds__(kThreads)
-k_chunk_keys(int64_t n, int64_t chunk_len, const int32_t* __restrict__ conn, int32_t* __restrict__ keys, int32_t* __restrict__ vmax)
+k_chunk_keys(int64_t n, int64_t chunk_len, const int32_t* __restrict__ conn, int32_t* __restrict__ keys)
 {
-  __shared__ int sh[kThreads / 32], shx[kThreads / 32];
+  __shared__ int sh[kThreads / 32];
   const int64_t lo = blockIdx.x * chunk_len, hi = (lo + chunk_len < n) ? lo + chunk_len : n;
-  int m = 0x7fffffff, x = 0;
-  for (int64_t i = lo * NV + threadIdx.x; i < hi * NV; i += kThreads) { int v = conn[i] & kVidMask; m = v < m ? v : m; x = v > x ? v : x; }
+  int m = 0x7fffffff;
+  for (int64_t i = lo * NV + threadIdx.x; i < hi * NV; i += kThreads) { int v = conn[i] & kVidMask; m = v < m ? v : m; }
   m = __reduce_min_sync(0xffffffffu, m);
-  x = __reduce_max_sync(0xffffffffu, x);
-  if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5] = m; shx[threadIdx.x >> 5] = x; }
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int i = 1; i < kThreads / 32; ++i) { m = sh[i] < m ? sh[i] : m; x = shx[i] > x ? shx[i] : x; }
+    for (int i = 1; i < kThreads / 32; ++i) m = sh[i] < m ? sh[i] : m;
     keys[blockIdx.x] = m;
-    vmax[blockIdx.x] = x;   // largest vertex id (-> L2 prefetch table)
   }
-}
-// largest vertex id touched by the `group` consecutive schedule positions of one ticket
-__global__ void __launch_bounds__(kThreads)
-k_group_vmax(int64_t ngroups, int group, int64_t nchunks, const int32_t* __restrict__ order, const int32_t* __restrict__ chunk_vmax,
-             int32_t* __restrict__ out)
-{
-  const int64_t g = blockIdx.x * (int64_t)kThreads + threadIdx.x;
-  if (g >= ngroups) return;
-  int m = 0;
-  for (int i = 0; i < group; ++i) {
-    const int64_t p = g * group + i;
-    if (p < nchunks) { const int x = chunk_vmax[order[p]]; m = x > m ? x : m; }
-  }
-  out[g] = m;
 }
 
 // export-time validation: every vertex id of a connectivity array must lie in [0, nv).  One streaming pass per array
@@ -1337,13 +1287,6 @@ static unsigned persistent_grid(mag_ctx* c, const void* kernel, int64_t n, int t
   return (unsigned)(g < 1 ? 1 : g);
 }
 
-// prefetch distance: the units in flight (one per CTA for the tile kernels, one per warp for the row kernels) and a margin
-static PfArgs pf_args(const mag_ctx* c, const int32_t* blk, int64_t n, int64_t dist)
-{
-  if (!c->l2_prefetch || !blk || n <= 0) return PfArgs{nullptr, 0, 1};
-  return PfArgs{blk, (int32_t)n, (int32_t)(dist < 1 ? 1 : dist)};
-}
-
 static EdgeParams edge_params(const SweepParams& P, bool zero_in)
 {
   EdgeParams E;
@@ -1373,8 +1316,7 @@ static int launch_edges_t(mag_ctx* c, const SweepParams& P, const Range& r)
   const VertArgs V{(int32_t)c->nv, c->dim, c->d_vpos, c->d_vq};
   k_edges<KIND, FAST, VERT><<<g, kEdgeThreads, 0, c->stream>>>((int32_t)r.n, reinterpret_cast<const int2*>(c->d_edge_v) + r.first, c->d_vedge,
                                                                c->d_edge_flags + r.first, c->d_len + r.first, edge_params(P, r.whole && c->edge_flags_zero), c->d_stats,
-                                                               c->d_near_edge, r.whole ? c->d_edge_order : nullptr, (int32_t)r.first, V,
-                                                               pf_args(c, r.whole ? c->d_edge_pf : nullptr, c->n_edge_pf, (int64_t)g + g / 4 + 8));
+                                                               c->d_near_edge, r.whole ? c->d_edge_order : nullptr, (int32_t)r.first, V);
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;
   return MAG_OK;
@@ -1410,8 +1352,7 @@ static int launch_tets_t(mag_ctx* c, const SweepParams& P, const Range& r)
   k_tets<KIND, FAST, USE_MAX><<<g, kTetThreads, 0, c->stream>>>((int32_t)r.n, (int32_t)(c->np + c->npy + r.first), c->nv,
                                                                  reinterpret_cast<const int4*>(c->d_tet_v) + r.first,
                                                                  c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_flags, c->d_qual, tet_params(P, r.whole && c->elem_flags_zero),
-                                                                 c->d_stats, c->d_near_elem, r.whole ? c->d_tet_order : nullptr,
-                                                                 pf_args(c, r.whole ? c->d_tet_pf : nullptr, c->n_tet_pf, (int64_t)g + g / 4 + 8));
+                                                                 c->d_stats, c->d_near_elem, r.whole ? c->d_tet_order : nullptr);
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;
   return MAG_OK;
@@ -1526,58 +1467,34 @@ int exclusive_scan(mag_ctx* c, Scratch& S, const int32_t* in, int32_t* out, int6
   MAG_CUDA(c, cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, in, out, (int)n, c->stream));
   return MAG_OK;
 }
-struct MaxOp { __host__ __device__ int32_t operator()(int32_t a, int32_t b) const { return a > b ? a : b; } };
-// a[j] := number of kVB-vertex blocks covering [0, max(a[0..j])], in place
-int running_max_blocks(mag_ctx* c, Scratch& S, int32_t* a, int64_t n)
-{
-  size_t tmp_bytes = 0;
-  void* d_tmp = nullptr;
-  MAG_CUDA(c, cub::DeviceScan::InclusiveScan(nullptr, tmp_bytes, a, a, MaxOp(), (int)n, c->stream));
-  MAG_CUDA(c, S.get(reinterpret_cast<char*&>(d_tmp), tmp_bytes));
-  MAG_CUDA(c, cub::DeviceScan::InclusiveScan(d_tmp, tmp_bytes, a, a, MaxOp(), (int)n, c->stream));
-  k_vmax_to_blocks<<<grid_for(n), kThreads, 0, c->stream>>>(n, a);
-  MAG_CUDA(c, cudaGetLastError());
-  return MAG_OK;
-}
 void free_rows(MagRows& r)
 {
-  cudaFree(r.d_anchor); cudaFree(r.d_slice_off); cudaFree(r.d_slots); cudaFree(r.d_pf);
-  r.d_anchor = r.d_slice_off = r.d_slots = r.d_pf = nullptr;
+  cudaFree(r.d_anchor); cudaFree(r.d_slice_off); cudaFree(r.d_slots);
+  r.d_anchor = r.d_slice_off = r.d_slots = nullptr;
   r.n_rows = r.n_slices = r.n_slots = 0;
   r.valid = false;
 }
 } // namespace
 // builds c->d_edge_order / c->d_tet_order (legacy tile kernels): chunk (tile) indices sorted by key on the device (LSD radix
 // sort is stable, so equal keys keep the caller's order); nothing travels to the host
-// + the L2 prefetch table of the schedule (PfArgs): one entry per ticket = `group` consecutive schedule positions
-static int build_order(mag_ctx* c, int64_t n, int64_t chunk_len, const int32_t* d_conn, int nv_per, int32_t*& d_order, int64_t& n_chunks,
-                       int group, int32_t*& d_pf, int64_t& n_pf)
+static int build_order(mag_ctx* c, int64_t n, int64_t chunk_len, const int32_t* d_conn, int nv_per, int32_t*& d_order, int64_t& n_chunks)
 {
   n_chunks = (n + chunk_len - 1) / chunk_len;
   if (d_order) { MAG_CUDA(c, cudaFree(d_order)); d_order = nullptr; }
-  if (d_pf) { MAG_CUDA(c, cudaFree(d_pf)); d_pf = nullptr; }
-  n_pf = 0;
   if (n_chunks == 0) return MAG_OK;
   Scratch S;
-  int32_t *d_keys = nullptr, *d_keys_out = nullptr, *d_idx = nullptr, *d_vmax = nullptr;
+  int32_t *d_keys = nullptr, *d_keys_out = nullptr, *d_idx = nullptr;
   MAG_CUDA(c, S.get(d_keys, (size_t)n_chunks));
   MAG_CUDA(c, S.get(d_keys_out, (size_t)n_chunks));
   MAG_CUDA(c, S.get(d_idx, (size_t)n_chunks));
-  MAG_CUDA(c, S.get(d_vmax, (size_t)n_chunks));
   MAG_CUDA(c, cudaMalloc((void**)&d_order, (size_t)n_chunks * 4));
-  if (nv_per == 2) k_chunk_keys<2><<<(unsigned)n_chunks, kThreads, 0, c->stream>>>(n, chunk_len, d_conn, d_keys, d_vmax);
-  else k_chunk_keys<4><<<(unsigned)n_chunks, kThreads, 0, c->stream>>>(n, chunk_len, d_conn, d_keys, d_vmax);
+  if (nv_per == 2) k_chunk_keys<2><<<(unsigned)n_chunks, kThreads, 0, c->stream>>>(n, chunk_len, d_conn, d_keys);
+  else k_chunk_keys<4><<<(unsigned)n_chunks, kThreads, 0, c->stream>>>(n, chunk_len, d_conn, d_keys);
   k_iota<<<grid_for(n_chunks), kThreads, 0, c->stream>>>(n_chunks, d_idx);
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches += 2;
   int rc = sort_pairs(c, S, d_keys, d_keys_out, d_idx, d_order, n_chunks, 31);
   if (rc) return rc;
-  n_pf = (n_chunks + group - 1) / group;
-  MAG_CUDA(c, cudaMalloc((void**)&d_pf, (size_t)n_pf * 4));
-  k_group_vmax<<<grid_for(n_pf), kThreads, 0, c->stream>>>(n_pf, group, n_chunks, d_order, d_vmax, d_pf);
-  MAG_CUDA(c, cudaGetLastError());
-  if ((rc = running_max_blocks(c, S, d_pf, n_pf))) return rc;
-  c->n_launches += 2;
   MAG_CUDA(c, cudaStreamSynchronize(c->stream));
   return MAG_OK;
 }
@@ -1642,11 +1559,9 @@ static int build_rows(mag_ctx* c, int64_t n, const int32_t* d_conn, MagRows& row
   const int64_t n_slots = n_slots32;
   MAG_CUDA(c, cudaMalloc((void**)&rows.d_slots, (size_t)n_slots * NV * 4));
   MAG_CUDA(c, cudaMemsetAsync(rows.d_slots, 0xFF, (size_t)n_slots * NV * 4, c->stream));
-  MAG_CUDA(c, cudaMalloc((void**)&rows.d_pf, (size_t)nslices * 4));
   k_slots_fill<NV><<<grid_for(Rpad), kThreads, 0, c->stream>>>(R, Rpad, order, row_anchor, row_len, row_first, sorted_e, d_conn,
-                                                               rows.d_slice_off, rows.d_anchor, rows.d_slots, rows.d_pf);
+                                                               rows.d_slice_off, rows.d_anchor, rows.d_slots);
   MAG_CUDA(c, cudaGetLastError());
-  if ((rc = running_max_blocks(c, S, rows.d_pf, nslices))) return rc;
   MAG_CUDA(c, cudaStreamSynchronize(c->stream));
   c->n_launches += 5;
   rows.n_rows = R;
@@ -1664,9 +1579,8 @@ int magk_build_schedule(mag_ctx* c)
   // the tile schedule of k_edges / k_tets (a few bytes per 256 entities) is always built: those kernels serve every sweep
   // the lean row kernels do not (incoming flag words, single marks, strict arithmetic, the log-Euclidean field)
   int64_t nch;
-  if ((rc = build_order(c, c->ne, MAG_EDGE_TILE_SCHED ? (int64_t)kStrictThreads : (int64_t)kEdgeChunk, c->d_edge_v, 2, c->d_edge_order, nch,
-                        MAG_EDGE_TILE_SCHED ? kEdgeChunk / kStrictThreads : 1, c->d_edge_pf, c->n_edge_pf))) return rc;
-  if ((rc = build_order(c, c->nt, (int64_t)kTetChunk, c->d_tet_v, 4, c->d_tet_order, nch, 1, c->d_tet_pf, c->n_tet_pf))) return rc;
+  if ((rc = build_order(c, c->ne, MAG_EDGE_TILE_SCHED ? (int64_t)kStrictThreads : (int64_t)kEdgeChunk, c->d_edge_v, 2, c->d_edge_order, nch))) return rc;
+  if ((rc = build_order(c, c->nt, (int64_t)kTetChunk, c->d_tet_v, 4, c->d_tet_order, nch))) return rc;
   if (c->legacy_sweep) return MAG_OK;
   if ((rc = build_rows<2>(c, c->ne, c->d_edge_v, c->erows))) return rc;
   if ((rc = build_rows<4>(c, c->nt, c->d_tet_v, c->trows))) return rc;
@@ -1674,28 +1588,13 @@ int magk_build_schedule(mag_ctx* c)
 }
 
 // ---- whole-part sweeps over the anchor rows
-template <int KIND, bool FAST>
-static int launch_edge_rows_t(mag_ctx* c, const SweepParams& P)
-{
-  constexpr int T = EdgeRowCfg<KIND, FAST>::T;
-  const int per_sm = blocks_per_sm(c, (const void*)k_edge_rows<KIND, FAST>, T);
-  int64_t g = (int64_t)per_sm * c->n_sms;
-  const int64_t need = (c->erows.n_slices + T / 32 - 1) / (T / 32);
-  if (g > need) g = need;
-  k_edge_rows<KIND, FAST><<<(unsigned)(g < 1 ? 1 : g), T, 0, c->stream>>>(
-      (int32_t)c->erows.n_slices, c->erows.d_anchor, c->erows.d_slice_off, reinterpret_cast<const int2*>(c->erows.d_slots), c->d_vedge,
-      c->d_edge_flags, c->d_len, edge_params(P, c->edge_flags_zero), c->d_stats, c->d_near_edge,
-      pf_args(c, c->erows.d_pf, c->erows.n_slices, (g < 1 ? 1 : g) * (T / 32) * 3 / 2 + 64));
-  MAG_CUDA(c, cudaGetLastError());
-  c->n_launches++;
-  return MAG_OK;
-}
 // Which kernel family serves a whole-part sweep (measured on B200, n = 203, r2c / r2d):
 //   lean row kernels (mag_lean.cuh)  MAG_FP_FAST over all-zero incoming flag words, every output of the dimension requested,
 //                                    max-Jacobian metric: 1.26 / 0.78 ms (edges / tets) against 1.35 / 0.80 for the tiles;
 //   tile kernels (k_edges / k_tets)  everything else.  The log-Euclidean edge kernel stays with the tiles as well (its QR
 //                                    iteration wants every register: 4.7 ms against 5.4 ms in a row kernel);
-//   general row kernels              only with MAG_GENERAL_ROWS=1 (A/B measurements): 1.43 / 0.82 ms, slower than the tiles.
+//   (general row kernels -- the lean ones plus incoming words and single marks -- were built and measured: 1.43 / 0.82 ms,
+//    slower than the tiles, and removed.)
 static bool lean_edges_ok(const mag_ctx* c, const SweepParams& P, bool fast)
 {
   constexpr uint32_t kEdgeFull = MAG_OP_LENGTHS | MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE;
@@ -1708,11 +1607,11 @@ static bool lean_tets_ok(const mag_ctx* c, const SweepParams& P, bool fast)
 }
 static bool use_edge_rows(const mag_ctx* c, const SweepParams& P, bool fast)
 {
-  return !c->legacy_sweep && (c->general_rows || lean_edges_ok(c, P, fast));
+  return !c->legacy_sweep && lean_edges_ok(c, P, fast);
 }
 static bool use_tet_rows(const mag_ctx* c, const SweepParams& P, bool fast)
 {
-  return !c->legacy_sweep && (c->general_rows || lean_tets_ok(c, P, fast));
+  return !c->legacy_sweep && lean_tets_ok(c, P, fast);
 }
 
 // the lean kernels (mag_lean.cuh): MAG_FP_FAST sweeps over all-zero incoming flag words
@@ -1735,7 +1634,7 @@ static int launch_edge_rows_z(mag_ctx* c, const SweepParams& P)
 template <int KIND>
 static int launch_tet_rows_z(mag_ctx* c, const SweepParams& P)
 {
-  constexpr int T = MAG_TZ2_THREADS;
+  constexpr int T = MAG_TZ_THREADS;
   const int per_sm = blocks_per_sm(c, (const void*)k_tet_rows_z<KIND>, T);
   int64_t g = (int64_t)per_sm * c->n_sms;
   const int64_t groups = (c->trows.n_slices + kTZGroup - 1) / kTZGroup;
@@ -1750,60 +1649,21 @@ static int launch_tet_rows_z(mag_ctx* c, const SweepParams& P)
   return MAG_OK;
 }
 
-static int launch_edge_rows(mag_ctx* c, const SweepParams& P, bool fast)
+static int launch_edge_rows(mag_ctx* c, const SweepParams& P, bool)
 {
-  if (lean_edges_ok(c, P, fast)) {
-    switch (c->kind) {
-      case MAG_KIND_IDENTITY: return launch_edge_rows_z<MAG_KIND_IDENTITY>(c, P);
-      case MAG_KIND_ISO: return launch_edge_rows_z<MAG_KIND_ISO>(c, P);
-      case MAG_KIND_ANISO: return launch_edge_rows_z<MAG_KIND_ANISO>(c, P);
-      default: return launch_edge_rows_z<MAG_KIND_LOGM>(c, P);
-    }
-  }
   switch (c->kind) {
-    case MAG_KIND_IDENTITY: return fast ? launch_edge_rows_t<MAG_KIND_IDENTITY, true>(c, P) : launch_edge_rows_t<MAG_KIND_IDENTITY, false>(c, P);
-    case MAG_KIND_ISO: return fast ? launch_edge_rows_t<MAG_KIND_ISO, true>(c, P) : launch_edge_rows_t<MAG_KIND_ISO, false>(c, P);
-    case MAG_KIND_ANISO: return fast ? launch_edge_rows_t<MAG_KIND_ANISO, true>(c, P) : launch_edge_rows_t<MAG_KIND_ANISO, false>(c, P);
-    default: return fast ? launch_edge_rows_t<MAG_KIND_LOGM, true>(c, P) : launch_edge_rows_t<MAG_KIND_LOGM, false>(c, P);
+    case MAG_KIND_IDENTITY: return launch_edge_rows_z<MAG_KIND_IDENTITY>(c, P);
+    case MAG_KIND_ISO: return launch_edge_rows_z<MAG_KIND_ISO>(c, P);
+    default: return launch_edge_rows_z<MAG_KIND_ANISO>(c, P);     // lean_edges_ok excludes the log-Euclidean field
   }
 }
-template <int KIND, bool FAST, bool USE_MAX>
-static int launch_tet_rows_t(mag_ctx* c, const SweepParams& P)
+static int launch_tet_rows(mag_ctx* c, const SweepParams& P, bool)
 {
-  constexpr int T = TetRowCfg<FAST>::T;
-  const int per_sm = blocks_per_sm(c, (const void*)k_tet_rows<KIND, FAST, USE_MAX>, T);
-  int64_t g = (int64_t)per_sm * c->n_sms;
-  const int64_t need = (c->trows.n_slices + T / 32 - 1) / (T / 32);
-  if (g > need) g = need;
-  k_tet_rows<KIND, FAST, USE_MAX><<<(unsigned)(g < 1 ? 1 : g), T, 0, c->stream>>>(
-      (int32_t)c->trows.n_slices, c->trows.d_anchor, c->trows.d_slice_off, reinterpret_cast<const int4*>(c->trows.d_slots),
-      (int32_t)(c->np + c->npy), c->nv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_flags, c->d_qual, tet_params(P, c->elem_flags_zero),
-      c->d_stats, c->d_near_elem, pf_args(c, c->trows.d_pf, c->trows.n_slices, (g < 1 ? 1 : g) * (T / 32) * 3 / 2 + 64));
-  MAG_CUDA(c, cudaGetLastError());
-  c->n_launches++;
-  return MAG_OK;
-}
-template <int KIND>
-static int launch_tet_rows_k(mag_ctx* c, const SweepParams& P, bool fast)
-{
-  if (P.use_max) return fast ? launch_tet_rows_t<KIND, true, true>(c, P) : launch_tet_rows_t<KIND, false, true>(c, P);
-  return fast ? launch_tet_rows_t<KIND, true, false>(c, P) : launch_tet_rows_t<KIND, false, false>(c, P);
-}
-static int launch_tet_rows(mag_ctx* c, const SweepParams& P, bool fast)
-{
-  if (lean_tets_ok(c, P, fast)) {
-    switch (c->kind) {
-      case MAG_KIND_IDENTITY: return launch_tet_rows_z<MAG_KIND_IDENTITY>(c, P);
-      case MAG_KIND_ISO: return launch_tet_rows_z<MAG_KIND_ISO>(c, P);
-      case MAG_KIND_ANISO: return launch_tet_rows_z<MAG_KIND_ANISO>(c, P);
-      default: return launch_tet_rows_z<MAG_KIND_LOGM>(c, P);
-    }
-  }
   switch (c->kind) {
-    case MAG_KIND_IDENTITY: return launch_tet_rows_k<MAG_KIND_IDENTITY>(c, P, fast);
-    case MAG_KIND_ISO: return launch_tet_rows_k<MAG_KIND_ISO>(c, P, fast);
-    case MAG_KIND_ANISO: return launch_tet_rows_k<MAG_KIND_ANISO>(c, P, fast);
-    default: return launch_tet_rows_k<MAG_KIND_LOGM>(c, P, fast);
+    case MAG_KIND_IDENTITY: return launch_tet_rows_z<MAG_KIND_IDENTITY>(c, P);
+    case MAG_KIND_ISO: return launch_tet_rows_z<MAG_KIND_ISO>(c, P);
+    case MAG_KIND_ANISO: return launch_tet_rows_z<MAG_KIND_ANISO>(c, P);
+    default: return launch_tet_rows_z<MAG_KIND_LOGM>(c, P);
   }
 }
 

@@ -213,150 +213,16 @@ k_edge_rows_z(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t
   if (lane == 0 && m) atomicMax(&st->max_len_bits, m);
 }
 
-// ------------------------------------------------------------------ tets, second form: two dependent gathers pipelined over two rows
-// The quality of a tet needs its four vertices and then -- a DEPENDENT gather -- the transform of the vertex with the largest
-// det Q_v.  Per lane and slot row k (one tet):
-//     row k-1, top:  {z, det Q_v} of the three other vertices of tet k+1 requested            (slot words: two rows earlier still)
-//     row k,   top:  e = x_i - x_0 and y = e Q_k computed (coordinates and Q_k are dead from here on); the max-Jacobian vertex
-//                    of tet k+1 chosen from the determinants that arrived during row k-1; ITS transform and the {x, y} of tet k+1
-//                    requested into the registers just freed; {z, det} of tet k+2 requested
-//     row k,   rest: quality from y (sum of squared edges, volume), outputs
-// so every gather has one whole row (~230 instructions of this warp, several hundred cycles with the SM's other warps) to
-// arrive, and nothing is waited for except at a slice boundary.  Registers instead of resident warps: 3 x 128 threads per SM.
-#ifndef MAG_TZ2_THREADS
-#define MAG_TZ2_THREADS 128
-#endif
-#ifndef MAG_TZ2_BLOCKS
-#define MAG_TZ2_BLOCKS 3
-#endif
-template <int KIND>
-__global__ void __launch_bounds__(MAG_TZ2_THREADS, MAG_TZ2_BLOCKS)
-k_tet_rows_z(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t* __restrict__ slice_off, const int4* __restrict__ slots,
-             int32_t elem_off, int64_t nv, const double* __restrict__ vpos, const double* __restrict__ vq, const double* __restrict__ vedge,
-             int32_t* __restrict__ flags, double* __restrict__ qual, TetParams P, MagDevStats* st, int32_t* __restrict__ near_list)
-{
-  const int lane = threadIdx.x & 31;
-  const double good_q = P.good_q, tol_q = P.tol_q;
-  unsigned c_bad = 0, c_eval = 0;
-  unsigned long long minkey = ~0ull;
-  int eig_any = 0;
-  flags += elem_off;
-  qual += elem_off;
-  const int4 kNone = make_int4(0, 0, 0, -1);
-  const double2 kZero = make_double2(0.0, 0.0);
-  auto load_zd = [&](const int4& sl, double2* zd) {
-    zd[0] = __ldg(chunk_ptr<2>(vpos, 1, sl.x & kVidMask)); zd[1] = __ldg(chunk_ptr<2>(vpos, 1, sl.y)); zd[2] = __ldg(chunk_ptr<2>(vpos, 1, sl.z));
-  };
-  // transform of the max-Jacobian vertex of (va, sl) and the {x, y} of its other three vertices
-  auto load_xyq = [&](const int4& sl, int32_t va, double a_det, const double2* zd, double2* xy, double2* q) {
-    const int32_t v1 = sl.x & kVidMask;
-    const int32_t vb = best_vertex(make_int4(va, v1, sl.y, sl.z), a_det, zd[0].y, zd[1].y, zd[2].y);
-    const double2* pq = chunk_ptr<5>(vq, 0, vb);
-    xy[0] = __ldg(chunk_ptr<2>(vpos, 0, v1)); xy[1] = __ldg(chunk_ptr<2>(vpos, 0, sl.y)); xy[2] = __ldg(chunk_ptr<2>(vpos, 0, sl.z));
-#pragma unroll
-    for (int i = 0; i < 5; ++i) q[i] = __ldg(pq + i * kVB);
-  };
-  GroupWalk<kTZGroup> w;
-  w.begin(&st->elem_chunk, nslices);
-  int off = 0, off1 = 0, va = -1;
-  int4 s0 = kNone, s1 = kNone, s2 = kNone;
-  if (w.s < nslices) {
-    off = __ldg(slice_off + w.s); off1 = __ldg(slice_off + w.s + 1); va = __ldg(anchor + (w.s << 5) + lane);
-    s0 = ld_stream(slots + off + lane);
-    if (off1 - off > 32) s1 = ld_stream(slots + off + lane + 32);
-    if (off1 - off > 64) s2 = ld_stream(slots + off + lane + 64);
-  }
-  while (w.s < nslices) {
-    const int s_nx = w.next_slice(&st->elem_chunk, nslices);
-    int off_nx = 0, off1_nx = 0, va_nx = -1;
-    if (s_nx < nslices) { off_nx = __ldg(slice_off + s_nx); off1_nx = __ldg(slice_off + s_nx + 1); va_nx = __ldg(anchor + (s_nx << 5) + lane); }
-    const int K = (off1 - off) >> 5;
-    const int4* sp = slots + off + lane;
-    double2 a_xy = kZero, a_zd = kZero;
-    if (va >= 0) { a_xy = __ldg(chunk_ptr<2>(vpos, 0, va)); a_zd = __ldg(chunk_ptr<2>(vpos, 1, va)); }
-    // prologue of the slice: tet 0 completely, {z, det} of tet 1
-    double2 zdA[3] = {kZero, kZero, kZero}, zdB[3] = {kZero, kZero, kZero}, xy[3] = {kZero, kZero, kZero}, q[5] = {kZero, kZero, kZero, kZero, kZero};
-    if (s0.w >= 0) load_zd(s0, zdA);
-    if (s1.w >= 0) load_zd(s1, zdB);
-    if (s0.w >= 0) load_xyq(s0, va, a_zd.y, zdA, xy, q);
-    int4 n0 = kNone, n1 = kNone, n2 = kNone;      // first three slot words of the next slice
-    bool have_next = false;
-    unsigned nearmask = 0;
-    // one row: cur = this tet (its zd in zc, xy / q loaded), nx = the next one (its zd in zn), n2 = the one after
-    auto row = [&](const int4 cur, const int4 nx, const int4 nn, double2* zc, double2* zn, const int k) {
-      double y[3][3];
-      const int t = cur.w;
-      if (t >= 0) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const double ex = xy[i].x - a_xy.x, ey = xy[i].y - a_xy.y, ez = zc[i].x - a_zd.x;
-          y[i][0] = fma(ez, q[3].x, fma(ey, q[1].y, __dmul_rn(ex, q[0].x)));   // Q row-major in q: {00,01} {02,10} {11,12} {20,21} {22,det}
-          y[i][1] = fma(ez, q[3].y, fma(ey, q[2].x, __dmul_rn(ex, q[0].y)));
-          y[i][2] = fma(ez, q[4].x, fma(ey, q[2].y, __dmul_rn(ex, q[1].x)));
-        }
-      }
-      if (nx.w >= 0) load_xyq(nx, va, a_zd.y, zn, xy, q);     // coordinates and transform of this tet are consumed
-      if (nn.w >= 0) load_zd(nn, zc);
-      if (t < 0) return;
-      const double qv = magfa::tet_quality_y(y);
-      st_stream(qual + t, qv);
-      const unsigned long long kq = dkey(qv);
-      minkey = kq < minkey ? kq : minkey;
-      const bool nr = fabs(qv - good_q) <= tol_q;
-      nearmask |= (nr ? 1u : 0u) << k;
-      if (!nr) {
-        ++c_eval;
-        const bool bad = qv < good_q;
-        c_bad += (bad && cur.x >= 0) ? 1u : 0u;
-        st_stream(flags + t, (int32_t)(bad ? MAG_BAD_QUALITY : MAG_OK_QUALITY));
-      }
-    };
-    for (int k = 0; k < K; k += 2) {
-      if (k == 2 && s_nx < nslices) {
-        n0 = ld_stream(slots + off_nx + lane);
-        if (off1_nx - off_nx > 32) n1 = ld_stream(slots + off_nx + lane + 32);
-        if (off1_nx - off_nx > 64) n2 = ld_stream(slots + off_nx + lane + 64);
-        have_next = true;
-      }
-      int4 s3 = kNone, s4 = kNone;
-      if (k + 3 < K) s3 = ld_stream(sp + (k + 3) * 32);
-      if (k + 4 < K) s4 = ld_stream(sp + (k + 4) * 32);
-      row(s0, s1, s2, zdA, zdB, k);
-      row(s1, s2, s3, zdB, zdA, k + 1);
-      s0 = s2; s1 = s3; s2 = s4;
-    }
-    if (!have_next && s_nx < nslices) {
-      n0 = ld_stream(slots + off_nx + lane);
-      if (off1_nx - off_nx > 32) n1 = ld_stream(slots + off_nx + lane + 32);
-      if (off1_nx - off_nx > 64) n2 = ld_stream(slots + off_nx + lane + 64);
-    }
-    for (unsigned any = __reduce_or_sync(0xffffffffu, nearmask); any; any &= any - 1) {
-      const int k = __ffs(any) - 1;
-      const bool nr = (nearmask >> k) & 1u;
-      const int4 qs = nr ? __ldg(sp + k * 32) : kNone;
-      const unsigned r = near_tets<KIND, true>(nr, qs.w, elem_off, make_int4(va, qs.x, qs.y, qs.z), 0, nv, vpos, vq, vedge, flags - elem_off,
-                                               qual - elem_off, P.ops, good_q, P.use_max, st, near_list);
-      c_eval += r & 1u; c_bad += (r >> 1) & 1u; eig_any |= (int)(r >> 2);
-    }
-    w.advance(s_nx);
-    off = off_nx; off1 = off1_nx; va = va_nx;
-    s0 = n0; s1 = n1; s2 = n2;
-  }
-  if (eig_any) atomicAdd(&st->n_eigen_fail, 1ull);
-  warp_count_to(c_bad, &st->n_bad);
-  warp_count_to(c_eval, &st->n_elems_eval);
-  const unsigned long long m = warp_min_u64(minkey);
-  if (lane == 0 && m != ~0ull) atomicMin(&st->min_q_key, m);
-}
-
-#if MAG_TZ_V1
 // ------------------------------------------------------------------ tets
+// (A second form was built and measured, r2e: both dependent gathers -- {z, det} two rows ahead, the winner's transform and {x, y}
+//  one row ahead -- pipelined so that nothing is waited for inside a slice, at 168 registers = 3 x 128 threads per SM: 0.87 ms
+//  against 0.78 ms for this one at 2 x 256.  Resident warps beat prefetch depth here: see DESIGN.md section 4, fp64 latency.)
 // qualities + BAD_QUALITY of every tet.  slot = {o1 | not-owned << 31, o2, o3, tet index}; the anchor is the tet's first vertex (see k_tet_rows).  Per lane: the
 // anchor's {x,y,z,det Q_v} for the whole row; the other three vertices' {x,y,z,det Q_v} one row ahead (ping-pong); the
 // transform of the max-Jacobian vertex (getMetricWithMaxJacobean, maQuality.cc:83-108) re-read only when the vertex changes.
 template <int KIND>
 __global__ void __launch_bounds__(MAG_TZ_THREADS, MAG_TZ_BLOCKS)
-k_tet_rows_z1(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t* __restrict__ slice_off, const int4* __restrict__ slots,
+k_tet_rows_z(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t* __restrict__ slice_off, const int4* __restrict__ slots,
              int32_t elem_off, int64_t nv, const double* __restrict__ vpos, const double* __restrict__ vq, const double* __restrict__ vedge,
              int32_t* __restrict__ flags, double* __restrict__ qual, TetParams P, MagDevStats* st, int32_t* __restrict__ near_list)
 {
@@ -461,4 +327,3 @@ k_tet_rows_z1(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t
   const unsigned long long m = warp_min_u64(minkey);
   if (lane == 0 && m != ~0ull) atomicMin(&st->min_q_key, m);
 }
-#endif

@@ -106,6 +106,10 @@ double now()
 
 } // namespace
 
+/* for ref_shape_shim.cc (same library) */
+ma::Adapt* refo_internal_adapt(void* hd) { return hd ? ((Ref*)hd)->a : 0; }
+apf::Mesh2* refo_internal_mesh(void* hd) { return hd ? ((Ref*)hd)->m : 0; }
+
 extern "C" {
 
 void* refo_box(int nx, int ny, int nz, double wx, double wy, double wz)

@@ -210,6 +210,17 @@ class RefMesh:
         assert lib().refo_sliver_codes(self.h, float(good_quality), _p(codes), _p(match), _p(f0)) == 0
         return codes, match, f0
 
+    def short_edge(self, max_edge_ratio):
+        """ShortEdgeFixer::shouldApply (maShape.cc:188-219) on every element, on the flags the last mark() left on the Adapt:
+        (short edge index or -1 per element, element flag words afterwards)."""
+        short = np.zeros(self.nelem, np.int32)
+        lf = np.zeros(self.nelem, np.int32)
+        f = lib().refo_short_edge
+        f.restype = C.c_int64
+        n = f(self.h, C.c_double(max_edge_ratio), _p(short), _p(lf))
+        assert n == self.nelem, n
+        return short, lf
+
     def split_vertices(self, edges):
         """Position and size-field values ma::makeSplitVert gives the vertex splitting each listed edge."""
         edges = np.ascontiguousarray(edges, dtype=np.int64)

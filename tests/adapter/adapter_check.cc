@@ -25,6 +25,7 @@
 #include <PCU.h>
 #include <cmath>
 #include <vector>
+#include <map>
 #include <chrono>
 
 namespace ma {
@@ -326,6 +327,82 @@ static int adapter_check(int n, int nz, int log_interp, int fp_mode, double jitt
   bad |= sliver_diffs != 0;
   bad |= stats_diffs != 0;
   return bad;
+}
+
+/* mag::buildEdgeLinks against a stub apf::Sharing (there is no MPI here): two boxes stand for the two x-slab parts of an
+   (nxA + nxB) x ny x nz box.  The stub says what PUMI would: an edge of part 0 in its plane x = max and the edge of part 1 in
+   its plane x = 0 with the same (y, z) end points are copies of each other; the owner is the part with fewer elements,
+   ties -> part 0 (apfPM.cc:109-126).  Returns the number of shared edges of `part` and writes their export indices / owner
+   bits in list order (tests/test_adapter.py compares them with boxmesh.slab_part's lists); < 0: error. */
+namespace {
+struct StubSharing : public apf::Sharing {
+  int self, peer;
+  bool selfOwns;
+  std::map<apf::MeshEntity*, apf::MeshEntity*> remote;
+  bool isShared(apf::MeshEntity* e) { return remote.count(e) != 0; }
+  bool isOwned(apf::MeshEntity* e) { return !isShared(e) || selfOwns; }
+  int getOwner(apf::MeshEntity* e) { return isOwned(e) ? self : peer; }
+  void getCopies(apf::MeshEntity* e, apf::CopyArray& copies)
+  {
+    std::map<apf::MeshEntity*, apf::MeshEntity*>::iterator it = remote.find(e);
+    copies.setSize(it == remote.end() ? 0 : 1);
+    if (it != remote.end()) copies[0] = apf::Copy(peer, it->second);
+  }
+};
+typedef std::vector<double> PlaneKey;
+/* edges with both ends in the plane x = px, keyed by the sorted (y, z) of their ends */
+void plane_edges(apf::Mesh2* m, double px, std::map<PlaneKey, apf::MeshEntity*>& out)
+{
+  apf::MeshIterator* it = m->begin(1);
+  apf::MeshEntity* e;
+  while ((e = m->iterate(it))) {
+    apf::Downward v;
+    m->getDownward(e, 0, v);
+    apf::Vector3 a, b;
+    m->getPoint(v[0], 0, a); m->getPoint(v[1], 0, b);
+    if (a[0] != px || b[0] != px) continue;
+    PlaneKey k(4);
+    const bool swap = (a[1] > b[1]) || (a[1] == b[1] && a[2] > b[2]);
+    k[0] = swap ? b[1] : a[1]; k[1] = swap ? b[2] : a[2]; k[2] = swap ? a[1] : b[1]; k[3] = swap ? a[2] : b[2];
+    out[k] = e;
+  }
+  m->end(it);
+}
+}
+extern "C" int mag_adapter_links_check(int nxA, int nxB, int ny, int nz, int part, int* idx_out, unsigned char* own_out, int cap)
+{
+  ensure_pcu();
+  apf::Mesh2* mesh[2] = {apf::makeMdsBox(nxA, ny, nz, nxA, ny, nz, true, g_pcu), apf::makeMdsBox(nxB, ny, nz, nxB, ny, nz, true, g_pcu)};
+  std::map<PlaneKey, apf::MeshEntity*> plane[2];
+  plane_edges(mesh[0], (double)nxA, plane[0]);
+  plane_edges(mesh[1], 0.0, plane[1]);
+  int rc = -1;
+  if (plane[0].size() == plane[1].size() && !plane[0].empty()) {
+    StubSharing sh;
+    sh.self = part; sh.peer = 1 - part;
+    const long nel[2] = {6L * nxA * ny * nz, 6L * nxB * ny * nz};
+    const int owner = (nel[1] < nel[0]) ? 1 : 0;
+    sh.selfOwns = owner == part;
+    bool ok = true;
+    for (std::map<PlaneKey, apf::MeshEntity*>::iterator it = plane[part].begin(); it != plane[part].end(); ++it) {
+      std::map<PlaneKey, apf::MeshEntity*>::iterator jt = plane[1 - part].find(it->first);
+      if (jt == plane[1 - part].end()) { ok = false; break; }
+      sh.remote[it->second] = jt->second;
+    }
+    std::vector<apf::MeshEntity*> edges;
+    apf::MeshIterator* it = mesh[part]->begin(1);
+    apf::MeshEntity* e;
+    while ((e = mesh[part]->iterate(it))) edges.push_back(e);
+    mesh[part]->end(it);
+    mag::EdgeLinks L;
+    mag::buildEdgeLinks(&sh, part, edges, L);
+    if (ok && L.peer.size() == 1 && L.peer[0] == 1 - part && (int)L.idx[0].size() <= cap) {
+      rc = (int)L.idx[0].size();
+      for (int i = 0; i < rc; ++i) { idx_out[i] = L.idx[0][i]; own_out[i] = L.peerOwns[0][i]; }
+    }
+  }
+  for (int i = 0; i < 2; ++i) { mesh[i]->destroyNative(); apf::destroyMesh(mesh[i]); }
+  return rc;
 }
 
 /* The drop-in claim end to end: ma::adapt (refine, coarsen, shape correction -- the UNMODIFIED reference driver) on two

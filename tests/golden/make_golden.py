@@ -66,6 +66,11 @@ def case(name, m, kind, h=None, R=None, good_quality=-1.0, edge_flags=None, elem
             if kind == refo.KIND_ANISO_FIELD:
                 out["split_a"] = sa
     if simplex_only and np.all(et == refo.TET):
+        # ShortEdgeFixer::shouldApply (maShape.cc:188-219; the class is local to that file: oracle/ref/ref_shape_shim.cc) on
+        # the BAD_QUALITY marks: the edge it hands to its ShortEdgeRemover (-1: not applied) and the flag words afterwards
+        for ratio in (2.0, 100.0):            # maInput.cc:35,43: the two defaults of maximumEdgeRatio
+            m.mark(which=which, good_quality=good_quality, edge_flags=edge_flags, elem_flags=elem_flags)
+            out["short_edge_%g" % ratio], out["short_flags_%g" % ratio] = m.short_edge(ratio)
         # ma::getSliverCode / matchSliver of every tet (maShape.cc:35-120) + the first face's own vertex order
         out["sliver_codes"], out["sliver_match"], out["face0_v"] = m.sliver_codes(good_quality)
     if not simplex_only:

@@ -216,3 +216,24 @@ def test_stats_tables_match_ma_stats(name, built, tmp_path):
     assert rows[0] == "%g" % el[0] and np.allclose(np.array(rows[:-1], float), el, rtol=1e-5)
     got = np.array([float(x) for x in open(pq).read().split()])   # empty on a mesh without simplex elements
     assert len(got) == len(lq) and np.allclose(got, lq, rtol=1e-5, atol=1e-300)
+
+
+@pytest.mark.parametrize("name", [n for n in util.golden_cases() if "short_edge_2" in util.load(n)])
+def test_short_edge_fixer_restatement_matches_reference(name):
+    """ShortEdgeFixer::shouldApply (maShape.cc:188-219), reached in the compiled reference through oracle/ref/ref_shape_shim.cc:
+    its answers (golden vectors) equal the few lines restated with numpy on the reference's own lengths and flag words --
+    ratio test max/min < maximumEdgeRatio clears BAD_QUALITY, otherwise the FIRST shortest edge in getDownward order."""
+    g = util.load(name)
+    _, _, tet_v = util.split_elements(g)
+    if len(tet_v) == 0:
+        pytest.skip("no tets")
+    from test_gpu_parity import tet_edge_table
+    te = tet_edge_table(g["edge_v"], tet_v)
+    BAD = 1 << 5
+    bad = (g["elem_flags_out"] & BAD) != 0
+    l = g["lengths"][te]
+    for ratio in (2.0, 100.0):
+        cleared = bad & (l.max(axis=1) / l.min(axis=1) < ratio)
+        want = np.where(bad & ~cleared, te[np.arange(len(te)), l.argmin(axis=1)], -1)
+        assert np.array_equal(want, g["short_edge_%g" % ratio])
+        assert np.array_equal(np.where(cleared, g["elem_flags_out"] & ~BAD, g["elem_flags_out"]), g["short_flags_%g" % ratio])
