@@ -1269,12 +1269,12 @@ static int launch_tris(mag_ctx* c, const SweepParams& P, bool fast)
 }
 
 // persistent grids: resident blocks per SM x number of SMs (queried once per context)
-static int blocks_per_sm(mag_ctx* c, const void* kernel, int threads)
+static int blocks_per_sm(mag_ctx* c, const void* kernel, int threads, size_t dyn_smem = 0)
 {
   auto it = c->occupancy.find(kernel);
   if (it != c->occupancy.end()) return it->second;
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem) != cudaSuccess || per_sm < 1) per_sm = 1;
   c->occupancy[kernel] = per_sm;
   return per_sm;
 }
@@ -1619,12 +1619,15 @@ template <int KIND>
 static int launch_edge_rows_z(mag_ctx* c, const SweepParams& P)
 {
   constexpr int T = EdgeLeanCfg<KIND>::T;
-  const int per_sm = blocks_per_sm(c, (const void*)k_edge_rows_z<KIND>, T);
+  constexpr size_t kSmem = EdgeLeanCfg<KIND>::kSmem;
+  if (c->occupancy.find((const void*)k_edge_rows_z<KIND>) == c->occupancy.end())
+    MAG_CUDA(c, cudaFuncSetAttribute(k_edge_rows_z<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+  const int per_sm = blocks_per_sm(c, (const void*)k_edge_rows_z<KIND>, T, kSmem);
   int64_t g = (int64_t)per_sm * c->n_sms;
   const int64_t groups = (c->erows.n_slices + kEZGroup - 1) / kEZGroup;
   const int64_t need = (groups + T / 32 - 1) / (T / 32);
   if (g > need) g = need;
-  k_edge_rows_z<KIND><<<(unsigned)(g < 1 ? 1 : g), T, 0, c->stream>>>(
+  k_edge_rows_z<KIND><<<(unsigned)(g < 1 ? 1 : g), T, kSmem, c->stream>>>(
       (int32_t)c->erows.n_slices, c->erows.d_anchor, c->erows.d_slice_off, reinterpret_cast<const int2*>(c->erows.d_slots), c->d_vedge,
       c->d_edge_flags, c->d_len, edge_params(P, true), c->d_stats, c->d_near_edge);
   MAG_CUDA(c, cudaGetLastError());

@@ -34,13 +34,6 @@
 #ifndef MAG_TZ_BLOCKS
 #define MAG_TZ_BLOCKS 2
 #endif
-#ifndef MAG_EZ_GROUP
-#define MAG_EZ_GROUP 2   /* slices per ticket, edges: 2 -> 0.845 / 1.233 ms, 4 -> 0.875 / 1.259 ms (jittered / lattice, r2d) */
-#endif
-#ifndef MAG_TZ_GROUP
-#define MAG_TZ_GROUP 4   /* tets: 4 -> 0.853 / 0.783 ms, 2 -> 0.880 / 0.811 ms */
-#endif
-constexpr int kEZGroup = MAG_EZ_GROUP, kTZGroup = MAG_TZ_GROUP;
 
 // Groups of G consecutive slices per ticket, two tickets in flight: the id of the slice after the current one is
 // known at the top of every slice (so its header can travel during the slice) without ever waiting for the atomic.
@@ -73,24 +66,99 @@ struct GroupWalk {
   }
 };
 
-template <int KIND>
-__device__ __forceinline__ double edge_length_fast_p(const double* __restrict__ a, const double* __restrict__ b, int* eig_fail)
+// ------------------------------------------------------------------ the stream kernels
+// ncu source page of the first lean kernels (r2d / r2e, n = 203): a third of the edge kernel's and half of the tet kernel's
+// warp time was "long scoreboard" -- not at the gathers themselves, which were requested a row ahead, but at the TEST OF A SLOT
+// WORD that had been loaded two rows earlier, and at the start of every slice (header -> slot words -> anchor -> first record:
+// four dependent round trips for seven rows of work).  A warp has six scoreboard entries; a load that shares one with a younger
+// load is only "complete" when the younger one is, so a deep register pipeline of loads of different ages stalls on its
+// youngest member.  The stream kernels therefore keep exactly ONE kind of long-latency load in flight in the steady state --
+// the next row's gather -- and obey one rule: whatever a long-latency load returned is consumed at a point where nothing
+// younger has been issued.
+//   * slot words and the anchor's data of a whole slice travel into per-warp shared memory with cp.async (its own completion
+//     counter, no register, no scoreboard entry), for the NEXT slice while this one is evaluated: double buffer, each lane
+//     reads back only what it copied itself (no barrier);
+//   * a row is evaluated in two phases: the gathered record is consumed first (aniso_pre: 21 numbers), THEN the next row's
+//     gather is issued -- also across a slice boundary -- into the registers just freed, then the long part runs;
+//   * slice headers are requested a slice ahead and tickets a group ahead, and both are consumed at the first row of a slice
+//     right after phase one, where no gather is in flight.
+#ifndef MAG_EZ_GROUP
+#define MAG_EZ_GROUP 2
+#endif
+#ifndef MAG_TZ_GROUP
+#define MAG_TZ_GROUP 4
+#endif
+constexpr int kEZGroup = MAG_EZ_GROUP, kTZGroup = MAG_TZ_GROUP;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
 {
-  if (KIND == MAG_KIND_IDENTITY) return magfa::edge_identity(a, b);
-  if (KIND == MAG_KIND_ISO) return magfa::edge_iso(a, b);
-  if (KIND == MAG_KIND_ANISO) return magfa::edge_aniso(a, b);
-  return magfa::edge_logm(a, b, eig_fail);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// successive slice ids for one warp: groups of G consecutive slices per ticket, the next ticket always requested a group ahead
+template <int G>
+struct TicketStream {
+  int s, s_end, raw;
+  __device__ __forceinline__ int first(unsigned long long* counter, int n)
+  {
+    const int r0 = SliceWalk::issue(counter);
+    const int g = __shfl_sync(0xffffffffu, r0, 0);
+    raw = SliceWalk::issue(counter);
+    s = g * G;
+    s_end = s + G < n ? s + G : n;
+    return s < n ? s : n;
+  }
+  __device__ __forceinline__ int next(unsigned long long* counter, int n)
+  {
+    if (s + 1 < s_end) return ++s;
+    const int g = __shfl_sync(0xffffffffu, raw, 0);   // requested a whole group ago
+    raw = SliceWalk::issue(counter);
+    s = g * G;
+    s_end = s + G < n ? s + G : n;
+    return s < n ? s : n;
+  }
+};
+
+// the two phases of one edge, per size-field kind (mag_math_fast.cuh: aniso_pre / aniso_post); the other kinds have four-number
+// records and nothing worth splitting: phase one copies, phase two evaluates
+template <int KIND> struct EdgePre { double a[4], b[4]; };
+template <> struct EdgePre<MAG_KIND_ANISO> { magfa::AnisoPre p; };
+template <int KIND>
+__device__ __forceinline__ void edge_pre(const double* __restrict__ a, const double* __restrict__ b, EdgePre<KIND>& e)
+{
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { e.a[i] = a[i]; e.b[i] = b[i]; }
+}
+template <>
+__device__ __forceinline__ void edge_pre<MAG_KIND_ANISO>(const double* __restrict__ a, const double* __restrict__ b, EdgePre<MAG_KIND_ANISO>& e)
+{
+  magfa::aniso_pre(a, b, e.p);
+}
+template <int KIND>
+__device__ __forceinline__ double edge_post(const EdgePre<KIND>& e)
+{
+  return KIND == MAG_KIND_ISO ? magfa::edge_iso(e.a, e.b) : magfa::edge_identity(e.a, e.b);
+}
+template <>
+__device__ __forceinline__ double edge_post<MAG_KIND_ANISO>(const EdgePre<MAG_KIND_ANISO>& e)
+{
+  return magfa::aniso_post(e.p);
 }
 
 template <int KIND> struct EdgeLeanCfg {
-  static constexpr int T = MAG_EZ_THREADS, B = KIND == MAG_KIND_LOGM ? MAG_EROW_BLOCKS_LOGM : MAG_EZ_BLOCKS;
+  static constexpr int T = MAG_EZ_THREADS, B = MAG_EZ_BLOCKS;
+  static constexpr int C = EdgeRecs<KIND>::N / 2;
+  struct WarpBuf { double2 a[C][32]; int2 sl[kRowMax][32]; };   // one slice: the anchors' records and every slot word, lane-major
+  static constexpr size_t kSmem = sizeof(WarpBuf) * 2 * (T / 32);
 };
 
-#ifndef MAG_EZ_ASMEM
-#define MAG_EZ_ASMEM 1   /* 1: the anchor record lives in shared memory (one 16-byte chunk plane per warp and chunk, read back with
-                            conflict-free LDS.128) instead of 24 registers: the other end's record of the next row stays in flight */
-#endif
-// lengths + SPLIT + COLLAPSE of every edge, flag words written from zero
+// lengths + SPLIT + COLLAPSE of every edge, flag words written from zero (MAG_FP_FAST; identity / iso / aniso fields)
 template <int KIND>
 __global__ void __launch_bounds__(EdgeLeanCfg<KIND>::T, EdgeLeanCfg<KIND>::B)
 k_edge_rows_z(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t* __restrict__ slice_off, const int2* __restrict__ slots,
@@ -98,112 +166,106 @@ k_edge_rows_z(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t
               MagDevStats* st, int32_t* __restrict__ near_list)
 {
   constexpr int N = EdgeRecs<KIND>::N, C = N / 2;
-#if MAG_EZ_ASMEM
-  __shared__ double2 sh_a[EdgeLeanCfg<KIND>::T / 32][C][32];
-  double2 (*as)[32] = sh_a[threadIdx.x >> 5];
-#endif
+  typedef typename EdgeLeanCfg<KIND>::WarpBuf WarpBuf;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WarpBuf* wb = reinterpret_cast<WarpBuf*>(smem_raw) + 2 * (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const double max_len = P.max_len, min_len = P.min_len, tol_max = P.tol_max, tol_min = P.tol_min;
   unsigned c_split = 0, c_coll = 0, c_eval = 0;
   double maxlen = 0.0;                  // getMaximumEdgeLength starts at 0 and ignores NaN (maSize.cc:673-691)
   int eig_any = 0;
   const int2 kNone = make_int2(0, -1);
-  // one slot: length of edge sl.y between the anchor (record a) and the other end (record b); flag word from zero
-  auto item = [&](const int2 sl, const int k, const double* __restrict__ a_reg, const double* __restrict__ b, unsigned& nearmask) {
-    const int e = sl.y;
-    if (e < 0) return;
-#if MAG_EZ_ASMEM
-    double a[N];
-#pragma unroll
-    for (int i = 0; i < C; ++i) { const double2 t = as[i][lane]; a[2 * i] = t.x; a[2 * i + 1] = t.y; }
-    (void)a_reg;
-#else
-    const double* a = a_reg;
-#endif
-    const double len = edge_length_fast_p<KIND>(a, b, &eig_any);
-    const bool owned = sl.x >= 0;               // sign bit of the other vertex id = "not owned"
-    st_stream(lengths + e, len);
-    if (owned && len > maxlen) maxlen = len;
-    const bool nr = fabs(len - max_len) <= tol_max || fabs(len - min_len) <= tol_min;
-    nearmask |= (nr ? 1u : 0u) << k;
-    if (!nr) {                                  // near ones are decided in strict arithmetic after the row (near_edges)
-      ++c_eval;
-      const bool sp = len > max_len, co = len < min_len;
-      c_split += (sp && owned) ? 1u : 0u;
-      c_coll += (co && owned) ? 1u : 0u;
-      st_stream(flags + e, (int32_t)((sp ? MAG_SPLIT : MAG_NEED_NOT_SPLIT) | (co ? MAG_COLLAPSE : MAG_NEED_NOT_COLLAPSE)));
-    }
+  unsigned long long* counter = &st->edge_chunk;
+  auto fetch_header = [&](int s, int& off, int& K, int& va) {
+    off = __ldg(slice_off + s);
+    K = (__ldg(slice_off + s + 1) - off) >> 5;
+    va = __ldg(anchor + (s << 5) + lane);
   };
-  GroupWalk<kEZGroup> w;
-  w.begin(&st->edge_chunk, nslices);
-  int off = 0, off1 = 0, va = -1;
-  int2 s0 = kNone, s1 = kNone;
-  if (w.s < nslices) {
-    off = __ldg(slice_off + w.s); off1 = __ldg(slice_off + w.s + 1); va = __ldg(anchor + (w.s << 5) + lane);
-    s0 = ld_stream(slots + off + lane);
-    if (off1 - off > 32) s1 = ld_stream(slots + off + lane + 32);
-  }
-  while (w.s < nslices) {
-    const int s_nx = w.next_slice(&st->edge_chunk, nslices);
-    int off_nx = 0, off1_nx = 0, va_nx = -1;
-    if (s_nx < nslices) { off_nx = __ldg(slice_off + s_nx); off1_nx = __ldg(slice_off + s_nx + 1); va_nx = __ldg(anchor + (s_nx << 5) + lane); }
-    const int K = (off1 - off) >> 5;
+  // the anchors' records and all slot words of one slice -> shared memory buffer bi (asynchronous)
+  auto prefetch_slice = [&](int bi, int off, int K, int va) {
+    if (va >= 0) {
+      const double2* pa = chunk_ptr<C>(vedge, 0, va);
+#pragma unroll
+      for (int i = 0; i < C; ++i) cp_async16(&wb[bi].a[i][lane], pa + i * kVB);
+    }
     const int2* sp = slots + off + lane;
-    double b0[N], b1[N];
+    for (int k = 0; k < K; ++k) cp_async8(&wb[bi].sl[k][lane], sp + 32 * k);
+    cp_async_commit();
+  };
+  TicketStream<kEZGroup> ts;
+  int s_cur = ts.first(counter, nslices);
+  if (s_cur < nslices) {
+    int off_c, K, va_c;
+    fetch_header(s_cur, off_c, K, va_c);
+    prefetch_slice(0, off_c, K, va_c);
+    int s_n1 = ts.next(counter, nslices), s_n2 = nslices;
+    int hb_off = 0, hb_K = 0, hb_va = -1;          // header of the slice after the current one: requested, consumed at the safe point
+    if (s_n1 < nslices) fetch_header(s_n1, hb_off, hb_K, hb_va);
+    cp_async_wait_all();
+    int K_n1 = 0, va_n1 = -1;
+    int cb = 0, k = 0;
+    int2 cur = wb[0].sl[0][lane];
+    double b[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) { b0[i] = 0.0; b1[i] = 0.0; }
-#if MAG_EZ_ASMEM
-    {
-      const double2 z = make_double2(0.0, 0.0);
-      const double2* pa = chunk_ptr<C>(vedge, 0, va < 0 ? 0 : va);
-      __syncwarp();                              // every lane is done with the previous slice's anchor
-#pragma unroll
-      for (int i = 0; i < C; ++i) as[i][lane] = va >= 0 ? __ldg(pa + i * kVB) : z;
-      __syncwarp();
-    }
-    const double* a = nullptr;
-#else
-    double a_r[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) a_r[i] = 0.0;
-    if (va >= 0) load_half_rec<KIND>(vedge, va, a_r);
-    const double* a = a_r;
-#endif
-    if (s0.y >= 0) load_half_rec<KIND>(vedge, s0.x & kVidMask, b0);
-    int2 n0 = kNone, n1 = kNone;                  // first two slot words of the next slice
-    bool have_next = false;
+    for (int i = 0; i < N; ++i) b[i] = 0.0;
+    if (cur.y >= 0) load_half_rec<KIND>(vedge, cur.x & kVidMask, b);
     unsigned nearmask = 0;
-    for (int k = 0; k < K; k += 2) {
-      if (k == 2 && s_nx < nslices) {             // the next slice's header has arrived by now
-        n0 = ld_stream(slots + off_nx + lane);
-        if (off1_nx - off_nx > 32) n1 = ld_stream(slots + off_nx + lane + 32);
-        have_next = true;
+    for (;;) {
+      // phase one: the gathered record and the anchor's are consumed
+      EdgePre<KIND> pre;
+      if (cur.y >= 0) {
+        double a[N];
+#pragma unroll
+        for (int i = 0; i < C; ++i) { const double2 t = wb[cb].a[i][lane]; a[2 * i] = t.x; a[2 * i + 1] = t.y; }
+        edge_pre<KIND>(a, b, pre);
       }
-      int2 s2 = kNone, s3 = kNone;
-      if (k + 2 < K) s2 = ld_stream(sp + (k + 2) * 32);
-      if (s1.y >= 0) load_half_rec<KIND>(vedge, s1.x & kVidMask, b1);
-      item(s0, k, a, b0, nearmask);
-      if (k + 3 < K) s3 = ld_stream(sp + (k + 3) * 32);
-      if (s2.y >= 0) load_half_rec<KIND>(vedge, s2.x & kVidMask, b0);
-      item(s1, k + 1, a, b1, nearmask);
-      s0 = s2;
-      s1 = s3;
+      // safe point, once per slice: no gather is in flight.  The next slice's header has arrived (requested a slice ago): its
+      // data starts travelling into the other buffer; the header after that and the next ticket are requested.
+      if (k == 0) {
+        K_n1 = hb_K;
+        va_n1 = hb_va;
+        if (s_n1 < nslices) prefetch_slice(cb ^ 1, hb_off, hb_K, hb_va);
+        s_n2 = ts.next(counter, nslices);
+        if (s_n2 < nslices) fetch_header(s_n2, hb_off, hb_K, hb_va);
+      }
+      // the next row of the stream: its slot word from shared memory, its gather into the registers phase one freed
+      const bool last = k + 1 >= K;
+      int2 nx = kNone;
+      if (!last) nx = wb[cb].sl[k + 1][lane];
+      else if (s_n1 < nslices) { cp_async_wait_all(); nx = wb[cb ^ 1].sl[0][lane]; }
+      if (nx.y >= 0) load_half_rec<KIND>(vedge, nx.x & kVidMask, b);
+      // phase two and the outputs of this row
+      if (cur.y >= 0) {
+        const int e = cur.y;
+        const double len = edge_post<KIND>(pre);
+        const bool owned = cur.x >= 0;               // sign bit of the other vertex id = "not owned"
+        st_stream(lengths + e, len);
+        if (owned && len > maxlen) maxlen = len;
+        const bool nr = fabs(len - max_len) <= tol_max || fabs(len - min_len) <= tol_min;
+        nearmask |= (nr ? 1u : 0u) << k;
+        if (!nr) {                                  // near ones are decided in strict arithmetic after the slice (near_edges)
+          ++c_eval;
+          const bool sp = len > max_len, co = len < min_len;
+          c_split += (sp && owned) ? 1u : 0u;
+          c_coll += (co && owned) ? 1u : 0u;
+          st_stream(flags + e, (int32_t)((sp ? MAG_SPLIT : MAG_NEED_NOT_SPLIT) | (co ? MAG_COLLAPSE : MAG_NEED_NOT_COLLAPSE)));
+        }
+      }
+      if (!last) ++k;
+      else {
+        // near-threshold entities of the finished slice, one slot row at a time (warp-collective; its buffer is still intact)
+        for (unsigned any = __reduce_or_sync(0xffffffffu, nearmask); any; any &= any - 1) {
+          const int kk = __ffs(any) - 1;
+          const bool nr = (nearmask >> kk) & 1u;
+          const int2 q = nr ? wb[cb].sl[kk][lane] : kNone;
+          const unsigned r = near_edges<KIND, true>(nr, q.y, va_c, q.x, 0, vedge, flags, lengths, P.ops, max_len, min_len, st, near_list);
+          c_eval += r & 1u; c_split += (r >> 1) & 1u; c_coll += (r >> 2) & 1u; eig_any |= (int)(r >> 3);
+        }
+        if (s_n1 >= nslices) break;
+        cb ^= 1; K = K_n1; k = 0; va_c = va_n1; s_cur = s_n1; s_n1 = s_n2; nearmask = 0;
+      }
+      cur = nx;
     }
-    if (!have_next && s_nx < nslices) {
-      n0 = ld_stream(slots + off_nx + lane);
-      if (off1_nx - off_nx > 32) n1 = ld_stream(slots + off_nx + lane + 32);
-    }
-    // near-threshold entities of this slice, one slot row at a time (see k_edge_rows)
-    for (unsigned any = __reduce_or_sync(0xffffffffu, nearmask); any; any &= any - 1) {
-      const int k = __ffs(any) - 1;
-      const bool nr = (nearmask >> k) & 1u;
-      const int2 q = nr ? __ldg(sp + k * 32) : kNone;
-      const unsigned r = near_edges<KIND, true>(nr, q.y, va, q.x, 0, vedge, flags, lengths, P.ops, max_len, min_len, st, near_list);
-      c_eval += r & 1u; c_split += (r >> 1) & 1u; c_coll += (r >> 2) & 1u; eig_any |= (int)(r >> 3);
-    }
-    w.advance(s_nx);
-    off = off_nx; off1 = off1_nx; va = va_nx;
-    s0 = n0; s1 = n1;
   }
   if (eig_any) atomicAdd(&st->n_eigen_fail, 1ull);
   warp_count_to(c_split, &st->n_split);

@@ -100,22 +100,33 @@ __device__ __forceinline__ double half_sum_sqrt_ratios(double np, double dp, dou
   return __dmul_rn(0.5, __dadd_rn(sp, sm));
 }
 
-// The records are consumed first -- both Gauss points' interpolated values c = a + t (b - a) -- so a and b are dead
-// before the long part starts (the kernels keep other records in flight meanwhile: registers)
-__device__ __forceinline__ double edge_aniso(const double* __restrict__ a, const double* __restrict__ b)
+// An edge evaluation in two phases, so that a kernel can put memory traffic between them:
+//   aniso_pre   consumes the two vertex records: d = x1 - x0 and both Gauss points' interpolated values c = a + t (b - a)
+//               (21 numbers); the records are dead afterwards -- their registers can take the next edge's loads
+//   aniso_post  the long part: two Gram-Schmidt points and the two square roots
+struct AnisoPre { double d[3], cp[9], cm[9]; };
+__device__ __forceinline__ void aniso_pre(const double* __restrict__ a, const double* __restrict__ b, AnisoPre& p)
 {
-  const double dx = b[0] - a[0], dy = b[1] - a[1], dz = b[2] - a[2]; // 2d; the 1/2 is applied at the end
-  double cp[9], cm[9];
+  p.d[0] = b[0] - a[0]; p.d[1] = b[1] - a[1]; p.d[2] = b[2] - a[2];   // 2d; the 1/2 is applied at the end
 #pragma unroll
   for (int i = 0; i < 9; ++i) {
     const double dl = b[3 + i] - a[3 + i];
-    cp[i] = fma(kNP1, dl, a[3 + i]);   // xi = +XI: weights (kNP0, kNP1)
-    cm[i] = fma(kNP0, dl, a[3 + i]);   // xi = -XI: weights (kNP1, kNP0)
+    p.cp[i] = fma(kNP1, dl, a[3 + i]);   // xi = +XI: weights (kNP0, kNP1)
+    p.cm[i] = fma(kNP0, dl, a[3 + i]);   // xi = -XI: weights (kNP1, kNP0)
   }
+}
+__device__ __forceinline__ double aniso_post(const AnisoPre& p)
+{
   double np, dp, nm, dm;
-  aniso_point_nd(cp, dx, dy, dz, np, dp);
-  aniso_point_nd(cm, dx, dy, dz, nm, dm);
+  aniso_point_nd(p.cp, p.d[0], p.d[1], p.d[2], np, dp);
+  aniso_point_nd(p.cm, p.d[0], p.d[1], p.d[2], nm, dm);
   return half_sum_sqrt_ratios(np, dp, nm, dm);
+}
+__device__ __forceinline__ double edge_aniso(const double* __restrict__ a, const double* __restrict__ b)
+{
+  AnisoPre p;
+  aniso_pre(a, b, p);
+  return aniso_post(p);
 }
 
 // log-Euclidean field.  The length at a Gauss point is sqrt(sum_k exp(lambda_k) (v_k . j)^2), j = (x1 - x0) / 2, with
