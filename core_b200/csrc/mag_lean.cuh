@@ -78,8 +78,9 @@ struct GroupWalk {
 //   * slot words and the anchor's data of a whole slice travel into per-warp shared memory with cp.async (its own completion
 //     counter, no register, no scoreboard entry), for the NEXT slice while this one is evaluated: double buffer, each lane
 //     reads back only what it copied itself (no barrier);
-//   * a row is evaluated in two phases: the gathered record is consumed first (aniso_pre: 21 numbers), THEN the next row's
-//     gather is issued -- also across a slice boundary -- into the registers just freed, then the long part runs;
+//   * a row is evaluated in phases: the gathered record is consumed first (aniso_pre: 21 numbers), the first Gauss point is
+//     evaluated, THEN the next row's gather is issued -- also across a slice boundary -- into registers that are free by then,
+//     and the second Gauss point and the square roots run while it travels;
 //   * slice headers are requested a slice ahead and tickets a group ahead, and both are consumed at the first row of a slice
 //     right after phase one, where no gather is in flight.
 #ifndef MAG_EZ_GROUP
@@ -125,10 +126,10 @@ struct TicketStream {
   }
 };
 
-// the two phases of one edge, per size-field kind (mag_math_fast.cuh: aniso_pre / aniso_post); the other kinds have four-number
-// records and nothing worth splitting: phase one copies, phase two evaluates
+// the phases of one edge, per size-field kind (mag_math_fast.cuh: aniso_pre / aniso_point / half_sum_sqrt_ratios); the other
+// kinds have four-number records and nothing worth splitting: phase one copies, the last phase evaluates
 template <int KIND> struct EdgePre { double a[4], b[4]; };
-template <> struct EdgePre<MAG_KIND_ANISO> { magfa::AnisoPre p; };
+template <> struct EdgePre<MAG_KIND_ANISO> { magfa::AnisoPre p; double np, dp; };
 template <int KIND>
 __device__ __forceinline__ void edge_pre(const double* __restrict__ a, const double* __restrict__ b, EdgePre<KIND>& e)
 {
@@ -140,6 +141,14 @@ __device__ __forceinline__ void edge_pre<MAG_KIND_ANISO>(const double* __restric
 {
   magfa::aniso_pre(a, b, e.p);
 }
+// the part of the evaluation that runs BEFORE the next row's gather is issued (first Gauss point)
+template <int KIND> __device__ __forceinline__ void edge_mid(EdgePre<KIND>&) {}
+template <>
+__device__ __forceinline__ void edge_mid<MAG_KIND_ANISO>(EdgePre<MAG_KIND_ANISO>& e)
+{
+  magfa::aniso_point(e.p, 0, e.np, e.dp);
+  magfa::aniso_fence(e.p, e.np, e.dp);
+}
 template <int KIND>
 __device__ __forceinline__ double edge_post(const EdgePre<KIND>& e)
 {
@@ -148,7 +157,9 @@ __device__ __forceinline__ double edge_post(const EdgePre<KIND>& e)
 template <>
 __device__ __forceinline__ double edge_post<MAG_KIND_ANISO>(const EdgePre<MAG_KIND_ANISO>& e)
 {
-  return magfa::aniso_post(e.p);
+  double nm, dm;
+  magfa::aniso_point(e.p, 1, nm, dm);
+  return magfa::half_sum_sqrt_ratios(e.np, e.dp, nm, dm);
 }
 
 template <int KIND> struct EdgeLeanCfg {
@@ -170,7 +181,6 @@ k_edge_rows_z(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WarpBuf* wb = reinterpret_cast<WarpBuf*>(smem_raw) + 2 * (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  const double max_len = P.max_len, min_len = P.min_len, tol_max = P.tol_max, tol_min = P.tol_min;
   unsigned c_split = 0, c_coll = 0, c_eval = 0;
   double maxlen = 0.0;                  // getMaximumEdgeLength starts at 0 and ignores NaN (maSize.cc:673-691)
   int eig_any = 0;
@@ -205,15 +215,15 @@ k_edge_rows_z(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t
     int K_n1 = 0, va_n1 = -1;
     int cb = 0, k = 0;
     int2 cur = wb[0].sl[0][lane];
+    // Every row is evaluated, also the empty slots of short rows (their gather reads vertex 0, their result is dropped):
+    // no value is then live across a divergent branch, and the gather's registers are dead between phase one and its issue.
     double b[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) b[i] = 0.0;
-    if (cur.y >= 0) load_half_rec<KIND>(vedge, cur.x & kVidMask, b);
+    load_half_rec<KIND>(vedge, cur.y >= 0 ? (cur.x & kVidMask) : 0, b);
     unsigned nearmask = 0;
     for (;;) {
       // phase one: the gathered record and the anchor's are consumed
       EdgePre<KIND> pre;
-      if (cur.y >= 0) {
+      {
         double a[N];
 #pragma unroll
         for (int i = 0; i < C; ++i) { const double2 t = wb[cb].a[i][lane]; a[2 * i] = t.x; a[2 * i + 1] = t.y; }
@@ -228,24 +238,25 @@ k_edge_rows_z(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t
         s_n2 = ts.next(counter, nslices);
         if (s_n2 < nslices) fetch_header(s_n2, hb_off, hb_K, hb_va);
       }
+      edge_mid<KIND>(pre);                       // first Gauss point
       // the next row of the stream: its slot word from shared memory, its gather into the registers phase one freed
       const bool last = k + 1 >= K;
       int2 nx = kNone;
       if (!last) nx = wb[cb].sl[k + 1][lane];
       else if (s_n1 < nslices) { cp_async_wait_all(); nx = wb[cb ^ 1].sl[0][lane]; }
-      if (nx.y >= 0) load_half_rec<KIND>(vedge, nx.x & kVidMask, b);
-      // phase two and the outputs of this row
+      load_half_rec<KIND>(vedge, nx.y >= 0 ? (nx.x & kVidMask) : 0, b);
+      // second Gauss point, square roots, and the outputs of this row
+      const double len = edge_post<KIND>(pre);
       if (cur.y >= 0) {
         const int e = cur.y;
-        const double len = edge_post<KIND>(pre);
         const bool owned = cur.x >= 0;               // sign bit of the other vertex id = "not owned"
         st_stream(lengths + e, len);
         if (owned && len > maxlen) maxlen = len;
-        const bool nr = fabs(len - max_len) <= tol_max || fabs(len - min_len) <= tol_min;
+        const bool nr = fabs(len - P.max_len) <= P.tol_max || fabs(len - P.min_len) <= P.tol_min;
         nearmask |= (nr ? 1u : 0u) << k;
         if (!nr) {                                  // near ones are decided in strict arithmetic after the slice (near_edges)
           ++c_eval;
-          const bool sp = len > max_len, co = len < min_len;
+          const bool sp = len > P.max_len, co = len < P.min_len;
           c_split += (sp && owned) ? 1u : 0u;
           c_coll += (co && owned) ? 1u : 0u;
           st_stream(flags + e, (int32_t)((sp ? MAG_SPLIT : MAG_NEED_NOT_SPLIT) | (co ? MAG_COLLAPSE : MAG_NEED_NOT_COLLAPSE)));
@@ -258,7 +269,7 @@ k_edge_rows_z(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t
           const int kk = __ffs(any) - 1;
           const bool nr = (nearmask >> kk) & 1u;
           const int2 q = nr ? wb[cb].sl[kk][lane] : kNone;
-          const unsigned r = near_edges<KIND, true>(nr, q.y, va_c, q.x, 0, vedge, flags, lengths, P.ops, max_len, min_len, st, near_list);
+          const unsigned r = near_edges<KIND, true>(nr, q.y, va_c, q.x, 0, vedge, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list);
           c_eval += r & 1u; c_split += (r >> 1) & 1u; c_coll += (r >> 2) & 1u; eig_any |= (int)(r >> 3);
         }
         if (s_n1 >= nslices) break;

@@ -100,10 +100,13 @@ __device__ __forceinline__ double half_sum_sqrt_ratios(double np, double dp, dou
   return __dmul_rn(0.5, __dadd_rn(sp, sm));
 }
 
-// An edge evaluation in two phases, so that a kernel can put memory traffic between them:
-//   aniso_pre   consumes the two vertex records: d = x1 - x0 and both Gauss points' interpolated values c = a + t (b - a)
-//               (21 numbers); the records are dead afterwards -- their registers can take the next edge's loads
-//   aniso_post  the long part: two Gram-Schmidt points and the two square roots
+// An edge evaluation in phases, so that a kernel can put memory traffic between them:
+//   aniso_pre     consumes the two vertex records: d = x1 - x0 and both Gauss points' interpolated values c = a + t (b - a)
+//                 (21 numbers); the records are dead afterwards -- their registers can take the next edge's loads
+//   aniso_point   one Gauss point: the Gram-Schmidt quadratic form (numerator, denominator)
+//   aniso_finish  the two square roots together
+// aniso_fence makes the second point wait for the first in the instruction stream: ptxas would otherwise interleave the two
+// points (twice the live values: 189 registers in the stream kernel against 128 with the fence).
 struct AnisoPre { double d[3], cp[9], cm[9]; };
 __device__ __forceinline__ void aniso_pre(const double* __restrict__ a, const double* __restrict__ b, AnisoPre& p)
 {
@@ -115,18 +118,25 @@ __device__ __forceinline__ void aniso_pre(const double* __restrict__ a, const do
     p.cm[i] = fma(kNP0, dl, a[3 + i]);   // xi = -XI: weights (kNP1, kNP0)
   }
 }
-__device__ __forceinline__ double aniso_post(const AnisoPre& p)
+// which = 0: the point xi = +XI, 1: xi = -XI
+__device__ __forceinline__ void aniso_point(const AnisoPre& p, int which, double& num, double& den)
 {
-  double np, dp, nm, dm;
-  aniso_point_nd(p.cp, p.d[0], p.d[1], p.d[2], np, dp);
-  aniso_point_nd(p.cm, p.d[0], p.d[1], p.d[2], nm, dm);
-  return half_sum_sqrt_ratios(np, dp, nm, dm);
+  aniso_point_nd(which ? p.cm : p.cp, p.d[0], p.d[1], p.d[2], num, den);
+}
+__device__ __forceinline__ void aniso_fence(AnisoPre& p, double num, double den)
+{
+  asm volatile("" : "+d"(p.cm[0]), "+d"(p.cm[1]), "+d"(p.cm[2]), "+d"(p.cm[3]), "+d"(p.cm[4]), "+d"(p.cm[5]), "+d"(p.cm[6]), "+d"(p.cm[7]),
+                    "+d"(p.cm[8]), "+d"(p.d[0]), "+d"(p.d[1]), "+d"(p.d[2])
+               : "d"(num), "d"(den));
 }
 __device__ __forceinline__ double edge_aniso(const double* __restrict__ a, const double* __restrict__ b)
 {
   AnisoPre p;
   aniso_pre(a, b, p);
-  return aniso_post(p);
+  double np, dp, nm, dm;
+  aniso_point(p, 0, np, dp);
+  aniso_point(p, 1, nm, dm);
+  return half_sum_sqrt_ratios(np, dp, nm, dm);
 }
 
 // log-Euclidean field.  The length at a Gauss point is sqrt(sum_k exp(lambda_k) (v_k . j)^2), j = (x1 - x0) / 2, with
