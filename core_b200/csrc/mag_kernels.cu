@@ -1637,13 +1637,16 @@ static int launch_edge_rows_z(mag_ctx* c, const SweepParams& P)
 template <int KIND>
 static int launch_tet_rows_z(mag_ctx* c, const SweepParams& P)
 {
-  constexpr int T = MAG_TZ_THREADS;
-  const int per_sm = blocks_per_sm(c, (const void*)k_tet_rows_z<KIND>, T);
+  constexpr int T = TetLeanCfg<KIND>::T;
+  constexpr size_t kSmem = TetLeanCfg<KIND>::kSmem;
+  if (c->occupancy.find((const void*)k_tet_rows_z<KIND>) == c->occupancy.end())
+    MAG_CUDA(c, cudaFuncSetAttribute(k_tet_rows_z<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+  const int per_sm = blocks_per_sm(c, (const void*)k_tet_rows_z<KIND>, T, kSmem);
   int64_t g = (int64_t)per_sm * c->n_sms;
   const int64_t groups = (c->trows.n_slices + kTZGroup - 1) / kTZGroup;
   const int64_t need = (groups + T / 32 - 1) / (T / 32);
   if (g > need) g = need;
-  k_tet_rows_z<KIND><<<(unsigned)(g < 1 ? 1 : g), T, 0, c->stream>>>(
+  k_tet_rows_z<KIND><<<(unsigned)(g < 1 ? 1 : g), T, kSmem, c->stream>>>(
       (int32_t)c->trows.n_slices, c->trows.d_anchor, c->trows.d_slice_off, reinterpret_cast<const int4*>(c->trows.d_slots),
       (int32_t)(c->np + c->npy), c->nv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_flags, c->d_qual, tet_params(P, true),
       c->d_stats, c->d_near_elem);
