@@ -1269,12 +1269,12 @@ static int launch_tris(mag_ctx* c, const SweepParams& P, bool fast)
 }
 
 // persistent grids: resident blocks per SM x number of SMs (queried once per context)
-static int blocks_per_sm(mag_ctx* c, const void* kernel, int threads, size_t dyn_smem = 0)
+static int blocks_per_sm(mag_ctx* c, const void* kernel, int threads)
 {
   auto it = c->occupancy.find(kernel);
   if (it != c->occupancy.end()) return it->second;
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
   c->occupancy[kernel] = per_sm;
   return per_sm;
 }
@@ -1619,15 +1619,12 @@ template <int KIND>
 static int launch_edge_rows_z(mag_ctx* c, const SweepParams& P)
 {
   constexpr int T = EdgeLeanCfg<KIND>::T;
-  constexpr size_t kSmem = EdgeLeanCfg<KIND>::kSmem;
-  if (c->occupancy.find((const void*)k_edge_rows_z<KIND>) == c->occupancy.end())
-    MAG_CUDA(c, cudaFuncSetAttribute(k_edge_rows_z<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
-  const int per_sm = blocks_per_sm(c, (const void*)k_edge_rows_z<KIND>, T, kSmem);
+  const int per_sm = blocks_per_sm(c, (const void*)k_edge_rows_z<KIND>, T);
   int64_t g = (int64_t)per_sm * c->n_sms;
   const int64_t groups = (c->erows.n_slices + kEZGroup - 1) / kEZGroup;
   const int64_t need = (groups + T / 32 - 1) / (T / 32);
   if (g > need) g = need;
-  k_edge_rows_z<KIND><<<(unsigned)(g < 1 ? 1 : g), T, kSmem, c->stream>>>(
+  k_edge_rows_z<KIND><<<(unsigned)(g < 1 ? 1 : g), T, 0, c->stream>>>(
       (int32_t)c->erows.n_slices, c->erows.d_anchor, c->erows.d_slice_off, reinterpret_cast<const int2*>(c->erows.d_slots), c->d_vedge,
       c->d_edge_flags, c->d_len, edge_params(P, true), c->d_stats, c->d_near_edge);
   MAG_CUDA(c, cudaGetLastError());
@@ -1637,16 +1634,13 @@ static int launch_edge_rows_z(mag_ctx* c, const SweepParams& P)
 template <int KIND>
 static int launch_tet_rows_z(mag_ctx* c, const SweepParams& P)
 {
-  constexpr int T = TetLeanCfg<KIND>::T;
-  constexpr size_t kSmem = TetLeanCfg<KIND>::kSmem;
-  if (c->occupancy.find((const void*)k_tet_rows_z<KIND>) == c->occupancy.end())
-    MAG_CUDA(c, cudaFuncSetAttribute(k_tet_rows_z<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
-  const int per_sm = blocks_per_sm(c, (const void*)k_tet_rows_z<KIND>, T, kSmem);
+  constexpr int T = MAG_TZ_THREADS;
+  const int per_sm = blocks_per_sm(c, (const void*)k_tet_rows_z<KIND>, T);
   int64_t g = (int64_t)per_sm * c->n_sms;
   const int64_t groups = (c->trows.n_slices + kTZGroup - 1) / kTZGroup;
   const int64_t need = (groups + T / 32 - 1) / (T / 32);
   if (g > need) g = need;
-  k_tet_rows_z<KIND><<<(unsigned)(g < 1 ? 1 : g), T, kSmem, c->stream>>>(
+  k_tet_rows_z<KIND><<<(unsigned)(g < 1 ? 1 : g), T, 0, c->stream>>>(
       (int32_t)c->trows.n_slices, c->trows.d_anchor, c->trows.d_slice_off, reinterpret_cast<const int4*>(c->trows.d_slots),
       (int32_t)(c->np + c->npy), c->nv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_flags, c->d_qual, tet_params(P, true),
       c->d_stats, c->d_near_elem);

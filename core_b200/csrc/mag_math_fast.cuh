@@ -100,42 +100,21 @@ __device__ __forceinline__ double half_sum_sqrt_ratios(double np, double dp, dou
   return __dmul_rn(0.5, __dadd_rn(sp, sm));
 }
 
-// An edge evaluation in phases, so that a kernel can put memory traffic between them:
-//   aniso_pre     consumes the two vertex records: d = x1 - x0 and both Gauss points' interpolated values c = a + t (b - a)
-//                 (21 numbers); the records are dead afterwards -- their registers can take the next edge's loads
-//   aniso_point   one Gauss point: the Gram-Schmidt quadratic form (numerator, denominator)
-//   aniso_finish  the two square roots together
-// aniso_fence makes the second point wait for the first in the instruction stream: ptxas would otherwise interleave the two
-// points (twice the live values: 189 registers in the stream kernel against 128 with the fence).
-struct AnisoPre { double d[3], cp[9], cm[9]; };
-__device__ __forceinline__ void aniso_pre(const double* __restrict__ a, const double* __restrict__ b, AnisoPre& p)
+// The records are consumed first -- both Gauss points' interpolated values c = a + t (b - a) -- so a and b are dead
+// before the long part starts (the kernels keep other records in flight meanwhile: registers)
+__device__ __forceinline__ double edge_aniso(const double* __restrict__ a, const double* __restrict__ b)
 {
-  p.d[0] = b[0] - a[0]; p.d[1] = b[1] - a[1]; p.d[2] = b[2] - a[2];   // 2d; the 1/2 is applied at the end
+  const double dx = b[0] - a[0], dy = b[1] - a[1], dz = b[2] - a[2]; // 2d; the 1/2 is applied at the end
+  double cp[9], cm[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) {
     const double dl = b[3 + i] - a[3 + i];
-    p.cp[i] = fma(kNP1, dl, a[3 + i]);   // xi = +XI: weights (kNP0, kNP1)
-    p.cm[i] = fma(kNP0, dl, a[3 + i]);   // xi = -XI: weights (kNP1, kNP0)
+    cp[i] = fma(kNP1, dl, a[3 + i]);   // xi = +XI: weights (kNP0, kNP1)
+    cm[i] = fma(kNP0, dl, a[3 + i]);   // xi = -XI: weights (kNP1, kNP0)
   }
-}
-// which = 0: the point xi = +XI, 1: xi = -XI
-__device__ __forceinline__ void aniso_point(const AnisoPre& p, int which, double& num, double& den)
-{
-  aniso_point_nd(which ? p.cm : p.cp, p.d[0], p.d[1], p.d[2], num, den);
-}
-__device__ __forceinline__ void aniso_fence(AnisoPre& p, double num, double den)
-{
-  asm volatile("" : "+d"(p.cm[0]), "+d"(p.cm[1]), "+d"(p.cm[2]), "+d"(p.cm[3]), "+d"(p.cm[4]), "+d"(p.cm[5]), "+d"(p.cm[6]), "+d"(p.cm[7]),
-                    "+d"(p.cm[8]), "+d"(p.d[0]), "+d"(p.d[1]), "+d"(p.d[2])
-               : "d"(num), "d"(den));
-}
-__device__ __forceinline__ double edge_aniso(const double* __restrict__ a, const double* __restrict__ b)
-{
-  AnisoPre p;
-  aniso_pre(a, b, p);
   double np, dp, nm, dm;
-  aniso_point(p, 0, np, dp);
-  aniso_point(p, 1, nm, dm);
+  aniso_point_nd(cp, dx, dy, dz, np, dp);
+  aniso_point_nd(cm, dx, dy, dz, nm, dm);
   return half_sum_sqrt_ratios(np, dp, nm, dm);
 }
 

@@ -26,8 +26,7 @@
 // lean kernels of mag_lean.cuh serve the full marking sweep, the tile kernels everything else.
 #pragma once
 
-constexpr int kRowMax = 8;           // longest row; an anchor with more entities gets several rows.  Eight slot words per lane
-                                     // is what the stream kernels stage per slice in shared memory (box meshes: 7 edges, 6 tets)
+constexpr int kRowMax = 32;          // longest row; an anchor with more entities gets several rows
 constexpr int kRowWindowLog2 = 11;   // rows are sorted by length inside windows of 2048 vertices
 
 #ifndef MAG_EROW_BLOCKS_LOGM
