@@ -20,7 +20,7 @@ SYMBOLS = [
     "mag_get_near_threshold", "mag_set_metric_logm_from_frames",
     "mag_timing_begin", "mag_timing_read", "mag_launch_count", "mag_get_row_layout",
     "mag_comm_unique_id", "mag_comm_init", "mag_set_edge_links", "mag_reconcile_edge_flags",
-    "mag_sync_edge_flags", "mag_check_edge_flag_consistency", "mag_allreduce_stats",
+    "mag_sync_edge_flags", "mag_sweep_reconciled", "mag_check_edge_flag_consistency", "mag_allreduce_stats",
 ]
 
 
@@ -90,6 +90,7 @@ def lib():
     L.mag_clear_flag.argtypes = [vp, C.c_int, i32]
     L.mag_reset_layer.argtypes = [vp, vp, C.POINTER(i64)]
     L.mag_sweep.argtypes = [vp, u32, f64, f64, f64, C.c_int, C.c_int]
+    L.mag_sweep_reconciled.argtypes = [vp, u32, f64, f64, f64, C.c_int, C.c_int, i32]
     L.mag_sweep_host.argtypes = [vp, C.POINTER(MagHostPart), C.POINTER(MagHostResult), u32, f64, f64, f64, C.c_int, C.c_int,
                                  C.POINTER(MagStats)]
     L.mag_resweep_host.argtypes = [vp, C.POINTER(MagHostUpdate), C.POINTER(MagHostMarks), u32, f64, f64, f64, C.c_int, C.c_int,

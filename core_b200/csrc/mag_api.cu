@@ -158,6 +158,7 @@ int mag_create(mag_ctx** out, int device)
   { const char* e = getenv("MAG_LEGACY_SWEEP"); c->legacy_sweep = e && e[0] == '1'; }
   { const char* e = getenv("MAG_LEAN_SWEEP"); c->lean_sweep = !(e && e[0] == '0'); }
   c->d_vstat = nullptr;
+  c->s_comm = nullptr; c->ev_comm[0] = c->ev_comm[1] = nullptr; c->comm_pending = false; c->overlap_mask = 0;
   c->d_edge_bytes = c->d_elem_bytes = nullptr;
   c->d_pair_keys = nullptr; c->d_pair_vals = nullptr; c->pair_bits = 0; c->d_layer_count = nullptr;
   c->d_near_edge = c->d_near_elem = nullptr;
@@ -399,6 +400,20 @@ int mag_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double g
   c->last_ops = ops;
   c->last_fp_mode = fp_mode;
   return magk_sweep(c, ops, max_len, min_len, good_quality, use_max_metric, fp_mode);
+}
+
+/* mag_sweep followed by mag_reconcile_edge_flags(flag_mask), with the exchange of the part-boundary edge words overlapped with
+   the element sweep: it starts on a side stream when the edge kernel has finished and the compute stream waits for it at the
+   end.  Same results as the two calls in sequence. */
+int mag_sweep_reconciled(mag_ctx* c, uint32_t ops, double max_len, double min_len, double good_quality, int use_max_metric, int fp_mode,
+                         int32_t flag_mask)
+{
+  CHECK_CTX(c);
+  c->overlap_mask = flag_mask;
+  int rc = mag_sweep(c, ops, max_len, min_len, good_quality, use_max_metric, fp_mode);
+  c->overlap_mask = 0;
+  int rc2 = magc_overlap_end(c);
+  return rc ? rc : rc2;
 }
 
 int mag_get_edge_lengths(mag_ctx* c, double* out)

@@ -76,24 +76,24 @@ __global__ void k_merge_flags(int64_t n, const int32_t* __restrict__ idx, const 
   }
 }
 
-int exchange(mag_ctx* c, int32_t mask, int mode)
+int exchange(mag_ctx* c, int32_t mask, int mode, cudaStream_t stream)
 {
   if (c->links.empty()) return MAG_OK;
   if (!c->nccl_comm) return mag_fail(c, MAG_ERR_ARG, "flag exchange: call mag_comm_init first");
   ncclComm_t comm = (ncclComm_t)c->nccl_comm;
   { int rc = magi_materialize_flags(c); if (rc) return rc; }
   for (auto& L : c->links)
-    if (L.n) k_gather_flags<<<(unsigned)((L.n + 255) / 256), 256, 0, c->stream>>>(L.n, L.d_idx, c->d_edge_flags, mask, L.d_send);
+    if (L.n) k_gather_flags<<<(unsigned)((L.n + 255) / 256), 256, 0, stream>>>(L.n, L.d_idx, c->d_edge_flags, mask, L.d_send);
   MAG_CUDA(c, cudaGetLastError());
   MAG_NCCL(c, g_nccl.GroupStart());
   for (auto& L : c->links) {
     if (!L.n) continue;
-    MAG_NCCL(c, g_nccl.Send(L.d_send, (size_t)L.n, ncclInt32, L.peer, comm, c->stream));
-    MAG_NCCL(c, g_nccl.Recv(L.d_recv, (size_t)L.n, ncclInt32, L.peer, comm, c->stream));
+    MAG_NCCL(c, g_nccl.Send(L.d_send, (size_t)L.n, ncclInt32, L.peer, comm, stream));
+    MAG_NCCL(c, g_nccl.Recv(L.d_recv, (size_t)L.n, ncclInt32, L.peer, comm, stream));
   }
   MAG_NCCL(c, g_nccl.GroupEnd());
   for (auto& L : c->links)
-    if (L.n) k_merge_flags<<<(unsigned)((L.n + 255) / 256), 256, 0, c->stream>>>(L.n, L.d_idx, L.d_recv, L.d_peer_owns, mask, mode, c->d_edge_flags, c->d_stats);
+    if (L.n) k_merge_flags<<<(unsigned)((L.n + 255) / 256), 256, 0, stream>>>(L.n, L.d_idx, L.d_recv, L.d_peer_owns, mask, mode, c->d_edge_flags, c->d_stats);
   MAG_CUDA(c, cudaGetLastError());
   return MAG_OK;
 }
@@ -106,8 +106,38 @@ void free_links(mag_ctx* c)
 
 } // namespace
 
+// The part-boundary exchange of the edge marks, started on a side stream as soon as the edge kernel has finished, so that it
+// runs under the element kernel (an edge's marks are final once the edge sweep ends).  magc_overlap_end makes the compute
+// stream wait for it.  Measured at N = 2 (bench.py multi_part_overhead): 0.13 ms when it runs after the sweep.
+int magc_overlap_begin(mag_ctx* c, int32_t mask)
+{
+  if (c->links.empty() || !c->nccl_comm) return MAG_OK;
+  if (!c->s_comm) MAG_CUDA(c, cudaStreamCreateWithFlags(&c->s_comm, cudaStreamNonBlocking));
+  if (!c->ev_comm[0]) {
+    MAG_CUDA(c, cudaEventCreateWithFlags(&c->ev_comm[0], cudaEventDisableTiming));
+    MAG_CUDA(c, cudaEventCreateWithFlags(&c->ev_comm[1], cudaEventDisableTiming));
+  }
+  { int rc = magi_materialize_flags(c); if (rc) return rc; }   // on the compute stream, before the hand-over
+  MAG_CUDA(c, cudaEventRecord(c->ev_comm[0], c->stream));
+  MAG_CUDA(c, cudaStreamWaitEvent(c->s_comm, c->ev_comm[0], 0));
+  int rc = exchange(c, mask, 0, c->s_comm);
+  if (rc) return rc;
+  MAG_CUDA(c, cudaEventRecord(c->ev_comm[1], c->s_comm));
+  c->comm_pending = true;
+  return MAG_OK;
+}
+int magc_overlap_end(mag_ctx* c)
+{
+  if (!c->comm_pending) return MAG_OK;
+  c->comm_pending = false;
+  MAG_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_comm[1], 0));
+  return MAG_OK;
+}
+
 void magc_destroy(mag_ctx* c)
 {
+  if (c->s_comm) { cudaStreamSynchronize(c->s_comm); cudaStreamDestroy(c->s_comm); c->s_comm = nullptr; }
+  for (int i = 0; i < 2; ++i) if (c->ev_comm[i]) { cudaEventDestroy(c->ev_comm[i]); c->ev_comm[i] = nullptr; }
   free_links(c);
   cudaFree(c->d_gather); c->d_gather = nullptr;
   cudaFreeHost(c->h_gather); c->h_gather = nullptr;
@@ -198,7 +228,7 @@ int mag_reconcile_edge_flags(mag_ctx* c, int32_t flag_mask)
 {
   if (!c) return MAG_ERR_ARG;
   MAG_CUDA(c, cudaSetDevice(c->device));
-  return exchange(c, flag_mask, 0);
+  return exchange(c, flag_mask, 0, c->stream);
 }
 /* ma::checkFlagConsistency (maAdapt.cc:226-256): the reference asserts that every copy of a shared edge carries the same
    bits; here the copies are compared (nothing is repaired) and a disagreement is MAG_ERR_INCONSISTENT */
@@ -208,7 +238,7 @@ int mag_check_edge_flag_consistency(mag_ctx* c, int32_t flag_mask, int64_t* n_mi
   MAG_CUDA(c, cudaSetDevice(c->device));
   unsigned long long before = 0, after = 0;
   MAG_CUDA(c, cudaMemcpyAsync(&before, &c->d_stats->n_flag_mismatch, sizeof(before), cudaMemcpyDeviceToHost, c->stream));
-  int rc = exchange(c, flag_mask, 2);
+  int rc = exchange(c, flag_mask, 2, c->stream);
   if (rc) return rc;
   MAG_CUDA(c, cudaMemcpyAsync(&after, &c->d_stats->n_flag_mismatch, sizeof(after), cudaMemcpyDeviceToHost, c->stream));
   MAG_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -221,7 +251,7 @@ int mag_sync_edge_flags(mag_ctx* c, int32_t flag_mask)
 {
   if (!c) return MAG_ERR_ARG;
   MAG_CUDA(c, cudaSetDevice(c->device));
-  return exchange(c, flag_mask, 1);
+  return exchange(c, flag_mask, 1, c->stream);
 }
 
 int mag_allreduce_stats(mag_ctx* c, mag_stats* global)

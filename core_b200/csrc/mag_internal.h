@@ -133,6 +133,10 @@ struct mag_ctx {
   std::vector<cudaEvent_t> pipe_ev;
 
   // multi-GPU
+  cudaStream_t s_comm;       // side stream of the overlapped flag exchange (mag_sweep_reconciled)
+  cudaEvent_t ev_comm[2];
+  bool comm_pending;
+  int32_t overlap_mask;      // != 0 while mag_sweep_reconciled runs: magk_sweep starts the exchange right after the edge kernel
   void* nccl_comm;
   int nranks, rank;
   std::vector<MagLinks> links;
@@ -148,6 +152,8 @@ int magi_materialize_flags(mag_ctx* c);
 int magi_reserve_metric(mag_ctx* c, int kind, size_t na, size_t nb);
 }
 void magl_free_pairs(mag_ctx* c);
+int magc_overlap_begin(mag_ctx* c, int32_t mask);
+int magc_overlap_end(mag_ctx* c);
 int mag_stats_from_dev(mag_ctx* c, const MagDevStats& s, mag_stats* out);
 #define MAG_CUDA(c, call)                                                                      \
   do {                                                                                         \

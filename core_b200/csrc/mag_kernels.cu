@@ -1685,6 +1685,8 @@ int magk_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double 
     if ((ops & MAG_OP_LENGTH_SUM) && (rc = magk_length_sum(c))) return rc;
   }
   if (tev) MAG_CUDA(c, cudaEventRecord(tev[2], c->stream));
+  // mag_sweep_reconciled: the edge marks are final; their part-boundary exchange runs under the element kernels
+  if (c->overlap_mask && (rc = magc_overlap_begin(c, c->overlap_mask))) return rc;
   if (ops & (MAG_OP_QUALITIES | MAG_OP_MARK_BAD)) {
     // only the tet kernel understands "all zero, not materialised" (it then writes every word it marks)
     if ((c->ntri || c->np + c->npy) && (rc = magi_materialize_flags(c))) return rc;

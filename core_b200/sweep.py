@@ -186,9 +186,15 @@ class Part:
 
     # ---- sweep + results
     def sweep(self, ops=OP_ALL, max_len=MAXLENGTH, min_len=MINLENGTH, good_quality=GOOD_QUALITY_3D,
-              use_max=True, fp_mode=FP_STRICT):
-        self._ck(self._L.mag_sweep(self._h, int(ops), float(max_len), float(min_len), float(good_quality),
-                                   int(bool(use_max)), int(fp_mode)))
+              use_max=True, fp_mode=FP_STRICT, reconcile_mask=None):
+        """mag_sweep; with reconcile_mask: mag_sweep_reconciled (the part-boundary exchange of those edge bits runs under the
+        element sweep)."""
+        if reconcile_mask is None:
+            self._ck(self._L.mag_sweep(self._h, int(ops), float(max_len), float(min_len), float(good_quality),
+                                       int(bool(use_max)), int(fp_mode)))
+        else:
+            self._ck(self._L.mag_sweep_reconciled(self._h, int(ops), float(max_len), float(min_len), float(good_quality),
+                                                  int(bool(use_max)), int(fp_mode), int(reconcile_mask)))
 
     def sweep_host(self, xyz, edge_v, tet_v, kind, field_a=None, field_b=None, edge_flags=None, elem_flags=None,
                    edge_owned=None, elem_owned=None, out_lengths=None, out_qualities=None, out_edge_flags=None,

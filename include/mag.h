@@ -325,6 +325,11 @@ int mag_set_edge_links(mag_ctx* c, int npeers, const int32_t* peer, const int64_
    disagreeing copies goes to mag_stats.n_flag_mismatch (the reference asserts it is 0) and, where peer_owns says so, the
    owner's bits overwrite the local ones. */
 int mag_reconcile_edge_flags(mag_ctx* c, int32_t flag_mask);
+/* mag_sweep + mag_reconcile_edge_flags(flag_mask) in one call, the exchange overlapped with the element sweep (an edge's marks are
+   final when the edge sweep ends: the exchange starts there, on a side stream, and is waited for at the end).  Same results as
+   the two calls in sequence; without links or communicator it is mag_sweep. */
+int mag_sweep_reconciled(mag_ctx* c, uint32_t ops, double max_len, double min_len, double good_quality, int use_max_metric, int fp_mode,
+                         int32_t flag_mask);
 /* ma::checkFlagConsistency as the reference uses it (maRefine.cc:430, maCoarsen.cc:305): copies are compared, nothing is
    repaired; any disagreement -> MAG_ERR_INCONSISTENT (the reference asserts).  *n_mismatch (may be NULL) = disagreeing local
    copies.  Synchronous. */

@@ -53,6 +53,15 @@ def main():
     assert (g["n_split"], g["n_collapse"], g["n_bad"]) == (s["n_split"], s["n_collapse"], s["n_bad"]), (g, s["n_split"])
     assert g["min_quality"] == s["min_quality"] and g["max_length"] == s["max_length"]
     ef_ok, lf = p.flags()
+    # 1b. the same through mag_sweep_reconciled (exchange overlapped with the element sweep), both arithmetic modes
+    for mode in (cb.FP_STRICT, cb.FP_FAST):
+        p.clear_flags()
+        p.sweep(cb.OP_ALL & ~cb.OP_LAYER_CHECK, fp_mode=mode, reconcile_mask=mask)
+        g2 = p.allreduce_stats()
+        ef_b, lf_b = p.flags()
+        assert np.array_equal(ef_b, ef_ok) and np.array_equal(lf_b, lf)
+        for key in ("n_split", "n_collapse", "n_bad", "n_flag_mismatch"):
+            assert g2[key] == g[key], key
     # 2. the non-owner's copies flip SPLIT: counted on both sides, owner wins
     ef = ef_ok.copy()
     flipped = 0
