@@ -20,6 +20,7 @@ SYMBOLS = [
     "mag_get_near_threshold", "mag_set_metric_logm_from_frames",
     "mag_timing_begin", "mag_timing_read", "mag_launch_count", "mag_get_row_layout",
     "mag_comm_unique_id", "mag_comm_init", "mag_set_edge_links", "mag_reconcile_edge_flags",
+    "mag_smb_read", "mag_smb_free", "mag_smb_last_error", "mag_smb_get", "mag_smb_vertex_field", "mag_set_mesh_smb",
     "mag_sync_edge_flags", "mag_sweep_reconciled", "mag_check_edge_flag_consistency", "mag_allreduce_stats",
 ]
 
@@ -51,6 +52,13 @@ class MagHostUpdate(C.Structure):
 
 class MagHostMarks(C.Structure):
     _fields_ = [("edge_marks", C.c_void_p), ("elem_marks", C.c_void_p), ("edge_lengths", C.c_void_p), ("qualities", C.c_void_p)]
+
+
+class MagSmbArrays(C.Structure):
+    """mag_smb_arrays of include/mag.h"""
+    _fields_ = [("dim", C.c_int), ("version", C.c_int), ("nparts", C.c_int)] + \
+               [(k, C.c_int64) for k in ("nv", "ne", "ntri", "nquad", "nt", "np", "npy", "nhex")] + \
+               [(k, C.c_void_p) for k in ("xyz", "edge_v", "tri_v", "tet_v", "prism_v", "pyr_v")]
 
 
 class MagHostResult(C.Structure):
@@ -120,6 +128,14 @@ def lib():
     L.mag_set_edge_links.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     L.mag_reconcile_edge_flags.argtypes = [vp, i32]
     L.mag_sync_edge_flags.argtypes = [vp, i32]
+    L.mag_smb_read.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.mag_smb_free.argtypes = [vp]
+    L.mag_smb_free.restype = None
+    L.mag_smb_last_error.argtypes = [vp]
+    L.mag_smb_last_error.restype = C.c_char_p
+    L.mag_smb_get.argtypes = [vp, C.POINTER(MagSmbArrays)]
+    L.mag_smb_vertex_field.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int), C.POINTER(vp)]
+    L.mag_set_mesh_smb.argtypes = [vp, vp]
     L.mag_check_edge_flag_consistency.argtypes = [vp, i32, C.POINTER(i64)]
     L.mag_allreduce_stats.argtypes = [vp, C.POINTER(MagStats)]
     _lib = L

@@ -138,3 +138,47 @@ def vertex_field(mesh, name):
     out[ids] = vals
     assert len(ids) == len(out), "tag %s is not set on every vertex" % name
     return out
+
+
+def read_smb_native(path):
+    """The same file through the C reader of the library (mag_smb_read, core_b200/csrc/mag_smb.cu: what the C ABI and the C++
+    adapter use; no device needed).  Returns (dict with the same array keys as read_smb, field getter name -> [nv, c])."""
+    import ctypes as C
+    from ._lib import lib, MagSmbArrays
+    L = lib()
+    h = C.c_void_p()
+    rc = L.mag_smb_read(str(path).encode(), C.byref(h))
+    try:
+        if rc:
+            raise ValueError("mag_smb_read: " + L.mag_smb_last_error(h).decode())
+        a = MagSmbArrays()
+        assert L.mag_smb_get(h, C.byref(a)) == 0
+
+        def arr(ptr, n, k, ctype, dtype):
+            if n == 0:
+                return np.zeros((0, k), dtype)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n * k,)).reshape(n, k).astype(dtype).copy()
+        out = dict(dim=a.dim, version=a.version, nparts=a.nparts,
+                   counts=dict(vertex=a.nv, edge=a.ne, triangle=a.ntri, quad=a.nquad, hex=a.nhex, prism=a.np, pyramid=a.npy, tet=a.nt),
+                   xyz=arr(a.xyz, a.nv, 3, C.c_double, np.float64), edge_v=arr(a.edge_v, a.ne, 2, C.c_int32, np.int32),
+                   tri_v=arr(a.tri_v, a.ntri, 3, C.c_int32, np.int32), tet_v=arr(a.tet_v, a.nt, 4, C.c_int32, np.int32),
+                   prism_v=arr(a.prism_v, a.np, 6, C.c_int32, np.int32), pyr_v=arr(a.pyr_v, a.npy, 5, C.c_int32, np.int32))
+        fields = {}
+
+        def field(name):
+            if name not in fields:
+                comps, ptr = C.c_int(0), C.c_void_p()
+                if L.mag_smb_vertex_field(h, name.encode(), C.byref(comps), C.byref(ptr)):
+                    raise KeyError(L.mag_smb_last_error(h).decode())
+                fields[name] = arr(ptr, a.nv, comps.value, C.c_double, np.float64)
+            return fields[name]
+        out["fields"] = {n: field(n) for n in ("sizes", "frames") if _has_field(L, h, n)}
+        return out
+    finally:
+        L.mag_smb_free(h)
+
+
+def _has_field(L, h, name):
+    import ctypes as C
+    comps, ptr = C.c_int(0), C.c_void_p()
+    return L.mag_smb_vertex_field(h, name.encode(), C.byref(comps), C.byref(ptr)) == 0

@@ -312,6 +312,31 @@ int64_t mag_launch_count(const mag_ctx* c);
    index -1 = empty slot.  Array pointers may be NULL (counts only). */
 int mag_get_row_layout(mag_ctx* c, int which, int64_t* counts, int32_t* anchor, int32_t* slice_off, int32_t* slots);
 
+/* ---- PUMI's native mesh format (.smb, mds/mds_smb.c:120-600) straight into these arrays, without building the mesh database:
+   entity order = m->begin(d) order of the loaded mesh, element vertices as getDownward(e, 0, .) returns them (derived with
+   MDS's own rule, mds/mds.c:496-508,634-670).  Host code: no device is needed to read a file.  SURVEY 8f row 4. ---- */
+typedef struct mag_smb mag_smb;            /* opaque: owns every array it hands out */
+typedef struct mag_smb_arrays {
+  int dim, version, nparts;
+  int64_t nv, ne, ntri, nquad, nt, np, npy, nhex;
+  const double* xyz;                       /* [nv][3] */
+  const int32_t* edge_v;                   /* [ne][2] */
+  const int32_t* tri_v;                    /* [ntri][3] (the elements of a 2-D mesh; the faces of a 3-D one) */
+  const int32_t* tet_v;                    /* [nt][4] */
+  const int32_t* prism_v;                  /* [np][6] */
+  const int32_t* pyr_v;                    /* [npy][5] */
+} mag_smb_arrays;
+/* *out is set also on failure (MAG_ERR_ARG): mag_smb_last_error(*out) says why; free it either way */
+int mag_smb_read(const char* path, mag_smb** out);
+void mag_smb_free(mag_smb* s);
+const char* mag_smb_last_error(const mag_smb* s);
+int mag_smb_get(const mag_smb* s, mag_smb_arrays* out);
+/* dense [nv][components] values of a double-valued vertex tag / field (apf keeps the vertex nodes of field <name> in the tag
+   <name>_ver, apf/apfTagData.cc): what mag_set_metric_* takes */
+int mag_smb_vertex_field(mag_smb* s, const char* name, int* components, const double** values);
+/* mag_set_mesh / mag_set_mesh_2d with the file's arrays (every entity owned) */
+int mag_set_mesh_smb(mag_ctx* c, const mag_smb* s);
+
 /* ---- multi-GPU: one part per GPU, NCCL over NVLink (replaces PCU on this path only) ---- */
 #define MAG_UNIQUE_ID_BYTES 128
 int mag_comm_unique_id(void* out_id /*[MAG_UNIQUE_ID_BYTES]*/);
