@@ -52,6 +52,8 @@ struct EdgeLinks {
    part's id (m->getPCU()->Self()). */
 void buildEdgeLinks(apf::Sharing* sh, int self, const std::vector<ma::Entity*>& edges, EdgeLinks& out);
 
+int exportSelfCheck(ma::Mesh* m, apf::Field* sizes, apf::Field* frames, ma::Tag* flags, int threads, double* times);
+
 class GpuSizeField : public ma::SizeField
 {
   public:
@@ -95,6 +97,7 @@ class GpuSizeField : public ma::SizeField
 
   private:
     friend struct Access;
+    friend int exportSelfCheck(ma::Mesh* m, apf::Field* sizes, apf::Field* frames, ma::Tag* flags, int threads, double* times);
     GpuSizeField();
     enum { kSweepDetect = 4096 };
     int kind;        /* 1 iso, 2 aniso, 3 logm */
@@ -116,6 +119,7 @@ class GpuSizeField : public ma::SizeField
     std::vector<int> vertSlot;                    /* MDS index of a vertex -> exported vertex id */
     std::vector<double> lengths, qualities;       /* host copies of the last sweep */
     std::vector<int> edgeFlags, elemFlags;        /* flags of the last sweep run on zero incoming words */
+    std::vector<int> flagScratch[4];              /* flag words in transit of the bulk marks (buffers kept between sweeps) */
     long nNonSimplex;
     int lastDim, lastId;  /* last per-entity query: dimension and MDS index */
   apf::Sharing* userSharing;   /* not owned */
@@ -150,6 +154,20 @@ ma::Tag* getElementWeights(ma::Adapt* a);
    the i-th element of m->begin(3) (layer elements: 0 and {-1,-1}).  The first face of every tet is exported in the face
    entity's own vertex order, which is what the reference's measureTriQuality walks. */
 void getSliverCodes(ma::Adapt* a, std::vector<int>& codes, std::vector<ma::CodeMatch>& matches);
+
+/* Exports read MDS's own arrays (struct mds / mds_apf / mds_tag) when the mesh is an MDS mesh -- see magAdapt.cc, "the direct
+   export route"; off = every entity through apf::Mesh2's public interface, as in round 1.  Process-wide; the environment
+   variable MAG_ADAPTER_PUBLIC_API_ONLY also switches it off. */
+void setDirectMds(bool on);
+/* where the host time of the bulk sweeps went since the last reset (seconds, process-wide): the MDS export, the re-validation
+   of the vertices of a kept export, uploads (mesh / coordinates / field), reading the incoming flag words, the device calls
+   of a sweep (flags up, sweep, statistics, flags down), writing changed flag words back, a snapshot refresh (sweep + downloads) */
+struct Profile { double export_s, revalidate_s, upload_s, flags_in_s, device_s, flags_out_s, refresh_s; };
+Profile& profile();
+/* Test hook, host only (no device is touched): exports m through both routes (Aniso field from sizes + frames) and compares every
+   array, the slot tables, the change detection of moved vertices / edited field values and -- flags != NULL -- the direct read of
+   an int tag.  Returns a bit mask of what differed (0 = identical); times[0] / times[1] = seconds of the public / direct export. */
+int exportSelfCheck(ma::Mesh* m, apf::Field* sizes, apf::Field* frames, ma::Tag* flags, int threads, double* times);
 
 /* ma::ShapeHandlerFunction: in->shapeHandler = mag::shapeHandler; getQuality(e) is then served from the device sweep */
 ma::ShapeHandler* shapeHandler(ma::Adapt* a);

@@ -55,7 +55,8 @@ void ensure_pcu()
 /* wall-clock seconds of the last check: [0] the reference's five sweeps (split, collapse, bad, min quality, max length),
    [1] the adapter's bulk entry points for the same five (each one exports the mesh from MDS, uploads, sweeps, writes the
    flag words back), [2] the unmodified reference loops served through the adapter */
-double g_times[3] = {0, 0, 0};
+double g_times[4] = {0, 0, 0, 0};   /* [3]: the bulk entry points again, warm (see adapter_check) */
+mag::Profile g_profile[2];
 int g_export_threads = 1;
 int g_adapt_dim = 3;         /* mag_adapter_set_adapt_dim: 3 = n^3 box of tets, 2 = n^2 box of triangles, 4 = unit ball on an
                                 analytic sphere model (vertices created on the boundary are SNAPPED: ma/ma.cc:37) */
@@ -184,9 +185,20 @@ static void jitter_mesh(apf::Mesh2* m, int n, double jitter)
 
 static int adapter_check(int n, int nz, int log_interp, int fp_mode, double jitter, double* report);
 extern "C" void mag_adapter_set_threads(int n) { g_export_threads = n; }
+extern "C" void mag_adapter_set_direct(int on) { mag::setDirectMds(on != 0); }
 extern "C" void mag_adapter_set_adapt_jitter(double j) { g_adapt_jitter = j; }
 extern "C" void mag_adapter_set_adapt_dim(int d) { g_adapt_dim = (d == 2 || d == 4) ? d : 3; }
 extern "C" void mag_adapter_times(double* t) { for (int i = 0; i < 3; ++i) t[i] = g_times[i]; }
+/* t[0]: the warm second round of the bulk sweeps; t[1..7] / t[8..14]: mag::Profile of the first (cold) / second (warm) round */
+extern "C" void mag_adapter_times2(double* t)
+{
+  t[0] = g_times[3];
+  for (int r = 0; r < 2; ++r) {
+    const mag::Profile& p = g_profile[r];
+    const double v[7] = {p.export_s, p.revalidate_s, p.upload_s, p.flags_in_s, p.device_s, p.flags_out_s, p.refresh_s};
+    for (int i = 0; i < 7; ++i) t[1 + 7 * r + i] = v[i];
+  }
+}
 extern "C" int mag_adapter_check(int n, int log_interp, int fp_mode, double jitter, double* report)
 {
   return adapter_check(n, n, log_interp, fp_mode, jitter, report);
@@ -235,12 +247,14 @@ static int adapter_check(int n, int nz, int log_interp, int fp_mode, double jitt
     in->shapeHandler = mag::shapeHandler;
     {
       ma::Adapt a(in);
+      mag::profile() = mag::Profile();
       const double t0 = now_s();
       A.n_split = mag::markEdgesToSplit(&a);
       A.n_collapse = mag::markEdgesToCollapse(&a);
       A.n_bad = mag::markBadQuality(&a);
       A.min_q = mag::getMinQuality(&a);
       g_times[1] = now_s() - t0;
+      g_profile[0] = mag::profile();
       collect_flags(&a, A);
       /* ma::getElementWeights (maBalance.cc:83-97) against the reference's own per-entity loop on the same Adapt */
       a.refinesLeft = 0; a.coarsensLeft = 1;
@@ -275,6 +289,26 @@ static int adapter_check(int n, int nz, int log_interp, int fp_mode, double jitt
       if (log_interp && sliver_diffs * 200 <= nel3) sliver_diffs = 0;   /* CUDA exp() vs glibc exp(): rare borderline bits */
     }
     { const double t0 = now_s(); A.max_len = mag::getMaximumEdgeLength(m, g); g_times[1] += now_s() - t0; }
+    { /* the same five sweeps once more on a fresh Adapt after invalidate(): a full re-export + upload with the context, the
+         buffers and the kernels warm -- what every further MeshAdapt iteration costs */
+      ma::Input* in2 = ma::makeAdvanced(ma::configureIdentity(m, g));
+      {
+        ma::Adapt a2(in2);
+        g->invalidate();
+        mag::Profile& pr = mag::profile();
+        pr = mag::Profile();
+        const double t0 = now_s();
+        long s2 = mag::markEdgesToSplit(&a2);
+        long c2 = mag::markEdgesToCollapse(&a2);
+        int b2 = mag::markBadQuality(&a2);
+        double q2 = mag::getMinQuality(&a2);
+        double l2 = mag::getMaximumEdgeLength(m, g);
+        g_times[3] = now_s() - t0;
+        g_profile[1] = pr;
+        if (s2 != A.n_split || c2 != A.n_collapse || b2 != A.n_bad || q2 != A.min_q || l2 != A.max_len) stats_diffs = -2;
+      }
+      delete in2;
+    }
     { /* ma::stats through the adapter against the reference's vectors */
       std::vector<double> el, lq;
       mag::stats(m, g, el, lq, true);
@@ -414,6 +448,73 @@ extern "C" int mag_adapter_links_check(int nxA, int nxB, int ny, int nz, int par
    which: 1 = reference only (no device), 3 = both.  out[0..2] counts of the reference run (verts, edges, tets), out[3..5] of
    the adapter run, out[6] differing coordinates / connectivity entries, out[7] longest metric edge after the adapter run,
    out[8] device kernel launches made during the adapter run, out[9] / out[10] wall-clock seconds of the two runs. */
+/* ---- the adapter's two export routes (MDS's own arrays against the public apf::Mesh2 walk), host only: no device is touched.
+   kind 0: jittered n^3 box of tets; 1: the same after `iters` iterations of the reference's own ma::adapt (free-list holes, new
+   entities interleaved with old ones); 2: n^2 box of triangles; 3: n^3 cells whose bottom n/3 layers are prisms, Kuhn tets
+   above, plus one detached pyramid.  Returns mag::exportSelfCheck's mask; times[0..1] = seconds public / direct, times[2..4] =
+   vertices, edges, elements exported. */
+extern "C" int mag_adapter_export_check(int n, int kind, int threads, int iters, double* times)
+{
+  ensure_pcu();
+  apf::Mesh2* m;
+  if (kind == 2) m = apf::makeMdsBox(n, n, 0, 1, 1, 0, true, g_pcu);
+  else if (kind == 3) {
+    m = apf::makeEmptyMdsMesh(gmi_load(".null"), 3, false, g_pcu);
+    apf::ModelEntity* region = m->findModelEntity(3, 0);
+    std::vector<apf::MeshEntity*> v((size_t)(n + 1) * (n + 1) * (n + 1));
+    for (int k = 0; k <= n; ++k) for (int j = 0; j <= n; ++j) for (int i = 0; i <= n; ++i)
+      v[(size_t)i + (size_t)(n + 1) * (j + (size_t)(n + 1) * k)] = m->createVertex(region, apf::Vector3((double)i / n, (double)j / n, (double)k / n), apf::Vector3(0, 0, 0));
+    const int layers = n / 3 > 0 ? n / 3 : 1;
+    for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+      apf::MeshEntity* c[8];
+      const int dx[8] = {0, 1, 1, 0, 0, 1, 1, 0}, dy[8] = {0, 0, 1, 1, 0, 0, 1, 1}, dz[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+      for (int q = 0; q < 8; ++q) c[q] = v[(size_t)(i + dx[q]) + (size_t)(n + 1) * ((j + dy[q]) + (size_t)(n + 1) * (k + dz[q]))];
+      if (k < layers) {
+        apf::MeshEntity* p0[6] = {c[0], c[1], c[2], c[4], c[5], c[6]};
+        apf::MeshEntity* p1[6] = {c[0], c[2], c[3], c[4], c[6], c[7]};
+        apf::buildElement(m, region, apf::Mesh::PRISM, p0);
+        apf::buildElement(m, region, apf::Mesh::PRISM, p1);
+      } else {
+        /* six tets around the diagonal 0-6, bottom face cut along 0-2 like the prisms' top face below */
+        const int kuhn[6][4] = {{0, 1, 2, 6}, {0, 2, 3, 6}, {0, 3, 7, 6}, {0, 7, 4, 6}, {0, 4, 5, 6}, {0, 5, 1, 6}};
+        for (int t = 0; t < 6; ++t) {
+          apf::MeshEntity* tv[4] = {c[kuhn[t][0]], c[kuhn[t][1]], c[kuhn[t][2]], c[kuhn[t][3]]};
+          apf::buildElement(m, region, apf::Mesh::TET, tv);
+        }
+      }
+    }
+    apf::MeshEntity* py[5];
+    const double px[5][3] = {{3, 0, 0}, {4, 0, 0}, {4, 1, 0}, {3, 1, 0}, {3.5, 0.5, 1}};
+    for (int q = 0; q < 5; ++q) py[q] = m->createVertex(region, apf::Vector3(px[q][0], px[q][1], px[q][2]), apf::Vector3(0, 0, 0));
+    apf::buildElement(m, region, apf::Mesh::PYRAMID, py);
+    m->acceptChanges();
+  } else m = apf::makeMdsBox(n, n, n, 1, 1, 1, true, g_pcu);
+  if (kind != 3) jitter_mesh(m, n, 0.25);
+  Fields f = make_fields(m, "exp", 1.0 / n);
+  if (kind == 1) {
+    ma::SizeField* sf = ma::makeSizeField(m, f.sizes, f.frames, false);
+    ma::Input* in = ma::makeAdvanced(ma::configureIdentity(m, sf));
+    in->maximumIterations = iters;
+    in->shouldSnap = false;
+    in->shouldTransferParametric = false;
+    ma::adapt(in);
+    /* ~AnisoSizeField would destroy the two fields it was built from (maSize.cc:385-389): keep it alive until the end */
+    static std::vector<ma::SizeField*> keep;
+    keep.push_back(sf);
+  }
+  /* a flag tag with a recognisable word on three quarters of the edges */
+  apf::MeshTag* flags = m->createIntTag("ma_flags", 1);
+  {
+    apf::MeshIterator* it = m->begin(1); apf::MeshEntity* e; int k = 0;
+    while ((e = m->iterate(it))) { if (k & 3) { int w = k * 7 + 1; m->setIntTag(e, flags, &w); } ++k; }
+    m->end(it);
+  }
+  const int bad = mag::exportSelfCheck(m, f.sizes, f.frames, flags, threads, times);
+  times[2] = (double)m->count(0); times[3] = (double)m->count(1); times[4] = (double)m->count(m->getDimension());
+  if (kind != 1) { m->destroyNative(); apf::destroyMesh(m); }   /* kind 1: the kept size field still points at the mesh */
+  return bad;
+}
+
 static int adapt_check(int n, int which, double size_scale, int iterations, int log_interp, int fp_mode, double* out);
 extern "C" int mag_adapter_adapt_check(int n, int which, double size_scale, int iterations, double* out)
 {

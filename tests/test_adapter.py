@@ -128,3 +128,40 @@ def test_edge_links_from_stub_sharing(built):
             assert peer == 1 - part
             assert np.array_equal(idx[:n], want_idx), (gnx, part)
             assert np.array_equal(own[:n], want_own), (gnx, part)
+
+
+@pytest.mark.parametrize("n,kind,threads,iters", [(8, 0, 1, 0), (7, 0, 3, 0), (9, 2, 1, 0), (6, 3, 1, 0), (6, 1, 1, 2), (8, 1, 4, 3)])
+def test_direct_mds_export_equals_public_walk(built, n, kind, threads, iters):
+    """The adapter's direct export (MDS's own arrays: struct mds one-level-down tables, point[][3], tag arrays) against its
+    walk through apf::Mesh2's public interface, host only: every exported array, the entity lists, the slot tables, the
+    change detection (a moved vertex, an edited field value) and the direct read of the ma_flags tag.  kind 0: jittered box of
+    tets; 1: the same after `iters` iterations of the reference's own ma::adapt (free-list holes, new entities between old
+    ones); 2: box of triangles; 3: prisms below Kuhn tets plus a detached pyramid.  No device needed."""
+    if not os.path.exists(LIB):
+        pytest.skip("libmag_ma.so not built (needs the reference headers)")
+    L = C.CDLL(LIB)
+    L.mag_adapter_export_check.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    t = np.zeros(8)
+    mask = L.mag_adapter_export_check(n, kind, threads, iters, t.ctypes.data_as(C.c_void_p))
+    assert mask == 0, "routes differ, mask %#x (1: direct route not taken, 2 vertices, 4 edges, 8 connectivity, 16 elements, 32/1024/2048 slot tables, 64-256 change detection, 512 flag tag)" % mask
+    assert t[2] > 0 and t[3] > 0 and t[4] > 0
+    if kind == 1:
+        assert t[4] > 6 * n ** 3        # the mesh was adapted
+
+
+@pytest.mark.gpu
+def test_adapter_public_api_route(built):
+    """The export route of round 1 (every entity through apf::Mesh2's public interface) still reproduces the reference: what a
+    non-MDS apf::Mesh2 would get."""
+    if not os.path.exists(LIB):
+        pytest.skip("libmag_ma.so not built (needs the reference headers)")
+    L = C.CDLL(LIB)
+    L.mag_adapter_check.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p]
+    L.mag_adapter_set_direct.argtypes = [C.c_int]
+    L.mag_adapter_set_direct(0)
+    try:
+        rep = np.zeros(20)
+        rc = L.mag_adapter_check(12, 0, 0, 0.25, rep.ctypes.data_as(C.c_void_p))
+        assert rc == 0 and np.all(rep[15:19] == 0) and np.array_equal(rep[0:3], rep[5:8])
+    finally:
+        L.mag_adapter_set_direct(1)
