@@ -1016,13 +1016,36 @@ ma::Tag* getElementWeights(ma::Adapt* a)
   const double w_max = pow(2.0, dim * (a->refinesLeft)), w_min = pow(4.0, -(a->coarsensLeft));
   std::vector<double> w(m->count(dim));
   MAG_DO(g->ctx, mag_element_weights(g->ctx, w_max, w_min, Access::fpMode(g), w.data()));
-  ma::Tag* weights = m->createDoubleTag("ma_weight", 1);
-  apf::MeshIterator* it = m->begin(dim);
+  /* layer prisms: weighed by their base triangle (maBalance.cc:31-37), walked in the face's own vertex order; they are the
+     first elements of the export (m->begin(3) order: prisms, pyramids, tets) */
+  std::vector<int> base;
+  apf::MeshIterator* it;
   ma::Entity* e;
+  if (dim == 3) {
+    it = m->begin(3);
+    while ((e = m->iterate(it)) && m->getType(e) == apf::Mesh::PRISM) {
+      apf::Downward fs, fv;
+      m->getDownward(e, 2, fs);
+      m->getDownward(fs[0], 0, fv);
+      for (int i = 0; i < 3; ++i) base.push_back(Access::vertSlotOf(g, fv[i]));
+    }
+    m->end(it);
+  }
+  if (!base.empty())
+    MAG_DO(g->ctx, mag_prism_weights(g->ctx, base.data(), w_max, w_min, a->input->shouldRefineLayer, a->input->shouldCoarsenLayer,
+                                     a->input->shouldTurnLayerToTets, Access::fpMode(g), w.data()));
+  const size_t nprism = base.size() / 3;
+  ma::Tag* weights = m->createDoubleTag("ma_weight", 1);
+  it = m->begin(dim);
+  size_t k = 0;
   while ((e = m->iterate(it))) {
     const int t = m->getType(e);
-    double weight = (t == apf::Mesh::TET || (dim == 2 && t == apf::Mesh::TRIANGLE)) ? w[Access::tetSlotOf(g, e)] : ma::getElementWeight(a, e);
+    double weight;
+    if (t == apf::Mesh::TET || (dim == 2 && t == apf::Mesh::TRIANGLE)) weight = w[Access::tetSlotOf(g, e)];
+    else if (t == apf::Mesh::PRISM && k < nprism) weight = w[k];
+    else weight = ma::getElementWeight(a, e);    /* pyramids: sparse by construction (maBalance.cc:27-29) */
     m->setDoubleTag(e, weights, &weight);
+    ++k;
   }
   m->end(it);
   return weights;

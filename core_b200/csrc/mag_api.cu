@@ -1,6 +1,9 @@
 // mag_api.cu -- the C ABI declared in include/mag.h: context, device memory, uploads, getters.
 // No CPU fallback anywhere: every entry point needs a live CUDA device.
 #include "mag_internal.h"
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -172,6 +175,15 @@ int mag_create(mag_ctx** out, int device)
     return rc;
   };
   if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e, "cudaSetDevice");
+  {
+    // the temporaries and the row layout of every export come from the device's stream-ordered pool (mag_kernels.cu: Scratch);
+    // freed blocks stay in the pool for the next export instead of going back to the driver (MAG_POOL_RELEASE=1: default policy)
+    cudaMemPool_t pool;
+    if (!getenv("MAG_POOL_RELEASE") && cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
   c->stream = c->own_stream;
   if ((e = cudaMalloc((void**)&c->d_stats, sizeof(MagDevStats))) != cudaSuccess) return fail(e, "cudaMalloc stats");
@@ -296,7 +308,19 @@ static int set_mesh_impl(mag_ctx* c, int dim, int64_t nv, const double* xyz, int
     return mag_fail(c, MAG_ERR_ARG, "mag_set_mesh: null array with non-zero count");
   if (nv == 0 && (ne > 0 || nt > 0 || np > 0 || npy > 0 || ntri > 0)) return mag_fail(c, MAG_ERR_ARG, "mag_set_mesh: entities without vertices");
   int rc;
+  // MAG_TRACE=1: wall clock of the stages of an export on stderr (each stage synchronised: diagnosis only)
+  static const bool trace = getenv("MAG_TRACE") != nullptr;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_stage = trace ? now() : 0.0;
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    cudaStreamSynchronize(c->stream);
+    const double t = now();
+    fprintf(stderr, "[mag_set_mesh] %-14s %8.3f ms\n", what, 1e3 * (t - t_stage));
+    t_stage = t;
+  };
   if ((rc = magi_reshape(c, dim, nv, ne, nt, np, npy, ntri, edge_owned != nullptr, elem_owned != nullptr))) return rc;
+  lap("reshape");
   const int64_t nel = np + npy + nt + ntri;
   // a new mesh starts with no flags (ma::getFlags returns 0 when the tag is absent, maAdapt.cc:80-88)
   c->edge_flags_zero = c->elem_flags_zero = true;
@@ -306,6 +330,7 @@ static int set_mesh_impl(mag_ctx* c, int dim, int64_t nv, const double* xyz, int
     return rc;
   if (edge_owned && (rc = upload(c, c->d_edge_owned, edge_owned, (size_t)ne))) return rc;
   if (elem_owned && (rc = upload(c, c->d_elem_owned, elem_owned, (size_t)nel))) return rc;
+  lap("upload");
   // every vertex id must address a vertex: checked on the device before anything gathers through it
   unsigned long long bad = 0;
   if ((rc = magk_conn_begin(c)) || (rc = magk_check_conn(c, c->d_edge_v, ne * 2)) || (rc = magk_check_conn(c, c->d_tet_v, nt * 4)) ||
@@ -317,9 +342,13 @@ static int set_mesh_impl(mag_ctx* c, int dim, int64_t nv, const double* xyz, int
     c->kind = MAG_KIND_NONE;
     return mag_fail(c, MAG_ERR_ARG, "mag_set_mesh: %llu vertex ids outside [0, %lld)", bad, (long long)nv);
   }
+  lap("check_conn");
   if ((rc = magk_fold_owned(c)) || (rc = magk_build_schedule(c))) return rc;
+  lap("schedule+rows");
   c->schedule_valid = true;
-  return repack(c);
+  rc = repack(c);
+  lap("repack");
+  return rc;
 }
 
 int mag_set_mesh(mag_ctx* c, int64_t nv, const double* xyz, int64_t ne, const int32_t* edge_v,

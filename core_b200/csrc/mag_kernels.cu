@@ -1437,13 +1437,19 @@ __global__ void k_iota(int64_t n, int32_t* __restrict__ out)
   if (i < n) out[i] = (int32_t)i;
 }
 // export-time temporaries: freed on every exit path
+// Temporaries of an export, from the device's stream-ordered pool (mag_create keeps freed blocks in the pool instead of
+// returning them to the driver): with plain cudaMalloc / cudaFree the ~25 temporaries of one export cost 35 - 700 ms on a
+// 663 k-tet part (r2o trace), every free being a device-wide synchronisation and an unmap; from the pool the same export is a
+// few milliseconds, every time.
 struct Scratch {
+  cudaStream_t stream;
   std::vector<void*> ptrs;
-  ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+  explicit Scratch(cudaStream_t s) : stream(s) {}
+  ~Scratch() { for (void* p : ptrs) cudaFreeAsync(p, stream); }
   template <class T> cudaError_t get(T*& p, size_t count)
   {
     p = nullptr;
-    cudaError_t e = cudaMalloc((void**)&p, (count ? count : 1) * sizeof(T));
+    cudaError_t e = cudaMallocAsync((void**)&p, (count ? count : 1) * sizeof(T), stream);
     if (e == cudaSuccess) ptrs.push_back(p);
     return e;
   }
@@ -1467,9 +1473,12 @@ int exclusive_scan(mag_ctx* c, Scratch& S, const int32_t* in, int32_t* out, int6
   MAG_CUDA(c, cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, in, out, (int)n, c->stream));
   return MAG_OK;
 }
-void free_rows(MagRows& r)
+void free_rows(MagRows& r, cudaStream_t stream)
 {
-  cudaFree(r.d_anchor); cudaFree(r.d_slice_off); cudaFree(r.d_slots);
+  // (allocated from the stream-ordered pool on the context's compute stream, the only stream that ever reads them)
+  if (r.d_anchor) cudaFreeAsync(r.d_anchor, stream);
+  if (r.d_slice_off) cudaFreeAsync(r.d_slice_off, stream);
+  if (r.d_slots) cudaFreeAsync(r.d_slots, stream);
   r.d_anchor = r.d_slice_off = r.d_slots = nullptr;
   r.n_rows = r.n_slices = r.n_slots = 0;
   r.valid = false;
@@ -1480,14 +1489,14 @@ void free_rows(MagRows& r)
 static int build_order(mag_ctx* c, int64_t n, int64_t chunk_len, const int32_t* d_conn, int nv_per, int32_t*& d_order, int64_t& n_chunks)
 {
   n_chunks = (n + chunk_len - 1) / chunk_len;
-  if (d_order) { MAG_CUDA(c, cudaFree(d_order)); d_order = nullptr; }
+  if (d_order) { MAG_CUDA(c, cudaFreeAsync(d_order, c->stream)); d_order = nullptr; }
   if (n_chunks == 0) return MAG_OK;
-  Scratch S;
+  Scratch S(c->stream);
   int32_t *d_keys = nullptr, *d_keys_out = nullptr, *d_idx = nullptr;
   MAG_CUDA(c, S.get(d_keys, (size_t)n_chunks));
   MAG_CUDA(c, S.get(d_keys_out, (size_t)n_chunks));
   MAG_CUDA(c, S.get(d_idx, (size_t)n_chunks));
-  MAG_CUDA(c, cudaMalloc((void**)&d_order, (size_t)n_chunks * 4));
+  MAG_CUDA(c, cudaMallocAsync((void**)&d_order, (size_t)n_chunks * 4, c->stream));
   if (nv_per == 2) k_chunk_keys<2><<<(unsigned)n_chunks, kThreads, 0, c->stream>>>(n, chunk_len, d_conn, d_keys);
   else k_chunk_keys<4><<<(unsigned)n_chunks, kThreads, 0, c->stream>>>(n, chunk_len, d_conn, d_keys);
   k_iota<<<grid_for(n_chunks), kThreads, 0, c->stream>>>(n_chunks, d_idx);
@@ -1504,10 +1513,10 @@ static int build_order(mag_ctx* c, int64_t n, int64_t chunk_len, const int32_t* 
 template <int NV>
 static int build_rows(mag_ctx* c, int64_t n, const int32_t* d_conn, MagRows& rows)
 {
-  free_rows(rows);
+  free_rows(rows, c->stream);
   if (n == 0 || c->nv == 0) { rows.valid = true; return MAG_OK; }
   const int64_t nv = c->nv;
-  Scratch S;
+  Scratch S(c->stream);
   int32_t *key = nullptr, *val = nullptr, *key2 = nullptr, *sorted_e = nullptr, *deg = nullptr, *start = nullptr, *nrows = nullptr, *rowstart = nullptr;
   MAG_CUDA(c, S.get(key, (size_t)n));
   MAG_CUDA(c, S.get(val, (size_t)n));
@@ -1541,8 +1550,8 @@ static int build_rows(mag_ctx* c, int64_t n, const int32_t* d_conn, MagRows& row
   k_row_records<<<grid_for(nv), kThreads, 0, c->stream>>>(nv, deg, start, rowstart, row_anchor, row_len, row_first, rkey, ridx);
   MAG_CUDA(c, cudaGetLastError());
   if ((rc = sort_pairs(c, S, rkey, rkey2, ridx, order, R, bits_for(nv >> kRowWindowLog2) + 6))) return rc;
-  MAG_CUDA(c, cudaMalloc((void**)&rows.d_slice_off, ((size_t)nslices + 1) * 4));
-  MAG_CUDA(c, cudaMalloc((void**)&rows.d_anchor, (size_t)Rpad * 4));
+  MAG_CUDA(c, cudaMallocAsync((void**)&rows.d_slice_off, ((size_t)nslices + 1) * 4, c->stream));
+  MAG_CUDA(c, cudaMallocAsync((void**)&rows.d_anchor, (size_t)Rpad * 4, c->stream));
   int32_t* width32 = nullptr;
   MAG_CUDA(c, S.get(width32, (size_t)nslices + 1));
   k_slice_width<<<grid_for((nslices + 1) * 32), kThreads, 0, c->stream>>>(R, nslices, order, row_len, width32);
@@ -1553,11 +1562,11 @@ static int build_rows(mag_ctx* c, int64_t n, const int32_t* d_conn, MagRows& row
   MAG_CUDA(c, cudaMemcpyAsync(&n_slots32, rows.d_slice_off + nslices, 4, cudaMemcpyDeviceToHost, c->stream));
   MAG_CUDA(c, cudaStreamSynchronize(c->stream));
   if (n_slots32 < 0 || (int64_t)n_slots32 < n) {
-    free_rows(rows);
+    free_rows(rows, c->stream);
     return mag_fail(c, MAG_ERR_ARG, "row layout: slot count overflows int32 (%lld entities)", (long long)n);
   }
   const int64_t n_slots = n_slots32;
-  MAG_CUDA(c, cudaMalloc((void**)&rows.d_slots, (size_t)n_slots * NV * 4));
+  MAG_CUDA(c, cudaMallocAsync((void**)&rows.d_slots, (size_t)n_slots * NV * 4, c->stream));
   MAG_CUDA(c, cudaMemsetAsync(rows.d_slots, 0xFF, (size_t)n_slots * NV * 4, c->stream));
   k_slots_fill<NV><<<grid_for(Rpad), kThreads, 0, c->stream>>>(R, Rpad, order, row_anchor, row_len, row_first, sorted_e, d_conn,
                                                                rows.d_slice_off, rows.d_anchor, rows.d_slots);
@@ -1571,7 +1580,7 @@ static int build_rows(mag_ctx* c, int64_t n, const int32_t* d_conn, MagRows& row
   return MAG_OK;
 }
 
-void magk_free_rows(mag_ctx* c) { free_rows(c->erows); free_rows(c->trows); }
+void magk_free_rows(mag_ctx* c) { free_rows(c->erows, c->stream); free_rows(c->trows, c->stream); }
 
 int magk_build_schedule(mag_ctx* c)
 {

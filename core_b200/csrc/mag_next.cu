@@ -230,6 +230,27 @@ k_tri_weights(int32_t nt, const int32_t* __restrict__ tri_v, const double* __res
   if (eig) atomicAdd(&st->n_eigen_aux, 1ull);
 }
 
+// a prism as ma::getElementWeight weighs it (maBalance.cc:21-81): measure(base triangle) / (1/2) -- the triangle walked in the
+// FACE's own vertex order --, clampForIterations, clampForLayerPermissions, accountForTets
+template <int KIND, bool FAST>
+__global__ void __launch_bounds__(kWThreads)
+k_prism_weights(int32_t np, const int32_t* __restrict__ base_v, const double* __restrict__ vedge, double w_max, double w_min,
+                int refine_layer, int coarsen_layer, int to_tets, double* __restrict__ weight, MagDevStats* st)
+{
+  int eig = 0;
+  for (int32_t t = blockIdx.x * kWThreads + threadIdx.x; t < np; t += gridDim.x * kWThreads) {
+    double w = FAST ? tri_weight<KIND, FusedOps>(vedge, base_v + 3 * (int64_t)t, &eig)
+                    : tri_weight<KIND, StrictOps>(vedge, base_v + 3 * (int64_t)t, &eig);
+    if (w > w_max) w = w_max;
+    else if (w < w_min) w = w_min;
+    if (!refine_layer) w = w > 1.0 ? w : 1.0;      // std::max(1.0, weight)
+    if (!coarsen_layer) w = w < 1.0 ? w : 1.0;     // std::min(1.0, weight)
+    if (to_tets) w = __dmul_rn(w, 3.0);
+    weight[t] = w;
+  }
+  if (eig) atomicAdd(&st->n_eigen_aux, 1ull);
+}
+
 // ------------------------------------------------------------------ sliver classification
 // ma::getSliverCode / matchSliver (ma/maShape.cc:35-120), the classification LargeAngleTetFixer runs over the BAD_QUALITY
 // tets: J (apfVectorElement.cc:44-52) and Q = getTransform at the centroid, J = J Q; the quality of the tet's FIRST face
@@ -649,6 +670,53 @@ int mag_element_weights(mag_ctx* c, double w_max, double w_min, int fp_mode, dou
   MAG_CUDA(c, cudaStreamSynchronize(c->stream));
   if (c->h_stats->n_eigen_aux)
     return mag_fail(c, MAG_ERR_EIGEN, "eigenQR failed in %llu blocks of the weight sweep (apf::eigen asserts convergence, apfMatrix.cc:76)", c->h_stats->n_eigen_aux);
+  return MAG_OK;
+}
+
+int mag_prism_weights(mag_ctx* c, const int32_t* base_v, double w_max, double w_min, int should_refine_layer, int should_coarsen_layer,
+                      int should_turn_layer_to_tets, int fp_mode, double* out)
+{
+  if (!c) return MAG_ERR_ARG;
+  MAG_CUDA(c, cudaSetDevice(c->device));
+  if (c->kind == MAG_KIND_NONE) return mag_fail(c, MAG_ERR_ARG, "mag_prism_weights: no size field set");
+  if (fp_mode != MAG_FP_STRICT && fp_mode != MAG_FP_FAST) return mag_fail(c, MAG_ERR_ARG, "mag_prism_weights: bad fp_mode %d", fp_mode);
+  if (c->np == 0) return MAG_OK;
+  if (!base_v) return mag_fail(c, MAG_ERR_ARG, "mag_prism_weights: no base triangles");
+  for (int64_t i = 0; i < 3 * c->np; ++i)
+    if (base_v[i] < 0 || base_v[i] >= c->nv) return mag_fail(c, MAG_ERR_ARG, "mag_prism_weights: vertex id %d out of range", base_v[i]);
+  const int64_t nel = c->np + c->npy + c->nt + c->ntri;
+  if (!c->d_weight) {
+    MAG_CUDA(c, cudaMalloc((void**)&c->d_weight, (size_t)nel * sizeof(double)));
+    MAG_CUDA(c, cudaMemsetAsync(c->d_weight, 0, (size_t)nel * sizeof(double), c->stream));
+  }
+  DevBuf d_base;
+  MAG_CUDA(c, cudaMalloc(&d_base.p, (size_t)c->np * 3 * sizeof(int32_t)));
+  MAG_CUDA(c, cudaMemcpyAsync(d_base.p, base_v, (size_t)c->np * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  MAG_CUDA(c, cudaMemsetAsync(&c->d_stats->n_eigen_aux, 0, sizeof(unsigned long long), c->stream));
+  const int64_t blocks = (c->np + kWThreads - 1) / kWThreads;
+  const unsigned g = (unsigned)(blocks < (int64_t)c->n_sms * 32 ? blocks : (int64_t)c->n_sms * 32);
+  const bool fast = fp_mode == MAG_FP_FAST;
+#define MAG_PW(K)                                                                                                                    \
+  do {                                                                                                                               \
+    if (fast) k_prism_weights<K, true><<<g, kWThreads, 0, c->stream>>>((int32_t)c->np, (const int32_t*)d_base.p, c->d_vedge, w_max, w_min, should_refine_layer, \
+                                                                       should_coarsen_layer, should_turn_layer_to_tets, c->d_weight, c->d_stats); \
+    else k_prism_weights<K, false><<<g, kWThreads, 0, c->stream>>>((int32_t)c->np, (const int32_t*)d_base.p, c->d_vedge, w_max, w_min, should_refine_layer,     \
+                                                                   should_coarsen_layer, should_turn_layer_to_tets, c->d_weight, c->d_stats);  \
+  } while (0)
+  switch (c->kind) {
+    case MAG_KIND_IDENTITY: MAG_PW(MAG_KIND_IDENTITY); break;
+    case MAG_KIND_ISO: MAG_PW(MAG_KIND_ISO); break;
+    case MAG_KIND_ANISO: MAG_PW(MAG_KIND_ANISO); break;
+    default: MAG_PW(MAG_KIND_LOGM); break;
+  }
+#undef MAG_PW
+  MAG_CUDA(c, cudaGetLastError());
+  c->n_launches++;
+  if (out) MAG_CUDA(c, cudaMemcpyAsync(out, c->d_weight, (size_t)c->np * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  MAG_CUDA(c, cudaMemcpyAsync(&c->h_stats->n_eigen_aux, &c->d_stats->n_eigen_aux, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->h_stats->n_eigen_aux)
+    return mag_fail(c, MAG_ERR_EIGEN, "eigenQR failed in %llu blocks of the prism weight sweep (apf::eigen asserts convergence, apfMatrix.cc:76)", c->h_stats->n_eigen_aux);
   return MAG_OK;
 }
 

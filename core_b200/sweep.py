@@ -276,6 +276,23 @@ class Part:
         self._ck(self._L.mag_element_weights(self._h, w_max, w_min, int(fp_mode), _ptr(out)))
         return out
 
+    def prism_weights(self, base_v, refines_left=None, coarsens_left=0, refine_layer=True, coarsen_layer=True, to_tets=False,
+                      fp_mode=FP_STRICT):
+        """ma::getElementWeight of every prism (maBalance.cc:21-81): its base triangle's getWeight (base_v [np][3]: the first
+        face in the face's own vertex order), clamped like clampForIterations (refines_left None: raw), then the layer
+        permissions and the tet conversion factor of ma::Input."""
+        base_v = np.ascontiguousarray(base_v, dtype=np.int32)
+        if base_v.shape != (self.np_, 3):
+            raise ValueError("base_v must be [np][3]")
+        if refines_left is None:
+            w_max, w_min = float("inf"), float("-inf")
+        else:
+            w_max, w_min = 2.0 ** (3 * refines_left), 4.0 ** (-coarsens_left)
+        out = np.empty(self.np_, dtype=np.float64)
+        self._ck(self._L.mag_prism_weights(self._h, _ptr(base_v), w_max, w_min, int(bool(refine_layer)), int(bool(coarsen_layer)),
+                                           int(bool(to_tets)), int(fp_mode), _ptr(out)))
+        return out
+
     def cavity_quality(self, offsets, tet_v, use_max=True, fp_mode=FP_STRICT, want_qualities=False):
         """Batch ma::getWorstQuality (maQuality.cc:184-210): worst[k] = min quality over the candidate tets
         tet_v[offsets[k]:offsets[k+1]] (vertex quadruples; the tets need not exist in the mesh)."""

@@ -249,6 +249,16 @@ int mag_resweep_host(mag_ctx* c, const mag_host_update* in, const mag_host_marks
    are triangles: 3-point rule apf/apfIntegrate.cc:146-159, dV = |row0(J Q) x row1(J Q)|, parent measure 1/2, out [ntri].
    Synchronous. */
 int mag_element_weights(mag_ctx* c, double w_max, double w_min, int fp_mode, double* out);
+/* The prisms of the resident part as ma::getElementWeight weighs them (ma/maBalance.cc:21-81): getSizeWeight measures a prism's
+   BASE TRIANGLE (its first face, :31-37: SizeField::getWeight(face) = measure(triangle) / (1/2), 3-point rule as for a 2-D
+   part), then clampForIterations to [w_min, w_max], clampForLayerPermissions (ma::Input::shouldRefineLayer / shouldCoarsenLayer:
+   without the permission the weight is raised / lowered to 1) and accountForTets (shouldTurnLayerToTets: x 3).
+   base_v [np][3] host: the first face of every prism in the FACE entity's own vertex order (getDownward(prism, 2)[0], then
+   getDownward(face, 0)) -- the order the reference's integrator walks, which decides the last bit.  out [np] host (may be NULL);
+   the values also replace the zeros mag_element_weights left for the prisms in the device copy.  Pyramids stay with the
+   reference (sparse by construction, maBalance.cc:27-29).  Synchronous. */
+int mag_prism_weights(mag_ctx* c, const int32_t* base_v /*[np][3]*/, double w_max, double w_min, int should_refine_layer,
+                      int should_coarsen_layer, int should_turn_layer_to_tets, int fp_mode, double* out /*[np]*/);
 /* Batch form of ma::getWorstQuality / hasWorseQuality (ma/maQuality.cc:184-226) for many candidate cavities at once
    (collapse / swap / snap operators: ma/maCollapse.cc:37-113, ma/maEdgeSwap.cc:598-740, ma/maSnapper.cc:407,573).
    Cavity k = the tets tet_v[offsets[k] .. offsets[k+1]) given by their four vertex ids: existing vertices of the resident

@@ -466,6 +466,38 @@ int refo_weights(void* hd, int refinesLeft, int coarsensLeft, double* raw, doubl
   return 0;
 }
 
+/* ---- the same for layer elements (maBalance.cc:21-81): a prism is weighed by its BASE TRIANGLE (raw = getWeight(first face),
+   getSizeWeight :31-37), a pyramid by itself; clamped = ma::getElementWeight (clampForIterations, clampForLayerPermissions with
+   the Input's defaults, accountForTets).  base_v [nelem][3] = the prism's first face in the FACE's own vertex order (-1 for
+   other elements).  Simplex elements get what refo_weights gives them. */
+int refo_layer_weights(void* hd, int refinesLeft, int coarsensLeft, double* raw, double* clamped, int32_t* base_v)
+{
+  Ref* r = (Ref*)hd; apf::Mesh2* m = r->m;
+  if (!r->sf) return 1;
+  if (r->a) { delete r->a; r->a = 0; }
+  if (r->in) { delete r->in; r->in = 0; }
+  r->in = ma::makeAdvanced(ma::configureIdentity(m, r->sf));
+  r->a = new ma::Adapt(r->in);
+  r->a->refinesLeft = refinesLeft;
+  r->a->coarsensLeft = coarsensLeft;
+  apf::MeshIterator* it = m->begin(m->getDimension()); apf::MeshEntity* e; int64_t k = 0;
+  while ((e = m->iterate(it))) {
+    const int t = m->getType(e);
+    for (int i = 0; i < 3; ++i) base_v[3 * k + i] = -1;
+    if (t == apf::Mesh::PRISM) {
+      apf::Downward fs, fv;
+      m->getDownward(e, 2, fs);
+      m->getDownward(fs[0], 0, fv);
+      for (int i = 0; i < 3; ++i) base_v[3 * k + i] = (int32_t)apf::getMdsIndex(m, fv[i]);
+      raw[k] = r->sf->getWeight(fs[0]);
+    } else raw[k] = r->sf->getWeight(e);
+    clamped[k] = ma::getElementWeight(r->a, e);
+    ++k;
+  }
+  m->end(it);
+  return 0;
+}
+
 /* ---- ma::stats(m, sf, edgeLengths, linearQualities, true) (maStats.cc:115-134): the two vectors measureAnisoStats writes
    to its tables.  The caller sizes the outputs for every edge / element; the counts come back in n[2]. */
 int refo_stats(void* hd, double* el, double* lq, int64_t* n)

@@ -195,6 +195,16 @@ class RefMesh:
             assert lib().refo_weights(self.h, int(refines_left), int(coarsens_left), None, _p(out)) == 0
         return out
 
+    def layer_weights(self, refines_left=0, coarsens_left=0):
+        """Every element as ma::getElementWeights weighs it, layer elements included (maBalance.cc:21-81): (raw getWeight -- of
+        the base triangle for a prism --, ma::getElementWeight, first face of every prism in the face's own vertex order)."""
+        raw, cl = np.zeros(self.nelem), np.zeros(self.nelem)
+        base = np.zeros((self.nelem, 3), np.int32)
+        f = lib().refo_layer_weights
+        f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        assert f(self.h, int(refines_left), int(coarsens_left), _p(raw), _p(cl), _p(base)) == 0
+        return raw, cl, base
+
     def stats(self):
         """ma::stats in metric space: (edge lengths of owned edges, cbrt / signed sqrt of owned simplex qualities)."""
         el, lq = np.zeros(self.ne), np.zeros(self.nelem)

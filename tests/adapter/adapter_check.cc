@@ -448,18 +448,11 @@ extern "C" int mag_adapter_links_check(int nxA, int nxB, int ny, int nz, int par
    which: 1 = reference only (no device), 3 = both.  out[0..2] counts of the reference run (verts, edges, tets), out[3..5] of
    the adapter run, out[6] differing coordinates / connectivity entries, out[7] longest metric edge after the adapter run,
    out[8] device kernel launches made during the adapter run, out[9] / out[10] wall-clock seconds of the two runs. */
-/* ---- the adapter's two export routes (MDS's own arrays against the public apf::Mesh2 walk), host only: no device is touched.
-   kind 0: jittered n^3 box of tets; 1: the same after `iters` iterations of the reference's own ma::adapt (free-list holes, new
-   entities interleaved with old ones); 2: n^2 box of triangles; 3: n^3 cells whose bottom n/3 layers are prisms, Kuhn tets
-   above, plus one detached pyramid.  Returns mag::exportSelfCheck's mask; times[0..1] = seconds public / direct, times[2..4] =
-   vertices, edges, elements exported. */
-extern "C" int mag_adapter_export_check(int n, int kind, int threads, int iters, double* times)
+/* n^3 cells whose bottom n/3 layers are prisms (two per cell), Kuhn tets above; optionally one detached pyramid */
+static apf::Mesh2* make_mixed(int n, bool with_pyramid)
 {
   ensure_pcu();
-  apf::Mesh2* m;
-  if (kind == 2) m = apf::makeMdsBox(n, n, 0, 1, 1, 0, true, g_pcu);
-  else if (kind == 3) {
-    m = apf::makeEmptyMdsMesh(gmi_load(".null"), 3, false, g_pcu);
+    apf::Mesh2* m = apf::makeEmptyMdsMesh(gmi_load(".null"), 3, false, g_pcu);
     apf::ModelEntity* region = m->findModelEntity(3, 0);
     std::vector<apf::MeshEntity*> v((size_t)(n + 1) * (n + 1) * (n + 1));
     for (int k = 0; k <= n; ++k) for (int j = 0; j <= n; ++j) for (int i = 0; i <= n; ++i)
@@ -483,12 +476,28 @@ extern "C" int mag_adapter_export_check(int n, int kind, int threads, int iters,
         }
       }
     }
+    if (with_pyramid) {
     apf::MeshEntity* py[5];
     const double px[5][3] = {{3, 0, 0}, {4, 0, 0}, {4, 1, 0}, {3, 1, 0}, {3.5, 0.5, 1}};
     for (int q = 0; q < 5; ++q) py[q] = m->createVertex(region, apf::Vector3(px[q][0], px[q][1], px[q][2]), apf::Vector3(0, 0, 0));
     apf::buildElement(m, region, apf::Mesh::PYRAMID, py);
+    }
     m->acceptChanges();
-  } else m = apf::makeMdsBox(n, n, n, 1, 1, 1, true, g_pcu);
+    return m;
+}
+
+/* ---- the adapter's two export routes (MDS's own arrays against the public apf::Mesh2 walk), host only: no device is touched.
+   kind 0: jittered n^3 box of tets; 1: the same after `iters` iterations of the reference's own ma::adapt (free-list holes, new
+   entities interleaved with old ones); 2: n^2 box of triangles; 3: n^3 cells whose bottom n/3 layers are prisms, Kuhn tets
+   above, plus one detached pyramid.  Returns mag::exportSelfCheck's mask; times[0..1] = seconds public / direct, times[2..4] =
+   vertices, edges, elements exported. */
+extern "C" int mag_adapter_export_check(int n, int kind, int threads, int iters, double* times)
+{
+  ensure_pcu();
+  apf::Mesh2* m;
+  if (kind == 2) m = apf::makeMdsBox(n, n, 0, 1, 1, 0, true, g_pcu);
+  else if (kind == 3) m = make_mixed(n, true);
+  else m = apf::makeMdsBox(n, n, n, 1, 1, 1, true, g_pcu);
   if (kind != 3) jitter_mesh(m, n, 0.25);
   Fields f = make_fields(m, "exp", 1.0 / n);
   if (kind == 1) {
@@ -513,6 +522,49 @@ extern "C" int mag_adapter_export_check(int n, int kind, int threads, int iters,
   times[2] = (double)m->count(0); times[3] = (double)m->count(1); times[4] = (double)m->count(m->getDimension());
   if (kind != 1) { m->destroyNative(); apf::destroyMesh(m); }   /* kind 1: the kept size field still points at the mesh */
   return bad;
+}
+
+/* ma::getElementWeights on a mixed prism / tet mesh: the reference's per-entity loop against mag::getElementWeights (tets:
+   mag_element_weights; prisms: mag_prism_weights on the base triangles).  No pyramid in the mesh: the reference itself cannot
+   weigh one -- SizeField::getWeight(pyramid) asks for an order-2 rule and apf has only a one-point rule of accuracy 1 for
+   pyramids (apf/apfIntegrate.cc:530-554), so the integrator dereferences a null rule.  Layer permissions as
+   given (ma::Input::shouldRefineLayer / shouldCoarsenLayer / shouldTurnLayerToTets).  Returns the number of elements whose
+   weight differs (strict arithmetic: any bit); out[0..2] = prisms, pyramids, tets. */
+extern "C" long mag_adapter_layer_weights_check(int n, int fp_mode, int refine_layer, int coarsen_layer, int to_tets, double* out)
+{
+  apf::Mesh2* m = make_mixed(n, false);
+  Fields f = make_fields(m, "lw", 1.0 / n);
+  mag::GpuSizeField* g = mag::makeSizeField(m, f.sizes, f.frames, false, 0);
+  g->setArithmetic(fp_mode);
+  ma::Input* in = ma::makeAdvanced(ma::configureIdentity(m, g));
+  in->shouldRefineLayer = refine_layer != 0;
+  in->shouldCoarsenLayer = coarsen_layer != 0;
+  in->shouldTurnLayerToTets = to_tets != 0;
+  long diffs = 0;
+  out[0] = out[1] = out[2] = 0;
+  {
+    ma::Adapt a(in);
+    a.refinesLeft = 1; a.coarsensLeft = 1;
+    ma::Tag* wt = mag::getElementWeights(&a);
+    apf::MeshIterator* it = m->begin(3);
+    apf::MeshEntity* e;
+    while ((e = m->iterate(it))) {
+      const int t = m->getType(e);
+      out[t == apf::Mesh::PRISM ? 0 : (t == apf::Mesh::PYRAMID ? 1 : 2)] += 1;
+      double wg, wr = ma::getElementWeight(&a, e);   /* through the adapter's getWeight -> the wrapped reference field */
+      m->getDoubleTag(e, wt, &wg);
+      const double tol = fp_mode == MAG_FP_STRICT ? 0.0 : 1e-12;
+      if (!(fabs(wg - wr) <= tol * fabs(wr))) ++diffs;
+    }
+    m->end(it);
+    apf::removeTagFromDimension(m, wt, 3);
+    m->destroyTag(wt);
+  }
+  delete in;
+  delete g;
+  m->destroyNative();
+  apf::destroyMesh(m);
+  return diffs;
 }
 
 static int adapt_check(int n, int which, double size_scale, int iterations, int log_interp, int fp_mode, double* out);

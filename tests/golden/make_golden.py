@@ -65,6 +65,9 @@ def case(name, m, kind, h=None, R=None, good_quality=-1.0, edge_flags=None, elem
             out["split_edges"], out["split_xyz"], out["split_b"] = se.astype(np.int32), sx, sb
             if kind == refo.KIND_ANISO_FIELD:
                 out["split_a"] = sa
+    if not simplex_only:
+        # layer elements as ma::getElementWeights weighs them (maBalance.cc:21-81): prisms by their base triangle
+        out["layer_weights_raw"], out["layer_weights_r0_c1"], out["prism_base_v"] = m.layer_weights(0, 1)
     if simplex_only and np.all(et == refo.TET):
         # ShortEdgeFixer::shouldApply (maShape.cc:188-219; the class is local to that file: oracle/ref/ref_shape_shim.cc) on
         # the BAD_QUALITY marks: the edge it hands to its ShortEdgeRemover (-1: not applied) and the flag words afterwards

@@ -165,3 +165,21 @@ def test_adapter_public_api_route(built):
         assert rc == 0 and np.all(rep[15:19] == 0) and np.array_equal(rep[0:3], rep[5:8])
     finally:
         L.mag_adapter_set_direct(1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fp_mode,refine_layer,coarsen_layer,to_tets", [(0, 0, 0, 0), (0, 1, 1, 0), (0, 1, 1, 1), (1, 1, 1, 0)])
+def test_adapter_layer_element_weights(built, fp_mode, refine_layer, coarsen_layer, to_tets):
+    """mag::getElementWeights on a mixed mesh (prisms under Kuhn tets) against ma::getElementWeight of the unmodified reference
+    for every element: prisms go through mag_prism_weights on their base triangles (face order from MDS), tets through
+    mag_element_weights -- for the layer permissions ma::Input offers.  (No pyramid: the reference's own getWeight crashes on
+    one, apf has no order-2 pyramid rule.)"""
+    if not os.path.exists(LIB):
+        pytest.skip("libmag_ma.so not built (needs the reference headers)")
+    L = C.CDLL(LIB)
+    L.mag_adapter_layer_weights_check.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.mag_adapter_layer_weights_check.restype = C.c_long
+    out = np.zeros(3)
+    diffs = L.mag_adapter_layer_weights_check(6, fp_mode, refine_layer, coarsen_layer, to_tets, out.ctypes.data_as(C.c_void_p))
+    assert out[0] == 2 * 6 * 6 * 2 and out[1] == 0 and out[2] == 6 * 6 * 6 * 4
+    assert diffs == 0

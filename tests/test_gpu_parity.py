@@ -148,6 +148,42 @@ def test_weights_and_split_vertices_golden(cb, name):
     p.close()
 
 
+@pytest.mark.parametrize("name", [n for n in util.golden_cases() if "prism_base_v" in util.load(n)])
+def test_prism_weights_golden(cb, name):
+    """ma::getElementWeight of layer prisms (maBalance.cc:21-81: the base triangle's getWeight, clamps, layer permissions) on the
+    device against the compiled reference: raw weights bit for bit in strict arithmetic, ma::getElementWeight with the Input's
+    defaults (no layer refinement / coarsening: exactly 1), and the tets of the same mixed part through mag_element_weights."""
+    g = util.load(name)
+    kind, ma, mb = util.metric_arrays(g)
+    pr, py, te = util.split_elements(g)
+    p = cb.Part(0)
+    p.set_mesh(g["xyz"], g["edge_v"], te, prism_v=pr, pyr_v=py)
+    util.set_part_metric(p, kind, ma, mb)
+    base = g["prism_base_v"][: len(pr)]
+    assert np.all(base >= 0)
+    raw, cl = g["layer_weights_raw"], g["layer_weights_r0_c1"]
+    n0 = len(pr) + len(py)
+    for mode in (cb.FP_STRICT, cb.FP_FAST):
+        w = p.prism_weights(base, fp_mode=mode)
+        if mode == cb.FP_STRICT:
+            assert np.array_equal(w, raw[: len(pr)])
+        else:
+            assert util.rel_err(w, raw[: len(pr)]) < TOL
+        wc = p.prism_weights(base, 0, 1, refine_layer=False, coarsen_layer=False, fp_mode=mode)
+        assert np.array_equal(wc, cl[: len(pr)])
+        w3 = p.prism_weights(base, 0, 1, refine_layer=True, coarsen_layer=True, to_tets=True, fp_mode=cb.FP_STRICT)
+        assert np.array_equal(w3, 3.0 * np.clip(raw[: len(pr)], 0.25, 1.0))
+        wt = p.element_weights(0, 1, fp_mode=mode)
+        if mode == cb.FP_STRICT:
+            assert np.array_equal(wt[n0:], cl[n0:])
+        else:
+            assert util.rel_err(wt[n0:], cl[n0:]) < TOL
+    with pytest.raises(cb.MagError):
+        bad = base.copy(); bad[0, 0] = len(g["xyz"])
+        p.prism_weights(bad)
+    p.close()
+
+
 @pytest.mark.parametrize("name", [n for n in util.golden_cases() if "sliver_codes" in util.load(n)])
 def test_sliver_codes_golden(cb, name):
     """SURVEY 8f row 1, second classification sweep: ma::getSliverCode / matchSliver on the device against the compiled

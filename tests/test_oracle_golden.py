@@ -237,3 +237,19 @@ def test_short_edge_fixer_restatement_matches_reference(name):
         want = np.where(bad & ~cleared, te[np.arange(len(te)), l.argmin(axis=1)], -1)
         assert np.array_equal(want, g["short_edge_%g" % ratio])
         assert np.array_equal(np.where(cleared, g["elem_flags_out"] & ~BAD, g["elem_flags_out"]), g["short_flags_%g" % ratio])
+
+
+@pytest.mark.parametrize("name", [n for n in util.golden_cases() if "prism_base_v" in util.load(n)])
+def test_prism_weights_restatement_matches_reference(name):
+    """ma::getElementWeight weighs a layer prism by its base triangle (maBalance.cc:31-37): the restated triangle measure on the
+    reference's own face vertex order reproduces the reference's raw weights bit for bit; with the Input's default layer
+    permissions every prism then comes out at exactly 1 (clampForLayerPermissions)."""
+    from oracle import mao
+    g = util.load(name)
+    kind, ma, mb = util.metric_arrays(g)
+    base = g["prism_base_v"]
+    pr = np.nonzero(base[:, 0] >= 0)[0]
+    assert len(pr) > 0
+    w = mao.tri_weights(kind, g["xyz"], ma, mb, np.ascontiguousarray(base[pr]))
+    assert np.array_equal(w, g["layer_weights_raw"][pr])
+    assert np.all(g["layer_weights_r0_c1"][pr] == 1.0)
