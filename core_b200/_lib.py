@@ -14,7 +14,7 @@ SYMBOLS = [
     "mag_create", "mag_destroy", "mag_last_error", "mag_set_stream", "mag_synchronize",
     "mag_set_mesh", "mag_set_mesh_2d", "mag_set_coords",
     "mag_set_metric_identity", "mag_set_metric_uniform_refiner", "mag_set_metric_iso", "mag_set_metric_aniso", "mag_set_metric_logm",
-    "mag_set_flags", "mag_clear_flag", "mag_reset_layer", "mag_sweep", "mag_sweep_host", "mag_resweep_host", "mag_set_mark_bytes", "mag_get_mark_bytes", "mag_element_weights", "mag_prism_weights", "mag_split_vertices", "mag_cavity_quality", "mag_short_edge_test",
+    "mag_set_flags", "mag_clear_flag", "mag_reset_layer", "mag_sweep", "mag_sweep_host", "mag_resweep_host", "mag_set_mark_bytes", "mag_get_mark_bytes", "mag_element_weights", "mag_prism_weights", "mag_split_vertices", "mag_cavity_quality", "mag_collapse_quality", "mag_short_edge_test",
     "mag_sliver_codes", "mag_linear_qualities",
     "mag_get_edge_lengths", "mag_get_qualities", "mag_get_flags", "mag_get_layer_ok", "mag_get_stats",
     "mag_get_near_threshold", "mag_set_metric_logm_from_frames",
@@ -106,6 +106,7 @@ def lib():
     L.mag_set_mark_bytes.argtypes = [vp, vp, vp]
     L.mag_get_mark_bytes.argtypes = [vp, vp, vp]
     L.mag_element_weights.argtypes = [vp, f64, f64, C.c_int, vp]
+    L.mag_collapse_quality.argtypes = [vp, i64, vp, vp, C.c_int, C.c_int, vp, vp, vp]
     L.mag_prism_weights.argtypes = [vp, vp, f64, f64, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     L.mag_cavity_quality.argtypes = [vp, i64, vp, vp, C.c_int, C.c_int, vp, vp]
     L.mag_short_edge_test.argtypes = [vp, vp, f64, vp, C.POINTER(i64), C.POINTER(i64)]

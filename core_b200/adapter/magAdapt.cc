@@ -242,6 +242,11 @@ struct Access {
   static int vertSlotOf(GpuSizeField* g, ma::Entity* v) { return g->vertSlot[apf::getMdsIndex(g->mesh, v)]; }
   static long nonSimplex(GpuSizeField* g) { return g->nNonSimplex; }
   static int tetSlotOf(GpuSizeField* g, ma::Entity* e) { return g->tetSlot[apf::getMdsIndex(g->mesh, e)]; }
+  static int edgeSlotOf(GpuSizeField* g, ma::Entity* e)
+  {
+    const size_t id = (size_t)apf::getMdsIndex(g->mesh, e);
+    return id < g->edgeSlot.size() ? g->edgeSlot[id] : -1;
+  }
   static double qualityOf(GpuSizeField* g, ma::Entity* e) { return g->qualities[g->tetSlot[apf::getMdsIndex(g->mesh, e)]]; }
   static bool serveQuality(GpuSizeField* g, ma::Entity* e, double goodQuality, double& q)
   {
@@ -1076,6 +1081,31 @@ void getSliverCodes(ma::Adapt* a, std::vector<int>& codes, std::vector<ma::CodeM
   MAG_DO(g->ctx, mag_sliver_codes(g->ctx, face0.data(), a->input->goodQuality, 0, codes.data(), match.data()));
   matches.resize(nel);
   for (size_t i = 0; i < nel; ++i) { matches[i].rotation = match[2 * i]; matches[i].code_index = match[2 * i + 1]; }
+}
+
+/* ma::Collapse's quality test (maCollapse.cc:88-113) for many candidates in one device call: see mag_collapse_quality */
+void collapseQualities(ma::Adapt* a, const std::vector<ma::Entity*>& edges, const std::vector<ma::Entity*>& vertsToCollapse,
+                       std::vector<double>& newWorst, std::vector<double>& oldWorst)
+{
+  GpuSizeField* g = gpuField(a->sizeField);
+  ma::Mesh* m = a->mesh;
+  if (edges.size() != vertsToCollapse.size()) { fprintf(stderr, "mag adapter: collapseQualities: one vertex per edge\n"); abort(); }
+  Access::ensureExported(g);
+  Access::resetOrder(g);
+  const size_t n = edges.size();
+  std::vector<int> slot(n);
+  std::vector<unsigned char> end(n);
+  for (size_t i = 0; i < n; ++i) {
+    slot[i] = Access::edgeSlotOf(g, edges[i]);
+    if (slot[i] < 0) { fprintf(stderr, "mag adapter: collapseQualities: edge %zu is not part of the export\n", i); abort(); }
+    apf::Downward v;
+    m->getDownward(edges[i], 0, v);
+    if (v[0] != vertsToCollapse[i] && v[1] != vertsToCollapse[i]) { fprintf(stderr, "mag adapter: collapseQualities: vertex %zu is not an end of its edge\n", i); abort(); }
+    end[i] = v[0] == vertsToCollapse[i] ? 0 : 1;
+  }
+  newWorst.resize(n);
+  oldWorst.resize(n);
+  MAG_DO(g->ctx, mag_collapse_quality(g->ctx, (int64_t)n, slot.data(), end.data(), 1, Access::fpMode(g), newWorst.data(), oldWorst.data(), 0));
 }
 
 /* ------------------------------------------------------------------ export self-check (host only, no device) */

@@ -13,6 +13,7 @@
 //   ma::stats(m, sf, el, lq, inMetric)  ma/maStats.cc:115-134  ->  mag::stats (both vectors from one sweep)
 //   ma::getElementWeights(Adapt*)     ma/maBalance.cc:83    ->  mag::getElementWeights(Adapt*)  (same "ma_weight" tag)
 //   ma::getSliverCode / matchSliver   ma/maShape.cc:35-120  ->  mag::getSliverCodes(Adapt*, ...)  (every tet in one sweep)
+//   ma::Collapse::tryBothDirections' quality test   ma/maCollapse.cc:88-113  ->  mag::collapseQualities (many candidates at once)
 //   ma::getShapeHandler(Adapt*)       ma/maShapeHandler.cc  ->  mag::shapeHandler  (an ma::ShapeHandlerFunction for Input::shapeHandler)
 //
 // 3-D meshes (tets, with prisms / pyramids as layer elements) and 2-D meshes (triangles: ma::measureTriQuality).
@@ -168,6 +169,15 @@ Profile& profile();
    array, the slot tables, the change detection of moved vertices / edited field values and -- flags != NULL -- the direct read of
    an int tag.  Returns a bit mask of what differed (0 = identical); times[0] / times[1] = seconds of the public / direct export. */
 int exportSelfCheck(ma::Mesh* m, apf::Field* sizes, apf::Field* frames, ma::Tag* flags, int threads, double* times);
+
+/* The quality test of ma::Collapse::tryBothDirections (ma/maCollapse.cc:88-113) for MANY edge-collapse candidates in one device
+   call (mag_collapse_quality): candidate i collapses vertsToCollapse[i], an end of edges[i], onto the other end.  newWorst[i] =
+   the worst quality of the elements the collapse would rebuild (what hasWorseQuality looks at), oldWorst[i] =
+   Collapse::getOldQuality().  Nothing is built in the mesh.  A coarsening pass evaluates the members of one independent set
+   (ma/maCoarsen.cc:163-169) -- or every marked edge, both directions -- at once and only runs the topological collapse for the
+   candidates that pass  !(newWorst < min(goodQuality, max(oldWorst, validQuality))). */
+void collapseQualities(ma::Adapt* a, const std::vector<ma::Entity*>& edges, const std::vector<ma::Entity*>& vertsToCollapse,
+                       std::vector<double>& newWorst, std::vector<double>& oldWorst);
 
 /* ma::ShapeHandlerFunction: in->shapeHandler = mag::shapeHandler; getQuality(e) is then served from the device sweep */
 ma::ShapeHandler* shapeHandler(ma::Adapt* a);

@@ -165,6 +165,7 @@ int mag_create(mag_ctx** out, int device)
   c->d_edge_bytes = c->d_elem_bytes = nullptr;
   c->d_pair_keys = nullptr; c->d_pair_vals = nullptr; c->pair_bits = 0; c->d_layer_count = nullptr;
   c->d_near_edge = c->d_near_elem = nullptr;
+  c->d_v2t_off = c->d_v2t = nullptr; c->v2t_valid = false;
   c->cap_vedge = c->cap_ma = c->cap_mb = 0;
   c->last_ops = 0; c->last_fp_mode = 0;
   c->nccl_comm = nullptr; c->nranks = 1; c->rank = 0; c->d_gather = nullptr; c->h_gather = nullptr;
@@ -212,6 +213,7 @@ void mag_destroy(mag_ctx* c)
   cudaFree(c->d_stats); cudaFreeHost(c->h_stats); cudaFree(c->d_block_sums);
   cudaFree(c->d_near_edge); cudaFree(c->d_near_elem); cudaFree(c->d_edge_order); cudaFree(c->d_tet_order);
   cudaFree(c->d_edge_bytes); cudaFree(c->d_elem_bytes);
+  cudaFree(c->d_v2t_off); cudaFree(c->d_v2t);
   magk_free_rows(c); cudaFree(c->d_vstat); magl_free_pairs(c); cudaFree(c->d_layer_count);
   for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
   for (cudaEvent_t e : c->pipe_ev) cudaEventDestroy(e);
@@ -324,6 +326,7 @@ static int set_mesh_impl(mag_ctx* c, int dim, int64_t nv, const double* xyz, int
   const int64_t nel = np + npy + nt + ntri;
   // a new mesh starts with no flags (ma::getFlags returns 0 when the tag is absent, maAdapt.cc:80-88)
   c->edge_flags_zero = c->elem_flags_zero = true;
+  c->v2t_valid = false;
   if ((rc = upload(c, c->d_xyz, xyz, (size_t)nv * 3)) || (rc = upload(c, c->d_edge_v, edge_v, (size_t)ne * 2)) ||
       (rc = upload(c, c->d_tet_v, tet_v, (size_t)nt * 4)) || (rc = upload(c, c->d_prism_v, prism_v, (size_t)np * 6)) ||
       (rc = upload(c, c->d_pyr_v, pyr_v, (size_t)npy * 5)) || (rc = upload(c, c->d_tri_v, tri_v, (size_t)ntri * 3)))

@@ -114,6 +114,7 @@ extern "C" int mag_sweep_host(mag_ctx* c, const mag_host_part* in, const mag_hos
   Events ev{c};
 
   if ((rc = magi_reshape(c, 3, nv, ne, nt, 0, 0, 0, in->edge_owned != nullptr, in->elem_owned != nullptr))) return rc;
+  c->v2t_valid = false;
   if ((rc = magi_reserve_metric(c, in->kind, na, nb))) return rc;
   c->kind = in->kind;
   c->uniform_refiner = false;

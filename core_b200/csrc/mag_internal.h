@@ -99,6 +99,9 @@ struct mag_ctx {
   MagDevStats* d_stats;
   MagDevStats* h_stats;  // pinned
   double* d_block_sums;  // [MAG_SUM_BLOCKS] partial sums of the edge lengths (MAG_OP_LENGTH_SUM)
+  int32_t* d_v2t_off;    // [nv+1] vertex -> tet incidence (CSR) of mag_collapse_quality, built on first use per mesh
+  int32_t* d_v2t;        // [4 nt]
+  bool v2t_valid;
   int32_t* d_near_edge;  // [ne]  near-threshold edge indices of the last sweep (an entity is listed at most once)
   int32_t* d_near_elem;  // [np+npy+nt]
   int n_sms;

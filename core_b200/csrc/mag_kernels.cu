@@ -834,7 +834,77 @@ k_cavity_quality(int64_t ncav, const int64_t* __restrict__ offsets, const int4* 
       worst[k] = __longlong_as_double((long long)b);
     }
   }
-  if (eig) atomicAdd(&st->n_eigen_fail, 1ull);
+  if (eig) atomicAdd(&st->n_eigen_aux, 1ull);
+}
+
+// ------------------------------------------------------------------ edge-collapse candidates (the consumer of the batch)
+// What ma::Collapse decides a collapse on (ma/maCollapse.cc:37-113,353-383,425-433), for many candidates at once, on the resident
+// part alone: candidate k collapses vertex vc of edge e onto the other end vk.  Elements around vc that contain the edge
+// disappear (elementsToCollapse); every other element around vc is rebuilt with vc replaced by vk, vertex order kept
+// (rebuildElements -> ma::rebuildElement).  new_worst[k] = getWorstQuality(newElements), old_worst[k] = getOldQuality() =
+// getWorstQuality of ALL elements around vc, n_keep[k] = number of rebuilt elements.  The caller accepts when
+// !(new_worst < min(goodQuality, max(old_worst, validQuality))) (tryBothDirections).  Needs the vertex -> tet incidence, built
+// on the device from the resident connectivity on first use (count, scan, fill); one warp per candidate, lanes stride over the
+// tets around vc, warp-wide minima.
+__global__ void __launch_bounds__(kThreads)
+k_v2t_count(int64_t nt, const int4* __restrict__ tet_v, int32_t* __restrict__ cnt)
+{
+  const int64_t t = blockIdx.x * (int64_t)kThreads + threadIdx.x;
+  if (t >= nt) return;
+  const int4 tv = tet_v[t];
+  atomicAdd(cnt + (tv.x & kVidMask), 1); atomicAdd(cnt + tv.y, 1); atomicAdd(cnt + tv.z, 1); atomicAdd(cnt + tv.w, 1);
+}
+__global__ void __launch_bounds__(kThreads)
+k_v2t_fill(int64_t nt, const int4* __restrict__ tet_v, int32_t* __restrict__ cursor, int32_t* __restrict__ list)
+{
+  const int64_t t = blockIdx.x * (int64_t)kThreads + threadIdx.x;
+  if (t >= nt) return;
+  const int4 tv = tet_v[t];
+  list[atomicAdd(cursor + (tv.x & kVidMask), 1)] = (int32_t)t;
+  list[atomicAdd(cursor + tv.y, 1)] = (int32_t)t;
+  list[atomicAdd(cursor + tv.z, 1)] = (int32_t)t;
+  list[atomicAdd(cursor + tv.w, 1)] = (int32_t)t;
+}
+template <int KIND, bool FAST>
+__global__ void __launch_bounds__(256)
+k_collapse_quality(int64_t ncand, const int32_t* __restrict__ cand_edge, const uint8_t* __restrict__ cand_end, const int2* __restrict__ edge_v,
+                   const int32_t* __restrict__ v2t_off, const int32_t* __restrict__ v2t, const int4* __restrict__ tet_v, int64_t nv,
+                   const double* __restrict__ vpos, const double* __restrict__ vq, const double* __restrict__ vedge, int use_max,
+                   double* __restrict__ new_worst, double* __restrict__ old_worst, int32_t* __restrict__ n_keep, MagDevStats* st)
+{
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  int eig = 0;
+  for (int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < ncand; k += nwarps) {
+    int2 ev = __ldg(edge_v + cand_edge[k]);
+    ev.x &= kVidMask;
+    const int32_t vc = cand_end[k] ? ev.y : ev.x, vk = cand_end[k] ? ev.x : ev.y;
+    const int32_t lo = v2t_off[vc], hi = v2t_off[vc + 1];
+    unsigned long long key_new = ~0ull, key_old = ~0ull;
+    int keep = 0;
+    for (int32_t i = lo + lane; i < hi; i += 32) {
+      int4 tv = __ldg(tet_v + v2t[i]);
+      tv.x &= kVidMask;
+      const unsigned long long ko = dkey(tet_quality_eval<KIND, FAST, false>(tv, nv, vpos, vq, vedge, use_max, &eig, nullptr));
+      key_old = ko < key_old ? ko : key_old;
+      if (tv.x == vk || tv.y == vk || tv.z == vk || tv.w == vk) continue;       // contains the edge: collapses away
+      if (tv.x == vc) tv.x = vk; else if (tv.y == vc) tv.y = vk; else if (tv.z == vc) tv.z = vk; else tv.w = vk;
+      const unsigned long long kn = dkey(tet_quality_eval<KIND, FAST, false>(tv, nv, vpos, vq, vedge, use_max, &eig, nullptr));
+      key_new = kn < key_new ? kn : key_new;
+      ++keep;
+    }
+    key_new = warp_min_u64(key_new);
+    key_old = warp_min_u64(key_old);
+    keep = __reduce_add_sync(0xffffffffu, keep);
+    if (lane == 0) {
+      const unsigned long long bn = (key_new >> 63) ? (key_new & 0x7fffffffffffffffull) : ~key_new;   // inverse of dkey()
+      const unsigned long long bo = (key_old >> 63) ? (key_old & 0x7fffffffffffffffull) : ~key_old;
+      new_worst[k] = keep ? __longlong_as_double((long long)bn) : __longlong_as_double(0x7ff0000000000000ll);   // nothing rebuilt: +inf
+      old_worst[k] = hi > lo ? __longlong_as_double((long long)bo) : __longlong_as_double(0x7ff0000000000000ll);
+      n_keep[k] = keep;
+    }
+  }
+  if (eig) atomicAdd(&st->n_eigen_aux, 1ull);
 }
 
 // ------------------------------------------------------------------ triangles (2-D meshes)
@@ -1747,6 +1817,58 @@ int magk_cavity_quality(mag_ctx* c, int fp_mode, int64_t ncav, const int64_t* d_
     case MAG_KIND_ISO: return launch_cavities<MAG_KIND_ISO>(c, fast, ncav, d_off, d_tv, use_max, d_worst, d_qual);
     case MAG_KIND_ANISO: return launch_cavities<MAG_KIND_ANISO>(c, fast, ncav, d_off, d_tv, use_max, d_worst, d_qual);
     default: return launch_cavities<MAG_KIND_LOGM>(c, fast, ncav, d_off, d_tv, use_max, d_worst, d_qual);
+  }
+}
+
+// vertex -> tet incidence of the resident part (CSR: c->d_v2t_off [nv + 1], c->d_v2t [4 nt]); kept until the mesh changes
+int magk_build_v2t(mag_ctx* c)
+{
+  if (c->v2t_valid) return MAG_OK;
+  if (c->d_v2t_off) { MAG_CUDA(c, cudaFreeAsync(c->d_v2t_off, c->stream)); c->d_v2t_off = nullptr; }
+  if (c->d_v2t) { MAG_CUDA(c, cudaFreeAsync(c->d_v2t, c->stream)); c->d_v2t = nullptr; }
+  MAG_CUDA(c, cudaMallocAsync((void**)&c->d_v2t_off, ((size_t)c->nv + 1) * 4, c->stream));
+  MAG_CUDA(c, cudaMallocAsync((void**)&c->d_v2t, ((size_t)c->nt * 4 + 1) * 4, c->stream));
+  Scratch S(c->stream);
+  int32_t *cnt = nullptr, *cursor = nullptr;
+  MAG_CUDA(c, S.get(cnt, (size_t)c->nv + 1));
+  MAG_CUDA(c, S.get(cursor, (size_t)c->nv + 1));
+  MAG_CUDA(c, cudaMemsetAsync(cnt, 0, ((size_t)c->nv + 1) * 4, c->stream));
+  const int4* tv = reinterpret_cast<const int4*>(c->d_tet_v);
+  if (c->nt) k_v2t_count<<<grid_for(c->nt), kThreads, 0, c->stream>>>(c->nt, tv, cnt);
+  MAG_CUDA(c, cudaGetLastError());
+  int rc;
+  if ((rc = exclusive_scan(c, S, cnt, c->d_v2t_off, c->nv + 1))) return rc;
+  MAG_CUDA(c, cudaMemcpyAsync(cursor, c->d_v2t_off, ((size_t)c->nv + 1) * 4, cudaMemcpyDeviceToDevice, c->stream));
+  if (c->nt) k_v2t_fill<<<grid_for(c->nt), kThreads, 0, c->stream>>>(c->nt, tv, cursor, c->d_v2t);
+  MAG_CUDA(c, cudaGetLastError());
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->n_launches += 3;
+  c->v2t_valid = true;
+  return MAG_OK;
+}
+template <int KIND>
+static int launch_collapse(mag_ctx* c, bool fast, int64_t ncand, const int32_t* d_edge, const uint8_t* d_end, int use_max,
+                           double* d_new, double* d_old, int32_t* d_keep)
+{
+  const int64_t blocks = (ncand + 7) / 8;
+  const unsigned g = (unsigned)(blocks < (int64_t)c->n_sms * 16 ? (blocks < 1 ? 1 : blocks) : (int64_t)c->n_sms * 16);
+  const int2* ev = reinterpret_cast<const int2*>(c->d_edge_v);
+  const int4* tv = reinterpret_cast<const int4*>(c->d_tet_v);
+  if (fast) k_collapse_quality<KIND, true><<<g, 256, 0, c->stream>>>(ncand, d_edge, d_end, ev, c->d_v2t_off, c->d_v2t, tv, c->nv, c->d_vpos, c->d_vq, c->d_vedge, use_max, d_new, d_old, d_keep, c->d_stats);
+  else k_collapse_quality<KIND, false><<<g, 256, 0, c->stream>>>(ncand, d_edge, d_end, ev, c->d_v2t_off, c->d_v2t, tv, c->nv, c->d_vpos, c->d_vq, c->d_vedge, use_max, d_new, d_old, d_keep, c->d_stats);
+  MAG_CUDA(c, cudaGetLastError());
+  c->n_launches++;
+  return MAG_OK;
+}
+int magk_collapse_quality(mag_ctx* c, int fp_mode, int64_t ncand, const int32_t* d_edge, const uint8_t* d_end, int use_max,
+                          double* d_new, double* d_old, int32_t* d_keep)
+{
+  const bool fast = fp_mode == MAG_FP_FAST;
+  switch (c->kind) {
+    case MAG_KIND_IDENTITY: return launch_collapse<MAG_KIND_IDENTITY>(c, fast, ncand, d_edge, d_end, use_max, d_new, d_old, d_keep);
+    case MAG_KIND_ISO: return launch_collapse<MAG_KIND_ISO>(c, fast, ncand, d_edge, d_end, use_max, d_new, d_old, d_keep);
+    case MAG_KIND_ANISO: return launch_collapse<MAG_KIND_ANISO>(c, fast, ncand, d_edge, d_end, use_max, d_new, d_old, d_keep);
+    default: return launch_collapse<MAG_KIND_LOGM>(c, fast, ncand, d_edge, d_end, use_max, d_new, d_old, d_keep);
   }
 }
 

@@ -15,6 +15,9 @@ using namespace maglay;
 
 int magk_vertex_pass(mag_ctx* c);
 int magk_cavity_quality(mag_ctx* c, int fp_mode, int64_t ncav, const int64_t* d_off, const int32_t* d_tv, int use_max, double* d_worst, double* d_qual);
+int magk_build_v2t(mag_ctx* c);
+int magk_collapse_quality(mag_ctx* c, int fp_mode, int64_t ncand, const int32_t* d_edge, const uint8_t* d_end, int use_max,
+                          double* d_new, double* d_old, int32_t* d_keep);
 
 namespace {
 
@@ -828,6 +831,47 @@ int mag_clear_flag(mag_ctx* c, int dimension, int32_t flag)
   k_clear_bits<<<g, 256, 0, c->stream>>>(n, flag, edges ? c->d_edge_flags : c->d_elem_flags);
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;
+  return MAG_OK;
+}
+
+int mag_collapse_quality(mag_ctx* c, int64_t ncand, const int32_t* edges, const uint8_t* which_end, int use_max_metric, int fp_mode,
+                         double* new_worst, double* old_worst, int32_t* n_keep)
+{
+  if (!c) return MAG_ERR_ARG;
+  MAG_CUDA(c, cudaSetDevice(c->device));
+  if (c->kind == MAG_KIND_NONE) return mag_fail(c, MAG_ERR_ARG, "mag_collapse_quality: no size field set");
+  if (c->dim != 3) return mag_fail(c, MAG_ERR_ARG, "mag_collapse_quality: 3-D parts only");
+  if (fp_mode != MAG_FP_STRICT && fp_mode != MAG_FP_FAST) return mag_fail(c, MAG_ERR_ARG, "mag_collapse_quality: bad fp_mode %d", fp_mode);
+  if (ncand < 0 || (ncand && (!edges || !which_end || !new_worst || !old_worst))) return mag_fail(c, MAG_ERR_ARG, "mag_collapse_quality: bad arguments");
+  if (ncand == 0) return MAG_OK;
+  for (int64_t k = 0; k < ncand; ++k)
+    if (edges[k] < 0 || edges[k] >= c->ne) return mag_fail(c, MAG_ERR_ARG, "mag_collapse_quality: edge %d out of range", edges[k]);
+  int rc;
+  if (!c->schedule_valid) return mag_fail(c, MAG_ERR_ARG, "mag_collapse_quality: the part came through mag_sweep_host; call mag_set_mesh");
+  if (!c->vertex_pass_valid) {
+    if ((rc = magk_vertex_pass(c))) return rc;
+    c->vertex_pass_valid = true;
+  }
+  if ((rc = magk_build_v2t(c))) return rc;
+  DevBuf de, dn, dnew, dold, dkeep;
+  MAG_CUDA(c, cudaMalloc(&de.p, (size_t)ncand * 4));
+  MAG_CUDA(c, cudaMalloc(&dn.p, (size_t)ncand));
+  MAG_CUDA(c, cudaMalloc(&dnew.p, (size_t)ncand * 8));
+  MAG_CUDA(c, cudaMalloc(&dold.p, (size_t)ncand * 8));
+  MAG_CUDA(c, cudaMalloc(&dkeep.p, (size_t)ncand * 4));
+  MAG_CUDA(c, cudaMemcpyAsync(de.p, edges, (size_t)ncand * 4, cudaMemcpyHostToDevice, c->stream));
+  MAG_CUDA(c, cudaMemcpyAsync(dn.p, which_end, (size_t)ncand, cudaMemcpyHostToDevice, c->stream));
+  MAG_CUDA(c, cudaMemsetAsync(&c->d_stats->n_eigen_aux, 0, sizeof(unsigned long long), c->stream));
+  if ((rc = magk_collapse_quality(c, fp_mode, ncand, (const int32_t*)de.p, (const uint8_t*)dn.p, use_max_metric, (double*)dnew.p,
+                                  (double*)dold.p, (int32_t*)dkeep.p)))
+    return rc;
+  MAG_CUDA(c, cudaMemcpyAsync(new_worst, dnew.p, (size_t)ncand * 8, cudaMemcpyDeviceToHost, c->stream));
+  MAG_CUDA(c, cudaMemcpyAsync(old_worst, dold.p, (size_t)ncand * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (n_keep) MAG_CUDA(c, cudaMemcpyAsync(n_keep, dkeep.p, (size_t)ncand * 4, cudaMemcpyDeviceToHost, c->stream));
+  MAG_CUDA(c, cudaMemcpyAsync(&c->h_stats->n_eigen_aux, &c->d_stats->n_eigen_aux, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->h_stats->n_eigen_aux)
+    return mag_fail(c, MAG_ERR_EIGEN, "eigenQR failed in %llu blocks of the collapse sweep (apf::eigen asserts convergence, apfMatrix.cc:76)", c->h_stats->n_eigen_aux);
   return MAG_OK;
 }
 

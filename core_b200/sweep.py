@@ -276,6 +276,20 @@ class Part:
         self._ck(self._L.mag_element_weights(self._h, w_max, w_min, int(fp_mode), _ptr(out)))
         return out
 
+    def collapse_quality(self, edges, which_end, use_max=True, fp_mode=FP_STRICT):
+        """ma::Collapse's quality test for many candidates (maCollapse.cc:88-113): candidate k collapses end which_end[k] of
+        edge edges[k] onto the other end.  Returns (new_worst, old_worst, n_keep): worst quality of the rebuilt tets, of all tets
+        around the collapsing vertex, number of rebuilt tets."""
+        edges = np.ascontiguousarray(edges, dtype=np.int32)
+        which_end = np.ascontiguousarray(which_end, dtype=np.uint8)
+        if edges.shape != which_end.shape or edges.ndim != 1:
+            raise ValueError("edges and which_end must be 1-D arrays of the same length")
+        n = len(edges)
+        new_w, old_w, keep = np.empty(n), np.empty(n), np.empty(n, np.int32)
+        self._ck(self._L.mag_collapse_quality(self._h, n, _ptr(edges), _ptr(which_end), int(bool(use_max)), int(fp_mode),
+                                              _ptr(new_w), _ptr(old_w), _ptr(keep)))
+        return new_w, old_w, keep
+
     def prism_weights(self, base_v, refines_left=None, coarsens_left=0, refine_layer=True, coarsen_layer=True, to_tets=False,
                       fp_mode=FP_STRICT):
         """ma::getElementWeight of every prism (maBalance.cc:21-81): its base triangle's getWeight (base_v [np][3]: the first

@@ -268,6 +268,21 @@ int mag_prism_weights(mag_ctx* c, const int32_t* base_v /*[np][3]*/, double w_ma
    The per-vertex transforms of the last sweep are reused while mesh and size field are unchanged.  Synchronous. */
 int mag_cavity_quality(mag_ctx* c, int64_t ncav, const int64_t* offsets, const int32_t* tet_v /*[.][4]*/,
                        int use_max_metric, int fp_mode, double* worst, double* qualities);
+/* The quality test of MANY edge-collapse candidates at once, from the resident part alone -- the consumer of the cavity batch
+   inside ma::coarsen (ma/maCoarsen.cc:163-169 picks an independent set of vertices, then every member runs
+   ma::Collapse::tryBothDirections, ma/maCollapse.cc:88-113).  Candidate k collapses one end of edge edges[k] (index in the
+   resident edge array) onto the other: which_end[k] = 0 collapses the edge's first vertex, 1 its second (Collapse::vertToCollapse).
+   As Collapse::computeElementSets / rebuildElements do (:353-383): tets around that vertex that contain the edge vanish, every
+   other tet around it is rebuilt with the vertex replaced by the one that is kept (vertex order unchanged).
+     new_worst [ncand] = ma::getWorstQuality of the rebuilt tets (+inf if there are none; the reference asserts there are)
+     old_worst [ncand] = Collapse::getOldQuality(): the worst of ALL tets around the collapsing vertex (:425-433)
+     n_keep    [ncand] = how many tets are rebuilt (may be NULL)
+   The collapse passes the reference's test iff !(new_worst < min(goodQuality, max(old_worst, validQuality))) (:93-99 with
+   ma::hasWorseQuality, maQuality.cc:200-226).  Strict arithmetic: bit-identical to what the reference computes on the mesh it
+   really rebuilds.  Tets only: candidates next to layer elements are the caller's to exclude (their edges carry DONT_COLLAPSE,
+   ma/maLayer.cc:75-103).  The vertex -> tet incidence is built on the device on first use after a mag_set_mesh and kept. */
+int mag_collapse_quality(mag_ctx* c, int64_t ncand, const int32_t* edges, const uint8_t* which_end, int use_max_metric, int fp_mode,
+                         double* new_worst, double* old_worst, int32_t* n_keep);
 /* ShortEdgeFixer::shouldApply (ma/maShape.cc:188-219), the classification sweep ma::fixElementShapes runs over the
    BAD_QUALITY elements right after markBadQuality: tet_edges [nt][6] = the edge indices of every tet in
    getDownward(tet, 1) order; the lengths are those of the last MAG_OP_LENGTHS sweep (resident).  For every tet carrying

@@ -13,6 +13,8 @@
 #include <maAdapt.h>
 #include <maRefine.h>
 #include <maShape.h>
+#include <maCollapse.h>
+#include <maShapeHandler.h>
 #include <maStats.h>
 #include <apfMDS.h>
 #include <apfBox.h>
@@ -561,6 +563,87 @@ extern "C" long mag_adapter_layer_weights_check(int n, int fp_mode, int refine_l
     m->destroyTag(wt);
   }
   delete in;
+  delete g;
+  m->destroyNative();
+  apf::destroyMesh(m);
+  return diffs;
+}
+
+/* mag::collapseQualities against ma::Collapse itself.  On a jittered box whose size field asks for coarsening, every edge the
+   reference marks COLLAPSE and whose collapse passes its classification / topology checks is REALLY rebuilt by the unmodified
+   reference in each permitted direction (Collapse::computeElementSets + rebuildElements), the qualities of the old and of the
+   new elements are taken through its shape handler, and the new elements are destroyed again.  The adapter then answers the
+   same candidates in one device call from its export of the restored mesh.  out[0] = candidates (edge, direction), out[1] =
+   candidates whose rebuilt cavity holds an inverted element, out[2] = candidates the reference's test would accept.
+   Returns the number of candidates whose old or new worst quality differs (strict: any bit; fast: 1e-12). */
+extern "C" long mag_adapter_collapse_check(int n, int fp_mode, double size_scale, double* out)
+{
+  ensure_pcu();
+  apf::Mesh2* m = apf::makeMdsBox(n, n, n, 1, 1, 1, true, g_pcu);
+  jitter_mesh(m, n, 0.25);
+  std::vector<ma::Entity*> edges, verts;
+  std::vector<double> refNew, refOld;
+  out[0] = out[1] = out[2] = 0;
+  {
+    Fields f = make_fields(m, "ref", size_scale / n);
+    ma::SizeField* sf = ma::makeSizeField(m, f.sizes, f.frames, false);
+    ma::Input* in = ma::makeAdvanced(ma::configureIdentity(m, sf));
+    {
+      ma::Adapt a(in);
+      ma::markEdgesToCollapse(&a);
+      std::vector<ma::Entity*> marked;
+      apf::MeshIterator* it = m->begin(1);
+      ma::Entity* e;
+      while ((e = m->iterate(it))) if (ma::getFlag(&a, e, ma::COLLAPSE)) marked.push_back(e);
+      m->end(it);
+      ma::Collapse c;
+      c.Init(&a);
+      for (size_t i = 0; i < marked.size(); ++i) {
+        if (!c.setEdge(marked[i]) || !c.checkClass() || !c.checkTopo()) continue;
+        for (int dir = 0; dir < 2; ++dir) {
+          if (dir == 1) {
+            if (!ma::getFlag(&a, c.vertToKeep, ma::COLLAPSE)) break;      /* tryBothDirections' condition for the other way */
+            std::swap(c.vertToKeep, c.vertToCollapse);
+          }
+          c.computeElementSets();
+          ma::EntityArray oldEl;
+          c.getOldElements(oldEl);
+          double oq = a.shape->getQuality(oldEl[0]);
+          for (size_t k = 1; k < oldEl.getSize(); ++k) { const double q = a.shape->getQuality(oldEl[k]); if (q < oq) oq = q; }
+          c.rebuildElements();
+          double nq = a.shape->getQuality(c.newElements[0]);
+          for (size_t k = 1; k < c.newElements.getSize(); ++k) { const double q = a.shape->getQuality(c.newElements[k]); if (q < nq) nq = q; }
+          c.destroyNewElements();
+          edges.push_back(marked[i]); verts.push_back(c.vertToCollapse);
+          refNew.push_back(nq); refOld.push_back(oq);
+          out[0] += 1;
+          if (nq < 0) out[1] += 1;
+          const double toBeat = std::min(in->goodQuality, std::max(oq, in->validQuality));
+          if (!(nq < toBeat)) out[2] += 1;
+        }
+        c.unmark();
+      }
+    }
+    delete in;
+    delete sf;
+  }
+  if (getenv("MAG_CHECK_VERBOSE")) fprintf(stderr, "collapse check: %g candidates, %g inverted, %g accepted\n", out[0], out[1], out[2]);
+  Fields f = make_fields(m, "gpu", size_scale / n);
+  mag::GpuSizeField* g = mag::makeSizeField(m, f.sizes, f.frames, false, 0);
+  g->setArithmetic(fp_mode);
+  long diffs = 0;
+  {
+    ma::Input* in = ma::makeAdvanced(ma::configureIdentity(m, g));
+    {
+      ma::Adapt a(in);
+      std::vector<double> nw, ow;
+      mag::collapseQualities(&a, edges, verts, nw, ow);
+      const double tol = fp_mode == MAG_FP_STRICT ? 0.0 : 1e-12;
+      for (size_t i = 0; i < edges.size(); ++i)
+        if (!(fabs(nw[i] - refNew[i]) <= tol * fabs(refNew[i]) + (tol > 0 ? 1e-15 : 0)) || !(fabs(ow[i] - refOld[i]) <= tol * fabs(refOld[i]))) ++diffs;
+    }
+    delete in;
+  }
   delete g;
   m->destroyNative();
   apf::destroyMesh(m);

@@ -183,3 +183,23 @@ def test_adapter_layer_element_weights(built, fp_mode, refine_layer, coarsen_lay
     diffs = L.mag_adapter_layer_weights_check(6, fp_mode, refine_layer, coarsen_layer, to_tets, out.ctypes.data_as(C.c_void_p))
     assert out[0] == 2 * 6 * 6 * 2 and out[1] == 0 and out[2] == 6 * 6 * 6 * 4
     assert diffs == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fp_mode", [0, 1])
+def test_adapter_collapse_candidates_against_ma_collapse(built, fp_mode):
+    """mag::collapseQualities (one mag_collapse_quality call) against ma::Collapse ITSELF: on a jittered 10^3 box whose size
+    field asks for coarsening, the unmodified reference really rebuilds the cavity of every collapse candidate that passes its
+    classification / topology checks, in each permitted direction (computeElementSets + rebuildElements), measures old and new
+    elements through its shape handler and destroys the new ones again; the device answers the same ~6800 candidates from its
+    export of the restored mesh (MDS now has free-list holes).  Old and new worst qualities agree bit for bit in strict
+    arithmetic (1e-12 fast), including the ~1600 candidates whose rebuilt cavity holds an inverted tet."""
+    if not os.path.exists(LIB):
+        pytest.skip("libmag_ma.so not built (needs the reference headers)")
+    L = C.CDLL(LIB)
+    L.mag_adapter_collapse_check.argtypes = [C.c_int, C.c_int, C.c_double, C.c_void_p]
+    L.mag_adapter_collapse_check.restype = C.c_long
+    out = np.zeros(3)
+    diffs = L.mag_adapter_collapse_check(10, fp_mode, 2.5, out.ctypes.data_as(C.c_void_p))
+    assert out[0] > 5000 and out[1] > 1000 and out[2] > 2000
+    assert diffs == 0

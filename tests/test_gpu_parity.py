@@ -304,6 +304,80 @@ def test_short_edge_classification(cb, name):
     p.close()
 
 
+@pytest.mark.parametrize("kindname", ["aniso", "iso"])
+def test_collapse_candidates_vs_oracle(cb, kindname):
+    """mag_collapse_quality (ma::Collapse's quality test, maCollapse.cc:88-113,353-383,425-433) against the restated oracle: for
+    both ends of sampled edges of a jittered box, the tets around the collapsing vertex that do not hold the edge are rebuilt
+    with the vertex replaced (numpy), their worst quality and the worst quality of all tets around the vertex must come out
+    bit for bit in strict arithmetic, within 1e-12 in fast arithmetic; boundary vertices give small one-sided cavities, and a
+    collapse across the box inverts tets (negative qualities)."""
+    from oracle import mao
+    n = 9
+    rng = np.random.default_rng(5)
+    xyz, ev, tv = cb.boxmesh.kuhn_box(n, n, n)
+    xyz = cb.fields.jitter(xyz, 0.3 / n)
+    h, R = cb.fields.shock_rotating(xyz, 1.0 / n)
+    if kindname == "aniso":
+        kind, ma, mb = mao.ANISO, h, R
+    else:
+        kind, ma, mb = mao.ISO, np.ascontiguousarray(h[:, 1] * (1 + xyz[:, 0])), None
+    eo = (rng.random(len(ev)) < 0.9).astype(np.uint8)        # ownership bits ride in the connectivity: must not leak into ids
+    lo = (rng.random(len(tv)) < 0.9).astype(np.uint8)
+    p = cb.Part(0)
+    p.set_mesh(xyz, ev, tv, edge_owned=eo, elem_owned=lo)
+    util.set_part_metric(p, kind, ma, mb)
+    q_all = mao.tet_qualities(kind, xyz, ma, mb, tv)
+    edges = rng.choice(len(ev), 1500, replace=False).astype(np.int32)
+    edges = np.concatenate([edges, edges])
+    ends = np.concatenate([np.zeros(1500, np.uint8), np.ones(1500, np.uint8)])
+    # vertex -> tets
+    order = np.argsort(tv.ravel(), kind="stable")
+    owner = (order // 4).astype(np.int64)
+    start = np.searchsorted(tv.ravel()[order], np.arange(len(xyz) + 1))
+    want_new, want_old, want_keep = np.empty(len(edges)), np.empty(len(edges)), np.empty(len(edges), np.int32)
+    cand, offs = [], [0]
+    for k, (e, w) in enumerate(zip(edges, ends)):
+        vc, vk = (ev[e, 1], ev[e, 0]) if w else (ev[e, 0], ev[e, 1])
+        around = owner[start[vc]:start[vc + 1]]
+        want_old[k] = q_all[around].min()
+        keep = around[~np.any(tv[around] == vk, axis=1)]
+        t = tv[keep].copy()
+        t[t == vc] = vk
+        cand.append(t)
+        offs.append(offs[-1] + len(t))
+        want_keep[k] = len(t)
+    cand = np.ascontiguousarray(np.concatenate(cand), np.int32)
+    qn = mao.tet_qualities(kind, xyz, ma, mb, cand)
+    offs = np.array(offs)
+    has = want_keep > 0
+    want_new[has] = np.minimum.reduceat(qn, offs[:-1][has])
+    want_new[~has] = np.inf
+    assert (want_new < 0).any() and has.mean() > 0.95      # a corner vertex may keep nothing: +inf
+    new_w, old_w, keep_n = p.collapse_quality(edges, ends, fp_mode=cb.FP_STRICT)
+    assert np.array_equal(keep_n, want_keep)
+    assert np.array_equal(old_w, want_old) and np.array_equal(new_w, want_new)
+    new_f, old_f, _ = p.collapse_quality(edges, ends, fp_mode=cb.FP_FAST)
+    assert np.all(np.abs(new_f[has] - want_new[has]) <= TOL * np.abs(want_new[has]) + 1e-15) and np.all(np.isinf(new_f[~has]))
+    assert util.rel_err(old_f, want_old) < TOL
+    # the batch through mag_cavity_quality gives the same numbers (the incidence lists are the only new ingredient)
+    offs_ne = np.concatenate([[0], np.cumsum(want_keep[has])]).astype(np.int64)        # mag_cavity_quality takes no empty cavity
+    worst = p.cavity_quality(offs_ne, cand, fp_mode=cb.FP_STRICT)
+    assert np.array_equal(worst, want_new[has])
+    # a new mesh in the same context: the incidence is rebuilt
+    xyz2, ev2, tv2 = cb.boxmesh.kuhn_box(4, 5, 3)
+    h2, R2 = cb.fields.shock_rotating(xyz2, 0.25)
+    p.set_mesh(xyz2, ev2, tv2)
+    p.set_size_field_aniso(h2, R2)
+    q2 = mao.tet_qualities(mao.ANISO, xyz2, h2, R2, tv2)
+    e2 = np.arange(len(ev2), dtype=np.int32)
+    _, old2, _ = p.collapse_quality(e2, np.zeros(len(ev2), np.uint8))
+    want2 = np.array([q2[np.any(tv2 == ev2[e, 0], axis=1)].min() for e in e2])
+    assert np.array_equal(old2, want2)
+    with pytest.raises(cb.sweep.MagError):
+        p.collapse_quality(np.array([len(ev2)], np.int32), np.zeros(1, np.uint8))
+    p.close()
+
+
 def test_cavity_quality_candidate_tets_vs_oracle(cb):
     """Would-be elements: random vertex quadruples (many inverted -> negative qualities) that are not mesh entities,
     ragged cavities of 1..40 tets, against the restated oracle; error paths of the batch call."""
