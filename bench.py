@@ -723,6 +723,11 @@ def run_b200(a):
         # the bit-exact arithmetic on the same part
         if a.fp == "fast":
             extras["strict"] = brief(T.run(p, make_step(p, cb.FP_STRICT, False), xs, 1), "aniso")
+            # MAG_FP_FAST_LISTED: near-threshold edges are listed and decided by the fast value instead of being re-evaluated in
+            # strict arithmetic -- the exception the parity rule itself allows; the lattice puts 8.4 M z edges ON the threshold
+            extras["fast_listed"] = brief(T.run(p, make_step(p, cb.FP_FAST_LISTED, False), xs, 2), "aniso")
+            extras["fast_listed"]["what"] = ("MAG_FP_FAST_LISTED: the same sweep with near-threshold edges listed, not re-evaluated; "
+                                             "n_collapse / n_split may differ from the headline's by at most n_near_threshold")
         # SURVEY 8d's perturbed variant: no edge sits exactly on a threshold
         if a.jitter == 0:
             xj = cb.fields.jitter(xyz0, 0.2 * hbar)
@@ -739,6 +744,8 @@ def run_b200(a):
         extras["logm"] = brief(T.run(p, make_step(p, fp_mode, False), xs, 2), "logm")
         extras["logm"]["field_build_s"] = t_logm
         extras["logm"]["workload"] = workload_name(n, "logm")
+        if a.fp == "fast":
+            extras["logm_fast_listed"] = brief(T.run(p, make_step(p, cb.FP_FAST_LISTED, False), xs, 2), "logm")
         p.set_size_field_aniso(h, R)
     p.close()
     del p

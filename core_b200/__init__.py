@@ -7,5 +7,5 @@ from .sweep import (Part, MagError, MAXLENGTH, MINLENGTH, GOOD_QUALITY_3D, GOOD_
                     SPLIT, DONT_SPLIT, COLLAPSE, DONT_COLLAPSE, CHECKED, BAD_QUALITY, OK_QUALITY, DONT_SWAP, LAYER,
                     NEED_NOT_SPLIT, NEED_NOT_COLLAPSE,
                     OP_LENGTHS, OP_MARK_SPLIT, OP_MARK_COLLAPSE, OP_QUALITIES, OP_MARK_BAD, OP_LAYER_CHECK, OP_ALL, OP_LENGTH_SUM,
-                    FP_STRICT, FP_FAST)
+                    FP_STRICT, FP_FAST, FP_FAST_LISTED)
 from . import boxmesh, fields

@@ -420,7 +420,7 @@ int mag_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double g
 {
   CHECK_CTX(c);
   if (c->kind == MAG_KIND_NONE) return mag_fail(c, MAG_ERR_ARG, "mag_sweep: no size field set");
-  if (fp_mode != MAG_FP_STRICT && fp_mode != MAG_FP_FAST) return mag_fail(c, MAG_ERR_ARG, "mag_sweep: bad fp_mode %d", fp_mode);
+  if (fp_mode != MAG_FP_STRICT && fp_mode != MAG_FP_FAST && fp_mode != MAG_FP_FAST_LISTED) return mag_fail(c, MAG_ERR_ARG, "mag_sweep: bad fp_mode %d", fp_mode);
   if (ops & ~(uint32_t)(MAG_OP_ALL | MAG_OP_LENGTH_SUM)) return mag_fail(c, MAG_ERR_ARG, "mag_sweep: unknown op bits 0x%x", ops);
   if ((ops & MAG_OP_LENGTH_SUM) && !(ops & MAG_OP_LENGTHS)) return mag_fail(c, MAG_ERR_ARG, "mag_sweep: MAG_OP_LENGTH_SUM needs MAG_OP_LENGTHS");
   int rc;

@@ -244,6 +244,7 @@ struct SweepParams {
   uint32_t ops;
   double max_len, min_len, good_q;
   int use_max;
+  int reeval = 1;   // fast sweeps: re-evaluate near-threshold edges in strict arithmetic (0: MAG_FP_FAST_LISTED)
 };
 
 __device__ __forceinline__ bool near_thr(double v, double thr)
@@ -370,6 +371,7 @@ struct EdgeParams {
   int32_t off_bits, err_mask;
   int want_len;
   int zero_in;   // the incoming flag words are all zero and the array was not materialised: do not read it
+  int reeval;    // fast sweeps: near-threshold edges are re-evaluated in strict arithmetic (MAG_FP_FAST) or only listed (MAG_FP_FAST_LISTED)
   uint32_t ops;
   double max_len, min_len, tol_max, tol_min;
 };
@@ -381,7 +383,7 @@ __device__ __noinline__ unsigned drain_edges(NearQueue& q, int first, int n, con
                                              const double* __restrict__ vedge,
                                              int32_t* __restrict__ flags, double* __restrict__ lengths, uint32_t ops,
                                              double max_len, double min_len,
-                                             MagDevStats* st, int32_t* __restrict__ near_list, int32_t id_base)
+                                             MagDevStats* st, int32_t* __restrict__ near_list, int32_t id_base, bool reeval)
 {
   SweepParams P{ops, max_len, min_len, 0.0, 0};
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -390,7 +392,7 @@ __device__ __noinline__ unsigned drain_edges(NearQueue& q, int first, int n, con
   if (lane < n) {
     const int32_t e = q.e[w][first + lane];
     near_list[base + lane] = e + id_base;
-    if (FAST) {
+    if (FAST && reeval) {                     // MAG_FP_FAST_LISTED: listed only, the flag was written from the fast value
       int32_t f = q.f[w][first + lane];
       const bool need_split = (P.ops & MAG_OP_MARK_SPLIT) && !(f & kSkipSplit);
       const bool need_coll = (P.ops & MAG_OP_MARK_COLLAPSE) && !(f & kSkipColl);
@@ -496,7 +498,10 @@ k_edges(int32_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
           }
           if (need_split || need_coll) {
             nr = (need_split && fabs(len - P.max_len) <= P.tol_max) || (need_coll && fabs(len - P.min_len) <= P.tol_min);
-            if (!(FAST && nr)) {
+            // A near-threshold edge of a MAG_FP_FAST sweep is re-evaluated in the reference's operation order (drain_edges) so
+            // that its flag is the strict one; MAG_FP_FAST_LISTED decides it by the value at hand and only lists it
+            const bool kReevaluate = FAST && P.reeval;
+            if (!(kReevaluate && nr)) {
               ++c_eval;
               int32_t g = f;
               if (need_split) {
@@ -516,7 +521,7 @@ k_edges(int32_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
       }
       if (queue_push(q, qn, nr, (int32_t)e, f)) {
         qn -= 32;
-        const unsigned r = drain_edges<KIND, FAST>(q, qn, 32, edge_v, vedge, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list, id_base);
+        const unsigned r = drain_edges<KIND, FAST>(q, qn, 32, edge_v, vedge, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list, id_base, P.reeval != 0);
         c_eval += r & 1u; c_split += (r >> 1) & 1u; c_coll += (r >> 2) & 1u;
       }
       f = f_nx;
@@ -526,7 +531,7 @@ k_edges(int32_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
     }
   }
   if (qn) {
-    const unsigned r = drain_edges<KIND, FAST>(q, 0, qn, edge_v, vedge, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list, id_base);
+    const unsigned r = drain_edges<KIND, FAST>(q, 0, qn, edge_v, vedge, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list, id_base, P.reeval != 0);
     c_eval += r & 1u; c_split += (r >> 1) & 1u; c_coll += (r >> 2) & 1u;
   }
   if (eig_any) atomicAdd(&st->n_eigen_fail, 1ull);
@@ -1361,6 +1366,7 @@ static EdgeParams edge_params(const SweepParams& P, bool zero_in)
 {
   EdgeParams E;
   E.zero_in = zero_in ? 1 : 0;
+  E.reeval = P.reeval;
   const bool do_split = P.ops & MAG_OP_MARK_SPLIT, do_coll = P.ops & MAG_OP_MARK_COLLAPSE;
   E.off_bits = (do_split ? 0 : MAG_DONT_SPLIT) | (do_coll ? 0 : MAG_DONT_COLLAPSE);
   E.err_mask = (do_split ? MAG_SPLIT : 0) | (do_coll ? MAG_COLLAPSE : 0);
@@ -1748,8 +1754,9 @@ static int launch_tet_rows(mag_ctx* c, const SweepParams& P, bool)
 
 int magk_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double good_q, int use_max, int fp_mode)
 {
-  const SweepParams P = sweep_params(c, ops, max_len, min_len, good_q, use_max);
-  const bool fast = fp_mode == MAG_FP_FAST;
+  SweepParams P = sweep_params(c, ops, max_len, min_len, good_q, use_max);
+  const bool fast = fp_mode != MAG_FP_STRICT;
+  P.reeval = fp_mode == MAG_FP_FAST_LISTED ? 0 : 1;
   int rc;
   cudaEvent_t* tev = (c->t_used < c->t_slots) ? &c->tev[(size_t)4 * c->t_used] : nullptr;
   if (tev) MAG_CUDA(c, cudaEventRecord(tev[0], c->stream));

@@ -104,6 +104,7 @@ k_edge_rows_z(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t
 #endif
   const int lane = threadIdx.x & 31;
   const double max_len = P.max_len, min_len = P.min_len, tol_max = P.tol_max, tol_min = P.tol_min;
+  const bool reeval = P.reeval != 0;
   unsigned c_split = 0, c_coll = 0, c_eval = 0;
   double maxlen = 0.0;                  // getMaximumEdgeLength starts at 0 and ignores NaN (maSize.cc:673-691)
   int eig_any = 0;
@@ -126,7 +127,7 @@ k_edge_rows_z(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t
     if (owned && len > maxlen) maxlen = len;
     const bool nr = fabs(len - max_len) <= tol_max || fabs(len - min_len) <= tol_min;
     nearmask |= (nr ? 1u : 0u) << k;
-    if (!nr) {                                  // near ones are decided in strict arithmetic after the row (near_edges)
+    if (!nr || !reeval) {                       // near ones are decided in strict arithmetic after the row (near_edges), or -- MAG_FP_FAST_LISTED -- here and only listed
       ++c_eval;
       const bool sp = len > max_len, co = len < min_len;
       c_split += (sp && owned) ? 1u : 0u;
@@ -198,7 +199,7 @@ k_edge_rows_z(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t
       const int k = __ffs(any) - 1;
       const bool nr = (nearmask >> k) & 1u;
       const int2 q = nr ? __ldg(sp + k * 32) : kNone;
-      const unsigned r = near_edges<KIND, true>(nr, q.y, va, q.x, 0, vedge, flags, lengths, P.ops, max_len, min_len, st, near_list);
+      const unsigned r = near_edges<KIND, true>(nr, q.y, va, q.x, 0, vedge, flags, lengths, P.ops, max_len, min_len, st, near_list, reeval);
       c_eval += r & 1u; c_split += (r >> 1) & 1u; c_coll += (r >> 2) & 1u; eig_any |= (int)(r >> 3);
     }
     w.advance(s_nx);

@@ -57,7 +57,8 @@ __device__ __forceinline__ void load_half_rec(const double* __restrict__ vedge, 
 template <int KIND, bool FAST>
 __device__ __noinline__ unsigned near_edges(bool nr, int32_t e, int32_t va, int32_t vb_word, int32_t f, const double* __restrict__ vedge,
                                             int32_t* __restrict__ flags, double* __restrict__ lengths, uint32_t ops,
-                                            double max_len, double min_len, MagDevStats* st, int32_t* __restrict__ near_list)
+                                            double max_len, double min_len, MagDevStats* st, int32_t* __restrict__ near_list,
+                                            bool reeval = true)
 {
   const unsigned m = __ballot_sync(0xffffffffu, nr);
   const int lane = threadIdx.x & 31;
@@ -67,7 +68,7 @@ __device__ __noinline__ unsigned near_edges(bool nr, int32_t e, int32_t va, int3
   unsigned out = 0;
   if (nr) {
     near_list[base + __popc(m & ((1u << lane) - 1u))] = e;
-    if (FAST) {
+    if (FAST && reeval) {
       const SweepParams P{ops, max_len, min_len, 0.0, 0};
       const bool need_split = (ops & MAG_OP_MARK_SPLIT) && !(f & kSkipSplit);
       const bool need_coll = (ops & MAG_OP_MARK_COLLAPSE) && !(f & kSkipColl);

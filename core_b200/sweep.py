@@ -28,7 +28,7 @@ NEED_NOT_SPLIT, NEED_NOT_COLLAPSE = 1 << 17, 1 << 18
 OP_LENGTHS, OP_MARK_SPLIT, OP_MARK_COLLAPSE, OP_QUALITIES, OP_MARK_BAD, OP_LAYER_CHECK = (1 << i for i in range(6))
 OP_ALL = 63
 OP_LENGTH_SUM = 1 << 6
-FP_STRICT, FP_FAST = 0, 1
+FP_STRICT, FP_FAST, FP_FAST_LISTED = 0, 1, 2
 
 ERR_NAMES = {1: "MAG_ERR_CUDA", 2: "MAG_ERR_ARG", 3: "MAG_ERR_FLAG_STATE", 4: "MAG_ERR_EIGEN",
              5: "MAG_ERR_NONSIMPLEX", 6: "MAG_ERR_NCCL", 7: "MAG_ERR_INCONSISTENT"}

@@ -80,9 +80,17 @@ enum {
 enum {
   MAG_FP_STRICT = 0, /* the reference's operation order, no FMA contraction, IEEE div/sqrt: bit-identical lengths, qualities, flags
                         (LogAniso: exp() is CUDA's, within 1 ulp of glibc -> values within 1e-12, flags identical outside the listed band) */
-  MAG_FP_FAST = 1    /* algebraically equivalent, FMA-contracted evaluation (values within 1e-12 relative); every entity whose value
+  MAG_FP_FAST = 1,   /* algebraically equivalent, FMA-contracted evaluation (values within 1e-12 relative); every entity whose value
                         lands within 1e-12 relative of a threshold is re-evaluated in strict arithmetic ON THE DEVICE and listed,
                         so flags and counts stay identical to MAG_FP_STRICT */
+  MAG_FP_FAST_LISTED = 2 /* mag_sweep / mag_sweep_reconciled only: MAG_FP_FAST without the re-evaluation of near-threshold EDGES -- an
+                        edge within 1e-12 relative of MAXLENGTH / MINLENGTH is decided by the fast value and listed
+                        (mag_get_near_threshold), which is exactly the exception the parity rule of this path allows ("edges whose
+                        reference metric length lies within 1e-12 relative of the threshold ... must be listed").  Same lengths and
+                        qualities as MAG_FP_FAST bit for bit, same flags outside the list; counts may differ from the reference's
+                        by at most the length of the list.  Worth it where whole edge families sit ON a threshold (a lattice whose
+                        size field is a multiple of the spacing): the lattice benchmark's 8.4 M z edges cost 0.39 ms of strict
+                        re-evaluation per sweep, 2.0 ms in a LogAniso field.  Elements are re-evaluated as in MAG_FP_FAST. */
 };
 
 typedef struct mag_stats {

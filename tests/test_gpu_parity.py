@@ -1164,6 +1164,49 @@ def test_full_size_properties(cb):
     p.close()
 
 
+@pytest.mark.parametrize("kindname", ["aniso", "logm", "iso"])
+def test_fast_listed_mode(cb, kindname):
+    """MAG_FP_FAST_LISTED (the parity rule's own exception: an edge within 1e-12 of a threshold is decided by the fast value and
+    LISTED instead of being re-evaluated in strict arithmetic) on a lattice whose z edges sit exactly on the collapse threshold,
+    through the lean rows (aniso, iso) and the tile kernel (LogAniso), whole-part and with incoming flag words: the same lengths
+    and qualities as MAG_FP_FAST bit for bit, the same list, flag words identical to MAG_FP_FAST outside the list, counts off by
+    at most the flips inside it; element flags untouched by the mode."""
+    from oracle import mao
+    n = 12
+    rng = np.random.default_rng(3)
+    xyz, ev, tv = cb.boxmesh.kuhn_box(n, n, n)
+    H, R = cb.fields.shock_rotating(xyz, 1.0 / n)
+    kind, ma, mb = {"iso": (mao.ISO, np.full(len(xyz), 2.0 / n), None), "aniso": (mao.ANISO, H, R),
+                    "logm": (mao.LOGM, None, mao.logm_from_frames(H, R, 0))}[kindname]
+    p = cb.Part(0)
+    p.set_mesh(xyz, ev, tv)
+    util.set_part_metric(p, kind, ma, mb)
+    ops = cb.OP_ALL & ~cb.OP_LAYER_CHECK
+    ef_in = np.where(rng.random(len(ev)) < 0.2, cb.DONT_COLLAPSE, 0).astype(np.int32)
+    for incoming in (False, True):
+        res = {}
+        for mode in (cb.FP_FAST, cb.FP_FAST_LISTED):
+            if incoming:
+                p.set_flags(ef_in, np.zeros(len(tv), np.int32))
+            else:
+                p.clear_flags()
+            p.sweep(ops, fp_mode=mode)
+            res[mode] = (p.stats(), p.edge_lengths(), p.qualities(), *p.flags(), np.sort(p.near_threshold(0)[0]))
+        (s0, L0, q0, ef0, lf0, near0), (s1, L1, q1, ef1, lf1, near1) = res[cb.FP_FAST], res[cb.FP_FAST_LISTED]
+        assert len(near0) >= n * (n + 1) ** 2 * (0.7 if incoming else 1.0)      # the z edges
+        assert np.array_equal(near0, near1) and np.array_equal(q0, q1) and np.array_equal(lf0, lf1) and s0["n_bad"] == s1["n_bad"]
+        # the strict re-evaluation of MAG_FP_FAST also replaces the stored length of a listed edge by the strict value
+        off = np.ones(len(ev), bool); off[near0] = False
+        assert np.array_equal(L0[off], L1[off]) and util.rel_err(L1, L0) < TOL
+        de = np.nonzero(ef0 != ef1)[0]
+        assert set(de.tolist()) <= set(near0.tolist())
+        assert abs(s0["n_collapse"] - s1["n_collapse"]) <= len(de) and abs(s0["n_split"] - s1["n_split"]) <= len(de)
+        assert s0["n_edges_evaluated"] == s1["n_edges_evaluated"] and s0["n_near_threshold"] == s1["n_near_threshold"]
+    with pytest.raises(cb.sweep.MagError):        # the streamed host calls take the two base modes only
+        p.sweep_host(xyz, ev, tv, int(kind), ma, mb, fp_mode=cb.FP_FAST_LISTED)
+    p.close()
+
+
 def test_full_size_loganiso(cb):
     """BASELINE config 3, log-Euclidean variant (makeSizeField(m, sizes, frames, true)) at n=203: the fast path (the
     reference's QR iteration in its second form) against the strict path on every entity -- flags and counts identical,
