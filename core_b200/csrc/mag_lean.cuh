@@ -182,6 +182,16 @@ k_edge_rows_z(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t
       }
       int2 s2 = kNone, s3 = kNone;
       if (k + 2 < K) s2 = ld_stream(sp + (k + 2) * 32);
+#if MAG_SLOT_PREFETCH_E
+      {  // two rows (this iteration's worth) of slot words, MAG_SLOT_PREFETCH_E rows ahead: in this slice, or the first rows of the next
+        const int kp = k + MAG_SLOT_PREFETCH_E;
+        if (kp + 1 < K) { if (lane < 4) prefetch_l2(reinterpret_cast<const char*>(sp - lane + kp * 32) + lane * 128); }
+        else {
+          const int kq = kp - K < 0 ? 0 : kp - K;
+          if (s_nx < nslices && off_nx + (kq + 2) * 32 <= off1_nx && lane < 4) prefetch_l2(reinterpret_cast<const char*>(slots + off_nx + kq * 32) + lane * 128);
+        }
+      }
+#endif
       if (s1.y >= 0) load_half_rec<KIND>(vedge, s1.x & kVidMask, b1);
       item(s0, k, a, b0, nearmask);
       if (k + 3 < K) s3 = ld_stream(sp + (k + 3) * 32);
@@ -298,6 +308,16 @@ k_tet_rows_z(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t*
       }
       int4 s2 = kNone, s3 = kNone;
       if (k + 2 < K) s2 = ld_stream(sp + (k + 2) * 32);
+#if MAG_SLOT_PREFETCH_T
+      {  // two rows of slot words (2 x 512 bytes), MAG_SLOT_PREFETCH_T rows ahead
+        const int kp = k + MAG_SLOT_PREFETCH_T;
+        if (kp + 1 < K) { if (lane < 8) prefetch_l2(reinterpret_cast<const char*>(sp - lane + kp * 32) + lane * 128); }
+        else {
+          const int kq = kp - K < 0 ? 0 : kp - K;
+          if (s_nx < nslices && off_nx + (kq + 2) * 32 <= off1_nx && lane < 8) prefetch_l2(reinterpret_cast<const char*>(slots + off_nx + kq * 32) + lane * 128);
+        }
+      }
+#endif
       if (s1.w >= 0) load_pos(s1, p1);
       item(s0, k, va, a_xy, a_zd, p0, nearmask);
       if (k + 3 < K) s3 = ld_stream(sp + (k + 3) * 32);

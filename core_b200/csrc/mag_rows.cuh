@@ -33,14 +33,36 @@ constexpr int kRowWindowLog2 = 11;   // rows are sorted by length inside windows
 #define MAG_EROW_BLOCKS_LOGM 2
 #endif
 // lane 0 draws a ticket from an atomic counter; the value is broadcast (and thereby waited for) only where it is needed
+// (PTX atomic: nvcc turns atomicAdd under `lane == 0` into its warp-aggregated form -- vote, ATOMG, and a SHFL that broadcasts the
+//  result AT ONCE, i.e. the warp waits ~1 us for every ticket it meant to draw ahead of time: 6 % of the edge kernel's warp time
+//  in the r2f profile.  Written as PTX the result stays in lane 0's register until GroupWalk::next_slice shuffles it.)
+#ifndef MAG_TICKET_PTX
+#define MAG_TICKET_PTX 1
+#endif
 struct SliceWalk {
   static __device__ __forceinline__ int issue(unsigned long long* counter)
   {
     unsigned long long t = 0;
+#if MAG_TICKET_PTX
+    if ((threadIdx.x & 31) == 0) asm volatile("atom.global.add.u64 %0, [%1], 1;" : "=l"(t) : "l"(counter) : "memory");
+#else
     if ((threadIdx.x & 31) == 0) t = atomicAdd(counter, 1ull);
+#endif
     return (int)t;
   }
 };
+// the slot words are the one stream of these kernels that comes straight from DRAM, a row (256 / 512 bytes) at a time; they
+// are loaded one row before the gather they address is issued, and a DRAM access under load takes longer than a row (r2f
+// profile: 15 % of the warp time of both kernels is spent waiting for a slot word).  Rows further ahead are pulled into L2.
+#ifndef MAG_SLOT_PREFETCH_E
+#define MAG_SLOT_PREFETCH_E 3   /* edges: rows ahead; 0 = off.  r2t / r2u (jittered / lattice): off 0.846 / 1.235 ms, 2: 0.846 / 1.220, 3: 0.786 / 1.173, 4: 0.844 / 1.237, 6: 0.830 / 1.223, 10: 0.843 / 1.238 */
+#endif
+#ifndef MAG_SLOT_PREFETCH_T
+#define MAG_SLOT_PREFETCH_T 0   /* tets: 0.855 / 0.784 ms off, 3: 0.891 / 0.806, 6: 0.866 / 0.781 -- the slot wait only gives way to the wait for the winner's transform */
+#endif
+// (an L2 prefetch of the other-end RECORDS two rows before their gather, every eighth lane asking for its lines, was measured
+//  too, r2u: 0.826 - 0.831 ms against 0.786 without it)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int KIND>
 __device__ __forceinline__ void load_half_rec(const double* __restrict__ vedge, int32_t v, double* r)
