@@ -160,6 +160,8 @@ int mag_create(mag_ctx** out, int device)
   c->trows = c->erows;
   { const char* e = getenv("MAG_LEGACY_SWEEP"); c->legacy_sweep = e && e[0] == '1'; }
   { const char* e = getenv("MAG_LEAN_SWEEP"); c->lean_sweep = !(e && e[0] == '0'); }
+  { const char* e = getenv("MAG_TET_WINNER"); c->tet_winner = !(e && e[0] == '0'); }
+  c->winners_valid = false;
   c->d_vstat = nullptr;
   c->s_comm = nullptr; c->ev_comm[0] = c->ev_comm[1] = nullptr; c->comm_pending = false; c->overlap_mask = 0;
   c->d_edge_bytes = c->d_elem_bytes = nullptr;
@@ -536,6 +538,9 @@ int mag_get_row_layout(mag_ctx* c, int which, int64_t* counts, int32_t* anchor, 
   if (slice_off && r.n_slices && (rc = download(c, slice_off, r.d_slice_off, (size_t)r.n_slices + 1))) return rc;
   if (slots && (rc = download(c, slots, r.d_slots, (size_t)r.n_slots * (which ? 4 : 2)))) return rc;
   MAG_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (slots && which == 1 && c->winners_valid)      // bits 29-30 of a tet slot's index hold its max-Jacobian vertex (mag_lean.cuh)
+    for (int64_t i = 0; i < r.n_slots; ++i)
+      if (slots[4 * i + 3] >= 0) slots[4 * i + 3] &= (1 << 29) - 1;
   return MAG_OK;
 }
 

@@ -109,6 +109,8 @@ struct mag_ctx {
   int32_t* d_tet_order;
   bool lean_sweep;       // MAG_LEAN_SWEEP=0: never use the lean kernels of mag_lean.cuh (A/B measurements, tests)
   MagRows erows, trows;  // anchor-row layout of the edges / tets (whole-part sweeps)
+  bool tet_winner;       // MAG_TET_WINNER=0: the tet rows keep the dependent gather of round-2f (A/B measurements); default on
+  bool winners_valid;    // the slot words of trows carry the max-Jacobian vertex of their tet (bits 29-30) for the current det Q_v
   bool legacy_sweep;     // MAG_LEGACY_SWEEP=1: whole-part sweeps run the round-1 tile kernels (A/B measurements)
   // (vertex pair) -> edge index hash table of mag_reset_layer (mag_layer.cu); pair_bits = 0: not built
   unsigned long long* d_pair_keys;

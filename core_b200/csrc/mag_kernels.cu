@@ -1314,6 +1314,7 @@ int magk_init_stats(mag_ctx* c)
 // cavity batch and sliver classification until the next change; eigen-solver failures are kept in c->d_vstat.
 int magk_vertex_pass(mag_ctx* c)
 {
+  c->winners_valid = false;     // det Q_v is about to change: the winner bits of the tet slots (k_tet_winners) go with it
   if (c->nv == 0) return MAG_OK;
   MAG_CUDA(c, cudaMemsetAsync(c->d_vstat, 0, sizeof(unsigned long long), c->stream));
   unsigned g = grid_for(c->nv);
@@ -1590,6 +1591,7 @@ template <int NV>
 static int build_rows(mag_ctx* c, int64_t n, const int32_t* d_conn, MagRows& rows)
 {
   free_rows(rows, c->stream);
+  if (NV == 4) c->winners_valid = false;
   if (n == 0 || c->nv == 0) { rows.valid = true; return MAG_OK; }
   const int64_t nv = c->nv;
   Scratch S(c->stream);
@@ -1734,6 +1736,40 @@ static int launch_tet_rows_z(mag_ctx* c, const SweepParams& P)
   return MAG_OK;
 }
 
+// the winner-in-slot tet kernel: the max-Jacobian vertex of every tet, written into its slot word after the per-vertex pass
+static bool tet_winner_ok(const mag_ctx* c) { return c->tet_winner && c->dim == 3 && c->nt < ((int64_t)1 << kWinShift); }
+static int ensure_tet_winners(mag_ctx* c)
+{
+  if (c->winners_valid) return MAG_OK;
+  if (c->trows.n_slices) {
+    k_tet_winners<<<grid_for(c->trows.n_slices * 32), kThreads, 0, c->stream>>>((int32_t)c->trows.n_slices, c->trows.d_anchor, c->trows.d_slice_off,
+                                                                               reinterpret_cast<int4*>(c->trows.d_slots), c->d_vpos);
+    MAG_CUDA(c, cudaGetLastError());
+    c->n_launches++;
+  }
+  c->winners_valid = true;
+  return MAG_OK;
+}
+template <int KIND>
+static int launch_tet_rows_w(mag_ctx* c, const SweepParams& P)
+{
+  int rc = ensure_tet_winners(c);
+  if (rc) return rc;
+  constexpr int T = MAG_TZ_THREADS;
+  const int per_sm = blocks_per_sm(c, (const void*)k_tet_rows_w<KIND>, T);
+  int64_t g = (int64_t)per_sm * c->n_sms;
+  const int64_t groups = (c->trows.n_slices + kTZGroup - 1) / kTZGroup;
+  const int64_t need = (groups + T / 32 - 1) / (T / 32);
+  if (g > need) g = need;
+  k_tet_rows_w<KIND><<<(unsigned)(g < 1 ? 1 : g), T, 0, c->stream>>>(
+      (int32_t)c->trows.n_slices, c->trows.d_anchor, c->trows.d_slice_off, reinterpret_cast<const int4*>(c->trows.d_slots),
+      (int32_t)(c->np + c->npy), c->nv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_flags, c->d_qual, tet_params(P, true),
+      c->d_stats, c->d_near_elem);
+  MAG_CUDA(c, cudaGetLastError());
+  c->n_launches++;
+  return MAG_OK;
+}
+
 static int launch_edge_rows(mag_ctx* c, const SweepParams& P, bool)
 {
   switch (c->kind) {
@@ -1744,6 +1780,14 @@ static int launch_edge_rows(mag_ctx* c, const SweepParams& P, bool)
 }
 static int launch_tet_rows(mag_ctx* c, const SweepParams& P, bool)
 {
+  if (tet_winner_ok(c)) {
+    switch (c->kind) {
+      case MAG_KIND_IDENTITY: return launch_tet_rows_w<MAG_KIND_IDENTITY>(c, P);
+      case MAG_KIND_ISO: return launch_tet_rows_w<MAG_KIND_ISO>(c, P);
+      case MAG_KIND_ANISO: return launch_tet_rows_w<MAG_KIND_ANISO>(c, P);
+      default: return launch_tet_rows_w<MAG_KIND_LOGM>(c, P);
+    }
+  }
   switch (c->kind) {
     case MAG_KIND_IDENTITY: return launch_tet_rows_z<MAG_KIND_IDENTITY>(c, P);
     case MAG_KIND_ISO: return launch_tet_rows_z<MAG_KIND_ISO>(c, P);

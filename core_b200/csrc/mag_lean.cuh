@@ -348,3 +348,172 @@ k_tet_rows_z(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t*
   const unsigned long long m = warp_min_u64(minkey);
   if (lane == 0 && m != ~0ull) atomicMin(&st->min_q_key, m);
 }
+
+// ------------------------------------------------------------------ tets, winner known from the slot word
+// r2f / r2t profiles of k_tet_rows_z: 55 % of the warp time is "long scoreboard", and the largest single place is the first use
+// of the winner's transform -- getMetricWithMaxJacobean (maQuality.cc:83-108) picks the vertex AFTER the four det Q_v have
+// arrived, so the gather of its 80-byte transform starts when the row is already being evaluated.  Which vertex wins depends on
+// the size field and the connectivity only, like det Q_v itself: k_tet_winners writes it (2 bits) into the slot word of every
+// tet whenever the per-vertex pass has run (mag_set_metric_* / mag_set_coords), with the reference's own rule (strict >, first
+// wins).  Here the slot word, read two rows ahead, names the winner, and its transform travels one row ahead like the
+// coordinates: by cp.async into a per-warp shared-memory stage (no registers are held in flight; a lane whose winner is the
+// previous row's keeps the registers it has), read back with conflict-free LDS.128 when the row is evaluated.
+constexpr int kWinShift = 29;                      // slot.w = tet index | winner << 29 (k_tet_winners); parts of 2^29 tets or more use k_tet_rows_z
+constexpr int32_t kTidMask = (1 << kWinShift) - 1;
+__global__ void __launch_bounds__(kThreads)
+k_tet_winners(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t* __restrict__ slice_off, int4* __restrict__ slots,
+              const double* __restrict__ vpos)
+{
+  const int64_t s = (blockIdx.x * (int64_t)kThreads + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (s >= nslices) return;
+  const int off = slice_off[s], K = (slice_off[s + 1] - off) >> 5;
+  const int32_t va = anchor[(s << 5) + lane];
+  const double d0 = va >= 0 ? __ldg(chunk_ptr<2>(vpos, 1, va)).y : 0.0;
+  for (int k = 0; k < K; ++k) {
+    int4* p = slots + off + 32 * k + lane;
+    const int4 sl = *p;
+    if (sl.w < 0) continue;
+    const double d1 = __ldg(chunk_ptr<2>(vpos, 1, sl.x & kVidMask)).y, d2 = __ldg(chunk_ptr<2>(vpos, 1, sl.y)).y,
+                 d3 = __ldg(chunk_ptr<2>(vpos, 1, sl.z)).y;
+    const int32_t w = best_vertex(make_int4(0, 1, 2, 3), d0, d1, d2, d3);
+    p->w = (sl.w & kTidMask) | (w << kWinShift);
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(MAG_TZ_THREADS, MAG_TZ_BLOCKS)
+k_tet_rows_w(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t* __restrict__ slice_off, const int4* __restrict__ slots,
+             int32_t elem_off, int64_t nv, const double* __restrict__ vpos, const double* __restrict__ vq, const double* __restrict__ vedge,
+             int32_t* __restrict__ flags, double* __restrict__ qual, TetParams P, MagDevStats* st, int32_t* __restrict__ near_list)
+{
+  __shared__ double2 sh_q[MAG_TZ_THREADS / 32][2][5][32];       // the winner's transform of the row in flight / being evaluated
+  const int lane = threadIdx.x & 31;
+  double2 (*stage)[5][32] = sh_q[threadIdx.x >> 5];
+  const double good_q = P.good_q, tol_q = P.tol_q;
+  unsigned c_bad = 0, c_eval = 0;
+  unsigned long long minkey = ~0ull;
+  int eig_any = 0;
+  flags += elem_off;
+  qual += elem_off;
+  const int4 kNone = make_int4(0, 0, 0, -1);
+  M3 Q;
+  int32_t q_of = -1;                              // vertex whose transform Q holds
+  int32_t q_sent = -1;                            // winner of the row whose transform was requested last
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Q.m[i / 3][i % 3] = 0.0;
+  auto winner = [&](const int4& sl, const int32_t va) -> int32_t {
+    const int w = (sl.w >> kWinShift) & 3;
+    return w == 0 ? va : (w == 1 ? (sl.x & kVidMask) : (w == 2 ? sl.y : sl.z));
+  };
+  auto load_pos = [&](const int4& sl, double2* p) {   // p[0..5] = xy, z. of o1, o2, o3
+    const int32_t v1 = sl.x & kVidMask;
+    p[0] = __ldg(chunk_ptr<2>(vpos, 0, v1)); p[1] = __ldg(chunk_ptr<2>(vpos, 1, v1));
+    p[2] = __ldg(chunk_ptr<2>(vpos, 0, sl.y)); p[3] = __ldg(chunk_ptr<2>(vpos, 1, sl.y));
+    p[4] = __ldg(chunk_ptr<2>(vpos, 0, sl.z)); p[5] = __ldg(chunk_ptr<2>(vpos, 1, sl.z));
+  };
+  // one row's requests: coordinates into registers, the winner's transform into stage[buf] unless the previous row asked for the same
+  auto request = [&](const int4& sl, const int32_t va, double2* p, const int buf) {
+    if (sl.w >= 0) {
+      load_pos(sl, p);
+      const int32_t vb = winner(sl, va);
+      if (vb != q_sent) {
+        const double2* src = chunk_ptr<5>(vq, 0, vb);
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(&stage[buf][i][lane])), "l"(src + i * kVB) : "memory");
+        q_sent = vb;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto item = [&](const int4 sl, const int k, const int32_t va, const double2 a_xy, const double2 a_zd, const double2* __restrict__ p,
+                  const int buf, unsigned& nearmask) {
+    const int t = sl.w & kTidMask;
+    if (sl.w < 0) return;
+    const int32_t vb = winner(sl, va);
+    if (vb != q_of) {
+      const double2 q0 = stage[buf][0][lane], q1 = stage[buf][1][lane], q2 = stage[buf][2][lane], q3 = stage[buf][3][lane], q4 = stage[buf][4][lane];
+      Q.m[0][0] = q0.x; Q.m[0][1] = q0.y; Q.m[0][2] = q1.x;
+      Q.m[1][0] = q1.y; Q.m[1][1] = q2.x; Q.m[1][2] = q2.y;
+      Q.m[2][0] = q3.x; Q.m[2][1] = q3.y; Q.m[2][2] = q4.x;
+      q_of = vb;
+    }
+    const V3 x[4] = {V3{a_xy.x, a_xy.y, a_zd.x}, V3{p[0].x, p[0].y, p[1].x}, V3{p[2].x, p[2].y, p[3].x}, V3{p[4].x, p[4].y, p[5].x}};
+    const double qv = magfa::tet_quality(x, Q, 0.0);
+    st_stream(qual + t, qv);
+    const unsigned long long kq = dkey(qv);
+    minkey = kq < minkey ? kq : minkey;
+    const bool nr = fabs(qv - good_q) <= tol_q;
+    nearmask |= (nr ? 1u : 0u) << k;
+    if (!nr) {
+      ++c_eval;
+      const bool bad = qv < good_q;
+      c_bad += (bad && sl.x >= 0) ? 1u : 0u;
+      st_stream(flags + t, (int32_t)(bad ? MAG_BAD_QUALITY : MAG_OK_QUALITY));
+    }
+  };
+  GroupWalk<kTZGroup> w;
+  w.begin(&st->elem_chunk, nslices);
+  int off = 0, off1 = 0, va = -1;
+  int4 s0 = kNone, s1 = kNone;
+  if (w.s < nslices) {
+    off = __ldg(slice_off + w.s); off1 = __ldg(slice_off + w.s + 1); va = __ldg(anchor + (w.s << 5) + lane);
+    s0 = ld_stream(slots + off + lane);
+    if (off1 - off > 32) s1 = ld_stream(slots + off + lane + 32);
+  }
+  while (w.s < nslices) {
+    const int s_nx = w.next_slice(&st->elem_chunk, nslices);
+    int off_nx = 0, off1_nx = 0, va_nx = -1;
+    if (s_nx < nslices) { off_nx = __ldg(slice_off + s_nx); off1_nx = __ldg(slice_off + s_nx + 1); va_nx = __ldg(anchor + (s_nx << 5) + lane); }
+    const int K = (off1 - off) >> 5;
+    const int4* sp = slots + off + lane;
+    double2 a_xy = make_double2(0.0, 0.0), a_zd = a_xy, p0[6], p1[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { p0[i] = make_double2(0.0, 0.0); p1[i] = p0[i]; }
+    if (va >= 0) { a_xy = __ldg(chunk_ptr<2>(vpos, 0, va)); a_zd = __ldg(chunk_ptr<2>(vpos, 1, va)); }
+    request(s0, va, p0, 0);
+    int4 n0 = kNone, n1 = kNone;
+    bool have_next = false;
+    unsigned nearmask = 0;
+    for (int k = 0; k < K; k += 2) {
+      if (k == 2 && s_nx < nslices) {
+        n0 = ld_stream(slots + off_nx + lane);
+        if (off1_nx - off_nx > 32) n1 = ld_stream(slots + off_nx + lane + 32);
+        have_next = true;
+      }
+      int4 s2 = kNone, s3 = kNone;
+      if (k + 2 < K) s2 = ld_stream(sp + (k + 2) * 32);
+      request(s1, va, p1, 1);                                    // row k + 1 (an empty request past the end of the slice)
+      asm volatile("cp.async.wait_group 1;" ::: "memory");      // row k's transform has landed
+      item(s0, k, va, a_xy, a_zd, p0, 0, nearmask);
+      if (k + 3 < K) s3 = ld_stream(sp + (k + 3) * 32);
+      request(s2, va, p0, 0);                                    // row k + 2
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      item(s1, k + 1, va, a_xy, a_zd, p1, 1, nearmask);
+      s0 = s2;
+      s1 = s3;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");        // (only empty requests are left)
+    if (!have_next && s_nx < nslices) {
+      n0 = ld_stream(slots + off_nx + lane);
+      if (off1_nx - off_nx > 32) n1 = ld_stream(slots + off_nx + lane + 32);
+    }
+    for (unsigned any = __reduce_or_sync(0xffffffffu, nearmask); any; any &= any - 1) {
+      const int k = __ffs(any) - 1;
+      const bool nr = (nearmask >> k) & 1u;
+      const int4 q = nr ? __ldg(sp + k * 32) : kNone;
+      const unsigned r = near_tets<KIND, true>(nr, q.w & kTidMask, elem_off, make_int4(va, q.x, q.y, q.z), 0, nv, vpos, vq, vedge, flags - elem_off,
+                                               qual - elem_off, P.ops, good_q, P.use_max, st, near_list);
+      c_eval += r & 1u; c_bad += (r >> 1) & 1u; eig_any |= (int)(r >> 2);
+    }
+    w.advance(s_nx);
+    off = off_nx; off1 = off1_nx; va = va_nx;
+    s0 = n0; s1 = n1;
+  }
+  if (eig_any) atomicAdd(&st->n_eigen_fail, 1ull);
+  warp_count_to(c_bad, &st->n_bad);
+  warp_count_to(c_eval, &st->n_elems_eval);
+  const unsigned long long m = warp_min_u64(minkey);
+  if (lane == 0 && m != ~0ull) atomicMin(&st->min_q_key, m);
+}

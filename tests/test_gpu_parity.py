@@ -1052,7 +1052,8 @@ def test_lean_kernels_equal_general(cb, kindname, mesh):
     lo = (rng.random(len(tv)) < 0.9).astype(np.uint8)
     ops = cb.OP_ALL & ~cb.OP_LAYER_CHECK
     res = []
-    for env in ({}, {"MAG_LEAN_SWEEP": "0"}, {"MAG_LEGACY_SWEEP": "1"}):
+    # lean rows (tets: winner-in-slot kernel); lean rows with the dependent gather of the max-Jacobian transform; general rows; tiles
+    for env in ({}, {"MAG_TET_WINNER": "0"}, {"MAG_LEAN_SWEEP": "0"}, {"MAG_LEGACY_SWEEP": "1"}):
         p = _part_with_env(cb, env)
         p.set_mesh(xyz, ev, tv, edge_owned=eo, elem_owned=lo)
         util.set_part_metric(p, kind, ma, mb)
