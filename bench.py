@@ -344,7 +344,8 @@ def _kernel_names(cb, field, fp, legacy):
     tiles = "k_edges<%d, %d, 0>" % (kind, fast), "k_tets<%d, %d, 1>" % (kind, fast)
     if legacy or not fast:
         return tiles
-    return (tiles[0] if field == "logm" else "k_edge_rows_z<%d>" % kind), "k_tet_rows_z<%d>" % kind
+    tet = "k_tet_rows_z<%d>" % kind if os.environ.get("MAG_TET_WINNER") == "0" else "k_tet_rows_w<%d>" % kind
+    return (tiles[0] if field == "logm" else "k_edge_rows_z<%d>" % kind), tet
 
 
 def _roofline(r, nv, ne, nt, field, fp, n, world, jitter):
