@@ -285,6 +285,15 @@ int magi_reshape(mag_ctx* c, int dim, int64_t nv, int64_t ne, int64_t nt, int64_
   return MAG_OK;
 }
 
+// the edge words only (the part-boundary exchange works on them while the element kernel still wants to see "all zero, not
+// materialised" for the element words: otherwise a multi-part sweep falls back from the lean tet kernel to the tiles)
+int magi_materialize_edge_flags(mag_ctx* c)
+{
+  if (c->edge_flags_zero && c->ne) MAG_CUDA(c, cudaMemsetAsync(c->d_edge_flags, 0, (size_t)c->ne * 4, c->stream));
+  c->edge_flags_zero = false;
+  return MAG_OK;
+}
+
 int magi_materialize_flags(mag_ctx* c)
 {
   if (c->edge_flags_zero && c->ne) MAG_CUDA(c, cudaMemsetAsync(c->d_edge_flags, 0, (size_t)c->ne * 4, c->stream));

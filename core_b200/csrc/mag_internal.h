@@ -154,6 +154,7 @@ extern "C" {
 int magi_reshape(mag_ctx* c, int dim, int64_t nv, int64_t ne, int64_t nt, int64_t np, int64_t npy, int64_t ntri,
                  bool has_edge_owned, bool has_elem_owned);
 int magi_materialize_flags(mag_ctx* c);
+int magi_materialize_edge_flags(mag_ctx* c);
 int magi_reserve_metric(mag_ctx* c, int kind, size_t na, size_t nb);
 }
 void magl_free_pairs(mag_ctx* c);

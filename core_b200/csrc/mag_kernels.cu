@@ -1701,6 +1701,17 @@ static bool use_tet_rows(const mag_ctx* c, const SweepParams& P, bool fast)
   return !c->legacy_sweep && lean_tets_ok(c, P, fast);
 }
 
+// mag_sweep_reconciled runs the part-boundary exchange of the edge marks on a side stream under the element kernel.  A
+// persistent element kernel that fills every SM (2 CTAs x 128 registers x 256 threads = the whole register file) leaves no SM
+// on which the pack / NCCL / merge kernels of the exchange could start, so the "overlapped" exchange ran AFTER the element
+// kernel (r2z, 8 GPUs: element phase 0.82 ms for a 0.67 ms kernel).  A few CTAs fewer leave half-empty SMs for it.
+static int64_t overlap_reserve(const mag_ctx* c, int64_t g)
+{
+  if (!c->comm_pending) return 0;
+  const int64_t r = c->n_sms / 16 > 4 ? c->n_sms / 16 : 4;
+  return g > 4 * r ? r : 0;
+}
+
 // the lean kernels (mag_lean.cuh): MAG_FP_FAST sweeps over all-zero incoming flag words
 template <int KIND>
 static int launch_edge_rows_z(mag_ctx* c, const SweepParams& P)
@@ -1727,6 +1738,7 @@ static int launch_tet_rows_z(mag_ctx* c, const SweepParams& P)
   const int64_t groups = (c->trows.n_slices + kTZGroup - 1) / kTZGroup;
   const int64_t need = (groups + T / 32 - 1) / (T / 32);
   if (g > need) g = need;
+  g -= overlap_reserve(c, g);
   k_tet_rows_z<KIND><<<(unsigned)(g < 1 ? 1 : g), T, 0, c->stream>>>(
       (int32_t)c->trows.n_slices, c->trows.d_anchor, c->trows.d_slice_off, reinterpret_cast<const int4*>(c->trows.d_slots),
       (int32_t)(c->np + c->npy), c->nv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_flags, c->d_qual, tet_params(P, true),
@@ -1761,6 +1773,7 @@ static int launch_tet_rows_w(mag_ctx* c, const SweepParams& P)
   const int64_t groups = (c->trows.n_slices + kTZGroup - 1) / kTZGroup;
   const int64_t need = (groups + T / 32 - 1) / (T / 32);
   if (g > need) g = need;
+  g -= overlap_reserve(c, g);
   k_tet_rows_w<KIND><<<(unsigned)(g < 1 ? 1 : g), T, 0, c->stream>>>(
       (int32_t)c->trows.n_slices, c->trows.d_anchor, c->trows.d_slice_off, reinterpret_cast<const int4*>(c->trows.d_slots),
       (int32_t)(c->np + c->npy), c->nv, c->d_vpos, c->d_vq, c->d_vedge, c->d_elem_flags, c->d_qual, tet_params(P, true),
