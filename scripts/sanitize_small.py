@@ -47,10 +47,20 @@ oe, ol = np.empty(len(ev), np.int32), np.empty(len(tv), np.int32)
 p.sweep_host(xyz, ev, tv, 2, h, R, edge_flags=ef, elem_flags=lf, edge_owned=eo, elem_owned=lo, out_lengths=oL, out_qualities=oq,
              out_edge_flags=oe, out_elem_flags=ol, fp_mode=cb.FP_FAST, slice_entities=61440)
 p.clear_flags(); p.sweep(cb.OP_ALL & ~cb.OP_LAYER_CHECK, fp_mode=cb.FP_FAST); p.stats()
+# round 2: the winner-in-slot tet kernel (cp.async stage) after a field change and after new coordinates, the listed-only fast
+# mode, edge-collapse candidates over the device-built vertex -> tet incidence (both ends of every 7th edge)
+p.set_size_field_aniso(h * 1.5, R); p.clear_flags(); p.sweep(cb.OP_ALL & ~cb.OP_LAYER_CHECK, fp_mode=cb.FP_FAST); p.stats()
+p.set_coords(xyz * 1.01); p.clear_flags(); p.sweep(cb.OP_ALL & ~cb.OP_LAYER_CHECK, fp_mode=cb.FP_FAST_LISTED); p.stats(); p.row_layout(1)
+ce = np.arange(0, len(ev), 7, dtype=np.int32)
+for mode in (cb.FP_STRICT, cb.FP_FAST):
+    p.collapse_quality(np.concatenate([ce, ce]), np.concatenate([np.zeros(len(ce), np.uint8), np.ones(len(ce), np.uint8)]), fp_mode=mode)
 x2, e2, t2, pr2 = cb.boxmesh.mixed_box(5, 2)
 ef2, lf2 = cb.boxmesh.layer_closure_flags(e2, pr2, None, len(t2))
 h2, R2 = cb.fields.shock_rotating(x2, 0.2)
 p.set_mesh(x2, e2, t2, prism_v=pr2); p.set_size_field_aniso(h2, R2); p.set_flags(ef2, lf2); p.sweep(cb.OP_ALL, fp_mode=cb.FP_FAST); p.stats(); p.layer_ok()
+# round 2: layer prisms weighed by their base triangle, the device LAYER closure, the listed-only fast mode on a mixed part
+p.prism_weights(np.ascontiguousarray(pr2[:, :3]), fp_mode=cb.FP_STRICT); p.prism_weights(np.ascontiguousarray(pr2[:, :3]), 0, 1, False, False, True, fp_mode=cb.FP_FAST)
+p.clear_flags(); p.reset_layer(); p.sweep(cb.OP_ALL, fp_mode=cb.FP_FAST_LISTED); p.stats()
 x3, e3, tr3 = cb.boxmesh.tri_box(9, 7)
 h3, R3 = cb.fields.shock_rotating(x3, 1.0 / 8)
 p.set_mesh_2d(x3, e3, tr3); p.set_size_field_aniso(h3, R3)
