@@ -1312,6 +1312,7 @@ int magk_init_stats(mag_ctx* c)
 // Q_v and det Q_v of every vertex (strict arithmetic in both modes).  They depend on the coordinates and the size field
 // only, so they are computed when either changes (repack in mag_api.cu, mag_sweep_host) and reused by every sweep,
 // cavity batch and sliver classification until the next change; eigen-solver failures are kept in c->d_vstat.
+int magk_tet_winners(mag_ctx* c);
 int magk_vertex_pass(mag_ctx* c)
 {
   c->winners_valid = false;     // det Q_v is about to change: the winner bits of the tet slots (k_tet_winners) go with it
@@ -1328,7 +1329,8 @@ int magk_vertex_pass(mag_ctx* c)
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;
   c->vertex_pass_valid = true;
-  return MAG_OK;
+  // the winner bits of the tet slots follow det Q_v (a no-op until the row layout exists; launch_tet_rows_w checks again)
+  return magk_tet_winners(c);
 }
 
 template <int KIND>
@@ -1671,7 +1673,7 @@ int magk_build_schedule(mag_ctx* c)
   if (c->legacy_sweep) return MAG_OK;
   if ((rc = build_rows<2>(c, c->ne, c->d_edge_v, c->erows))) return rc;
   if ((rc = build_rows<4>(c, c->nt, c->d_tet_v, c->trows))) return rc;
-  return MAG_OK;
+  return magk_tet_winners(c);      // (a no-op until the per-vertex pass has run)
 }
 
 // ---- whole-part sweeps over the anchor rows
@@ -1750,9 +1752,9 @@ static int launch_tet_rows_z(mag_ctx* c, const SweepParams& P)
 
 // the winner-in-slot tet kernel: the max-Jacobian vertex of every tet, written into its slot word after the per-vertex pass
 static bool tet_winner_ok(const mag_ctx* c) { return c->tet_winner && c->dim == 3 && c->nt < ((int64_t)1 << kWinShift); }
-static int ensure_tet_winners(mag_ctx* c)
+int magk_tet_winners(mag_ctx* c)
 {
-  if (c->winners_valid) return MAG_OK;
+  if (c->winners_valid || !tet_winner_ok(c) || c->legacy_sweep || !c->trows.valid || !c->vertex_pass_valid) return MAG_OK;
   if (c->trows.n_slices) {
     k_tet_winners<<<grid_for(c->trows.n_slices * 32), kThreads, 0, c->stream>>>((int32_t)c->trows.n_slices, c->trows.d_anchor, c->trows.d_slice_off,
                                                                                reinterpret_cast<int4*>(c->trows.d_slots), c->d_vpos);
@@ -1765,8 +1767,9 @@ static int ensure_tet_winners(mag_ctx* c)
 template <int KIND>
 static int launch_tet_rows_w(mag_ctx* c, const SweepParams& P)
 {
-  int rc = ensure_tet_winners(c);
+  int rc = magk_tet_winners(c);
   if (rc) return rc;
+  if (!c->winners_valid) return mag_fail(c, MAG_ERR_ARG, "internal: tet winners not in place (rows %d, vertex pass %d)", (int)c->trows.valid, (int)c->vertex_pass_valid);
   constexpr int T = MAG_TZ_THREADS;
   const int per_sm = blocks_per_sm(c, (const void*)k_tet_rows_w<KIND>, T);
   int64_t g = (int64_t)per_sm * c->n_sms;

@@ -882,6 +882,51 @@ def test_two_parts_one_gpu_partition_invariance(cb):
     assert abs(mx - want["max_length"]) <= TOL * mx and abs(mn - want["min_quality"]) <= TOL * abs(mn)
 
 
+def test_eight_parts_counts_equal_the_one_part_sweep(cb):
+    """BASELINE configs[3] in small: a 208 x 40 x 40 box (2.0 M tets) cut into EIGHT x-slabs, each part swept in its own context
+    with the lean kernels, against the same box swept as ONE part on the device: the owned counts add up to the one-part counts
+    exactly, min quality / max length are the one-part values bit for bit, and every shared edge carries the same word on both
+    of its copies -- what the 8-GPU line's global statistics rest on (there the parts are 50 M tets each and the sum cannot be
+    checked against anything but itself)."""
+    gnx, ny, nz, nparts = 208, 40, 40, 8
+
+    def field(xyz):
+        f = xyz.copy()
+        f[:, 0] /= float(nparts)
+        return cb.fields.shock_rotating(f, 1.0 / ny)
+    xyz, ev, tv = cb.boxmesh.kuhn_box(gnx, ny, nz, wx=float(nparts))
+    h, R = field(xyz)
+    one = cb.Part(0)
+    one.set_mesh(xyz, ev, tv)
+    one.set_size_field_aniso(h, R)
+    one.clear_flags()
+    one.sweep(fp_mode=cb.FP_FAST)
+    want = one.stats()
+    one.close()
+    assert want["n_split"] > 10000 and want["n_collapse"] > 10000 and want["n_bad"] > 10000
+    tot = np.zeros(3, np.int64)
+    mx, mn = 0.0, 1.0
+    words, links = [], []
+    for r in range(nparts):
+        part = cb.boxmesh.slab_part(gnx, ny, nz, nparts, r, wx=float(nparts))
+        p = cb.Part(0)
+        p.set_mesh(part["xyz"], part["edge_v"], part["tet_v"], edge_owned=part["edge_owned"], elem_owned=part["elem_owned"])
+        hh, RR = field(part["xyz"])
+        p.set_size_field_aniso(hh, RR)
+        p.clear_flags()
+        p.sweep(fp_mode=cb.FP_FAST)
+        st = p.stats()
+        tot += [st["n_split"], st["n_collapse"], st["n_bad"]]
+        mx, mn = max(mx, st["max_length"]), min(mn, st["min_quality"])
+        words.append(p.flags()[0])
+        links.append({peer: idx for peer, idx, _ in part["links"]})
+        p.close()
+    assert tot.tolist() == [want["n_split"], want["n_collapse"], want["n_bad"]]
+    assert mx == want["max_length"] and mn == want["min_quality"]
+    for r in range(nparts - 1):
+        assert np.array_equal(words[r][links[r][r + 1]], words[r + 1][links[r + 1][r]])
+
+
 @pytest.mark.parametrize("kindname", ["iso", "aniso", "logm"])
 def test_sweep_host_streamed_equals_resident(cb, kindname):
     """mag_sweep_host (export + sweep + results in one streamed call, several slices) returns bit for bit what the
