@@ -238,7 +238,8 @@ struct Access {
   static void resetOrder(GpuSizeField* g) { g->lastDim = g->lastId = -1; }
   static size_t exportedElems(GpuSizeField* g) { return g->exported ? g->exported->elems.size() : 0; }
   static bool isDirty(GpuSizeField* g) { return g->dirty; }
-  static int fpMode(GpuSizeField* g) { return g->fpMode; }
+  /* the arithmetic of the calls beside the marking sweep: MAG_FP_FAST_LISTED is a mode of mag_sweep only */
+  static int fpMode(GpuSizeField* g) { return g->fpMode == MAG_FP_FAST_LISTED ? MAG_FP_FAST : g->fpMode; }
   static int vertSlotOf(GpuSizeField* g, ma::Entity* v) { return g->vertSlot[apf::getMdsIndex(g->mesh, v)]; }
   static long nonSimplex(GpuSizeField* g) { return g->nNonSimplex; }
   static int tetSlotOf(GpuSizeField* g, ma::Entity* e) { return g->tetSlot[apf::getMdsIndex(g->mesh, e)]; }

@@ -75,7 +75,8 @@ class GpuSizeField : public ma::SizeField
        code).  Moved vertices (apf::Mesh2::setPoint, snapping) and in-place edits of the size fields need no call: every
        bulk sweep and every sweep start re-reads the vertices and compares a hash with what the device holds. */
     void invalidate() { dirty = true; topoValid = false; }
-    /* MAG_FP_STRICT (default) or MAG_FP_FAST, see include/mag.h */
+    /* MAG_FP_STRICT (default), MAG_FP_FAST, or MAG_FP_FAST_LISTED (near-threshold edges listed instead of re-evaluated: the marks
+       may then differ from the reference's on exactly those edges), see include/mag.h */
     void setArithmetic(int fp_mode) { fpMode = fp_mode; invalidate(); }
     /* host threads for the read-only part of the MDS walk of an export (getDownward / isOwned of every edge and element, the
        "ma_flags" tag reads); default 1 = the reference's own single-threaded access pattern.  MDS adjacency queries do not

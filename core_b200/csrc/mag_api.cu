@@ -156,7 +156,7 @@ int mag_create(mag_ctx** out, int device)
   c->d_stats = nullptr; c->h_stats = nullptr;
   c->d_block_sums = nullptr; c->n_sms = 148;
   c->d_edge_order = c->d_tet_order = nullptr;
-  c->erows = MagRows{0, 0, 0, nullptr, nullptr, nullptr, false};
+  c->erows = MagRows{0, 0, 0, nullptr, nullptr, nullptr, false, {true, true, true}};
   c->trows = c->erows;
   { const char* e = getenv("MAG_LEGACY_SWEEP"); c->legacy_sweep = e && e[0] == '1'; }
   { const char* e = getenv("MAG_LEAN_SWEEP"); c->lean_sweep = !(e && e[0] == '0'); }

@@ -46,6 +46,7 @@ struct MagRows {
   int32_t* d_slice_off;  // [n_slices + 1] first slot of every slice
   int32_t* d_slots;      // edges: int2 {other vertex | not-owned << 31, edge id}; tets: int4 {o1 | not-owned << 31, o2, o3, tet id}; id -1 = empty
   bool valid;
+  bool pooled[3];        // d_anchor / d_slice_off / d_slots came from the stream-ordered pool (small blocks) or from cudaMalloc
 };
 
 struct MagLinks {

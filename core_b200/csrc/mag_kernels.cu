@@ -1520,16 +1520,30 @@ __global__ void k_iota(int64_t n, int32_t* __restrict__ out)
 // returning them to the driver): with plain cudaMalloc / cudaFree the ~25 temporaries of one export cost 35 - 700 ms on a
 // 663 k-tet part (r2o trace), every free being a device-wide synchronisation and an unmap; from the pool the same export is a
 // few milliseconds, every time.
+// Blocks of kPoolMax bytes or more keep cudaMalloc / cudaFree: for them the driver call is a small part of the work that
+// follows, and a pool grown by the gigabytes of a 50 M-tet export would hold them for the life of the process.
+constexpr size_t kPoolMax = (size_t)64 << 20;
+cudaError_t temp_alloc(void** p, size_t bytes, cudaStream_t stream, bool* pooled)
+{
+  *pooled = bytes < kPoolMax;
+  return *pooled ? cudaMallocAsync(p, bytes, stream) : cudaMalloc(p, bytes);
+}
+void temp_free(void* p, cudaStream_t stream, bool pooled)
+{
+  if (!p) return;
+  if (pooled) cudaFreeAsync(p, stream); else cudaFree(p);
+}
 struct Scratch {
   cudaStream_t stream;
-  std::vector<void*> ptrs;
+  std::vector<std::pair<void*, bool> > ptrs;
   explicit Scratch(cudaStream_t s) : stream(s) {}
-  ~Scratch() { for (void* p : ptrs) cudaFreeAsync(p, stream); }
+  ~Scratch() { for (auto& p : ptrs) temp_free(p.first, stream, p.second); }
   template <class T> cudaError_t get(T*& p, size_t count)
   {
     p = nullptr;
-    cudaError_t e = cudaMallocAsync((void**)&p, (count ? count : 1) * sizeof(T), stream);
-    if (e == cudaSuccess) ptrs.push_back(p);
+    bool pooled = true;
+    cudaError_t e = temp_alloc((void**)&p, (count ? count : 1) * sizeof(T), stream, &pooled);
+    if (e == cudaSuccess) ptrs.push_back(std::make_pair((void*)p, pooled));
     return e;
   }
 };
@@ -1555,9 +1569,9 @@ int exclusive_scan(mag_ctx* c, Scratch& S, const int32_t* in, int32_t* out, int6
 void free_rows(MagRows& r, cudaStream_t stream)
 {
   // (allocated from the stream-ordered pool on the context's compute stream, the only stream that ever reads them)
-  if (r.d_anchor) cudaFreeAsync(r.d_anchor, stream);
-  if (r.d_slice_off) cudaFreeAsync(r.d_slice_off, stream);
-  if (r.d_slots) cudaFreeAsync(r.d_slots, stream);
+  temp_free(r.d_anchor, stream, r.pooled[0]);
+  temp_free(r.d_slice_off, stream, r.pooled[1]);
+  temp_free(r.d_slots, stream, r.pooled[2]);
   r.d_anchor = r.d_slice_off = r.d_slots = nullptr;
   r.n_rows = r.n_slices = r.n_slots = 0;
   r.valid = false;
@@ -1630,8 +1644,8 @@ static int build_rows(mag_ctx* c, int64_t n, const int32_t* d_conn, MagRows& row
   k_row_records<<<grid_for(nv), kThreads, 0, c->stream>>>(nv, deg, start, rowstart, row_anchor, row_len, row_first, rkey, ridx);
   MAG_CUDA(c, cudaGetLastError());
   if ((rc = sort_pairs(c, S, rkey, rkey2, ridx, order, R, bits_for(nv >> kRowWindowLog2) + 6))) return rc;
-  MAG_CUDA(c, cudaMallocAsync((void**)&rows.d_slice_off, ((size_t)nslices + 1) * 4, c->stream));
-  MAG_CUDA(c, cudaMallocAsync((void**)&rows.d_anchor, (size_t)Rpad * 4, c->stream));
+  MAG_CUDA(c, temp_alloc((void**)&rows.d_slice_off, ((size_t)nslices + 1) * 4, c->stream, &rows.pooled[1]));
+  MAG_CUDA(c, temp_alloc((void**)&rows.d_anchor, (size_t)Rpad * 4, c->stream, &rows.pooled[0]));
   int32_t* width32 = nullptr;
   MAG_CUDA(c, S.get(width32, (size_t)nslices + 1));
   k_slice_width<<<grid_for((nslices + 1) * 32), kThreads, 0, c->stream>>>(R, nslices, order, row_len, width32);
@@ -1646,7 +1660,7 @@ static int build_rows(mag_ctx* c, int64_t n, const int32_t* d_conn, MagRows& row
     return mag_fail(c, MAG_ERR_ARG, "row layout: slot count overflows int32 (%lld entities)", (long long)n);
   }
   const int64_t n_slots = n_slots32;
-  MAG_CUDA(c, cudaMallocAsync((void**)&rows.d_slots, (size_t)n_slots * NV * 4, c->stream));
+  MAG_CUDA(c, temp_alloc((void**)&rows.d_slots, (size_t)n_slots * NV * 4, c->stream, &rows.pooled[2]));
   MAG_CUDA(c, cudaMemsetAsync(rows.d_slots, 0xFF, (size_t)n_slots * NV * 4, c->stream));
   k_slots_fill<NV><<<grid_for(Rpad), kThreads, 0, c->stream>>>(R, Rpad, order, row_anchor, row_len, row_first, sorted_e, d_conn,
                                                                rows.d_slice_off, rows.d_anchor, rows.d_slots);
@@ -1891,10 +1905,11 @@ int magk_cavity_quality(mag_ctx* c, int fp_mode, int64_t ncav, const int64_t* d_
 int magk_build_v2t(mag_ctx* c)
 {
   if (c->v2t_valid) return MAG_OK;
-  if (c->d_v2t_off) { MAG_CUDA(c, cudaFreeAsync(c->d_v2t_off, c->stream)); c->d_v2t_off = nullptr; }
-  if (c->d_v2t) { MAG_CUDA(c, cudaFreeAsync(c->d_v2t, c->stream)); c->d_v2t = nullptr; }
-  MAG_CUDA(c, cudaMallocAsync((void**)&c->d_v2t_off, ((size_t)c->nv + 1) * 4, c->stream));
-  MAG_CUDA(c, cudaMallocAsync((void**)&c->d_v2t, ((size_t)c->nt * 4 + 1) * 4, c->stream));
+  if (c->d_v2t_off) { MAG_CUDA(c, cudaFree(c->d_v2t_off)); c->d_v2t_off = nullptr; }      // (cudaFree takes blocks of either kind)
+  if (c->d_v2t) { MAG_CUDA(c, cudaFree(c->d_v2t)); c->d_v2t = nullptr; }
+  bool pooled_unused;
+  MAG_CUDA(c, temp_alloc((void**)&c->d_v2t_off, ((size_t)c->nv + 1) * 4, c->stream, &pooled_unused));
+  MAG_CUDA(c, temp_alloc((void**)&c->d_v2t, ((size_t)c->nt * 4 + 1) * 4, c->stream, &pooled_unused));
   Scratch S(c->stream);
   int32_t *cnt = nullptr, *cursor = nullptr;
   MAG_CUDA(c, S.get(cnt, (size_t)c->nv + 1));
