@@ -681,6 +681,22 @@ def run_b200(a):
                "what": "mag_resweep_host per step and rank, connectivity resident on the device: vertex coordinates + size field + "
                        "one mark byte per entity up from pinned host buffers, sweep, mark bytes + statistics down "
                        "(uploads / kernels / downloads on three streams)"}
+        # (a') the other sweeps of the SAME MeshAdapt iteration: mesh, coordinates and size field are unchanged, only the mark
+        # bytes travel (one byte per entity up, one down).  Reported beside the headline e2e, which re-sends coordinates + field.
+        if not a.no_extras:
+            def marks_step():
+                s = p.resweep_host(xyz=None, kind=-1, edge_marks=h_em, elem_marks=h_lm, out_edge_marks=o_em, out_elem_marks=o_lm,
+                                   ops=ops, fp_mode=fp_mode)
+                if world > 1:
+                    p.reconcile_edge_flags(mark_mask)
+                    s = p.allreduce_stats()
+                return s
+            dtm = time_host(marks_step, a.e2e_steps)
+            extras["e2e_marks_only"] = {
+                "value": ents_all / dtm, "unit": UNIT, "ms_per_step": 1e3 * dtm,
+                "h2d_bytes_per_step": int(nbytes((h_em, h_lm))), "d2h_bytes_per_step": int(nbytes((o_em, o_lm)) + 88),
+                "what": "mag_resweep_host with coordinates and size field unchanged (NULL): mark bytes up, sweep, mark bytes + "
+                        "statistics down -- every sweep of a MeshAdapt iteration after its first"}
         # (b) full re-export every step (a MeshAdapt iteration after the mesh changed): the round-1 end-to-end leg
         if not a.no_extras:
             h_ef = torch.zeros(ne, dtype=torch.int32).pin_memory()
