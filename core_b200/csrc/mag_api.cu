@@ -146,7 +146,7 @@ int mag_create(mag_ctx** out, int device)
   c->dim = 3;
   c->kind = MAG_KIND_NONE;
   c->uniform_refiner = false;
-  c->vertex_pass_valid = false; c->schedule_valid = false; c->edge_flags_zero = c->elem_flags_zero = false; c->s_up = c->s_down = nullptr;
+  c->vertex_pass_valid = false; c->schedule_valid = false; c->edge_flags_zero = c->elem_flags_zero = false; c->tet_words_zero = false; c->s_up = c->s_down = nullptr;
   c->d_xyz = c->d_ma = c->d_mb = c->d_vedge = c->d_vpos = c->d_vq = nullptr;
   c->d_edge_v = c->d_tet_v = c->d_prism_v = c->d_pyr_v = c->d_tri_v = nullptr;
   c->d_edge_owned = c->d_elem_owned = nullptr;
@@ -337,6 +337,7 @@ static int set_mesh_impl(mag_ctx* c, int dim, int64_t nv, const double* xyz, int
   const int64_t nel = np + npy + nt + ntri;
   // a new mesh starts with no flags (ma::getFlags returns 0 when the tag is absent, maAdapt.cc:80-88)
   c->edge_flags_zero = c->elem_flags_zero = true;
+  c->tet_words_zero = true;
   c->v2t_valid = false;
   if ((rc = upload(c, c->d_xyz, xyz, (size_t)nv * 3)) || (rc = upload(c, c->d_edge_v, edge_v, (size_t)ne * 2)) ||
       (rc = upload(c, c->d_tet_v, tet_v, (size_t)nt * 4)) || (rc = upload(c, c->d_prism_v, prism_v, (size_t)np * 6)) ||
@@ -423,6 +424,7 @@ int mag_set_flags(mag_ctx* c, const int32_t* edge_flags, const int32_t* elem_fla
   c->edge_flags_zero = edge_flags == nullptr;
   if (elem_flags) { int rc = upload(c, c->d_elem_flags, elem_flags, (size_t)nel); if (rc) return rc; }
   c->elem_flags_zero = elem_flags == nullptr;
+  c->tet_words_zero = elem_flags == nullptr;
   (void)nel;
   return MAG_OK;
 }

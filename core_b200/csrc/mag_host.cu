@@ -119,6 +119,7 @@ extern "C" int mag_sweep_host(mag_ctx* c, const mag_host_part* in, const mag_hos
   c->kind = in->kind;
   c->uniform_refiner = false;
   c->edge_flags_zero = c->elem_flags_zero = false;   // every slice below is uploaded or zeroed explicitly
+  c->tet_words_zero = false;
   c->last_ops = ops;
   c->last_fp_mode = fp_mode;
   // everything queued from here on is drained before the call returns, also when a step fails (the caller may free or
@@ -203,6 +204,7 @@ extern "C" int mag_set_mark_bytes(mag_ctx* c, const uint8_t* edge_marks, const u
     if ((rc = magk_marks_expand(c, c->stream, c->d_elem_bytes, c->d_elem_flags, nel))) return rc;
   }
   c->elem_flags_zero = elem_marks == nullptr;
+  c->tet_words_zero = elem_marks == nullptr;
   return MAG_OK;
 }
 
@@ -292,6 +294,7 @@ extern "C" int mag_resweep_host(mag_ctx* c, const mag_host_update* in, const mag
     if (in->elem_marks && (rc = magk_marks_expand(c, s_cmp, c->d_elem_bytes, c->d_elem_flags, nel))) return rc;
     c->edge_flags_zero = in->edge_marks == nullptr;
     c->elem_flags_zero = in->elem_marks == nullptr;
+    c->tet_words_zero = in->elem_marks == nullptr;
     if ((rc = magk_init_stats(c))) return rc;
     const uint32_t edge_ops = ops & (MAG_OP_LENGTHS | MAG_OP_MARK_SPLIT | MAG_OP_MARK_COLLAPSE | MAG_OP_LENGTH_SUM);
     const uint32_t elem_ops = ops & (MAG_OP_QUALITIES | MAG_OP_MARK_BAD | MAG_OP_LAYER_CHECK);

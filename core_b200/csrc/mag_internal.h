@@ -73,6 +73,10 @@ struct mag_ctx {
   // device arrays have not been zeroed: the whole-part edge / tet kernels then skip reading them; every other consumer
   // calls magi_materialize_flags first
   bool edge_flags_zero, elem_flags_zero;
+  // the words of the TETS are all zero (logically, or as materialised zeros), whatever the layer elements in front of them
+  // carry: after mag_reset_layer on a mixed part the element words are materialised (LAYER | OK_QUALITY on prisms / pyramids)
+  // but no tet has been touched, and the element sweep may still use the lean tet kernel, which writes every tet word from zero
+  bool tet_words_zero;
   bool schedule_valid;   // d_edge_order / d_tet_order match the resident connectivity
 
   // raw uploads (kept so coordinates or metric can be replaced independently)

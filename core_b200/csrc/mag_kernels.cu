@@ -1706,7 +1706,7 @@ static bool lean_edges_ok(const mag_ctx* c, const SweepParams& P, bool fast)
 static bool lean_tets_ok(const mag_ctx* c, const SweepParams& P, bool fast)
 {
   constexpr uint32_t kElemFull = MAG_OP_QUALITIES | MAG_OP_MARK_BAD;
-  return fast && c->elem_flags_zero && P.use_max && c->lean_sweep && (P.ops & kElemFull) == kElemFull;
+  return fast && (c->elem_flags_zero || c->tet_words_zero) && P.use_max && c->lean_sweep && (P.ops & kElemFull) == kElemFull;
 }
 static bool use_edge_rows(const mag_ctx* c, const SweepParams& P, bool fast)
 {
@@ -1852,7 +1852,7 @@ int magk_sweep(mag_ctx* c, uint32_t ops, double max_len, double min_len, double 
     if ((c->ntri || c->np + c->npy) && (rc = magi_materialize_flags(c))) return rc;
     if (c->nt) {
       if ((rc = use_tet_rows(c, P, fast) ? launch_tet_rows(c, P, fast) : launch_tets_kind(c, P, fast, Range{0, c->nt, true}))) return rc;
-      if (ops & MAG_OP_MARK_BAD) c->elem_flags_zero = false;
+      if (ops & MAG_OP_MARK_BAD) c->elem_flags_zero = c->tet_words_zero = false;
     }
     if (c->ntri) {
       switch (c->kind) {

@@ -136,6 +136,7 @@ extern "C" int mag_reset_layer(mag_ctx* c, const int32_t* user_layer_tag, int64_
   int rc;
   if ((rc = magi_materialize_flags(c))) return rc;
   int32_t* d_tag = nullptr;
+  if (user_layer_tag) c->tet_words_zero = false;    // a user tag may put LAYER on tets; without one only prisms / pyramids get words
   if (user_layer_tag && nel) {
     MAG_CUDA(c, cudaMalloc((void**)&d_tag, (size_t)nel * 4));
     cudaError_t e = cudaMemcpyAsync(d_tag, user_layer_tag, (size_t)nel * 4, cudaMemcpyHostToDevice, c->stream);

@@ -882,6 +882,42 @@ def test_two_parts_one_gpu_partition_invariance(cb):
     assert abs(mx - want["max_length"]) <= TOL * mx and abs(mn - want["min_quality"]) <= TOL * abs(mn)
 
 
+@pytest.mark.parametrize("tagged", [False, True])
+def test_mixed_part_lean_tets_after_reset_layer(cb, tagged):
+    """BASELINE configs[4] in small: on a mixed prism / tet part the device LAYER closure (mag_reset_layer) materialises the
+    element flag words -- LAYER | OK_QUALITY on the prisms -- but touches no tet, so the element sweep that follows may still run
+    the lean tet kernel (it writes every tet word from zero).  Lengths, qualities, flag words, counts, layer verdicts and lists
+    equal bit for bit what the tile kernels return (MAG_LEAN_SWEEP=0); with a user layer tag on some tets the lean kernel must
+    not be chosen, and the results are the same again."""
+    rng = np.random.default_rng(17)
+    xyz, ev, tv, pr = cb.boxmesh.mixed_box(9, 3)
+    xyz = cb.fields.jitter(xyz, 0.15 / 9)
+    h, R = cb.fields.shock_rotating(xyz, 1.0 / 9)
+    tag = None
+    if tagged:
+        tag = np.zeros(len(pr) + len(tv), np.int32)
+        tag[len(pr) + rng.choice(len(tv), 40, replace=False)] = 1
+    res = []
+    for env in ({}, {"MAG_LEAN_SWEEP": "0"}):
+        p = _part_with_env(cb, env)
+        p.set_mesh(xyz, ev, tv, prism_v=pr)
+        p.set_size_field_aniso(h, R)
+        for rep in range(2):                       # the second sweep starts from the state the first one left
+            p.clear_flags()
+            nl = p.reset_layer(tag)
+            p.sweep(cb.OP_ALL, fp_mode=cb.FP_FAST)
+        st = p.stats()
+        res.append((nl, p.edge_lengths(), p.qualities(), *p.flags(), st, np.sort(p.near_threshold(1)[0]), p.layer_ok()))
+        p.close()
+    (n0, L0, q0, ef0, lf0, s0, ne0, ok0), (n1, L1, q1, ef1, lf1, s1, ne1, ok1) = res
+    assert n0 == n1 == len(pr) + (40 if tagged else 0)
+    assert np.array_equal(L0, L1) and np.array_equal(q0, q1) and np.array_equal(ef0, ef1) and np.array_equal(lf0, lf1)
+    assert np.array_equal(ne0, ne1) and np.array_equal(ok0[0] if isinstance(ok0, tuple) else ok0, ok1[0] if isinstance(ok1, tuple) else ok1)
+    for k in ("n_split", "n_collapse", "n_bad", "n_elems_evaluated", "n_near_threshold", "min_quality", "max_length", "n_layer_unsafe"):
+        assert s0[k] == s1[k], k
+    assert np.all(lf0[: len(pr)] & cb.LAYER) and s0["n_bad"] > 0
+
+
 def test_eight_parts_counts_equal_the_one_part_sweep(cb):
     """BASELINE configs[3] in small: a 208 x 40 x 40 box (2.0 M tets) cut into EIGHT x-slabs, each part swept in its own context
     with the lean kernels, against the same box swept as ONE part on the device: the owned counts add up to the one-part counts
