@@ -200,35 +200,40 @@ __device__ __forceinline__ double edge_length_strict(const EdgeRecs<KIND>& R, in
   const double* rb = R.b;
   V3 j = magst::edge_j0(V3{ra[0], ra[1], ra[2]}, V3{rb[0], rb[1], rb[2]});
   if (KIND == MAG_KIND_IDENTITY) return magst::mul(2.0, magst::length(j)); // apf::measure, N1 rule
-  double len[2];
-  if (KIND == MAG_KIND_ISO) {
+  // The second Gauss point interpolates with the two shape values swapped ((1 - (-XI)) / 2 is the same operation as (1 + XI) / 2,
+  // bit for bit).  When both ends carry the SAME size-field values -- an edge along a direction the field does not vary in, any
+  // edge of a uniform region -- a * N0 + a * N1 is therefore the same sum with its terms exchanged, floating-point addition
+  // commutes, both points see identical interpolated values, identical transforms and identical lengths, and one evaluation
+  // serves both: exact, not an approximation.  (The benchmark lattice's z edges are such edges, and they are the ones that sit
+  // on the collapse threshold and come here to be re-evaluated: their strict evaluation costs half.)
+  static_assert(NM0 == NP1 && NM1 == NP0, "the two Gauss points swap their shape values");
+  bool same = true;
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
-      double h = magst::lerp2(ra[3], p ? NM0 : NP0, rb[3], p ? NM1 : NP1);
+  for (int i = 3; i < EdgeRecs<KIND>::N; ++i) same = same && (__double_as_longlong(ra[i]) == __double_as_longlong(rb[i]));
+  auto point = [&](const double n0, const double n1) -> double {
+    if (KIND == MAG_KIND_ISO) {
+      double h = magst::lerp2(ra[3], n0, rb[3], n1);
       double ih = magst::div(1.0, h);
       V3 r{magst::mul(j.x, ih), magst::mul(j.y, ih), magst::mul(j.z, ih)};
-      len[p] = magst::length(r);
+      return magst::length(r);
     }
-  } else {
+    double c[9];
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
-      const double n0 = p ? NM0 : NP0, n1 = p ? NM1 : NP1;
-      double c[9];
+    for (int i = 0; i < 9; ++i) c[i] = magst::lerp2(ra[(3 + i) % EdgeRecs<KIND>::N], n0, rb[(3 + i) % EdgeRecs<KIND>::N], n1);
+    M3 Q;
+    if (KIND == MAG_KIND_ANISO) {
+      magst::transform_aniso(V3{c[3], c[4], c[5]}, V3{c[6], c[7], c[8]}, c[0], c[1], c[2], Q);
+    } else {
+      M3 A;
 #pragma unroll
-      for (int i = 0; i < 9; ++i) c[i] = magst::lerp2(ra[(3 + i) % EdgeRecs<KIND>::N], n0, rb[(3 + i) % EdgeRecs<KIND>::N], n1);
-      M3 Q;
-      if (KIND == MAG_KIND_ANISO) {
-        magst::transform_aniso(V3{c[3], c[4], c[5]}, V3{c[6], c[7], c[8]}, c[0], c[1], c[2], Q);
-      } else {
-        M3 A;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) A.m[i / 3][i % 3] = c[i];
-        if (magst::transform_logm(A, Q) != 1) *eig_fail = 1;
-      }
-      len[p] = magst::row0_length(j, Q);
+      for (int i = 0; i < 9; ++i) A.m[i / 3][i % 3] = c[i];
+      if (magst::transform_logm(A, Q) != 1) *eig_fail = 1;
     }
-  }
-  return magst::add(len[0], len[1]);
+    return magst::row0_length(j, Q);
+  };
+  const double len0 = point(NP0, NP1);
+  const double len1 = same ? len0 : point(NM0, NM1);
+  return magst::add(len0, len1);
 }
 
 template <int KIND>
