@@ -147,7 +147,7 @@ int mag_create(mag_ctx** out, int device)
   c->kind = MAG_KIND_NONE;
   c->uniform_refiner = false;
   c->vertex_pass_valid = false; c->schedule_valid = false; c->edge_flags_zero = c->elem_flags_zero = false; c->tet_words_zero = false; c->s_up = c->s_down = nullptr;
-  c->d_xyz = c->d_ma = c->d_mb = c->d_vedge = c->d_vpos = c->d_vq = nullptr;
+  c->d_xyz = c->d_ma = c->d_mb = c->d_vedge = c->d_vpos = c->d_vq = c->d_vqu = nullptr; c->vqu_kind = MAG_KIND_NONE;
   c->d_edge_v = c->d_tet_v = c->d_prism_v = c->d_pyr_v = c->d_tri_v = nullptr;
   c->d_edge_owned = c->d_elem_owned = nullptr;
   c->d_edge_flags = c->d_elem_flags = nullptr;
@@ -208,7 +208,7 @@ void mag_destroy(mag_ctx* c)
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   magc_destroy(c);
-  cudaFree(c->d_xyz); cudaFree(c->d_ma); cudaFree(c->d_mb); cudaFree(c->d_vedge); cudaFree(c->d_vpos); cudaFree(c->d_vq);
+  cudaFree(c->d_xyz); cudaFree(c->d_ma); cudaFree(c->d_mb); cudaFree(c->d_vedge); cudaFree(c->d_vpos); cudaFree(c->d_vq); cudaFree(c->d_vqu);
   cudaFree(c->d_edge_v); cudaFree(c->d_tet_v); cudaFree(c->d_prism_v); cudaFree(c->d_pyr_v); cudaFree(c->d_tri_v);
   cudaFree(c->d_edge_owned); cudaFree(c->d_elem_owned); cudaFree(c->d_edge_flags); cudaFree(c->d_elem_flags);
   cudaFree(c->d_len); cudaFree(c->d_qual); cudaFree(c->d_weight); cudaFree(c->d_layer_ok); cudaFree(c->d_layer_codes);
@@ -261,6 +261,7 @@ int magi_reshape(mag_ctx* c, int dim, int64_t nv, int64_t ne, int64_t nt, int64_
   const bool keep_field = nv == c->nv;
   c->nv = c->ne = c->nt = c->np = c->npy = c->ntri = 0;
   c->vertex_pass_valid = false;
+  c->vqu_kind = MAG_KIND_NONE;
   magk_free_rows(c);
   if ((rc = dev_free(c, c->d_weight)) || (rc = dev_free(c, c->d_edge_bytes)) || (rc = dev_free(c, c->d_elem_bytes))) return rc;
   if (!keep_field) { // size field arrays are per vertex: drop them
@@ -270,7 +271,8 @@ int magi_reshape(mag_ctx* c, int dim, int64_t nv, int64_t ne, int64_t nt, int64_
   }
   auto fail_empty = [&](int code) { c->kind = MAG_KIND_NONE; return code; };
   if ((rc = dev_alloc(c, c->d_xyz, (size_t)nv * 3)) || (rc = dev_alloc(c, c->d_vpos, (size_t)vpad(nv) * 4)) ||
-      (rc = dev_alloc(c, c->d_vq, (size_t)vpad(nv) * 10)) || (rc = dev_alloc(c, c->d_edge_v, (size_t)ne * 2)) ||
+      (rc = dev_alloc(c, c->d_vq, (size_t)vpad(nv) * 10)) || (rc = dev_alloc(c, c->d_vqu, (size_t)vpad(nv) * 10)) ||
+      (rc = dev_alloc(c, c->d_edge_v, (size_t)ne * 2)) ||
       (rc = dev_alloc(c, c->d_tet_v, (size_t)nt * 4)) || (rc = dev_alloc(c, c->d_prism_v, (size_t)np * 6)) ||
       (rc = dev_alloc(c, c->d_pyr_v, (size_t)npy * 5)) || (rc = dev_alloc(c, c->d_tri_v, (size_t)ntri * 3)) ||
       (rc = dev_alloc(c, c->d_edge_owned, has_edge_owned ? (size_t)ne : 0)) ||

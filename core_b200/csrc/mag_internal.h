@@ -87,6 +87,9 @@ struct mag_ctx {
   double* d_vedge; // per vertex: iso/identity 4 doubles {x,y,z,s}; aniso/logm 12 doubles
   double* d_vpos;  // per vertex 4 doubles {x,y,z,det Q_v}
   double* d_vq;    // per vertex 10 doubles {Q_v row-major, det Q_v}
+  double* d_vqu;   // per vertex 10 doubles {Q_u row-major, eigen-solver failure}: the transform both Gauss points of an edge see whose
+                   // two ends carry THIS vertex's size-field values (k_vertex_uniform); valid with the vertex pass, for vqu_kind
+  int vqu_kind;    // size-field kind d_vqu was computed for (MAG_KIND_NONE: none)
   int32_t* d_edge_v;  // [ne][2]
   int32_t* d_tet_v;   // [nt][4]
   int32_t* d_prism_v; // [np][6]

@@ -169,6 +169,44 @@ __global__ void k_vertex_pass(int64_t nv, int dim, const double* __restrict__ ve
   if (eig) atomicAdd(eig_fail, 1ull);
 }
 
+// shape values of the edge's two Gauss points exactly as apfShape.cc:123-124 computes them (xi = +-0.577350269189626)
+constexpr double kXI = 0.577350269189626;
+constexpr double kNP0s = (1.0 - kXI) / 2.0, kNP1s = (1.0 + kXI) / 2.0;       // point 0: xi = +XI
+constexpr double kNM0s = (1.0 - (-kXI)) / 2.0, kNM1s = (1.0 + (-kXI)) / 2.0; // point 1: xi = -XI
+static_assert(kNM0s == kNP1s && kNM1s == kNP0s, "the two Gauss points swap their shape values");
+
+// Q_u(v): the transform BOTH Gauss points of an edge see when its two ends carry vertex v's size-field values bit for bit (an edge
+// along a direction the field does not vary in, any edge of a uniform region): the interpolated values are a N0 + a N1, the same
+// sum in either order (edge_length_strict below), so the transform depends on the vertex alone and every such edge around it shares
+// it.  Strict arithmetic, the reference's operation order: what edge_length_strict would compute in place, computed once per vertex
+// with the per-vertex pass.  Chunk 4 carries the eigen-solver's failure flag of the log-Euclidean field in its second half.
+template <int KIND>
+__global__ void k_vertex_uniform(int64_t nv, const double* __restrict__ vedge, double* __restrict__ vqu)
+{
+  static_assert(KIND == MAG_KIND_ANISO || KIND == MAG_KIND_LOGM, "only the frame-carrying fields have a transform worth caching");
+  const int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  const Rec12 r = load_rec12(vedge, (int32_t)v);
+  double c[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) c[i] = magst::lerp2(r.v[3 + i], kNP0s, r.v[3 + i], kNP1s);
+  M3 Q;
+  double fail = 0.0;
+  if (KIND == MAG_KIND_ANISO) {
+    magst::transform_aniso(V3{c[3], c[4], c[5]}, V3{c[6], c[7], c[8]}, c[0], c[1], c[2], Q);
+  } else {
+    M3 A;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) A.m[i / 3][i % 3] = c[i];
+    if (magst::transform_logm(A, Q) != 1) fail = 1.0;
+  }
+  *chunk_ptr_w<5>(vqu, 0, v) = make_double2(Q.m[0][0], Q.m[0][1]);
+  *chunk_ptr_w<5>(vqu, 1, v) = make_double2(Q.m[0][2], Q.m[1][0]);
+  *chunk_ptr_w<5>(vqu, 2, v) = make_double2(Q.m[1][1], Q.m[1][2]);
+  *chunk_ptr_w<5>(vqu, 3, v) = make_double2(Q.m[2][0], Q.m[2][1]);
+  *chunk_ptr_w<5>(vqu, 4, v) = make_double2(Q.m[2][2], fail);
+}
+
 // ------------------------------------------------------------------ edge metric length
 // the two vertex records of an edge, in registers: 4 doubles each (identity / iso) or 12 (aniso / logm)
 template <int KIND>
@@ -190,12 +228,9 @@ __device__ __forceinline__ void load_edge_recs(const double* __restrict__ vedge,
 
 // MetricSizeField::measure: order 2 -> EdgeIntegration::N2, points +-0.577350269189626, weights 1
 template <int KIND>
-__device__ __forceinline__ double edge_length_strict(const EdgeRecs<KIND>& R, int* eig_fail)
+__device__ __forceinline__ double edge_length_strict(const EdgeRecs<KIND>& R, int* eig_fail, const double* __restrict__ vqu = nullptr, int32_t va = 0)
 {
-  constexpr double XI = 0.577350269189626;
-  // shape values exactly as apfShape.cc:123-124 computes them
-  constexpr double NP0 = (1.0 - XI) / 2.0, NP1 = (1.0 + XI) / 2.0;       // point 0: xi = +XI
-  constexpr double NM0 = (1.0 - (-XI)) / 2.0, NM1 = (1.0 + (-XI)) / 2.0; // point 1: xi = -XI
+  constexpr double NP0 = kNP0s, NP1 = kNP1s, NM0 = kNM0s, NM1 = kNM1s;
   const double* ra = R.a;
   const double* rb = R.b;
   V3 j = magst::edge_j0(V3{ra[0], ra[1], ra[2]}, V3{rb[0], rb[1], rb[2]});
@@ -205,11 +240,23 @@ __device__ __forceinline__ double edge_length_strict(const EdgeRecs<KIND>& R, in
   // edge of a uniform region -- a * N0 + a * N1 is therefore the same sum with its terms exchanged, floating-point addition
   // commutes, both points see identical interpolated values, identical transforms and identical lengths, and one evaluation
   // serves both: exact, not an approximation.  (The benchmark lattice's z edges are such edges, and they are the ones that sit
-  // on the collapse threshold and come here to be re-evaluated: their strict evaluation costs half.)
-  static_assert(NM0 == NP1 && NM1 == NP0, "the two Gauss points swap their shape values");
+  // on the collapse threshold and come here to be re-evaluated.)  That one transform is a function of vertex `va`'s record alone:
+  // with the per-vertex pass in place it is read from vqu (k_vertex_uniform: the same operations on the same values) and the
+  // edge costs its Jacobian row and one 3 x 3 product.
   bool same = true;
 #pragma unroll
   for (int i = 3; i < EdgeRecs<KIND>::N; ++i) same = same && (__double_as_longlong(ra[i]) == __double_as_longlong(rb[i]));
+  if ((KIND == MAG_KIND_ANISO || KIND == MAG_KIND_LOGM) && vqu != nullptr && same) {
+    const double2 q0 = __ldg(chunk_ptr<5>(vqu, 0, va)), q1 = __ldg(chunk_ptr<5>(vqu, 1, va)), q2 = __ldg(chunk_ptr<5>(vqu, 2, va)),
+                  q3 = __ldg(chunk_ptr<5>(vqu, 3, va)), q4 = __ldg(chunk_ptr<5>(vqu, 4, va));
+    M3 Q;
+    Q.m[0][0] = q0.x; Q.m[0][1] = q0.y; Q.m[0][2] = q1.x;
+    Q.m[1][0] = q1.y; Q.m[1][1] = q2.x; Q.m[1][2] = q2.y;
+    Q.m[2][0] = q3.x; Q.m[2][1] = q3.y; Q.m[2][2] = q4.x;
+    if (q4.y != 0.0) *eig_fail = 1;
+    const double len = magst::row0_length(j, Q);
+    return magst::add(len, len);
+  }
   auto point = [&](const double n0, const double n1) -> double {
     if (KIND == MAG_KIND_ISO) {
       double h = magst::lerp2(ra[3], n0, rb[3], n1);
@@ -379,6 +426,7 @@ struct EdgeParams {
   int reeval;    // fast sweeps: near-threshold edges are re-evaluated in strict arithmetic (MAG_FP_FAST) or only listed (MAG_FP_FAST_LISTED)
   uint32_t ops;
   double max_len, min_len, tol_max, tol_min;
+  const double* vqu;   // k_vertex_uniform's per-vertex transforms when they are in place for this size field, else null
 };
 constexpr int32_t kSkipSplit = MAG_DONT_SPLIT | MAG_NEED_NOT_SPLIT, kSkipColl = MAG_DONT_COLLAPSE | MAG_NEED_NOT_COLLAPSE;
 
@@ -388,7 +436,8 @@ __device__ __noinline__ unsigned drain_edges(NearQueue& q, int first, int n, con
                                              const double* __restrict__ vedge,
                                              int32_t* __restrict__ flags, double* __restrict__ lengths, uint32_t ops,
                                              double max_len, double min_len,
-                                             MagDevStats* st, int32_t* __restrict__ near_list, int32_t id_base, bool reeval)
+                                             MagDevStats* st, int32_t* __restrict__ near_list, int32_t id_base, bool reeval,
+                                             const double* __restrict__ vqu)
 {
   SweepParams P{ops, max_len, min_len, 0.0, 0};
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -407,7 +456,7 @@ __device__ __noinline__ unsigned drain_edges(NearQueue& q, int first, int n, con
       ev.x &= kVidMask;
       load_edge_recs<KIND>(vedge, ev, R);
       int eig = 0;
-      const double len = edge_length_strict<KIND>(R, &eig);
+      const double len = edge_length_strict<KIND>(R, &eig, vqu, ev.x);
       unsigned cs = 0, cc = 0;
       mark_edge(len, f, need_split, need_coll, owned, P, cs, cc);
       out = 1u | (cs << 1) | (cc << 2);
@@ -496,7 +545,7 @@ k_edges(int32_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
           EdgeRecs<KIND> R;
           const bool owned = ev.x >= 0;                 // sign bit of the first vertex id = "not owned" (k_fold_owned)
           load_edge_recs<KIND>(vedge, make_int2(ev.x & kVidMask, ev.y), R);
-          const double len = FAST ? edge_length_fast<KIND>(R, &eig_any) : edge_length_strict<KIND>(R, &eig_any);
+          const double len = FAST ? edge_length_fast<KIND>(R, &eig_any) : edge_length_strict<KIND>(R, &eig_any);   // (no Q_u here: a third of a tile's lanes taking the short way costs the warp both ways -- lattice 2.95 -> 3.19 ms)
           if (P.want_len) {
             st_stream(lengths + e, len);
             if (owned && len > maxlen) maxlen = len;
@@ -526,7 +575,7 @@ k_edges(int32_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
       }
       if (queue_push(q, qn, nr, (int32_t)e, f)) {
         qn -= 32;
-        const unsigned r = drain_edges<KIND, FAST>(q, qn, 32, edge_v, vedge, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list, id_base, P.reeval != 0);
+        const unsigned r = drain_edges<KIND, FAST>(q, qn, 32, edge_v, vedge, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list, id_base, P.reeval != 0, P.vqu);
         c_eval += r & 1u; c_split += (r >> 1) & 1u; c_coll += (r >> 2) & 1u;
       }
       f = f_nx;
@@ -536,7 +585,7 @@ k_edges(int32_t ne, const int2* __restrict__ edge_v, const double* __restrict__ 
     }
   }
   if (qn) {
-    const unsigned r = drain_edges<KIND, FAST>(q, 0, qn, edge_v, vedge, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list, id_base, P.reeval != 0);
+    const unsigned r = drain_edges<KIND, FAST>(q, 0, qn, edge_v, vedge, flags, lengths, P.ops, P.max_len, P.min_len, st, near_list, id_base, P.reeval != 0, P.vqu);
     c_eval += r & 1u; c_split += (r >> 1) & 1u; c_coll += (r >> 2) & 1u;
   }
   if (eig_any) atomicAdd(&st->n_eigen_fail, 1ull);
@@ -1333,6 +1382,14 @@ int magk_vertex_pass(mag_ctx* c)
   }
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;
+  c->vqu_kind = MAG_KIND_NONE;
+  if (c->ne && (c->kind == MAG_KIND_ANISO || c->kind == MAG_KIND_LOGM)) {
+    if (c->kind == MAG_KIND_ANISO) k_vertex_uniform<MAG_KIND_ANISO><<<g, kThreads, 0, c->stream>>>(c->nv, c->d_vedge, c->d_vqu);
+    else k_vertex_uniform<MAG_KIND_LOGM><<<g, kThreads, 0, c->stream>>>(c->nv, c->d_vedge, c->d_vqu);
+    MAG_CUDA(c, cudaGetLastError());
+    c->n_launches++;
+    c->vqu_kind = c->kind;
+  }
   c->vertex_pass_valid = true;
   // the winner bits of the tet slots follow det Q_v (a no-op until the row layout exists; launch_tet_rows_w checks again)
   return magk_tet_winners(c);
@@ -1370,9 +1427,10 @@ static unsigned persistent_grid(mag_ctx* c, const void* kernel, int64_t n, int t
   return (unsigned)(g < 1 ? 1 : g);
 }
 
-static EdgeParams edge_params(const SweepParams& P, bool zero_in)
+static EdgeParams edge_params(const mag_ctx* c, const SweepParams& P, bool zero_in)
 {
   EdgeParams E;
+  E.vqu = (c->vertex_pass_valid && c->vqu_kind == c->kind && c->vqu_kind != MAG_KIND_NONE) ? c->d_vqu : nullptr;
   E.zero_in = zero_in ? 1 : 0;
   E.reeval = P.reeval;
   const bool do_split = P.ops & MAG_OP_MARK_SPLIT, do_coll = P.ops & MAG_OP_MARK_COLLAPSE;
@@ -1399,7 +1457,7 @@ static int launch_edges_t(mag_ctx* c, const SweepParams& P, const Range& r)
   const unsigned g = persistent_grid(c, (const void*)k_edges<KIND, FAST, VERT>, work, kEdgeThreads, kEdgeChunk);
   const VertArgs V{(int32_t)c->nv, c->dim, c->d_vpos, c->d_vq};
   k_edges<KIND, FAST, VERT><<<g, kEdgeThreads, 0, c->stream>>>((int32_t)r.n, reinterpret_cast<const int2*>(c->d_edge_v) + r.first, c->d_vedge,
-                                                               c->d_edge_flags + r.first, c->d_len + r.first, edge_params(P, r.whole && c->edge_flags_zero), c->d_stats,
+                                                               c->d_edge_flags + r.first, c->d_len + r.first, edge_params(c, P, r.whole && c->edge_flags_zero), c->d_stats,
                                                                c->d_near_edge, r.whole ? c->d_edge_order : nullptr, (int32_t)r.first, V);
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;
@@ -1745,7 +1803,7 @@ static int launch_edge_rows_z(mag_ctx* c, const SweepParams& P)
   if (g > need) g = need;
   k_edge_rows_z<KIND><<<(unsigned)(g < 1 ? 1 : g), T, 0, c->stream>>>(
       (int32_t)c->erows.n_slices, c->erows.d_anchor, c->erows.d_slice_off, reinterpret_cast<const int2*>(c->erows.d_slots), c->d_vedge,
-      c->d_edge_flags, c->d_len, edge_params(P, true), c->d_stats, c->d_near_edge);
+      c->d_edge_flags, c->d_len, edge_params(c, P, true), c->d_stats, c->d_near_edge);
   MAG_CUDA(c, cudaGetLastError());
   c->n_launches++;
   return MAG_OK;

@@ -86,6 +86,9 @@ template <int KIND> struct EdgeLeanCfg {
   static constexpr int T = MAG_EZ_THREADS, B = KIND == MAG_KIND_LOGM ? MAG_EROW_BLOCKS_LOGM : MAG_EZ_BLOCKS;
 };
 
+#ifndef MAG_VQU_PREFETCH
+#define MAG_VQU_PREFETCH 1
+#endif
 #ifndef MAG_EZ_ASMEM
 #define MAG_EZ_ASMEM 1   /* 1: the anchor record lives in shared memory (one 16-byte chunk plane per warp and chunk, read back with
                             conflict-free LDS.128) instead of 24 registers: the other end's record of the next row stays in flight */
@@ -200,6 +203,14 @@ k_edge_rows_z(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t
       s0 = s2;
       s1 = s3;
     }
+#if MAG_VQU_PREFETCH
+    // a lane with a near-threshold edge: its anchor's Q_u (k_vertex_uniform) is asked for now, so that it travels while near_edges
+    // fetches the slot word and the two records (inside the k loop the request costs the loop registers: 24 bytes of spills)
+    if (nearmask && P.vqu && reeval) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) prefetch_l2(chunk_ptr<5>(P.vqu, i, va < 0 ? 0 : va));
+    }
+#endif
     if (!have_next && s_nx < nslices) {
       n0 = ld_stream(slots + off_nx + lane);
       if (off1_nx - off_nx > 32) n1 = ld_stream(slots + off_nx + lane + 32);
@@ -209,7 +220,7 @@ k_edge_rows_z(int32_t nslices, const int32_t* __restrict__ anchor, const int32_t
       const int k = __ffs(any) - 1;
       const bool nr = (nearmask >> k) & 1u;
       const int2 q = nr ? __ldg(sp + k * 32) : kNone;
-      const unsigned r = near_edges<KIND, true>(nr, q.y, va, q.x, 0, vedge, flags, lengths, P.ops, max_len, min_len, st, near_list, reeval);
+      const unsigned r = near_edges<KIND, true>(nr, q.y, va, q.x, 0, vedge, flags, lengths, P.ops, max_len, min_len, st, near_list, reeval, P.vqu);
       c_eval += r & 1u; c_split += (r >> 1) & 1u; c_coll += (r >> 2) & 1u; eig_any |= (int)(r >> 3);
     }
     w.advance(s_nx);

@@ -80,7 +80,7 @@ template <int KIND, bool FAST>
 __device__ __noinline__ unsigned near_edges(bool nr, int32_t e, int32_t va, int32_t vb_word, int32_t f, const double* __restrict__ vedge,
                                             int32_t* __restrict__ flags, double* __restrict__ lengths, uint32_t ops,
                                             double max_len, double min_len, MagDevStats* st, int32_t* __restrict__ near_list,
-                                            bool reeval = true)
+                                            bool reeval = true, const double* __restrict__ vqu = nullptr)
 {
   const unsigned m = __ballot_sync(0xffffffffu, nr);
   const int lane = threadIdx.x & 31;
@@ -97,7 +97,7 @@ __device__ __noinline__ unsigned near_edges(bool nr, int32_t e, int32_t va, int3
       EdgeRecs<KIND> R;
       load_edge_recs<KIND>(vedge, make_int2(va, vb_word & kVidMask), R);
       int eig = 0;
-      const double len = edge_length_strict<KIND>(R, &eig);
+      const double len = edge_length_strict<KIND>(R, &eig, vqu, va);
       unsigned cs = 0, cc = 0;
       mark_edge(len, f, need_split, need_coll, vb_word >= 0, P, cs, cc);
       out = 1u | (cs << 1) | (cc << 2) | (eig ? 8u : 0u);
