@@ -1246,6 +1246,49 @@ def test_full_size_properties(cb):
     p.close()
 
 
+@pytest.mark.parametrize("kindname", ["aniso", "logm"])
+def test_uniform_edge_transform_cache(cb, kindname):
+    """Near-threshold edges whose two ends carry bit-identical size-field values are re-evaluated with the per-vertex transform
+    of k_vertex_uniform (both Gauss points see the same interpolated values: maSize.cc:395-413 / 511-521 at apfShape.cc:123-124's
+    swapped shape values).  On a lattice whose field does not vary along z the z edges are such edges AND sit exactly on the
+    collapse threshold: their fast-mode lengths and flag words must be the strict sweep's bit for bit (the strict sweep
+    evaluates both points in place, without the cache), through the lean rows (aniso) and the tile kernel's queue (LogAniso);
+    aniso also against the oracle.  Then the same after the coordinates moved (the cache follows the per-vertex pass)."""
+    from oracle import mao
+    n = 10
+    xyz, ev, tv = cb.boxmesh.kuhn_box(n, n, n)
+    H, R = cb.fields.shock_rotating(xyz, 1.0 / n)
+    lm = mao.logm_from_frames(H, R, 0)
+    p = cb.Part(0)
+    p.set_mesh(xyz, ev, tv)
+    ops = cb.OP_LENGTHS | cb.OP_MARK_SPLIT | cb.OP_MARK_COLLAPSE
+    same_ends = np.all(H[ev[:, 0]] == H[ev[:, 1]], axis=1) & np.all(R[ev[:, 0]] == R[ev[:, 1]], axis=1)
+    assert same_ends.sum() >= n * (n + 1) ** 2
+    if kindname == "aniso":
+        p.set_size_field_aniso(H, R)
+    else:
+        p.set_size_field_logm(lm)
+    for x in (xyz, cb.fields.jitter(xyz, 0.05 / n)):
+        if x is not xyz:
+            p.set_coords(x)
+        out = {}
+        for mode in (cb.FP_STRICT, cb.FP_FAST):
+            p.clear_flags()
+            p.sweep(ops, fp_mode=mode)
+            idx, cnt = p.near_threshold(0)
+            out[mode] = (p.edge_lengths(), p.flags()[0], np.sort(idx[:cnt]), p.stats())
+        (L0, f0, near0, s0), (L1, f1, near1, s1) = out[cb.FP_STRICT], out[cb.FP_FAST]
+        assert np.array_equal(f0, f1) and (s0["n_split"], s0["n_collapse"]) == (s1["n_split"], s1["n_collapse"])
+        assert np.array_equal(near0, near1)
+        if x is xyz:
+            assert len(near1) >= n * (n + 1) ** 2 and same_ends[near1].sum() >= n * (n + 1) ** 2   # the z family is listed
+        assert np.array_equal(L1[near1], L0[near1])                   # re-evaluated = the reference's own operation order
+        assert util.rel_err(L1, L0) < TOL
+        if kindname == "aniso":
+            assert np.array_equal(L0, mao.edge_lengths(mao.ANISO, x, H, R, ev))
+    p.close()
+
+
 @pytest.mark.parametrize("kindname", ["aniso", "logm", "iso"])
 def test_fast_listed_mode(cb, kindname):
     """MAG_FP_FAST_LISTED (the parity rule's own exception: an edge within 1e-12 of a threshold is decided by the fast value and
