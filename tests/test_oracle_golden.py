@@ -253,3 +253,40 @@ def test_prism_weights_restatement_matches_reference(name):
     w = mao.tri_weights(kind, g["xyz"], ma, mb, np.ascontiguousarray(base[pr]))
     assert np.array_equal(w, g["layer_weights_raw"][pr])
     assert np.all(g["layer_weights_r0_c1"][pr] == 1.0)
+
+
+@pytest.mark.parametrize("name", [n for n in util.golden_cases() if not n.startswith(("tri9x7_iso", "box6_identity", "box6_iso", "box6_uniform"))])
+def test_uniform_edge_identity_on_reference_lengths(name, built):
+    """The claim behind k_vertex_uniform (core_b200/csrc/mag_kernels.cu), pinned on the compiled reference's own lengths: an edge
+    whose two ends carry bit-identical size-field values sees the same interpolated values at both Gauss points (the second point
+    uses the first one's shape values exchanged, apfShape.cc:123-124, and a N0 + a N1 commutes), so its measure
+    (maSize.cc:158-216) is twice |row0(J) Q_u| with Q_u = getTransform of fl(fl(a N0) + fl(a N1)) -- a function of the vertex
+    alone.  Rebuilt here with numpy in the reference's operation order and compared bit for bit with the golden lengths of every
+    such edge (the planar shock-layer fields do not vary along y and z; random-frame fixtures have no such edge and only check
+    that the selection is empty)."""
+    g = util.load(name)
+    kind, ma, mb = util.metric_arrays(g)
+    if kind not in (mao.ANISO, mao.LOGM):
+        pytest.skip("no frames")
+    xyz, ev, L = g["xyz"], g["edge_v"], g["lengths"]
+    vals = np.concatenate([ma, mb], axis=1) if kind == mao.ANISO else mb
+    same = np.all(vals[ev[:, 0]].view(np.int64) == vals[ev[:, 1]].view(np.int64), axis=1)
+    if name.startswith("box6_shock_planar"):
+        assert same.sum() >= 2 * 6 * 7 * 7          # the y and z families of the 6^3 lattice at least
+    if not same.any():
+        return
+    XI = 0.577350269189626
+    N0, N1 = (1.0 - XI) / 2.0, (1.0 + XI) / 2.0
+    assert (1.0 - (-XI)) / 2.0 == N1 and (1.0 + (-XI)) / 2.0 == N0
+    c = vals * N0 + vals * N1                        # c = 0; c += a N0; c += a N1 (apfElement.cc:109-113), per component
+    nv = len(xyz)
+    Qu = (mao.vertex_transforms(kind, np.ascontiguousarray(c[:, :3]), np.ascontiguousarray(c[:, 3:]), nv) if kind == mao.ANISO
+          else mao.vertex_transforms(kind, None, np.ascontiguousarray(c), nv)).reshape(nv, 3, 3)
+    e = ev[same]
+    x0, x1 = xyz[e[:, 0]], xyz[e[:, 1]]
+    j = x0 * (-0.5) + x1 * 0.5                       # row 0 of the edge Jacobian (apfVectorElement.cc:44-52)
+    Q = Qu[e[:, 0]]
+    r = [(j[:, 0] * Q[:, 0, k] + j[:, 1] * Q[:, 1, k]) + j[:, 2] * Q[:, 2, k] for k in range(3)]
+    ln = np.sqrt((r[0] * r[0] + r[1] * r[1]) + r[2] * r[2])
+    assert np.array_equal(ln + ln, L[same])
+    assert np.array_equal(Qu[e[:, 0]], Qu[e[:, 1]])
